@@ -1,0 +1,410 @@
+// gg_gemm_bf16: the one GEMM of the training step.
+//
+//   D[M,N] = epilogue( sum over <=2 K-segments of A_seg * B_seg^T )
+//
+// sm_100a design: one 128 x BN output tile per CTA, 6 warps —
+//   warp 0   TMA producer   (cp.async.bulk.tensor.2d into a STAGES-deep 128B-swizzled smem ring)
+//   warp 1   MMA issuer     (one thread issues tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators
+//                            live in BN columns of tensor memory; tcgen05.commit frees smem stages)
+//   warps 2-5 epilogue      (tcgen05.ld 32x32b -> registers -> fused bias / activation / dropout /
+//                            mask / residual -> vectorised global stores)
+// Both operands can be K-major (row = M/N index) or MN-major (row = K index), so dgrad and wgrad
+// read the forward tensors in place with no transpose pass. Split-K (grid.z) writes fp32 partials
+// that a second kernel reduces in a fixed order (deterministic, no float atomics) and then runs
+// the same epilogue.
+//
+// Replaces: nn.Linear forward and autograd's mm backward in
+//   src/conditional_gan_cross_attention_with_film.py:56-72,129-162,197-231 (reference).
+#include "epilogue.cuh"
+#include "host_util.h"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace gg {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int ATOM_BYTES = 64 * BK * 2;  // one MN-major 64x64 box
+
+struct GemmArgs {
+  int M, N;
+  int K0, K1;
+  int a_mn, b_mn;
+  int splits;
+  float* partial;
+  gg_epilogue epi;
+};
+
+template <int BN, int STAGES>
+struct TileCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                   const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                   const GemmArgs g) {
+  using Cfg = TileCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum_full = empty + STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int kb0 = (g.K0 + BK - 1) / BK;
+  const int kb1 = (g.K1 + BK - 1) / BK;
+  const int total_kb = kb0 + kb1;
+  const int kb_begin = static_cast<int>(static_cast<int64_t>(total_kb) * blockIdx.z / g.splits);
+  const int kb_end = static_cast<int>(static_cast<int64_t>(total_kb) * (blockIdx.z + 1) / g.splits);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (kb1 > 0) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        const bool second = kb >= kb0;
+        const int kloc = (second ? kb - kb0 : kb) * BK;
+        const CUtensorMap* ma = second ? &tmA1 : &tmA0;
+        const CUtensorMap* mb = second ? &tmB1 : &tmB0;
+        uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + A_TILE_BYTES;
+        mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        if (!g.a_mn) {
+          tma_load_2d(a_dst, ma, &full[s], kloc, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d(a_dst + j * ATOM_BYTES, ma, &full[s], m0 + 64 * j, kloc);
+        }
+        if (!g.b_mn) {
+          tma_load_2d(b_dst, mb, &full[s], kloc, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(b_dst + j * ATOM_BYTES, mb, &full[s], n0 + 64 * j, kloc);
+        }
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after_sync();
+        const uint32_t a_base = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t b_base = a_base + A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // K-major: 16 bf16 of K = 32 bytes inside the 128 B swizzle row.
+          // MN-major: 16 k-rows of 128 B = 2048 bytes; 64-wide MN atoms are ATOM_BYTES apart.
+          const uint64_t ad = g.a_mn ? make_smem_desc(a_base + k * 2048, ATOM_BYTES, 1024)
+                                     : make_smem_desc(a_base + k * 32, 16, 1024);
+          const uint64_t bd = g.b_mn ? make_smem_desc(b_base + k * 2048, ATOM_BYTES, 1024)
+                                     : make_smem_desc(b_base + k * 32, 16, 1024);
+          tc_mma_bf16(tmem_base, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty[s]);
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      tc_commit(accum_full);
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(accum_full, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      const int nc0 = n0 + c * 32;
+      if (m < g.M && nc0 < g.N) {
+        const int ncols = min(32, g.N - nc0);
+        if (g.splits > 1) {
+          float* p = g.partial + (static_cast<int64_t>(blockIdx.z) * g.M + m) * g.N + nc0;
+          if (ncols == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(p)[j] =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) p[j] = v[j];
+          }
+        } else {
+          epilogue_chunk(g.epi, g.N, m, nc0, ncols, v);
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// Sums split-K partials in split order (deterministic) and applies the epilogue.
+__global__ void __launch_bounds__(256)
+    splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
+                         const gg_epilogue epi) {
+  const int chunks = (N + 31) / 32;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(M) * chunks) return;
+  const int m = static_cast<int>(idx / chunks);
+  const int nc0 = static_cast<int>(idx % chunks) * 32;
+  const int ncols = min(32, N - nc0);
+  float v[32], t[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  for (int z = 0; z < splits; ++z) {
+    load_row_chunk(partial + static_cast<int64_t>(z) * M * N, 1, N, m, nc0, ncols, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += t[j];
+  }
+  epilogue_chunk(epi, N, m, nc0, ncols, v);
+}
+
+// CUDA-core fp32 check path on the same bf16 operands and the same epilogue (tests only).
+__global__ void __launch_bounds__(128)
+    gemm_simt_kernel(const __nv_bfloat16* a0, const __nv_bfloat16* b0, int64_t lda0, int64_t ldb0,
+                     int K0, const __nv_bfloat16* a1, const __nv_bfloat16* b1, int64_t lda1,
+                     int64_t ldb1, int K1, int M, int N, int a_mn, int b_mn, const gg_epilogue epi) {
+  const int chunks = (N + 31) / 32;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(M) * chunks) return;
+  const int m = static_cast<int>(idx / chunks);
+  const int nc0 = static_cast<int>(idx % chunks) * 32;
+  const int ncols = min(32, N - nc0);
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  for (int seg = 0; seg < 2; ++seg) {
+    const __nv_bfloat16* a = seg ? a1 : a0;
+    const __nv_bfloat16* b = seg ? b1 : b0;
+    const int64_t lda = seg ? lda1 : lda0, ldb = seg ? ldb1 : ldb0;
+    const int K = seg ? K1 : K0;
+    for (int k = 0; k < K; ++k) {
+      const float av = __bfloat162float(a_mn ? a[static_cast<int64_t>(k) * lda + m]
+                                             : a[static_cast<int64_t>(m) * lda + k]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < ncols) {
+          const int n = nc0 + j;
+          const float bv = __bfloat162float(b_mn ? b[static_cast<int64_t>(k) * ldb + n]
+                                                 : b[static_cast<int64_t>(n) * ldb + k]);
+          v[j] = fmaf(av, bv, v[j]);
+        }
+      }
+    }
+  }
+  epilogue_chunk(epi, N, m, nc0, ncols, v);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor [outer, inner] with row pitch ld (elements); box = {64, box_outer}, 128B swizzle.
+static int encode_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld,
+                      int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");
+    return GG_ERR_CUDA;
+  }
+  GG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand %p not 16-byte aligned",
+             ptr);
+  GG_REQUIRE(ld % 8 == 0 && ld >= inner, "GEMM operand ld=%lld must be a multiple of 8 and >= %lld",
+             (long long)ld, (long long)inner);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", (int)r,
+              (long long)inner, (long long)outer, (long long)ld);
+    return GG_ERR_CUDA;
+  }
+  return GG_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = TileCfg<BN, STAGES>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  });
+  GG_CUDA_CHECK(attr_err);
+  dim3 grid(ceil_div(args.N, BN), ceil_div(args.M, BM), args.splits);
+  gemm_tc_kernel<BN, STAGES><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
+                                                                     maps[3], args);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
+  GG_REQUIRE(d != nullptr, "null gemm desc");
+  GG_REQUIRE(d->M > 0 && d->N > 0, "bad GEMM shape M=%d N=%d", d->M, d->N);
+  GG_REQUIRE(d->nseg == 1 || d->nseg == 2, "nseg must be 1 or 2");
+  for (int s = 0; s < d->nseg; ++s)
+    GG_REQUIRE(d->seg[s].K > 0 && d->seg[s].a && d->seg[s].b, "bad GEMM segment %d", s);
+  GG_REQUIRE(d->epi.out_bf16 || d->epi.out_f32, "GEMM has no output");
+  GG_REQUIRE(d->epi.drop_p == 0.f || d->epi.rng, "dropout needs an rng state pointer");
+
+  if (d->impl == GG_IMPL_SIMT_F32) {
+    const gg_gemm_seg& s0 = d->seg[0];
+    const gg_gemm_seg& s1 = d->seg[1];
+    const int chunks = ceil_div(d->N, 32);
+    const int64_t work = static_cast<int64_t>(d->M) * chunks;
+    gemm_simt_kernel<<<static_cast<unsigned>((work + 127) / 128), 128, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(s0.a), reinterpret_cast<const __nv_bfloat16*>(s0.b),
+        s0.lda, s0.ldb, s0.K, reinterpret_cast<const __nv_bfloat16*>(d->nseg > 1 ? s1.a : nullptr),
+        reinterpret_cast<const __nv_bfloat16*>(d->nseg > 1 ? s1.b : nullptr),
+        d->nseg > 1 ? s1.lda : 0, d->nseg > 1 ? s1.ldb : 0, d->nseg > 1 ? s1.K : 0, d->M, d->N,
+        d->a_mn_major, d->b_mn_major, d->epi);
+    GG_LAUNCH_CHECK();
+    return GG_OK;
+  }
+  GG_REQUIRE(d->impl == GG_IMPL_TCGEN05, "unknown GEMM impl %d", d->impl);
+
+  int bn = d->block_n;
+  if (bn == 0) bn = d->N <= 64 ? 64 : 128;
+  GG_REQUIRE(bn == 64 || bn == 128 || bn == 256, "block_n must be 64, 128 or 256");
+
+  CUtensorMap maps[4];
+  for (int s = 0; s < 2; ++s) {
+    const gg_gemm_seg& sg = d->seg[s < d->nseg ? s : 0];
+    int rc;
+    if (!d->a_mn_major) rc = encode_map(&maps[2 * s], sg.a, sg.K, d->M, sg.lda, BM);
+    else rc = encode_map(&maps[2 * s], sg.a, d->M, sg.K, sg.lda, BK);
+    if (rc) return rc;
+    if (!d->b_mn_major) rc = encode_map(&maps[2 * s + 1], sg.b, sg.K, d->N, sg.ldb, bn);
+    else rc = encode_map(&maps[2 * s + 1], sg.b, d->N, sg.K, sg.ldb, BK);
+    if (rc) return rc;
+  }
+
+  GemmArgs args;
+  args.M = d->M;
+  args.N = d->N;
+  args.K0 = d->seg[0].K;
+  args.K1 = d->nseg > 1 ? d->seg[1].K : 0;
+  args.a_mn = d->a_mn_major;
+  args.b_mn = d->b_mn_major;
+  args.epi = d->epi;
+  args.partial = reinterpret_cast<float*>(d->workspace);
+
+  const int total_kb = ceil_div(args.K0, BK) + ceil_div(args.K1, BK);
+  const int tiles = ceil_div(d->M, BM) * ceil_div(d->N, bn);
+  int splits = 1;
+  if (d->force_splits > 0) {
+    splits = d->force_splits;
+  } else if (d->workspace && tiles < 100 && total_kb >= 8) {
+    splits = 296 / tiles;
+    if (splits > total_kb / 2) splits = total_kb / 2;
+    if (splits > 32) splits = 32;
+  }
+  if (splits > total_kb) splits = total_kb;
+  if (splits < 1) splits = 1;
+  if (splits > 1) {
+    const int64_t need = static_cast<int64_t>(splits) * d->M * d->N * 4;
+    if (!d->workspace || d->workspace_bytes < need) {
+      if (d->force_splits > 0) {
+        set_error("split-K workspace too small: need %lld bytes, have %lld", (long long)need,
+                  (long long)d->workspace_bytes);
+        return GG_ERR_WORKSPACE;
+      }
+      splits = static_cast<int>(d->workspace_bytes / (static_cast<int64_t>(d->M) * d->N * 4));
+      if (splits < 2) splits = 1;
+    }
+  }
+  args.splits = splits;
+
+  int rc;
+  if (bn == 64) rc = launch_tc<64, 4>(maps, args, stream);
+  else if (bn == 128) rc = launch_tc<128, 3>(maps, args, stream);
+  else rc = launch_tc<256, 4>(maps, args, stream);
+  if (rc) return rc;
+
+  if (splits > 1) {
+    const int64_t work = static_cast<int64_t>(d->M) * ceil_div(d->N, 32);
+    splitk_reduce_kernel<<<static_cast<unsigned>((work + 255) / 256), 256, 0, stream>>>(
+        args.partial, splits, d->M, d->N, d->epi);
+    GG_LAUNCH_CHECK();
+  }
+  return GG_OK;
+}
+
+}  // namespace gg
+
+extern "C" int gg_gemm_bf16(const gg_gemm_desc* desc, void* stream) {
+  return gg::gemm_dispatch(desc, reinterpret_cast<cudaStream_t>(stream));
+}

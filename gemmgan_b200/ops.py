@@ -1,0 +1,72 @@
+"""Thin torch-tensor wrappers over single C-ABI kernels (used by tests and micro-benchmarks)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, GemmDesc
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(
+    a, b, *, a_mn=False, b_mn=False, M=None, N=None, a2=None, b2=None,
+    bias=None, pre=None, act=_lib.ACT_NONE, slope=0.0, drop_p=0.0, rng=None, site=0,
+    mask=None, mask_pos=1.0, mask_neg=0.0, res=None, alpha=1.0,
+    out_bf16=None, out_f32=None, accum=False, row_map=None,
+    workspace=None, impl=_lib.IMPL_TCGEN05, splits=0, block_n=0,
+):
+    """D = epilogue(alpha * (A @ B^T [+ A2 @ B2^T])).
+
+    a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] or [K,N] bf16 (2-D, last dim contiguous).
+    """
+    L = _lib.lib()
+    d = GemmDesc()
+    if M is None:
+        M = a.shape[1] if a_mn else a.shape[0]
+    if N is None:
+        N = b.shape[1] if b_mn else b.shape[0]
+    d.M, d.N = M, N
+    segs = [(a, b)] + ([(a2, b2)] if a2 is not None else [])
+    d.nseg = len(segs)
+    for i, (x, w) in enumerate(segs):
+        assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+        assert x.stride(-1) == 1 and w.stride(-1) == 1
+        K = x.shape[0] if a_mn else x.shape[1]
+        Kb = w.shape[0] if b_mn else w.shape[1]
+        assert K == Kb, (x.shape, w.shape)
+        d.seg[i].a, d.seg[i].b = x.data_ptr(), w.data_ptr()
+        d.seg[i].lda, d.seg[i].ldb = x.stride(0), w.stride(0)
+        d.seg[i].K = K
+    d.a_mn_major, d.b_mn_major = int(a_mn), int(b_mn)
+    e = d.epi
+    e.alpha = alpha
+    e.bias = _ptr(bias)
+    if pre is not None:
+        e.pre, e.pre_ld, e.pre_f32 = pre.data_ptr(), pre.stride(0), int(pre.dtype == torch.float32)
+    e.act, e.slope = act, slope
+    e.drop_p, e.rng, e.site = drop_p, _ptr(rng), site
+    if mask is not None:
+        e.mask, e.mask_ld, e.mask_f32 = mask.data_ptr(), mask.stride(0), int(mask.dtype == torch.float32)
+    e.mask_pos, e.mask_neg = mask_pos, mask_neg
+    if res is not None:
+        e.res, e.res_ld, e.res_f32 = res.data_ptr(), res.stride(0), int(res.dtype == torch.float32)
+    if out_bf16 is not None:
+        e.out_bf16, e.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    if out_f32 is not None:
+        e.out_f32, e.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    e.accum_f32 = int(accum)
+    if row_map is not None:
+        e.row_div, e.row_mul, e.row_add = row_map
+    if workspace is not None:
+        d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    d.impl, d.force_splits, d.block_n = impl, splits, block_n
+    _lib.check(L.gg_gemm_bf16(C.byref(d), _stream()))
