@@ -1,0 +1,207 @@
+"""Drop-in for the reference's src/conditional_gan_cross_attention_with_film.py — the GeMM-GAN paper
+model (FiLM + cross-attention multimodal fusion, WGAN-GP) — backed by the sm_100a engine.
+
+Same public names and signatures as the reference (file:line of the reference in brackets):
+  wasserstein_loss / G_loss / D_loss [:32-46], build_linear_block / build_generator /
+  build_discriminator [:56-95], generator [:97-164], discriminator [:167-233], WGAN_GP_model
+  [:236-253], WGAN_GP [:256-898] with init_train, build_WGAN_GP, gradient_penalty, train_disc,
+  train_gen, train, generate_samples_all, generate_samples, set_requires_grad, fit,
+  print_best_epoch. Model argument order: (x, patches, patches_padding_mask, text_tokens,
+  text_padding_mask) [:128]; train() order: (gene, text, text_pad, patches, pad) [:463].
+Evaluation / plotting / .npy dumps done by the reference inside fit() are outside the hot path
+ and not reproduced; checkpoints are saved with the reference's file names.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import numpy as np
+import torch
+
+from gemmgan_b200.models import PaperDiscriminator, PaperGenerator, build_linear_block, build_stack  # noqa: F401
+from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, wasserstein_loss  # noqa: F401
+
+
+def build_generator(input_dims, generator_dims, negative_slope=0.0, is_bn=False):
+    return build_stack(input_dims, generator_dims, negative_slope, is_bn)
+
+
+def build_discriminator(input_dims, dicriminator_dims, negative_slope=0.0, is_bn=False):
+    return build_stack(input_dims, dicriminator_dims, negative_slope, is_bn)
+
+
+class generator(PaperGenerator):
+    pass
+
+
+class discriminator(PaperDiscriminator):
+    pass
+
+
+def WGAN_GP_model(latent_dims, vector_dims, embedding_dims, generator_dims, discriminator_dims,
+                  text_embedding_dims=768, patches_embedding_dims=1024, negative_slope=0.0, is_bn=False):
+    gen = generator(latent_dims, embedding_dims, generator_dims, text_embedding_dims, patches_embedding_dims,
+                    negative_slope, is_bn)
+    disc = discriminator(vector_dims, embedding_dims, discriminator_dims, text_embedding_dims,
+                         patches_embedding_dims, negative_slope, is_bn)
+    return gen, disc
+
+
+class WGAN_GP(TrainerBase):
+    variant = "paper"
+    clip_d, clip_g = 10.0, 2.0  # clip_grad_norm_ max norms [:414, :457]
+
+    def __init__(self, input_dims, latent_dims, embedding_dims, generator_dims, discriminator_dims,
+                 text_embedding_dims=768, patches_embedding_dims=1024, negative_slope=0.0, is_bn=False,
+                 lr_d=5e-4, lr_g=5e-4, optimizer='rms_prop', gp_weight=10, p_aug=0, norm_scale=0.5, train=True,
+                 n_critic=5, freq_print=2, freq_compute_test=50, freq_visualize_test=100, patience=10,
+                 normalization='standardize', log2=False, rpm=False, results_dire=''):
+        self.embedding_dims = embedding_dims
+        self.text_embedding_dims = text_embedding_dims
+        self.patches_embedding_dims = patches_embedding_dims
+        self._init_common(input_dims, latent_dims, generator_dims, discriminator_dims, negative_slope, is_bn,
+                          lr_d, lr_g, optimizer, gp_weight, p_aug, norm_scale, train, n_critic, freq_print,
+                          freq_compute_test, freq_visualize_test, patience, normalization, log2, rpm,
+                          results_dire)
+        self._tokens = None  # (P, T) of the staged batch
+
+    def _shape_cfg(self):
+        P, T = self._tokens
+        return dict(E=self.embedding_dims, H=self.generator_dims[0], Dt=self.text_embedding_dims,
+                    Dp=self.patches_embedding_dims, P=P, T=T, tower_bias=True)
+
+    def build_WGAN_GP(self):
+        self.numerical_dims = []
+        gen, disc = WGAN_GP_model(self.latent_dims, self.input_dims, self.embedding_dims, self.generator_dims,
+                                  self.discriminator_dims, self.text_embedding_dims, self.patches_embedding_dims,
+                                  self.negative_slope, self.is_bn)
+        self._attach(gen, disc)
+
+    def _engine_for(self, B, patches, text_token):
+        tokens = (patches.shape[1], text_token.shape[1])
+        if tokens != self._tokens:  # token counts are part of the engine's static shapes
+            self._tokens = tokens
+            self._engines.clear()
+        return self._engine(B)
+
+    def _stage(self, genes, text_token, text_token_padding, patches, padding_mask):
+        dev = self.device
+        B = patches.shape[0]
+        eng = self._engine_for(B, patches, text_token)
+        eng.set_batch(genes=None if genes is None else genes.to(dev), patches=patches.to(dev),
+                      patch_pad=padding_mask.to(dev), text=text_token.to(dev), text_pad=text_token_padding.to(dev))
+        return eng
+
+    # ---- reference-signature entry points -------------------------------------------------
+    def gradient_penalty(self, real_data, fake_data, patches, padding_mask, text_token, text_token_padding,
+                         alpha=None):
+        eng = self._stage(None, text_token, text_token_padding, patches, padding_mask)
+        if alpha is None:
+            alpha = self._alpha(eng.B)
+        return eng.gradient_penalty(real_data.to(self.device), fake_data.to(self.device), alpha,
+                                    training=self.disc.training)
+
+    def train_disc(self, real_data, z, text_token, text_token_padding, patches, padding_mask, alpha=None):
+        eng = self._stage(real_data, text_token, text_token_padding, patches, padding_mask)
+        self._train_disc_staged(eng, z.to(self.device), alpha)
+
+    def train_gen(self, z, text_token, text_token_padding, patches, padding_mask):
+        eng = self._stage(None, text_token, text_token_padding, patches, padding_mask)
+        self._train_gen_staged(eng, z.to(self.device))
+
+    def train(self, gene_expression, text_token, text_token_padding, patches, padding_mask, zs=None, alphas=None):
+        eng = self._stage(gene_expression, text_token, text_token_padding, patches, padding_mask)
+        self._train_staged(eng, zs, alphas)
+
+    def _module_forward(self, module, x, patches, patches_padding_mask, text_tokens, text_padding_mask):
+        eng = self._stage(None, text_tokens, text_padding_mask, patches, patches_padding_mask)
+        if module is self.gen:
+            return eng.generate(x.to(self.device), training=module.training)
+        return eng.critic(x.to(self.device), training=module.training)
+
+    def generate_samples(self, gene_expression, text_embedding, text_padding, patches, padding_mask):
+        with torch.no_grad():
+            self.gen.eval()
+            x_real = gene_expression.clone().to(torch.float32)
+            z = torch.normal(0, 1, size=(x_real.shape[0], self.latent_dims), device=self.device)
+            x_gen = self.gen(z, patches, padding_mask, text_embedding, text_padding)
+        return x_real, x_gen
+
+    def generate_samples_all(self, data_loader, num_repeats=1, balanced=False, balanced_max_oversample=5):
+        """Unbalanced branch of the reference [:560-598]; batch tuple layout of
+        multi_patch_multi_token_gan_dataloader.py:55. (balanced=True raises NameError in the reference, :531.)"""
+        if balanced:
+            raise NotImplementedError("balanced=True is broken in the reference (undefined text_padding, :531)")
+        real, gen, dt_r, dt_g, ps_r, ps_g = [], [], [], [], [], []
+        for i in range(num_repeats):
+            for batch in data_loader:
+                text, tpad, genes, patches, ppad, dtype_, psite = batch[:7]
+                x_real, x_gen = self.generate_samples(genes.to(self.device), text, tpad, patches, ppad)
+                gen.append(x_gen.cpu().numpy())
+                dt_g.append(dtype_.cpu().numpy())
+                ps_g.append(psite.cpu().numpy())
+                if i == 0:
+                    real.append(x_real.cpu().numpy())
+                    dt_r.append(dtype_.cpu().numpy())
+                    ps_r.append(psite.cpu().numpy())
+        return (np.vstack(real), np.vstack(gen), np.concatenate(dt_r), np.concatenate(dt_g), np.concatenate(ps_r),
+                np.concatenate(ps_g))
+
+    def fit(self, train_data, val_data=None, test_data=None, epochs=1, val=True):
+        """Training loop of the reference fit() [:619-744] without its evaluation / plotting."""
+        self.build_WGAN_GP()
+        if self.isTrain:
+            self.init_train()
+        for epoch in range(epochs):
+            self._epoch_lr_decay(epoch, 100)  # both LRs halve every 100 epochs [:649-657]
+            self.epoch = epoch
+            d_sum, g_sum, n = 0.0, 0.0, 0
+            for i, data in enumerate(train_data):
+                self.train(data[2], data[0], data[1], data[3], data[4])
+                d_sum, g_sum, n = d_sum + self.d_batch_loss, g_sum + self.g_batch_loss, n + 1
+                if (i + 1) % self.freq_print == 0:
+                    print('[Epoch %d/%d] [Batch %d/%d] [D loss : %f] [G loss : %f]' %
+                          (epoch + 1, epochs, i + 1, len(train_data), self.disc_loss.item(), self.gen_loss.item()))
+            d_mean = d_sum / max(n, 1)
+            self.loss_dict['d loss'].append(d_mean[0])
+            self.loss_dict['d real loss'].append(d_mean[1])
+            self.loss_dict['d fake loss'].append(d_mean[2])
+            self.loss_dict['g loss'].append((g_sum / max(n, 1))[0])
+            last = epoch == epochs - 1
+            if self.result_dire and ((epoch + 1) % self.freq_compute_test == 0 or last):
+                tag = 'last_epoch' if last else f'epoch_{epoch + 1}'
+                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, f'gen_{tag}.pt'))
+                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, f'disc_{tag}.pt'))
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument('--seed', type=int, default=42)
+    p.add_argument('--num_epochs', type=int, default=1)
+    p.add_argument('--batch_size', type=int, default=8)
+    p.add_argument('--latent_dim', type=int, default=256)
+    p.add_argument('--hidden_dim', type=int, default=256)
+    p.add_argument('--embedding_dim', type=int, default=256)
+    p.add_argument('--num_patches', type=int, default=8)
+    p.add_argument('--num_text_tokens', type=int, default=1)
+    p.add_argument('--n_genes', type=int, default=18868)
+    p.add_argument('--output_path', type=str, default='')
+    p.add_argument('--optimizer', type=str, default='rms_prop')
+    return p.parse_args()
+
+
+if __name__ == '__main__':
+    from gemmgan_b200.synthetic import synthetic_loader
+
+    args = parse_args()
+    torch.manual_seed(args.seed)
+    loader = synthetic_loader('paper', n_samples=args.batch_size * 4, batch_size=args.batch_size,
+                              n_genes=args.n_genes, n_patches=args.num_patches, n_tokens=args.num_text_tokens,
+                              seed=args.seed)
+    model = WGAN_GP(input_dims=args.n_genes, latent_dims=args.latent_dim, embedding_dims=args.embedding_dim,
+                    generator_dims=[args.hidden_dim, args.hidden_dim, args.n_genes],
+                    discriminator_dims=[args.hidden_dim, args.hidden_dim, 1], optimizer=args.optimizer,
+                    results_dire=args.output_path)
+    model.fit(loader, None, None, epochs=args.num_epochs)
+    print(model.loss_dict)

@@ -1,8 +1,74 @@
-"""argtypes for the entry points of include/gemmgan.h beyond gg_gemm_bf16."""
+"""ctypes mirrors of the engine structs / entry points of include/gemmgan.h."""
 from __future__ import annotations
 
 import ctypes as C
 
+VARIANT_VANILLA, VARIANT_FILM, VARIANT_PAPER = 0, 1, 2
+OPT_RMSPROP, OPT_ADAM, OPT_ADAMW = 0, 1, 2
+NET_GEN, NET_DISC = 0, 1
+
+# enum gg_param_slot
+P_FILM_W, P_FILM_B, P_TEXT_W, P_TEXT_B, P_PATCH_W, P_PATCH_B, P_CLS = range(7)
+P_LAYER0 = 7
+(L_IN_W, L_IN_B, L_OUT_W, L_OUT_B, L_FF1_W, L_FF1_B, L_FF2_W, L_FF2_B,
+ L_N1_W, L_N1_B, L_N2_W, L_N2_B) = range(12)
+L_COUNT = 12
+P_P2T_IN_W = P_LAYER0 + 24
+P_P2T_IN_B, P_P2T_OUT_W, P_P2T_OUT_B = P_P2T_IN_W + 1, P_P2T_IN_W + 2, P_P2T_IN_W + 3
+P_T2P_IN_W, P_T2P_IN_B, P_T2P_OUT_W, P_T2P_OUT_B = (P_P2T_IN_W + 4, P_P2T_IN_W + 5, P_P2T_IN_W + 6,
+                                                    P_P2T_IN_W + 7)
+P_TR0_W, P_TR0_B, P_TR1_W, P_TR1_B, P_FIN_W, P_FIN_B = (P_P2T_IN_W + 8 + i for i in range(6))
+NSLOTS = P_FIN_B + 1
+
+STAT_LOSS_REAL, STAT_LOSS_FAKE, STAT_GP, STAT_D_LOSS, STAT_G_LOSS = 0, 1, 2, 3, 4
+STAT_D_GRAD_NORM, STAT_D_CLIP_COEF, STAT_G_GRAD_NORM, STAT_G_CLIP_COEF = 5, 6, 7, 8
+STATS_COUNT = 16
+
+
+class ModelCfg(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int32), ("B", C.c_int32), ("G", C.c_int32), ("L", C.c_int32), ("E", C.c_int32),
+        ("H", C.c_int32), ("Dt", C.c_int32), ("Dp", C.c_int32), ("P", C.c_int32), ("T", C.c_int32),
+        ("n_layers", C.c_int32), ("n_heads", C.c_int32), ("ffn", C.c_int32), ("tower_bias", C.c_int32),
+        ("slope", C.c_float), ("dropout_p", C.c_float), ("gp_weight", C.c_float), ("clip_d", C.c_float),
+        ("clip_g", C.c_float), ("ln_eps", C.c_float), ("optimizer", C.c_int32), ("gemm_impl", C.c_int32),
+        ("seed", C.c_uint64),
+    ]
+
+
+class NetBuffers(C.Structure):
+    _fields_ = [
+        ("params", C.c_void_p), ("grads", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("step_count", C.c_void_p),
+        ("n_used", C.c_int64), ("off", C.c_int64 * NSLOTS),
+    ]
+
 
 def declare(L: C.CDLL) -> None:
-    pass
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.gg_engine_workspace_bytes.argtypes = [C.POINTER(ModelCfg), C.POINTER(i64)]
+    L.gg_engine_create.argtypes = [C.POINTER(ModelCfg), C.POINTER(NetBuffers), C.POINTER(NetBuffers), vp, i64, vp,
+                                   C.POINTER(vp)]
+    L.gg_engine_destroy.argtypes = [vp]
+    L.gg_engine_destroy.restype = None
+    L.gg_engine_refresh_shadows.argtypes = [vp, i32, vp]
+    L.gg_engine_set_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.gg_engine_disc_grads.argtypes = [vp, vp, vp, i32, vp]
+    L.gg_engine_gen_grads.argtypes = [vp, vp, i32, vp]
+    L.gg_engine_optim_step.argtypes = [vp, i32, f32, vp]
+    L.gg_engine_generate.argtypes = [vp, vp, vp, i32, vp]
+    L.gg_engine_critic.argtypes = [vp, vp, vp, i32, vp]
+    L.gg_engine_gradient_penalty.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    L.gg_engine_stats.argtypes = [vp]
+    L.gg_engine_stats.restype = vp
+    L.gg_engine_buffer.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    L.gg_engine_buffer.restype = vp
+    L.gg_optim_step.argtypes = [i32, vp, vp, vp, vp, i64, f32, f32, vp, vp, vp, vp]
+
+
+EXPORTS = [
+    "gg_last_error", "gg_abi_version", "gg_check_device", "gg_gemm_bf16", "gg_engine_workspace_bytes",
+    "gg_engine_create", "gg_engine_destroy", "gg_engine_refresh_shadows", "gg_engine_set_batch",
+    "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_optim_step", "gg_engine_generate",
+    "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
+]

@@ -1,0 +1,306 @@
+// Multi-head attention core for the fusion tower: softmax(q k^T / sqrt(hd) + key_padding_mask) v with
+// dropout on the probabilities, forward and backward, one CTA per (batch row, head).
+// Sequence lengths here are tiny (S = P+1 <= 257 tokens, T <= 300, single-query cross attention in the
+// paper model), so K/V (and Q/dO in the backward) live in shared memory for the whole CTA and the
+// probabilities are recomputed in the backward instead of being stored (flash-style, deterministic:
+// pass A owns query rows -> dQ, pass B owns key rows -> dK, dV; no atomics).
+//
+// Replaces F.multi_head_attention_forward / scaled_dot_product_attention and their autograd backward
+// used by nn.TransformerEncoderLayer.self_attn and the patch2text / text2patch nn.MultiheadAttention
+// modules (src/conditional_gan_cross_attention_with_film.py:114-123, 144-152). As in torch, q is scaled
+// by 1/sqrt(head_dim) before q k^T and padded keys get -inf.
+#include "host_util.h"
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace gg {
+
+constexpr int ATT_MAXC = 10;  // keys / queries per lane: sequence length <= 320
+constexpr int ATT_WARPS = 4;
+
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float wsum2(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// rows of `n` x hd bf16 from global (pitch ld) into smem with row pitch hd+2 (bank-conflict-free columns)
+__device__ __forceinline__ void load_rows(bf16* dst, const bf16* src, int64_t ld, int n, int hd) {
+  const int pitch = hd + 2;
+  const int half = hd >> 1;
+  for (int i = threadIdx.x; i < n * half; i += blockDim.x) {
+    const int r = i / half, c = (i % half) * 2;
+    *reinterpret_cast<__nv_bfloat162*>(dst + r * pitch + c) =
+        *reinterpret_cast<const __nv_bfloat162*>(src + static_cast<int64_t>(r) * ld + c);
+  }
+}
+
+__device__ __forceinline__ float dot_row(const bf16* a, const bf16* b, int hd) {
+  float acc = 0.f;
+  for (int d = 0; d < hd; d += 2) {
+    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + d));
+    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + d));
+    acc = fmaf(x.x, y.x, acc);
+    acc = fmaf(x.y, y.y, acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_fwd_kernel(const AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int hd = a.hd, pitch = hd + 2, Lk = a.Lk, Lq = a.Lq;
+  bf16* Ks = reinterpret_cast<bf16*>(smem_att);
+  bf16* Vs = Ks + Lk * pitch;
+  bf16* Qs = Vs + Lk * pitch;
+  float* pbuf = reinterpret_cast<float*>(Qs + ((Lq * pitch + 1) & ~1));
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t kvrow0 = static_cast<int64_t>(b % a.kv_mod) * Lk;
+  const int64_t qrow0 = static_cast<int64_t>(b % a.q_mod) * Lq;
+  load_rows(Ks, a.k + kvrow0 * a.ldkv + h * hd, a.ldkv, Lk, hd);
+  load_rows(Vs, a.v + kvrow0 * a.ldkv + h * hd, a.ldkv, Lk, hd);
+  load_rows(Qs, a.q + qrow0 * a.ldq + h * hd, a.ldq, Lq, hd);
+  __syncthreads();
+  const uint8_t* mk = a.mask ? a.mask + static_cast<int64_t>(b % a.mask_mod) * Lk : nullptr;
+  const float scale = rsqrtf(static_cast<float>(hd));
+  uint64_t seed = 0, step = 0;
+  if (a.drop_p > 0.f) {
+    seed = a.rng[0];
+    step = a.rng[1];
+  }
+  const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  float* pw = pbuf + warp * Lk;
+  for (int i = warp; i < Lq; i += ATT_WARPS) {
+    float s[ATT_MAXC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < ATT_MAXC; ++c) {
+      const int j = c * 32 + lane;
+      s[c] = -INFINITY;
+      if (j < Lk && !(mk && mk[j])) s[c] = scale * dot_row(Qs + i * pitch, Ks + j * pitch, hd);
+      m = fmaxf(m, s[c]);
+    }
+    m = wmax(m);
+    float l = 0.f;
+#pragma unroll
+    for (int c = 0; c < ATT_MAXC; ++c) {
+      s[c] = (s[c] == -INFINITY) ? 0.f : __expf(s[c] - m);
+      l += s[c];
+    }
+    l = wsum2(l);
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    const uint64_t pbase = ((static_cast<uint64_t>(b) * a.H + h) * Lq + i) * static_cast<uint64_t>(Lk);
+#pragma unroll
+    for (int c = 0; c < ATT_MAXC; ++c) {
+      const int j = c * 32 + lane;
+      if (j < Lk) {
+        float p = s[c] * inv_l;
+        if (a.drop_p > 0.f) p = dropout_keep(seed, step, a.site, pbase + j, a.drop_p) ? p * keep_scale : 0.f;
+        pw[j] = p;
+      }
+    }
+    __syncwarp();
+    const int d = lane * 2;
+    if (d < hd) {
+      float o0 = 0.f, o1 = 0.f;
+      for (int j = 0; j < Lk; ++j) {
+        const float p = pw[j];
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vs + j * pitch + d));
+        o0 = fmaf(p, v.x, o0);
+        o1 = fmaf(p, v.y, o1);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(a.o + (static_cast<int64_t>(b) * Lq + i) * a.ldo + h * hd + d) =
+          __floats2bfloat162_rn(o0, o1);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_kernel(const AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int hd = a.hd, pitch = hd + 2, Lk = a.Lk, Lq = a.Lq;
+  const int Lmax = Lk > Lq ? Lk : Lq;
+  bf16* Ks = reinterpret_cast<bf16*>(smem_att);
+  bf16* Vs = Ks + Lk * pitch;
+  bf16* Qs = Vs + Lk * pitch;
+  bf16* dOs = Qs + Lq * pitch;
+  float* lse = reinterpret_cast<float*>(dOs + ((Lq * pitch + 1) & ~1));
+  float* delta = lse + Lq;
+  float* wbuf = delta + Lq;  // [ATT_WARPS][2 * Lmax]
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t kvrow0 = static_cast<int64_t>(b % a.kv_mod) * Lk;
+  const int64_t qrow0 = static_cast<int64_t>(b % a.q_mod) * Lq;
+  load_rows(Ks, a.k + kvrow0 * a.ldkv + h * hd, a.ldkv, Lk, hd);
+  load_rows(Vs, a.v + kvrow0 * a.ldkv + h * hd, a.ldkv, Lk, hd);
+  load_rows(Qs, a.q + qrow0 * a.ldq + h * hd, a.ldq, Lq, hd);
+  load_rows(dOs, a.dout + (static_cast<int64_t>(b) * Lq) * a.lddo + h * hd, a.lddo, Lq, hd);
+  __syncthreads();
+  const uint8_t* mk = a.mask ? a.mask + static_cast<int64_t>(b % a.mask_mod) * Lk : nullptr;
+  const float scale = rsqrtf(static_cast<float>(hd));
+  uint64_t seed = 0, step = 0;
+  if (a.drop_p > 0.f) {
+    seed = a.rng[0];
+    step = a.rng[1];
+  }
+  const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  float* w0 = wbuf + warp * 2 * Lmax;
+  float* w1 = w0 + Lmax;
+
+  // ---- pass A: one warp per query row -> softmax stats, delta, dQ
+  for (int i = warp; i < Lq; i += ATT_WARPS) {
+    float s[ATT_MAXC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < ATT_MAXC; ++c) {
+      const int j = c * 32 + lane;
+      s[c] = -INFINITY;
+      if (j < Lk && !(mk && mk[j])) s[c] = scale * dot_row(Qs + i * pitch, Ks + j * pitch, hd);
+      m = fmaxf(m, s[c]);
+    }
+    m = wmax(m);
+    float l = 0.f;
+#pragma unroll
+    for (int c = 0; c < ATT_MAXC; ++c) {
+      s[c] = (s[c] == -INFINITY) ? 0.f : __expf(s[c] - m);
+      l += s[c];
+    }
+    l = wsum2(l);
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    const uint64_t pbase = ((static_cast<uint64_t>(b) * a.H + h) * Lq + i) * static_cast<uint64_t>(Lk);
+    float dp[ATT_MAXC];
+    float dl = 0.f;
+#pragma unroll
+    for (int c = 0; c < ATT_MAXC; ++c) {
+      const int j = c * 32 + lane;
+      dp[c] = 0.f;
+      if (j < Lk) {
+        s[c] *= inv_l;  // p_ij
+        float g = dot_row(dOs + i * pitch, Vs + j * pitch, hd);
+        if (a.drop_p > 0.f) g = dropout_keep(seed, step, a.site, pbase + j, a.drop_p) ? g * keep_scale : 0.f;
+        dp[c] = g;
+        dl = fmaf(s[c], g, dl);
+      }
+    }
+    dl = wsum2(dl);
+#pragma unroll
+    for (int c = 0; c < ATT_MAXC; ++c) {
+      const int j = c * 32 + lane;
+      if (j < Lk) w0[j] = s[c] * (dp[c] - dl);  // dS_ij
+    }
+    if (lane == 0) {
+      lse[i] = l > 0.f ? m + __logf(l) : INFINITY;
+      delta[i] = dl;
+    }
+    __syncwarp();
+    const int d = lane * 2;
+    if (d < hd) {
+      float g0 = 0.f, g1 = 0.f;
+      for (int j = 0; j < Lk; ++j) {
+        const float ds = w0[j];
+        const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Ks + j * pitch + d));
+        g0 = fmaf(ds, kk.x, g0);
+        g1 = fmaf(ds, kk.y, g1);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(a.dq + (static_cast<int64_t>(b) * Lq + i) * a.lddq + h * hd + d) =
+          __floats2bfloat162_rn(g0 * scale, g1 * scale);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- pass B: one warp per key row -> dK, dV
+  for (int j = warp; j < Lk; j += ATT_WARPS) {
+    const bool masked = mk && mk[j];
+#pragma unroll
+    for (int c = 0; c < ATT_MAXC; ++c) {
+      const int i = c * 32 + lane;
+      if (i < Lq) {
+        float ds = 0.f, pd = 0.f;
+        if (!masked) {
+          const float sc = scale * dot_row(Qs + i * pitch, Ks + j * pitch, hd);
+          const float p = __expf(sc - lse[i]);
+          float g = dot_row(dOs + i * pitch, Vs + j * pitch, hd);
+          pd = p;
+          if (a.drop_p > 0.f) {
+            const uint64_t pbase = ((static_cast<uint64_t>(b) * a.H + h) * Lq + i) * static_cast<uint64_t>(Lk);
+            const bool keep = dropout_keep(seed, step, a.site, pbase + j, a.drop_p);
+            g = keep ? g * keep_scale : 0.f;
+            pd = keep ? p * keep_scale : 0.f;
+          }
+          ds = p * (g - delta[i]);
+        }
+        w0[i] = ds;
+        w1[i] = pd;
+      }
+    }
+    __syncwarp();
+    const int d = lane * 2;
+    if (d < hd) {
+      float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+      for (int i = 0; i < Lq; ++i) {
+        const float ds = w0[i], pd = w1[i];
+        const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Qs + i * pitch + d));
+        const float2 dd = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dOs + i * pitch + d));
+        k0 = fmaf(ds, qq.x, k0);
+        k1 = fmaf(ds, qq.y, k1);
+        v0 = fmaf(pd, dd.x, v0);
+        v1 = fmaf(pd, dd.y, v1);
+      }
+      const int64_t row = static_cast<int64_t>(b) * Lk + j;
+      *reinterpret_cast<__nv_bfloat162*>(a.dk + row * a.lddkv + h * hd + d) = __floats2bfloat162_rn(k0 * scale, k1 * scale);
+      *reinterpret_cast<__nv_bfloat162*>(a.dv + row * a.lddkv + h * hd + d) = __floats2bfloat162_rn(v0, v1);
+    }
+    __syncwarp();
+  }
+}
+
+static int check_args(const AttnArgs& a) {
+  GG_REQUIRE(a.hd >= 2 && a.hd <= 64 && a.hd % 2 == 0, "attention head_dim %d unsupported (even, <= 64)", a.hd);
+  GG_REQUIRE(a.Lk >= 1 && a.Lk <= 32 * ATT_MAXC && a.Lq >= 1 && a.Lq <= 32 * ATT_MAXC,
+             "attention length Lq=%d Lk=%d unsupported (<= %d)", a.Lq, a.Lk, 32 * ATT_MAXC);
+  GG_REQUIRE(a.drop_p == 0.f || a.rng, "dropout needs rng state");
+  return GG_OK;
+}
+
+int k_attention_fwd(const AttnArgs& a, cudaStream_t st) {
+  int rc = check_args(a);
+  if (rc) return rc;
+  const int pitch = a.hd + 2;
+  const size_t smem = (static_cast<size_t>(2 * a.Lk * pitch + ((a.Lq * pitch + 1) & ~1))) * 2 +
+                      static_cast<size_t>(ATT_WARPS) * a.Lk * 4 + 16;
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    GG_CUDA_CHECK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  GG_REQUIRE(smem <= 200 * 1024, "attention working set too large");
+  attention_fwd_kernel<<<a.nb * a.H, ATT_WARPS * 32, smem, st>>>(a);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+int k_attention_bwd(const AttnArgs& a, cudaStream_t st) {
+  int rc = check_args(a);
+  if (rc) return rc;
+  const int pitch = a.hd + 2;
+  const int Lmax = a.Lk > a.Lq ? a.Lk : a.Lq;
+  const size_t smem = (static_cast<size_t>(2 * a.Lk * pitch + a.Lq * pitch + ((a.Lq * pitch + 1) & ~1))) * 2 +
+                      static_cast<size_t>(2 * a.Lq) * 4 + static_cast<size_t>(ATT_WARPS) * 2 * Lmax * 4 + 16;
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    GG_CUDA_CHECK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = 220 * 1024;
+  }
+  GG_REQUIRE(smem <= 220 * 1024, "attention backward working set too large");
+  attention_bwd_kernel<<<a.nb * a.H, ATT_WARPS * 32, smem, st>>>(a);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+}  // namespace gg

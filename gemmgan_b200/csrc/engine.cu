@@ -1,0 +1,933 @@
+// gg_engine: the WGAN-GP training step of GeMM-GAN as a fixed kernel sequence.
+//
+// Restructuring relative to the reference's autograd execution (see DESIGN.md for the derivations):
+//  * critic layer 1 is linear in the gene vector, so the interpolated pass re-uses the fake/real GEMM
+//    results (a1x_interp = alpha*a1x_real + (1-alpha)*a1x_fake): no third [B,G] GEMM and no interpolated
+//    [B,G] tensor (reference :358-360);
+//  * gradient penalty via the Gram matrix M = W1x W1x^T: ||grad_b||^2 = u1_b M u1_b^T, and its W1 gradient
+//    (U1^T diag(r) U1) W1x rides as a second K-segment on the W1 weight-gradient GEMM (reference :351-374
+//    + the double backward inside :412);
+//  * the three critic tower passes of train_disc (fake / real / interpolated, :403,:404,:360) differ only by
+//    their dropout draws: they run as one batch of 3B rows (or one pass of B rows when dropout is off), and
+//    only the fake and real replicas are back-propagated (the GP's tower gradient is identically zero);
+//  * torch.cat((x, c)) (:157,:226) is a second K-segment, never materialised.
+#include "host_util.h"
+#include "kernels.h"
+
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace gg {
+
+#define GG_TRY(x)            \
+  do {                       \
+    int _rc = (x);           \
+    if (_rc) return _rc;     \
+  } while (0)
+
+struct Op {
+  const bf16* p = nullptr;
+  int64_t ld = 0;
+};
+
+struct Epi {
+  gg_epilogue e;
+  Epi() {
+    memset(&e, 0, sizeof(e));
+    e.alpha = 1.f;
+    e.mask_pos = 1.f;
+  }
+  Epi& bias(const float* b) { e.bias = b; return *this; }
+  Epi& act(int a, float s = 0.f) { e.act = a; e.slope = s; return *this; }
+  Epi& drop(float p, const uint64_t* rng, uint32_t site) {
+    if (p > 0.f) { e.drop_p = p; e.rng = rng; e.site = site; }
+    return *this;
+  }
+  Epi& mask(const void* m, int64_t ld, float pos, float neg) {
+    e.mask = m; e.mask_ld = ld; e.mask_f32 = 0; e.mask_pos = pos; e.mask_neg = neg; return *this;
+  }
+  Epi& res(const bf16* r, int64_t ld) { e.res = r; e.res_ld = ld; e.res_f32 = 0; return *this; }
+  Epi& obf(bf16* o, int64_t ld) { e.out_bf16 = o; e.ld_bf16 = ld; return *this; }
+  Epi& of32(float* o, int64_t ld) { e.out_f32 = o; e.ld_f32 = ld; return *this; }
+  Epi& rowmap(int div, int mul, int add) { e.row_div = div; e.row_mul = mul; e.row_add = add; return *this; }
+};
+
+struct Arena {
+  uint8_t* base;
+  int64_t off = 0;
+  explicit Arena(uint8_t* b) : base(b) {}
+  template <class T>
+  T* take(int64_t n) {
+    off = round_up64(off, 256);
+    T* p = reinterpret_cast<T*>(base + off);  // base may be null during the sizing pass
+    off += n * static_cast<int64_t>(sizeof(T));
+    return p;
+  }
+};
+
+struct WShadow {
+  bf16* p = nullptr;
+  int64_t ld = 0;
+};
+struct NetShadow {
+  WShadow w[GG_NSLOTS];
+  WShadow tr0_c;  // conditioning column block of the first trunk layer
+  bf16* base = nullptr;
+  int64_t elems = 0;
+  std::vector<ShadowSeg> segs;
+  ShadowSeg* segs_dev = nullptr;
+};
+
+struct TowerLayer {
+  bf16 *qkv, *ao, *z1, *x1, *h, *z2;
+  float *mean1, *rstd1, *mean2, *rstd2;
+};
+struct Tower {
+  int Rmax = 1;
+  float* gb;
+  bf16 *mod, *te, *X[3];
+  TowerLayer L[2];
+  bf16 *qp, *kvp, *ap, *pv, *qt, *kvt, *at, *c, *tmpE;
+};
+struct GradScratch {
+  bf16 *dc, *dat, *dqt, *dkvt, *dkvt_sum, *dp, *dap, *dqp, *dqp_sum, *dkvp;
+  bf16 *ga, *gb, *gz, *gy, *gh, *gao, *gqkv, *dte, *dte0, *dpe, *dmod, *dgb;
+};
+struct TrunkBufs {
+  float *a1x, *a1c, *h2f, *score, *Mg, *u1f, *y, *norms, *pen, *du2f, *roww;
+  bf16 *h1, *h2, *Mgb, *u2, *u1b, *ru1, *dv1, *Qb, *da2, *da1;
+  bf16 *hg1, *hg2, *dfake, *dag2, *dag1;
+};
+
+}  // namespace gg
+
+using namespace gg;
+
+struct gg_engine {
+  gg_model_cfg cfg;
+  gg_net_buffers nets[2];
+  NetShadow sh[2];
+  int S = 1, Gp = 0, F = 0, hd = 0;
+  bool cond = false, paper = false;
+  // staged inputs
+  bf16 *xfr, *patches, *text, *zbf, *xin;
+  uint8_t *mask_s, *tpad;
+  bool has_tpad = false, has_ppad = false;
+  Tower tw[2];
+  GradScratch gs;
+  TrunkBufs tb;
+  float *scratch, *stats, *opt_step[2], *normbuf;
+  uint64_t* rng;
+  void* splitk;
+  int64_t splitk_bytes = 0;
+  int64_t total_bytes = 0;
+
+  float* P(int net, int slot) const { return nets[net].off[slot] < 0 ? nullptr : nets[net].params + nets[net].off[slot]; }
+  float* Gr(int net, int slot) const { return nets[net].off[slot] < 0 ? nullptr : nets[net].grads + nets[net].off[slot]; }
+  Op W(int net, int slot) const { return Op{sh[net].w[slot].p, sh[net].w[slot].ld}; }
+
+  int mm(cudaStream_t st, int M, int N, int K, Op A, int a_mn, Op B, int b_mn, const Epi& epi, int K2 = 0,
+         Op A2 = Op(), Op B2 = Op()) const {
+    gg_gemm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.M = M; d.N = N;
+    d.nseg = K2 > 0 ? 2 : 1;
+    d.seg[0].a = A.p; d.seg[0].b = B.p; d.seg[0].lda = A.ld; d.seg[0].ldb = B.ld; d.seg[0].K = K;
+    if (K2 > 0) { d.seg[1].a = A2.p; d.seg[1].b = B2.p; d.seg[1].lda = A2.ld; d.seg[1].ldb = B2.ld; d.seg[1].K = K2; }
+    d.a_mn_major = a_mn; d.b_mn_major = b_mn;
+    d.epi = epi.e;
+    d.workspace = splitk; d.workspace_bytes = splitk_bytes;
+    d.impl = cfg.gemm_impl;
+    return gemm_dispatch(&d, st);
+  }
+  // Y = X W^T (+b): X [rows, in], W [out, in]
+  int linear(cudaStream_t st, int rows, int out, int in, Op X, Op Wt, const Epi& epi) const {
+    return mm(st, rows, out, in, X, 0, Wt, 0, epi);
+  }
+  // dX = dY W: dY [rows, out], W [out, in]
+  int dgrad(cudaStream_t st, int rows, int in, int out, Op dY, Op Wt, const Epi& epi) const {
+    return mm(st, rows, in, out, dY, 0, Wt, 1, epi);
+  }
+  // dW[out, in] = dY^T X, fp32 into the gradient buffer (pitch ldw)
+  int wgrad(cudaStream_t st, int out, int in, int rows, Op dY, Op X, float* dW, int64_t ldw) const {
+    return mm(st, out, in, rows, dY, 1, X, 1, Epi().of32(dW, ldw));
+  }
+  int bgrad(cudaStream_t st, const bf16* dY, int64_t ld, int64_t rows, int N, float* db) const {
+    if (!db) return GG_OK;
+    return k_colsum(dY, 0, ld, rows, N, nullptr, 1.f, db, 0, scratch, st);
+  }
+};
+
+namespace gg {
+
+static bool slot_matrix_shape(const gg_model_cfg& c, int net, int slot, int* rows, int* cols) {
+  const int E = c.E, F = c.ffn, condw = c.variant == GG_VARIANT_VANILLA ? 0 : E;
+  if (slot == GG_P_FILM_W) { *rows = 2 * c.Dp; *cols = c.Dt; return true; }
+  if (slot == GG_P_TEXT_W) { *rows = E; *cols = c.Dt; return true; }
+  if (slot == GG_P_PATCH_W) { *rows = E; *cols = c.Dp; return true; }
+  if (slot >= GG_P_LAYER0 && slot < GG_P_LAYER0 + 24) {
+    const int k = (slot - GG_P_LAYER0) % GG_L_COUNT;
+    if (k == GG_L_IN_W) { *rows = 3 * E; *cols = E; return true; }
+    if (k == GG_L_OUT_W) { *rows = E; *cols = E; return true; }
+    if (k == GG_L_FF1_W) { *rows = F; *cols = E; return true; }
+    if (k == GG_L_FF2_W) { *rows = E; *cols = F; return true; }
+    return false;
+  }
+  if (slot == GG_P_P2T_IN_W || slot == GG_P_T2P_IN_W) { *rows = 3 * E; *cols = E; return true; }
+  if (slot == GG_P_P2T_OUT_W || slot == GG_P_T2P_OUT_W) { *rows = E; *cols = E; return true; }
+  if (slot == GG_P_TR0_W) { *rows = c.H; *cols = (net == GG_NET_GEN ? c.L : c.G) + condw; return true; }
+  if (slot == GG_P_TR1_W) { *rows = c.H; *cols = c.H; return true; }
+  if (slot == GG_P_FIN_W) { *rows = net == GG_NET_GEN ? c.G : 1; *cols = c.H; return true; }
+  return false;
+}
+
+static void layout_shadows(gg_engine& e, Arena& ar) {
+  const gg_model_cfg& c = e.cfg;
+  for (int net = 0; net < 2; ++net) {
+    NetShadow& s = e.sh[net];
+    s.segs.clear();
+    int64_t elems = 0;
+    std::vector<std::pair<int, int64_t>> where;  // (slot or -1 for tr0_c, offset)
+    for (int slot = 0; slot < GG_NSLOTS; ++slot) {
+      int rows, cols;
+      if (e.nets[net].off[slot] < 0 || !slot_matrix_shape(c, net, slot, &rows, &cols)) continue;
+      if (slot == GG_P_FIN_W && net == GG_NET_DISC) continue;  // used as an fp32 vector
+      auto add = [&](int col0, int ncols, WShadow* dst) {
+        const int64_t ld = round_up64(ncols, 8);
+        elems = round_up64(elems, 128);
+        ShadowSeg sg;
+        sg.p_off = e.nets[net].off[slot];
+        sg.rows = rows; sg.cols = cols; sg.col0 = col0; sg.ncols = ncols;
+        sg.s_off = elems; sg.s_ld = ld;
+        s.segs.push_back(sg);
+        dst->ld = ld;
+        dst->p = reinterpret_cast<bf16*>(static_cast<uintptr_t>(elems));  // offset for now
+        elems += static_cast<int64_t>(rows) * ld;
+      };
+      if (slot == GG_P_TR0_W && c.variant != GG_VARIANT_VANILLA) {
+        const int first = cols - c.E;
+        add(0, first, &s.w[slot]);
+        add(first, c.E, &s.tr0_c);
+      } else {
+        add(0, cols, &s.w[slot]);
+      }
+    }
+    s.elems = elems;
+    s.base = ar.take<bf16>(elems);
+    for (int slot = 0; slot < GG_NSLOTS; ++slot)
+      if (s.w[slot].ld) s.w[slot].p = s.base + reinterpret_cast<uintptr_t>(s.w[slot].p);
+    if (s.tr0_c.ld) s.tr0_c.p = s.base + reinterpret_cast<uintptr_t>(s.tr0_c.p);
+    s.segs_dev = ar.take<ShadowSeg>(static_cast<int64_t>(s.segs.size()) + 1);
+  }
+}
+
+static void layout_tower(gg_engine& e, Tower& t, int Rmax, Arena& ar) {
+  const gg_model_cfg& c = e.cfg;
+  const int64_t B = c.B, S = e.S, E = c.E, F = e.F, P = c.P, T = c.T;
+  const int64_t rows = static_cast<int64_t>(Rmax) * B * S;
+  t.Rmax = Rmax;
+  t.gb = ar.take<float>(B * 2 * c.Dp);
+  t.mod = ar.take<bf16>(B * P * c.Dp);
+  t.te = ar.take<bf16>(B * T * E);
+  for (int i = 0; i < 3; ++i) t.X[i] = ar.take<bf16>(rows * E);
+  for (int l = 0; l < 2; ++l) {
+    TowerLayer& L = t.L[l];
+    L.qkv = ar.take<bf16>(rows * 3 * E);
+    L.ao = ar.take<bf16>(rows * E);
+    L.z1 = ar.take<bf16>(rows * E);
+    L.x1 = ar.take<bf16>(rows * E);
+    L.h = ar.take<bf16>(rows * F);
+    L.z2 = ar.take<bf16>(rows * E);
+    L.mean1 = ar.take<float>(rows);
+    L.rstd1 = ar.take<float>(rows);
+    L.mean2 = ar.take<float>(rows);
+    L.rstd2 = ar.take<float>(rows);
+  }
+  const int64_t rb = static_cast<int64_t>(Rmax) * B;
+  t.qp = ar.take<bf16>(B * E);
+  t.kvp = ar.take<bf16>(rows * 2 * E);
+  t.ap = ar.take<bf16>(rb * E);
+  t.pv = ar.take<bf16>(rb * E);
+  t.qt = ar.take<bf16>(rb * E);
+  t.kvt = ar.take<bf16>(B * T * 2 * E);
+  t.at = ar.take<bf16>(rb * E);
+  t.c = ar.take<bf16>(rb * E);
+  t.tmpE = ar.take<bf16>(rows * E);
+}
+
+static int64_t layout(gg_engine& e, uint8_t* base) {
+  const gg_model_cfg& c = e.cfg;
+  Arena ar(base);
+  const int64_t B = c.B, S = e.S, E = c.E, F = e.F, P = c.P, T = c.T, H = c.H, Gp = e.Gp;
+  layout_shadows(e, ar);
+  e.xfr = ar.take<bf16>(2 * B * Gp);
+  e.xin = ar.take<bf16>(B * Gp);
+  e.zbf = ar.take<bf16>(B * round_up64(c.L, 8));
+  e.stats = ar.take<float>(GG_STATS_COUNT);
+  e.opt_step[0] = ar.take<float>(4);
+  e.opt_step[1] = ar.take<float>(4);
+  e.normbuf = ar.take<float>(8);
+  e.rng = ar.take<uint64_t>(2);
+  if (e.cond) {
+    e.patches = ar.take<bf16>(B * P * c.Dp);
+    e.text = ar.take<bf16>(B * T * c.Dt);
+    e.mask_s = ar.take<uint8_t>(B * S);
+    e.tpad = ar.take<uint8_t>(B * T);
+    layout_tower(e, e.tw[GG_NET_GEN], 1, ar);
+    layout_tower(e, e.tw[GG_NET_DISC], c.dropout_p > 0.f ? 3 : 1, ar);
+    GradScratch& g = e.gs;
+    const int64_t n = 2 * B, rows = n * S;
+    g.dc = ar.take<bf16>(n * E);
+    g.dat = ar.take<bf16>(n * E);
+    g.dqt = ar.take<bf16>(n * E);
+    g.dkvt = ar.take<bf16>(n * T * 2 * E);
+    g.dkvt_sum = ar.take<bf16>(B * T * 2 * E);
+    g.dp = ar.take<bf16>(n * E);
+    g.dap = ar.take<bf16>(n * E);
+    g.dqp = ar.take<bf16>(n * E);
+    g.dqp_sum = ar.take<bf16>(B * E);
+    g.dkvp = ar.take<bf16>(rows * 2 * E);
+    g.ga = ar.take<bf16>(rows * E);
+    g.gb = ar.take<bf16>(rows * E);
+    g.gz = ar.take<bf16>(rows * E);
+    g.gy = ar.take<bf16>(rows * E);
+    g.gh = ar.take<bf16>(rows * F);
+    g.gao = ar.take<bf16>(rows * E);
+    g.gqkv = ar.take<bf16>(rows * 3 * E);
+    g.dte = ar.take<bf16>(B * T * E);
+    g.dte0 = ar.take<bf16>(B * E);
+    g.dpe = ar.take<bf16>(B * P * E);
+    g.dmod = ar.take<bf16>(B * P * c.Dp);
+    g.dgb = ar.take<bf16>(B * 2 * c.Dp);
+  }
+  TrunkBufs& t = e.tb;
+  t.a1x = ar.take<float>(2 * B * H);
+  t.a1c = ar.take<float>(3 * B * H);
+  t.h2f = ar.take<float>(3 * B * H);
+  t.score = ar.take<float>(3 * B);
+  t.Mg = ar.take<float>(H * H);
+  t.u1f = ar.take<float>(B * H);
+  t.y = ar.take<float>(B * H);
+  t.norms = ar.take<float>(B);
+  t.pen = ar.take<float>(B);
+  t.du2f = ar.take<float>(B * H);
+  t.roww = ar.take<float>(3 * B);
+  t.h1 = ar.take<bf16>(3 * B * H);
+  t.h2 = ar.take<bf16>(3 * B * H);
+  t.Mgb = ar.take<bf16>(H * H);
+  t.u2 = ar.take<bf16>(B * H);
+  t.u1b = ar.take<bf16>(B * H);
+  t.ru1 = ar.take<bf16>(B * H);
+  t.dv1 = ar.take<bf16>(B * H);
+  t.Qb = ar.take<bf16>(H * H);
+  t.da2 = ar.take<bf16>(2 * B * H);
+  t.da1 = ar.take<bf16>(2 * B * H);
+  t.hg1 = ar.take<bf16>(B * H);
+  t.hg2 = ar.take<bf16>(B * H);
+  t.dfake = ar.take<bf16>(B * Gp);
+  t.dag2 = ar.take<bf16>(B * H);
+  t.dag1 = ar.take<bf16>(B * H);
+  // scratch for deterministic column sums / LayerNorm weight grads
+  int64_t maxN = c.G;
+  if (3 * E > maxN) maxN = 3 * E;
+  if (2 * c.Dp > maxN) maxN = 2 * c.Dp;
+  if (F > maxN) maxN = F;
+  if (H > maxN) maxN = H;
+  int64_t scratch_floats = 64 * maxN;
+  if (scratch_floats < 296 * 2 * E) scratch_floats = 296 * 2 * E;
+  if (scratch_floats < 1024) scratch_floats = 1024;
+  e.scratch = ar.take<float>(scratch_floats);
+  e.splitk_bytes = 96LL << 20;
+  e.splitk = ar.take<uint8_t>(e.splitk_bytes);
+  return round_up64(ar.off, 256);
+}
+
+static int validate_cfg(const gg_model_cfg& c) {
+  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_PAPER, "unknown variant %d", c.variant);
+  GG_REQUIRE(c.B > 0 && c.G > 0 && c.L > 0 && c.H > 0, "bad sizes B=%d G=%d L=%d H=%d", c.B, c.G, c.L, c.H);
+  GG_REQUIRE(c.L % 8 == 0 && c.H % 8 == 0, "latent and hidden widths must be multiples of 8");
+  if (c.variant != GG_VARIANT_VANILLA) {
+    GG_REQUIRE(c.E % 32 == 0 && c.E <= 1024, "embedding width %d must be a multiple of 32 (<= 1024)", c.E);
+    GG_REQUIRE(c.n_heads > 0 && c.E % c.n_heads == 0 && (c.E / c.n_heads) % 2 == 0 && c.E / c.n_heads <= 64,
+               "unsupported head configuration E=%d heads=%d", c.E, c.n_heads);
+    GG_REQUIRE(c.n_layers >= 1 && c.n_layers <= 2, "n_layers must be 1 or 2");
+    GG_REQUIRE(c.Dt % 8 == 0 && c.Dp % 8 == 0 && c.ffn % 8 == 0, "feature widths must be multiples of 8");
+    GG_REQUIRE(c.P >= 1 && c.P + 1 <= 320 && c.T >= 1 && c.T <= 320, "token counts out of range P=%d T=%d", c.P, c.T);
+    GG_REQUIRE(c.dropout_p >= 0.f && c.dropout_p < 1.f, "bad dropout");
+  }
+  return GG_OK;
+}
+
+static void derive(gg_engine& e) {
+  const gg_model_cfg& c = e.cfg;
+  e.cond = c.variant != GG_VARIANT_VANILLA;
+  e.paper = c.variant == GG_VARIANT_PAPER;
+  e.S = e.cond ? c.P + 1 : 1;
+  e.Gp = static_cast<int>(round_up64(c.G, 8));
+  e.F = c.ffn;
+  e.hd = e.cond ? c.E / c.n_heads : 0;
+}
+
+// ------------------------------------------------------------------------------- tower forward
+static int tower_forward(gg_engine& e, int net, int R, float p, cudaStream_t st) {
+  const gg_model_cfg& c = e.cfg;
+  Tower& t = e.tw[net];
+  GG_REQUIRE(R <= t.Rmax, "tower replicas %d > allocated %d", R, t.Rmax);
+  const int B = c.B, S = e.S, E = c.E, F = e.F, P = c.P, T = c.T, Dp = c.Dp, Dt = c.Dt;
+  const int rows = R * B * S;
+  const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
+  // FiLM parameters from the text CLS / text vector (:129-134)
+  GG_TRY(e.linear(st, B, 2 * Dp, Dt, Op{e.text, static_cast<int64_t>(T) * Dt}, e.W(net, GG_P_FILM_W),
+                  Epi().bias(e.P(net, GG_P_FILM_B)).act(GG_ACT_FILM).of32(t.gb, 2 * Dp)));
+  GG_TRY(k_film_apply(e.patches, t.gb, t.mod, B, P, Dp, st));
+  if (e.paper)
+    GG_TRY(e.linear(st, B * T, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W),
+                    Epi().bias(e.P(net, GG_P_TEXT_B)).obf(t.te, E)));
+  // patch projection written straight behind the CLS row of replica 0 (:139-142)
+  GG_TRY(e.linear(st, B * P, E, Dp, Op{t.mod, Dp}, e.W(net, GG_P_PATCH_W),
+                  Epi().bias(e.P(net, GG_P_PATCH_B)).obf(t.X[0], E).rowmap(P, S, 1)));
+  GG_TRY(k_assemble_tokens(t.X[0], e.P(net, GG_P_CLS), R, B, S, E, st));
+  for (int l = 0; l < c.n_layers; ++l) {
+    TowerLayer& L = t.L[l];
+    const int ls = GG_P_LAYER0 + GG_L_COUNT * l;
+    const uint32_t site = site0 + 8u * l;
+    GG_TRY(e.linear(st, rows, 3 * E, E, Op{t.X[l], E}, e.W(net, ls + GG_L_IN_W),
+                    Epi().bias(e.P(net, ls + GG_L_IN_B)).obf(L.qkv, 3 * E)));
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = L.qkv; a.ldq = 3 * E; a.q_mod = R * B;
+    a.k = L.qkv + E; a.v = L.qkv + 2 * E; a.ldkv = 3 * E; a.kv_mod = R * B;
+    a.mask = e.mask_s; a.mask_mod = B;
+    a.nb = R * B; a.H = c.n_heads; a.hd = e.hd; a.Lq = S; a.Lk = S;
+    a.drop_p = p; a.rng = e.rng; a.site = site + 0;
+    a.o = L.ao; a.ldo = E;
+    GG_TRY(k_attention_fwd(a, st));
+    GG_TRY(e.linear(st, rows, E, E, Op{L.ao, E}, e.W(net, ls + GG_L_OUT_W),
+                    Epi().bias(e.P(net, ls + GG_L_OUT_B)).obf(t.tmpE, E)));
+    GG_TRY(k_add_ln_fwd(t.X[l], t.tmpE, e.P(net, ls + GG_L_N1_W), e.P(net, ls + GG_L_N1_B), L.z1, L.x1, L.mean1,
+                        L.rstd1, rows, E, c.ln_eps, p, e.rng, site + 1, st));
+    GG_TRY(e.linear(st, rows, F, E, Op{L.x1, E}, e.W(net, ls + GG_L_FF1_W),
+                    Epi().bias(e.P(net, ls + GG_L_FF1_B)).act(GG_ACT_LEAKY, 0.f).drop(p, e.rng, site + 2).obf(L.h, F)));
+    GG_TRY(e.linear(st, rows, E, F, Op{L.h, F}, e.W(net, ls + GG_L_FF2_W),
+                    Epi().bias(e.P(net, ls + GG_L_FF2_B)).obf(t.tmpE, E)));
+    GG_TRY(k_add_ln_fwd(L.x1, t.tmpE, e.P(net, ls + GG_L_N2_W), e.P(net, ls + GG_L_N2_B), L.z2, t.X[l + 1],
+                        L.mean2, L.rstd2, rows, E, c.ln_eps, p, e.rng, site + 3, st));
+  }
+  if (!e.paper) return GG_OK;  // film: conditioning = CLS row of X[n_layers]
+  bf16* Xf = t.X[c.n_layers];
+  const Op Wp = e.W(net, GG_P_P2T_IN_W), Wt = e.W(net, GG_P_T2P_IN_W);
+  const float* bp = e.P(net, GG_P_P2T_IN_B);
+  const float* bt = e.P(net, GG_P_T2P_IN_B);
+  // patch2text: query = encoded text CLS, keys/values = encoder output (:149-150)
+  GG_TRY(e.linear(st, B, E, E, Op{t.te, static_cast<int64_t>(T) * E}, Wp, Epi().bias(bp).obf(t.qp, E)));
+  GG_TRY(e.linear(st, rows, 2 * E, E, Op{Xf, E}, Op{Wp.p + static_cast<int64_t>(E) * Wp.ld, Wp.ld},
+                  Epi().bias(bp ? bp + E : nullptr).obf(t.kvp, 2 * E)));
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.q = t.qp; a.ldq = E; a.q_mod = B;
+  a.k = t.kvp; a.v = t.kvp + E; a.ldkv = 2 * E; a.kv_mod = R * B;
+  a.mask = e.mask_s; a.mask_mod = B;
+  a.nb = R * B; a.H = c.n_heads; a.hd = e.hd; a.Lq = 1; a.Lk = S;
+  a.o = t.ap; a.ldo = E;
+  GG_TRY(k_attention_fwd(a, st));
+  GG_TRY(e.linear(st, R * B, E, E, Op{t.ap, E}, e.W(net, GG_P_P2T_OUT_W),
+                  Epi().bias(e.P(net, GG_P_P2T_OUT_B)).obf(t.pv, E)));
+  // text2patch: query = that vector, keys/values = encoded text tokens (:151-152)
+  GG_TRY(e.linear(st, R * B, E, E, Op{t.pv, E}, Wt, Epi().bias(bt).obf(t.qt, E)));
+  GG_TRY(e.linear(st, B * T, 2 * E, E, Op{t.te, E}, Op{Wt.p + static_cast<int64_t>(E) * Wt.ld, Wt.ld},
+                  Epi().bias(bt ? bt + E : nullptr).obf(t.kvt, 2 * E)));
+  memset(&a, 0, sizeof(a));
+  a.q = t.qt; a.ldq = E; a.q_mod = R * B;
+  a.k = t.kvt; a.v = t.kvt + E; a.ldkv = 2 * E; a.kv_mod = B;
+  a.mask = e.has_tpad ? e.tpad : nullptr; a.mask_mod = B;
+  a.nb = R * B; a.H = c.n_heads; a.hd = e.hd; a.Lq = 1; a.Lk = T;
+  a.o = t.at; a.ldo = E;
+  GG_TRY(k_attention_fwd(a, st));
+  // c = text vector + patch vector (:153-155)
+  GG_TRY(e.linear(st, R * B, E, E, Op{t.at, E}, e.W(net, GG_P_T2P_OUT_W),
+                  Epi().bias(e.P(net, GG_P_T2P_OUT_B)).res(t.pv, E).obf(t.c, E)));
+  return GG_OK;
+}
+
+static Op cond_vec(const gg_engine& e, int net) {
+  const Tower& t = e.tw[net];
+  if (e.paper) return Op{t.c, e.cfg.E};
+  return Op{t.X[e.cfg.n_layers], static_cast<int64_t>(e.S) * e.cfg.E};
+}
+
+// ------------------------------------------------------------------------------ tower backward
+// dc: [Rg*B, E] gradient of the loss w.r.t. the conditioning vectors of the first Rg replicas.
+static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc, cudaStream_t st) {
+  const gg_model_cfg& c = e.cfg;
+  Tower& t = e.tw[net];
+  GradScratch& g = e.gs;
+  const int B = c.B, S = e.S, E = c.E, F = e.F, P = c.P, T = c.T, Dp = c.Dp, Dt = c.Dt;
+  const int n = Rg * B, rows = n * S;
+  const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
+  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  bf16* Xf = t.X[c.n_layers];
+  if (e.paper) {
+    const Op Wp = e.W(net, GG_P_P2T_IN_W), Wt = e.W(net, GG_P_T2P_IN_W);
+    const Op Wp_kv{Wp.p + static_cast<int64_t>(E) * Wp.ld, Wp.ld}, Wt_kv{Wt.p + static_cast<int64_t>(E) * Wt.ld, Wt.ld};
+    float* gWp = e.Gr(net, GG_P_P2T_IN_W);
+    float* gWt = e.Gr(net, GG_P_T2P_IN_W);
+    float* gbp = e.Gr(net, GG_P_P2T_IN_B);
+    float* gbt = e.Gr(net, GG_P_T2P_IN_B);
+    // c = at Wo_t^T + bo_t + pv
+    GG_TRY(e.wgrad(st, E, E, n, Op{dc, E}, Op{t.at, E}, e.Gr(net, GG_P_T2P_OUT_W), E));
+    GG_TRY(e.bgrad(st, dc, E, n, E, e.Gr(net, GG_P_T2P_OUT_B)));
+    GG_TRY(e.dgrad(st, n, E, E, Op{dc, E}, e.W(net, GG_P_T2P_OUT_W), Epi().obf(g.dat, E)));
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = t.qt; a.ldq = E; a.q_mod = n;
+    a.k = t.kvt; a.v = t.kvt + E; a.ldkv = 2 * E; a.kv_mod = B;
+    a.mask = e.has_tpad ? e.tpad : nullptr; a.mask_mod = B;
+    a.nb = n; a.H = c.n_heads; a.hd = e.hd; a.Lq = 1; a.Lk = T;
+    a.dout = g.dat; a.lddo = E; a.dq = g.dqt; a.lddq = E;
+    a.dk = g.dkvt; a.dv = g.dkvt + E; a.lddkv = 2 * E;
+    GG_TRY(k_attention_bwd(a, st));
+    // qt = pv Wq_t^T + bq_t ; dp = dqt Wq_t + dc (residual path)
+    GG_TRY(e.wgrad(st, E, E, n, Op{g.dqt, E}, Op{t.pv, E}, gWt, E));
+    GG_TRY(e.bgrad(st, g.dqt, E, n, E, gbt));
+    GG_TRY(e.dgrad(st, n, E, E, Op{g.dqt, E}, Wt, Epi().res(dc, E).obf(g.dp, E)));
+    // kvt = te Wkv_t^T + bkv_t (shared by the replicas)
+    const bf16* dkvt = g.dkvt;
+    if (Rg > 1) {
+      GG_TRY(k_sum_replicas(g.dkvt, g.dkvt_sum, Rg, static_cast<int64_t>(B) * T * 2 * E, st));
+      dkvt = g.dkvt_sum;
+    }
+    GG_TRY(e.wgrad(st, 2 * E, E, B * T, Op{dkvt, 2 * E}, Op{t.te, E}, gWt + static_cast<int64_t>(E) * E, E));
+    GG_TRY(e.bgrad(st, dkvt, 2 * E, B * T, 2 * E, gbt ? gbt + E : nullptr));
+    GG_TRY(e.dgrad(st, B * T, E, 2 * E, Op{dkvt, 2 * E}, Wt_kv, Epi().obf(g.dte, E)));
+    // pv = ap Wo_p^T + bo_p
+    GG_TRY(e.wgrad(st, E, E, n, Op{g.dp, E}, Op{t.ap, E}, e.Gr(net, GG_P_P2T_OUT_W), E));
+    GG_TRY(e.bgrad(st, g.dp, E, n, E, e.Gr(net, GG_P_P2T_OUT_B)));
+    GG_TRY(e.dgrad(st, n, E, E, Op{g.dp, E}, e.W(net, GG_P_P2T_OUT_W), Epi().obf(g.dap, E)));
+    memset(&a, 0, sizeof(a));
+    a.q = t.qp; a.ldq = E; a.q_mod = B;
+    a.k = t.kvp; a.v = t.kvp + E; a.ldkv = 2 * E; a.kv_mod = n;
+    a.mask = e.mask_s; a.mask_mod = B;
+    a.nb = n; a.H = c.n_heads; a.hd = e.hd; a.Lq = 1; a.Lk = S;
+    a.dout = g.dap; a.lddo = E; a.dq = g.dqp; a.lddq = E;
+    a.dk = g.dkvp; a.dv = g.dkvp + E; a.lddkv = 2 * E;
+    GG_TRY(k_attention_bwd(a, st));
+    // qp = te[:,0] Wq_p^T + bq_p (shared by the replicas)
+    const bf16* dqp = g.dqp;
+    if (Rg > 1) {
+      GG_TRY(k_sum_replicas(g.dqp, g.dqp_sum, Rg, static_cast<int64_t>(B) * E, st));
+      dqp = g.dqp_sum;
+    }
+    GG_TRY(e.wgrad(st, E, E, B, Op{dqp, E}, Op{t.te, static_cast<int64_t>(T) * E}, gWp, E));
+    GG_TRY(e.bgrad(st, dqp, E, B, E, gbp));
+    GG_TRY(e.dgrad(st, B, E, E, Op{dqp, E}, Wp, Epi().obf(g.dte0, E)));
+    GG_TRY(k_scatter_add_rows(g.dte, g.dte0, B, T, E, st));
+    // kvp = Xf Wkv_p^T + bkv_p
+    GG_TRY(e.wgrad(st, 2 * E, E, rows, Op{g.dkvp, 2 * E}, Op{Xf, E}, gWp + static_cast<int64_t>(E) * E, E));
+    GG_TRY(e.bgrad(st, g.dkvp, 2 * E, rows, 2 * E, gbp ? gbp + E : nullptr));
+    GG_TRY(e.dgrad(st, rows, E, 2 * E, Op{g.dkvp, 2 * E}, Wp_kv, Epi().obf(g.ga, E)));
+    // text encoder
+    GG_TRY(e.wgrad(st, E, Dt, B * T, Op{g.dte, E}, Op{e.text, Dt}, e.Gr(net, GG_P_TEXT_W), Dt));
+    GG_TRY(e.bgrad(st, g.dte, E, B * T, E, e.Gr(net, GG_P_TEXT_B)));
+  } else {
+    GG_TRY(k_scatter_cls(g.ga, dc, n, S, E, st));
+  }
+  for (int l = c.n_layers - 1; l >= 0; --l) {
+    TowerLayer& L = t.L[l];
+    const int ls = GG_P_LAYER0 + GG_L_COUNT * l;
+    const uint32_t site = site0 + 8u * l;
+    // x_out = LN2(x1 + drop(ff))
+    GG_TRY(k_add_ln_bwd(g.ga, L.z2, L.mean2, L.rstd2, e.P(net, ls + GG_L_N2_W), g.gz, p > 0.f ? g.gy : nullptr,
+                        e.Gr(net, ls + GG_L_N2_W), e.Gr(net, ls + GG_L_N2_B), rows, E, p, e.rng, site + 3,
+                        e.scratch, st));
+    const bf16* dff = p > 0.f ? g.gy : g.gz;
+    GG_TRY(e.wgrad(st, E, F, rows, Op{dff, E}, Op{L.h, F}, e.Gr(net, ls + GG_L_FF2_W), F));
+    GG_TRY(e.bgrad(st, dff, E, rows, E, e.Gr(net, ls + GG_L_FF2_B)));
+    GG_TRY(e.dgrad(st, rows, F, E, Op{dff, E}, e.W(net, ls + GG_L_FF2_W),
+                   Epi().mask(L.h, F, keep_scale, 0.f).obf(g.gh, F)));
+    GG_TRY(e.wgrad(st, F, E, rows, Op{g.gh, F}, Op{L.x1, E}, e.Gr(net, ls + GG_L_FF1_W), E));
+    GG_TRY(e.bgrad(st, g.gh, F, rows, F, e.Gr(net, ls + GG_L_FF1_B)));
+    GG_TRY(e.dgrad(st, rows, E, F, Op{g.gh, F}, e.W(net, ls + GG_L_FF1_W), Epi().res(g.gz, E).obf(g.gb, E)));
+    // x1 = LN1(x_in + drop(sa))
+    GG_TRY(k_add_ln_bwd(g.gb, L.z1, L.mean1, L.rstd1, e.P(net, ls + GG_L_N1_W), g.gz, p > 0.f ? g.gy : nullptr,
+                        e.Gr(net, ls + GG_L_N1_W), e.Gr(net, ls + GG_L_N1_B), rows, E, p, e.rng, site + 1,
+                        e.scratch, st));
+    const bf16* dsa = p > 0.f ? g.gy : g.gz;
+    GG_TRY(e.wgrad(st, E, E, rows, Op{dsa, E}, Op{L.ao, E}, e.Gr(net, ls + GG_L_OUT_W), E));
+    GG_TRY(e.bgrad(st, dsa, E, rows, E, e.Gr(net, ls + GG_L_OUT_B)));
+    GG_TRY(e.dgrad(st, rows, E, E, Op{dsa, E}, e.W(net, ls + GG_L_OUT_W), Epi().obf(g.gao, E)));
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = L.qkv; a.ldq = 3 * E; a.q_mod = n;
+    a.k = L.qkv + E; a.v = L.qkv + 2 * E; a.ldkv = 3 * E; a.kv_mod = n;
+    a.mask = e.mask_s; a.mask_mod = B;
+    a.nb = n; a.H = c.n_heads; a.hd = e.hd; a.Lq = S; a.Lk = S;
+    a.drop_p = p; a.rng = e.rng; a.site = site + 0;
+    a.dout = g.gao; a.lddo = E; a.dq = g.gqkv; a.lddq = 3 * E;
+    a.dk = g.gqkv + E; a.dv = g.gqkv + 2 * E; a.lddkv = 3 * E;
+    GG_TRY(k_attention_bwd(a, st));
+    GG_TRY(e.wgrad(st, 3 * E, E, rows, Op{g.gqkv, 3 * E}, Op{t.X[l], E}, e.Gr(net, ls + GG_L_IN_W), E));
+    GG_TRY(e.bgrad(st, g.gqkv, 3 * E, rows, 3 * E, e.Gr(net, ls + GG_L_IN_B)));
+    GG_TRY(e.dgrad(st, rows, E, 3 * E, Op{g.gqkv, 3 * E}, e.W(net, ls + GG_L_IN_W), Epi().res(g.gz, E).obf(g.ga, E)));
+  }
+  // X0 = [cls | patch projections], replicas share the projections
+  GG_TRY(k_colsum(g.ga, 0, static_cast<int64_t>(S) * E, n, E, nullptr, 1.f, e.Gr(net, GG_P_CLS), 0, e.scratch, st));
+  GG_TRY(k_unassemble_tokens(g.ga, g.dpe, nullptr, Rg, B, S, E, st));
+  GG_TRY(e.wgrad(st, E, Dp, B * P, Op{g.dpe, E}, Op{t.mod, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
+  GG_TRY(e.bgrad(st, g.dpe, E, B * P, E, e.Gr(net, GG_P_PATCH_B)));
+  GG_TRY(e.dgrad(st, B * P, Dp, E, Op{g.dpe, E}, e.W(net, GG_P_PATCH_W), Epi().obf(g.dmod, Dp)));
+  GG_TRY(k_film_bwd(g.dmod, e.patches, t.gb, g.dgb, B, P, Dp, st));
+  GG_TRY(e.wgrad(st, 2 * Dp, Dt, B, Op{g.dgb, 2 * Dp}, Op{e.text, static_cast<int64_t>(T) * Dt},
+                 e.Gr(net, GG_P_FILM_W), Dt));
+  GG_TRY(e.bgrad(st, g.dgb, 2 * Dp, B, 2 * Dp, e.Gr(net, GG_P_FILM_B)));
+  return GG_OK;
+}
+
+// --------------------------------------------------------------------------- generator forward
+static int gen_forward(gg_engine& e, const float* z, float p, float* out_f32, cudaStream_t st) {
+  const gg_model_cfg& c = e.cfg;
+  TrunkBufs& t = e.tb;
+  const int B = c.B, H = c.H, L = c.L, G = c.G, E = c.E;
+  const int Lp = static_cast<int>(round_up64(L, 8));
+  GG_TRY(k_cast_f32_bf16(z, L, e.zbf, Lp, B, L, st));
+  const int net = GG_NET_GEN;
+  Epi e1 = Epi().bias(e.P(net, GG_P_TR0_B)).act(GG_ACT_LEAKY, c.slope).obf(t.hg1, H);
+  if (e.cond) {
+    GG_TRY(tower_forward(e, net, 1, p, st));
+    const Op cv = cond_vec(e, net);
+    GG_TRY(e.mm(st, B, H, L, Op{e.zbf, Lp}, 0, e.W(net, GG_P_TR0_W), 0, e1, E, cv,
+                Op{e.sh[net].tr0_c.p, e.sh[net].tr0_c.ld}));
+  } else {
+    GG_TRY(e.linear(st, B, H, L, Op{e.zbf, Lp}, e.W(net, GG_P_TR0_W), e1));
+  }
+  GG_TRY(e.linear(st, B, H, H, Op{t.hg1, H}, e.W(net, GG_P_TR1_W),
+                  Epi().bias(e.P(net, GG_P_TR1_B)).act(GG_ACT_LEAKY, c.slope).obf(t.hg2, H)));
+  Epi ef = Epi().bias(e.P(net, GG_P_FIN_B)).obf(e.xfr, e.Gp);
+  if (out_f32) ef.of32(out_f32, G);
+  GG_TRY(e.linear(st, B, G, H, Op{t.hg2, H}, e.W(net, GG_P_FIN_W), ef));
+  return GG_OK;
+}
+
+// critic trunk forward on npass row groups; nx = number of gene matrices in xfr (1: fake, 2: fake+real)
+static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, int R, const float* alpha,
+                                cudaStream_t st) {
+  const gg_model_cfg& c = e.cfg;
+  TrunkBufs& t = e.tb;
+  const int B = c.B, H = c.H, G = c.G, E = c.E, net = GG_NET_DISC;
+  GG_TRY(e.linear(st, nx * B, H, G, Op{x, e.Gp}, e.W(net, GG_P_TR0_W), Epi().of32(t.a1x, H)));
+  const float* a1c = nullptr;
+  if (e.cond) {
+    const Op cv = cond_vec(e, net);
+    GG_TRY(e.linear(st, R * B, H, E, cv, Op{e.sh[net].tr0_c.p, e.sh[net].tr0_c.ld},
+                    Epi().bias(e.P(net, GG_P_TR0_B)).of32(t.a1c, H)));
+    a1c = t.a1c;
+  }
+  GG_TRY(k_trunk1_combine(t.a1x, a1c, e.P(net, GG_P_TR0_B), alpha, t.h1, B, H, npass, R, c.slope, st));
+  GG_TRY(e.linear(st, npass * B, H, H, Op{t.h1, H}, e.W(net, GG_P_TR1_W),
+                  Epi().bias(e.P(net, GG_P_TR1_B)).act(GG_ACT_LEAKY, c.slope).obf(t.h2, H).of32(t.h2f, H)));
+  GG_TRY(k_rowdot_bias(t.h2f, e.P(net, GG_P_FIN_W), e.P(net, GG_P_FIN_B), t.score, npass * B, H, st));
+  return GG_OK;
+}
+
+// Critic forward on [fake; real] + interpolated rows and the gradient-penalty value through the Gram
+// matrix of W1x. Leaves u2, u1, y, dv1, ru1, norms, pen and the loss stats behind.
+static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, cudaStream_t st) {
+  const gg_model_cfg& c = e.cfg;
+  TrunkBufs& t = e.tb;
+  const int B = c.B, H = c.H, G = c.G, net = GG_NET_DISC;
+  const float inv_b = 1.f / static_cast<float>(B);
+  if (e.cond) GG_TRY(tower_forward(e, net, R, p, st));
+  GG_TRY(critic_trunk_forward(e, e.xfr, 2, 3, R, alpha, st));
+  const Op W1x = e.W(net, GG_P_TR0_W), W2 = e.W(net, GG_P_TR1_W);
+  const float* w3 = e.P(net, GG_P_FIN_W);
+  const bf16* h1i = t.h1 + static_cast<int64_t>(2) * B * H;
+  const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;
+  GG_TRY(e.mm(st, H, H, G, W1x, 0, W1x, 0, Epi().of32(t.Mg, H).obf(t.Mgb, H)));
+  GG_TRY(k_gp_u2(h2i, w3, t.u2, B, H, c.slope, st));
+  GG_TRY(e.dgrad(st, B, H, H, Op{t.u2, H}, W2, Epi().mask(h1i, H, 1.f, c.slope).obf(t.u1b, H).of32(t.u1f, H)));
+  GG_TRY(e.linear(st, B, H, H, Op{t.u1b, H}, Op{t.Mgb, H}, Epi().of32(t.y, H)));
+  GG_TRY(k_gp_rows(t.y, t.u1f, h1i, t.norms, t.pen, t.ru1, t.dv1, B, H, c.slope, c.gp_weight, inv_b, st));
+  GG_TRY(k_disc_losses(t.score, t.pen, e.stats, B, c.gp_weight, inv_b, st));
+  return GG_OK;
+}
+
+}  // namespace gg
+
+// =============================================================================== C ABI
+extern "C" int gg_engine_workspace_bytes(const gg_model_cfg* cfg, int64_t* bytes) {
+  GG_REQUIRE(cfg && bytes, "null argument");
+  GG_TRY(validate_cfg(*cfg));
+  gg_engine tmp;
+  tmp.cfg = *cfg;
+  for (int n = 0; n < 2; ++n)
+    for (int s = 0; s < GG_NSLOTS; ++s) tmp.nets[n].off[s] = 0;  // assume every tensor present (upper bound)
+  derive(tmp);
+  *bytes = layout(tmp, nullptr);
+  return GG_OK;
+}
+
+extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* gen, const gg_net_buffers* disc,
+                                void* workspace, int64_t workspace_bytes, void* stream, gg_engine** out) {
+  GG_REQUIRE(cfg && gen && disc && workspace && out, "null argument");
+  GG_REQUIRE(gen->step_count && disc->step_count, "net buffers need a step_count");
+  GG_TRY(validate_cfg(*cfg));
+  int dev = 0;
+  GG_CUDA_CHECK(cudaGetDevice(&dev));
+  GG_TRY(gg_check_device(dev));
+  gg_engine* e = new gg_engine();
+  e->cfg = *cfg;
+  e->nets[GG_NET_GEN] = *gen;
+  e->nets[GG_NET_DISC] = *disc;
+  derive(*e);
+  GG_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  const int64_t need = layout(*e, reinterpret_cast<uint8_t*>(workspace));
+  if (need > workspace_bytes) {
+    set_error("workspace too small: need %lld bytes, have %lld", (long long)need, (long long)workspace_bytes);
+    delete e;
+    return GG_ERR_WORKSPACE;
+  }
+  e->total_bytes = need;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int n = 0; n < 2; ++n) {
+    NetShadow& s = e->sh[n];
+    if (!s.segs.empty())
+      GG_CUDA_CHECK(cudaMemcpyAsync(s.segs_dev, s.segs.data(), s.segs.size() * sizeof(ShadowSeg),
+                                    cudaMemcpyHostToDevice, st));
+  }
+  GG_CUDA_CHECK(cudaStreamSynchronize(st));  // segs vectors stay alive, but keep create() simple and safe
+  GG_CUDA_CHECK(cudaMemsetAsync(e->stats, 0, GG_STATS_COUNT * sizeof(float), st));
+  GG_CUDA_CHECK(cudaMemsetAsync(e->opt_step[0], 0, 4 * sizeof(float), st));
+  GG_CUDA_CHECK(cudaMemsetAsync(e->opt_step[1], 0, 4 * sizeof(float), st));
+  uint64_t rng0[2] = {cfg->seed, 0};
+  GG_CUDA_CHECK(cudaMemcpyAsync(e->rng, rng0, sizeof(rng0), cudaMemcpyHostToDevice, st));
+  GG_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int n = 0; n < 2; ++n) GG_TRY(gg_engine_refresh_shadows(e, n, stream));
+  *out = e;
+  return GG_OK;
+}
+
+extern "C" void gg_engine_destroy(gg_engine* e) { delete e; }
+
+extern "C" int gg_engine_refresh_shadows(gg_engine* e, int net, void* stream) {
+  GG_REQUIRE(e && (net == 0 || net == 1), "bad argument");
+  NetShadow& s = e->sh[net];
+  return k_refresh_shadows(e->nets[net].params, s.base, s.segs_dev, static_cast<int>(s.segs.size()), 0,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float* patches, const uint8_t* patch_pad,
+                                   const float* text, const uint8_t* text_pad, void* stream) {
+  GG_REQUIRE(e, "null engine");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const gg_model_cfg& c = e->cfg;
+  if (genes)  // real genes -> second half of the [fake; real] matrix
+    GG_TRY(k_cast_f32_bf16(genes, c.G, e->xfr + static_cast<int64_t>(c.B) * e->Gp, e->Gp, c.B, c.G, st));
+  if (e->cond) {
+    GG_REQUIRE(patches && text, "conditional variants need patches and text");
+    GG_TRY(k_cast_f32_bf16(patches, c.Dp, e->patches, c.Dp, static_cast<int64_t>(c.B) * c.P, c.Dp, st));
+    GG_TRY(k_cast_f32_bf16(text, c.Dt, e->text, c.Dt, static_cast<int64_t>(c.B) * c.T, c.Dt, st));
+    if (patch_pad) {
+      GG_TRY(k_mask_with_cls(patch_pad, e->mask_s, c.B, c.P, st));
+    } else {
+      GG_CUDA_CHECK(cudaMemsetAsync(e->mask_s, 0, static_cast<size_t>(c.B) * e->S, st));
+    }
+    e->has_tpad = text_pad != nullptr && e->paper;
+    if (e->has_tpad)
+      GG_CUDA_CHECK(cudaMemcpyAsync(e->tpad, text_pad, static_cast<size_t>(c.B) * c.T, cudaMemcpyDeviceToDevice, st));
+  }
+  return GG_OK;
+}
+
+extern "C" int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream) {
+  GG_REQUIRE(e && z && alpha, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const gg_model_cfg& c = e->cfg;
+  TrunkBufs& t = e->tb;
+  const int B = c.B, H = c.H, G = c.G, E = c.E, net = GG_NET_DISC;
+  const float p = (training && e->cond) ? c.dropout_p : 0.f;
+  const int R = p > 0.f ? 3 : 1;   // independently-dropped tower passes: fake, real, interpolated
+  const int Rg = p > 0.f ? 2 : 1;  // replicas that carry gradient (the GP's tower gradient is zero)
+  const float inv_b = 1.f / static_cast<float>(B);
+  GG_TRY(k_bump_rng(e->rng, st));
+  // ---- forward: G(z) (no graph), D on fake / real / interpolated (:391-408), GP value (:351-374)
+  GG_TRY(gen_forward(*e, z, p, nullptr, st));
+  GG_TRY(disc_forward_gp(*e, R, p, alpha, st));
+  const Op W1x = e->W(net, GG_P_TR0_W), W2 = e->W(net, GG_P_TR1_W);
+  const float* w3 = e->P(net, GG_P_FIN_W);
+  const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;
+  GG_TRY(e->mm(st, H, H, B, Op{t.ru1, H}, 1, Op{t.u1b, H}, 1, Epi().obf(t.Qb, H)));
+  // du2 = dv1 W2^T, masked by m2 -> gradient of the GP w.r.t. w3
+  GG_TRY(e->linear(st, B, H, H, Op{t.dv1, H}, W2, Epi().mask(h2i, H, 1.f, c.slope).of32(t.du2f, H)));
+  // ---- backward of loss_real + loss_fake on the fake / real rows
+  GG_TRY(k_score_bwd(t.h2, w3, t.da2, t.roww, 2 * B, B, H, c.slope, +1.f, -1.f, inv_b, st));
+  float* gw3 = e->Gr(net, GG_P_FIN_W);
+  GG_TRY(k_colsum(t.h2f, 1, H, 2 * B, H, t.roww, 1.f, gw3, 0, e->scratch, st));
+  GG_TRY(k_colsum(t.du2f, 1, H, B, H, nullptr, 1.f, gw3, 1, e->scratch, st));
+  GG_TRY(k_fill_f32(e->Gr(net, GG_P_FIN_B), 0.f, 1, st));  // d/db3 of mean(D(fake)) - mean(D(real)) is exactly 0
+  // dW2 = da2^T h1(fake,real)  +  u2^T dv1 (GP)
+  GG_TRY(e->mm(st, H, H, 2 * B, Op{t.da2, H}, 1, Op{t.h1, H}, 1, Epi().of32(e->Gr(net, GG_P_TR1_W), H), B,
+               Op{t.u2, H}, Op{t.dv1, H}));
+  GG_TRY(e->bgrad(st, t.da2, H, 2 * B, H, e->Gr(net, GG_P_TR1_B)));
+  GG_TRY(e->dgrad(st, 2 * B, H, H, Op{t.da2, H}, W2, Epi().mask(t.h1, H, 1.f, c.slope).obf(t.da1, H)));
+  GG_TRY(e->bgrad(st, t.da1, H, 2 * B, H, e->Gr(net, GG_P_TR0_B)));
+  // dW1[:, :G] = da1^T [fake; real]  +  Q W1x (GP, second K-segment)
+  const int64_t ldw1 = static_cast<int64_t>(G) + (e->cond ? E : 0);
+  float* gW1 = e->Gr(net, GG_P_TR0_W);
+  GG_TRY(e->mm(st, H, G, 2 * B, Op{t.da1, H}, 1, Op{e->xfr, e->Gp}, 1, Epi().of32(gW1, ldw1), H, Op{t.Qb, H}, W1x));
+  if (e->cond) {
+    const Op cv = cond_vec(*e, net);
+    const Op W1c{e->sh[net].tr0_c.p, e->sh[net].tr0_c.ld};
+    const Op da1_f{t.da1, H}, da1_r{t.da1 + static_cast<int64_t>(B) * H, H};
+    if (Rg == 2) {
+      GG_TRY(e->mm(st, H, E, 2 * B, da1_f, 1, cv, 1, Epi().of32(gW1 + G, ldw1)));
+      GG_TRY(e->dgrad(st, 2 * B, E, H, da1_f, W1c, Epi().obf(e->gs.dc, E)));
+    } else {  // one shared tower pass: both row groups meet the same conditioning vectors
+      GG_TRY(e->mm(st, H, E, B, da1_f, 1, cv, 1, Epi().of32(gW1 + G, ldw1), B, da1_r, cv));
+      GG_TRY(e->mm(st, B, E, H, da1_f, 0, W1c, 1, Epi().obf(e->gs.dc, E), H, da1_r, W1c));
+    }
+    GG_TRY(tower_backward(*e, net, Rg, p, e->gs.dc, st));
+  }
+  return GG_OK;
+}
+
+extern "C" int gg_engine_gen_grads(gg_engine* e, const float* z, int training, void* stream) {
+  GG_REQUIRE(e && z, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const gg_model_cfg& c = e->cfg;
+  TrunkBufs& t = e->tb;
+  const int B = c.B, H = c.H, G = c.G, E = c.E, L = c.L;
+  const int Lp = static_cast<int>(round_up64(L, 8));
+  const float p = (training && e->cond) ? c.dropout_p : 0.f;
+  const float inv_b = 1.f / static_cast<float>(B);
+  const int D = GG_NET_DISC, Gn = GG_NET_GEN;
+  GG_TRY(k_bump_rng(e->rng, st));
+  // ---- forward: fake = G(z), D(fake) (:441-452)
+  GG_TRY(gen_forward(*e, z, p, nullptr, st));
+  if (e->cond) GG_TRY(tower_forward(*e, D, 1, p, st));
+  GG_TRY(critic_trunk_forward(*e, e->xfr, 1, 1, 1, nullptr, st));
+  GG_TRY(k_gen_loss(t.score, e->stats, B, inv_b, st));
+  // ---- critic trunk input gradient (critic weights frozen, its tower is not on G's path)
+  const Op W1x = e->W(D, GG_P_TR0_W), W2 = e->W(D, GG_P_TR1_W);
+  GG_TRY(k_score_bwd(t.h2, e->P(D, GG_P_FIN_W), t.da2, nullptr, B, B, H, c.slope, -1.f, -1.f, inv_b, st));
+  GG_TRY(e->dgrad(st, B, H, H, Op{t.da2, H}, W2, Epi().mask(t.h1, H, 1.f, c.slope).obf(t.da1, H)));
+  GG_TRY(e->dgrad(st, B, G, H, Op{t.da1, H}, W1x, Epi().obf(t.dfake, e->Gp)));
+  // ---- generator trunk backward
+  const Op Wf = e->W(Gn, GG_P_FIN_W), Wg2 = e->W(Gn, GG_P_TR1_W), Wg1 = e->W(Gn, GG_P_TR0_W);
+  GG_TRY(e->wgrad(st, G, H, B, Op{t.dfake, e->Gp}, Op{t.hg2, H}, e->Gr(Gn, GG_P_FIN_W), H));
+  GG_TRY(e->bgrad(st, t.dfake, e->Gp, B, G, e->Gr(Gn, GG_P_FIN_B)));
+  GG_TRY(e->dgrad(st, B, H, G, Op{t.dfake, e->Gp}, Wf, Epi().mask(t.hg2, H, 1.f, c.slope).obf(t.dag2, H)));
+  GG_TRY(e->wgrad(st, H, H, B, Op{t.dag2, H}, Op{t.hg1, H}, e->Gr(Gn, GG_P_TR1_W), H));
+  GG_TRY(e->bgrad(st, t.dag2, H, B, H, e->Gr(Gn, GG_P_TR1_B)));
+  GG_TRY(e->dgrad(st, B, H, H, Op{t.dag2, H}, Wg2, Epi().mask(t.hg1, H, 1.f, c.slope).obf(t.dag1, H)));
+  const int64_t ldw = static_cast<int64_t>(L) + (e->cond ? E : 0);
+  float* gW1 = e->Gr(Gn, GG_P_TR0_W);
+  GG_TRY(e->wgrad(st, H, L, B, Op{t.dag1, H}, Op{e->zbf, Lp}, gW1, ldw));
+  GG_TRY(e->bgrad(st, t.dag1, H, B, H, e->Gr(Gn, GG_P_TR0_B)));
+  (void)Wg1;
+  if (e->cond) {
+    const Op cv = cond_vec(*e, Gn);
+    const Op Wc{e->sh[Gn].tr0_c.p, e->sh[Gn].tr0_c.ld};
+    GG_TRY(e->mm(st, H, E, B, Op{t.dag1, H}, 1, cv, 1, Epi().of32(gW1 + L, ldw)));
+    GG_TRY(e->dgrad(st, B, E, H, Op{t.dag1, H}, Wc, Epi().obf(e->gs.dc, E)));
+    GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc, st));
+  }
+  return GG_OK;
+}
+
+extern "C" int gg_engine_optim_step(gg_engine* e, int net, float lr, void* stream) {
+  GG_REQUIRE(e && (net == 0 || net == 1), "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const gg_net_buffers& nb = e->nets[net];
+  const float max_norm = net == GG_NET_DISC ? e->cfg.clip_d : e->cfg.clip_g;
+  const float* coef = nullptr;
+  float* statp = e->stats + (net == GG_NET_DISC ? GG_STAT_D_GRAD_NORM : GG_STAT_G_GRAD_NORM);
+  if (max_norm > 0.f) {
+    GG_TRY(k_grad_norm_clip(nb.grads, nb.n_used, max_norm, statp, e->scratch, st));
+    coef = statp + 1;
+  }
+  GG_TRY(k_optim_step(e->cfg.optimizer, nb.params, nb.grads, nb.exp_avg, nb.exp_avg_sq, nb.n_used, lr, coef,
+                      nb.step_count, st));
+  return gg_engine_refresh_shadows(e, net, stream);
+}
+
+extern "C" int gg_engine_generate(gg_engine* e, const float* z, float* out_f32, int training, void* stream) {
+  GG_REQUIRE(e && z && out_f32, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float p = (training && e->cond) ? e->cfg.dropout_p : 0.f;
+  if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
+  return gen_forward(*e, z, p, out_f32, st);
+}
+
+extern "C" int gg_engine_critic(gg_engine* e, const float* genes_f32, float* score_f32, int training, void* stream) {
+  GG_REQUIRE(e && genes_f32 && score_f32, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const gg_model_cfg& c = e->cfg;
+  const float p = (training && e->cond) ? c.dropout_p : 0.f;
+  if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
+  GG_TRY(k_cast_f32_bf16(genes_f32, c.G, e->xin, e->Gp, c.B, c.G, st));
+  if (e->cond) GG_TRY(tower_forward(*e, GG_NET_DISC, 1, p, st));
+  GG_TRY(critic_trunk_forward(*e, e->xin, 1, 1, 1, nullptr, st));
+  GG_CUDA_CHECK(cudaMemcpyAsync(score_f32, e->tb.score, sizeof(float) * c.B, cudaMemcpyDeviceToDevice, st));
+  return GG_OK;
+}
+
+extern "C" int gg_engine_gradient_penalty(gg_engine* e, const float* real_f32, const float* fake_f32,
+                                          const float* alpha, int training, float* gp_out, void* stream) {
+  GG_REQUIRE(e && fake_f32 && alpha && gp_out, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const gg_model_cfg& c = e->cfg;
+  const float p = (training && e->cond) ? c.dropout_p : 0.f;
+  if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
+  GG_TRY(k_cast_f32_bf16(fake_f32, c.G, e->xfr, e->Gp, c.B, c.G, st));
+  if (real_f32)
+    GG_TRY(k_cast_f32_bf16(real_f32, c.G, e->xfr + static_cast<int64_t>(c.B) * e->Gp, e->Gp, c.B, c.G, st));
+  GG_TRY(disc_forward_gp(*e, p > 0.f ? 3 : 1, p, alpha, st));
+  GG_CUDA_CHECK(cudaMemcpyAsync(gp_out, e->stats + GG_STAT_GP, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return GG_OK;
+}
+
+extern "C" float* gg_engine_stats(gg_engine* e) { return e ? e->stats : nullptr; }
+
+extern "C" void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows, int64_t* cols, int64_t* ld,
+                                  int32_t* is_f32) {
+  if (!e || !name) return nullptr;
+  const gg_model_cfg& c = e->cfg;
+  const std::string s(name);
+  void* p = nullptr;
+  int64_t r = 0, cc = 0, l = 0;
+  int32_t f = 0;
+  if (s == "fake_bf16") { p = e->xfr; r = c.B; cc = c.G; l = e->Gp; }
+  else if (s == "real_bf16") { p = e->xfr + static_cast<int64_t>(c.B) * e->Gp; r = c.B; cc = c.G; l = e->Gp; }
+  else if (s == "score") { p = e->tb.score; r = 3 * c.B; cc = 1; l = 1; f = 1; }
+  else if (s == "gp_norms") { p = e->tb.norms; r = c.B; cc = 1; l = 1; f = 1; }
+  else if (s == "gp_pen") { p = e->tb.pen; r = c.B; cc = 1; l = 1; f = 1; }
+  else if (s == "h1") { p = e->tb.h1; r = 3 * c.B; cc = c.H; l = c.H; }
+  else if (s == "h2f") { p = e->tb.h2f; r = 3 * c.B; cc = c.H; l = c.H; f = 1; }
+  else if (s == "gram") { p = e->tb.Mg; r = c.H; cc = c.H; l = c.H; f = 1; }
+  else if (s == "dfake") { p = e->tb.dfake; r = c.B; cc = c.G; l = e->Gp; }
+  else if (e->cond && (s == "cond_gen" || s == "cond_disc")) {
+    const int net = s == "cond_gen" ? GG_NET_GEN : GG_NET_DISC;
+    const Op cv = cond_vec(*e, net);
+    p = const_cast<bf16*>(cv.p); r = static_cast<int64_t>(e->tw[net].Rmax) * c.B; cc = c.E; l = cv.ld;
+  } else if (e->cond && s == "film_gb_disc") { p = e->tw[GG_NET_DISC].gb; r = c.B; cc = 2 * c.Dp; l = 2 * c.Dp; f = 1; }
+  else if (e->cond && s == "tokens_disc") { p = e->tw[GG_NET_DISC].X[c.n_layers]; r = static_cast<int64_t>(e->tw[GG_NET_DISC].Rmax) * c.B * e->S; cc = c.E; l = c.E; }
+  else if (e->cond && s == "tokens0_disc") { p = e->tw[GG_NET_DISC].X[0]; r = static_cast<int64_t>(e->tw[GG_NET_DISC].Rmax) * c.B * e->S; cc = c.E; l = c.E; }
+  if (rows) *rows = r;
+  if (cols) *cols = cc;
+  if (ld) *ld = l;
+  if (is_f32) *is_f32 = f;
+  return p;
+}
+
+extern "C" int gg_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, float lr, float max_norm,
+                             float* step_count, float* norm_out2, float* scratch, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float* coef = nullptr;
+  if (max_norm > 0.f) {
+    GG_REQUIRE(norm_out2 && scratch, "clipping needs norm_out2[2] and scratch[>=592]");
+    GG_TRY(k_grad_norm_clip(g, n, max_norm, norm_out2, scratch, st));
+    coef = norm_out2 + 1;
+  }
+  return k_optim_step(kind, p, g, m, v, n, lr, coef, step_count, st);
+}

@@ -1,0 +1,109 @@
+// Internal launch API of the non-GEMM kernels (all enqueue on `st`, return GG_OK / error code).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gemmgan.h"
+
+namespace gg {
+
+typedef __nv_bfloat16 bf16;
+
+int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t st);
+
+// ---- elementwise.cu -------------------------------------------------------------------------
+// dst[r, 0:cols] (bf16, pitch ld_dst) = src[r, 0:cols] (fp32, pitch ld_src)
+int k_cast_f32_bf16(const float* src, int64_t ld_src, bf16* dst, int64_t ld_dst, int64_t rows, int cols,
+                    cudaStream_t st);
+// key-padding mask with a never-padded CLS column in front: out[b, 0] = 0, out[b, 1+j] = in[b, j]
+int k_mask_with_cls(const uint8_t* in, uint8_t* out, int B, int P, cudaStream_t st);
+// mod[b, j, k] = gamma[b, k] * patches[b, j, k] + beta[b, k]; gb = [gamma | beta] fp32 [B, 2*Dp]
+int k_film_apply(const bf16* patches, const float* gb, bf16* mod, int B, int P, int Dp, cudaStream_t st);
+// dgb[b, k] = (sum_j dmod*patch) * (1 - gamma^2); dgb[b, Dp+k] = (sum_j dmod) * (|beta| < 5)
+int k_film_bwd(const bf16* dmod, const bf16* patches, const float* gb, bf16* dgb, int B, int P, int Dp,
+               cudaStream_t st);
+// x[r, b, 0, :] = cls; x[r, b, 1+j, :] = x[0, b, 1+j, :] for r >= 1 (replica 0 rows 1.. are already there)
+int k_assemble_tokens(bf16* x, const float* cls, int R, int B, int S, int E, cudaStream_t st);
+// dpe[b, j, :] = sum_r dx[r, b, 1+j, :]; dcls[:] = sum_{r,b} dx[r, b, 0, :]  (fp32 out for dcls)
+int k_unassemble_tokens(const bf16* dx, bf16* dpe, float* dcls, int R, int B, int S, int E, cudaStream_t st);
+// out[i] = sum_r in[r * n + i]
+int k_sum_replicas(const bf16* in, bf16* out, int R, int64_t n, cudaStream_t st);
+// dst[b * stride_rows, :] += src[b, :]   (bf16, E columns)
+int k_scatter_add_rows(bf16* dst, const bf16* src, int B, int stride_rows, int E, cudaStream_t st);
+// dst[b, 0, :] = src[b, :], other token rows zero: dst [B, S, E]
+int k_scatter_cls(bf16* dst, const bf16* src, int B, int S, int E, cudaStream_t st);
+// out[n] (fp32) = scale * sum_rows w[row] * in[row, n]; in bf16 or fp32; w may be NULL (=1). Deterministic.
+int k_colsum(const void* in, int in_f32, int64_t ld, int64_t rows, int N, const float* roww, float scale,
+             float* out, int accumulate, float* scratch, cudaStream_t st);
+
+// ---- trunk / gradient-penalty glue (elementwise.cu) ------------------------------------------
+// First critic layer after the big GEMM. a1x [nx*B, H] fp32 holds x*W1x^T for the fake (and real) rows;
+// a1c [R*B, H] fp32 (or NULL) holds c*W1c^T; bias b1 [H]. Writes h1 [npass*B, H] bf16 =
+// leaky(a1x-mix + a1c + b1) for passes {fake, real, interp}; interp mixes alpha*real+(1-alpha)*fake.
+int k_trunk1_combine(const float* a1x, const float* a1c, const float* b1, const float* alpha, bf16* h1,
+                     int B, int H, int npass, int R, float slope, cudaStream_t st);
+// score[m] = h2f[m, :] . w3 + b3
+int k_rowdot_bias(const float* h2f, const float* w3, const float* b3, float* score, int rows, int H,
+                  cudaStream_t st);
+// u2[b, o] = (h2i[b, o] > 0 ? 1 : slope) * w3[o]      (bf16 out)
+int k_gp_u2(const bf16* h2i, const float* w3, bf16* u2, int B, int H, float slope, cudaStream_t st);
+// per row: n = sqrt(sum_h y*u1); r = gpw*(2/Bglobal)*(1-1/n); ru1 = r*u1 ; dv1 = m1 .* (r*y) ; pen[b] = (n-1)^2
+int k_gp_rows(const float* y, const float* u1f, const bf16* h1i, float* norms, float* pen, bf16* ru1,
+              bf16* dv1, int B, int H, float slope, float gp_weight, float inv_batch, cudaStream_t st);
+// da2[m, o] = sign(m)/B * w3[o] * (h2[m, o] > 0 ? 1 : slope); rows [0,B): sign_fake, rows [B,2B): sign_real
+int k_score_bwd(const bf16* h2, const float* w3, bf16* da2, float* roww, int rows, int B, int H, float slope,
+                float sign_first, float sign_second, float inv_batch, cudaStream_t st);
+// stats: [0]=loss_real=-mean(score_real) [1]=loss_fake=mean(score_fake) [2]=gp=mean(pen) [3]=d_loss total
+int k_disc_losses(const float* score, const float* pen, float* stats, int B, float gp_weight, float inv_batch,
+                  cudaStream_t st);
+int k_gen_loss(const float* score, float* stats, int B, float inv_batch, cudaStream_t st);
+int k_fill_f32(float* p, float v, int64_t n, cudaStream_t st);
+int k_bump_rng(uint64_t* rng, cudaStream_t st);
+
+// ---- layernorm.cu ---------------------------------------------------------------------------
+// z = x + dropout(y); out = LayerNorm(z) * w + b. One warp per row; E % 32 == 0, E <= 1024.
+int k_add_ln_fwd(const bf16* x, const bf16* y, const float* w, const float* b, bf16* z, bf16* out,
+                 float* mean, float* rstd, int64_t rows, int E, float eps, float drop_p, const uint64_t* rng,
+                 uint32_t site, cudaStream_t st);
+// dz = LN backward of dout (grad to the residual input); dy = dropout-mask(dz) (grad to the sublayer output,
+// may be NULL when drop_p == 0); dw/db fp32 [E] (deterministic two-stage; scratch >= 2*E*nblocks floats)
+int k_add_ln_bwd(const bf16* dout, const bf16* z, const float* mean, const float* rstd, const float* w,
+                 bf16* dz, bf16* dy, float* dw, float* db, int64_t rows, int E, float drop_p,
+                 const uint64_t* rng, uint32_t site, float* scratch, cudaStream_t st);
+int64_t ln_bwd_scratch_floats(int64_t rows, int E);
+
+// ---- attention.cu ---------------------------------------------------------------------------
+struct AttnArgs {
+  const bf16* q; int64_t ldq; int q_mod;     // query row = (b % q_mod) * Lq + i
+  const bf16* k; const bf16* v; int64_t ldkv; int kv_mod;   // key row = (b % kv_mod) * Lk + j
+  const uint8_t* mask; int mask_mod;         // [mask_mod, Lk], 1 = padded key; may be NULL
+  int nb, H, hd, Lq, Lk;
+  float drop_p; const uint64_t* rng; uint32_t site;
+  bf16* o; int64_t ldo;                      // forward output [nb*Lq, H*hd]
+  // backward
+  const bf16* dout; int64_t lddo;            // [nb*Lq, H*hd]
+  bf16* dq; int64_t lddq;                    // [nb*Lq, H*hd]   (per replica even if q is shared)
+  bf16* dk; bf16* dv; int64_t lddkv;         // [nb*Lk, ...]    (per replica even if kv is shared)
+};
+int k_attention_fwd(const AttnArgs& a, cudaStream_t st);
+int k_attention_bwd(const AttnArgs& a, cudaStream_t st);
+
+// ---- optim.cu -------------------------------------------------------------------------------
+// total = sqrt(sum g^2) over n elements -> norm_out[0]; clip coefficient -> norm_out[1]
+int k_grad_norm_clip(const float* g, int64_t n, float max_norm, float* norm_out, float* scratch,
+                     cudaStream_t st);
+// One fused pass over the flat buffers: g *= coef (if coef_ptr), optimizer update, step counter in state.
+int k_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, float lr, const float* coef_ptr,
+                 float* step_count, cudaStream_t st);
+struct ShadowSeg {            // fp32 parameter sub-matrix -> bf16 shadow (padded pitch)
+  int64_t p_off;              // offset of the parameter tensor in the flat buffer
+  int32_t rows, cols;         // parameter shape [rows, cols]
+  int32_t col0, ncols;        // column range copied
+  int64_t s_off;              // offset (elements) in the shadow buffer
+  int64_t s_ld;
+};
+int k_refresh_shadows(const float* p, bf16* shadow, const ShadowSeg* segs_dev, int nseg, int max_rows,
+                      cudaStream_t st);
+
+}  // namespace gg

@@ -1,0 +1,219 @@
+"""Model classes behind the drop-in modules at the repo root.
+
+The parameters are ordinary nn.Parameters created by the same torch constructors, in the same order
+and under the same attribute names as the reference classes, so torch.manual_seed(s) reproduces the
+reference's initial weights and state_dict()s are interchangeable with reference checkpoints
+(including the never-used prototype `patches_transformer_layer.*` entries):
+  paper   generator/discriminator  src/conditional_gan_cross_attention_with_film.py:97-233
+  film    generator/discriminator  src/conditional_gan_film.py:97-204
+  vanilla generator_nocond/discriminator_nocond  src/vanilla_gan_unconditional.py:93-184
+
+forward() does not run torch kernels: it calls the engine (libgemmgan_sm100a.so) the trainer attached
+to the module. It is an inference forward (no autograd graph); the training step uses the engine's
+hand-written backward instead (gemmgan_b200/trainer.py).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _abi_decl as A
+
+VARIANT_IDS = {"vanilla": A.VARIANT_VANILLA, "film": A.VARIANT_FILM, "paper": A.VARIANT_PAPER}
+
+
+def build_linear_block(input_dims, output_dims, negative_slope=0.0, is_bn=False):
+    """Linear + LeakyReLU(negative_slope) (reference :56-72). BatchNorm (is_bn=True) is not on any
+    script's path (every __main__ passes is_bn=False) and is rejected."""
+    if is_bn:
+        raise NotImplementedError("is_bn=True is not used by any reference script and is not data-parallel safe")
+    return nn.Sequential(nn.Linear(input_dims, output_dims), nn.LeakyReLU(negative_slope=negative_slope))
+
+
+def build_stack(input_dims, dims, negative_slope=0.0, is_bn=False):
+    """nn.ModuleList of linear blocks (reference build_generator / build_discriminator :76-95)."""
+    stack = nn.ModuleList()
+    for i, d in enumerate(dims):
+        stack.append(build_linear_block(input_dims if i == 0 else dims[i - 1], d, negative_slope, is_bn))
+    return stack
+
+
+class _Net(nn.Module):
+    """Common body; subclasses fix role / variant and the reference constructor signature."""
+
+    _role = "gen"
+    _variant = "paper"
+
+    def _build(self, first_dim, embedding_dims, dims, text_embedding_dims, patches_embedding_dims,
+               negative_slope, is_bn):
+        v = self._variant
+        self.embedding_dims = embedding_dims
+        self.text_embedding_dims = text_embedding_dims
+        self.patches_embedding_dims = patches_embedding_dims
+        self.negative_slope = negative_slope
+        self.is_bn = is_bn
+        E = embedding_dims
+        if v in ("paper", "film"):
+            self.film_generator = nn.Linear(text_embedding_dims, patches_embedding_dims * 2)
+            if v == "paper":
+                self.text_encoder = nn.Linear(text_embedding_dims, E)
+            self.patches_encoder = nn.Linear(patches_embedding_dims, E)
+            self.patches_transformer_layer = nn.TransformerEncoderLayer(
+                d_model=E, nhead=4, dim_feedforward=E * 2, dropout=0.1, activation="relu", batch_first=True,
+                bias=(v == "paper"))
+            self.patches_cls_token = nn.Parameter(torch.empty(1, 1, E))
+            torch.nn.init.trunc_normal_(self.patches_cls_token, std=0.02)
+            self.patches_transformer = nn.TransformerEncoder(self.patches_transformer_layer, num_layers=2)
+            if v == "paper":
+                self.patch2text_attention = nn.MultiheadAttention(embed_dim=E, num_heads=4, batch_first=True)
+                self.text2patch_attention = nn.MultiheadAttention(embed_dim=E, num_heads=4, batch_first=True)
+        self.input_dims = first_dim + (0 if v == "vanilla" else E)
+        stack = build_stack(self.input_dims, dims[:-1], negative_slope, is_bn)
+        setattr(self, "generator" if self._role == "gen" else "discriminator", stack)
+        self.final_layer = nn.Linear(dims[-2], dims[-1])
+        self._gg_owner = None  # set by the trainer: object with ._module_forward(module, *args)
+
+    # -- engine plumbing ------------------------------------------------------------------
+    def trunk_blocks(self):
+        return self.generator if self._role == "gen" else self.discriminator
+
+    def slot_table(self):
+        """C-ABI parameter slot -> nn.Parameter (include/gemmgan.h enum gg_param_slot)."""
+        t = {}
+        v = self._variant
+        if v in ("paper", "film"):
+            t[A.P_FILM_W], t[A.P_FILM_B] = self.film_generator.weight, self.film_generator.bias
+            if v == "paper":
+                t[A.P_TEXT_W], t[A.P_TEXT_B] = self.text_encoder.weight, self.text_encoder.bias
+            t[A.P_PATCH_W], t[A.P_PATCH_B] = self.patches_encoder.weight, self.patches_encoder.bias
+            t[A.P_CLS] = self.patches_cls_token
+            for l, layer in enumerate(self.patches_transformer.layers):
+                b = A.P_LAYER0 + A.L_COUNT * l
+                t[b + A.L_IN_W], t[b + A.L_IN_B] = layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias
+                t[b + A.L_OUT_W], t[b + A.L_OUT_B] = layer.self_attn.out_proj.weight, layer.self_attn.out_proj.bias
+                t[b + A.L_FF1_W], t[b + A.L_FF1_B] = layer.linear1.weight, layer.linear1.bias
+                t[b + A.L_FF2_W], t[b + A.L_FF2_B] = layer.linear2.weight, layer.linear2.bias
+                t[b + A.L_N1_W], t[b + A.L_N1_B] = layer.norm1.weight, layer.norm1.bias
+                t[b + A.L_N2_W], t[b + A.L_N2_B] = layer.norm2.weight, layer.norm2.bias
+            if v == "paper":
+                p2t, t2p = self.patch2text_attention, self.text2patch_attention
+                t[A.P_P2T_IN_W], t[A.P_P2T_IN_B] = p2t.in_proj_weight, p2t.in_proj_bias
+                t[A.P_P2T_OUT_W], t[A.P_P2T_OUT_B] = p2t.out_proj.weight, p2t.out_proj.bias
+                t[A.P_T2P_IN_W], t[A.P_T2P_IN_B] = t2p.in_proj_weight, t2p.in_proj_bias
+                t[A.P_T2P_OUT_W], t[A.P_T2P_OUT_B] = t2p.out_proj.weight, t2p.out_proj.bias
+        blocks = self.trunk_blocks()
+        if len(blocks) != 2:
+            raise NotImplementedError("the engine implements the reference's 2-hidden-layer trunks "
+                                      "(generator_dims=[h,h,G], discriminator_dims=[h,h,1])")
+        t[A.P_TR0_W], t[A.P_TR0_B] = blocks[0][0].weight, blocks[0][0].bias
+        t[A.P_TR1_W], t[A.P_TR1_B] = blocks[1][0].weight, blocks[1][0].bias
+        t[A.P_FIN_W], t[A.P_FIN_B] = self.final_layer.weight, self.final_layer.bias
+        return {k: p for k, p in t.items() if p is not None}
+
+    def _engine_forward(self, *args):
+        if self._gg_owner is None:
+            raise RuntimeError(
+                f"{type(self).__name__}.forward needs the sm_100a engine: build the model through "
+                "WGAN_GP.build_WGAN_GP() (there is no PyTorch/CPU fallback path)")
+        return self._gg_owner._module_forward(self, *args)
+
+
+# ----------------------------------------------------------------------------- paper model
+class PaperGenerator(_Net):
+    _role, _variant = "gen", "paper"
+
+    def __init__(self, latent_dims, embedding_dims, generator_dims, text_embedding_dims=768,
+                 patches_embedding_dims=1024, negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.latent_dims = latent_dims
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.generator_dims = generator_dims
+        self._build(latent_dims, embedding_dims, generator_dims, text_embedding_dims, patches_embedding_dims,
+                    negative_slope, is_bn)
+
+    def forward(self, gene_expression, patches, patches_padding_mask, text_tokens, text_padding_mask):
+        return self._engine_forward(gene_expression, patches, patches_padding_mask, text_tokens, text_padding_mask)
+
+
+class PaperDiscriminator(_Net):
+    _role, _variant = "disc", "paper"
+
+    def __init__(self, vector_dims, embedding_dims, discriminator_dims, text_embedding_dims=768,
+                 patches_embedding_dims=1024, negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.vector_dims = vector_dims
+        self.discriminator_dims = discriminator_dims
+        self._build(vector_dims, embedding_dims, discriminator_dims, text_embedding_dims, patches_embedding_dims,
+                    negative_slope, is_bn)
+
+    def forward(self, gene_expression, patches, patches_padding_mask, text_tokens, text_padding_mask):
+        return self._engine_forward(gene_expression, patches, patches_padding_mask, text_tokens, text_padding_mask)
+
+
+# ------------------------------------------------------------------------------ film model
+class FilmGenerator(_Net):
+    _role, _variant = "gen", "film"
+
+    def __init__(self, latent_dims, embedding_dims, generator_dims, text_embedding_dims=768,
+                 patches_embedding_dims=1024, negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.latent_dims = latent_dims
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.generator_dims = generator_dims
+        self.embeding_dims = embedding_dims
+        self._build(latent_dims, embedding_dims, generator_dims, text_embedding_dims, patches_embedding_dims,
+                    negative_slope, is_bn)
+
+    def forward(self, x, text_embedding, patches, padding_mask):
+        return self._engine_forward(x, text_embedding, patches, padding_mask)
+
+
+class FilmDiscriminator(_Net):
+    _role, _variant = "disc", "film"
+
+    def __init__(self, vector_dims, embedding_dims, discriminator_dims, text_embedding_dims=768,
+                 patches_embedding_dims=1024, negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.vector_dims = vector_dims
+        self.discriminator_dims = discriminator_dims
+        self._build(vector_dims, embedding_dims, discriminator_dims, text_embedding_dims, patches_embedding_dims,
+                    negative_slope, is_bn)
+
+    def forward(self, x, text_embedding, patches, padding_mask):
+        return self._engine_forward(x, text_embedding, patches, padding_mask)
+
+
+# --------------------------------------------------------------------------- vanilla model
+class VanillaGenerator(_Net):
+    _role, _variant = "gen", "vanilla"
+
+    def __init__(self, latent_dims, numerical_dims, vocab_sizes, generator_dims, negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.latent_dims = latent_dims
+        self.numerical_dims = len(numerical_dims)
+        self.vocab_sizes = vocab_sizes
+        self.generator_dims = generator_dims
+        self.n_cat_vars = len(vocab_sizes)
+        self._build(latent_dims, 0, generator_dims, 0, 0, negative_slope, is_bn)
+        self.final_activation = nn.ReLU()
+        self.threshold = nn.Threshold(0, 0)
+
+    def forward(self, x):
+        return self._engine_forward(x)
+
+
+class VanillaDiscriminator(_Net):
+    _role, _variant = "disc", "vanilla"
+
+    def __init__(self, vector_dims, numerical_dims, vocab_sizes, discriminator_dims, negative_slope=0.0,
+                 is_bn=False):
+        super().__init__()
+        self.vector_dims = vector_dims
+        self.numerical_dims = len(numerical_dims)
+        self.vocab_sizes = vocab_sizes
+        self.discriminator_dims = discriminator_dims
+        self.n_cat_vars = len(vocab_sizes)
+        self._build(vector_dims, 0, discriminator_dims, 0, 0, negative_slope, is_bn)
+
+    def forward(self, x):
+        return self._engine_forward(x)

@@ -1,0 +1,230 @@
+"""Host-side runtime: flat parameter buffers and the ctypes wrapper of gg_engine.
+
+PyTorch provides device memory and streams; every computation is a C-ABI call into
+libgemmgan_sm100a.so. Nothing here has a CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import _abi_decl as A
+from . import _lib
+
+_ALIGN = 64  # elements (256 B): every tensor starts 16-byte aligned for 128-bit accesses
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+class FlatNet:
+    """Moves a module's parameters into one flat fp32 buffer (nn.Parameters become views), with a
+    matching flat gradient buffer and optimizer-state buffers. Tensors the forward never uses
+    (the prototype encoder layer the reference registers at :114) are placed behind `n_used`:
+    they get no gradient (`grad is None`, as in the reference) and are never updated."""
+
+    def __init__(self, module: nn.Module, device: torch.device, optimizer: str):
+        self.module = module
+        slots: Dict[int, nn.Parameter] = module.slot_table()
+        used_ids = {id(p) for p in slots.values()}
+        unused = [p for p in module.parameters() if id(p) not in used_ids]
+        off, self.offsets = 0, {}
+        for slot in sorted(slots):
+            self.offsets[slot] = off
+            off += (slots[slot].numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.n_used = off
+        tail = {}
+        for p in unused:
+            tail[id(p)] = off
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.params = torch.zeros(off, device=device, dtype=torch.float32)
+        self.grads = torch.zeros(self.n_used, device=device, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(self.n_used, device=device, dtype=torch.float32)
+        self.exp_avg = (torch.zeros(self.n_used, device=device, dtype=torch.float32)
+                        if optimizer in ("adam", "adamw") else None)
+        self.step_count = torch.zeros(4, device=device, dtype=torch.float32)
+        self.slots = slots
+        with torch.no_grad():
+            for slot, p in slots.items():
+                o = self.offsets[slot]
+                view = self.params[o:o + p.numel()].view(p.shape)
+                view.copy_(p.detach().to(device=device, dtype=torch.float32))
+                p.data = view
+                p.grad = self.grads[o:o + p.numel()].view(p.shape)
+            for p in unused:
+                o = tail[id(p)]
+                view = self.params[o:o + p.numel()].view(p.shape)
+                view.copy_(p.detach().to(device=device, dtype=torch.float32))
+                p.data = view
+                p.grad = None
+        # buffers (none in these models) and anything else follow the module to the device
+        self._versions = self._version_sum()
+
+    def _version_sum(self) -> int:
+        return sum(p._version for p in self.slots.values())
+
+    def externally_modified(self) -> bool:
+        """True when someone wrote to the parameters through PyTorch (load_state_dict, manual
+        edits) since the last call: the bf16 weight shadows then need a refresh."""
+        v = self._version_sum()
+        if v != self._versions:
+            self._versions = v
+            return True
+        return False
+
+    def reattach_grads(self) -> None:
+        """optimizer.zero_grad(set_to_none=True) drops p.grad; point it back at the flat buffer."""
+        for slot, p in self.slots.items():
+            if p.grad is None or p.grad.data_ptr() != self.grads.data_ptr() + 4 * self.offsets[slot]:
+                o = self.offsets[slot]
+                p.grad = self.grads[o:o + p.numel()].view(p.shape)
+
+    def c_struct(self) -> A.NetBuffers:
+        nb = A.NetBuffers()
+        nb.params = self.params.data_ptr()
+        nb.grads = self.grads.data_ptr()
+        nb.exp_avg = None if self.exp_avg is None else self.exp_avg.data_ptr()
+        nb.exp_avg_sq = self.exp_avg_sq.data_ptr()
+        nb.step_count = self.step_count.data_ptr()
+        nb.n_used = self.n_used
+        for s in range(A.NSLOTS):
+            nb.off[s] = self.offsets.get(s, -1)
+        return nb
+
+
+_OPT_IDS = {"rms_prop": A.OPT_RMSPROP, "adam": A.OPT_ADAM, "adamw": A.OPT_ADAMW}
+
+
+class Engine:
+    """One gg_engine: a (generator, critic) pair at a fixed per-rank batch size."""
+
+    def __init__(self, *, variant: str, B: int, G: int, L: int, E: int, H: int, Dt: int, Dp: int, P: int, T: int,
+                 gen: FlatNet, disc: FlatNet, slope: float, dropout_p: float, gp_weight: float, clip_d: float,
+                 clip_g: float, optimizer: str, seed: int = 0, gemm_impl: int = _lib.IMPL_TCGEN05,
+                 tower_bias: bool = True, device: Optional[torch.device] = None):
+        from .models import VARIANT_IDS
+
+        self.lib = _lib.lib()
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        _lib.require_device(self.device.index or 0)
+        cfg = A.ModelCfg()
+        cfg.variant = VARIANT_IDS[variant]
+        cfg.B, cfg.G, cfg.L, cfg.E, cfg.H = B, G, L, E, H
+        cfg.Dt, cfg.Dp, cfg.P, cfg.T = Dt, Dp, P, T
+        cfg.n_layers, cfg.n_heads, cfg.ffn = 2, 4, 2 * E
+        cfg.tower_bias = int(tower_bias)
+        cfg.slope, cfg.dropout_p, cfg.gp_weight = slope, dropout_p, gp_weight
+        cfg.clip_d, cfg.clip_g, cfg.ln_eps = clip_d, clip_g, 1e-5
+        cfg.optimizer = _OPT_IDS[optimizer]
+        cfg.gemm_impl = gemm_impl
+        cfg.seed = seed
+        self.cfg = cfg
+        self.variant, self.B, self.G, self.L = variant, B, G, L
+        self.gen, self.disc = gen, disc
+        nbytes = C.c_int64(0)
+        _lib.check(self.lib.gg_engine_workspace_bytes(C.byref(cfg), C.byref(nbytes)))
+        self.workspace = torch.empty(nbytes.value, device=self.device, dtype=torch.uint8)
+        self._gen_c, self._disc_c = gen.c_struct(), disc.c_struct()
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gg_engine_create(C.byref(cfg), C.byref(self._gen_c), C.byref(self._disc_c),
+                                                 _ptr(self.workspace), nbytes.value, _stream(), C.byref(h)))
+        self.handle = h
+        sp = self.lib.gg_engine_stats(self.handle)
+        self.stats = self._view(sp, A.STATS_COUNT, torch.float32)
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.gg_engine_destroy(self.handle)
+                self.handle = None
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def _view(self, ptr: int, n: int, dtype: torch.dtype) -> torch.Tensor:
+        off = ptr - self.workspace.data_ptr()
+        size = n * torch.empty((), dtype=dtype).element_size()
+        assert 0 <= off and off + size <= self.workspace.numel(), "pointer outside the engine workspace"
+        return self.workspace[off:off + size].view(dtype)
+
+    def buffer(self, name: str) -> torch.Tensor:
+        """Named internal device buffer as a [rows, cols] tensor view (tests / diagnostics)."""
+        rows, cols, ld, f32 = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        p = self.lib.gg_engine_buffer(self.handle, name.encode(), C.byref(rows), C.byref(cols), C.byref(ld),
+                                      C.byref(f32))
+        if not p:
+            raise KeyError(name)
+        dt = torch.float32 if f32.value else torch.bfloat16
+        flat = self._view(p, (rows.value - 1) * ld.value + cols.value, dt)
+        return torch.as_strided(flat, (rows.value, cols.value), (ld.value, 1))
+
+    # ---- thin wrappers ---------------------------------------------------------------------
+    def refresh_shadows(self, net: Optional[int] = None) -> None:
+        for n in ((A.NET_GEN, A.NET_DISC) if net is None else (net,)):
+            _lib.check(self.lib.gg_engine_refresh_shadows(self.handle, n, _stream()))
+
+    def sync_external_param_writes(self) -> None:
+        if self.gen.externally_modified():
+            self.refresh_shadows(A.NET_GEN)
+        if self.disc.externally_modified():
+            self.refresh_shadows(A.NET_DISC)
+
+    @staticmethod
+    def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if t is None:
+            return None
+        return t.contiguous() if t.dtype == torch.float32 else t.to(torch.float32).contiguous()
+
+    @staticmethod
+    def _u8(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if t is None:
+            return None
+        t = t.contiguous()
+        return t.view(torch.uint8) if t.dtype == torch.bool else t.to(torch.uint8)
+
+    def set_batch(self, genes=None, patches=None, patch_pad=None, text=None, text_pad=None) -> None:
+        g, p, t = self._f32(genes), self._f32(patches), self._f32(text)
+        pm, tm = self._u8(patch_pad), self._u8(text_pad)
+        self._keep = (g, p, t, pm, tm)  # keep alive until the enqueued casts have run
+        _lib.check(self.lib.gg_engine_set_batch(self.handle, _ptr(g), _ptr(p), _ptr(pm), _ptr(t), _ptr(tm), _stream()))
+
+    def disc_grads(self, z: torch.Tensor, alpha: torch.Tensor, training: bool = True) -> None:
+        z, alpha = self._f32(z), self._f32(alpha)
+        assert z.shape == (self.B, self.L) and alpha.numel() == self.B
+        _lib.check(self.lib.gg_engine_disc_grads(self.handle, _ptr(z), _ptr(alpha), int(training), _stream()))
+
+    def gen_grads(self, z: torch.Tensor, training: bool = True) -> None:
+        z = self._f32(z)
+        assert z.shape == (self.B, self.L)
+        _lib.check(self.lib.gg_engine_gen_grads(self.handle, _ptr(z), int(training), _stream()))
+
+    def optim_step(self, net: int, lr: float) -> None:
+        _lib.check(self.lib.gg_engine_optim_step(self.handle, net, float(lr), _stream()))
+
+    def generate(self, z: torch.Tensor, training: bool = False) -> torch.Tensor:
+        z = self._f32(z)
+        out = torch.empty(self.B, self.G, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.gg_engine_generate(self.handle, _ptr(z), _ptr(out), int(training), _stream()))
+        return out
+
+    def gradient_penalty(self, real, fake, alpha, training: bool = True) -> torch.Tensor:
+        r, f, a = self._f32(real), self._f32(fake), self._f32(alpha)
+        out = torch.empty((), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.gg_engine_gradient_penalty(self.handle, _ptr(r), _ptr(f), _ptr(a), int(training),
+                                                       _ptr(out), _stream()))
+        return out
+
+    def critic(self, genes: torch.Tensor, training: bool = False) -> torch.Tensor:
+        g = self._f32(genes)
+        out = torch.empty(self.B, 1, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.gg_engine_critic(self.handle, _ptr(g), _ptr(out), int(training), _stream()))
+        return out

@@ -1,0 +1,266 @@
+"""Trainer behind the drop-in WGAN_GP classes: same constructor kwargs, methods and attributes as
+the reference trainers, with train_disc / train_gen executed by the sm_100a engine.
+
+Reference: class WGAN_GP, src/conditional_gan_cross_attention_with_film.py:256-477 (paper model),
+src/conditional_gan_film.py:237-445 (film), class WGAN_GP_nocond src/vanilla_gan_unconditional.py:211-431.
+
+Differences that are deliberate (documented in DESIGN.md / INTEGRATION.md):
+  * the per-step `.item()` host syncs (:421-423, :461) are replaced by an async copy of the engine's
+    stats vector into pinned memory; `d_batch_loss`, `g_batch_loss`, `disc_loss`, `gen_loss` are
+    properties that synchronise on first read;
+  * `optimizer_disc` / `optimizer_gen` are real torch.optim objects over the same Parameters (so
+    `param_groups[i]['lr']` scheduling in fit() works) but their `.step()` is never called: the
+    update is the engine's fused flat-buffer kernel;
+  * data parallelism (absent in the reference): when torch.distributed is initialised the flat
+    gradient buffer is all-reduced (mean) between the backward and the optimizer kernel.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _abi_decl as A
+from . import _lib
+from .runtime import Engine, FlatNet
+
+
+def wasserstein_loss(y_pred, y_true):
+    return torch.mean(y_pred * y_true)
+
+
+def G_loss(fake_labels):
+    return wasserstein_loss(fake_labels, -torch.ones_like(fake_labels))
+
+
+def D_loss(real_labels, fake_labels):
+    loss_real = wasserstein_loss(-torch.ones_like(real_labels), real_labels)
+    loss_fake = wasserstein_loss(torch.ones_like(fake_labels), fake_labels)
+    return loss_real + loss_fake, loss_real, loss_fake
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+class TrainerBase:
+    """Variant-independent machinery. Subclasses define `variant`, build the nets and translate the
+    reference's argument orders into the engine's (genes, patches, patch_pad, text, text_pad)."""
+
+    variant = "paper"
+    clip_d: Optional[float] = None
+    clip_g: Optional[float] = None
+
+    # ---- construction -------------------------------------------------------------------
+    def _init_common(self, input_dims, latent_dims, generator_dims, discriminator_dims, negative_slope, is_bn,
+                     lr_d, lr_g, optimizer, gp_weight, p_aug, norm_scale, train, n_critic, freq_print,
+                     freq_compute_test, freq_visualize_test, patience, normalization, log2, rpm, results_dire):
+        self.input_dims = input_dims
+        self.latent_dims = latent_dims
+        self.generator_dims = generator_dims
+        self.discriminator_dims = discriminator_dims
+        self.negative_slope = negative_slope
+        self.is_bn = is_bn
+        self.gp_weight = gp_weight
+        self.isTrain = train
+        self.p_aug = p_aug
+        self.norm_scale = norm_scale
+        self.n_genes = input_dims
+        self.n_critic = n_critic
+        self.freq_print = freq_print
+        self.freq_compute_test = freq_compute_test
+        self.freq_visualize_test = freq_visualize_test
+        self.result_dire = self.results_dire = results_dire
+        if results_dire:
+            os.makedirs(results_dire, exist_ok=True)
+            self.results_dire_fig = os.path.join(results_dire, "figures")
+            os.makedirs(self.results_dire_fig, exist_ok=True)
+        self.dend = False
+        self.lr_d, self.lr_g = lr_d, lr_g
+        self.optimizer = optimizer
+        self.patience = patience
+        if p_aug != 0:
+            # the reference's p_aug branch reads an undefined variable (:401) and cannot run
+            raise NotImplementedError("p_aug != 0 is dead code in the reference (NameError at :401)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("gemmgan_b200 needs a CUDA device of compute capability 10.x (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.loss_dict = {"d loss": [], "d real loss": [], "d fake loss": [], "g loss": []}
+        self.corr_scores, self.corr_dend_scores = {}, {}
+        self.precision_scores, self.recall_scores = {}, {}
+        self.normalization, self.log2, self.rpm = normalization, log2, rpm
+        self.dropout_p = 0.1          # nn.TransformerEncoderLayer(dropout=0.1) in the reference towers
+        self.dropout_seed = 0
+        self.gemm_impl = _lib.IMPL_TCGEN05
+        self.dp_global_noise = False   # draw z/alpha for the GLOBAL batch and slice (N-rank == 1-rank parity)
+        self._engines = {}
+        self._flat_gen = self._flat_disc = None
+        self._pinned = None
+        self._events = {}
+        self._noise_gen = None
+
+    def init_train(self):
+        opt = self.optimizer.lower()
+        if opt == "rms_prop":
+            mk = lambda ps, lr: torch.optim.RMSprop(ps, lr=lr)
+        elif opt == "adam":
+            mk = lambda ps, lr: torch.optim.Adam(ps, lr=lr, betas=(0.9, 0.99))
+        elif opt == "adamw":
+            mk = lambda ps, lr: torch.optim.AdamW(ps, lr=lr, betas=(0.9, 0.99), weight_decay=0.01)
+        else:
+            raise ValueError(f"unknown optimizer {self.optimizer!r}")
+        self.optimizer_disc = mk(self.disc.parameters(), self.lr_d)
+        self.optimizer_gen = mk(self.gen.parameters(), self.lr_g)
+        # the update itself is the engine's kernel; optimizer state lives in the flat buffers
+        self._flatten()
+
+    def _attach(self, gen, disc):
+        self.gen, self.disc = gen.to(self.device), disc.to(self.device)
+        self.gen._gg_owner = self
+        self.disc._gg_owner = self
+
+    def _flatten(self):
+        if self._flat_gen is None:
+            opt = self.optimizer.lower()
+            self._flat_gen = FlatNet(self.gen, self.device, opt)
+            self._flat_disc = FlatNet(self.disc, self.device, opt)
+            self._engines.clear()
+
+    def _shape_cfg(self):
+        raise NotImplementedError
+
+    def _engine(self, B: int) -> Engine:
+        """Engines are per batch size (fixed buffers); they all share the flat parameter buffers."""
+        self._flatten()
+        eng = self._engines.get(B)
+        if eng is None:
+            s = self._shape_cfg()
+            eng = Engine(variant=self.variant, B=B, G=self.n_genes, L=self.latent_dims, gen=self._flat_gen,
+                         disc=self._flat_disc, slope=float(self.negative_slope), dropout_p=float(self.dropout_p),
+                         gp_weight=float(self.gp_weight), clip_d=float(self.clip_d or 0.0),
+                         clip_g=float(self.clip_g or 0.0), optimizer=self.optimizer.lower(),
+                         seed=int(self.dropout_seed), gemm_impl=self.gemm_impl, device=self.device, **s)
+            self._engines[B] = eng
+        else:
+            eng.sync_external_param_writes()
+        return eng
+
+    # ---- noise --------------------------------------------------------------------------
+    def _normal(self, B):
+        d = _dist()
+        if d is not None and self.dp_global_noise:
+            w, r = d.get_world_size(), d.get_rank()
+            z = torch.normal(0, 1, size=(w * B, self.latent_dims), device=self.device)
+            return z[r * B:(r + 1) * B].contiguous()
+        return torch.normal(0, 1, size=(B, self.latent_dims), device=self.device)
+
+    def _alpha(self, B):
+        d = _dist()
+        if d is not None and self.dp_global_noise:
+            w, r = d.get_world_size(), d.get_rank()
+            a = torch.rand(w * B, 1, device=self.device)
+            return a[r * B:(r + 1) * B].contiguous()
+        return torch.rand(B, 1, device=self.device)
+
+    # ---- stats readback -----------------------------------------------------------------
+    def _snapshot(self, eng: Engine, key: str):
+        if self._pinned is None:
+            self._pinned = {k: torch.zeros(A.STATS_COUNT, dtype=torch.float32).pin_memory() for k in ("d", "g")}
+        self._pinned[key].copy_(eng.stats, non_blocking=True)
+        ev = self._events.get(key)
+        if ev is None:
+            ev = self._events[key] = torch.cuda.Event()
+        ev.record()
+
+    def _stats(self, key: str) -> np.ndarray:
+        ev = self._events.get(key)
+        if ev is None:
+            raise AttributeError("no training step has run yet")
+        ev.synchronize()
+        return self._pinned[key].numpy()
+
+    @property
+    def d_batch_loss(self):
+        s = self._stats("d")
+        return np.array([float(s[A.STAT_LOSS_REAL] + s[A.STAT_LOSS_FAKE]), float(s[A.STAT_LOSS_REAL]),
+                         float(s[A.STAT_LOSS_FAKE])])
+
+    @property
+    def g_batch_loss(self):
+        return np.array([float(self._stats("g")[A.STAT_G_LOSS])])
+
+    @property
+    def disc_loss(self):
+        return torch.tensor(float(self._stats("d")[A.STAT_D_LOSS]))
+
+    @property
+    def gen_loss(self):
+        return torch.tensor(float(self._stats("g")[A.STAT_G_LOSS]))
+
+    @property
+    def last_gp(self):
+        return float(self._stats("d")[A.STAT_GP])
+
+    # ---- the hot path -------------------------------------------------------------------
+    def _allreduce(self, flat: FlatNet):
+        d = _dist()
+        if d is not None:
+            d.all_reduce(flat.grads, op=d.ReduceOp.AVG)
+
+    def _lr(self, opt):
+        return opt.param_groups[0]["lr"]
+
+    def _train_disc_staged(self, eng: Engine, z, alpha=None):
+        """train_disc (:376-423) on the batch already staged in the engine."""
+        self.disc.train()
+        self._flat_disc.reattach_grads()
+        if alpha is None:
+            alpha = self._alpha(eng.B)
+        eng.disc_grads(z, alpha, training=True)
+        self._allreduce(self._flat_disc)
+        eng.optim_step(A.NET_DISC, self._lr(self.optimizer_disc))
+        self._snapshot(eng, "d")
+
+    def _train_gen_staged(self, eng: Engine, z):
+        """train_gen (:425-461) on the batch already staged in the engine."""
+        self.gen.train()
+        self._flat_gen.reattach_grads()
+        for w in self.disc.parameters():  # observable side effect of the reference (:433-434)
+            w.requires_grad = False
+        for w in self.gen.parameters():
+            w.requires_grad = True
+        eng.gen_grads(z, training=True)
+        self._allreduce(self._flat_gen)
+        eng.optim_step(A.NET_GEN, self._lr(self.optimizer_gen))
+        self._snapshot(eng, "g")
+
+    def _train_staged(self, eng: Engine, zs=None, alphas=None):
+        for i in range(self.n_critic):
+            z = zs[i] if zs is not None else self._normal(eng.B)
+            self._train_disc_staged(eng, z, None if alphas is None else alphas[i])
+        z = zs[self.n_critic] if zs is not None else self._normal(eng.B)
+        self._train_gen_staged(eng, z)
+
+    def set_requires_grad(self, nets, requires_grad=False):
+        if not isinstance(nets, list):
+            nets = [nets]
+        for net in nets:
+            if net is not None:
+                for param in net.parameters():
+                    param.requires_grad = requires_grad
+
+    def print_best_epoch(self, d, name="correlation"):
+        idx = np.argmax(list(d.values()))
+        print("Best epoch " + name + ":", list(d.keys())[idx], "score:", list(d.values())[idx])
+
+    def _epoch_lr_decay(self, epoch, every):
+        if epoch > 0 and epoch % every == 0:
+            for opt in (self.optimizer_disc, self.optimizer_gen):
+                for g in opt.param_groups:
+                    g["lr"] *= 0.5

@@ -111,6 +111,123 @@ typedef struct gg_gemm_desc {
 
 int gg_gemm_bf16(const gg_gemm_desc* desc, void* stream);
 
+/* -------------------------------------------------------- training engine --
+ * One engine = one (generator, critic) pair of one model variant at a fixed per-rank batch
+ * size. It executes the bodies of WGAN_GP.train_disc / train_gen / generate_samples
+ * (src/conditional_gan_cross_attention_with_film.py:376-461, :601-608; film variant
+ * conditional_gan_film.py:347-430; vanilla vanilla_gan_unconditional.py:329-418) as a fixed
+ * sequence of kernels with a hand-written backward and double-backward (no autograd replay).
+ *
+ * Parameters, gradients and optimizer state stay in caller-owned flat fp32 buffers (the
+ * PyTorch nn.Parameters are views into them); `off[slot]` locates each tensor, in the
+ * reference's native [out, in] layout. All activations live in one caller-owned workspace.
+ */
+#define GG_VARIANT_VANILLA 0 /* vanilla_gan_unconditional.py: trunk only                      */
+#define GG_VARIANT_FILM 1    /* conditional_gan_film.py: FiLM + encoder (no bias), CLS vector */
+#define GG_VARIANT_PAPER 2   /* conditional_gan_cross_attention_with_film.py (paper model)    */
+
+#define GG_OPT_RMSPROP 0
+#define GG_OPT_ADAM 1
+#define GG_OPT_ADAMW 2
+
+enum gg_param_slot {
+  GG_P_FILM_W = 0, GG_P_FILM_B, GG_P_TEXT_W, GG_P_TEXT_B, GG_P_PATCH_W, GG_P_PATCH_B, GG_P_CLS,
+  /* encoder layer l: GG_P_LAYER0 + 12*l + {IN_W, IN_B, OUT_W, OUT_B, FF1_W, FF1_B, FF2_W, FF2_B,
+   *                                        N1_W, N1_B, N2_W, N2_B} */
+  GG_P_LAYER0 = 7,
+  GG_P_P2T_IN_W = GG_P_LAYER0 + 24, GG_P_P2T_IN_B, GG_P_P2T_OUT_W, GG_P_P2T_OUT_B,
+  GG_P_T2P_IN_W, GG_P_T2P_IN_B, GG_P_T2P_OUT_W, GG_P_T2P_OUT_B,
+  GG_P_TR0_W, GG_P_TR0_B, GG_P_TR1_W, GG_P_TR1_B, GG_P_FIN_W, GG_P_FIN_B,
+  GG_NSLOTS
+};
+enum gg_layer_slot {
+  GG_L_IN_W = 0, GG_L_IN_B, GG_L_OUT_W, GG_L_OUT_B, GG_L_FF1_W, GG_L_FF1_B, GG_L_FF2_W, GG_L_FF2_B,
+  GG_L_N1_W, GG_L_N1_B, GG_L_N2_W, GG_L_N2_B, GG_L_COUNT
+};
+
+typedef struct gg_model_cfg {
+  int32_t variant;
+  int32_t B;              /* per-rank batch */
+  int32_t G, L, E, H;     /* genes, latent, embedding, trunk hidden width */
+  int32_t Dt, Dp;         /* text / patch feature widths (768 / 1024) */
+  int32_t P, T;           /* patch tokens, text tokens (film: T = 1, text is [B, Dt]) */
+  int32_t n_layers, n_heads, ffn;
+  int32_t tower_bias;     /* 1: encoder layers carry biases (paper), 0: bias=False (film) */
+  float slope;            /* LeakyReLU negative slope of the trunk (scripts use 0.0) */
+  float dropout_p;        /* encoder dropout in train mode (reference: 0.1) */
+  float gp_weight;        /* 10 */
+  float clip_d, clip_g;   /* clip_grad_norm_ max norms; <= 0 disables (:414, :457) */
+  float ln_eps;           /* 1e-5 */
+  int32_t optimizer;      /* GG_OPT_* */
+  int32_t gemm_impl;      /* GG_IMPL_TCGEN05, or GG_IMPL_SIMT_F32 for the check path */
+  uint64_t seed;          /* dropout stream seed */
+} gg_model_cfg;
+
+typedef struct gg_net_buffers {
+  float* params;          /* flat fp32, 16-byte aligned */
+  float* grads;
+  float* exp_avg;         /* Adam/AdamW first moment; NULL for RMSprop */
+  float* exp_avg_sq;      /* second moment / RMSprop square_avg */
+  float* step_count;      /* device float[1]: optimizer steps taken (Adam bias correction) */
+  int64_t n_used;         /* [0, n_used) are trained; never-used tensors (the prototype encoder
+                             layer, :114) sit behind and are left untouched like in the reference */
+  int64_t off[GG_NSLOTS]; /* element offsets, -1 = tensor absent in this variant */
+} gg_net_buffers;
+
+#define GG_NET_GEN 0
+#define GG_NET_DISC 1
+
+/* device-resident results, float[GG_STATS_COUNT] (gg_engine_stats) */
+#define GG_STAT_LOSS_REAL 0  /* -mean D(real)                         (:407, :41-46) */
+#define GG_STAT_LOSS_FAKE 1  /*  mean D(fake)                                        */
+#define GG_STAT_GP 2         /*  mean (||grad||-1)^2                  (:372-374)     */
+#define GG_STAT_D_LOSS 3     /*  loss_real + loss_fake + gp_weight*gp (:409)         */
+#define GG_STAT_G_LOSS 4     /* -mean D(G(z))                         (:452)         */
+#define GG_STAT_D_GRAD_NORM 5
+#define GG_STAT_D_CLIP_COEF 6
+#define GG_STAT_G_GRAD_NORM 7
+#define GG_STAT_G_CLIP_COEF 8
+#define GG_STATS_COUNT 16
+
+typedef struct gg_engine gg_engine;
+
+int gg_engine_workspace_bytes(const gg_model_cfg* cfg, int64_t* bytes);
+int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* gen, const gg_net_buffers* disc,
+                     void* workspace, int64_t workspace_bytes, void* stream, gg_engine** out);
+void gg_engine_destroy(gg_engine* e);
+/* fp32 master weights -> bf16 shadows (call after any external change of `params`). */
+int gg_engine_refresh_shadows(gg_engine* e, int net, void* stream);
+/* Stages one batch (the dataloader tuple, already on the device, fp32 / uint8 masks):
+ * casts to bf16 once per train() call (:465-469). Unused pointers may be NULL per variant. */
+int gg_engine_set_batch(gg_engine* e, const float* genes, const float* patches, const uint8_t* patch_pad,
+                        const float* text, const uint8_t* text_pad, void* stream);
+/* train_disc minus optimizer: fills critic grads + stats. z [B,L], alpha [B,1] fp32. training=1
+ * uses dropout_p (three independently-dropped critic tower passes, as the reference). */
+int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream);
+/* train_gen minus optimizer: fills generator grads + stats. */
+int gg_engine_gen_grads(gg_engine* e, const float* z, int training, void* stream);
+/* clip_grad_norm_ (if configured) + optimizer.step() on the flat buffers + shadow refresh.
+ * In data-parallel runs the caller all-reduces `grads` between *_grads and this call. */
+int gg_engine_optim_step(gg_engine* e, int net, float lr, void* stream);
+/* generator forward only: out_f32 [B, G] (generate_samples :601-608; training=0 = eval mode). */
+int gg_engine_generate(gg_engine* e, const float* z, float* out_f32, int training, void* stream);
+/* critic forward only on `genes_f32` [B, G] with the staged conditioning: score_f32 [B]. */
+int gg_engine_critic(gg_engine* e, const float* genes_f32, float* score_f32, int training, void* stream);
+/* WGAN_GP.gradient_penalty (:351-374) on caller-provided real / fake [B, G] fp32 (real may be NULL =
+ * the staged batch): gp_out[0] (device) = mean_b (||dD/dx_hat||_2 - 1)^2. */
+int gg_engine_gradient_penalty(gg_engine* e, const float* real_f32, const float* fake_f32, const float* alpha,
+                               int training, float* gp_out, void* stream);
+float* gg_engine_stats(gg_engine* e);
+/* named internal device buffers for tests ("fake_bf16", "score", "gp_norms", "cond_disc", ...);
+ * returns NULL for unknown names. rows/cols/ld (elements) are optional outputs. */
+void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows, int64_t* cols, int64_t* ld,
+                       int32_t* is_f32);
+
+/* ----------------------------------------------------- standalone kernels --
+ * Exposed for unit tests and micro-benchmarks; the engine calls the same code. */
+int gg_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, float lr, float max_norm,
+                  float* step_count, float* norm_out2, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

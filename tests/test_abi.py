@@ -1,0 +1,61 @@
+"""CPU-side checks of the C-ABI library: it builds/loads and exports every symbol include/gemmgan.h declares
+(no compute calls — there is no GPU in the build container)."""
+import ctypes as C
+import os
+import re
+
+from gemmgan_b200 import _abi_decl, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "gemmgan.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = declared_functions()
+    assert "gg_gemm_bf16" in names and "gg_engine_disc_grads" in names
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in gemmgan.h but not exported"
+    assert set(_abi_decl.EXPORTS) <= set(names)
+    assert L.gg_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """ctypes mirrors vs. the real C layout: compile a probe against include/gemmgan.h with gcc."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("gcc not available")
+    src = tmp_path / "probe.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "gemmgan.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %d\\n", sizeof(gg_epilogue), sizeof(gg_gemm_seg),'
+        'sizeof(gg_gemm_desc), sizeof(gg_net_buffers), sizeof(gg_model_cfg), offsetof(gg_gemm_desc, epi),'
+        'offsetof(gg_net_buffers, off), (int)GG_NSLOTS);return 0;}\n')
+    exe = tmp_path / "probe"
+    subprocess.check_call([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert vals == [C.sizeof(_lib.Epilogue), C.sizeof(_lib.GemmSeg), C.sizeof(_lib.GemmDesc),
+                    C.sizeof(_abi_decl.NetBuffers), C.sizeof(_abi_decl.ModelCfg), _lib.GemmDesc.epi.offset,
+                    _abi_decl.NetBuffers.off.offset, _abi_decl.NSLOTS]
+
+
+def test_no_cpu_fallback_in_product_path():
+    """The product package must not import the oracle or run torch math as a fallback."""
+    pkg = os.path.join(ROOT, "gemmgan_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            text = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in text and "from oracle" not in text, fn
+    for fn in ("vanilla_gan_unconditional.py", "conditional_gan_film.py",
+               "conditional_gan_cross_attention_with_film.py"):
+        text = open(os.path.join(ROOT, fn)).read()
+        assert "oracle" not in text.replace("oracle/", ""), fn

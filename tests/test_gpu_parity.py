@@ -1,0 +1,245 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the drop-in classes and
+the C ABI, against the CPU oracle (oracle/restated.py) on the same seeded inputs, and against the golden
+vectors produced by the unmodified reference (tests/golden, oracle/make_golden.py).
+
+Tolerances (stated per SURVEY.md §8c): GEMM/attention paths use bf16 operands with fp32 accumulation, the
+oracle is fp32 ⇒ |Δ| <= 2e-2 * max|ref| on generator output, critic scores and gradients, GP rel 2e-2;
+fp32-only kernels (optimizer, clip, reductions) rel 1e-5. Dropout is off on both sides for exact runs
+(its random stream cannot match torch's); with dropout on only statistical properties are asserted.
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from oracle import restated
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-2
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+def build_pair(variant, cfg, optimizer="adam", slope=0.0, seed=11, dropout=0.0):
+    """(oracle on CPU, drop-in trainer on GPU) with identical initial weights."""
+    torch.manual_seed(seed)
+    o = restated.OracleWGANGP(variant, cfg["G"], latent=cfg["latent"], embed=cfg["embed"], hidden=cfg["hidden"],
+                              optimizer=optimizer, negative_slope=slope, dropout=0.0, text_dim=cfg["text_dim"],
+                              patch_dim=cfg["patch_dim"])
+    torch.manual_seed(seed)
+    H, G = cfg["hidden"], cfg["G"]
+    if variant == "vanilla":
+        mod = importlib.import_module("vanilla_gan_unconditional")
+        t = mod.WGAN_GP_nocond(input_dims=G, latent_dims=cfg["latent"], vocab_sizes=[], generator_dims=[H, H, G],
+                               discriminator_dims=[H, H, 1], optimizer=optimizer, negative_slope=slope)
+        t.build_WGAN_GP_nocond()
+    else:
+        mod = importlib.import_module({"paper": "conditional_gan_cross_attention_with_film",
+                                       "film": "conditional_gan_film"}[variant])
+        t = mod.WGAN_GP(input_dims=G, latent_dims=cfg["latent"], embedding_dims=cfg["embed"],
+                        generator_dims=[H, H, G], discriminator_dims=[H, H, 1], optimizer=optimizer,
+                        negative_slope=slope, text_embedding_dims=cfg["text_dim"],
+                        patches_embedding_dims=cfg["patch_dim"])
+        t.build_WGAN_GP()
+    t.dropout_p = dropout
+    t.init_train()
+    for (k1, v1), (k2, v2) in zip(o.gen.state_dict().items(), t.gen.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2.cpu()), k1
+    for (k1, v1), (k2, v2) in zip(o.disc.state_dict().items(), t.disc.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2.cpu()), k1
+    return o, t
+
+
+def ref_order(variant, x, cond):
+    """oracle cond tuple -> drop-in train()/train_disc() argument tuples (reference orders)."""
+    if variant == "paper":
+        patches, ppad, text, tpad = cond
+        return (text, tpad, patches, ppad)
+    if variant == "film":
+        text, patches, ppad = cond
+        return (text, patches, ppad)
+    return ()
+
+
+SMALL = dict(B=8, G=203, P=5, T=3, embed=32, hidden=32, latent=16, text_dim=24, patch_dim=32)
+MID = dict(B=64, G=1000, P=8, T=2, embed=256, hidden=256, latent=256, text_dim=768, patch_dim=1024)
+
+
+@pytest.mark.parametrize("variant,cfg,slope", [
+    ("vanilla", SMALL, 0.0), ("vanilla", MID, 0.2), ("paper", SMALL, 0.0), ("paper", MID, 0.0),
+    ("film", SMALL, 0.0), ("film", MID, 0.0)])
+def test_critic_step_matches_oracle(variant, cfg, slope):
+    o, t = build_pair(variant, cfg, "adam", slope)
+    B, G, L = cfg["B"], cfg["G"], cfg["latent"]
+    x, cond = restated.synthetic_batch(variant, B, G, cfg["P"], cfg["T"], seed=5, ragged=True,
+                                       text_dim=cfg["text_dim"], patch_dim=cfg["patch_dim"])
+    g = torch.Generator().manual_seed(99)
+    z = torch.randn(B, L, generator=g)
+    alpha = torch.rand(B, 1, generator=g)
+    o.train_disc(x, z, cond, alpha)
+    dev = t.device
+    t.train_disc(x.to(dev), z.to(dev), *[c.to(dev) for c in ref_order(variant, x, cond)], alpha=alpha.to(dev))
+    eng = t._engine(B)
+    torch.cuda.synchronize()
+    assert rel(eng.buffer("fake_bf16"), o.last["fake"]) < TOL
+    score = eng.buffer("score")[:, 0]
+    assert rel(score[:B], o.last["d_fake"][:, 0]) < TOL
+    assert rel(score[B:2 * B], o.last["d_true"][:, 0]) < TOL
+    assert rel(eng.buffer("gp_norms")[:, 0], o.last["grad_norm"]) < TOL
+    assert abs(t.last_gp - o.last["gp"].item()) <= TOL * max(abs(o.last["gp"].item()), 1e-3)
+    np.testing.assert_allclose(t.d_batch_loss, o.d_batch_loss, rtol=TOL, atol=TOL * 0.05)
+    # gradients (after clipping in the paper model), parameter by parameter
+    for (k, po), (_, pt) in zip(o.disc.named_parameters(), t.disc.named_parameters()):
+        if po.grad is None:
+            assert pt.grad is None, k
+            continue
+        scale = max(po.grad.abs().max().item(), 1e-6)
+        err = (pt.grad.cpu() - po.grad).abs().max().item()
+        assert err <= 4e-2 * scale + 1e-7, (k, err, scale)
+    # generator untouched by the critic step
+    for (k, po), (_, pt) in zip(o.gen.named_parameters(), t.gen.named_parameters()):
+        assert torch.equal(po.detach(), pt.detach().cpu()), k
+
+
+@pytest.mark.parametrize("variant,cfg", [("vanilla", SMALL), ("paper", SMALL), ("film", SMALL), ("paper", MID)])
+def test_generator_step_matches_oracle(variant, cfg):
+    o, t = build_pair(variant, cfg, "adam")
+    B, G, L = cfg["B"], cfg["G"], cfg["latent"]
+    x, cond = restated.synthetic_batch(variant, B, G, cfg["P"], cfg["T"], seed=6, ragged=True,
+                                       text_dim=cfg["text_dim"], patch_dim=cfg["patch_dim"])
+    z = torch.randn(B, L, generator=torch.Generator().manual_seed(3))
+    o.train_gen(z, cond)
+    dev = t.device
+    t.train_gen(z.to(dev), *[c.to(dev) for c in ref_order(variant, x, cond)])
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(t.g_batch_loss, o.g_batch_loss, rtol=TOL, atol=TOL * 0.05)
+    for (k, po), (_, pt) in zip(o.gen.named_parameters(), t.gen.named_parameters()):
+        if po.grad is None:
+            assert pt.grad is None, k
+            continue
+        scale = max(po.grad.abs().max().item(), 1e-6)
+        err = (pt.grad.cpu() - po.grad).abs().max().item()
+        assert err <= 4e-2 * scale + 1e-7, (k, err, scale)
+    # side effect of the reference: critic params are left frozen (:433-434), and not updated
+    assert all(not p.requires_grad for p in t.disc.parameters())
+    for (k, po), (_, pt) in zip(o.disc.named_parameters(), t.disc.named_parameters()):
+        assert torch.equal(po.detach(), pt.detach().cpu()), k
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "small" in n])
+def test_against_reference_golden(name):
+    """The CUDA path replays the recorded noise of a reference run and must reproduce its numbers."""
+    fx = load_golden(name)
+    cfg, variant = fx["cfg"], fx["variant"]
+    o, t = build_pair(variant, cfg, fx["optimizer"], fx["negative_slope"], seed=fx["init_seed"])
+    dev = t.device
+    x, cond, zs, alphas = fx["x"], fx["cond"], fx["zs"], fx["alphas"]
+    args = [c.to(dev) for c in ref_order(variant, x, cond)]
+    nc = t.n_critic
+    B = cfg["B"]
+    # first critic step against the recorded internals
+    t.train_disc(x.to(dev), zs[0].to(dev), *args, alpha=alphas[0].to(dev))
+    eng = t._engine(B)
+    torch.cuda.synchronize()
+    assert rel(eng.buffer("fake_bf16"), fx["step0"]["fake"]) < TOL
+    assert rel(eng.buffer("score")[:B, 0], fx["step0"]["d_fake"][:, 0]) < TOL
+    assert rel(eng.buffer("score")[B:2 * B, 0], fx["step0"]["d_true"][:, 0]) < TOL
+    np.testing.assert_allclose(t.d_batch_loss, fx["after_disc0"]["d_batch_loss"].numpy(), rtol=TOL, atol=1e-3)
+    if fx["after_disc0"]["grads"] is not None:
+        for k, pt in t.disc.named_parameters():
+            gref = fx["after_disc0"]["grads"][k]
+            if gref is None:
+                assert pt.grad is None, k
+                continue
+            scale = max(gref.abs().max().item(), 1e-6)
+            assert (pt.grad.cpu() - gref).abs().max().item() <= 4e-2 * scale + 1e-7, k
+    # finish the first train() call, then the remaining ones, and compare the loss curves
+    for i in range(1, nc):
+        t.train_disc(x.to(dev), zs[i].to(dev), *args, alpha=alphas[i].to(dev))
+    t.train_gen(zs[nc].to(dev), *args)
+    d_curve, g_curve = [t.d_batch_loss], [t.g_batch_loss]
+    for call in range(1, fx["n_calls"]):
+        zc = [z.to(dev) for z in zs[call * (nc + 1):(call + 1) * (nc + 1)]]
+        ac = [a.to(dev) for a in alphas[call * nc:(call + 1) * nc]]
+        if variant == "vanilla":
+            t.train(x.to(dev), zs=zc, alphas=ac)
+        else:
+            t.train(x.to(dev), *args, zs=zc, alphas=ac)
+        d_curve.append(t.d_batch_loss)
+        g_curve.append(t.g_batch_loss)
+    d_ref, g_ref = fx["curves"]["d"].numpy(), fx["curves"]["g"].numpy()
+    rms = fx["optimizer"] == "rms_prop"
+    for call in range(fx["n_calls"]):
+        # loss values are O(0.1-10); RMSprop's sign-like steps amplify rounding after the first call
+        tol = (0.05 if call == 0 else 0.35) if rms else 0.05
+        scale = max(np.abs(d_ref[call]).max(), 0.05)
+        assert np.abs(d_curve[call] - d_ref[call]).max() <= tol * scale + 2e-3, (call, d_curve[call], d_ref[call])
+        scale = max(np.abs(g_ref[call]).max(), 0.05)
+        assert np.abs(g_curve[call] - g_ref[call]).max() <= tol * scale + 2e-3, (call, g_curve[call], g_ref[call])
+
+
+@pytest.mark.parametrize("kind,name", [(0, "rms_prop"), (1, "adam"), (2, "adamw")])
+@pytest.mark.parametrize("clip", [0.0, 0.5])
+def test_optimizer_kernel_matches_torch(kind, name, clip):
+    import ctypes as C
+    from gemmgan_b200 import _lib
+
+    L = _lib.lib()
+    n = 100003
+    g0 = torch.Generator(device="cuda").manual_seed(1)
+    p = torch.randn(n, device="cuda", generator=g0)
+    pr = p.clone().requires_grad_(True)
+    opt = {"rms_prop": lambda: torch.optim.RMSprop([pr], lr=5e-4),
+           "adam": lambda: torch.optim.Adam([pr], lr=5e-4, betas=(0.9, 0.99)),
+           "adamw": lambda: torch.optim.AdamW([pr], lr=5e-4, betas=(0.9, 0.99), weight_decay=0.01)}[name]()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(4, device="cuda")
+    norm = torch.zeros(2, device="cuda")
+    scratch = torch.zeros(1024, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for it in range(5):
+        g = torch.randn(n, device="cuda", generator=g0) * (10.0 ** (it - 3))
+        pr.grad = g.clone()
+        if clip > 0:
+            torch.nn.utils.clip_grad_norm_([pr], clip)
+        opt.step()
+        gk = g.clone()
+        _lib.check(L.gg_optim_step(kind, p.data_ptr(), gk.data_ptr(), m.data_ptr(), v.data_ptr(), n, 5e-4, clip,
+                                   step.data_ptr(), norm.data_ptr(), scratch.data_ptr(), st))
+        torch.cuda.synchronize()
+        if clip > 0:
+            assert abs(norm[0].item() - g.norm().item()) <= 1e-5 * g.norm().item()
+            torch.testing.assert_close(gk, pr.grad, rtol=1e-5, atol=1e-9)
+        torch.testing.assert_close(p, pr.detach(), rtol=2e-5, atol=2e-7)
+
+
+def test_dropout_statistics_and_determinism():
+    """With dropout on (reference default p=0.1) the step must be reproducible for a fixed seed and close,
+    in expectation, to the dropout-free step."""
+    cfg = MID
+    _, t = build_pair("paper", cfg, "adam", dropout=0.1)
+    B, G, L = cfg["B"], cfg["G"], cfg["latent"]
+    x, cond = restated.synthetic_batch("paper", B, G, cfg["P"], cfg["T"], seed=5, text_dim=768, patch_dim=1024)
+    dev = t.device
+    args = [c.to(dev) for c in ref_order("paper", x, cond)]
+    g = torch.Generator().manual_seed(1)
+    z, alpha = torch.randn(B, L, generator=g).to(dev), torch.rand(B, 1, generator=g).to(dev)
+    eng = t._stage(x.to(dev), *args)
+    eng.disc_grads(z, alpha, training=True)
+    torch.cuda.synchronize()
+    c_drop = eng.buffer("cond_disc").float().clone()
+    g1 = t._flat_disc.grads.clone()
+    assert torch.isfinite(g1).all() and torch.isfinite(c_drop).all()
+    # three independently dropped passes really differ
+    assert (c_drop[:B] - c_drop[B:2 * B]).abs().max() > 1e-4
+    # dropout-free conditioning is close to the mean behaviour
+    eng.disc_grads(z, alpha, training=False)
+    torch.cuda.synchronize()
+    c_eval = eng.buffer("cond_disc").float()[:B]
+    assert (c_drop[:B] - c_eval).abs().mean() < 0.5 * c_eval.abs().mean() + 1e-3
