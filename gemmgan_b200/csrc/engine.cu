@@ -906,6 +906,16 @@ extern "C" void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows,
   else if (s == "h2f") { p = e->tb.h2f; r = 3 * c.B; cc = c.H; l = c.H; f = 1; }
   else if (s == "gram") { p = e->tb.Mg; r = c.H; cc = c.H; l = c.H; f = 1; }
   else if (s == "dfake") { p = e->tb.dfake; r = c.B; cc = c.G; l = e->Gp; }
+  else if (s == "da1") { p = e->tb.da1; r = 2 * c.B; cc = c.H; l = c.H; }
+  else if (s == "da2") { p = e->tb.da2; r = 2 * c.B; cc = c.H; l = c.H; }
+  else if (s == "u2") { p = e->tb.u2; r = c.B; cc = c.H; l = c.H; }
+  else if (s == "u1f") { p = e->tb.u1f; r = c.B; cc = c.H; l = c.H; f = 1; }
+  else if (s == "y") { p = e->tb.y; r = c.B; cc = c.H; l = c.H; f = 1; }
+  else if (s == "dv1") { p = e->tb.dv1; r = c.B; cc = c.H; l = c.H; }
+  else if (s == "ru1") { p = e->tb.ru1; r = c.B; cc = c.H; l = c.H; }
+  else if (s == "Qb") { p = e->tb.Qb; r = c.H; cc = c.H; l = c.H; }
+  else if (s == "a1x") { p = e->tb.a1x; r = 2 * c.B; cc = c.H; l = c.H; f = 1; }
+  else if (s == "h2") { p = e->tb.h2; r = 3 * c.B; cc = c.H; l = c.H; }
   else if (e->cond && (s == "cond_gen" || s == "cond_disc")) {
     const int net = s == "cond_gen" ? GG_NET_GEN : GG_NET_DISC;
     const Op cv = cond_vec(*e, net);

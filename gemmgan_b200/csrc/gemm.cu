@@ -316,7 +316,8 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
   GG_REQUIRE(d->M > 0 && d->N > 0, "bad GEMM shape M=%d N=%d", d->M, d->N);
   GG_REQUIRE(d->nseg == 1 || d->nseg == 2, "nseg must be 1 or 2");
   for (int s = 0; s < d->nseg; ++s)
-    GG_REQUIRE(d->seg[s].K > 0 && d->seg[s].a && d->seg[s].b, "bad GEMM segment %d", s);
+    GG_REQUIRE(d->seg[s].K > 0 && d->seg[s].a && d->seg[s].b, "bad GEMM segment %d (M=%d N=%d K=%d a=%p b=%p)", s,
+               d->M, d->N, d->seg[s].K, d->seg[s].a, d->seg[s].b);
   GG_REQUIRE(d->epi.out_bf16 || d->epi.out_f32, "GEMM has no output");
   GG_REQUIRE(d->epi.drop_p == 0.f || d->epi.rng, "dropout needs an rng state pointer");
 
