@@ -89,8 +89,9 @@ class WGAN_GP(TrainerBase):
         dev = self.device
         B = patches.shape[0]
         eng = self._engine_for(B, patches, text_token)
-        eng.set_batch(genes=None if genes is None else genes.to(dev), patches=patches.to(dev),
-                      patch_pad=padding_mask.to(dev), text=text_token.to(dev), text_pad=text_token_padding.to(dev))
+        eng.set_batch(genes=None if genes is None else genes.to(dev, non_blocking=True), patches=patches.to(dev, non_blocking=True),
+                      patch_pad=padding_mask.to(dev, non_blocking=True), text=text_token.to(dev, non_blocking=True),
+                      text_pad=text_token_padding.to(dev, non_blocking=True))
         return eng
 
     # ---- reference-signature entry points -------------------------------------------------

@@ -79,8 +79,9 @@ class WGAN_GP(TrainerBase):
             self._tokens = patches.shape[1]
             self._engines.clear()
         eng = self._engine(patches.shape[0])
-        eng.set_batch(genes=None if genes is None else genes.to(dev), patches=patches.to(dev),
-                      patch_pad=padding_mask.to(dev), text=text_embedding.to(dev), text_pad=None)
+        eng.set_batch(genes=None if genes is None else genes.to(dev, non_blocking=True), patches=patches.to(dev, non_blocking=True),
+                      patch_pad=padding_mask.to(dev, non_blocking=True), text=text_embedding.to(dev, non_blocking=True),
+                      text_pad=None)
         return eng
 
     # ---- reference-signature entry points -------------------------------------------------

@@ -6,6 +6,7 @@
 namespace gg {
 
 static thread_local char g_err[512] = "";
+std::atomic<long long> g_launch_count{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -19,6 +20,10 @@ void set_error(const char* fmt, ...) {
 extern "C" const char* gg_last_error(void) { return gg::g_err; }
 
 extern "C" int gg_abi_version(void) { return GG_ABI_VERSION; }
+
+extern "C" long long gg_launch_count(int reset) {
+  return reset ? gg::g_launch_count.exchange(0) : gg::g_launch_count.load();
+}
 
 extern "C" int gg_check_device(int dev) {
   cudaDeviceProp prop;

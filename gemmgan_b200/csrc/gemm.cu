@@ -20,6 +20,7 @@
 #include "ptx.cuh"
 
 #include <mutex>
+#include <vector>
 
 namespace gg {
 
@@ -294,6 +295,16 @@ static int encode_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t 
   return GG_OK;
 }
 
+// Optional live profiler: CUDA-event pairs around every tcgen05 GEMM launch (bench.py roofline leg).
+struct GemmProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // start/stop pairs
+  size_t used = 0;
+  double flops = 0.0;
+  long long launches = 0;
+};
+static GemmProfile g_prof;
+
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = TileCfg<BN, STAGES>;
@@ -305,9 +316,26 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
   });
   GG_CUDA_CHECK(attr_err);
   dim3 grid(ceil_div(args.N, BN), ceil_div(args.M, BM), args.splits);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on) {
+    if (g_prof.used + 2 > g_prof.ev.size()) {
+      cudaEvent_t a, b;
+      GG_CUDA_CHECK(cudaEventCreate(&a));
+      GG_CUDA_CHECK(cudaEventCreate(&b));
+      g_prof.ev.push_back(a);
+      g_prof.ev.push_back(b);
+    }
+    e0 = g_prof.ev[g_prof.used];
+    e1 = g_prof.ev[g_prof.used + 1];
+    g_prof.used += 2;
+    g_prof.flops += 2.0 * args.M * args.N * (static_cast<double>(args.K0) + args.K1);
+    g_prof.launches += 1;
+    GG_CUDA_CHECK(cudaEventRecord(e0, stream));
+  }
   gemm_tc_kernel<BN, STAGES><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
                                                                      maps[3], args);
   GG_LAUNCH_CHECK();
+  if (e1) GG_CUDA_CHECK(cudaEventRecord(e1, stream));
   return GG_OK;
 }
 
@@ -405,6 +433,31 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
 }
 
 }  // namespace gg
+
+extern "C" int gg_gemm_profile_begin(void) {
+  gg::g_prof.on = true;
+  gg::g_prof.used = 0;
+  gg::g_prof.flops = 0.0;
+  gg::g_prof.launches = 0;
+  return GG_OK;
+}
+// Synchronises the device and returns the summed duration (ms), FLOPs (2*M*N*K) and count of the
+// tcgen05 GEMM launches issued since gg_gemm_profile_begin().
+extern "C" int gg_gemm_profile_end(double* ms, double* flops, long long* launches) {
+  using namespace gg;
+  g_prof.on = false;
+  GG_CUDA_CHECK(cudaDeviceSynchronize());
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    float t = 0.f;
+    GG_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (flops) *flops = g_prof.flops;
+  if (launches) *launches = g_prof.launches;
+  return GG_OK;
+}
 
 extern "C" int gg_gemm_bf16(const gg_gemm_desc* desc, void* stream) {
   return gg::gemm_dispatch(desc, reinterpret_cast<cudaStream_t>(stream));

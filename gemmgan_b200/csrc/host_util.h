@@ -6,9 +6,12 @@
 
 #include "../../include/gemmgan.h"
 
+#include <atomic>
+
 namespace gg {
 
 void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launch_count;  // kernels launched by this library (all streams)
 
 #define GG_CUDA_CHECK(expr)                                                                \
   do {                                                                                     \
@@ -22,6 +25,7 @@ void set_error(const char* fmt, ...);
 
 #define GG_LAUNCH_CHECK()                                                                  \
   do {                                                                                     \
+    gg::g_launch_count.fetch_add(1, std::memory_order_relaxed);                            \
     cudaError_t _e = cudaGetLastError();                                                   \
     if (_e != cudaSuccess) {                                                               \
       gg::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__,  \

@@ -110,6 +110,11 @@ typedef struct gg_gemm_desc {
 } gg_gemm_desc;
 
 int gg_gemm_bf16(const gg_gemm_desc* desc, void* stream);
+/* Measurement hooks (bench.py): kernels launched by the library so far; CUDA-event timing of every
+ * tcgen05 GEMM launch between begin/end (summed ms, 2*M*N*K FLOPs, launch count). */
+long long gg_launch_count(int reset);
+int gg_gemm_profile_begin(void);
+int gg_gemm_profile_end(double* ms, double* flops, long long* launches);
 
 /* -------------------------------------------------------- training engine --
  * One engine = one (generator, critic) pair of one model variant at a fixed per-rank batch

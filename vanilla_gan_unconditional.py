@@ -86,7 +86,7 @@ class WGAN_GP_nocond(TrainerBase):
         self._train_gen_staged(eng, z.to(self.device))
 
     def train(self, x_GE, zs=None, alphas=None):
-        x_real = x_GE.to(self.device)
+        x_real = x_GE.to(self.device, non_blocking=True)
         eng = self._engine(x_real.shape[0])
         eng.set_batch(genes=x_real)
         self._train_staged(eng, zs, alphas)
