@@ -183,7 +183,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = dict(workload=f"{args.workload}: {w['desc']}", per_gpu_batch=w["B"], genes=w["G"], patch_tokens=w["P"],
                text_tokens=w["T"], optimizer=args.optimizer, n_critic=5, dropout=0.1,
-               parallelism=f"dp{world}", l2="flushed between timed steps (512 MB write)")
+               parallelism=f"dp{world}", l2="flushed between timed steps (512 MB write)",
+               cuda_graphs=os.environ.get("GEMMGAN_CUDA_GRAPHS", "1") != "0")
 
     if args.impl == "reference":
         if rank != 0:
@@ -243,10 +244,14 @@ def main():
     losses = dict(d=[float(v) for v in t.d_batch_loss], g=float(t.g_batch_loss[0]))
 
     # ---- live GEMM roofline leg: CUDA events around every tcgen05 GEMM launch of one more train() call
+    graphs_on, t.use_cuda_graphs = t.use_cuda_graphs, False   # events need real launches, not a graph replay
+    t.train(*batch_dev)
+    torch.cuda.synchronize()
     L.gg_gemm_profile_begin()
     t.train(*batch_dev)
     ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
     _lib.check(L.gg_gemm_profile_end(C.byref(ms), C.byref(fl), C.byref(nl)))
+    t.use_cuda_graphs = graphs_on
     achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
     roofline = dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s",
                     frac=achieved / pk["tflops"], traffic=None, kernel="gemm_tc_kernel (tcgen05, all launches of one train())",

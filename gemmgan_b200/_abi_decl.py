@@ -66,6 +66,8 @@ def declare(L: C.CDLL) -> None:
     L.gg_optim_step.argtypes = [i32, vp, vp, vp, vp, i64, f32, f32, vp, vp, vp, vp]
     L.gg_launch_count.argtypes = [i32]
     L.gg_launch_count.restype = C.c_longlong
+    L.gg_launch_count_add.argtypes = [C.c_longlong]
+    L.gg_launch_count_add.restype = None
     L.gg_gemm_profile_begin.argtypes = []
     L.gg_gemm_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
 
@@ -75,5 +77,5 @@ EXPORTS = [
     "gg_engine_create", "gg_engine_destroy", "gg_engine_refresh_shadows", "gg_engine_set_batch",
     "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_optim_step", "gg_engine_generate",
     "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
-    "gg_launch_count", "gg_gemm_profile_begin", "gg_gemm_profile_end",
+    "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end",
 ]

@@ -21,6 +21,10 @@ extern "C" const char* gg_last_error(void) { return gg::g_err; }
 
 extern "C" int gg_abi_version(void) { return GG_ABI_VERSION; }
 
+// kernels replayed through a captured CUDA graph are added by the host runtime (it knows how many
+// launches each captured graph holds)
+extern "C" void gg_launch_count_add(long long n) { gg::g_launch_count.fetch_add(n); }
+
 extern "C" long long gg_launch_count(int reset) {
   return reset ? gg::g_launch_count.exchange(0) : gg::g_launch_count.load();
 }

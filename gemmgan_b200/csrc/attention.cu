@@ -260,6 +260,217 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_kernel(const Att
   }
 }
 
+// ------------------------------------------------------------------ short sequences (Lk <= 16)
+// Four threads per row, each owning hd/4 head dims; scores live in registers. A warp covers 8 rows, a CTA 32:
+// at S = 9 (8 patch tokens + CLS) this keeps every lane busy, where one-CTA-per-(row, head) would idle.
+constexpr int SM_MAXL = 16;
+
+template <int DPT>
+__device__ __forceinline__ void ld_slice(const bf16* p, float* v) {
+#pragma unroll
+  for (int d = 0; d < DPT; d += 2) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + d));
+    v[d] = f.x;
+    v[d + 1] = f.y;
+  }
+}
+template <int DPT>
+__device__ __forceinline__ void st_slice(bf16* p, const float* v, float scale) {
+#pragma unroll
+  for (int d = 0; d < DPT; d += 2)
+    *reinterpret_cast<__nv_bfloat162*>(p + d) = __floats2bfloat162_rn(v[d] * scale, v[d + 1] * scale);
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// MODE 0: forward (writes o). MODE 1: backward pass A (writes dq, lse, delta).
+template <int DPT, int MODE>
+__global__ void __launch_bounds__(128) attn_small_q_kernel(const AttnArgs a, float* __restrict__ stat) {
+  const int hd = a.hd, Lk = a.Lk, Lq = a.Lq;
+  const int64_t total = static_cast<int64_t>(a.nb) * a.H * Lq;
+  int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 2;
+  const int part = threadIdx.x & 3;
+  const bool valid = r < total;
+  if (!valid) r = total - 1;
+  const int i = static_cast<int>(r % Lq);
+  const int h = static_cast<int>((r / Lq) % a.H);
+  const int b = static_cast<int>(r / (static_cast<int64_t>(Lq) * a.H));
+  const int col = h * hd + part * DPT;
+  const float scale = rsqrtf(static_cast<float>(hd));
+  float q[DPT], g[DPT], acc[DPT];
+  ld_slice<DPT>(a.q + (static_cast<int64_t>(b % a.q_mod) * Lq + i) * a.ldq + col, q);
+  if (MODE == 1) ld_slice<DPT>(a.dout + (static_cast<int64_t>(b) * Lq + i) * a.lddo + col, g);
+#pragma unroll
+  for (int d = 0; d < DPT; ++d) acc[d] = 0.f;
+  const bf16* kbase = a.k + static_cast<int64_t>(b % a.kv_mod) * Lk * a.ldkv + col;
+  const bf16* vbase = a.v + static_cast<int64_t>(b % a.kv_mod) * Lk * a.ldkv + col;
+  const uint8_t* mk = a.mask ? a.mask + static_cast<int64_t>(b % a.mask_mod) * Lk : nullptr;
+  uint64_t seed = 0, step = 0;
+  if (a.drop_p > 0.f) {
+    seed = a.rng[0];
+    step = a.rng[1];
+  }
+  const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  const uint64_t pbase = ((static_cast<uint64_t>(b) * a.H + h) * Lq + i) * static_cast<uint64_t>(Lk);
+  float s[SM_MAXL], dp[SM_MAXL];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < SM_MAXL; ++j) {
+    s[j] = -INFINITY;
+    dp[j] = 0.f;
+    if (j < Lk) {
+      float kk[DPT];
+      ld_slice<DPT>(kbase + static_cast<int64_t>(j) * a.ldkv, kk);
+      float t = 0.f;
+#pragma unroll
+      for (int d = 0; d < DPT; ++d) t = fmaf(q[d], kk[d], t);
+      t = quad_sum(t) * scale;
+      if (!(mk && mk[j])) s[j] = t;
+      m = fmaxf(m, s[j]);
+    }
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < SM_MAXL; ++j) {
+    s[j] = (s[j] == -INFINITY) ? 0.f : __expf(s[j] - m);
+    l += s[j];
+  }
+  const float inv_l = l > 0.f ? 1.f / l : 0.f;
+  float delta = 0.f;
+#pragma unroll
+  for (int j = 0; j < SM_MAXL; ++j) {
+    if (j < Lk) {
+      s[j] *= inv_l;  // p_ij
+      const bool keep = a.drop_p > 0.f ? dropout_keep(seed, step, a.site, pbase + j, a.drop_p) : true;
+      float vv[DPT];
+      ld_slice<DPT>(vbase + static_cast<int64_t>(j) * a.ldkv, vv);
+      if (MODE == 0) {
+        const float pd = keep ? s[j] * keep_scale : 0.f;
+#pragma unroll
+        for (int d = 0; d < DPT; ++d) acc[d] = fmaf(pd, vv[d], acc[d]);
+      } else {
+        float t = 0.f;
+#pragma unroll
+        for (int d = 0; d < DPT; ++d) t = fmaf(g[d], vv[d], t);
+        t = quad_sum(t);
+        dp[j] = keep ? t * keep_scale : 0.f;
+        delta = fmaf(s[j], dp[j], delta);
+      }
+    }
+  }
+  if (MODE == 0) {
+    if (valid) st_slice<DPT>(a.o + (static_cast<int64_t>(b) * Lq + i) * a.ldo + col, acc, 1.f);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < SM_MAXL; ++j) {
+    if (j < Lk) {
+      const float ds = s[j] * (dp[j] - delta);
+      float kk[DPT];
+      ld_slice<DPT>(kbase + static_cast<int64_t>(j) * a.ldkv, kk);
+#pragma unroll
+      for (int d = 0; d < DPT; ++d) acc[d] = fmaf(ds, kk[d], acc[d]);
+    }
+  }
+  if (valid) {
+    st_slice<DPT>(a.dq + (static_cast<int64_t>(b) * Lq + i) * a.lddq + col, acc, scale);
+    if (part == 0) {
+      stat[2 * r] = l > 0.f ? m + __logf(l) : INFINITY;
+      stat[2 * r + 1] = delta;
+    }
+  }
+}
+
+// backward pass B: one thread quad per key row -> dK, dV (sums over the queries; deterministic)
+template <int DPT>
+__global__ void __launch_bounds__(128) attn_small_kv_kernel(const AttnArgs a, const float* __restrict__ stat) {
+  const int hd = a.hd, Lk = a.Lk, Lq = a.Lq;
+  const int64_t total = static_cast<int64_t>(a.nb) * a.H * Lk;
+  int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 2;
+  const int part = threadIdx.x & 3;
+  const bool valid = r < total;
+  if (!valid) r = total - 1;
+  const int j = static_cast<int>(r % Lk);
+  const int h = static_cast<int>((r / Lk) % a.H);
+  const int b = static_cast<int>(r / (static_cast<int64_t>(Lk) * a.H));
+  const int col = h * hd + part * DPT;
+  const float scale = rsqrtf(static_cast<float>(hd));
+  float kk[DPT], vv[DPT], dk[DPT], dv[DPT];
+  const int64_t kvrow = static_cast<int64_t>(b % a.kv_mod) * Lk + j;
+  ld_slice<DPT>(a.k + kvrow * a.ldkv + col, kk);
+  ld_slice<DPT>(a.v + kvrow * a.ldkv + col, vv);
+#pragma unroll
+  for (int d = 0; d < DPT; ++d) dk[d] = dv[d] = 0.f;
+  const bool masked = a.mask && a.mask[static_cast<int64_t>(b % a.mask_mod) * Lk + j];
+  uint64_t seed = 0, step = 0;
+  if (a.drop_p > 0.f) {
+    seed = a.rng[0];
+    step = a.rng[1];
+  }
+  const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  const bf16* qbase = a.q + static_cast<int64_t>(b % a.q_mod) * Lq * a.ldq + col;
+  const bf16* gbase = a.dout + static_cast<int64_t>(b) * Lq * a.lddo + col;
+  const int64_t srow = (static_cast<int64_t>(b) * a.H + h) * Lq;
+  for (int i = 0; i < Lq; ++i) {
+    float q[DPT], g[DPT];
+    ld_slice<DPT>(qbase + static_cast<int64_t>(i) * a.ldq, q);
+    ld_slice<DPT>(gbase + static_cast<int64_t>(i) * a.lddo, g);
+    float t = 0.f, u = 0.f;
+#pragma unroll
+    for (int d = 0; d < DPT; ++d) {
+      t = fmaf(q[d], kk[d], t);
+      u = fmaf(g[d], vv[d], u);
+    }
+    t = quad_sum(t) * scale;
+    u = quad_sum(u);
+    const float p = masked ? 0.f : __expf(t - stat[2 * (srow + i)]);
+    const bool keep = a.drop_p > 0.f
+                          ? dropout_keep(seed, step, a.site, static_cast<uint64_t>(srow + i) * Lk + j, a.drop_p)
+                          : true;
+    const float pd = keep ? p * keep_scale : 0.f;
+    const float ds = p * ((keep ? u * keep_scale : 0.f) - stat[2 * (srow + i) + 1]);
+#pragma unroll
+    for (int d = 0; d < DPT; ++d) {
+      dk[d] = fmaf(ds, q[d], dk[d]);
+      dv[d] = fmaf(pd, g[d], dv[d]);
+    }
+  }
+  if (valid) {
+    const int64_t orow = static_cast<int64_t>(b) * Lk + j;
+    st_slice<DPT>(a.dk + orow * a.lddkv + col, dk, scale);
+    st_slice<DPT>(a.dv + orow * a.lddkv + col, dv, 1.f);
+  }
+}
+
+static bool small_path(const AttnArgs& a) {
+  const int dpt = a.hd / 4;
+  return a.Lk <= SM_MAXL && a.hd % 8 == 0 && (dpt == 2 || dpt == 4 || dpt == 8 || dpt == 16);
+}
+template <int MODE>
+static void launch_small_q(const AttnArgs& a, float* stat, cudaStream_t st) {
+  const int64_t threads = static_cast<int64_t>(a.nb) * a.H * a.Lq * 4;
+  const unsigned grid = static_cast<unsigned>((threads + 127) / 128);
+  switch (a.hd / 4) {
+    case 2: attn_small_q_kernel<2, MODE><<<grid, 128, 0, st>>>(a, stat); break;
+    case 4: attn_small_q_kernel<4, MODE><<<grid, 128, 0, st>>>(a, stat); break;
+    case 8: attn_small_q_kernel<8, MODE><<<grid, 128, 0, st>>>(a, stat); break;
+    default: attn_small_q_kernel<16, MODE><<<grid, 128, 0, st>>>(a, stat); break;
+  }
+}
+static void launch_small_kv(const AttnArgs& a, const float* stat, cudaStream_t st) {
+  const int64_t threads = static_cast<int64_t>(a.nb) * a.H * a.Lk * 4;
+  const unsigned grid = static_cast<unsigned>((threads + 127) / 128);
+  switch (a.hd / 4) {
+    case 2: attn_small_kv_kernel<2><<<grid, 128, 0, st>>>(a, stat); break;
+    case 4: attn_small_kv_kernel<4><<<grid, 128, 0, st>>>(a, stat); break;
+    case 8: attn_small_kv_kernel<8><<<grid, 128, 0, st>>>(a, stat); break;
+    default: attn_small_kv_kernel<16><<<grid, 128, 0, st>>>(a, stat); break;
+  }
+}
+
 static int check_args(const AttnArgs& a) {
   GG_REQUIRE(a.hd >= 2 && a.hd <= 64 && a.hd % 2 == 0, "attention head_dim %d unsupported (even, <= 64)", a.hd);
   GG_REQUIRE(a.Lk >= 1 && a.Lk <= 32 * ATT_MAXC && a.Lq >= 1 && a.Lq <= 32 * ATT_MAXC,
@@ -271,6 +482,11 @@ static int check_args(const AttnArgs& a) {
 int k_attention_fwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_args(a);
   if (rc) return rc;
+  if (small_path(a)) {
+    launch_small_q<0>(a, nullptr, st);
+    GG_LAUNCH_CHECK();
+    return GG_OK;
+  }
   const int pitch = a.hd + 2;
   const size_t smem = (static_cast<size_t>(2 * a.Lk * pitch + ((a.Lq * pitch + 1) & ~1))) * 2 +
                       static_cast<size_t>(ATT_WARPS) * a.Lk * 4 + 16;
@@ -288,6 +504,14 @@ int k_attention_fwd(const AttnArgs& a, cudaStream_t st) {
 int k_attention_bwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_args(a);
   if (rc) return rc;
+  if (small_path(a)) {
+    GG_REQUIRE(a.stat != nullptr, "short-sequence attention backward needs a stats scratch buffer");
+    launch_small_q<1>(a, a.stat, st);
+    GG_LAUNCH_CHECK();
+    launch_small_kv(a, a.stat, st);
+    GG_LAUNCH_CHECK();
+    return GG_OK;
+  }
   const int pitch = a.hd + 2;
   const int Lmax = a.Lk > a.Lq ? a.Lk : a.Lq;
   const size_t smem = (static_cast<size_t>(2 * a.Lk * pitch + a.Lq * pitch + ((a.Lq * pitch + 1) & ~1))) * 2 +

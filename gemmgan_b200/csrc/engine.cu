@@ -118,7 +118,7 @@ struct gg_engine {
   Tower tw[2];
   GradScratch gs;
   TrunkBufs tb;
-  float *scratch, *stats, *opt_step[2], *normbuf;
+  float *scratch, *stats, *opt_step[2], *normbuf, *attn_stat;
   uint64_t* rng;
   void* splitk;
   int64_t splitk_bytes = 0;
@@ -275,6 +275,10 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
     e.text = ar.take<bf16>(B * T * c.Dt);
     e.mask_s = ar.take<uint8_t>(B * S);
     e.tpad = ar.take<uint8_t>(B * T);
+    {
+      const int64_t lmax = S > T ? S : T;
+      e.attn_stat = ar.take<float>(2 * 3 * B * c.n_heads * lmax);
+    }
     layout_tower(e, e.tw[GG_NET_GEN], 1, ar);
     layout_tower(e, e.tw[GG_NET_DISC], c.dropout_p > 0.f ? 3 : 1, ar);
     GradScratch& g = e.gs;
@@ -487,6 +491,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     a.nb = n; a.H = c.n_heads; a.hd = e.hd; a.Lq = 1; a.Lk = T;
     a.dout = g.dat; a.lddo = E; a.dq = g.dqt; a.lddq = E;
     a.dk = g.dkvt; a.dv = g.dkvt + E; a.lddkv = 2 * E;
+    a.stat = e.attn_stat;
     GG_TRY(k_attention_bwd(a, st));
     // qt = pv Wq_t^T + bq_t ; dp = dqt Wq_t + dc (residual path)
     GG_TRY(e.wgrad(st, E, E, n, Op{g.dqt, E}, Op{t.pv, E}, gWt, E));
@@ -512,6 +517,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     a.nb = n; a.H = c.n_heads; a.hd = e.hd; a.Lq = 1; a.Lk = S;
     a.dout = g.dap; a.lddo = E; a.dq = g.dqp; a.lddq = E;
     a.dk = g.dkvp; a.dv = g.dkvp + E; a.lddkv = 2 * E;
+    a.stat = e.attn_stat;
     GG_TRY(k_attention_bwd(a, st));
     // qp = te[:,0] Wq_p^T + bq_p (shared by the replicas)
     const bf16* dqp = g.dqp;
@@ -566,6 +572,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     a.drop_p = p; a.rng = e.rng; a.site = site + 0;
     a.dout = g.gao; a.lddo = E; a.dq = g.gqkv; a.lddq = 3 * E;
     a.dk = g.gqkv + E; a.dv = g.gqkv + 2 * E; a.lddkv = 3 * E;
+    a.stat = e.attn_stat;
     GG_TRY(k_attention_bwd(a, st));
     GG_TRY(e.wgrad(st, 3 * E, E, rows, Op{g.gqkv, 3 * E}, Op{t.X[l], E}, e.Gr(net, ls + GG_L_IN_W), E));
     GG_TRY(e.bgrad(st, g.gqkv, 3 * E, rows, 3 * E, e.Gr(net, ls + GG_L_IN_B)));

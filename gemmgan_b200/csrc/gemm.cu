@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(192)
               if (j < ncols) p[j] = v[j];
           }
         } else {
-          epilogue_chunk(g.epi, g.N, m, nc0, ncols, v);
+          epilogue_chunk<32>(g.epi, g.N, m, nc0, ncols, v);
         }
       }
     }
@@ -191,25 +191,42 @@ __global__ void __launch_bounds__(192)
   if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
-// Sums split-K partials in split order (deterministic) and applies the epilogue.
+// Sums split-K partials in split order (deterministic) and applies the epilogue. One thread per 4
+// consecutive columns: a warp reads / writes 512 contiguous bytes per split.
 __global__ void __launch_bounds__(256)
     splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
                          const gg_epilogue epi) {
-  const int chunks = (N + 31) / 32;
+  const int chunks = (N + 3) / 4;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(M) * chunks) return;
   const int m = static_cast<int>(idx / chunks);
-  const int nc0 = static_cast<int>(idx % chunks) * 32;
-  const int ncols = min(32, N - nc0);
-  float v[32], t[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = 0.f;
-  for (int z = 0; z < splits; ++z) {
-    load_row_chunk(partial + static_cast<int64_t>(z) * M * N, 1, N, m, nc0, ncols, t);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += t[j];
+  const int nc0 = static_cast<int>(idx % chunks) * 4;
+  const int ncols = min(4, N - nc0);
+  const int64_t stride = static_cast<int64_t>(M) * N;
+  const float* p = partial + static_cast<int64_t>(m) * N + nc0;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ncols == 4 && ((reinterpret_cast<uintptr_t>(p) | (static_cast<uintptr_t>(stride) * 4)) & 15) == 0) {
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {  // 4 independent 16-byte loads in flight
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(p + (z + 0) * stride));
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(p + (z + 1) * stride));
+      const float4 c = __ldcs(reinterpret_cast<const float4*>(p + (z + 2) * stride));
+      const float4 d = __ldcs(reinterpret_cast<const float4*>(p + (z + 3) * stride));
+      v[0] = (((v[0] + a.x) + b.x) + c.x) + d.x;
+      v[1] = (((v[1] + a.y) + b.y) + c.y) + d.y;
+      v[2] = (((v[2] + a.z) + b.z) + c.z) + d.z;
+      v[3] = (((v[3] + a.w) + b.w) + c.w) + d.w;
+    }
+    for (; z < splits; ++z) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(p + z * stride));
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    }
+  } else {
+    for (int z = 0; z < splits; ++z)
+      for (int j = 0; j < 4; ++j)
+        if (j < ncols) v[j] += p[z * stride + j];
   }
-  epilogue_chunk(epi, N, m, nc0, ncols, v);
+  epilogue_chunk<4>(epi, N, m, nc0, ncols, v);
 }
 
 // CUDA-core fp32 check path on the same bf16 operands and the same epilogue (tests only).
@@ -245,7 +262,7 @@ __global__ void __launch_bounds__(128)
       }
     }
   }
-  epilogue_chunk(epi, N, m, nc0, ncols, v);
+  epilogue_chunk<32>(epi, N, m, nc0, ncols, v);
 }
 
 // ------------------------------------------------------------------ host side
@@ -424,7 +441,7 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
   if (rc) return rc;
 
   if (splits > 1) {
-    const int64_t work = static_cast<int64_t>(d->M) * ceil_div(d->N, 32);
+    const int64_t work = static_cast<int64_t>(d->M) * ceil_div(d->N, 4);
     splitk_reduce_kernel<<<static_cast<unsigned>((work + 255) / 256), 256, 0, stream>>>(
         args.partial, splits, d->M, d->N, d->epi);
     GG_LAUNCH_CHECK();

@@ -85,6 +85,7 @@ struct AttnArgs {
   const bf16* dout; int64_t lddo;            // [nb*Lq, H*hd]
   bf16* dq; int64_t lddq;                    // [nb*Lq, H*hd]   (per replica even if q is shared)
   bf16* dk; bf16* dv; int64_t lddkv;         // [nb*Lk, ...]    (per replica even if kv is shared)
+  float* stat;                               // backward scratch: 2 * nb * H * Lq floats (lse, delta)
 };
 int k_attention_fwd(const AttnArgs& a, cudaStream_t st);
 int k_attention_bwd(const AttnArgs& a, cudaStream_t st);

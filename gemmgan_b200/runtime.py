@@ -141,6 +141,10 @@ class Engine:
         sp = self.lib.gg_engine_stats(self.handle)
         self.stats = self._view(sp, A.STATS_COUNT, torch.float32)
         self._keep = None
+        # fixed-address noise inputs so that a captured CUDA graph of the step can be replayed
+        self.z_in = torch.empty(B, L, device=self.device, dtype=torch.float32)
+        self.alpha_in = torch.empty(B, 1, device=self.device, dtype=torch.float32)
+        self.graphs, self.warmed = {}, set()
 
     def __del__(self):
         try:

@@ -99,6 +99,7 @@ class TrainerBase:
         self.dropout_seed = 0
         self.gemm_impl = _lib.IMPL_TCGEN05
         self.dp_global_noise = False   # draw z/alpha for the GLOBAL batch and slice (N-rank == 1-rank parity)
+        self.use_cuda_graphs = os.environ.get("GEMMGAN_CUDA_GRAPHS", "1") != "0"
         self._engines = {}
         self._flat_gen = self._flat_disc = None
         self._pinned = None
@@ -216,15 +217,50 @@ class TrainerBase:
     def _lr(self, opt):
         return opt.param_groups[0]["lr"]
 
+    def _replay(self, eng: Engine, key, body):
+        """Runs `body` (which only enqueues library kernels on the current stream). With
+        use_cuda_graphs the kernel sequence is captured once per key and replayed afterwards: the
+        step is ~200 short kernels, so launch latency would otherwise dominate.
+        The first call per engine runs eagerly (one-time lazy initialisation inside the library)."""
+        if not self.use_cuda_graphs:
+            body()
+            return
+        g = eng.graphs.get(key)
+        if g is None:
+            if key[0] not in eng.warmed:
+                eng.warmed.add(key[0])
+                body()
+                return
+            g = torch.cuda.CUDAGraph()
+            n0 = eng.lib.gg_launch_count(0)
+            with torch.cuda.graph(g):
+                body()
+            n_kernels = eng.lib.gg_launch_count(0) - n0
+            eng.lib.gg_launch_count_add(-n_kernels)     # capture enqueues nothing
+            g = eng.graphs[key] = (g, n_kernels)
+        g[0].replay()
+        eng.lib.gg_launch_count_add(g[1])
+
+    def _step(self, eng: Engine, tag, net, flat, lr, grads_fn):
+        lr = float(lr)
+        if _dist() is None:
+            def body():
+                grads_fn()
+                eng.optim_step(net, lr)
+            self._replay(eng, (tag, lr), body)
+        else:  # the gradient all-reduce sits between the backward and the optimizer kernel
+            self._replay(eng, (tag + "_grads",), grads_fn)
+            self._allreduce(flat)
+            self._replay(eng, (tag + "_optim", lr), lambda: eng.optim_step(net, lr))
+
     def _train_disc_staged(self, eng: Engine, z, alpha=None):
         """train_disc (:376-423) on the batch already staged in the engine."""
         self.disc.train()
         self._flat_disc.reattach_grads()
-        if alpha is None:
-            alpha = self._alpha(eng.B)
-        eng.disc_grads(z, alpha, training=True)
-        self._allreduce(self._flat_disc)
-        eng.optim_step(A.NET_DISC, self._lr(self.optimizer_disc))
+        eng.z_in.copy_(z, non_blocking=True)
+        eng.alpha_in.copy_(self._alpha(eng.B) if alpha is None else alpha.reshape(eng.B, 1), non_blocking=True)
+        self._step(eng, "d", A.NET_DISC, self._flat_disc, self._lr(self.optimizer_disc),
+                   lambda: eng.disc_grads(eng.z_in, eng.alpha_in, training=True))
         self._snapshot(eng, "d")
 
     def _train_gen_staged(self, eng: Engine, z):
@@ -235,9 +271,9 @@ class TrainerBase:
             w.requires_grad = False
         for w in self.gen.parameters():
             w.requires_grad = True
-        eng.gen_grads(z, training=True)
-        self._allreduce(self._flat_gen)
-        eng.optim_step(A.NET_GEN, self._lr(self.optimizer_gen))
+        eng.z_in.copy_(z, non_blocking=True)
+        self._step(eng, "g", A.NET_GEN, self._flat_gen, self._lr(self.optimizer_gen),
+                   lambda: eng.gen_grads(eng.z_in, training=True))
         self._snapshot(eng, "g")
 
     def _train_staged(self, eng: Engine, zs=None, alphas=None):

@@ -113,6 +113,7 @@ int gg_gemm_bf16(const gg_gemm_desc* desc, void* stream);
 /* Measurement hooks (bench.py): kernels launched by the library so far; CUDA-event timing of every
  * tcgen05 GEMM launch between begin/end (summed ms, 2*M*N*K FLOPs, launch count). */
 long long gg_launch_count(int reset);
+void gg_launch_count_add(long long n); /* a replayed CUDA graph adds the launches it contains */
 int gg_gemm_profile_begin(void);
 int gg_gemm_profile_end(double* ms, double* flops, long long* launches);
 
