@@ -38,16 +38,36 @@ struct GemmArgs {
   gg_epilogue epi;
 };
 
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+
 template <int BN, int STAGES>
 struct TileCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+  // epilogue: each of the 8 warps owns 32 rows x SPAN columns of the tile and stages SW columns at a
+  // time through padded shared memory (pitch SW+4 floats: conflict-free 16-byte writes and reads)
+  static constexpr int SPAN = BN / 2;
+  static constexpr int SW = SPAN < 64 ? SPAN : 64;
+  static constexpr int PASSES = SPAN / SW;
+  static constexpr int SPITCH = SW + 4;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * SPITCH * 4;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;  // full/empty per stage + tmem full/empty x 2
+  static constexpr int SMEM_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;         // two accumulator stages
 };
 
+// Persistent: CTA c processes work items c, c + gridDim.x, ... where a work item is one
+// (split, m-tile, n-tile) with the n-tile fastest (CTAs running side by side share the A rows in L2).
+// The fp32 accumulator is double-buffered in tensor memory: while the epilogue warps drain stage a,
+// the MMA warp already accumulates the next tile into stage a^1, and the TMA ring keeps running across
+// tile boundaries. Epilogue = two phases per warp: (1) tcgen05.ld (thread = row) -> shared memory,
+// release the TMEM stage; (2) thread = 4 consecutive columns, rows in turn: every global load
+// (mask / residual) and store is a contiguous >= 128-byte row segment per warp instruction.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                    const GemmArgs g) {
@@ -56,18 +76,18 @@ __global__ void __launch_bounds__(192)
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
   uint64_t* empty = full + STAGES;
-  uint64_t* accum_full = empty + STAGES;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* tmem_full = empty + STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM;
-  const int n0 = blockIdx.x * BN;
   const int kb0 = (g.K0 + BK - 1) / BK;
   const int kb1 = (g.K1 + BK - 1) / BK;
   const int total_kb = kb0 + kb1;
-  const int kb_begin = static_cast<int>(static_cast<int64_t>(total_kb) * blockIdx.z / g.splits);
-  const int kb_end = static_cast<int>(static_cast<int64_t>(total_kb) * (blockIdx.z + 1) / g.splits);
+  const int tiles_n = (g.N + BN - 1) / BN;
+  const int tiles_m = (g.M + BM - 1) / BM;
+  const int64_t total_work = static_cast<int64_t>(tiles_n) * tiles_m * g.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -80,11 +100,14 @@ __global__ void __launch_bounds__(192)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], EPI_WARPS);  // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_holder, BN);
+    tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -96,32 +119,40 @@ __global__ void __launch_bounds__(192)
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty[s], ph ^ 1);
-        const bool second = kb >= kb0;
-        const int kloc = (second ? kb - kb0 : kb) * BK;
-        const CUtensorMap* ma = second ? &tmA1 : &tmA0;
-        const CUtensorMap* mb = second ? &tmB1 : &tmB0;
-        uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_TILE_BYTES;
-        mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        if (!g.a_mn) {
-          tma_load_2d(a_dst, ma, &full[s], kloc, m0);
-        } else {
+      for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tn = static_cast<int>(w % tiles_n);
+        const int tm = static_cast<int>((w / tiles_n) % tiles_m);
+        const int z = static_cast<int>(w / (static_cast<int64_t>(tiles_n) * tiles_m));
+        const int m0 = tm * BM, n0 = tn * BN;
+        const int kb_begin = static_cast<int>(static_cast<int64_t>(total_kb) * z / g.splits);
+        const int kb_end = static_cast<int>(static_cast<int64_t>(total_kb) * (z + 1) / g.splits);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          const bool second = kb >= kb0;
+          const int kloc = (second ? kb - kb0 : kb) * BK;
+          const CUtensorMap* ma = second ? &tmA1 : &tmA0;
+          const CUtensorMap* mb = second ? &tmB1 : &tmB0;
+          uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          if (!g.a_mn) {
+            tma_load_2d(a_dst, ma, &full[s], kloc, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j)
-            tma_load_2d(a_dst + j * ATOM_BYTES, ma, &full[s], m0 + 64 * j, kloc);
-        }
-        if (!g.b_mn) {
-          tma_load_2d(b_dst, mb, &full[s], kloc, n0);
-        } else {
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(a_dst + j * ATOM_BYTES, ma, &full[s], m0 + 64 * j, kloc);
+          }
+          if (!g.b_mn) {
+            tma_load_2d(b_dst, mb, &full[s], kloc, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(b_dst + j * ATOM_BYTES, mb, &full[s], n0 + 64 * j, kloc);
-        }
-        if (++s == STAGES) {
-          s = 0;
-          ph ^= 1;
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b_dst + j * ATOM_BYTES, mb, &full[s], n0 + 64 * j, kloc);
+          }
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
     }
@@ -130,65 +161,106 @@ __global__ void __launch_bounds__(192)
       const uint32_t idesc = make_idesc_bf16(BM, BN, g.a_mn, g.b_mn);
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full[s], ph);
+      int it = 0;
+      for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        const int z = static_cast<int>(w / (static_cast<int64_t>(tiles_n) * tiles_m));
+        const int kb_begin = static_cast<int>(static_cast<int64_t>(total_kb) * z / g.splits);
+        const int kb_end = static_cast<int>(static_cast<int64_t>(total_kb) * (z + 1) / g.splits);
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this stage
         tc_fence_after_sync();
-        const uint32_t a_base = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t b_base = a_base + A_TILE_BYTES;
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_base = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + A_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major: 16 bf16 of K = 32 bytes inside the 128 B swizzle row.
-          // MN-major: 16 k-rows of 128 B = 2048 bytes; 64-wide MN atoms are ATOM_BYTES apart.
-          const uint64_t ad = g.a_mn ? make_smem_desc(a_base + k * 2048, ATOM_BYTES, 1024)
-                                     : make_smem_desc(a_base + k * 32, 16, 1024);
-          const uint64_t bd = g.b_mn ? make_smem_desc(b_base + k * 2048, ATOM_BYTES, 1024)
-                                     : make_smem_desc(b_base + k * 32, 16, 1024);
-          tc_mma_bf16(tmem_base, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 bf16 of K = 32 bytes inside the 128 B swizzle row.
+            // MN-major: 16 k-rows of 128 B = 2048 bytes; 64-wide MN atoms are ATOM_BYTES apart.
+            const uint64_t ad = g.a_mn ? make_smem_desc(a_base + k * 2048, ATOM_BYTES, 1024)
+                                       : make_smem_desc(a_base + k * 32, 16, 1024);
+            const uint64_t bd = g.b_mn ? make_smem_desc(b_base + k * 2048, ATOM_BYTES, 1024)
+                                       : make_smem_desc(b_base + k * 32, 16, 1024);
+            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
-        tc_commit(&empty[s]);
-        if (++s == STAGES) {
-          s = 0;
-          ph ^= 1;
-        }
+        tc_commit(&tmem_full[acc]);
       }
-      tc_commit(accum_full);
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    mbar_wait(accum_full, 0);
-    tc_fence_after_sync();
+    const int ew = warp - 2;   // 0..7
+    const int q = warp & 3;    // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int hsel = ew >> 2;  // which half of the tile's columns this warp drains
+    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGING_OFFSET) + ew * 32 * Cfg::SPITCH;
+    constexpr int LPR = Cfg::SW / 4;  // lanes per row in phase 2
+    constexpr int RPI = 32 / LPR;     // rows per phase-2 iteration
+    const int lr = lane / LPR, lc = (lane % LPR) * 4;
+    int it = 0;
+    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const int tn = static_cast<int>(w % tiles_n);
+      const int tm = static_cast<int>((w / tiles_n) % tiles_m);
+      const int z = static_cast<int>(w / (static_cast<int64_t>(tiles_n) * tiles_m));
+      const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after_sync();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      const int nc0 = n0 + c * 32;
-      if (m < g.M && nc0 < g.N) {
-        const int ncols = min(32, g.N - nc0);
-        if (g.splits > 1) {
-          float* p = g.partial + (static_cast<int64_t>(blockIdx.z) * g.M + m) * g.N + nc0;
-          if (ncols == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      for (int pass = 0; pass < Cfg::PASSES; ++pass) {
+        const int colbase = hsel * Cfg::SPAN + pass * Cfg::SW;
+        // ---- phase 1: accumulator rows -> shared memory
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(p)[j] =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
+        for (int c = 0; c < Cfg::SW / 32; ++c) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + colbase + c * 32, v);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(stg + lane * Cfg::SPITCH + c * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) p[j] = v[j];
-          }
-        } else {
-          epilogue_chunk<32>(g.epi, g.N, m, nc0, ncols, v);
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+        if (pass == Cfg::PASSES - 1) {
+          // every tcgen05.ld of this warp has completed: hand the TMEM stage back to the MMA warp
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        } else {
+          __syncwarp();
+        }
+        // ---- phase 2: coalesced epilogue, 4 consecutive columns per lane
+        const int n = tn * BN + colbase + lc;
+#pragma unroll 2
+        for (int r0 = 0; r0 < 32; r0 += RPI) {
+          const int r = r0 + lr;
+          const float4 t = *reinterpret_cast<const float4*>(stg + r * Cfg::SPITCH + lc);
+          float v4[4] = {t.x, t.y, t.z, t.w};
+          const int m = tm * BM + q * 32 + r;
+          if (m < g.M && n < g.N) {
+            const int ncols = min(4, g.N - n);
+            if (g.splits > 1) {
+              float* p = g.partial + (static_cast<int64_t>(z) * g.M + m) * g.N + n;
+              if (ncols == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                *reinterpret_cast<float4*>(p) = t;
+              } else {
+                for (int j = 0; j < ncols; ++j) p[j] = v4[j];
+              }
+            } else {
+              epilogue_chunk<4>(g.epi, g.N, m, n, ncols, v4);
+            }
+          }
+        }
+        __syncwarp();  // the staging buffer is reused by the next pass / tile
       }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // Sums split-K partials in split order (deterministic) and applies the epilogue. One thread per 4
@@ -332,7 +404,14 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   GG_CUDA_CHECK(attr_err);
-  dim3 grid(ceil_div(args.N, BN), ceil_div(args.M, BM), args.splits);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    GG_CUDA_CHECK(cudaGetDevice(&dev));
+    GG_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int64_t work = static_cast<int64_t>(ceil_div(args.N, BN)) * ceil_div(args.M, BM) * args.splits;
+  dim3 grid(static_cast<unsigned>(work < num_sms ? work : num_sms));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
     if (g_prof.used + 2 > g_prof.ev.size()) {
@@ -349,7 +428,7 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
     g_prof.launches += 1;
     GG_CUDA_CHECK(cudaEventRecord(e0, stream));
   }
-  gemm_tc_kernel<BN, STAGES><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
+  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
                                                                      maps[3], args);
   GG_LAUNCH_CHECK();
   if (e1) GG_CUDA_CHECK(cudaEventRecord(e1, stream));
@@ -435,9 +514,9 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
   args.splits = splits;
 
   int rc;
-  if (bn == 64) rc = launch_tc<64, 4>(maps, args, stream);
-  else if (bn == 128) rc = launch_tc<128, 3>(maps, args, stream);
-  else rc = launch_tc<256, 4>(maps, args, stream);
+  if (bn == 64) rc = launch_tc<64, 6>(maps, args, stream);
+  else if (bn == 128) rc = launch_tc<128, 4>(maps, args, stream);
+  else rc = launch_tc<256, 3>(maps, args, stream);
   if (rc) return rc;
 
   if (splits > 1) {

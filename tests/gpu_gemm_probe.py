@@ -53,6 +53,11 @@ def main():
         (256, 512, 320, 128, 0, 192),   # two K segments
         (384, 1000, 256, 256, 0, 0),
         (100, 72, 40, 64, 0, 0),
+        (4096, 1024, 256, 128, 0, 0),   # 256 tiles > 148 SMs: persistent loop + TMEM double buffering
+        (1024, 18868, 256, 128, 0, 0),  # generator output shape, ragged N
+        (2048, 1280, 192, 256, 0, 0),   # BN=256, 80 tiles
+        (27648, 512, 256, 128, 0, 0),   # tower FFN shape
+        (512, 256, 9000, 128, 9, 0),    # long K split 9 ways
     ]
     ok = True
     for (M, N, K, bn, splits, K2) in cases:
