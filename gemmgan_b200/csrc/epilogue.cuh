@@ -54,10 +54,11 @@ __device__ __forceinline__ void load_row_chunk(const void* base, int is_f32, int
   }
 }
 
-// v[0..ncols) holds the raw accumulators of row m, columns [n0, n0+ncols).
+// v[0..ncols) holds the raw accumulators of row m, columns [n0, n0+ncols): everything between the
+// accumulator and the stores (scale, bias, pre-add, activation, dropout, mask, residual).
 template <int W>
-__device__ __forceinline__ void epilogue_chunk(const gg_epilogue& e, int N, int m, int n0,
-                                               int ncols, float* v) {
+__device__ __forceinline__ void epilogue_math(const gg_epilogue& e, int N, int m, int n0,
+                                              int ncols, float* v) {
   float t[W];
   if (e.alpha != 1.0f) {
 #pragma unroll
@@ -112,9 +113,18 @@ __device__ __forceinline__ void epilogue_chunk(const gg_epilogue& e, int N, int 
 #pragma unroll
     for (int j = 0; j < W; ++j) v[j] += t[j];
   }
-  int row = m;
-  if (e.row_div > 0) row = (m / e.row_div) * e.row_mul + e.row_add + (m % e.row_div);
-  if (e.out_f32) {
+}
+
+__device__ __forceinline__ int epilogue_out_row(const gg_epilogue& e, int m) {
+  return e.row_div > 0 ? (m / e.row_div) * e.row_mul + e.row_add + (m % e.row_div) : m;
+}
+
+// Direct global stores of a finished run of <= W columns of row m (either output may be skipped).
+template <int W>
+__device__ __forceinline__ void epilogue_store(const gg_epilogue& e, int m, int n0, int ncols,
+                                               const float* v, bool do_f32, bool do_bf16) {
+  const int row = epilogue_out_row(e, m);
+  if (do_f32 && e.out_f32) {
     float* p = e.out_f32 + static_cast<int64_t>(row) * e.ld_f32 + n0;
     if (e.accum_f32) {
 #pragma unroll
@@ -131,7 +141,7 @@ __device__ __forceinline__ void epilogue_chunk(const gg_epilogue& e, int N, int 
         if (j < ncols) p[j] = v[j];
     }
   }
-  if (e.out_bf16) {
+  if (do_bf16 && e.out_bf16) {
     __nv_bfloat16* p =
         reinterpret_cast<__nv_bfloat16*>(e.out_bf16) + static_cast<int64_t>(row) * e.ld_bf16 + n0;
     if (ncols == W && (reinterpret_cast<uintptr_t>(p) & (W >= 8 ? 15 : 7)) == 0) {
@@ -158,6 +168,13 @@ __device__ __forceinline__ void epilogue_chunk(const gg_epilogue& e, int N, int 
         if (j < ncols) p[j] = __float2bfloat16_rn(v[j]);
     }
   }
+}
+
+template <int W>
+__device__ __forceinline__ void epilogue_chunk(const gg_epilogue& e, int N, int m, int n0,
+                                               int ncols, float* v) {
+  epilogue_math<W>(e, N, m, n0, ncols, v);
+  epilogue_store<W>(e, m, n0, ncols, v, true, true);
 }
 
 }  // namespace gg

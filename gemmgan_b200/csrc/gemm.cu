@@ -34,25 +34,27 @@ struct GemmArgs {
   int K0, K1;
   int a_mn, b_mn;
   int splits;
+  int tma_out_bf16, tma_out_f32;  // outputs written by TMA stores (alignment permitting)
   float* partial;
   gg_epilogue epi;
 };
 
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int SLOT_BYTES = 4096;   // one 32-row x 128-byte box of the output, 128B-swizzled
+constexpr int SLOTS_PER_WARP = 2;
 
 template <int BN, int STAGES>
 struct TileCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  // epilogue: each of the 8 warps owns 32 rows x SPAN columns of the tile and stages SW columns at a
-  // time through padded shared memory (pitch SW+4 floats: conflict-free 16-byte writes and reads)
-  static constexpr int SPAN = BN / 2;
-  static constexpr int SW = SPAN < 64 ? SPAN : 64;
-  static constexpr int PASSES = SPAN / SW;
-  static constexpr int SPITCH = SW + 4;
+  // epilogue: warp w drains TMEM lanes [32*(w%4), +32) (a hardware rule) and COLS_PER_WARP columns.
+  // BN = 64 keeps only four epilogue warps busy.
+  static constexpr int ACTIVE_EPI_WARPS = BN == 64 ? 4 : 8;
+  static constexpr int COLS_PER_WARP = BN == 64 ? 64 : BN / 2;
+  static constexpr int CHUNKS = COLS_PER_WARP / 32;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * SPITCH * 4;
+  static constexpr int STAGING_BYTES = EPI_WARPS * SLOTS_PER_WARP * SLOT_BYTES;
   static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;  // full/empty per stage + tmem full/empty x 2
   static constexpr int SMEM_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
@@ -63,13 +65,16 @@ struct TileCfg {
 // (split, m-tile, n-tile) with the n-tile fastest (CTAs running side by side share the A rows in L2).
 // The fp32 accumulator is double-buffered in tensor memory: while the epilogue warps drain stage a,
 // the MMA warp already accumulates the next tile into stage a^1, and the TMA ring keeps running across
-// tile boundaries. Epilogue = two phases per warp: (1) tcgen05.ld (thread = row) -> shared memory,
-// release the TMEM stage; (2) thread = 4 consecutive columns, rows in turn: every global load
-// (mask / residual) and store is a contiguous >= 128-byte row segment per warp instruction.
+// tile boundaries.
+// Epilogue: thread = accumulator row. Per 32-column chunk: tcgen05.ld -> fused math in registers ->
+// 16-byte writes into a 128B-swizzled staging box -> one TMA store per box (bf16: 32 rows x 64 columns,
+// fp32: 32 x 32; the hardware clips the M / N tails). Outputs whose pitch or base is not 16-byte
+// aligned, row-remapped outputs and split-K partials take direct per-row vector stores instead.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                   const __grid_constant__ CUtensorMap tmOutB, const __grid_constant__ CUtensorMap tmOutF,
                    const GemmArgs g) {
   using Cfg = TileCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -96,13 +101,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tma_prefetch_desc(&tmA1);
       tma_prefetch_desc(&tmB1);
     }
+    if (g.tma_out_bf16) tma_prefetch_desc(&tmOutB);
+    if (g.tma_out_f32) tma_prefetch_desc(&tmOutF);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], Cfg::ACTIVE_EPI_WARPS);  // one arrival per active epilogue warp
     }
     fence_mbar_init();
   }
@@ -194,68 +201,106 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tc_commit(&tmem_full[acc]);
       }
     }
-  } else {
+  } else if (warp - 2 < Cfg::ACTIVE_EPI_WARPS) {
     const int ew = warp - 2;   // 0..7
     const int q = warp & 3;    // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int hsel = ew >> 2;  // which half of the tile's columns this warp drains
-    float* stg = reinterpret_cast<float*>(smem + Cfg::STAGING_OFFSET) + ew * 32 * Cfg::SPITCH;
-    constexpr int LPR = Cfg::SW / 4;  // lanes per row in phase 2
-    constexpr int RPI = 32 / LPR;     // rows per phase-2 iteration
-    const int lr = lane / LPR, lc = (lane % LPR) * 4;
+    const int hsel = ew >> 2;  // which run of COLS_PER_WARP columns this warp drains
+    uint8_t* slots = smem + Cfg::STAGING_OFFSET + ew * (SLOTS_PER_WARP * SLOT_BYTES);
+    const uint32_t lane_row = static_cast<uint32_t>(lane) * 128u;
+    const uint32_t swz = static_cast<uint32_t>(lane & 7);
+    const bool tma_b = g.tma_out_bf16 != 0, tma_f = g.tma_out_f32 != 0;
+    int slot = 0;
+    uint8_t* bslot = slots;  // staging box of the bf16 output (spans two chunks)
     int it = 0;
     for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int tn = static_cast<int>(w % tiles_n);
       const int tm = static_cast<int>((w / tiles_n) % tiles_m);
       const int z = static_cast<int>(w / (static_cast<int64_t>(tiles_n) * tiles_m));
       const int acc = it & 1;
+      const int row0 = tm * BM + q * 32;
+      const int m = row0 + lane;
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int pass = 0; pass < Cfg::PASSES; ++pass) {
-        const int colbase = hsel * Cfg::SPAN + pass * Cfg::SW;
-        // ---- phase 1: accumulator rows -> shared memory
-#pragma unroll
-        for (int c = 0; c < Cfg::SW / 32; ++c) {
-          float v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + colbase + c * 32, v);
-          tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(stg + lane * Cfg::SPITCH + c * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (pass == Cfg::PASSES - 1) {
+      for (int c = 0; c < Cfg::CHUNKS; ++c) {
+        const int col0 = hsel * Cfg::COLS_PER_WARP + c * 32;
+        const int n0 = tn * BN + col0;
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0, v);
+        tmem_ld_wait();
+        if (c == Cfg::CHUNKS - 1) {
           // every tcgen05.ld of this warp has completed: hand the TMEM stage back to the MMA warp
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        } else {
-          __syncwarp();
         }
-        // ---- phase 2: coalesced epilogue, 4 consecutive columns per lane
-        const int n = tn * BN + colbase + lc;
-#pragma unroll 2
-        for (int r0 = 0; r0 < 32; r0 += RPI) {
-          const int r = r0 + lr;
-          const float4 t = *reinterpret_cast<const float4*>(stg + r * Cfg::SPITCH + lc);
-          float v4[4] = {t.x, t.y, t.z, t.w};
-          const int m = tm * BM + q * 32 + r;
-          if (m < g.M && n < g.N) {
-            const int ncols = min(4, g.N - n);
-            if (g.splits > 1) {
-              float* p = g.partial + (static_cast<int64_t>(z) * g.M + m) * g.N + n;
-              if (ncols == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-                *reinterpret_cast<float4*>(p) = t;
-              } else {
-                for (int j = 0; j < ncols; ++j) p[j] = v4[j];
-              }
+        const int ncols = min(32, g.N - n0);  // <= 0: this chunk lies beyond N (warp-uniform)
+        const bool live = m < g.M && ncols > 0;
+        if (g.splits > 1) {
+          if (live) {
+            float* p = g.partial + (static_cast<int64_t>(z) * g.M + m) * g.N + n0;
+            if (ncols == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             } else {
-              epilogue_chunk<4>(g.epi, g.N, m, n, ncols, v4);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) p[j] = v[j];
+            }
+          }
+          continue;
+        }
+        if (live) epilogue_math<32>(g.epi, g.N, m, n0, ncols, v);
+        if (live && ((g.epi.out_f32 && !tma_f) || (g.epi.out_bf16 && !tma_b)))
+          epilogue_store<32>(g.epi, m, n0, ncols, v, !tma_f, !tma_b);
+        if (tma_f && ncols > 0) {
+          slot ^= 1;
+          uint8_t* fs = slots + slot * SLOT_BYTES;
+          if (lane == 0) tma_store_wait_read<SLOTS_PER_WARP - 1>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(fs + lane_row + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOutF, fs, n0, row0);
+            tma_store_commit();
+          }
+        }
+        if (tma_b) {
+          const int half = c & 1;
+          if (half == 0 && ncols > 0) {
+            slot ^= 1;
+            bslot = slots + slot * SLOT_BYTES;
+            if (lane == 0) tma_store_wait_read<SLOTS_PER_WARP - 1>();
+            __syncwarp();
+          }
+          if (ncols > 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]);
+              *reinterpret_cast<uint4*>(bslot + lane_row + ((static_cast<uint32_t>(half * 4 + j) ^ swz) << 4)) = pk;
+            }
+          }
+          // the box is complete after its second chunk; a box whose first column lies beyond N is skipped
+          if (half == 1 && n0 - 32 < g.N) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmOutB, bslot, n0 - 32, row0);
+              tma_store_commit();
             }
           }
         }
-        __syncwarp();  // the staging buffer is reused by the next pass / tile
       }
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before_sync();
@@ -357,25 +402,28 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor [outer, inner] with row pitch ld (elements); box = {64, box_outer}, 128B swizzle.
+// 2-D tensor [outer, inner] of bf16 (or fp32) with row pitch ld (elements); box = {box_inner, box_outer},
+// 128B swizzle (box_inner * element size = 128 bytes).
 static int encode_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld,
-                      int box_outer) {
+                      int box_outer, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");
     return GG_ERR_CUDA;
   }
+  const int esz = f32 ? 4 : 2;
   GG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand %p not 16-byte aligned",
              ptr);
-  GG_REQUIRE(ld % 8 == 0 && ld >= inner, "GEMM operand ld=%lld must be a multiple of 8 and >= %lld",
-             (long long)ld, (long long)inner);
+  GG_REQUIRE((ld * esz) % 16 == 0 && ld >= inner, "GEMM operand ld=%lld must be a multiple of %d and >= %lld",
+             (long long)ld, 16 / esz, (long long)inner);
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", (int)r,
               (long long)inner, (long long)outer, (long long)ld);
@@ -429,7 +477,7 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
     GG_CUDA_CHECK(cudaEventRecord(e0, stream));
   }
   gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
-                                                                     maps[3], args);
+                                                                     maps[3], maps[4], maps[5], args);
   GG_LAUNCH_CHECK();
   if (e1) GG_CUDA_CHECK(cudaEventRecord(e1, stream));
   return GG_OK;
@@ -465,7 +513,7 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
   if (bn == 0) bn = d->N <= 64 ? 64 : 128;
   GG_REQUIRE(bn == 64 || bn == 128 || bn == 256, "block_n must be 64, 128 or 256");
 
-  CUtensorMap maps[4];
+  CUtensorMap maps[6];
   for (int s = 0; s < 2; ++s) {
     const gg_gemm_seg& sg = d->seg[s < d->nseg ? s : 0];
     int rc;
@@ -512,6 +560,24 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
     }
   }
   args.splits = splits;
+
+  // outputs go through TMA stores when their layout allows it (16-byte aligned base and pitch, identity
+  // row map, plain overwrite); split-K runs its epilogue in the reduce kernel instead
+  const gg_epilogue& ep = d->epi;
+  args.tma_out_bf16 = splits == 1 && ep.out_bf16 && ep.row_div <= 0 && ep.ld_bf16 % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0;
+  args.tma_out_f32 = splits == 1 && ep.out_f32 && ep.row_div <= 0 && !ep.accum_f32 && ep.ld_f32 % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0;
+  maps[4] = maps[0];
+  maps[5] = maps[0];
+  if (args.tma_out_bf16) {
+    int rc = encode_map(&maps[4], ep.out_bf16, d->N, d->M, ep.ld_bf16, 32, false);
+    if (rc) return rc;
+  }
+  if (args.tma_out_f32) {
+    int rc = encode_map(&maps[5], ep.out_f32, d->N, d->M, ep.ld_f32, 32, true);
+    if (rc) return rc;
+  }
 
   int rc;
   if (bn == 64) rc = launch_tc<64, 6>(maps, args, stream);

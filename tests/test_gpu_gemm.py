@@ -1,0 +1,119 @@
+"""GPU tests of gg_gemm_bf16 (tcgen05 / TMEM / TMA kernel) through the C ABI: every epilogue feature, both
+output paths (TMA-store boxes and direct per-row stores), ragged M / N / K, both operand majors, split-K,
+the persistent multi-tile loop, and all three tile widths — against a torch fp32 reference on the same bf16
+operands (tolerance: fp32 accumulation-order noise, plus one bf16 rounding step on bf16 outputs) and against
+the CUDA-core check kernel that shares the epilogue code (dropout masks must agree bit for bit)."""
+import pytest
+import torch
+
+from gemmgan_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rows, cols, g, ld=None, scale=1.0):
+    ld = ld or (cols + 7) // 8 * 8
+    buf = torch.zeros(rows, ld, device="cuda", dtype=torch.bfloat16)
+    buf[:, :cols] = (torch.randn(rows, cols, device="cuda", generator=g) * scale).to(torch.bfloat16)
+    return buf[:, :cols]
+
+
+def _ref(a, b, a_mn, b_mn):
+    af = a.float().t() if a_mn else a.float()
+    bf = b.float().t() if b_mn else b.float()
+    return af @ bf.t()
+
+
+def _leaky(x, s):
+    return torch.where(x > 0, x, s * x)
+
+
+CASES = [
+    # M, N, K, a_mn, b_mn, bn, splits
+    (1000, 200, 256, 0, 0, 0, 0),
+    (128, 64, 64, 0, 0, 64, 0),
+    (300, 520, 136, 0, 1, 128, 0),
+    (260, 1000, 200, 1, 1, 256, 0),
+    (520, 264, 1000, 1, 0, 128, 3),
+    (27648, 768, 256, 0, 0, 128, 0),     # persistent loop: ~9 tiles per CTA
+    (18432, 512, 256, 0, 1, 256, 0),
+    (256, 18872, 512, 1, 1, 256, 0),
+]
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,bn,splits", CASES)
+@pytest.mark.parametrize("aligned", [True, False])
+def test_gemm_epilogue_features(M, N, K, a_mn, b_mn, bn, splits, aligned):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 7 * K)
+    a = _mk(K, M, g) if a_mn else _mk(M, K, g)
+    b = _mk(K, N, g) if b_mn else _mk(N, K, g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    pre = _mk(M, N, g)
+    mask = _mk(M, N, g)
+    res = torch.randn(M, N, device="cuda", generator=g)           # fp32 residual
+    # aligned: pitches that allow TMA stores; unaligned: odd pitches force the direct-store path
+    ld_b = (N + 7) // 8 * 8 if aligned else (N + 7) // 8 * 8 + 2
+    ld_f = (N + 3) // 4 * 4 if aligned else (N + 3) // 4 * 4 + 1
+    ob = torch.full((M, ld_b), 7.0, device="cuda", dtype=torch.bfloat16)
+    of = torch.full((M, ld_f), 7.0, device="cuda", dtype=torch.float32)
+    ws = torch.empty(max(1, splits) * M * N * 4 + 1024, device="cuda", dtype=torch.uint8)
+    ops.gemm(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), bias=bias, pre=pre, act=_lib.ACT_LEAKY, slope=0.2,
+             mask=mask, mask_pos=1.5, mask_neg=-0.5, res=res, alpha=0.5, out_bf16=ob[:, :N], out_f32=of[:, :N],
+             workspace=ws, splits=splits, block_n=bn)
+    torch.cuda.synchronize()
+    want = _leaky(0.5 * _ref(a, b, a_mn, b_mn) + bias + pre.float(), 0.2)
+    want = want * torch.where(mask.float() > 0, 1.5, -0.5) + res
+    scale = want.abs().max().item()
+    assert (of[:, :N] - want).abs().max().item() <= 1e-4 * scale
+    assert (ob[:, :N].float() - want).abs().max().item() <= 5e-3 * scale
+    # nothing outside the [M, N] window was touched (clipped TMA boxes, guarded direct stores)
+    if ld_b > N:
+        assert (ob[:, N:] == 7.0).all()
+    if ld_f > N:
+        assert (of[:, N:] == 7.0).all()
+
+
+def test_gemm_two_segments_row_map_and_film():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Bn, P, S, E, K, K2 = 37, 5, 6, 64, 192, 72
+    M = Bn * P
+    a, b = _mk(M, K, g), _mk(E, K, g)
+    a2, b2 = _mk(M, K2, g), _mk(E, K2, g)
+    out = torch.zeros(Bn * S, E, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, a2=a2, b2=b2, out_bf16=out, row_map=(P, S, 1))
+    torch.cuda.synchronize()
+    want = (_ref(a, b, 0, 0) + _ref(a2, b2, 0, 0)).view(Bn, P, E)
+    got = out.view(Bn, S, E)
+    assert (got[:, 0] == 0).all()
+    assert (got[:, 1:].float() - want).abs().max().item() <= 5e-3 * want.abs().max().item()
+    # FiLM activation: tanh on the first half of the columns, clamp(-5, 5) on the second
+    w = _mk(128, K, g, scale=2.0)
+    of = torch.empty(M, 128, device="cuda", dtype=torch.float32)
+    ops.gemm(a, w, act=_lib.ACT_FILM, out_f32=of)
+    torch.cuda.synchronize()
+    r = _ref(a, w, 0, 0)
+    want = torch.cat([torch.tanh(r[:, :64]), r[:, 64:].clamp(-5, 5)], 1)
+    assert (of - want).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_dropout_matches_check_kernel(bn):
+    """Dropout is a pure function of (seed, step, site, element index): the tensor-core kernel and the
+    CUDA-core check kernel must drop exactly the same elements, whatever the tiling."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    M, N, K = 1111, 512, 128
+    a, b = _mk(M, K, g), _mk(N, K, g)
+    rng = torch.tensor([1234, 7], device="cuda", dtype=torch.int64)
+    o1 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    o2 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, drop_p=0.25, rng=rng, site=3, out_f32=o1, block_n=bn)
+    ops.gemm(a, b, drop_p=0.25, rng=rng, site=3, out_f32=o2, impl=_lib.IMPL_SIMT_F32)
+    torch.cuda.synchronize()
+    assert ((o1 == 0) == (o2 == 0)).all()
+    frac = (o1 == 0).float().mean().item()
+    assert abs(frac - 0.25) < 0.01
+    assert (o1 - o2).abs().max().item() <= 1e-3 * o2.abs().max().item()
+    keep = o1 != 0
+    want = _ref(a, b, 0, 0) / 0.75
+    assert (o1[keep] - want[keep]).abs().max().item() <= 1e-3 * want.abs().max().item()
