@@ -52,6 +52,7 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_destroy.argtypes = [vp]
     L.gg_engine_destroy.restype = None
     L.gg_engine_refresh_shadows.argtypes = [vp, i32, vp]
+    L.gg_engine_set_lanes.argtypes = [vp, i32]
     L.gg_engine_set_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.gg_engine_disc_grads.argtypes = [vp, vp, vp, i32, vp]
     L.gg_engine_gen_grads.argtypes = [vp, vp, i32, vp]
@@ -74,7 +75,7 @@ def declare(L: C.CDLL) -> None:
 
 EXPORTS = [
     "gg_last_error", "gg_abi_version", "gg_check_device", "gg_gemm_bf16", "gg_engine_workspace_bytes",
-    "gg_engine_create", "gg_engine_destroy", "gg_engine_refresh_shadows", "gg_engine_set_batch",
+    "gg_engine_create", "gg_engine_destroy", "gg_engine_set_lanes", "gg_engine_refresh_shadows", "gg_engine_set_batch",
     "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_optim_step", "gg_engine_generate",
     "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end",

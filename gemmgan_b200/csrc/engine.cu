@@ -14,6 +14,7 @@
 #include "host_util.h"
 #include "kernels.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -91,9 +92,13 @@ struct Tower {
   TowerLayer L[2];
   bf16 *qp, *kvp, *ap, *pv, *qt, *kvt, *at, *c, *tmpE;
 };
+struct LayerGrads {  // per layer: side-lane weight-gradient GEMMs read these while lane 0 moves on
+  bf16 *gz2, *gy2, *gz1, *gy1, *gh, *gqkv;
+};
 struct GradScratch {
   bf16 *dc, *dat, *dqt, *dkvt, *dkvt_sum, *dp, *dap, *dqp, *dqp_sum, *dkvp;
-  bf16 *ga, *gb, *gz, *gy, *gh, *gao, *gqkv, *dte, *dte0, *dpe, *dmod, *dgb;
+  bf16 *ga, *gb, *gao, *dte, *dte0, *dpe, *dmod, *dgb;
+  LayerGrads L[2];
 };
 struct TrunkBufs {
   float *a1x, *a1c, *h2f, *score, *Mg, *u1f, *y, *norms, *pen, *du2f, *roww;
@@ -109,7 +114,7 @@ struct gg_engine {
   gg_model_cfg cfg;
   gg_net_buffers nets[2];
   NetShadow sh[2];
-  int S = 1, Gp = 0, F = 0, hd = 0;
+  int S_ = 1, Gp = 0, F = 0, hd = 0;
   bool cond = false, paper = false;
   // staged inputs
   bf16 *xfr, *patches, *text, *zbf, *xin;
@@ -118,17 +123,63 @@ struct gg_engine {
   Tower tw[2];
   GradScratch gs;
   TrunkBufs tb;
-  float *scratch, *stats, *opt_step[2], *normbuf, *attn_stat;
+  float *stats, *opt_step[2], *normbuf, *attn_stat;
   uint64_t* rng;
-  void* splitk;
+  // Lanes: lane 0 is the caller's stream (the dependent chain: forwards, dgrads, attention / LayerNorm
+  // backward); lanes 1.. are engine-owned streams for work nothing on the chain waits for (weight- and
+  // bias-gradient GEMMs / reductions, the generator forward next to the critic tower forward). Each lane
+  // has its own split-K workspace and reduction scratch. Forks and joins are event edges, so the whole
+  // step stays capturable into one CUDA graph; every entry point joins all lanes before it returns.
+  static constexpr int NLANES = 3;
+  static constexpr int NEVENTS = 16;
+  cudaStream_t cur[NLANES] = {nullptr, nullptr, nullptr};
+  cudaEvent_t evs[NEVENTS];
+  int ev_next = 0;
+  bool forked[NLANES] = {false, false, false};
+  bool multi_lane = true;
+  float* scratch_l[NLANES];
+  void* splitk_l[NLANES];
   int64_t splitk_bytes = 0;
   int64_t total_bytes = 0;
+
+  int L(int lane) const { return multi_lane ? lane : 0; }
+  cudaStream_t S(int lane) const { return cur[L(lane)]; }
+  // lane `lane` waits for everything enqueued on lane 0 so far
+  int fork(int lane) {
+    lane = L(lane);
+    if (lane == 0) return GG_OK;
+    cudaEvent_t ev = evs[ev_next];
+    ev_next = (ev_next + 1) % NEVENTS;
+    GG_CUDA_CHECK(cudaEventRecord(ev, cur[0]));
+    GG_CUDA_CHECK(cudaStreamWaitEvent(cur[lane], ev, 0));
+    forked[lane] = true;
+    return GG_OK;
+  }
+  // lane 0 waits for everything enqueued on `lane`
+  int join(int lane) {
+    lane = L(lane);
+    if (lane == 0 || !forked[lane]) return GG_OK;
+    cudaEvent_t ev = evs[ev_next];
+    ev_next = (ev_next + 1) % NEVENTS;
+    GG_CUDA_CHECK(cudaEventRecord(ev, cur[lane]));
+    GG_CUDA_CHECK(cudaStreamWaitEvent(cur[0], ev, 0));
+    forked[lane] = false;
+    return GG_OK;
+  }
+  int join_all() {
+    for (int l = 1; l < NLANES; ++l) {
+      int rc = join(l);
+      if (rc) return rc;
+    }
+    return GG_OK;
+  }
+  void begin(void* stream) { cur[0] = reinterpret_cast<cudaStream_t>(stream); }
 
   float* P(int net, int slot) const { return nets[net].off[slot] < 0 ? nullptr : nets[net].params + nets[net].off[slot]; }
   float* Gr(int net, int slot) const { return nets[net].off[slot] < 0 ? nullptr : nets[net].grads + nets[net].off[slot]; }
   Op W(int net, int slot) const { return Op{sh[net].w[slot].p, sh[net].w[slot].ld}; }
 
-  int mm(cudaStream_t st, int M, int N, int K, Op A, int a_mn, Op B, int b_mn, const Epi& epi, int K2 = 0,
+  int mm(int lane, int M, int N, int K, Op A, int a_mn, Op B, int b_mn, const Epi& epi, int K2 = 0,
          Op A2 = Op(), Op B2 = Op()) const {
     gg_gemm_desc d;
     memset(&d, 0, sizeof(d));
@@ -138,25 +189,29 @@ struct gg_engine {
     if (K2 > 0) { d.seg[1].a = A2.p; d.seg[1].b = B2.p; d.seg[1].lda = A2.ld; d.seg[1].ldb = B2.ld; d.seg[1].K = K2; }
     d.a_mn_major = a_mn; d.b_mn_major = b_mn;
     d.epi = epi.e;
-    d.workspace = splitk; d.workspace_bytes = splitk_bytes;
+    d.workspace = splitk_l[L(lane)]; d.workspace_bytes = splitk_bytes;
     d.impl = cfg.gemm_impl;
-    return gemm_dispatch(&d, st);
+    return gemm_dispatch(&d, S(lane));
   }
   // Y = X W^T (+b): X [rows, in], W [out, in]
-  int linear(cudaStream_t st, int rows, int out, int in, Op X, Op Wt, const Epi& epi) const {
-    return mm(st, rows, out, in, X, 0, Wt, 0, epi);
+  int linear(int lane, int rows, int out, int in, Op X, Op Wt, const Epi& epi) const {
+    return mm(lane, rows, out, in, X, 0, Wt, 0, epi);
   }
   // dX = dY W: dY [rows, out], W [out, in]
-  int dgrad(cudaStream_t st, int rows, int in, int out, Op dY, Op Wt, const Epi& epi) const {
-    return mm(st, rows, in, out, dY, 0, Wt, 1, epi);
+  int dgrad(int lane, int rows, int in, int out, Op dY, Op Wt, const Epi& epi) const {
+    return mm(lane, rows, in, out, dY, 0, Wt, 1, epi);
   }
+  // Weight / bias gradients feed nothing but the optimizer: they run on side lanes, ordered after
+  // everything lane 0 has enqueued so far (their operands), and are joined at the end of the entry point.
   // dW[out, in] = dY^T X, fp32 into the gradient buffer (pitch ldw)
-  int wgrad(cudaStream_t st, int out, int in, int rows, Op dY, Op X, float* dW, int64_t ldw) const {
-    return mm(st, out, in, rows, dY, 1, X, 1, Epi().of32(dW, ldw));
+  int wgrad(int rows_out, int in, int rows, Op dY, Op X, float* dW, int64_t ldw) {
+    GG_TRY(fork(1));
+    return mm(1, rows_out, in, rows, dY, 1, X, 1, Epi().of32(dW, ldw));
   }
-  int bgrad(cudaStream_t st, const bf16* dY, int64_t ld, int64_t rows, int N, float* db) const {
+  int bgrad(const bf16* dY, int64_t ld, int64_t rows, int N, float* db) {
     if (!db) return GG_OK;
-    return k_colsum(dY, 0, ld, rows, N, nullptr, 1.f, db, 0, scratch, st);
+    GG_TRY(fork(2));
+    return k_colsum(dY, 0, ld, rows, N, nullptr, 1.f, db, 0, scratch_l[L(2)], S(2));
   }
 };
 
@@ -225,7 +280,7 @@ static void layout_shadows(gg_engine& e, Arena& ar) {
 
 static void layout_tower(gg_engine& e, Tower& t, int Rmax, Arena& ar) {
   const gg_model_cfg& c = e.cfg;
-  const int64_t B = c.B, S = e.S, E = c.E, F = e.F, P = c.P, T = c.T;
+  const int64_t B = c.B, S = e.S_, E = c.E, F = e.F, P = c.P, T = c.T;
   const int64_t rows = static_cast<int64_t>(Rmax) * B * S;
   t.Rmax = Rmax;
   t.gb = ar.take<float>(B * 2 * c.Dp);
@@ -260,7 +315,7 @@ static void layout_tower(gg_engine& e, Tower& t, int Rmax, Arena& ar) {
 static int64_t layout(gg_engine& e, uint8_t* base) {
   const gg_model_cfg& c = e.cfg;
   Arena ar(base);
-  const int64_t B = c.B, S = e.S, E = c.E, F = e.F, P = c.P, T = c.T, H = c.H, Gp = e.Gp;
+  const int64_t B = c.B, S = e.S_, E = c.E, F = e.F, P = c.P, T = c.T, H = c.H, Gp = e.Gp;
   layout_shadows(e, ar);
   e.xfr = ar.take<bf16>(2 * B * Gp);
   e.xin = ar.take<bf16>(B * Gp);
@@ -295,11 +350,16 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
     g.dkvp = ar.take<bf16>(rows * 2 * E);
     g.ga = ar.take<bf16>(rows * E);
     g.gb = ar.take<bf16>(rows * E);
-    g.gz = ar.take<bf16>(rows * E);
-    g.gy = ar.take<bf16>(rows * E);
-    g.gh = ar.take<bf16>(rows * F);
     g.gao = ar.take<bf16>(rows * E);
-    g.gqkv = ar.take<bf16>(rows * 3 * E);
+    for (int l = 0; l < 2; ++l) {
+      LayerGrads& lg = g.L[l];
+      lg.gz2 = ar.take<bf16>(rows * E);
+      lg.gy2 = ar.take<bf16>(rows * E);
+      lg.gz1 = ar.take<bf16>(rows * E);
+      lg.gy1 = ar.take<bf16>(rows * E);
+      lg.gh = ar.take<bf16>(rows * F);
+      lg.gqkv = ar.take<bf16>(rows * 3 * E);
+    }
     g.dte = ar.take<bf16>(B * T * E);
     g.dte0 = ar.take<bf16>(B * E);
     g.dpe = ar.take<bf16>(B * P * E);
@@ -342,9 +402,11 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
   int64_t scratch_floats = 64 * maxN;
   if (scratch_floats < 296 * 2 * E) scratch_floats = 296 * 2 * E;
   if (scratch_floats < 1024) scratch_floats = 1024;
-  e.scratch = ar.take<float>(scratch_floats);
   e.splitk_bytes = 96LL << 20;
-  e.splitk = ar.take<uint8_t>(e.splitk_bytes);
+  for (int l = 0; l < gg_engine::NLANES; ++l) {
+    e.scratch_l[l] = ar.take<float>(scratch_floats);
+    e.splitk_l[l] = ar.take<uint8_t>(e.splitk_bytes);
+  }
   return round_up64(ar.off, 256);
 }
 
@@ -368,36 +430,38 @@ static void derive(gg_engine& e) {
   const gg_model_cfg& c = e.cfg;
   e.cond = c.variant != GG_VARIANT_VANILLA;
   e.paper = c.variant == GG_VARIANT_PAPER;
-  e.S = e.cond ? c.P + 1 : 1;
+  e.S_ = e.cond ? c.P + 1 : 1;
   e.Gp = static_cast<int>(round_up64(c.G, 8));
   e.F = c.ffn;
   e.hd = e.cond ? c.E / c.n_heads : 0;
 }
 
 // ------------------------------------------------------------------------------- tower forward
-static int tower_forward(gg_engine& e, int net, int R, float p, cudaStream_t st) {
+// Runs entirely on lane `ln` (the generator's tower runs next to the critic's on another lane).
+static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
   const gg_model_cfg& c = e.cfg;
   Tower& t = e.tw[net];
+  cudaStream_t st = e.S(ln);
   GG_REQUIRE(R <= t.Rmax, "tower replicas %d > allocated %d", R, t.Rmax);
-  const int B = c.B, S = e.S, E = c.E, F = e.F, P = c.P, T = c.T, Dp = c.Dp, Dt = c.Dt;
+  const int B = c.B, S = e.S_, E = c.E, F = e.F, P = c.P, T = c.T, Dp = c.Dp, Dt = c.Dt;
   const int rows = R * B * S;
   const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
   // FiLM parameters from the text CLS / text vector (:129-134)
-  GG_TRY(e.linear(st, B, 2 * Dp, Dt, Op{e.text, static_cast<int64_t>(T) * Dt}, e.W(net, GG_P_FILM_W),
+  GG_TRY(e.linear(ln, B, 2 * Dp, Dt, Op{e.text, static_cast<int64_t>(T) * Dt}, e.W(net, GG_P_FILM_W),
                   Epi().bias(e.P(net, GG_P_FILM_B)).act(GG_ACT_FILM).of32(t.gb, 2 * Dp)));
   GG_TRY(k_film_apply(e.patches, t.gb, t.mod, B, P, Dp, st));
   if (e.paper)
-    GG_TRY(e.linear(st, B * T, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W),
+    GG_TRY(e.linear(ln, B * T, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W),
                     Epi().bias(e.P(net, GG_P_TEXT_B)).obf(t.te, E)));
   // patch projection written straight behind the CLS row of replica 0 (:139-142)
-  GG_TRY(e.linear(st, B * P, E, Dp, Op{t.mod, Dp}, e.W(net, GG_P_PATCH_W),
+  GG_TRY(e.linear(ln, B * P, E, Dp, Op{t.mod, Dp}, e.W(net, GG_P_PATCH_W),
                   Epi().bias(e.P(net, GG_P_PATCH_B)).obf(t.X[0], E).rowmap(P, S, 1)));
   GG_TRY(k_assemble_tokens(t.X[0], e.P(net, GG_P_CLS), R, B, S, E, st));
   for (int l = 0; l < c.n_layers; ++l) {
     TowerLayer& L = t.L[l];
     const int ls = GG_P_LAYER0 + GG_L_COUNT * l;
     const uint32_t site = site0 + 8u * l;
-    GG_TRY(e.linear(st, rows, 3 * E, E, Op{t.X[l], E}, e.W(net, ls + GG_L_IN_W),
+    GG_TRY(e.linear(ln, rows, 3 * E, E, Op{t.X[l], E}, e.W(net, ls + GG_L_IN_W),
                     Epi().bias(e.P(net, ls + GG_L_IN_B)).obf(L.qkv, 3 * E)));
     AttnArgs a;
     memset(&a, 0, sizeof(a));
@@ -408,13 +472,13 @@ static int tower_forward(gg_engine& e, int net, int R, float p, cudaStream_t st)
     a.drop_p = p; a.rng = e.rng; a.site = site + 0;
     a.o = L.ao; a.ldo = E;
     GG_TRY(k_attention_fwd(a, st));
-    GG_TRY(e.linear(st, rows, E, E, Op{L.ao, E}, e.W(net, ls + GG_L_OUT_W),
+    GG_TRY(e.linear(ln, rows, E, E, Op{L.ao, E}, e.W(net, ls + GG_L_OUT_W),
                     Epi().bias(e.P(net, ls + GG_L_OUT_B)).obf(t.tmpE, E)));
     GG_TRY(k_add_ln_fwd(t.X[l], t.tmpE, e.P(net, ls + GG_L_N1_W), e.P(net, ls + GG_L_N1_B), L.z1, L.x1, L.mean1,
                         L.rstd1, rows, E, c.ln_eps, p, e.rng, site + 1, st));
-    GG_TRY(e.linear(st, rows, F, E, Op{L.x1, E}, e.W(net, ls + GG_L_FF1_W),
+    GG_TRY(e.linear(ln, rows, F, E, Op{L.x1, E}, e.W(net, ls + GG_L_FF1_W),
                     Epi().bias(e.P(net, ls + GG_L_FF1_B)).act(GG_ACT_LEAKY, 0.f).drop(p, e.rng, site + 2).obf(L.h, F)));
-    GG_TRY(e.linear(st, rows, E, F, Op{L.h, F}, e.W(net, ls + GG_L_FF2_W),
+    GG_TRY(e.linear(ln, rows, E, F, Op{L.h, F}, e.W(net, ls + GG_L_FF2_W),
                     Epi().bias(e.P(net, ls + GG_L_FF2_B)).obf(t.tmpE, E)));
     GG_TRY(k_add_ln_fwd(L.x1, t.tmpE, e.P(net, ls + GG_L_N2_W), e.P(net, ls + GG_L_N2_B), L.z2, t.X[l + 1],
                         L.mean2, L.rstd2, rows, E, c.ln_eps, p, e.rng, site + 3, st));
@@ -425,8 +489,8 @@ static int tower_forward(gg_engine& e, int net, int R, float p, cudaStream_t st)
   const float* bp = e.P(net, GG_P_P2T_IN_B);
   const float* bt = e.P(net, GG_P_T2P_IN_B);
   // patch2text: query = encoded text CLS, keys/values = encoder output (:149-150)
-  GG_TRY(e.linear(st, B, E, E, Op{t.te, static_cast<int64_t>(T) * E}, Wp, Epi().bias(bp).obf(t.qp, E)));
-  GG_TRY(e.linear(st, rows, 2 * E, E, Op{Xf, E}, Op{Wp.p + static_cast<int64_t>(E) * Wp.ld, Wp.ld},
+  GG_TRY(e.linear(ln, B, E, E, Op{t.te, static_cast<int64_t>(T) * E}, Wp, Epi().bias(bp).obf(t.qp, E)));
+  GG_TRY(e.linear(ln, rows, 2 * E, E, Op{Xf, E}, Op{Wp.p + static_cast<int64_t>(E) * Wp.ld, Wp.ld},
                   Epi().bias(bp ? bp + E : nullptr).obf(t.kvp, 2 * E)));
   AttnArgs a;
   memset(&a, 0, sizeof(a));
@@ -436,11 +500,11 @@ static int tower_forward(gg_engine& e, int net, int R, float p, cudaStream_t st)
   a.nb = R * B; a.H = c.n_heads; a.hd = e.hd; a.Lq = 1; a.Lk = S;
   a.o = t.ap; a.ldo = E;
   GG_TRY(k_attention_fwd(a, st));
-  GG_TRY(e.linear(st, R * B, E, E, Op{t.ap, E}, e.W(net, GG_P_P2T_OUT_W),
+  GG_TRY(e.linear(ln, R * B, E, E, Op{t.ap, E}, e.W(net, GG_P_P2T_OUT_W),
                   Epi().bias(e.P(net, GG_P_P2T_OUT_B)).obf(t.pv, E)));
   // text2patch: query = that vector, keys/values = encoded text tokens (:151-152)
-  GG_TRY(e.linear(st, R * B, E, E, Op{t.pv, E}, Wt, Epi().bias(bt).obf(t.qt, E)));
-  GG_TRY(e.linear(st, B * T, 2 * E, E, Op{t.te, E}, Op{Wt.p + static_cast<int64_t>(E) * Wt.ld, Wt.ld},
+  GG_TRY(e.linear(ln, R * B, E, E, Op{t.pv, E}, Wt, Epi().bias(bt).obf(t.qt, E)));
+  GG_TRY(e.linear(ln, B * T, 2 * E, E, Op{t.te, E}, Op{Wt.p + static_cast<int64_t>(E) * Wt.ld, Wt.ld},
                   Epi().bias(bt ? bt + E : nullptr).obf(t.kvt, 2 * E)));
   memset(&a, 0, sizeof(a));
   a.q = t.qt; a.ldq = E; a.q_mod = R * B;
@@ -450,7 +514,7 @@ static int tower_forward(gg_engine& e, int net, int R, float p, cudaStream_t st)
   a.o = t.at; a.ldo = E;
   GG_TRY(k_attention_fwd(a, st));
   // c = text vector + patch vector (:153-155)
-  GG_TRY(e.linear(st, R * B, E, E, Op{t.at, E}, e.W(net, GG_P_T2P_OUT_W),
+  GG_TRY(e.linear(ln, R * B, E, E, Op{t.at, E}, e.W(net, GG_P_T2P_OUT_W),
                   Epi().bias(e.P(net, GG_P_T2P_OUT_B)).res(t.pv, E).obf(t.c, E)));
   return GG_OK;
 }
@@ -458,16 +522,19 @@ static int tower_forward(gg_engine& e, int net, int R, float p, cudaStream_t st)
 static Op cond_vec(const gg_engine& e, int net) {
   const Tower& t = e.tw[net];
   if (e.paper) return Op{t.c, e.cfg.E};
-  return Op{t.X[e.cfg.n_layers], static_cast<int64_t>(e.S) * e.cfg.E};
+  return Op{t.X[e.cfg.n_layers], static_cast<int64_t>(e.S_) * e.cfg.E};
 }
 
 // ------------------------------------------------------------------------------ tower backward
 // dc: [Rg*B, E] gradient of the loss w.r.t. the conditioning vectors of the first Rg replicas.
-static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc, cudaStream_t st) {
+// The dependent chain (dgrads, attention / LayerNorm backward) runs on lane 0; every weight- and
+// bias-gradient reduction is forked onto the side lanes (e.wgrad / e.bgrad).
+static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc) {
   const gg_model_cfg& c = e.cfg;
   Tower& t = e.tw[net];
   GradScratch& g = e.gs;
-  const int B = c.B, S = e.S, E = c.E, F = e.F, P = c.P, T = c.T, Dp = c.Dp, Dt = c.Dt;
+  cudaStream_t st = e.S(0);
+  const int B = c.B, S = e.S_, E = c.E, F = e.F, P = c.P, T = c.T, Dp = c.Dp, Dt = c.Dt;
   const int n = Rg * B, rows = n * S;
   const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -480,9 +547,9 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     float* gbp = e.Gr(net, GG_P_P2T_IN_B);
     float* gbt = e.Gr(net, GG_P_T2P_IN_B);
     // c = at Wo_t^T + bo_t + pv
-    GG_TRY(e.wgrad(st, E, E, n, Op{dc, E}, Op{t.at, E}, e.Gr(net, GG_P_T2P_OUT_W), E));
-    GG_TRY(e.bgrad(st, dc, E, n, E, e.Gr(net, GG_P_T2P_OUT_B)));
-    GG_TRY(e.dgrad(st, n, E, E, Op{dc, E}, e.W(net, GG_P_T2P_OUT_W), Epi().obf(g.dat, E)));
+    GG_TRY(e.wgrad(E, E, n, Op{dc, E}, Op{t.at, E}, e.Gr(net, GG_P_T2P_OUT_W), E));
+    GG_TRY(e.bgrad(dc, E, n, E, e.Gr(net, GG_P_T2P_OUT_B)));
+    GG_TRY(e.dgrad(0, n, E, E, Op{dc, E}, e.W(net, GG_P_T2P_OUT_W), Epi().obf(g.dat, E)));
     AttnArgs a;
     memset(&a, 0, sizeof(a));
     a.q = t.qt; a.ldq = E; a.q_mod = n;
@@ -494,22 +561,22 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     a.stat = e.attn_stat;
     GG_TRY(k_attention_bwd(a, st));
     // qt = pv Wq_t^T + bq_t ; dp = dqt Wq_t + dc (residual path)
-    GG_TRY(e.wgrad(st, E, E, n, Op{g.dqt, E}, Op{t.pv, E}, gWt, E));
-    GG_TRY(e.bgrad(st, g.dqt, E, n, E, gbt));
-    GG_TRY(e.dgrad(st, n, E, E, Op{g.dqt, E}, Wt, Epi().res(dc, E).obf(g.dp, E)));
+    GG_TRY(e.wgrad(E, E, n, Op{g.dqt, E}, Op{t.pv, E}, gWt, E));
+    GG_TRY(e.bgrad(g.dqt, E, n, E, gbt));
+    GG_TRY(e.dgrad(0, n, E, E, Op{g.dqt, E}, Wt, Epi().res(dc, E).obf(g.dp, E)));
     // kvt = te Wkv_t^T + bkv_t (shared by the replicas)
     const bf16* dkvt = g.dkvt;
     if (Rg > 1) {
       GG_TRY(k_sum_replicas(g.dkvt, g.dkvt_sum, Rg, static_cast<int64_t>(B) * T * 2 * E, st));
       dkvt = g.dkvt_sum;
     }
-    GG_TRY(e.wgrad(st, 2 * E, E, B * T, Op{dkvt, 2 * E}, Op{t.te, E}, gWt + static_cast<int64_t>(E) * E, E));
-    GG_TRY(e.bgrad(st, dkvt, 2 * E, B * T, 2 * E, gbt ? gbt + E : nullptr));
-    GG_TRY(e.dgrad(st, B * T, E, 2 * E, Op{dkvt, 2 * E}, Wt_kv, Epi().obf(g.dte, E)));
+    GG_TRY(e.wgrad(2 * E, E, B * T, Op{dkvt, 2 * E}, Op{t.te, E}, gWt + static_cast<int64_t>(E) * E, E));
+    GG_TRY(e.bgrad(dkvt, 2 * E, B * T, 2 * E, gbt ? gbt + E : nullptr));
+    GG_TRY(e.dgrad(0, B * T, E, 2 * E, Op{dkvt, 2 * E}, Wt_kv, Epi().obf(g.dte, E)));
     // pv = ap Wo_p^T + bo_p
-    GG_TRY(e.wgrad(st, E, E, n, Op{g.dp, E}, Op{t.ap, E}, e.Gr(net, GG_P_P2T_OUT_W), E));
-    GG_TRY(e.bgrad(st, g.dp, E, n, E, e.Gr(net, GG_P_P2T_OUT_B)));
-    GG_TRY(e.dgrad(st, n, E, E, Op{g.dp, E}, e.W(net, GG_P_P2T_OUT_W), Epi().obf(g.dap, E)));
+    GG_TRY(e.wgrad(E, E, n, Op{g.dp, E}, Op{t.ap, E}, e.Gr(net, GG_P_P2T_OUT_W), E));
+    GG_TRY(e.bgrad(g.dp, E, n, E, e.Gr(net, GG_P_P2T_OUT_B)));
+    GG_TRY(e.dgrad(0, n, E, E, Op{g.dp, E}, e.W(net, GG_P_P2T_OUT_W), Epi().obf(g.dap, E)));
     memset(&a, 0, sizeof(a));
     a.q = t.qp; a.ldq = E; a.q_mod = B;
     a.k = t.kvp; a.v = t.kvp + E; a.ldkv = 2 * E; a.kv_mod = n;
@@ -525,44 +592,45 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
       GG_TRY(k_sum_replicas(g.dqp, g.dqp_sum, Rg, static_cast<int64_t>(B) * E, st));
       dqp = g.dqp_sum;
     }
-    GG_TRY(e.wgrad(st, E, E, B, Op{dqp, E}, Op{t.te, static_cast<int64_t>(T) * E}, gWp, E));
-    GG_TRY(e.bgrad(st, dqp, E, B, E, gbp));
-    GG_TRY(e.dgrad(st, B, E, E, Op{dqp, E}, Wp, Epi().obf(g.dte0, E)));
+    GG_TRY(e.wgrad(E, E, B, Op{dqp, E}, Op{t.te, static_cast<int64_t>(T) * E}, gWp, E));
+    GG_TRY(e.bgrad(dqp, E, B, E, gbp));
+    GG_TRY(e.dgrad(0, B, E, E, Op{dqp, E}, Wp, Epi().obf(g.dte0, E)));
     GG_TRY(k_scatter_add_rows(g.dte, g.dte0, B, T, E, st));
     // kvp = Xf Wkv_p^T + bkv_p
-    GG_TRY(e.wgrad(st, 2 * E, E, rows, Op{g.dkvp, 2 * E}, Op{Xf, E}, gWp + static_cast<int64_t>(E) * E, E));
-    GG_TRY(e.bgrad(st, g.dkvp, 2 * E, rows, 2 * E, gbp ? gbp + E : nullptr));
-    GG_TRY(e.dgrad(st, rows, E, 2 * E, Op{g.dkvp, 2 * E}, Wp_kv, Epi().obf(g.ga, E)));
+    GG_TRY(e.wgrad(2 * E, E, rows, Op{g.dkvp, 2 * E}, Op{Xf, E}, gWp + static_cast<int64_t>(E) * E, E));
+    GG_TRY(e.bgrad(g.dkvp, 2 * E, rows, 2 * E, gbp ? gbp + E : nullptr));
+    GG_TRY(e.dgrad(0, rows, E, 2 * E, Op{g.dkvp, 2 * E}, Wp_kv, Epi().obf(g.ga, E)));
     // text encoder
-    GG_TRY(e.wgrad(st, E, Dt, B * T, Op{g.dte, E}, Op{e.text, Dt}, e.Gr(net, GG_P_TEXT_W), Dt));
-    GG_TRY(e.bgrad(st, g.dte, E, B * T, E, e.Gr(net, GG_P_TEXT_B)));
+    GG_TRY(e.wgrad(E, Dt, B * T, Op{g.dte, E}, Op{e.text, Dt}, e.Gr(net, GG_P_TEXT_W), Dt));
+    GG_TRY(e.bgrad(g.dte, E, B * T, E, e.Gr(net, GG_P_TEXT_B)));
   } else {
     GG_TRY(k_scatter_cls(g.ga, dc, n, S, E, st));
   }
   for (int l = c.n_layers - 1; l >= 0; --l) {
     TowerLayer& L = t.L[l];
+    LayerGrads& lg = g.L[l];
     const int ls = GG_P_LAYER0 + GG_L_COUNT * l;
     const uint32_t site = site0 + 8u * l;
     // x_out = LN2(x1 + drop(ff))
-    GG_TRY(k_add_ln_bwd(g.ga, L.z2, L.mean2, L.rstd2, e.P(net, ls + GG_L_N2_W), g.gz, p > 0.f ? g.gy : nullptr,
+    GG_TRY(k_add_ln_bwd(g.ga, L.z2, L.mean2, L.rstd2, e.P(net, ls + GG_L_N2_W), lg.gz2, p > 0.f ? lg.gy2 : nullptr,
                         e.Gr(net, ls + GG_L_N2_W), e.Gr(net, ls + GG_L_N2_B), rows, E, p, e.rng, site + 3,
-                        e.scratch, st));
-    const bf16* dff = p > 0.f ? g.gy : g.gz;
-    GG_TRY(e.wgrad(st, E, F, rows, Op{dff, E}, Op{L.h, F}, e.Gr(net, ls + GG_L_FF2_W), F));
-    GG_TRY(e.bgrad(st, dff, E, rows, E, e.Gr(net, ls + GG_L_FF2_B)));
-    GG_TRY(e.dgrad(st, rows, F, E, Op{dff, E}, e.W(net, ls + GG_L_FF2_W),
-                   Epi().mask(L.h, F, keep_scale, 0.f).obf(g.gh, F)));
-    GG_TRY(e.wgrad(st, F, E, rows, Op{g.gh, F}, Op{L.x1, E}, e.Gr(net, ls + GG_L_FF1_W), E));
-    GG_TRY(e.bgrad(st, g.gh, F, rows, F, e.Gr(net, ls + GG_L_FF1_B)));
-    GG_TRY(e.dgrad(st, rows, E, F, Op{g.gh, F}, e.W(net, ls + GG_L_FF1_W), Epi().res(g.gz, E).obf(g.gb, E)));
+                        e.scratch_l[0], st));
+    const bf16* dff = p > 0.f ? lg.gy2 : lg.gz2;
+    GG_TRY(e.wgrad(E, F, rows, Op{dff, E}, Op{L.h, F}, e.Gr(net, ls + GG_L_FF2_W), F));
+    GG_TRY(e.bgrad(dff, E, rows, E, e.Gr(net, ls + GG_L_FF2_B)));
+    GG_TRY(e.dgrad(0, rows, F, E, Op{dff, E}, e.W(net, ls + GG_L_FF2_W),
+                   Epi().mask(L.h, F, keep_scale, 0.f).obf(lg.gh, F)));
+    GG_TRY(e.wgrad(F, E, rows, Op{lg.gh, F}, Op{L.x1, E}, e.Gr(net, ls + GG_L_FF1_W), E));
+    GG_TRY(e.bgrad(lg.gh, F, rows, F, e.Gr(net, ls + GG_L_FF1_B)));
+    GG_TRY(e.dgrad(0, rows, E, F, Op{lg.gh, F}, e.W(net, ls + GG_L_FF1_W), Epi().res(lg.gz2, E).obf(g.gb, E)));
     // x1 = LN1(x_in + drop(sa))
-    GG_TRY(k_add_ln_bwd(g.gb, L.z1, L.mean1, L.rstd1, e.P(net, ls + GG_L_N1_W), g.gz, p > 0.f ? g.gy : nullptr,
+    GG_TRY(k_add_ln_bwd(g.gb, L.z1, L.mean1, L.rstd1, e.P(net, ls + GG_L_N1_W), lg.gz1, p > 0.f ? lg.gy1 : nullptr,
                         e.Gr(net, ls + GG_L_N1_W), e.Gr(net, ls + GG_L_N1_B), rows, E, p, e.rng, site + 1,
-                        e.scratch, st));
-    const bf16* dsa = p > 0.f ? g.gy : g.gz;
-    GG_TRY(e.wgrad(st, E, E, rows, Op{dsa, E}, Op{L.ao, E}, e.Gr(net, ls + GG_L_OUT_W), E));
-    GG_TRY(e.bgrad(st, dsa, E, rows, E, e.Gr(net, ls + GG_L_OUT_B)));
-    GG_TRY(e.dgrad(st, rows, E, E, Op{dsa, E}, e.W(net, ls + GG_L_OUT_W), Epi().obf(g.gao, E)));
+                        e.scratch_l[0], st));
+    const bf16* dsa = p > 0.f ? lg.gy1 : lg.gz1;
+    GG_TRY(e.wgrad(E, E, rows, Op{dsa, E}, Op{L.ao, E}, e.Gr(net, ls + GG_L_OUT_W), E));
+    GG_TRY(e.bgrad(dsa, E, rows, E, e.Gr(net, ls + GG_L_OUT_B)));
+    GG_TRY(e.dgrad(0, rows, E, E, Op{dsa, E}, e.W(net, ls + GG_L_OUT_W), Epi().obf(g.gao, E)));
     AttnArgs a;
     memset(&a, 0, sizeof(a));
     a.q = L.qkv; a.ldq = 3 * E; a.q_mod = n;
@@ -570,68 +638,69 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     a.mask = e.mask_s; a.mask_mod = B;
     a.nb = n; a.H = c.n_heads; a.hd = e.hd; a.Lq = S; a.Lk = S;
     a.drop_p = p; a.rng = e.rng; a.site = site + 0;
-    a.dout = g.gao; a.lddo = E; a.dq = g.gqkv; a.lddq = 3 * E;
-    a.dk = g.gqkv + E; a.dv = g.gqkv + 2 * E; a.lddkv = 3 * E;
+    a.dout = g.gao; a.lddo = E; a.dq = lg.gqkv; a.lddq = 3 * E;
+    a.dk = lg.gqkv + E; a.dv = lg.gqkv + 2 * E; a.lddkv = 3 * E;
     a.stat = e.attn_stat;
     GG_TRY(k_attention_bwd(a, st));
-    GG_TRY(e.wgrad(st, 3 * E, E, rows, Op{g.gqkv, 3 * E}, Op{t.X[l], E}, e.Gr(net, ls + GG_L_IN_W), E));
-    GG_TRY(e.bgrad(st, g.gqkv, 3 * E, rows, 3 * E, e.Gr(net, ls + GG_L_IN_B)));
-    GG_TRY(e.dgrad(st, rows, E, 3 * E, Op{g.gqkv, 3 * E}, e.W(net, ls + GG_L_IN_W), Epi().res(g.gz, E).obf(g.ga, E)));
+    GG_TRY(e.wgrad(3 * E, E, rows, Op{lg.gqkv, 3 * E}, Op{t.X[l], E}, e.Gr(net, ls + GG_L_IN_W), E));
+    GG_TRY(e.bgrad(lg.gqkv, 3 * E, rows, 3 * E, e.Gr(net, ls + GG_L_IN_B)));
+    GG_TRY(e.dgrad(0, rows, E, 3 * E, Op{lg.gqkv, 3 * E}, e.W(net, ls + GG_L_IN_W), Epi().res(lg.gz1, E).obf(g.ga, E)));
   }
   // X0 = [cls | patch projections], replicas share the projections
-  GG_TRY(k_colsum(g.ga, 0, static_cast<int64_t>(S) * E, n, E, nullptr, 1.f, e.Gr(net, GG_P_CLS), 0, e.scratch, st));
+  GG_TRY(k_colsum(g.ga, 0, static_cast<int64_t>(S) * E, n, E, nullptr, 1.f, e.Gr(net, GG_P_CLS), 0, e.scratch_l[0], st));
   GG_TRY(k_unassemble_tokens(g.ga, g.dpe, nullptr, Rg, B, S, E, st));
-  GG_TRY(e.wgrad(st, E, Dp, B * P, Op{g.dpe, E}, Op{t.mod, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
-  GG_TRY(e.bgrad(st, g.dpe, E, B * P, E, e.Gr(net, GG_P_PATCH_B)));
-  GG_TRY(e.dgrad(st, B * P, Dp, E, Op{g.dpe, E}, e.W(net, GG_P_PATCH_W), Epi().obf(g.dmod, Dp)));
+  GG_TRY(e.wgrad(E, Dp, B * P, Op{g.dpe, E}, Op{t.mod, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
+  GG_TRY(e.bgrad(g.dpe, E, B * P, E, e.Gr(net, GG_P_PATCH_B)));
+  GG_TRY(e.dgrad(0, B * P, Dp, E, Op{g.dpe, E}, e.W(net, GG_P_PATCH_W), Epi().obf(g.dmod, Dp)));
   GG_TRY(k_film_bwd(g.dmod, e.patches, t.gb, g.dgb, B, P, Dp, st));
-  GG_TRY(e.wgrad(st, 2 * Dp, Dt, B, Op{g.dgb, 2 * Dp}, Op{e.text, static_cast<int64_t>(T) * Dt},
+  GG_TRY(e.wgrad(2 * Dp, Dt, B, Op{g.dgb, 2 * Dp}, Op{e.text, static_cast<int64_t>(T) * Dt},
                  e.Gr(net, GG_P_FILM_W), Dt));
-  GG_TRY(e.bgrad(st, g.dgb, 2 * Dp, B, 2 * Dp, e.Gr(net, GG_P_FILM_B)));
+  GG_TRY(e.bgrad(g.dgb, 2 * Dp, B, 2 * Dp, e.Gr(net, GG_P_FILM_B)));
   return GG_OK;
 }
 
 // --------------------------------------------------------------------------- generator forward
-static int gen_forward(gg_engine& e, const float* z, float p, float* out_f32, cudaStream_t st) {
+static int gen_forward(gg_engine& e, const float* z, float p, float* out_f32, int ln) {
   const gg_model_cfg& c = e.cfg;
   TrunkBufs& t = e.tb;
+  cudaStream_t st = e.S(ln);
   const int B = c.B, H = c.H, L = c.L, G = c.G, E = c.E;
   const int Lp = static_cast<int>(round_up64(L, 8));
   GG_TRY(k_cast_f32_bf16(z, L, e.zbf, Lp, B, L, st));
   const int net = GG_NET_GEN;
   Epi e1 = Epi().bias(e.P(net, GG_P_TR0_B)).act(GG_ACT_LEAKY, c.slope).obf(t.hg1, H);
   if (e.cond) {
-    GG_TRY(tower_forward(e, net, 1, p, st));
+    GG_TRY(tower_forward(e, net, 1, p, ln));
     const Op cv = cond_vec(e, net);
-    GG_TRY(e.mm(st, B, H, L, Op{e.zbf, Lp}, 0, e.W(net, GG_P_TR0_W), 0, e1, E, cv,
+    GG_TRY(e.mm(ln, B, H, L, Op{e.zbf, Lp}, 0, e.W(net, GG_P_TR0_W), 0, e1, E, cv,
                 Op{e.sh[net].tr0_c.p, e.sh[net].tr0_c.ld}));
   } else {
-    GG_TRY(e.linear(st, B, H, L, Op{e.zbf, Lp}, e.W(net, GG_P_TR0_W), e1));
+    GG_TRY(e.linear(ln, B, H, L, Op{e.zbf, Lp}, e.W(net, GG_P_TR0_W), e1));
   }
-  GG_TRY(e.linear(st, B, H, H, Op{t.hg1, H}, e.W(net, GG_P_TR1_W),
+  GG_TRY(e.linear(ln, B, H, H, Op{t.hg1, H}, e.W(net, GG_P_TR1_W),
                   Epi().bias(e.P(net, GG_P_TR1_B)).act(GG_ACT_LEAKY, c.slope).obf(t.hg2, H)));
   Epi ef = Epi().bias(e.P(net, GG_P_FIN_B)).obf(e.xfr, e.Gp);
   if (out_f32) ef.of32(out_f32, G);
-  GG_TRY(e.linear(st, B, G, H, Op{t.hg2, H}, e.W(net, GG_P_FIN_W), ef));
+  GG_TRY(e.linear(ln, B, G, H, Op{t.hg2, H}, e.W(net, GG_P_FIN_W), ef));
   return GG_OK;
 }
 
 // critic trunk forward on npass row groups; nx = number of gene matrices in xfr (1: fake, 2: fake+real)
-static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, int R, const float* alpha,
-                                cudaStream_t st) {
+static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, int R, const float* alpha) {
   const gg_model_cfg& c = e.cfg;
   TrunkBufs& t = e.tb;
+  cudaStream_t st = e.S(0);
   const int B = c.B, H = c.H, G = c.G, E = c.E, net = GG_NET_DISC;
-  GG_TRY(e.linear(st, nx * B, H, G, Op{x, e.Gp}, e.W(net, GG_P_TR0_W), Epi().of32(t.a1x, H)));
+  GG_TRY(e.linear(0, nx * B, H, G, Op{x, e.Gp}, e.W(net, GG_P_TR0_W), Epi().of32(t.a1x, H)));
   const float* a1c = nullptr;
   if (e.cond) {
     const Op cv = cond_vec(e, net);
-    GG_TRY(e.linear(st, R * B, H, E, cv, Op{e.sh[net].tr0_c.p, e.sh[net].tr0_c.ld},
+    GG_TRY(e.linear(0, R * B, H, E, cv, Op{e.sh[net].tr0_c.p, e.sh[net].tr0_c.ld},
                     Epi().bias(e.P(net, GG_P_TR0_B)).of32(t.a1c, H)));
     a1c = t.a1c;
   }
   GG_TRY(k_trunk1_combine(t.a1x, a1c, e.P(net, GG_P_TR0_B), alpha, t.h1, B, H, npass, R, c.slope, st));
-  GG_TRY(e.linear(st, npass * B, H, H, Op{t.h1, H}, e.W(net, GG_P_TR1_W),
+  GG_TRY(e.linear(0, npass * B, H, H, Op{t.h1, H}, e.W(net, GG_P_TR1_W),
                   Epi().bias(e.P(net, GG_P_TR1_B)).act(GG_ACT_LEAKY, c.slope).obf(t.h2, H).of32(t.h2f, H)));
   GG_TRY(k_rowdot_bias(t.h2f, e.P(net, GG_P_FIN_W), e.P(net, GG_P_FIN_B), t.score, npass * B, H, st));
   return GG_OK;
@@ -639,21 +708,27 @@ static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, 
 
 // Critic forward on [fake; real] + interpolated rows and the gradient-penalty value through the Gram
 // matrix of W1x. Leaves u2, u1, y, dv1, ru1, norms, pen and the loss stats behind.
-static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, cudaStream_t st) {
+// `fake_lane`: lane that is producing the fake rows of xfr (joined before the trunk reads them); the
+// critic tower (conditioning only) and the Gram matrix (weights only) do not wait for it.
+static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int fake_lane) {
   const gg_model_cfg& c = e.cfg;
   TrunkBufs& t = e.tb;
+  cudaStream_t st = e.S(0);
   const int B = c.B, H = c.H, G = c.G, net = GG_NET_DISC;
   const float inv_b = 1.f / static_cast<float>(B);
-  if (e.cond) GG_TRY(tower_forward(e, net, R, p, st));
-  GG_TRY(critic_trunk_forward(e, e.xfr, 2, 3, R, alpha, st));
   const Op W1x = e.W(net, GG_P_TR0_W), W2 = e.W(net, GG_P_TR1_W);
+  GG_TRY(e.fork(2));
+  GG_TRY(e.mm(2, H, H, G, W1x, 0, W1x, 0, Epi().of32(t.Mg, H).obf(t.Mgb, H)));
+  if (e.cond) GG_TRY(tower_forward(e, net, R, p, 0));
+  GG_TRY(e.join(fake_lane));
+  GG_TRY(critic_trunk_forward(e, e.xfr, 2, 3, R, alpha));
   const float* w3 = e.P(net, GG_P_FIN_W);
   const bf16* h1i = t.h1 + static_cast<int64_t>(2) * B * H;
   const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;
-  GG_TRY(e.mm(st, H, H, G, W1x, 0, W1x, 0, Epi().of32(t.Mg, H).obf(t.Mgb, H)));
   GG_TRY(k_gp_u2(h2i, w3, t.u2, B, H, c.slope, st));
-  GG_TRY(e.dgrad(st, B, H, H, Op{t.u2, H}, W2, Epi().mask(h1i, H, 1.f, c.slope).obf(t.u1b, H).of32(t.u1f, H)));
-  GG_TRY(e.linear(st, B, H, H, Op{t.u1b, H}, Op{t.Mgb, H}, Epi().of32(t.y, H)));
+  GG_TRY(e.dgrad(0, B, H, H, Op{t.u2, H}, W2, Epi().mask(h1i, H, 1.f, c.slope).obf(t.u1b, H).of32(t.u1f, H)));
+  GG_TRY(e.join(2));
+  GG_TRY(e.linear(0, B, H, H, Op{t.u1b, H}, Op{t.Mgb, H}, Epi().of32(t.y, H)));
   GG_TRY(k_gp_rows(t.y, t.u1f, h1i, t.norms, t.pen, t.ru1, t.dv1, B, H, c.slope, c.gp_weight, inv_b, st));
   GG_TRY(k_disc_losses(t.score, t.pen, e.stats, B, c.gp_weight, inv_b, st));
   return GG_OK;
@@ -696,6 +771,15 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
   }
   e->total_bytes = need;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->cur[0] = st;
+  {
+    const char* ml = getenv("GEMMGAN_LANES");
+    e->multi_lane = !(ml && ml[0] == '1' && ml[1] == 0);
+  }
+  for (int l = 1; l < gg_engine::NLANES; ++l)
+    GG_CUDA_CHECK(cudaStreamCreateWithFlags(&e->cur[l], cudaStreamNonBlocking));
+  for (int i = 0; i < gg_engine::NEVENTS; ++i)
+    GG_CUDA_CHECK(cudaEventCreateWithFlags(&e->evs[i], cudaEventDisableTiming));
   for (int n = 0; n < 2; ++n) {
     NetShadow& s = e->sh[n];
     if (!s.segs.empty())
@@ -714,7 +798,19 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
   return GG_OK;
 }
 
-extern "C" void gg_engine_destroy(gg_engine* e) { delete e; }
+extern "C" void gg_engine_destroy(gg_engine* e) {
+  if (!e) return;
+  for (int l = 1; l < gg_engine::NLANES; ++l)
+    if (e->cur[l]) cudaStreamDestroy(e->cur[l]);
+  for (int i = 0; i < gg_engine::NEVENTS; ++i) cudaEventDestroy(e->evs[i]);
+  delete e;
+}
+
+extern "C" int gg_engine_set_lanes(gg_engine* e, int enabled) {
+  GG_REQUIRE(e, "null engine");
+  e->multi_lane = enabled != 0;
+  return GG_OK;
+}
 
 extern "C" int gg_engine_refresh_shadows(gg_engine* e, int net, void* stream) {
   GG_REQUIRE(e && (net == 0 || net == 1), "bad argument");
@@ -737,7 +833,7 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
     if (patch_pad) {
       GG_TRY(k_mask_with_cls(patch_pad, e->mask_s, c.B, c.P, st));
     } else {
-      GG_CUDA_CHECK(cudaMemsetAsync(e->mask_s, 0, static_cast<size_t>(c.B) * e->S, st));
+      GG_CUDA_CHECK(cudaMemsetAsync(e->mask_s, 0, static_cast<size_t>(c.B) * e->S_, st));
     }
     e->has_tpad = text_pad != nullptr && e->paper;
     if (e->has_tpad)
@@ -748,7 +844,8 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
 
 extern "C" int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream) {
   GG_REQUIRE(e && z && alpha, "null argument");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->begin(stream);
+  cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
   TrunkBufs& t = e->tb;
   const int B = c.B, H = c.H, G = c.G, E = c.E, net = GG_NET_DISC;
@@ -757,50 +854,61 @@ extern "C" int gg_engine_disc_grads(gg_engine* e, const float* z, const float* a
   const int Rg = p > 0.f ? 2 : 1;  // replicas that carry gradient (the GP's tower gradient is zero)
   const float inv_b = 1.f / static_cast<float>(B);
   GG_TRY(k_bump_rng(e->rng, st));
-  // ---- forward: G(z) (no graph), D on fake / real / interpolated (:391-408), GP value (:351-374)
-  GG_TRY(gen_forward(*e, z, p, nullptr, st));
-  GG_TRY(disc_forward_gp(*e, R, p, alpha, st));
+  // ---- forward: G(z) (no graph) on lane 1 next to the critic tower on lane 0; D on fake / real /
+  // interpolated rows (:391-408), GP value (:351-374)
+  GG_TRY(e->fork(1));
+  GG_TRY(gen_forward(*e, z, p, nullptr, 1));
+  GG_TRY(disc_forward_gp(*e, R, p, alpha, 1));
   const Op W1x = e->W(net, GG_P_TR0_W), W2 = e->W(net, GG_P_TR1_W);
   const float* w3 = e->P(net, GG_P_FIN_W);
   const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;
-  GG_TRY(e->mm(st, H, H, B, Op{t.ru1, H}, 1, Op{t.u1b, H}, 1, Epi().obf(t.Qb, H)));
-  // du2 = dv1 W2^T, masked by m2 -> gradient of the GP w.r.t. w3
-  GG_TRY(e->linear(st, B, H, H, Op{t.dv1, H}, W2, Epi().mask(h2i, H, 1.f, c.slope).of32(t.du2f, H)));
-  // ---- backward of loss_real + loss_fake on the fake / real rows
-  GG_TRY(k_score_bwd(t.h2, w3, t.da2, t.roww, 2 * B, B, H, c.slope, +1.f, -1.f, inv_b, st));
   float* gw3 = e->Gr(net, GG_P_FIN_W);
-  GG_TRY(k_colsum(t.h2f, 1, H, 2 * B, H, t.roww, 1.f, gw3, 0, e->scratch, st));
-  GG_TRY(k_colsum(t.du2f, 1, H, B, H, nullptr, 1.f, gw3, 1, e->scratch, st));
-  GG_TRY(k_fill_f32(e->Gr(net, GG_P_FIN_B), 0.f, 1, st));  // d/db3 of mean(D(fake)) - mean(D(real)) is exactly 0
-  // dW2 = da2^T h1(fake,real)  +  u2^T dv1 (GP)
-  GG_TRY(e->mm(st, H, H, 2 * B, Op{t.da2, H}, 1, Op{t.h1, H}, 1, Epi().of32(e->Gr(net, GG_P_TR1_W), H), B,
-               Op{t.u2, H}, Op{t.dv1, H}));
-  GG_TRY(e->bgrad(st, t.da2, H, 2 * B, H, e->Gr(net, GG_P_TR1_B)));
-  GG_TRY(e->dgrad(st, 2 * B, H, H, Op{t.da2, H}, W2, Epi().mask(t.h1, H, 1.f, c.slope).obf(t.da1, H)));
-  GG_TRY(e->bgrad(st, t.da1, H, 2 * B, H, e->Gr(net, GG_P_TR0_B)));
-  // dW1[:, :G] = da1^T [fake; real]  +  Q W1x (GP, second K-segment)
+  // ---- the chain towards the tower backward first (lane 0): loss_real + loss_fake on the fake / real rows
+  GG_TRY(k_score_bwd(t.h2, w3, t.da2, t.roww, 2 * B, B, H, c.slope, +1.f, -1.f, inv_b, st));
+  GG_TRY(e->dgrad(0, 2 * B, H, H, Op{t.da2, H}, W2, Epi().mask(t.h1, H, 1.f, c.slope).obf(t.da1, H)));
   const int64_t ldw1 = static_cast<int64_t>(G) + (e->cond ? E : 0);
   float* gW1 = e->Gr(net, GG_P_TR0_W);
-  GG_TRY(e->mm(st, H, G, 2 * B, Op{t.da1, H}, 1, Op{e->xfr, e->Gp}, 1, Epi().of32(gW1, ldw1), H, Op{t.Qb, H}, W1x));
+  const Op da1_f{t.da1, H}, da1_r{t.da1 + static_cast<int64_t>(B) * H, H};
+  Op cv, W1c;
   if (e->cond) {
-    const Op cv = cond_vec(*e, net);
-    const Op W1c{e->sh[net].tr0_c.p, e->sh[net].tr0_c.ld};
-    const Op da1_f{t.da1, H}, da1_r{t.da1 + static_cast<int64_t>(B) * H, H};
+    cv = cond_vec(*e, net);
+    W1c = Op{e->sh[net].tr0_c.p, e->sh[net].tr0_c.ld};
     if (Rg == 2) {
-      GG_TRY(e->mm(st, H, E, 2 * B, da1_f, 1, cv, 1, Epi().of32(gW1 + G, ldw1)));
-      GG_TRY(e->dgrad(st, 2 * B, E, H, da1_f, W1c, Epi().obf(e->gs.dc, E)));
+      GG_TRY(e->dgrad(0, 2 * B, E, H, da1_f, W1c, Epi().obf(e->gs.dc, E)));
     } else {  // one shared tower pass: both row groups meet the same conditioning vectors
-      GG_TRY(e->mm(st, H, E, B, da1_f, 1, cv, 1, Epi().of32(gW1 + G, ldw1), B, da1_r, cv));
-      GG_TRY(e->mm(st, B, E, H, da1_f, 0, W1c, 1, Epi().obf(e->gs.dc, E), H, da1_r, W1c));
+      GG_TRY(e->mm(0, B, E, H, da1_f, 0, W1c, 1, Epi().obf(e->gs.dc, E), H, da1_r, W1c));
     }
-    GG_TRY(tower_backward(*e, net, Rg, p, e->gs.dc, st));
   }
-  return GG_OK;
+  // ---- everything that only feeds the optimizer goes to lane 1 (GEMMs) / lane 2 (column sums)
+  GG_TRY(e->fork(1));
+  // GP: Q = (r u1)^T u1 ; du2 = dv1 W2^T masked by m2 -> gradient of the GP w.r.t. w3
+  GG_TRY(e->mm(1, H, H, B, Op{t.ru1, H}, 1, Op{t.u1b, H}, 1, Epi().obf(t.Qb, H)));
+  GG_TRY(e->linear(1, B, H, H, Op{t.dv1, H}, W2, Epi().mask(h2i, H, 1.f, c.slope).of32(t.du2f, H)));
+  GG_TRY(k_colsum(t.h2f, 1, H, 2 * B, H, t.roww, 1.f, gw3, 0, e->scratch_l[e->L(1)], e->S(1)));
+  GG_TRY(k_colsum(t.du2f, 1, H, B, H, nullptr, 1.f, gw3, 1, e->scratch_l[e->L(1)], e->S(1)));
+  GG_TRY(k_fill_f32(e->Gr(net, GG_P_FIN_B), 0.f, 1, e->S(1)));  // d/db3 of mean(D(fake)) - mean(D(real)) is exactly 0
+  // dW2 = da2^T h1(fake,real)  +  u2^T dv1 (GP)
+  GG_TRY(e->mm(1, H, H, 2 * B, Op{t.da2, H}, 1, Op{t.h1, H}, 1, Epi().of32(e->Gr(net, GG_P_TR1_W), H), B,
+               Op{t.u2, H}, Op{t.dv1, H}));
+  // dW1[:, :G] = da1^T [fake; real]  +  Q W1x (GP, second K-segment)
+  GG_TRY(e->mm(1, H, G, 2 * B, Op{t.da1, H}, 1, Op{e->xfr, e->Gp}, 1, Epi().of32(gW1, ldw1), H, Op{t.Qb, H}, W1x));
+  if (e->cond) {
+    if (Rg == 2) {
+      GG_TRY(e->mm(1, H, E, 2 * B, da1_f, 1, cv, 1, Epi().of32(gW1 + G, ldw1)));
+    } else {
+      GG_TRY(e->mm(1, H, E, B, da1_f, 1, cv, 1, Epi().of32(gW1 + G, ldw1), B, da1_r, cv));
+    }
+  }
+  GG_TRY(e->bgrad(t.da2, H, 2 * B, H, e->Gr(net, GG_P_TR1_B)));
+  GG_TRY(e->bgrad(t.da1, H, 2 * B, H, e->Gr(net, GG_P_TR0_B)));
+  if (e->cond) GG_TRY(tower_backward(*e, net, Rg, p, e->gs.dc));
+  return e->join_all();
 }
 
 extern "C" int gg_engine_gen_grads(gg_engine* e, const float* z, int training, void* stream) {
   GG_REQUIRE(e && z, "null argument");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->begin(stream);
+  cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
   TrunkBufs& t = e->tb;
   const int B = c.B, H = c.H, G = c.G, E = c.E, L = c.L;
@@ -809,48 +917,55 @@ extern "C" int gg_engine_gen_grads(gg_engine* e, const float* z, int training, v
   const float inv_b = 1.f / static_cast<float>(B);
   const int D = GG_NET_DISC, Gn = GG_NET_GEN;
   GG_TRY(k_bump_rng(e->rng, st));
-  // ---- forward: fake = G(z), D(fake) (:441-452)
-  GG_TRY(gen_forward(*e, z, p, nullptr, st));
-  if (e->cond) GG_TRY(tower_forward(*e, D, 1, p, st));
-  GG_TRY(critic_trunk_forward(*e, e->xfr, 1, 1, 1, nullptr, st));
+  // ---- forward: fake = G(z) on lane 0, the critic's tower (conditioning only) next to it on lane 1,
+  // then D(fake) (:441-452)
+  if (e->cond) {
+    GG_TRY(e->fork(1));
+    GG_TRY(tower_forward(*e, D, 1, p, 1));
+  }
+  GG_TRY(gen_forward(*e, z, p, nullptr, 0));
+  GG_TRY(e->join(1));
+  GG_TRY(critic_trunk_forward(*e, e->xfr, 1, 1, 1, nullptr));
   GG_TRY(k_gen_loss(t.score, e->stats, B, inv_b, st));
   // ---- critic trunk input gradient (critic weights frozen, its tower is not on G's path)
   const Op W1x = e->W(D, GG_P_TR0_W), W2 = e->W(D, GG_P_TR1_W);
   GG_TRY(k_score_bwd(t.h2, e->P(D, GG_P_FIN_W), t.da2, nullptr, B, B, H, c.slope, -1.f, -1.f, inv_b, st));
-  GG_TRY(e->dgrad(st, B, H, H, Op{t.da2, H}, W2, Epi().mask(t.h1, H, 1.f, c.slope).obf(t.da1, H)));
-  GG_TRY(e->dgrad(st, B, G, H, Op{t.da1, H}, W1x, Epi().obf(t.dfake, e->Gp)));
+  GG_TRY(e->dgrad(0, B, H, H, Op{t.da2, H}, W2, Epi().mask(t.h1, H, 1.f, c.slope).obf(t.da1, H)));
+  GG_TRY(e->dgrad(0, B, G, H, Op{t.da1, H}, W1x, Epi().obf(t.dfake, e->Gp)));
   // ---- generator trunk backward
-  const Op Wf = e->W(Gn, GG_P_FIN_W), Wg2 = e->W(Gn, GG_P_TR1_W), Wg1 = e->W(Gn, GG_P_TR0_W);
-  GG_TRY(e->wgrad(st, G, H, B, Op{t.dfake, e->Gp}, Op{t.hg2, H}, e->Gr(Gn, GG_P_FIN_W), H));
-  GG_TRY(e->bgrad(st, t.dfake, e->Gp, B, G, e->Gr(Gn, GG_P_FIN_B)));
-  GG_TRY(e->dgrad(st, B, H, G, Op{t.dfake, e->Gp}, Wf, Epi().mask(t.hg2, H, 1.f, c.slope).obf(t.dag2, H)));
-  GG_TRY(e->wgrad(st, H, H, B, Op{t.dag2, H}, Op{t.hg1, H}, e->Gr(Gn, GG_P_TR1_W), H));
-  GG_TRY(e->bgrad(st, t.dag2, H, B, H, e->Gr(Gn, GG_P_TR1_B)));
-  GG_TRY(e->dgrad(st, B, H, H, Op{t.dag2, H}, Wg2, Epi().mask(t.hg1, H, 1.f, c.slope).obf(t.dag1, H)));
+  const Op Wf = e->W(Gn, GG_P_FIN_W), Wg2 = e->W(Gn, GG_P_TR1_W);
+  GG_TRY(e->wgrad(G, H, B, Op{t.dfake, e->Gp}, Op{t.hg2, H}, e->Gr(Gn, GG_P_FIN_W), H));
+  GG_TRY(e->bgrad(t.dfake, e->Gp, B, G, e->Gr(Gn, GG_P_FIN_B)));
+  GG_TRY(e->dgrad(0, B, H, G, Op{t.dfake, e->Gp}, Wf, Epi().mask(t.hg2, H, 1.f, c.slope).obf(t.dag2, H)));
+  GG_TRY(e->wgrad(H, H, B, Op{t.dag2, H}, Op{t.hg1, H}, e->Gr(Gn, GG_P_TR1_W), H));
+  GG_TRY(e->bgrad(t.dag2, H, B, H, e->Gr(Gn, GG_P_TR1_B)));
+  GG_TRY(e->dgrad(0, B, H, H, Op{t.dag2, H}, Wg2, Epi().mask(t.hg1, H, 1.f, c.slope).obf(t.dag1, H)));
   const int64_t ldw = static_cast<int64_t>(L) + (e->cond ? E : 0);
   float* gW1 = e->Gr(Gn, GG_P_TR0_W);
-  GG_TRY(e->wgrad(st, H, L, B, Op{t.dag1, H}, Op{e->zbf, Lp}, gW1, ldw));
-  GG_TRY(e->bgrad(st, t.dag1, H, B, H, e->Gr(Gn, GG_P_TR0_B)));
-  (void)Wg1;
+  if (e->cond) {
+    const Op Wc{e->sh[Gn].tr0_c.p, e->sh[Gn].tr0_c.ld};
+    GG_TRY(e->dgrad(0, B, E, H, Op{t.dag1, H}, Wc, Epi().obf(e->gs.dc, E)));
+  }
+  GG_TRY(e->wgrad(H, L, B, Op{t.dag1, H}, Op{e->zbf, Lp}, gW1, ldw));
+  GG_TRY(e->bgrad(t.dag1, H, B, H, e->Gr(Gn, GG_P_TR0_B)));
   if (e->cond) {
     const Op cv = cond_vec(*e, Gn);
-    const Op Wc{e->sh[Gn].tr0_c.p, e->sh[Gn].tr0_c.ld};
-    GG_TRY(e->mm(st, H, E, B, Op{t.dag1, H}, 1, cv, 1, Epi().of32(gW1 + L, ldw)));
-    GG_TRY(e->dgrad(st, B, E, H, Op{t.dag1, H}, Wc, Epi().obf(e->gs.dc, E)));
-    GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc, st));
+    GG_TRY(e->wgrad(H, E, B, Op{t.dag1, H}, cv, gW1 + L, ldw));
+    GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc));
   }
-  return GG_OK;
+  return e->join_all();
 }
 
 extern "C" int gg_engine_optim_step(gg_engine* e, int net, float lr, void* stream) {
   GG_REQUIRE(e && (net == 0 || net == 1), "bad argument");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->begin(stream);
+  cudaStream_t st = e->S(0);
   const gg_net_buffers& nb = e->nets[net];
   const float max_norm = net == GG_NET_DISC ? e->cfg.clip_d : e->cfg.clip_g;
   const float* coef = nullptr;
   float* statp = e->stats + (net == GG_NET_DISC ? GG_STAT_D_GRAD_NORM : GG_STAT_G_GRAD_NORM);
   if (max_norm > 0.f) {
-    GG_TRY(k_grad_norm_clip(nb.grads, nb.n_used, max_norm, statp, e->scratch, st));
+    GG_TRY(k_grad_norm_clip(nb.grads, nb.n_used, max_norm, statp, e->scratch_l[0], st));
     coef = statp + 1;
   }
   GG_TRY(k_optim_step(e->cfg.optimizer, nb.params, nb.grads, nb.exp_avg, nb.exp_avg_sq, nb.n_used, lr, coef,
@@ -860,21 +975,22 @@ extern "C" int gg_engine_optim_step(gg_engine* e, int net, float lr, void* strea
 
 extern "C" int gg_engine_generate(gg_engine* e, const float* z, float* out_f32, int training, void* stream) {
   GG_REQUIRE(e && z && out_f32, "null argument");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->begin(stream);
   const float p = (training && e->cond) ? e->cfg.dropout_p : 0.f;
-  if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
-  return gen_forward(*e, z, p, out_f32, st);
+  if (p > 0.f) GG_TRY(k_bump_rng(e->rng, e->S(0)));
+  return gen_forward(*e, z, p, out_f32, 0);
 }
 
 extern "C" int gg_engine_critic(gg_engine* e, const float* genes_f32, float* score_f32, int training, void* stream) {
   GG_REQUIRE(e && genes_f32 && score_f32, "null argument");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->begin(stream);
+  cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
   const float p = (training && e->cond) ? c.dropout_p : 0.f;
   if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
   GG_TRY(k_cast_f32_bf16(genes_f32, c.G, e->xin, e->Gp, c.B, c.G, st));
-  if (e->cond) GG_TRY(tower_forward(*e, GG_NET_DISC, 1, p, st));
-  GG_TRY(critic_trunk_forward(*e, e->xin, 1, 1, 1, nullptr, st));
+  if (e->cond) GG_TRY(tower_forward(*e, GG_NET_DISC, 1, p, 0));
+  GG_TRY(critic_trunk_forward(*e, e->xin, 1, 1, 1, nullptr));
   GG_CUDA_CHECK(cudaMemcpyAsync(score_f32, e->tb.score, sizeof(float) * c.B, cudaMemcpyDeviceToDevice, st));
   return GG_OK;
 }
@@ -882,14 +998,16 @@ extern "C" int gg_engine_critic(gg_engine* e, const float* genes_f32, float* sco
 extern "C" int gg_engine_gradient_penalty(gg_engine* e, const float* real_f32, const float* fake_f32,
                                           const float* alpha, int training, float* gp_out, void* stream) {
   GG_REQUIRE(e && fake_f32 && alpha && gp_out, "null argument");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  e->begin(stream);
+  cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
   const float p = (training && e->cond) ? c.dropout_p : 0.f;
   if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
   GG_TRY(k_cast_f32_bf16(fake_f32, c.G, e->xfr, e->Gp, c.B, c.G, st));
   if (real_f32)
     GG_TRY(k_cast_f32_bf16(real_f32, c.G, e->xfr + static_cast<int64_t>(c.B) * e->Gp, e->Gp, c.B, c.G, st));
-  GG_TRY(disc_forward_gp(*e, p > 0.f ? 3 : 1, p, alpha, st));
+  GG_TRY(disc_forward_gp(*e, p > 0.f ? 3 : 1, p, alpha, 0));
+  GG_TRY(e->join_all());
   GG_CUDA_CHECK(cudaMemcpyAsync(gp_out, e->stats + GG_STAT_GP, sizeof(float), cudaMemcpyDeviceToDevice, st));
   return GG_OK;
 }
@@ -928,8 +1046,8 @@ extern "C" void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows,
     const Op cv = cond_vec(*e, net);
     p = const_cast<bf16*>(cv.p); r = static_cast<int64_t>(e->tw[net].Rmax) * c.B; cc = c.E; l = cv.ld;
   } else if (e->cond && s == "film_gb_disc") { p = e->tw[GG_NET_DISC].gb; r = c.B; cc = 2 * c.Dp; l = 2 * c.Dp; f = 1; }
-  else if (e->cond && s == "tokens_disc") { p = e->tw[GG_NET_DISC].X[c.n_layers]; r = static_cast<int64_t>(e->tw[GG_NET_DISC].Rmax) * c.B * e->S; cc = c.E; l = c.E; }
-  else if (e->cond && s == "tokens0_disc") { p = e->tw[GG_NET_DISC].X[0]; r = static_cast<int64_t>(e->tw[GG_NET_DISC].Rmax) * c.B * e->S; cc = c.E; l = c.E; }
+  else if (e->cond && s == "tokens_disc") { p = e->tw[GG_NET_DISC].X[c.n_layers]; r = static_cast<int64_t>(e->tw[GG_NET_DISC].Rmax) * c.B * e->S_; cc = c.E; l = c.E; }
+  else if (e->cond && s == "tokens0_disc") { p = e->tw[GG_NET_DISC].X[0]; r = static_cast<int64_t>(e->tw[GG_NET_DISC].Rmax) * c.B * e->S_; cc = c.E; l = c.E; }
   if (rows) *rows = r;
   if (cols) *cols = cc;
   if (ld) *ld = l;

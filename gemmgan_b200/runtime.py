@@ -172,6 +172,11 @@ class Engine:
         return torch.as_strided(flat, (rows.value, cols.value), (ld.value, 1))
 
     # ---- thin wrappers ---------------------------------------------------------------------
+    def set_lanes(self, enabled: bool) -> None:
+        """Side-stream concurrency inside the entry points (see gg_engine_set_lanes); drops captured graphs."""
+        _lib.check(self.lib.gg_engine_set_lanes(self.handle, int(enabled)))
+        self.graphs.clear()
+
     def refresh_shadows(self, net: Optional[int] = None) -> None:
         for n in ((A.NET_GEN, A.NET_DISC) if net is None else (net,)):
             _lib.check(self.lib.gg_engine_refresh_shadows(self.handle, n, _stream()))

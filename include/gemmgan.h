@@ -201,6 +201,11 @@ int gg_engine_workspace_bytes(const gg_model_cfg* cfg, int64_t* bytes);
 int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* gen, const gg_net_buffers* disc,
                      void* workspace, int64_t workspace_bytes, void* stream, gg_engine** out);
 void gg_engine_destroy(gg_engine* e);
+/* Concurrency inside one entry point: enabled != 0 (default) forks work nothing on the dependent chain waits
+ * for (weight / bias gradients, the generator forward next to the critic tower) onto engine-owned side streams
+ * and joins them before returning; 0 keeps every kernel on the caller's stream (profiling, debugging). The
+ * setting must not change between capture and replay of a CUDA graph. */
+int gg_engine_set_lanes(gg_engine* e, int enabled);
 /* fp32 master weights -> bf16 shadows (call after any external change of `params`). */
 int gg_engine_refresh_shadows(gg_engine* e, int net, void* stream);
 /* Stages one batch (the dataloader tuple, already on the device, fp32 / uint8 masks):
