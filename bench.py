@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (diagnostics only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gemm-csv", default="", help="write per-launch GEMM shapes / durations of one train() here")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -256,6 +257,9 @@ def main():
     t.train(*batch_dev)
     ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
     _lib.check(L.gg_gemm_profile_end(C.byref(ms), C.byref(fl), C.byref(nl)))
+    if args.gemm_csv and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.gemm_csv)), exist_ok=True)
+        _lib.check(L.gg_gemm_profile_dump(args.gemm_csv.encode()))
     t.use_cuda_graphs = graphs_on
     for eng in t._engines.values():
         eng.set_lanes(True)

@@ -44,6 +44,15 @@ class NetBuffers(C.Structure):
     ]
 
 
+class WgradItem(C.Structure):
+    _fields_ = [("dy", C.c_void_p), ("ld_dy", C.c_int64), ("x", C.c_void_p), ("ld_x", C.c_int64),
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("out", C.c_void_p), ("ld", C.c_int64)]
+
+
+class ColsumItem(C.Structure):
+    _fields_ = [("inp", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int64), ("N", C.c_int32), ("out", C.c_void_p)]
+
+
 def declare(L: C.CDLL) -> None:
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     L.gg_engine_workspace_bytes.argtypes = [C.POINTER(ModelCfg), C.POINTER(i64)]
@@ -56,6 +65,8 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_set_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.gg_engine_disc_grads.argtypes = [vp, vp, vp, i32, vp]
     L.gg_engine_gen_grads.argtypes = [vp, vp, i32, vp]
+    L.gg_engine_disc_grads_phase.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.gg_engine_gen_grads_phase.argtypes = [vp, vp, i32, i32, vp]
     L.gg_engine_optim_step.argtypes = [vp, i32, f32, vp]
     L.gg_engine_generate.argtypes = [vp, vp, vp, i32, vp]
     L.gg_engine_critic.argtypes = [vp, vp, vp, i32, vp]
@@ -65,18 +76,26 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_buffer.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.gg_engine_buffer.restype = vp
     L.gg_optim_step.argtypes = [i32, vp, vp, vp, vp, i64, f32, f32, vp, vp, vp, vp]
+    L.gg_wgrad_group_workspace_bytes.argtypes = [i64]
+    L.gg_wgrad_group_workspace_bytes.restype = i64
+    L.gg_wgrad_group.argtypes = [C.POINTER(WgradItem), i32, vp, i64, vp]
+    L.gg_colsum_group_workspace_bytes.argtypes = [i64]
+    L.gg_colsum_group_workspace_bytes.restype = i64
+    L.gg_colsum_group.argtypes = [C.POINTER(ColsumItem), i32, vp, i64, vp]
     L.gg_launch_count.argtypes = [i32]
     L.gg_launch_count.restype = C.c_longlong
     L.gg_launch_count_add.argtypes = [C.c_longlong]
     L.gg_launch_count_add.restype = None
     L.gg_gemm_profile_begin.argtypes = []
+    L.gg_gemm_profile_dump.argtypes = [C.c_char_p]
     L.gg_gemm_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
 
 
 EXPORTS = [
     "gg_last_error", "gg_abi_version", "gg_check_device", "gg_gemm_bf16", "gg_engine_workspace_bytes",
     "gg_engine_create", "gg_engine_destroy", "gg_engine_set_lanes", "gg_engine_refresh_shadows", "gg_engine_set_batch",
-    "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_optim_step", "gg_engine_generate",
+    "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_disc_grads_phase", "gg_engine_gen_grads_phase", "gg_engine_optim_step", "gg_engine_generate",
     "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
-    "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end",
+    "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump",
+    "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

@@ -265,20 +265,47 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_kernel(const Att
 // at S = 9 (8 patch tokens + CLS) this keeps every lane busy, where one-CTA-per-(row, head) would idle.
 constexpr int SM_MAXL = 16;
 
+// DPT consecutive head dims of one row; runs of 8 use 16-byte accesses (row pitches and head offsets are
+// multiples of 8 elements whenever DPT is, and every base pointer is 16-byte aligned).
 template <int DPT>
 __device__ __forceinline__ void ld_slice(const bf16* p, float* v) {
+  if constexpr (DPT % 8 == 0) {
 #pragma unroll
-  for (int d = 0; d < DPT; d += 2) {
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + d));
-    v[d] = f.x;
-    v[d + 1] = f.y;
+    for (int d = 0; d < DPT; d += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + d));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        v[d + 2 * q] = f.x;
+        v[d + 2 * q + 1] = f.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DPT; d += 2) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + d));
+      v[d] = f.x;
+      v[d + 1] = f.y;
+    }
   }
 }
 template <int DPT>
 __device__ __forceinline__ void st_slice(bf16* p, const float* v, float scale) {
+  if constexpr (DPT % 8 == 0) {
 #pragma unroll
-  for (int d = 0; d < DPT; d += 2)
-    *reinterpret_cast<__nv_bfloat162*>(p + d) = __floats2bfloat162_rn(v[d] * scale, v[d + 1] * scale);
+    for (int d = 0; d < DPT; d += 8) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[d + 2 * q] * scale, v[d + 2 * q + 1] * scale);
+      *reinterpret_cast<uint4*>(p + d) = u;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DPT; d += 2)
+      *reinterpret_cast<__nv_bfloat162*>(p + d) = __floats2bfloat162_rn(v[d] * scale, v[d + 1] * scale);
+  }
 }
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -445,9 +472,18 @@ __global__ void __launch_bounds__(128) attn_small_kv_kernel(const AttnArgs a, co
   }
 }
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static bool small_path(const AttnArgs& a) {
   const int dpt = a.hd / 4;
-  return a.Lk <= SM_MAXL && a.hd % 8 == 0 && (dpt == 2 || dpt == 4 || dpt == 8 || dpt == 16);
+  if (!(a.Lk <= SM_MAXL && a.hd % 8 == 0 && (dpt == 2 || dpt == 4 || dpt == 8 || dpt == 16))) return false;
+  if (dpt % 8 == 0) {  // the 16-byte path needs aligned bases and pitches
+    const bool ok = a.ldq % 8 == 0 && a.ldkv % 8 == 0 && aligned16(a.q) && aligned16(a.k) && aligned16(a.v) &&
+                    (!a.o || (a.ldo % 8 == 0 && aligned16(a.o))) &&
+                    (!a.dout || (a.lddo % 8 == 0 && aligned16(a.dout) && a.lddq % 8 == 0 && aligned16(a.dq) &&
+                                 a.lddkv % 8 == 0 && aligned16(a.dk) && aligned16(a.dv)));
+    if (!ok) return false;
+  }
+  return true;
 }
 template <int MODE>
 static void launch_small_q(const AttnArgs& a, float* stat, cudaStream_t st) {

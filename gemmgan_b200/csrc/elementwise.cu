@@ -264,6 +264,154 @@ int k_colsum(const void* in, int in_f32, int64_t ld, int64_t rows, int N, const 
   return GG_OK;
 }
 
+// ------------------------------------------------------------------ grouped column sums
+// All bias gradients of one backward pass in one launch: problem p sums the rows of a bf16 matrix
+// [rows_p, N_p] (pitch ld_p) into out_p[N_p] (fp32). A work item is (problem, 64-column group, row chunk);
+// the chunk partials of a column group are summed in chunk order by the last CTA to arrive (fixed order =>
+// bit-reproducible, no float atomics). Thread = 8 consecutive columns (one 16-byte load per row), 32 row
+// lanes per CTA.
+struct ColsumGroupParams {
+  int nprob;
+  int total_work;
+  struct {
+    const bf16* in;
+    int64_t ld;
+    int rows, N;
+    int work0, ngroups, nchunks, rows_per_chunk;
+    float* out;
+    float* partial;      // [nchunks][N]
+    unsigned* counters;  // [ngroups]
+  } p[COLSUM_GROUP_MAX];
+};
+
+__global__ void __launch_bounds__(256) colsum_group_kernel(const __grid_constant__ ColsumGroupParams P) {
+  __shared__ float sm[32][65];
+  __shared__ unsigned last_flag;
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  for (int w = blockIdx.x; w < P.total_work; w += gridDim.x) {
+    int pi = 0;
+    while (pi + 1 < P.nprob && w >= P.p[pi + 1].work0) ++pi;
+    const auto& p = P.p[pi];
+    const int local = w - p.work0;
+    const int chunk = local / p.ngroups, grp = local % p.ngroups;
+    const int n0 = grp * 64 + cg * 8;
+    const int r0 = chunk * p.rows_per_chunk;
+    const int r1 = min(p.rows, r0 + p.rows_per_chunk);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const bool vec = (p.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) && n0 + 8 <= p.N;
+    if (vec) {
+      const bf16* base = p.in + n0;
+      int r = r0 + rl;
+      for (; r + 96 < r1; r += 128) {  // four independent 16-byte loads in flight per thread
+        uint4 u[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) u[t] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(r + 32 * t) * p.ld));
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[t]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(h[q]);
+            acc[2 * q] += f.x;
+            acc[2 * q + 1] += f.y;
+          }
+        }
+      }
+      for (; r < r1; r += 32) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(r) * p.ld));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(h[q]);
+          acc[2 * q] += f.x;
+          acc[2 * q + 1] += f.y;
+        }
+      }
+    } else {
+      for (int r = r0 + rl; r < r1; r += 32)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n0 + j < p.N) acc[j] += __bfloat162float(p.in[static_cast<int64_t>(r) * p.ld + n0 + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[rl][cg * 8 + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 32; ++y) t += sm[y][threadIdx.x];
+      const int n = grp * 64 + threadIdx.x;
+      if (n < p.N) {
+        if (p.nchunks == 1) p.out[n] = t;
+        else __stcg(p.partial + static_cast<int64_t>(chunk) * p.N + n, t);
+      }
+    }
+    if (p.nchunks > 1) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(p.counters + grp, 1u);
+        const bool last = prev == static_cast<unsigned>(p.nchunks - 1);
+        if (last) p.counters[grp] = 0;
+        last_flag = last ? 1u : 0u;
+        __threadfence();
+      }
+      __syncthreads();
+      if (last_flag && threadIdx.x < 64) {
+        const int n = grp * 64 + threadIdx.x;
+        if (n < p.N) {
+          float t = 0.f;
+          for (int c = 0; c < p.nchunks; ++c) t += __ldcg(p.partial + static_cast<int64_t>(c) * p.N + n);
+          p.out[n] = t;
+        }
+      }
+    }
+    __syncthreads();  // sm / last_flag are reused by the next work item
+  }
+}
+
+int64_t colsum_group_workspace_bytes(int64_t max_total_columns) {
+  return GROUP_COUNTER_BYTES + static_cast<int64_t>(COLSUM_GROUP_MAX_CHUNKS) * max_total_columns * 4 +
+         256LL * COLSUM_GROUP_MAX;
+}
+
+// The first GROUP_COUNTER_BYTES of `workspace` must be zero-initialised once (arrival counters).
+int k_colsum_group(const ColsumItem* items, int n, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (n <= 0) return GG_OK;
+  GG_REQUIRE(n <= COLSUM_GROUP_MAX, "too many grouped column sums (%d > %d)", n, COLSUM_GROUP_MAX);
+  static thread_local ColsumGroupParams P;
+  P.nprob = n;
+  int work = 0;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int64_t off = GROUP_COUNTER_BYTES, ctr_off = 0;
+  for (int i = 0; i < n; ++i) {
+    const ColsumItem& it = items[i];
+    GG_REQUIRE(it.in && it.out && it.rows > 0 && it.N > 0, "bad grouped column-sum item %d", i);
+    auto& p = P.p[i];
+    p.in = reinterpret_cast<const bf16*>(it.in); p.ld = it.ld; p.rows = static_cast<int>(it.rows); p.N = it.N; p.out = it.out;
+    p.ngroups = ceil_div(it.N, 64);
+    int nch = static_cast<int>((it.rows + 2047) / 2048);
+    if (nch > COLSUM_GROUP_MAX_CHUNKS) nch = COLSUM_GROUP_MAX_CHUNKS;
+    if (nch < 1) nch = 1;
+    p.nchunks = nch;
+    p.rows_per_chunk = static_cast<int>((it.rows + nch - 1) / nch);
+    p.work0 = work;
+    work += p.ngroups * nch;
+    p.partial = reinterpret_cast<float*>(ws + off);
+    if (nch > 1) off += round_up64(static_cast<int64_t>(nch) * it.N * 4, 256);
+    p.counters = reinterpret_cast<unsigned*>(ws + ctr_off);
+    ctr_off += static_cast<int64_t>(p.ngroups) * 4;
+    GG_REQUIRE(off <= workspace_bytes && ctr_off <= GROUP_COUNTER_BYTES, "grouped column-sum workspace too small");
+  }
+  P.total_work = work;
+  const unsigned grid = static_cast<unsigned>(work < 148 * 8 ? work : 148 * 8);
+  colsum_group_kernel<<<grid, 256, 0, st>>>(P);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 // ---------------------------------------------------------------------- trunk / GP glue
 __global__ void trunk1_combine_kernel(const float* __restrict__ a1x, const float* __restrict__ a1c,
                                       const float* __restrict__ b1, const float* __restrict__ alpha,

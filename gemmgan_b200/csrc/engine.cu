@@ -204,15 +204,45 @@ struct gg_engine {
   // Weight / bias gradients feed nothing but the optimizer: they run on side lanes, ordered after
   // everything lane 0 has enqueued so far (their operands), and are joined at the end of the entry point.
   // dW[out, in] = dY^T X, fp32 into the gradient buffer (pitch ldw)
+  // They are queued and launched as ONE grouped GEMM / ONE grouped column-sum kernel per flush_grads().
   int wgrad(int rows_out, int in, int rows, Op dY, Op X, float* dW, int64_t ldw) {
-    GG_TRY(fork(1));
-    return mm(1, rows_out, in, rows, dY, 1, X, 1, Epi().of32(dW, ldw));
+    if (!group_grads || cfg.gemm_impl != GG_IMPL_TCGEN05 || wq.size() >= WGRAD_GROUP_MAX) {
+      GG_TRY(fork(1));
+      return mm(1, rows_out, in, rows, dY, 1, X, 1, Epi().of32(dW, ldw));
+    }
+    wq.push_back(WgradItem{dY.p, dY.ld, X.p, X.ld, rows_out, in, rows, dW, ldw});
+    return GG_OK;
   }
   int bgrad(const bf16* dY, int64_t ld, int64_t rows, int N, float* db) {
     if (!db) return GG_OK;
-    GG_TRY(fork(2));
-    return k_colsum(dY, 0, ld, rows, N, nullptr, 1.f, db, 0, scratch_l[L(2)], S(2));
+    if (!group_grads || bq.size() >= COLSUM_GROUP_MAX) {
+      GG_TRY(fork(2));
+      return k_colsum(dY, 0, ld, rows, N, nullptr, 1.f, db, 0, scratch_l[L(2)], S(2));
+    }
+    bq.push_back(ColsumItem{dY, ld, rows, N, db});
+    return GG_OK;
   }
+  // launches what has been queued: ordered after everything lane 0 has enqueued so far
+  int flush_grads() {
+    if (!wq.empty()) {
+      GG_TRY(fork(1));
+      GG_TRY(k_wgrad_group(wq.data(), static_cast<int>(wq.size()), wg_ws, wg_ws_bytes, S(1)));
+      wq.clear();
+    }
+    if (!bq.empty()) {
+      GG_TRY(fork(2));
+      GG_TRY(k_colsum_group(bq.data(), static_cast<int>(bq.size()), cs_ws, cs_ws_bytes, S(2)));
+      bq.clear();
+    }
+    return GG_OK;
+  }
+  std::vector<WgradItem> wq;
+  std::vector<ColsumItem> bq;
+  bool group_grads = true;
+  // one workspace per flush in flight: flushes of one entry point run back to back on their lane, so
+  // they rotate through GROUP_WS_SLOTS regions
+  void *wg_ws = nullptr, *cs_ws = nullptr;
+  int64_t wg_ws_bytes = 0, cs_ws_bytes = 0;
 };
 
 namespace gg {
@@ -402,6 +432,25 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
   int64_t scratch_floats = 64 * maxN;
   if (scratch_floats < 296 * 2 * E) scratch_floats = 296 * 2 * E;
   if (scratch_floats < 1024) scratch_floats = 1024;
+  {
+    int64_t max_elems = 0, max_cols = 0;
+    for (int net = 0; net < 2; ++net) {
+      int64_t elems = 0, cols = 0;
+      for (int slot = 0; slot < GG_NSLOTS; ++slot) {
+        int r, cc;
+        if (slot_matrix_shape(c, net, slot, &r, &cc)) {
+          elems += static_cast<int64_t>(r) * cc;
+          cols += 3LL * r;  // bias gradients are column sums of [rows, out] matrices (in_proj parts counted apart)
+        }
+      }
+      if (elems > max_elems) max_elems = elems;
+      if (cols > max_cols) max_cols = cols;
+    }
+    e.wg_ws_bytes = wgrad_group_workspace_bytes(max_elems);
+    e.cs_ws_bytes = colsum_group_workspace_bytes(max_cols);
+    e.wg_ws = ar.take<uint8_t>(e.wg_ws_bytes);
+    e.cs_ws = ar.take<uint8_t>(e.cs_ws_bytes);
+  }
   e.splitk_bytes = 96LL << 20;
   for (int l = 0; l < gg_engine::NLANES; ++l) {
     e.scratch_l[l] = ar.take<float>(scratch_floats);
@@ -603,6 +652,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     // text encoder
     GG_TRY(e.wgrad(E, Dt, B * T, Op{g.dte, E}, Op{e.text, Dt}, e.Gr(net, GG_P_TEXT_W), Dt));
     GG_TRY(e.bgrad(g.dte, E, B * T, E, e.Gr(net, GG_P_TEXT_B)));
+    GG_TRY(e.flush_grads());
   } else {
     GG_TRY(k_scatter_cls(g.ga, dc, n, S, E, st));
   }
@@ -645,6 +695,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     GG_TRY(e.wgrad(3 * E, E, rows, Op{lg.gqkv, 3 * E}, Op{t.X[l], E}, e.Gr(net, ls + GG_L_IN_W), E));
     GG_TRY(e.bgrad(lg.gqkv, 3 * E, rows, 3 * E, e.Gr(net, ls + GG_L_IN_B)));
     GG_TRY(e.dgrad(0, rows, E, 3 * E, Op{lg.gqkv, 3 * E}, e.W(net, ls + GG_L_IN_W), Epi().res(lg.gz1, E).obf(g.ga, E)));
+    GG_TRY(e.flush_grads());
   }
   // X0 = [cls | patch projections], replicas share the projections
   GG_TRY(k_colsum(g.ga, 0, static_cast<int64_t>(S) * E, n, E, nullptr, 1.f, e.Gr(net, GG_P_CLS), 0, e.scratch_l[0], st));
@@ -656,7 +707,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
   GG_TRY(e.wgrad(2 * Dp, Dt, B, Op{g.dgb, 2 * Dp}, Op{e.text, static_cast<int64_t>(T) * Dt},
                  e.Gr(net, GG_P_FILM_W), Dt));
   GG_TRY(e.bgrad(g.dgb, 2 * Dp, B, 2 * Dp, e.Gr(net, GG_P_FILM_B)));
-  return GG_OK;
+  return e.flush_grads();
 }
 
 // --------------------------------------------------------------------------- generator forward
@@ -775,6 +826,8 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
   {
     const char* ml = getenv("GEMMGAN_LANES");
     e->multi_lane = !(ml && ml[0] == '1' && ml[1] == 0);
+    const char* gr = getenv("GEMMGAN_GROUP_GRADS");
+    e->group_grads = !(gr && gr[0] == '0');
   }
   for (int l = 1; l < gg_engine::NLANES; ++l)
     GG_CUDA_CHECK(cudaStreamCreateWithFlags(&e->cur[l], cudaStreamNonBlocking));
@@ -787,6 +840,8 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
                                     cudaMemcpyHostToDevice, st));
   }
   GG_CUDA_CHECK(cudaStreamSynchronize(st));  // segs vectors stay alive, but keep create() simple and safe
+  GG_CUDA_CHECK(cudaMemsetAsync(e->wg_ws, 0, GROUP_COUNTER_BYTES, st));
+  GG_CUDA_CHECK(cudaMemsetAsync(e->cs_ws, 0, GROUP_COUNTER_BYTES, st));
   GG_CUDA_CHECK(cudaMemsetAsync(e->stats, 0, GG_STATS_COUNT * sizeof(float), st));
   GG_CUDA_CHECK(cudaMemsetAsync(e->opt_step[0], 0, 4 * sizeof(float), st));
   GG_CUDA_CHECK(cudaMemsetAsync(e->opt_step[1], 0, 4 * sizeof(float), st));
@@ -842,8 +897,10 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
   return GG_OK;
 }
 
-extern "C" int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream) {
+// phase 0: whole step; 1: forward + trunk backward (trunk gradients final on return); 2: tower backward
+static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int training, int phase, void* stream) {
   GG_REQUIRE(e && z && alpha, "null argument");
+  GG_REQUIRE(phase >= 0 && phase <= 2, "bad phase %d", phase);
   e->begin(stream);
   cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
@@ -853,6 +910,10 @@ extern "C" int gg_engine_disc_grads(gg_engine* e, const float* z, const float* a
   const int R = p > 0.f ? 3 : 1;   // independently-dropped tower passes: fake, real, interpolated
   const int Rg = p > 0.f ? 2 : 1;  // replicas that carry gradient (the GP's tower gradient is zero)
   const float inv_b = 1.f / static_cast<float>(B);
+  if (phase == 2) {
+    if (e->cond) GG_TRY(tower_backward(*e, net, Rg, p, e->gs.dc));
+    return e->join_all();
+  }
   GG_TRY(k_bump_rng(e->rng, st));
   // ---- forward: G(z) (no graph) on lane 1 next to the critic tower on lane 0; D on fake / real /
   // interpolated rows (:391-408), GP value (:351-374)
@@ -894,19 +955,30 @@ extern "C" int gg_engine_disc_grads(gg_engine* e, const float* z, const float* a
   GG_TRY(e->mm(1, H, G, 2 * B, Op{t.da1, H}, 1, Op{e->xfr, e->Gp}, 1, Epi().of32(gW1, ldw1), H, Op{t.Qb, H}, W1x));
   if (e->cond) {
     if (Rg == 2) {
-      GG_TRY(e->mm(1, H, E, 2 * B, da1_f, 1, cv, 1, Epi().of32(gW1 + G, ldw1)));
+      GG_TRY(e->wgrad(H, E, 2 * B, da1_f, cv, gW1 + G, ldw1));
     } else {
       GG_TRY(e->mm(1, H, E, B, da1_f, 1, cv, 1, Epi().of32(gW1 + G, ldw1), B, da1_r, cv));
     }
   }
   GG_TRY(e->bgrad(t.da2, H, 2 * B, H, e->Gr(net, GG_P_TR1_B)));
   GG_TRY(e->bgrad(t.da1, H, 2 * B, H, e->Gr(net, GG_P_TR0_B)));
-  if (e->cond) GG_TRY(tower_backward(*e, net, Rg, p, e->gs.dc));
+  GG_TRY(e->flush_grads());
+  if (phase == 0 && e->cond) GG_TRY(tower_backward(*e, net, Rg, p, e->gs.dc));
   return e->join_all();
 }
 
-extern "C" int gg_engine_gen_grads(gg_engine* e, const float* z, int training, void* stream) {
+extern "C" int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream) {
+  return disc_grads_impl(e, z, alpha, training, 0, stream);
+}
+extern "C" int gg_engine_disc_grads_phase(gg_engine* e, const float* z, const float* alpha, int training, int phase,
+                                          void* stream) {
+  GG_REQUIRE(phase == 1 || phase == 2, "phase must be 1 or 2");
+  return disc_grads_impl(e, z, alpha, training, phase, stream);
+}
+
+static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase, void* stream) {
   GG_REQUIRE(e && z, "null argument");
+  GG_REQUIRE(phase >= 0 && phase <= 2, "bad phase %d", phase);
   e->begin(stream);
   cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
@@ -916,6 +988,10 @@ extern "C" int gg_engine_gen_grads(gg_engine* e, const float* z, int training, v
   const float p = (training && e->cond) ? c.dropout_p : 0.f;
   const float inv_b = 1.f / static_cast<float>(B);
   const int D = GG_NET_DISC, Gn = GG_NET_GEN;
+  if (phase == 2) {
+    if (e->cond) GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc));
+    return e->join_all();
+  }
   GG_TRY(k_bump_rng(e->rng, st));
   // ---- forward: fake = G(z) on lane 0, the critic's tower (conditioning only) next to it on lane 1,
   // then D(fake) (:441-452)
@@ -951,9 +1027,18 @@ extern "C" int gg_engine_gen_grads(gg_engine* e, const float* z, int training, v
   if (e->cond) {
     const Op cv = cond_vec(*e, Gn);
     GG_TRY(e->wgrad(H, E, B, Op{t.dag1, H}, cv, gW1 + L, ldw));
-    GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc));
   }
+  GG_TRY(e->flush_grads());
+  if (e->cond && phase == 0) GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc));
   return e->join_all();
+}
+
+extern "C" int gg_engine_gen_grads(gg_engine* e, const float* z, int training, void* stream) {
+  return gen_grads_impl(e, z, training, 0, stream);
+}
+extern "C" int gg_engine_gen_grads_phase(gg_engine* e, const float* z, int training, int phase, void* stream) {
+  GG_REQUIRE(phase == 1 || phase == 2, "phase must be 1 or 2");
+  return gen_grads_impl(e, z, training, phase, stream);
 }
 
 extern "C" int gg_engine_optim_step(gg_engine* e, int net, float lr, void* stream) {
@@ -1053,6 +1138,23 @@ extern "C" void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows,
   if (ld) *ld = l;
   if (is_f32) *is_f32 = f;
   return p;
+}
+
+extern "C" int64_t gg_wgrad_group_workspace_bytes(int64_t sum_output_elems) {
+  return wgrad_group_workspace_bytes(sum_output_elems);
+}
+extern "C" int gg_wgrad_group(const gg_wgrad_item* items, int n, void* workspace, int64_t workspace_bytes,
+                              void* stream) {
+  GG_REQUIRE(items && workspace, "null argument");
+  return k_wgrad_group(items, n, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int64_t gg_colsum_group_workspace_bytes(int64_t sum_columns) {
+  return colsum_group_workspace_bytes(sum_columns);
+}
+extern "C" int gg_colsum_group(const gg_colsum_item* items, int n, void* workspace, int64_t workspace_bytes,
+                               void* stream) {
+  GG_REQUIRE(items && workspace, "null argument");
+  return k_colsum_group(items, n, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gg_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, float lr, float max_norm,

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
       }
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_read<0>();  // smem may go; the writes themselves drain before the grid completes
   }
 
   tc_fence_before_sync();
@@ -433,9 +433,13 @@ static int encode_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t 
 }
 
 // Optional live profiler: CUDA-event pairs around every tcgen05 GEMM launch (bench.py roofline leg).
+struct GemmRecord {
+  int M, N, K0, K1, bn, splits, a_mn, b_mn;
+};
 struct GemmProfile {
   bool on = false;
   std::vector<cudaEvent_t> ev;  // start/stop pairs
+  std::vector<GemmRecord> rec;  // one per pair
   size_t used = 0;
   double flops = 0.0;
   long long launches = 0;
@@ -474,6 +478,7 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
     g_prof.used += 2;
     g_prof.flops += 2.0 * args.M * args.N * (static_cast<double>(args.K0) + args.K1);
     g_prof.launches += 1;
+    g_prof.rec.push_back(GemmRecord{args.M, args.N, args.K0, args.K1, BN, args.splits, args.a_mn, args.b_mn});
     GG_CUDA_CHECK(cudaEventRecord(e0, stream));
   }
   gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
@@ -599,6 +604,7 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
 extern "C" int gg_gemm_profile_begin(void) {
   gg::g_prof.on = true;
   gg::g_prof.used = 0;
+  gg::g_prof.rec.clear();
   gg::g_prof.flops = 0.0;
   gg::g_prof.launches = 0;
   return GG_OK;
@@ -618,6 +624,25 @@ extern "C" int gg_gemm_profile_end(double* ms, double* flops, long long* launche
   if (ms) *ms = total;
   if (flops) *flops = g_prof.flops;
   if (launches) *launches = g_prof.launches;
+  return GG_OK;
+}
+
+// Writes one CSV line per GEMM launch of the last profiled region (call after gg_gemm_profile_end).
+extern "C" int gg_gemm_profile_dump(const char* path) {
+  using namespace gg;
+  GG_REQUIRE(path, "null path");
+  FILE* f = fopen(path, "w");
+  GG_REQUIRE(f, "cannot open %s", path);
+  fprintf(f, "idx,M,N,K0,K1,block_n,splits,a_mn,b_mn,us,tflops\n");
+  for (size_t i = 0; i + 1 < g_prof.used && i / 2 < g_prof.rec.size(); i += 2) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]) != cudaSuccess) t = 0.f;
+    const GemmRecord& r = g_prof.rec[i / 2];
+    const double fl = 2.0 * r.M * r.N * (static_cast<double>(r.K0) + r.K1);
+    fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%d,%d,%.2f,%.1f\n", i / 2, r.M, r.N, r.K0, r.K1, r.bn, r.splits, r.a_mn,
+            r.b_mn, t * 1e3, t > 0.f ? fl / (t * 1e-3) / 1e12 : 0.0);
+  }
+  fclose(f);
   return GG_OK;
 }
 

@@ -42,6 +42,12 @@ extern std::atomic<long long> g_launch_count;  // kernels launched by this libra
     }                                    \
   } while (0)
 
+#define GG_TRY_RC(x)        \
+  do {                      \
+    int _rc = (x);          \
+    if (_rc) return _rc;    \
+  } while (0)
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 

@@ -37,6 +37,21 @@ int k_scatter_cls(bf16* dst, const bf16* src, int B, int S, int E, cudaStream_t 
 int k_colsum(const void* in, int in_f32, int64_t ld, int64_t rows, int N, const float* roww, float scale,
              float* out, int accumulate, float* scratch, cudaStream_t st);
 
+// All bias gradients of one backward pass in one launch (deterministic; see elementwise.cu).
+constexpr int COLSUM_GROUP_MAX = 40;
+constexpr int COLSUM_GROUP_MAX_CHUNKS = 16;
+typedef gg_colsum_item ColsumItem;
+constexpr int64_t GROUP_COUNTER_BYTES = 64 * 1024;  // zeroed arrival counters at the head of a group workspace
+int64_t colsum_group_workspace_bytes(int64_t max_total_columns);
+int k_colsum_group(const ColsumItem* items, int n, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+
+// ---- wgrad_group.cu: all single-segment weight gradients dW = dY^T X of one backward pass in one launch
+constexpr int WGRAD_GROUP_MAX = 32;
+constexpr int WGRAD_GROUP_MAX_SPLITS = 4;
+typedef gg_wgrad_item WgradItem;
+int64_t wgrad_group_workspace_bytes(int64_t max_output_elems);
+int k_wgrad_group(const WgradItem* items, int n, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+
 // ---- trunk / gradient-penalty glue (elementwise.cu) ------------------------------------------
 // First critic layer after the big GEMM. a1x [nx*B, H] fp32 holds x*W1x^T for the fake (and real) rows;
 // a1c [R*B, H] fp32 (or NULL) holds c*W1c^T; bias b1 [H]. Writes h1 [npass*B, H] bf16 =

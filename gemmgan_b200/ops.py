@@ -70,3 +70,44 @@ def gemm(
         d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     d.impl, d.force_splits, d.block_n = impl, splits, block_n
     _lib.check(L.gg_gemm_bf16(C.byref(d), _stream()))
+
+
+def wgrad_group(problems, workspace=None):
+    """problems: list of (dy [K, M] bf16, x [K, N] bf16, out [M, N] fp32). One launch (gg_wgrad_group)."""
+    from . import _abi_decl as A
+
+    L = _lib.lib()
+    n = len(problems)
+    items = (A.WgradItem * n)()
+    total = 0
+    for i, (dy, x, out) in enumerate(problems):
+        assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and out.dtype == torch.float32
+        assert dy.shape[0] == x.shape[0] and out.shape == (dy.shape[1], x.shape[1])
+        it = items[i]
+        it.dy, it.ld_dy, it.x, it.ld_x = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0)
+        it.M, it.N, it.K = dy.shape[1], x.shape[1], dy.shape[0]
+        it.out, it.ld = out.data_ptr(), out.stride(0)
+        total += it.M * it.N
+    if workspace is None:
+        workspace = torch.zeros(L.gg_wgrad_group_workspace_bytes(total), device=problems[0][0].device, dtype=torch.uint8)
+    _lib.check(L.gg_wgrad_group(items, n, _ptr(workspace), workspace.numel(), _stream()))
+    return workspace
+
+
+def colsum_group(problems, workspace=None):
+    """problems: list of (x [rows, N] bf16, out [N] fp32). One launch (gg_colsum_group)."""
+    from . import _abi_decl as A
+
+    L = _lib.lib()
+    n = len(problems)
+    items = (A.ColsumItem * n)()
+    total = 0
+    for i, (x, out) in enumerate(problems):
+        assert x.dtype == torch.bfloat16 and out.dtype == torch.float32 and out.numel() == x.shape[1]
+        it = items[i]
+        it.inp, it.ld, it.rows, it.N, it.out = x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr()
+        total += x.shape[1]
+    if workspace is None:
+        workspace = torch.zeros(L.gg_colsum_group_workspace_bytes(total), device=problems[0][0].device, dtype=torch.uint8)
+    _lib.check(L.gg_colsum_group(items, n, _ptr(workspace), workspace.numel(), _stream()))
+    return workspace

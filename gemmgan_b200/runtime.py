@@ -206,15 +206,23 @@ class Engine:
         self._keep = (g, p, t, pm, tm)  # keep alive until the enqueued casts have run
         _lib.check(self.lib.gg_engine_set_batch(self.handle, _ptr(g), _ptr(p), _ptr(pm), _ptr(t), _ptr(tm), _stream()))
 
-    def disc_grads(self, z: torch.Tensor, alpha: torch.Tensor, training: bool = True) -> None:
+    def disc_grads(self, z: torch.Tensor, alpha: torch.Tensor, training: bool = True, phase: int = 0) -> None:
+        """phase 0 = whole step; 1 = forward + trunk backward; 2 = tower backward (gg_engine_disc_grads_phase)."""
         z, alpha = self._f32(z), self._f32(alpha)
         assert z.shape == (self.B, self.L) and alpha.numel() == self.B
-        _lib.check(self.lib.gg_engine_disc_grads(self.handle, _ptr(z), _ptr(alpha), int(training), _stream()))
+        if phase == 0:
+            _lib.check(self.lib.gg_engine_disc_grads(self.handle, _ptr(z), _ptr(alpha), int(training), _stream()))
+        else:
+            _lib.check(self.lib.gg_engine_disc_grads_phase(self.handle, _ptr(z), _ptr(alpha), int(training), phase,
+                                                           _stream()))
 
-    def gen_grads(self, z: torch.Tensor, training: bool = True) -> None:
+    def gen_grads(self, z: torch.Tensor, training: bool = True, phase: int = 0) -> None:
         z = self._f32(z)
         assert z.shape == (self.B, self.L)
-        _lib.check(self.lib.gg_engine_gen_grads(self.handle, _ptr(z), int(training), _stream()))
+        if phase == 0:
+            _lib.check(self.lib.gg_engine_gen_grads(self.handle, _ptr(z), int(training), _stream()))
+        else:
+            _lib.check(self.lib.gg_engine_gen_grads_phase(self.handle, _ptr(z), int(training), phase, _stream()))
 
     def optim_step(self, net: int, lr: float) -> None:
         _lib.check(self.lib.gg_engine_optim_step(self.handle, net, float(lr), _stream()))

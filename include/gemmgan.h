@@ -116,6 +116,7 @@ long long gg_launch_count(int reset);
 void gg_launch_count_add(long long n); /* a replayed CUDA graph adds the launches it contains */
 int gg_gemm_profile_begin(void);
 int gg_gemm_profile_end(double* ms, double* flops, long long* launches);
+int gg_gemm_profile_dump(const char* csv_path); /* per-launch shapes and durations of the last region */
 
 /* -------------------------------------------------------- training engine --
  * One engine = one (generator, critic) pair of one model variant at a fixed per-rank batch
@@ -217,6 +218,13 @@ int gg_engine_set_batch(gg_engine* e, const float* genes, const float* patches, 
 int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream);
 /* train_gen minus optimizer: fills generator grads + stats. */
 int gg_engine_gen_grads(gg_engine* e, const float* z, int training, void* stream);
+/* The same steps in two halves, for data-parallel runs that overlap the gradient all-reduce with the rest of
+ * the backward: phase 1 = forward + trunk backward (on return every trunk gradient — slots GG_P_TR0_W ..
+ * GG_P_FIN_B, one contiguous range at the end of `grads` — is final), phase 2 = fusion-tower backward (the
+ * remaining slots). Phase 2 must follow phase 1 of the same step on the same stream. */
+int gg_engine_disc_grads_phase(gg_engine* e, const float* z, const float* alpha, int training, int phase,
+                               void* stream);
+int gg_engine_gen_grads_phase(gg_engine* e, const float* z, int training, int phase, void* stream);
 /* clip_grad_norm_ (if configured) + optimizer.step() on the flat buffers + shadow refresh.
  * In data-parallel runs the caller all-reduces `grads` between *_grads and this call. */
 int gg_engine_optim_step(gg_engine* e, int net, float lr, void* stream);
@@ -238,6 +246,29 @@ void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows, int64_t* c
  * Exposed for unit tests and micro-benchmarks; the engine calls the same code. */
 int gg_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, float lr, float max_norm,
                   float* step_count, float* norm_out2, float* scratch, void* stream);
+
+/* Grouped weight gradients: out_i[M_i, N_i] (fp32, pitch ld) = dY_i^T X_i for up to 32 problems in ONE launch
+ * (autograd's grad_output.t().mm(input) of every Linear of one backward pass, :412 / :455). dY_i is stored
+ * [K_i rows, M_i], X_i [K_i rows, N_i], both bf16 with 16-byte aligned bases and pitches that are multiples of
+ * 8. `workspace` (gg_wgrad_group_workspace_bytes(sum_i M_i*N_i) bytes) holds split-K partials behind 64 KiB of
+ * arrival counters; the counters must be zero before the first launch and every launch leaves them zero.
+ * Deterministic (partials are summed in split order). */
+typedef struct gg_wgrad_item {
+  const void* dy; int64_t ld_dy;
+  const void* x; int64_t ld_x;
+  int32_t M, N, K;
+  float* out; int64_t ld;
+} gg_wgrad_item;
+int64_t gg_wgrad_group_workspace_bytes(int64_t sum_output_elems);
+int gg_wgrad_group(const gg_wgrad_item* items, int n, void* workspace, int64_t workspace_bytes, void* stream);
+/* Grouped column sums: out_i[N_i] (fp32) = sum over the rows of in_i [rows_i, N_i] (bf16, pitch ld) for up to 40
+ * problems in ONE launch (every bias gradient of one backward pass). Same workspace / counter contract, sized by
+ * gg_colsum_group_workspace_bytes(sum_i N_i). Deterministic. */
+typedef struct gg_colsum_item {
+  const void* in; int64_t ld; int64_t rows; int32_t N; float* out;
+} gg_colsum_item;
+int64_t gg_colsum_group_workspace_bytes(int64_t sum_columns);
+int gg_colsum_group(const gg_colsum_item* items, int n, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

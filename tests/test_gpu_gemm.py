@@ -117,3 +117,56 @@ def test_gemm_dropout_matches_check_kernel(bn):
     keep = o1 != 0
     want = _ref(a, b, 0, 0) / 0.75
     assert (o1[keep] - want[keep]).abs().max().item() <= 1e-3 * want.abs().max().item()
+
+
+def test_wgrad_group_matches_reference_and_is_deterministic():
+    """All weight gradients of one backward pass in one launch (ragged shapes, K-splits, TMA and direct stores)."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    shapes = [  # K (rows), M (out), N (in), out pitch
+        (18432, 256, 512, 512), (18432, 512, 256, 256), (18432, 768, 256, 256), (9216, 256, 256, 256),
+        (1024, 2048, 768, 768), (2048, 256, 256, 19124), (1000, 200, 72, 75), (64, 128, 128, 128), (300, 40, 1000, 1000),
+    ]
+    probs, refs = [], []
+    for K, M, N, ld in shapes:
+        dy, x = _mk(K, M, g, scale=0.5), _mk(K, N, g, scale=0.5)
+        buf = torch.full((M, ld), 3.0, device="cuda", dtype=torch.float32)
+        probs.append((dy, x, buf[:, :N]))
+        refs.append(dy.float().t() @ x.float())
+    ws = ops.wgrad_group(probs)
+    torch.cuda.synchronize()
+    first = [p[2].clone() for p in probs]
+    for (dy, x, out), ref in zip(probs, refs):
+        assert (out - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-3, (dy.shape, x.shape)
+        buf = out._base if out._base is not None else out
+        if buf.shape[1] > out.shape[1]:
+            assert (buf[:, out.shape[1]:] == 3.0).all()
+    # replay with the same workspace (counters must have been left at zero) -> bit-identical results
+    for _ in range(3):
+        for p in probs:
+            p[2].fill_(-1.0)
+        ops.wgrad_group(probs, workspace=ws)
+        torch.cuda.synchronize()
+        for p, f in zip(probs, first):
+            assert torch.equal(p[2], f)
+
+
+def test_colsum_group_matches_reference_and_is_deterministic():
+    g = torch.Generator(device="cuda").manual_seed(22)
+    shapes = [(18432, 256), (18432, 768), (27648, 512), (1024, 2048), (1000, 203), (37, 64), (5000, 8), (2049, 100)]
+    probs, refs = [], []
+    for rows, N in shapes:
+        x = _mk(rows, N, g)
+        probs.append((x, torch.full((N,), 5.0, device="cuda", dtype=torch.float32)))
+        refs.append(x.double().sum(0))
+    ws = ops.colsum_group(probs)
+    torch.cuda.synchronize()
+    first = [p[1].clone() for p in probs]
+    for (x, out), ref in zip(probs, refs):
+        assert (out.double() - ref).abs().max().item() <= 1e-5 * x.shape[0] ** 0.5 * 4 + 1e-3
+    for _ in range(3):
+        for p in probs:
+            p[1].fill_(-1.0)
+        ops.colsum_group(probs, workspace=ws)
+        torch.cuda.synchronize()
+        for p, f in zip(probs, first):
+            assert torch.equal(p[1], f)
