@@ -49,6 +49,17 @@ class WgradItem(C.Structure):
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("out", C.c_void_p), ("ld", C.c_int64)]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("ldq", C.c_int64), ("q_mod", C.c_int32),
+                ("k", C.c_void_p), ("v", C.c_void_p), ("ldkv", C.c_int64), ("kv_mod", C.c_int32),
+                ("mask", C.c_void_p), ("mask_mod", C.c_int32),
+                ("nb", C.c_int32), ("H", C.c_int32), ("hd", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
+                ("drop_p", C.c_float), ("rng", C.c_void_p), ("site", C.c_uint32),
+                ("o", C.c_void_p), ("ldo", C.c_int64),
+                ("dout", C.c_void_p), ("lddo", C.c_int64), ("dq", C.c_void_p), ("lddq", C.c_int64),
+                ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddkv", C.c_int64), ("stat", C.c_void_p)]
+
+
 class ColsumItem(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int64), ("N", C.c_int32), ("out", C.c_void_p)]
 
@@ -76,6 +87,8 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_buffer.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.gg_engine_buffer.restype = vp
     L.gg_optim_step.argtypes = [i32, vp, vp, vp, vp, i64, f32, f32, vp, vp, vp, vp]
+    L.gg_attention_fwd.argtypes = [C.POINTER(AttnArgs), vp]
+    L.gg_attention_bwd.argtypes = [C.POINTER(AttnArgs), vp]
     L.gg_wgrad_group_workspace_bytes.argtypes = [i64]
     L.gg_wgrad_group_workspace_bytes.restype = i64
     L.gg_wgrad_group.argtypes = [C.POINTER(WgradItem), i32, vp, i64, vp]
@@ -97,5 +110,5 @@ EXPORTS = [
     "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_disc_grads_phase", "gg_engine_gen_grads_phase", "gg_engine_optim_step", "gg_engine_generate",
     "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump",
-    "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
+    "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

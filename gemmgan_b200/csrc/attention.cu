@@ -472,6 +472,244 @@ __global__ void __launch_bounds__(128) attn_small_kv_kernel(const AttnArgs a, co
   }
 }
 
+// ------------------------------------------------------- short self-attention, head_dim 64 (the tower)
+// S = Lq = Lk <= 16 tokens, hd = 64: the encoder layers of the paper / FiLM models at P = 8 patches.
+// One thread per (sequence, head, token) row with all 64 head dims in registers; a CTA owns SELF_GROUPS
+// (sequence, head) groups whose Q / K / V (/ dO) rows are staged in shared memory with coalesced 16-byte
+// loads (row pitch 144 B: conflict-free 16-byte reads). Scores never leave registers. The backward is one
+// kernel: pass A (thread = query row) recomputes the probabilities, writes dQ and leaves dS / dropped P in
+// shared memory; pass B (thread = key row) forms dK, dV from them (no atomics, deterministic).
+constexpr int SELF_HD = 64;
+constexpr int SELF_PITCH = SELF_HD + 8;  // bf16 elements
+constexpr int SELF_THREADS = 128;
+
+struct SelfGeom {
+  int G;       // groups per CTA
+  int rows;    // G * S
+};
+__host__ __device__ inline SelfGeom self_geom(int S) {
+  SelfGeom g;
+  g.G = SELF_THREADS / S;
+  g.rows = g.G * S;
+  return g;
+}
+
+// cooperative copy of nrows x 64 bf16 rows of up to four tensors into smem (pitch SELF_PITCH) with 16-byte
+// cp.async (no register staging: every load of the CTA is in flight at once). off(t, r) = element offset of
+// row r of tensor t (head column included), or -1 beyond the last group (zero-filled).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+template <int NT, class OffFn>
+__device__ __forceinline__ void self_stage(bf16* const* dst, const bf16* const* src, int nrows, OffFn off) {
+  const int n = nrows * 8;
+  for (int c = threadIdx.x; c < n; c += SELF_THREADS) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int64_t o = off(t, c >> 3);
+      cp_async16(dst[t] + (c >> 3) * SELF_PITCH + (c & 7) * 8, src[t] + (o >= 0 ? o : 0) + (c & 7) * 8, o >= 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void self_row_f32(const bf16* row, float* v) {
+#pragma unroll
+  for (int d = 0; d < SELF_HD; d += 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + d);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = __bfloat1622float2(h[q]);
+      v[d + 2 * q] = f.x;
+      v[d + 2 * q + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ float self_dot(const float* q, const bf16* row) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains
+#pragma unroll
+  for (int d = 0; d < SELF_HD; d += 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + d);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __bfloat1622float2(h[t]);
+      acc[t] = fmaf(q[d + 2 * t], f.x, acc[t]);
+      acc[t] = fmaf(q[d + 2 * t + 1], f.y, acc[t]);
+    }
+  }
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+__device__ __forceinline__ void self_axpy(float* acc, float w, const bf16* row) {
+#pragma unroll
+  for (int d = 0; d < SELF_HD; d += 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + d);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __bfloat1622float2(h[t]);
+      acc[d + 2 * t] = fmaf(w, f.x, acc[d + 2 * t]);
+      acc[d + 2 * t + 1] = fmaf(w, f.y, acc[d + 2 * t + 1]);
+    }
+  }
+}
+__device__ __forceinline__ void self_store_row(bf16* dst, const float* v, float scale) {
+#pragma unroll
+  for (int d = 0; d < SELF_HD; d += 8) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[d + 2 * t] * scale, v[d + 2 * t + 1] * scale);
+    *reinterpret_cast<uint4*>(dst + d) = u;
+  }
+}
+
+// MODE 0: forward. MODE 1: backward (dq, dk, dv).
+template <int MODE>
+__global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_self[];
+  const int S = a.Lq;
+  const SelfGeom geo = self_geom(S);
+  bf16* Qs = reinterpret_cast<bf16*>(smem_self);
+  bf16* Ks = Qs + geo.rows * SELF_PITCH;
+  bf16* Vs = Ks + geo.rows * SELF_PITCH;
+  bf16* Gs = Vs + geo.rows * SELF_PITCH;                                    // dO (backward only)
+  float* sc = reinterpret_cast<float*>(Gs + (MODE == 1 ? geo.rows * SELF_PITCH : 0));  // [2][SM_MAXL][threads]
+  float* dS = sc + 2 * SM_MAXL * SELF_THREADS;                                          // [G][S][S] x 2
+  const int64_t ngroups = static_cast<int64_t>(a.nb) * a.H;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * geo.G;
+  auto off = [&](int t, int r) -> int64_t {
+    const int64_t gid = g0 + r / S;
+    if (gid >= ngroups) return -1;
+    const int64_t bb = gid / a.H, col = (gid % a.H) * SELF_HD;
+    const int tok = r % S;
+    if (t == 0) return ((bb % a.q_mod) * S + tok) * a.ldq + col;
+    if (t == 3) return (bb * S + tok) * a.lddo + col;
+    return ((bb % a.kv_mod) * S + tok) * a.ldkv + col;
+  };
+  {
+    bf16* dsts[4] = {Qs, Ks, Vs, Gs};
+    const bf16* srcs[4] = {a.q, a.k, a.v, a.dout};
+    if (MODE == 1) self_stage<4>(dsts, srcs, geo.rows, off);
+    else self_stage<3>(dsts, srcs, geo.rows, off);
+  }
+  __syncthreads();
+  const int r = threadIdx.x;
+  const int g = r / S, i = r % S;
+  const int64_t gid = g0 + g;
+  const bool active = r < geo.rows && gid < ngroups;
+  const int b = active ? static_cast<int>(gid / a.H) : 0;
+  const int h = active ? static_cast<int>(gid % a.H) : 0;
+  const uint8_t* mk = (a.mask && active) ? a.mask + static_cast<int64_t>(b % a.mask_mod) * S : nullptr;
+  const float scale = 0.125f;  // 1/sqrt(64)
+  uint64_t seed = 0, step = 0;
+  if (a.drop_p > 0.f) {
+    seed = a.rng[0];
+    step = a.rng[1];
+  }
+  const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  const bf16* Kg = Ks + g * S * SELF_PITCH;
+  const bf16* Vg = Vs + g * S * SELF_PITCH;
+  // per-thread score rows live in shared memory (column = thread => conflict-free), so the key loops stay
+  // rolled: fully unrolled they are ~50 KB of SASS and thrash the instruction cache
+  float* pr = sc + threadIdx.x;   // p_j   at pr[j * SELF_THREADS]
+  float* pd = pr + SM_MAXL * SELF_THREADS;  // dropped p_j (forward weight) / dP_j (backward)
+  if (active) {
+    float q[SELF_HD];
+    self_row_f32(Qs + r * SELF_PITCH, q);
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int j = 0; j < S; ++j) {
+      float t = -INFINITY;
+      if (!(mk && mk[j])) t = self_dot(q, Kg + j * SELF_PITCH) * scale;
+      pr[j * SELF_THREADS] = t;
+      m = fmaxf(m, t);
+    }
+    float l = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < S; ++j) {
+      const float t = pr[j * SELF_THREADS];
+      const float e = (t == -INFINITY) ? 0.f : __expf(t - m);
+      pr[j * SELF_THREADS] = e;
+      l += e;
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    const uint64_t pbase = ((static_cast<uint64_t>(b) * a.H + h) * S + i) * static_cast<uint64_t>(S);
+#pragma unroll 1
+    for (int j = 0; j < S; ++j) {
+      const float pj = pr[j * SELF_THREADS] * inv_l;
+      const bool keep = a.drop_p > 0.f ? dropout_keep(seed, step, a.site, pbase + j, a.drop_p) : true;
+      pr[j * SELF_THREADS] = pj;
+      pd[j * SELF_THREADS] = keep ? keep_scale : 0.f;  // dropout multiplier
+    }
+  }
+  if (MODE == 0) {
+    if (active) {
+      float acc[SELF_HD];
+#pragma unroll
+      for (int d = 0; d < SELF_HD; ++d) acc[d] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < S; ++j) self_axpy(acc, pr[j * SELF_THREADS] * pd[j * SELF_THREADS], Vg + j * SELF_PITCH);
+      self_store_row(a.o + (static_cast<int64_t>(b) * S + i) * a.ldo + h * SELF_HD, acc, 1.f);
+    }
+    return;
+  }
+  // ---- backward pass A: thread = query row
+  float* dSg = dS + g * 2 * S * S;
+  if (active) {
+    float go[SELF_HD];
+    self_row_f32(Gs + r * SELF_PITCH, go);
+    float delta = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < S; ++j) {
+      const float mult = pd[j * SELF_THREADS];
+      const float dpj = self_dot(go, Vg + j * SELF_PITCH) * mult;   // dP_ij through the dropout mask
+      delta = fmaf(pr[j * SELF_THREADS], dpj, delta);
+      dSg[S * S + i * S + j] = pr[j * SELF_THREADS] * mult;          // dropped probability (for dV)
+      pd[j * SELF_THREADS] = dpj;
+    }
+    float acc[SELF_HD];
+#pragma unroll
+    for (int d = 0; d < SELF_HD; ++d) acc[d] = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < S; ++j) {
+      const float ds = pr[j * SELF_THREADS] * (pd[j * SELF_THREADS] - delta);
+      self_axpy(acc, ds, Kg + j * SELF_PITCH);
+      dSg[i * S + j] = ds;
+    }
+    self_store_row(a.dq + (static_cast<int64_t>(b) * S + i) * a.lddq + h * SELF_HD, acc, scale);
+  }
+  __syncthreads();
+  // ---- pass B: thread = key row j (= i)
+  if (active) {
+    const int j = i;
+    float dk[SELF_HD], dv[SELF_HD];
+#pragma unroll
+    for (int d = 0; d < SELF_HD; ++d) dk[d] = dv[d] = 0.f;
+    const bf16* Qg = Qs + g * S * SELF_PITCH;
+    const bf16* Gg = Gs + g * S * SELF_PITCH;
+#pragma unroll 1
+    for (int ii = 0; ii < S; ++ii) {
+      self_axpy(dk, dSg[ii * S + j], Qg + ii * SELF_PITCH);
+      self_axpy(dv, dSg[S * S + ii * S + j], Gg + ii * SELF_PITCH);
+    }
+    const int64_t row = static_cast<int64_t>(b) * S + j;
+    self_store_row(a.dk + row * a.lddkv + h * SELF_HD, dk, scale);
+    self_store_row(a.dv + row * a.lddkv + h * SELF_HD, dv, 1.f);
+  }
+}
+
+static size_t self_smem_bytes(int S, int mode) {
+  const SelfGeom geo = self_geom(S);
+  size_t b = static_cast<size_t>(mode == 1 ? 4 : 3) * geo.rows * SELF_PITCH * 2;
+  b += static_cast<size_t>(2) * SM_MAXL * SELF_THREADS * 4;
+  if (mode == 1) b += static_cast<size_t>(geo.G) * 2 * S * S * 4;
+  return b + 16;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static bool small_path(const AttnArgs& a) {
   const int dpt = a.hd / 4;
@@ -507,6 +745,31 @@ static void launch_small_kv(const AttnArgs& a, const float* stat, cudaStream_t s
   }
 }
 
+static bool self_path(const AttnArgs& a) {
+  if (!(a.Lq == a.Lk && a.Lk <= SM_MAXL && a.hd == SELF_HD)) return false;
+  const bool ok = a.ldq % 8 == 0 && a.ldkv % 8 == 0 && aligned16(a.q) && aligned16(a.k) && aligned16(a.v) &&
+                  (!a.o || (a.ldo % 8 == 0 && aligned16(a.o))) &&
+                  (!a.dout || (a.lddo % 8 == 0 && aligned16(a.dout) && a.lddq % 8 == 0 && aligned16(a.dq) &&
+                               a.lddkv % 8 == 0 && aligned16(a.dk) && aligned16(a.dv)));
+  return ok;
+}
+template <int MODE>
+static int launch_self(const AttnArgs& a, cudaStream_t st) {
+  const SelfGeom geo = self_geom(a.Lq);
+  const size_t smem = self_smem_bytes(a.Lq, MODE);
+  static bool configured = false;
+  if (!configured) {
+    GG_CUDA_CHECK(cudaFuncSetAttribute(attn_self_small_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(self_smem_bytes(SM_MAXL, MODE))));
+    configured = true;
+  }
+  const int64_t ngroups = static_cast<int64_t>(a.nb) * a.H;
+  const unsigned grid = static_cast<unsigned>((ngroups + geo.G - 1) / geo.G);
+  attn_self_small_kernel<MODE><<<grid, SELF_THREADS, smem, st>>>(a);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 static int check_args(const AttnArgs& a) {
   GG_REQUIRE(a.hd >= 2 && a.hd <= 64 && a.hd % 2 == 0, "attention head_dim %d unsupported (even, <= 64)", a.hd);
   GG_REQUIRE(a.Lk >= 1 && a.Lk <= 32 * ATT_MAXC && a.Lq >= 1 && a.Lq <= 32 * ATT_MAXC,
@@ -518,6 +781,7 @@ static int check_args(const AttnArgs& a) {
 int k_attention_fwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_args(a);
   if (rc) return rc;
+  if (self_path(a)) return launch_self<0>(a, st);
   if (small_path(a)) {
     launch_small_q<0>(a, nullptr, st);
     GG_LAUNCH_CHECK();
@@ -540,6 +804,7 @@ int k_attention_fwd(const AttnArgs& a, cudaStream_t st) {
 int k_attention_bwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_args(a);
   if (rc) return rc;
+  if (self_path(a)) return launch_self<1>(a, st);
   if (small_path(a)) {
     GG_REQUIRE(a.stat != nullptr, "short-sequence attention backward needs a stats scratch buffer");
     launch_small_q<1>(a, a.stat, st);

@@ -94,6 +94,7 @@ struct Tower {
 };
 struct LayerGrads {  // per layer: side-lane weight-gradient GEMMs read these while lane 0 moves on
   bf16 *gz2, *gy2, *gz1, *gy1, *gh, *gqkv;
+  float *lnp2, *lnp1;  // LayerNorm weight/bias-gradient block partials (finished on a side lane)
 };
 struct GradScratch {
   bf16 *dc, *dat, *dqt, *dkvt, *dkvt_sum, *dp, *dap, *dqp, *dqp_sum, *dkvp;
@@ -389,6 +390,8 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
       lg.gy1 = ar.take<bf16>(rows * E);
       lg.gh = ar.take<bf16>(rows * F);
       lg.gqkv = ar.take<bf16>(rows * 3 * E);
+      lg.lnp2 = ar.take<float>(ln_bwd_scratch_floats(rows, static_cast<int>(E)));
+      lg.lnp1 = ar.take<float>(ln_bwd_scratch_floats(rows, static_cast<int>(E)));
     }
     g.dte = ar.take<bf16>(B * T * E);
     g.dte0 = ar.take<bf16>(B * E);
@@ -663,8 +666,9 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     const uint32_t site = site0 + 8u * l;
     // x_out = LN2(x1 + drop(ff))
     GG_TRY(k_add_ln_bwd(g.ga, L.z2, L.mean2, L.rstd2, e.P(net, ls + GG_L_N2_W), lg.gz2, p > 0.f ? lg.gy2 : nullptr,
-                        e.Gr(net, ls + GG_L_N2_W), e.Gr(net, ls + GG_L_N2_B), rows, E, p, e.rng, site + 3,
-                        e.scratch_l[0], st));
+                        nullptr, nullptr, rows, E, p, e.rng, site + 3, lg.lnp2, st));
+    GG_TRY(e.fork(2));
+    GG_TRY(k_ln_bwd_finish(lg.lnp2, rows, E, e.Gr(net, ls + GG_L_N2_W), e.Gr(net, ls + GG_L_N2_B), e.S(2)));
     const bf16* dff = p > 0.f ? lg.gy2 : lg.gz2;
     GG_TRY(e.wgrad(E, F, rows, Op{dff, E}, Op{L.h, F}, e.Gr(net, ls + GG_L_FF2_W), F));
     GG_TRY(e.bgrad(dff, E, rows, E, e.Gr(net, ls + GG_L_FF2_B)));
@@ -675,8 +679,9 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     GG_TRY(e.dgrad(0, rows, E, F, Op{lg.gh, F}, e.W(net, ls + GG_L_FF1_W), Epi().res(lg.gz2, E).obf(g.gb, E)));
     // x1 = LN1(x_in + drop(sa))
     GG_TRY(k_add_ln_bwd(g.gb, L.z1, L.mean1, L.rstd1, e.P(net, ls + GG_L_N1_W), lg.gz1, p > 0.f ? lg.gy1 : nullptr,
-                        e.Gr(net, ls + GG_L_N1_W), e.Gr(net, ls + GG_L_N1_B), rows, E, p, e.rng, site + 1,
-                        e.scratch_l[0], st));
+                        nullptr, nullptr, rows, E, p, e.rng, site + 1, lg.lnp1, st));
+    GG_TRY(e.fork(2));
+    GG_TRY(k_ln_bwd_finish(lg.lnp1, rows, E, e.Gr(net, ls + GG_L_N1_W), e.Gr(net, ls + GG_L_N1_B), e.S(2)));
     const bf16* dsa = p > 0.f ? lg.gy1 : lg.gz1;
     GG_TRY(e.wgrad(E, E, rows, Op{dsa, E}, Op{L.ao, E}, e.Gr(net, ls + GG_L_OUT_W), E));
     GG_TRY(e.bgrad(dsa, E, rows, E, e.Gr(net, ls + GG_L_OUT_B)));
@@ -698,7 +703,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     GG_TRY(e.flush_grads());
   }
   // X0 = [cls | patch projections], replicas share the projections
-  GG_TRY(k_colsum(g.ga, 0, static_cast<int64_t>(S) * E, n, E, nullptr, 1.f, e.Gr(net, GG_P_CLS), 0, e.scratch_l[0], st));
+  GG_TRY(e.bgrad(g.ga, static_cast<int64_t>(S) * E, n, E, e.Gr(net, GG_P_CLS)));  // d cls = sum over the CLS rows
   GG_TRY(k_unassemble_tokens(g.ga, g.dpe, nullptr, Rg, B, S, E, st));
   GG_TRY(e.wgrad(E, Dp, B * P, Op{g.dpe, E}, Op{t.mod, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
   GG_TRY(e.bgrad(g.dpe, E, B * P, E, e.Gr(net, GG_P_PATCH_B)));
@@ -1138,6 +1143,15 @@ extern "C" void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows,
   if (ld) *ld = l;
   if (is_f32) *is_f32 = f;
   return p;
+}
+
+extern "C" int gg_attention_fwd(const gg_attn_args* a, void* stream) {
+  GG_REQUIRE(a && a->q && a->k && a->v && a->o, "null argument");
+  return k_attention_fwd(*reinterpret_cast<const AttnArgs*>(a), reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int gg_attention_bwd(const gg_attn_args* a, void* stream) {
+  GG_REQUIRE(a && a->q && a->k && a->v && a->dout && a->dq && a->dk && a->dv, "null argument");
+  return k_attention_bwd(*reinterpret_cast<const AttnArgs*>(a), reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int64_t gg_wgrad_group_workspace_bytes(int64_t sum_output_elems) {

@@ -86,9 +86,11 @@ int k_add_ln_fwd(const bf16* x, const bf16* y, const float* w, const float* b, b
 int k_add_ln_bwd(const bf16* dout, const bf16* z, const float* mean, const float* rstd, const float* w,
                  bf16* dz, bf16* dy, float* dw, float* db, int64_t rows, int E, float drop_p,
                  const uint64_t* rng, uint32_t site, float* scratch, cudaStream_t st);
+int k_ln_bwd_finish(const float* scratch, int64_t rows, int E, float* dw, float* db, cudaStream_t st);
 int64_t ln_bwd_scratch_floats(int64_t rows, int E);
 
 // ---- attention.cu ---------------------------------------------------------------------------
+// public mirror: gg_attn_args (include/gemmgan.h); the internal view types the pointers
 struct AttnArgs {
   const bf16* q; int64_t ldq; int q_mod;     // query row = (b % q_mod) * Lq + i
   const bf16* k; const bf16* v; int64_t ldkv; int kv_mod;   // key row = (b % kv_mod) * Lk + j
@@ -102,6 +104,7 @@ struct AttnArgs {
   bf16* dk; bf16* dv; int64_t lddkv;         // [nb*Lk, ...]    (per replica even if kv is shared)
   float* stat;                               // backward scratch: 2 * nb * H * Lq floats (lse, delta)
 };
+static_assert(sizeof(AttnArgs) == sizeof(gg_attn_args), "AttnArgs must mirror gg_attn_args");
 int k_attention_fwd(const AttnArgs& a, cudaStream_t st);
 int k_attention_bwd(const AttnArgs& a, cudaStream_t st);
 

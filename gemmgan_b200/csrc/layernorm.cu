@@ -268,14 +268,21 @@ __global__ void __launch_bounds__(256)
     partial[static_cast<int64_t>(blockIdx.x) * 2 * E + i] = t;
   }
 }
-__global__ void ln_bwd_finish_kernel(const float* __restrict__ partial, int nblocks, int E, float* __restrict__ dw,
-                                     float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element: lanes sum the block partials strided by 32, then a fixed shuffle tree
+// (same order every run => deterministic)
+__global__ void __launch_bounds__(256)
+    ln_bwd_finish_kernel(const float* __restrict__ partial, int nblocks, int E, float* __restrict__ dw,
+                         float* __restrict__ db) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= 2 * E) return;
   float t = 0.f;
-  for (int c = 0; c < nblocks; ++c) t += partial[static_cast<int64_t>(c) * 2 * E + i];
-  if (i < E) dw[i] = t;
-  else if (db) db[i - E] = t;
+  for (int c = lane; c < nblocks; c += 32) t += partial[static_cast<int64_t>(c) * 2 * E + i];
+  t = wsum(t);
+  if (lane == 0) {
+    if (i < E) dw[i] = t;
+    else if (db) db[i - E] = t;
+  }
 }
 
 template <int PER, bool VEC>
@@ -308,7 +315,14 @@ int k_add_ln_bwd(const bf16* dout, const bf16* z, const float* mean, const float
   else if (E == 1024) rc = launch_ln_bwd<4, true>(blocks, smem, st, dout, z, mean, rstd, w, dz, dy, scratch, rows, E, drop_p, rng, site);
   else rc = launch_ln_bwd<8, false>(blocks, smem, st, dout, z, mean, rstd, w, dz, dy, scratch, rows, E, drop_p, rng, site);
   if (rc) return rc;
-  ln_bwd_finish_kernel<<<(2 * E + 255) / 256, 256, 0, st>>>(scratch, blocks, E, dw, db);
+  if (dw) return k_ln_bwd_finish(scratch, rows, E, dw, db, st);
+  return GG_OK;
+}
+
+// dw / db from the per-block partials k_add_ln_bwd left in `scratch` (call it with dw = NULL to defer this)
+int k_ln_bwd_finish(const float* scratch, int64_t rows, int E, float* dw, float* db, cudaStream_t st) {
+  const int blocks = ln_bwd_blocks(rows);
+  ln_bwd_finish_kernel<<<(2 * E + 7) / 8, 256, 0, st>>>(scratch, blocks, E, dw, db);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -144,15 +144,34 @@ int k_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, fl
   return GG_OK;
 }
 
+// One (segment, 4-column run) per thread iteration: float4 load, 8-byte bf16x4 store, 32-bit index math.
 __global__ void __launch_bounds__(256)
     refresh_shadows_kernel(const float* __restrict__ p, bf16* __restrict__ shadow, const ShadowSeg* __restrict__ segs) {
   const ShadowSeg s = segs[blockIdx.y];
-  const int64_t total = static_cast<int64_t>(s.rows) * s.ncols;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / s.ncols;
-    const int c = static_cast<int>(i % s.ncols);
-    shadow[s.s_off + r * s.s_ld + c] = __float2bfloat16_rn(p[s.p_off + r * s.cols + s.col0 + c]);
+  const float* src = p + s.p_off + s.col0;
+  bf16* dst = shadow + s.s_off;
+  const bool vec = (s.ncols % 4 == 0) && (s.cols % 4 == 0) && (s.s_ld % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+  if (vec) {
+    const unsigned c4 = static_cast<unsigned>(s.ncols) >> 2;
+    const unsigned total = static_cast<unsigned>(s.rows) * c4;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const unsigned r = i / c4, c = (i - r * c4) * 4;
+      const float4 f = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(r) * s.cols + c));
+      __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dst + static_cast<int64_t>(r) * s.s_ld + c) = pk;
+    }
+  } else {
+    const int64_t total = static_cast<int64_t>(s.rows) * s.ncols;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t r = i / s.ncols;
+      const int c = static_cast<int>(i % s.ncols);
+      dst[r * s.s_ld + c] = __float2bfloat16_rn(src[r * s.cols + c]);
+    }
   }
 }
 int k_refresh_shadows(const float* p, bf16* shadow, const ShadowSeg* segs_dev, int nseg, int /*max_rows*/,

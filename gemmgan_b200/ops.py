@@ -111,3 +111,33 @@ def colsum_group(problems, workspace=None):
         workspace = torch.zeros(L.gg_colsum_group_workspace_bytes(total), device=problems[0][0].device, dtype=torch.uint8)
     _lib.check(L.gg_colsum_group(items, n, _ptr(workspace), workspace.numel(), _stream()))
     return workspace
+
+
+def attention(qkv, nb, H, Lq, Lk=None, mask=None, drop_p=0.0, rng=None, site=0, dout=None):
+    """Self-attention on a packed [nb*L, 3*H*hd] bf16 qkv tensor (the encoder-layer layout). Returns o, or
+    (o, dqkv) when `dout` is given (gg_attention_fwd / gg_attention_bwd)."""
+    from . import _abi_decl as A
+
+    L = _lib.lib()
+    Lk = Lk or Lq
+    E = qkv.shape[1] // 3
+    a = A.AttnArgs()
+    a.q, a.ldq, a.q_mod = qkv.data_ptr(), qkv.stride(0), nb
+    a.k, a.v, a.ldkv, a.kv_mod = qkv.data_ptr() + 2 * E, qkv.data_ptr() + 4 * E, qkv.stride(0), nb
+    if mask is not None:
+        a.mask, a.mask_mod = mask.data_ptr(), mask.shape[0]
+    a.nb, a.H, a.hd, a.Lq, a.Lk = nb, H, E // H, Lq, Lk
+    a.drop_p, a.rng, a.site = drop_p, (rng.data_ptr() if rng is not None else None), site
+    o = torch.empty(nb * Lq, E, device=qkv.device, dtype=torch.bfloat16)
+    a.o, a.ldo = o.data_ptr(), E
+    _lib.check(L.gg_attention_fwd(C.byref(a), _stream()))
+    if dout is None:
+        return o
+    dqkv = torch.empty_like(qkv)
+    stat = torch.empty(2 * nb * H * Lq, device=qkv.device, dtype=torch.float32)
+    a.dout, a.lddo = dout.data_ptr(), dout.stride(0)
+    a.dq, a.lddq = dqkv.data_ptr(), dqkv.stride(0)
+    a.dk, a.dv, a.lddkv = dqkv.data_ptr() + 2 * E, dqkv.data_ptr() + 4 * E, dqkv.stride(0)
+    a.stat = stat.data_ptr()
+    _lib.check(L.gg_attention_bwd(C.byref(a), _stream()))
+    return o, dqkv

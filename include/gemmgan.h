@@ -247,6 +247,26 @@ void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows, int64_t* c
 int gg_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, float lr, float max_norm,
                   float* step_count, float* norm_out2, float* scratch, void* stream);
 
+/* Multi-head attention core softmax(q k^T / sqrt(hd) + key_padding_mask) v with dropout on the probabilities,
+ * forward and hand-written backward (F.multi_head_attention_forward / SDPA inside nn.TransformerEncoderLayer and
+ * nn.MultiheadAttention, :114-123, :144-152). bf16 tensors; rows of sequence b are b*L + i; heads are 64-column
+ * slices (hd columns each). q / kv / mask may be shared by replicas through the *_mod fields (row block =
+ * b % mod). Backward needs `stat` (2*nb*H*Lq floats) for the generic short-sequence path. */
+typedef struct gg_attn_args {
+  const void* q; int64_t ldq; int32_t q_mod;
+  const void* k; const void* v; int64_t ldkv; int32_t kv_mod;
+  const uint8_t* mask; int32_t mask_mod;      /* [mask_mod, Lk], 1 = padded key; may be NULL */
+  int32_t nb, H, hd, Lq, Lk;
+  float drop_p; const uint64_t* rng; uint32_t site;
+  void* o; int64_t ldo;                       /* forward output [nb*Lq, H*hd] */
+  const void* dout; int64_t lddo;             /* backward inputs / outputs */
+  void* dq; int64_t lddq;
+  void* dk; void* dv; int64_t lddkv;
+  float* stat;
+} gg_attn_args;
+int gg_attention_fwd(const gg_attn_args* a, void* stream);
+int gg_attention_bwd(const gg_attn_args* a, void* stream);
+
 /* Grouped weight gradients: out_i[M_i, N_i] (fp32, pitch ld) = dY_i^T X_i for up to 32 problems in ONE launch
  * (autograd's grad_output.t().mm(input) of every Linear of one backward pass, :412 / :455). dY_i is stored
  * [K_i rows, M_i], X_i [K_i rows, N_i], both bf16 with 16-byte aligned bases and pitches that are multiples of
