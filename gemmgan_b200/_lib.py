@@ -76,6 +76,7 @@ class GemmDesc(C.Structure):
         ("impl", C.c_int32),
         ("force_splits", C.c_int32),
         ("block_n", C.c_int32),
+        ("light", C.c_int32),
     ]
 
 

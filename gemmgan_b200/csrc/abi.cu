@@ -1,12 +1,21 @@
 // Error reporting and device probing for the C ABI (include/gemmgan.h).
 #include "host_util.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace gg {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launch_count{0};
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("GEMMGAN_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -10,6 +10,7 @@
 // modules (src/conditional_gan_cross_attention_with_film.py:114-123, 144-152). As in torch, q is scaled
 // by 1/sqrt(head_dim) before q k^T and padded keys get -inf.
 #include "host_util.h"
+#include "pdl.cuh"
 #include "kernels.h"
 #include "philox.cuh"
 
@@ -52,6 +53,7 @@ __device__ __forceinline__ float dot_row(const bf16* a, const bf16* b, int hd) {
 }
 
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_fwd_kernel(const AttnArgs a) {
+  pdl_entry();
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int hd = a.hd, pitch = hd + 2, Lk = a.Lk, Lq = a.Lq;
   bf16* Ks = reinterpret_cast<bf16*>(smem_att);
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_fwd_kernel(const Att
 }
 
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_bwd_kernel(const AttnArgs a) {
+  pdl_entry();
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int hd = a.hd, pitch = hd + 2, Lk = a.Lk, Lq = a.Lq;
   const int Lmax = Lk > Lq ? Lk : Lq;
@@ -316,6 +319,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 // MODE 0: forward (writes o). MODE 1: backward pass A (writes dq, lse, delta).
 template <int DPT, int MODE>
 __global__ void __launch_bounds__(128) attn_small_q_kernel(const AttnArgs a, float* __restrict__ stat) {
+  pdl_entry();
   const int hd = a.hd, Lk = a.Lk, Lq = a.Lq;
   const int64_t total = static_cast<int64_t>(a.nb) * a.H * Lq;
   int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 2;
@@ -414,6 +418,7 @@ __global__ void __launch_bounds__(128) attn_small_q_kernel(const AttnArgs a, flo
 // backward pass B: one thread quad per key row -> dK, dV (sums over the queries; deterministic)
 template <int DPT>
 __global__ void __launch_bounds__(128) attn_small_kv_kernel(const AttnArgs a, const float* __restrict__ stat) {
+  pdl_entry();
   const int hd = a.hd, Lk = a.Lk, Lq = a.Lq;
   const int64_t total = static_cast<int64_t>(a.nb) * a.H * Lk;
   int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 2;
@@ -570,6 +575,7 @@ __device__ __forceinline__ void self_store_row(bf16* dst, const float* v, float 
 // MODE 0: forward. MODE 1: backward (dq, dk, dv).
 template <int MODE>
 __global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const AttnArgs a) {
+  pdl_entry();
   extern __shared__ __align__(16) uint8_t smem_self[];
   const int S = a.Lq;
   const SelfGeom geo = self_geom(S);
@@ -728,20 +734,20 @@ static void launch_small_q(const AttnArgs& a, float* stat, cudaStream_t st) {
   const int64_t threads = static_cast<int64_t>(a.nb) * a.H * a.Lq * 4;
   const unsigned grid = static_cast<unsigned>((threads + 127) / 128);
   switch (a.hd / 4) {
-    case 2: attn_small_q_kernel<2, MODE><<<grid, 128, 0, st>>>(a, stat); break;
-    case 4: attn_small_q_kernel<4, MODE><<<grid, 128, 0, st>>>(a, stat); break;
-    case 8: attn_small_q_kernel<8, MODE><<<grid, 128, 0, st>>>(a, stat); break;
-    default: attn_small_q_kernel<16, MODE><<<grid, 128, 0, st>>>(a, stat); break;
+    case 2: launch_k(attn_small_q_kernel<2, MODE>, grid, 128, 0, st, a, stat); break;
+    case 4: launch_k(attn_small_q_kernel<4, MODE>, grid, 128, 0, st, a, stat); break;
+    case 8: launch_k(attn_small_q_kernel<8, MODE>, grid, 128, 0, st, a, stat); break;
+    default: launch_k(attn_small_q_kernel<16, MODE>, grid, 128, 0, st, a, stat); break;
   }
 }
 static void launch_small_kv(const AttnArgs& a, const float* stat, cudaStream_t st) {
   const int64_t threads = static_cast<int64_t>(a.nb) * a.H * a.Lk * 4;
   const unsigned grid = static_cast<unsigned>((threads + 127) / 128);
   switch (a.hd / 4) {
-    case 2: attn_small_kv_kernel<2><<<grid, 128, 0, st>>>(a, stat); break;
-    case 4: attn_small_kv_kernel<4><<<grid, 128, 0, st>>>(a, stat); break;
-    case 8: attn_small_kv_kernel<8><<<grid, 128, 0, st>>>(a, stat); break;
-    default: attn_small_kv_kernel<16><<<grid, 128, 0, st>>>(a, stat); break;
+    case 2: launch_k(attn_small_kv_kernel<2>, grid, 128, 0, st, a, stat); break;
+    case 4: launch_k(attn_small_kv_kernel<4>, grid, 128, 0, st, a, stat); break;
+    case 8: launch_k(attn_small_kv_kernel<8>, grid, 128, 0, st, a, stat); break;
+    default: launch_k(attn_small_kv_kernel<16>, grid, 128, 0, st, a, stat); break;
   }
 }
 
@@ -765,7 +771,7 @@ static int launch_self(const AttnArgs& a, cudaStream_t st) {
   }
   const int64_t ngroups = static_cast<int64_t>(a.nb) * a.H;
   const unsigned grid = static_cast<unsigned>((ngroups + geo.G - 1) / geo.G);
-  attn_self_small_kernel<MODE><<<grid, SELF_THREADS, smem, st>>>(a);
+  launch_k(attn_self_small_kernel<MODE>, grid, SELF_THREADS, smem, st, a);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -796,7 +802,7 @@ int k_attention_fwd(const AttnArgs& a, cudaStream_t st) {
     configured = 200 * 1024;
   }
   GG_REQUIRE(smem <= 200 * 1024, "attention working set too large");
-  attention_fwd_kernel<<<a.nb * a.H, ATT_WARPS * 32, smem, st>>>(a);
+  launch_k(attention_fwd_kernel, a.nb * a.H, ATT_WARPS * 32, smem, st, a);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -823,7 +829,7 @@ int k_attention_bwd(const AttnArgs& a, cudaStream_t st) {
     configured = 220 * 1024;
   }
   GG_REQUIRE(smem <= 220 * 1024, "attention backward working set too large");
-  attention_bwd_kernel<<<a.nb * a.H, ATT_WARPS * 32, smem, st>>>(a);
+  launch_k(attention_bwd_kernel, a.nb * a.H, ATT_WARPS * 32, smem, st, a);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -7,6 +7,7 @@
 //   FiLM gamma*x+beta :136, torch.cat(cls, patches) :142, interpolation :358,
 //   grad_norm / (norm-1)^2 mean :372-374, D_loss / G_loss :32-46.
 #include "host_util.h"
+#include "pdl.cuh"
 #include "kernels.h"
 
 namespace gg {
@@ -21,6 +22,7 @@ static inline unsigned grid_for(int64_t work, int block, int64_t cap = 148LL * 1
 // ----------------------------------------------------------------------------------- cast
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, int64_t ld_src, bf16* __restrict__ dst,
                                      int64_t ld_dst, int64_t rows, int cols, int vec) {
+  pdl_entry();
   if (vec) {
     const int c4 = cols >> 2;
     const int64_t total = rows * c4;
@@ -52,12 +54,13 @@ int k_cast_f32_bf16(const float* src, int64_t ld_src, bf16* dst, int64_t ld_dst,
   const int vec = (cols % 4 == 0) && (ld_src % 4 == 0) && (ld_dst % 4 == 0) &&
                   ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
   const int64_t work = vec ? rows * (cols / 4) : rows * cols;
-  cast_f32_bf16_kernel<<<grid_for(work, 256), 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, cols, vec);
+  launch_k(cast_f32_bf16_kernel, grid_for(work, 256), 256, 0, st, src, ld_src, dst, ld_dst, rows, cols, vec);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 __global__ void mask_with_cls_kernel(const uint8_t* in, uint8_t* out, int B, int P) {
+  pdl_entry();
   const int S = P + 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * S) return;
@@ -65,7 +68,7 @@ __global__ void mask_with_cls_kernel(const uint8_t* in, uint8_t* out, int B, int
   out[i] = s == 0 ? 0 : (in[b * P + s - 1] ? 1 : 0);
 }
 int k_mask_with_cls(const uint8_t* in, uint8_t* out, int B, int P, cudaStream_t st) {
-  mask_with_cls_kernel<<<(B * (P + 1) + 255) / 256, 256, 0, st>>>(in, out, B, P);
+  launch_k(mask_with_cls_kernel, (B * (P + 1) + 255) / 256, 256, 0, st, in, out, B, P);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -73,6 +76,7 @@ int k_mask_with_cls(const uint8_t* in, uint8_t* out, int B, int P, cudaStream_t 
 // ----------------------------------------------------------------------------------- FiLM
 __global__ void film_apply_kernel(const bf16* __restrict__ patches, const float* __restrict__ gb,
                                   bf16* __restrict__ mod, int B, int P, int Dp) {
+  pdl_entry();
   const int d2 = Dp >> 1;
   const int64_t total = static_cast<int64_t>(B) * P * d2;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -89,7 +93,7 @@ __global__ void film_apply_kernel(const bf16* __restrict__ patches, const float*
 }
 int k_film_apply(const bf16* patches, const float* gb, bf16* mod, int B, int P, int Dp, cudaStream_t st) {
   GG_REQUIRE(Dp % 2 == 0, "patch feature dim must be even");
-  film_apply_kernel<<<grid_for(static_cast<int64_t>(B) * P * Dp / 2, 256), 256, 0, st>>>(patches, gb, mod, B,
+  launch_k(film_apply_kernel, grid_for(static_cast<int64_t>(B) * P * Dp / 2, 256), 256, 0, st, patches, gb, mod, B,
                                                                                         P, Dp);
   GG_LAUNCH_CHECK();
   return GG_OK;
@@ -97,6 +101,7 @@ int k_film_apply(const bf16* patches, const float* gb, bf16* mod, int B, int P, 
 
 __global__ void film_bwd_kernel(const bf16* __restrict__ dmod, const bf16* __restrict__ patches,
                                 const float* __restrict__ gb, bf16* __restrict__ dgb, int B, int P, int Dp) {
+  pdl_entry();
   const int64_t total = static_cast<int64_t>(B) * Dp;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -116,13 +121,14 @@ __global__ void film_bwd_kernel(const bf16* __restrict__ dmod, const bf16* __res
 }
 int k_film_bwd(const bf16* dmod, const bf16* patches, const float* gb, bf16* dgb, int B, int P, int Dp,
                cudaStream_t st) {
-  film_bwd_kernel<<<grid_for(static_cast<int64_t>(B) * Dp, 256), 256, 0, st>>>(dmod, patches, gb, dgb, B, P, Dp);
+  launch_k(film_bwd_kernel, grid_for(static_cast<int64_t>(B) * Dp, 256), 256, 0, st, dmod, patches, gb, dgb, B, P, Dp);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 // ----------------------------------------------------------------------------- token plumbing
 __global__ void assemble_tokens_kernel(bf16* x, const float* __restrict__ cls, int R, int B, int S, int E) {
+  pdl_entry();
   const int64_t total = static_cast<int64_t>(R) * B * S * E;
   const int64_t rep = static_cast<int64_t>(B) * S * E;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -134,13 +140,14 @@ __global__ void assemble_tokens_kernel(bf16* x, const float* __restrict__ cls, i
   }
 }
 int k_assemble_tokens(bf16* x, const float* cls, int R, int B, int S, int E, cudaStream_t st) {
-  assemble_tokens_kernel<<<grid_for(static_cast<int64_t>(R) * B * S * E, 256), 256, 0, st>>>(x, cls, R, B, S, E);
+  launch_k(assemble_tokens_kernel, grid_for(static_cast<int64_t>(R) * B * S * E, 256), 256, 0, st, x, cls, R, B, S, E);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 __global__ void unassemble_tokens_kernel(const bf16* __restrict__ dx, bf16* __restrict__ dpe, int R, int B,
                                          int S, int E) {
+  pdl_entry();
   const int P = S - 1;
   const int64_t total = static_cast<int64_t>(B) * P * E;
   const int64_t rep = static_cast<int64_t>(B) * S * E;
@@ -158,12 +165,13 @@ __global__ void unassemble_tokens_kernel(const bf16* __restrict__ dx, bf16* __re
 int k_unassemble_tokens(const bf16* dx, bf16* dpe, float* /*unused*/, int R, int B, int S, int E,
                         cudaStream_t st) {
   if (S <= 1) return GG_OK;
-  unassemble_tokens_kernel<<<grid_for(static_cast<int64_t>(B) * (S - 1) * E, 256), 256, 0, st>>>(dx, dpe, R, B, S, E);
+  launch_k(unassemble_tokens_kernel, grid_for(static_cast<int64_t>(B) * (S - 1) * E, 256), 256, 0, st, dx, dpe, R, B, S, E);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 __global__ void sum_replicas_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int R, int64_t n) {
+  pdl_entry();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float acc = 0.f;
@@ -172,12 +180,13 @@ __global__ void sum_replicas_kernel(const bf16* __restrict__ in, bf16* __restric
   }
 }
 int k_sum_replicas(const bf16* in, bf16* out, int R, int64_t n, cudaStream_t st) {
-  sum_replicas_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, out, R, n);
+  launch_k(sum_replicas_kernel, grid_for(n, 256), 256, 0, st, in, out, R, n);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 __global__ void scatter_add_rows_kernel(bf16* dst, const bf16* __restrict__ src, int B, int stride_rows, int E) {
+  pdl_entry();
   const int64_t total = static_cast<int64_t>(B) * E;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -188,12 +197,13 @@ __global__ void scatter_add_rows_kernel(bf16* dst, const bf16* __restrict__ src,
   }
 }
 int k_scatter_add_rows(bf16* dst, const bf16* src, int B, int stride_rows, int E, cudaStream_t st) {
-  scatter_add_rows_kernel<<<grid_for(static_cast<int64_t>(B) * E, 256), 256, 0, st>>>(dst, src, B, stride_rows, E);
+  launch_k(scatter_add_rows_kernel, grid_for(static_cast<int64_t>(B) * E, 256), 256, 0, st, dst, src, B, stride_rows, E);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 __global__ void scatter_cls_kernel(bf16* __restrict__ dst, const bf16* __restrict__ src, int B, int S, int E) {
+  pdl_entry();
   const int64_t total = static_cast<int64_t>(B) * S * E;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -204,7 +214,7 @@ __global__ void scatter_cls_kernel(bf16* __restrict__ dst, const bf16* __restric
   }
 }
 int k_scatter_cls(bf16* dst, const bf16* src, int B, int S, int E, cudaStream_t st) {
-  scatter_cls_kernel<<<grid_for(static_cast<int64_t>(B) * S * E, 256), 256, 0, st>>>(dst, src, B, S, E);
+  launch_k(scatter_cls_kernel, grid_for(static_cast<int64_t>(B) * S * E, 256), 256, 0, st, dst, src, B, S, E);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -214,6 +224,7 @@ int k_scatter_cls(bf16* dst, const bf16* src, int B, int S, int E, cudaStream_t 
 __global__ void colsum_stage1_kernel(const void* __restrict__ in, int in_f32, int64_t ld, int64_t rows, int N,
                                      const float* __restrict__ roww, int64_t rows_per_chunk,
                                      float* __restrict__ partial) {
+  pdl_entry();
   __shared__ float sm[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_chunk;
@@ -238,6 +249,7 @@ __global__ void colsum_stage1_kernel(const void* __restrict__ in, int in_f32, in
 }
 __global__ void colsum_stage2_kernel(const float* __restrict__ partial, int nchunks, int N, float scale,
                                      float* __restrict__ out, int accumulate) {
+  pdl_entry();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float t = 0.f;
@@ -257,9 +269,9 @@ int k_colsum(const void* in, int in_f32, int64_t ld, int64_t rows, int N, const 
   const int nchunks = colsum_chunks(rows);
   const int64_t rpc = (rows + nchunks - 1) / nchunks;
   dim3 grid((N + 31) / 32, nchunks), block(32, 8);
-  colsum_stage1_kernel<<<grid, block, 0, st>>>(in, in_f32, ld, rows, N, roww, rpc, scratch);
+  launch_k(colsum_stage1_kernel, grid, block, 0, st, in, in_f32, ld, rows, N, roww, rpc, scratch);
   GG_LAUNCH_CHECK();
-  colsum_stage2_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, nchunks, N, scale, out, accumulate);
+  launch_k(colsum_stage2_kernel, (N + 255) / 256, 256, 0, st, scratch, nchunks, N, scale, out, accumulate);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -285,6 +297,7 @@ struct ColsumGroupParams {
 };
 
 __global__ void __launch_bounds__(256) colsum_group_kernel(const __grid_constant__ ColsumGroupParams P) {
+  pdl_entry();
   __shared__ float sm[32][65];
   __shared__ unsigned last_flag;
   const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
@@ -407,7 +420,7 @@ int k_colsum_group(const ColsumItem* items, int n, void* workspace, int64_t work
   }
   P.total_work = work;
   const unsigned grid = static_cast<unsigned>(work < 148 * 8 ? work : 148 * 8);
-  colsum_group_kernel<<<grid, 256, 0, st>>>(P);
+  launch_k(colsum_group_kernel, grid, 256, 0, st, P);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -416,6 +429,7 @@ int k_colsum_group(const ColsumItem* items, int n, void* workspace, int64_t work
 __global__ void trunk1_combine_kernel(const float* __restrict__ a1x, const float* __restrict__ a1c,
                                       const float* __restrict__ b1, const float* __restrict__ alpha,
                                       bf16* __restrict__ h1, int B, int H, int npass, int R, float slope) {
+  pdl_entry();
   const int64_t total = static_cast<int64_t>(npass) * B * H;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -440,8 +454,7 @@ __global__ void trunk1_combine_kernel(const float* __restrict__ a1x, const float
 int k_trunk1_combine(const float* a1x, const float* a1c, const float* b1, const float* alpha, bf16* h1, int B,
                      int H, int npass, int R, float slope, cudaStream_t st) {
   GG_REQUIRE(npass == 1 || npass == 3, "npass must be 1 or 3");
-  trunk1_combine_kernel<<<grid_for(static_cast<int64_t>(npass) * B * H, 256), 256, 0, st>>>(
-      a1x, a1c, b1, alpha, h1, B, H, npass, R, slope);
+  launch_k(trunk1_combine_kernel, grid_for(static_cast<int64_t>(npass) * B * H, 256), 256, 0, st, a1x, a1c, b1, alpha, h1, B, H, npass, R, slope);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -454,6 +467,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __global__ void rowdot_bias_kernel(const float* __restrict__ h2f, const float* __restrict__ w3,
                                    const float* __restrict__ b3, float* __restrict__ score, int rows, int H) {
+  pdl_entry();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -464,13 +478,14 @@ __global__ void rowdot_bias_kernel(const float* __restrict__ h2f, const float* _
 }
 int k_rowdot_bias(const float* h2f, const float* w3, const float* b3, float* score, int rows, int H,
                   cudaStream_t st) {
-  rowdot_bias_kernel<<<(rows + 7) / 8, 256, 0, st>>>(h2f, w3, b3, score, rows, H);
+  launch_k(rowdot_bias_kernel, (rows + 7) / 8, 256, 0, st, h2f, w3, b3, score, rows, H);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 __global__ void gp_u2_kernel(const bf16* __restrict__ h2i, const float* __restrict__ w3, bf16* __restrict__ u2,
                              int B, int H, float slope) {
+  pdl_entry();
   const int64_t total = static_cast<int64_t>(B) * H;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -480,7 +495,7 @@ __global__ void gp_u2_kernel(const bf16* __restrict__ h2i, const float* __restri
   }
 }
 int k_gp_u2(const bf16* h2i, const float* w3, bf16* u2, int B, int H, float slope, cudaStream_t st) {
-  gp_u2_kernel<<<grid_for(static_cast<int64_t>(B) * H, 256), 256, 0, st>>>(h2i, w3, u2, B, H, slope);
+  launch_k(gp_u2_kernel, grid_for(static_cast<int64_t>(B) * H, 256), 256, 0, st, h2i, w3, u2, B, H, slope);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -490,6 +505,7 @@ __global__ void gp_rows_kernel(const float* __restrict__ y, const float* __restr
                                const bf16* __restrict__ h1i, float* __restrict__ norms, float* __restrict__ pen,
                                bf16* __restrict__ ru1, bf16* __restrict__ dv1, int B, int H, float slope,
                                float gp_weight, float inv_batch) {
+  pdl_entry();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -512,7 +528,7 @@ __global__ void gp_rows_kernel(const float* __restrict__ y, const float* __restr
 }
 int k_gp_rows(const float* y, const float* u1f, const bf16* h1i, float* norms, float* pen, bf16* ru1, bf16* dv1,
               int B, int H, float slope, float gp_weight, float inv_batch, cudaStream_t st) {
-  gp_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(y, u1f, h1i, norms, pen, ru1, dv1, B, H, slope, gp_weight,
+  launch_k(gp_rows_kernel, (B + 7) / 8, 256, 0, st, y, u1f, h1i, norms, pen, ru1, dv1, B, H, slope, gp_weight,
                                              inv_batch);
   GG_LAUNCH_CHECK();
   return GG_OK;
@@ -521,6 +537,7 @@ int k_gp_rows(const float* y, const float* u1f, const bf16* h1i, float* norms, f
 __global__ void score_bwd_kernel(const bf16* __restrict__ h2, const float* __restrict__ w3, bf16* __restrict__ da2,
                                  float* __restrict__ roww, int rows, int B, int H, float slope, float s0, float s1,
                                  float inv_batch) {
+  pdl_entry();
   const int64_t total = static_cast<int64_t>(rows) * H;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -534,8 +551,7 @@ __global__ void score_bwd_kernel(const bf16* __restrict__ h2, const float* __res
 }
 int k_score_bwd(const bf16* h2, const float* w3, bf16* da2, float* roww, int rows, int B, int H, float slope,
                 float sign_first, float sign_second, float inv_batch, cudaStream_t st) {
-  score_bwd_kernel<<<grid_for(static_cast<int64_t>(rows) * H, 256), 256, 0, st>>>(
-      h2, w3, da2, roww, rows, B, H, slope, sign_first, sign_second, inv_batch);
+  launch_k(score_bwd_kernel, grid_for(static_cast<int64_t>(rows) * H, 256), 256, 0, st, h2, w3, da2, roww, rows, B, H, slope, sign_first, sign_second, inv_batch);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -556,6 +572,7 @@ __device__ float block_sum_ordered(float v, float* sm) {
 
 __global__ void disc_losses_kernel(const float* __restrict__ score, const float* __restrict__ pen,
                                    float* __restrict__ stats, int B, float gp_weight, float inv_batch) {
+  pdl_entry();
   __shared__ float sm[256];
   float f = 0.f, r = 0.f, p = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -576,11 +593,12 @@ __global__ void disc_losses_kernel(const float* __restrict__ score, const float*
 }
 int k_disc_losses(const float* score, const float* pen, float* stats, int B, float gp_weight, float inv_batch,
                   cudaStream_t st) {
-  disc_losses_kernel<<<1, 256, 0, st>>>(score, pen, stats, B, gp_weight, inv_batch);
+  launch_k(disc_losses_kernel, 1, 256, 0, st, score, pen, stats, B, gp_weight, inv_batch);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 __global__ void gen_loss_kernel(const float* __restrict__ score, float* __restrict__ stats, int B, float inv_batch) {
+  pdl_entry();
   __shared__ float sm[256];
   float f = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) f += score[b];
@@ -588,25 +606,27 @@ __global__ void gen_loss_kernel(const float* __restrict__ score, float* __restri
   if (threadIdx.x == 0) stats[4] = -f * inv_batch;
 }
 int k_gen_loss(const float* score, float* stats, int B, float inv_batch, cudaStream_t st) {
-  gen_loss_kernel<<<1, 256, 0, st>>>(score, stats, B, inv_batch);
+  launch_k(gen_loss_kernel, 1, 256, 0, st, score, stats, B, inv_batch);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 __global__ void fill_f32_kernel(float* p, float v, int64_t n) {
+  pdl_entry();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     p[i] = v;
 }
 int k_fill_f32(float* p, float v, int64_t n, cudaStream_t st) {
   if (n <= 0) return GG_OK;
-  fill_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, v, n);
+  launch_k(fill_f32_kernel, grid_for(n, 256), 256, 0, st, p, v, n);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
-__global__ void bump_rng_kernel(uint64_t* rng) { rng[1] += 1; }
+__global__ void bump_rng_kernel(uint64_t* rng) {
+  pdl_entry(); rng[1] += 1; }
 int k_bump_rng(uint64_t* rng, cudaStream_t st) {
-  bump_rng_kernel<<<1, 1, 0, st>>>(rng);
+  launch_k(bump_rng_kernel, 1, 1, 0, st, rng);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -17,6 +17,7 @@
 //   src/conditional_gan_cross_attention_with_film.py:56-72,129-162,197-231 (reference).
 #include "epilogue.cuh"
 #include "host_util.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 #include <mutex>
@@ -39,22 +40,25 @@ struct GemmArgs {
   gg_epilogue epi;
 };
 
-constexpr int EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int SLOT_BYTES = 4096;   // one 32-row x 128-byte box of the output, 128B-swizzled
-constexpr int SLOTS_PER_WARP = 2;
 
-template <int BN, int STAGES>
+// EPIW epilogue warps (4 or 8). The 8-warp configurations own an SM (deep TMA ring, two staging slots per
+// warp); the 4-warp "light" configuration fits twice on an SM (2-stage ring, one slot per warp, <= 32 K
+// registers), so that for short-K tiles one CTA's load latency is covered by the other CTA's math.
+template <int BN, int STAGES, int EPIW>
 struct TileCfg {
+  static constexpr int THREADS = 64 + EPIW * 32;
+  static constexpr int CTAS_PER_SM = EPIW == 4 ? 2 : 1;
+  static constexpr int SLOTS_PER_WARP = EPIW == 4 ? 1 : 2;
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   // epilogue: warp w drains TMEM lanes [32*(w%4), +32) (a hardware rule) and COLS_PER_WARP columns.
   // BN = 64 keeps only four epilogue warps busy.
-  static constexpr int ACTIVE_EPI_WARPS = BN == 64 ? 4 : 8;
-  static constexpr int COLS_PER_WARP = BN == 64 ? 64 : BN / 2;
+  static constexpr int ACTIVE_EPI_WARPS = (BN == 64 || EPIW == 4) ? 4 : 8;
+  static constexpr int COLS_PER_WARP = ACTIVE_EPI_WARPS == 4 ? BN : BN / 2;
   static constexpr int CHUNKS = COLS_PER_WARP / 32;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_BYTES = EPI_WARPS * SLOTS_PER_WARP * SLOT_BYTES;
+  static constexpr int STAGING_BYTES = EPIW * SLOTS_PER_WARP * SLOT_BYTES;
   static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;  // full/empty per stage + tmem full/empty x 2
   static constexpr int SMEM_BYTES = BAR_OFFSET + NUM_BARS * 8 + 16 + 1024;
@@ -70,13 +74,14 @@ struct TileCfg {
 // 16-byte writes into a 128B-swizzled staging box -> one TMA store per box (bf16: 32 rows x 64 columns,
 // fp32: 32 x 32; the hardware clips the M / N tails). Outputs whose pitch or base is not 16-byte
 // aligned, row-remapped outputs and split-K partials take direct per-row vector stores instead.
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int STAGES, int EPIW>
+__global__ void __launch_bounds__(TileCfg<BN, STAGES, EPIW>::THREADS, TileCfg<BN, STAGES, EPIW>::CTAS_PER_SM)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                    const __grid_constant__ CUtensorMap tmOutB, const __grid_constant__ CUtensorMap tmOutF,
                    const GemmArgs g) {
-  using Cfg = TileCfg<BN, STAGES>;
+  using Cfg = TileCfg<BN, STAGES, EPIW>;
+  constexpr int SLOTS_PER_WARP = Cfg::SLOTS_PER_WARP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
@@ -121,6 +126,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
+  // everything above (barriers, TMEM, descriptor prefetch) touched no tensor: it overlaps the previous kernel
+  pdl_entry();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -204,11 +211,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   } else if (warp - 2 < Cfg::ACTIVE_EPI_WARPS) {
     const int ew = warp - 2;   // 0..7
     const int q = warp & 3;    // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int hsel = ew >> 2;  // which run of COLS_PER_WARP columns this warp drains
+    const int hsel = Cfg::ACTIVE_EPI_WARPS == 4 ? 0 : (ew >> 2);  // which run of COLS_PER_WARP columns this warp drains
     uint8_t* slots = smem + Cfg::STAGING_OFFSET + ew * (SLOTS_PER_WARP * SLOT_BYTES);
     const uint32_t lane_row = static_cast<uint32_t>(lane) * 128u;
     const uint32_t swz = static_cast<uint32_t>(lane & 7);
     const bool tma_b = g.tma_out_bf16 != 0, tma_f = g.tma_out_f32 != 0;
+    const bool dual = tma_b && tma_f && SLOTS_PER_WARP > 1;
     int slot = 0;
     uint8_t* bslot = slots;  // staging box of the bf16 output (spans two chunks)
     int it = 0;
@@ -255,9 +263,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (live && ((g.epi.out_f32 && !tma_f) || (g.epi.out_bf16 && !tma_b)))
           epilogue_store<32>(g.epi, m, n0, ncols, v, !tma_f, !tma_b);
         if (tma_f && ncols > 0) {
-          slot ^= 1;
-          uint8_t* fs = slots + slot * SLOT_BYTES;
-          if (lane == 0) tma_store_wait_read<SLOTS_PER_WARP - 1>();
+          uint8_t* fs;
+          if (dual) {  // both outputs: fixed slots (0 = the bf16 box that spans two chunks, 1 = fp32)
+            fs = slots + SLOT_BYTES;
+            if (lane == 0) tma_store_wait_read<0>();
+          } else {
+            slot = (slot + 1) % SLOTS_PER_WARP;
+            fs = slots + slot * SLOT_BYTES;
+            if (lane == 0) tma_store_wait_read<SLOTS_PER_WARP - 1>();
+          }
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -273,9 +287,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (tma_b) {
           const int half = c & 1;
           if (half == 0 && ncols > 0) {
-            slot ^= 1;
-            bslot = slots + slot * SLOT_BYTES;
-            if (lane == 0) tma_store_wait_read<SLOTS_PER_WARP - 1>();
+            if (dual) {
+              bslot = slots;
+              if (lane == 0) tma_store_wait_read<0>();
+            } else {
+              slot = (slot + 1) % SLOTS_PER_WARP;
+              bslot = slots + slot * SLOT_BYTES;
+              if (lane == 0) tma_store_wait_read<SLOTS_PER_WARP - 1>();
+            }
             __syncwarp();
           }
           if (ncols > 0) {
@@ -313,6 +332,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 __global__ void __launch_bounds__(256)
     splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N,
                          const gg_epilogue epi) {
+  pdl_entry();
   const int chunks = (N + 3) / 4;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(M) * chunks) return;
@@ -351,6 +371,7 @@ __global__ void __launch_bounds__(128)
     gemm_simt_kernel(const __nv_bfloat16* a0, const __nv_bfloat16* b0, int64_t lda0, int64_t ldb0,
                      int K0, const __nv_bfloat16* a1, const __nv_bfloat16* b1, int64_t lda1,
                      int64_t ldb1, int K1, int M, int N, int a_mn, int b_mn, const gg_epilogue epi) {
+  pdl_entry();
   const int chunks = (N + 31) / 32;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(M) * chunks) return;
@@ -446,13 +467,13 @@ struct GemmProfile {
 };
 static GemmProfile g_prof;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPIW>
 static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t stream) {
-  using Cfg = TileCfg<BN, STAGES>;
+  using Cfg = TileCfg<BN, STAGES, EPIW>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>,
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPIW>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   GG_CUDA_CHECK(attr_err);
@@ -463,7 +484,8 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
     GG_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int64_t work = static_cast<int64_t>(ceil_div(args.N, BN)) * ceil_div(args.M, BM) * args.splits;
-  dim3 grid(static_cast<unsigned>(work < num_sms ? work : num_sms));
+  const int64_t slots = static_cast<int64_t>(num_sms) * Cfg::CTAS_PER_SM;
+  dim3 grid(static_cast<unsigned>(work < slots ? work : slots));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
     if (g_prof.used + 2 > g_prof.ev.size()) {
@@ -481,8 +503,8 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
     g_prof.rec.push_back(GemmRecord{args.M, args.N, args.K0, args.K1, BN, args.splits, args.a_mn, args.b_mn});
     GG_CUDA_CHECK(cudaEventRecord(e0, stream));
   }
-  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2],
-                                                                     maps[3], maps[4], maps[5], args);
+  launch_k(gemm_tc_kernel<BN, STAGES, EPIW>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, maps[0], maps[1], maps[2],
+                                                                           maps[3], maps[4], maps[5], args);
   GG_LAUNCH_CHECK();
   if (e1) GG_CUDA_CHECK(cudaEventRecord(e1, stream));
   return GG_OK;
@@ -503,8 +525,7 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
     const gg_gemm_seg& s1 = d->seg[1];
     const int chunks = ceil_div(d->N, 32);
     const int64_t work = static_cast<int64_t>(d->M) * chunks;
-    gemm_simt_kernel<<<static_cast<unsigned>((work + 127) / 128), 128, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(s0.a), reinterpret_cast<const __nv_bfloat16*>(s0.b),
+    launch_k(gemm_simt_kernel, static_cast<unsigned>((work + 127) / 128), 128, 0, stream, reinterpret_cast<const __nv_bfloat16*>(s0.a), reinterpret_cast<const __nv_bfloat16*>(s0.b),
         s0.lda, s0.ldb, s0.K, reinterpret_cast<const __nv_bfloat16*>(d->nseg > 1 ? s1.a : nullptr),
         reinterpret_cast<const __nv_bfloat16*>(d->nseg > 1 ? s1.b : nullptr),
         d->nseg > 1 ? s1.lda : 0, d->nseg > 1 ? s1.ldb : 0, d->nseg > 1 ? s1.K : 0, d->M, d->N,
@@ -584,16 +605,19 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
     if (rc) return rc;
   }
 
+  // short-K, many-tile GEMMs (the tower's [rows, 256..512] x [N, K] products): two light CTAs per SM
+  // (measured on B200: no faster than the one-CTA configuration on these shapes, so it is opt-in only)
+  bool light = d->light > 0 && bn == 128 && splits == 1 && !(args.tma_out_bf16 && args.tma_out_f32);
   int rc;
-  if (bn == 64) rc = launch_tc<64, 6>(maps, args, stream);
-  else if (bn == 128) rc = launch_tc<128, 4>(maps, args, stream);
-  else rc = launch_tc<256, 3>(maps, args, stream);
+  if (bn == 64) rc = launch_tc<64, 6, 8>(maps, args, stream);
+  else if (bn == 128 && light) rc = launch_tc<128, 2, 4>(maps, args, stream);
+  else if (bn == 128) rc = launch_tc<128, 4, 8>(maps, args, stream);
+  else rc = launch_tc<256, 3, 8>(maps, args, stream);
   if (rc) return rc;
 
   if (splits > 1) {
     const int64_t work = static_cast<int64_t>(d->M) * ceil_div(d->N, 4);
-    splitk_reduce_kernel<<<static_cast<unsigned>((work + 255) / 256), 256, 0, stream>>>(
-        args.partial, splits, d->M, d->N, d->epi);
+    launch_k(splitk_reduce_kernel, static_cast<unsigned>((work + 255) / 256), 256, 0, stream, args.partial, splits, d->M, d->N, d->epi);
     GG_LAUNCH_CHECK();
   }
   return GG_OK;

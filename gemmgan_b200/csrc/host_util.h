@@ -42,6 +42,30 @@ extern std::atomic<long long> g_launch_count;  // kernels launched by this libra
     }                                    \
   } while (0)
 
+// Programmatic dependent launch (PDL): every kernel of this library starts with pdl_entry() (griddepcontrol.wait,
+// then griddepcontrol.launch_dependents) and is launched with the programmatic-stream-serialization attribute,
+// so the launch latency and the prologue of kernel n+1 (block scheduling, barrier init, TMEM allocation,
+// tensor-map prefetch) overlap the body of kernel n instead of following its tail. Nothing is read or written
+// before the wait, which orders a kernel after the complete predecessor (and, by induction, after everything
+// earlier in the stream). GEMMGAN_PDL=0 launches without the attribute (the instructions are then no-ops).
+bool pdl_enabled();
+
+template <class... KArgs, class... Args>
+static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through GG_LAUNCH_CHECK()
+}
+
 #define GG_TRY_RC(x)        \
   do {                      \
     int _rc = (x);          \

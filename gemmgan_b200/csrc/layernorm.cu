@@ -9,6 +9,7 @@
 // post-norm branch used at src/conditional_gan_cross_attention_with_film.py:114-119,144
 // (torch/nn/modules/transformer.py, norm_first=False).
 #include "host_util.h"
+#include "pdl.cuh"
 #include "kernels.h"
 #include "philox.cuh"
 
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(256)
                       const float* __restrict__ b, bf16* __restrict__ z, bf16* __restrict__ out,
                       float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int E, float eps,
                       float drop_p, const uint64_t* __restrict__ rng, uint32_t site) {
+  pdl_entry();
   using IO = RowIO<PER, VEC>;
   constexpr int N = IO::N;
   const int lane = threadIdx.x & 31;
@@ -172,7 +174,7 @@ int k_add_ln_fwd(const bf16* x, const bf16* y, const float* w, const float* b, b
   if (blocks > 148 * 8) blocks = 148 * 8;
   const unsigned gb = static_cast<unsigned>(blocks);
 #define LN_FWD(PER, VEC) \
-  add_ln_fwd_kernel<PER, VEC><<<gb, 256, 0, st>>>(x, y, w, b, z, out, mean, rstd, rows, E, eps, drop_p, rng, site)
+  launch_k(add_ln_fwd_kernel<PER, VEC>, gb, 256, 0, st, x, y, w, b, z, out, mean, rstd, rows, E, eps, drop_p, rng, site)
   if (E == 256) LN_FWD(1, true);
   else if (E == 512) LN_FWD(2, true);
   else if (E == 768 || E == 1024) {
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(256)
                       const float* __restrict__ rstd, const float* __restrict__ w, bf16* __restrict__ dz,
                       bf16* __restrict__ dy, float* __restrict__ partial, int64_t rows, int E, float drop_p,
                       const uint64_t* __restrict__ rng, uint32_t site) {
+  pdl_entry();
   using IO = RowIO<PER, VEC>;
   constexpr int N = IO::N;
   extern __shared__ float sm[];  // [8 warps][2E]
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     ln_bwd_finish_kernel(const float* __restrict__ partial, int nblocks, int E, float* __restrict__ dw,
                          float* __restrict__ db) {
+  pdl_entry();
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= 2 * E) return;
@@ -297,7 +301,7 @@ static int launch_ln_bwd(int blocks, size_t smem, cudaStream_t st, const bf16* d
       set = true;
     }
   }
-  add_ln_bwd_kernel<PER, VEC><<<blocks, 256, smem, st>>>(dout, z, mean, rstd, w, dz, dy, scratch, rows, E, drop_p,
+  launch_k(add_ln_bwd_kernel<PER, VEC>, blocks, 256, smem, st, dout, z, mean, rstd, w, dz, dy, scratch, rows, E, drop_p,
                                                          rng, site);
   GG_LAUNCH_CHECK();
   return GG_OK;
@@ -322,7 +326,7 @@ int k_add_ln_bwd(const bf16* dout, const bf16* z, const float* mean, const float
 // dw / db from the per-block partials k_add_ln_bwd left in `scratch` (call it with dw = NULL to defer this)
 int k_ln_bwd_finish(const float* scratch, int64_t rows, int E, float* dw, float* db, cudaStream_t st) {
   const int blocks = ln_bwd_blocks(rows);
-  ln_bwd_finish_kernel<<<(2 * E + 7) / 8, 256, 0, st>>>(scratch, blocks, E, dw, db);
+  launch_k(ln_bwd_finish_kernel, (2 * E + 7) / 8, 256, 0, st, scratch, blocks, E, dw, db);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

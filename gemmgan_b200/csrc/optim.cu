@@ -7,6 +7,7 @@
 // Update rules follow torch 2.11 defaults: RMSprop(alpha=.99, eps=1e-8, no momentum, not centered),
 // Adam(betas=(.9,.99), eps=1e-8), AdamW(weight_decay=.01); clip: coef = min(1, max/(norm+1e-6)).
 #include "host_util.h"
+#include "pdl.cuh"
 #include "kernels.h"
 
 namespace gg {
@@ -15,6 +16,7 @@ constexpr int NORM_BLOCKS = 592;  // 4 per SM; fixed so the reduction order neve
 
 __global__ void __launch_bounds__(256) sumsq_stage1_kernel(const float* __restrict__ g, int64_t n,
                                                            float* __restrict__ partial) {
+  pdl_entry();
   __shared__ float sm[256];
   const int64_t per = (n + gridDim.x - 1) / gridDim.x;
   const int64_t lo = per * blockIdx.x;
@@ -35,6 +37,7 @@ __global__ void __launch_bounds__(256) sumsq_stage1_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) sumsq_stage2_kernel(const float* __restrict__ partial, int nparts,
                                                            float max_norm, float* __restrict__ out) {
+  pdl_entry();
   __shared__ double sm[256];
   double acc = 0.0;
   for (int i = threadIdx.x; i < nparts; i += 256) acc += static_cast<double>(partial[i]);
@@ -57,9 +60,9 @@ __global__ void __launch_bounds__(256) sumsq_stage2_kernel(const float* __restri
 }
 int k_grad_norm_clip(const float* g, int64_t n, float max_norm, float* norm_out, float* scratch,
                      cudaStream_t st) {
-  sumsq_stage1_kernel<<<NORM_BLOCKS, 256, 0, st>>>(g, n, scratch);
+  launch_k(sumsq_stage1_kernel, NORM_BLOCKS, 256, 0, st, g, n, scratch);
   GG_LAUNCH_CHECK();
-  sumsq_stage2_kernel<<<1, 256, 0, st>>>(scratch, NORM_BLOCKS, max_norm, norm_out);
+  launch_k(sumsq_stage2_kernel, 1, 256, 0, st, scratch, NORM_BLOCKS, max_norm, norm_out);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -84,6 +87,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256)
     optim_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int64_t n, float lr, const float* __restrict__ coef_ptr, const float* __restrict__ step_count) {
+  pdl_entry();
   const float coef = coef_ptr ? coef_ptr[0] : 1.f;
   float bc1 = 1.f, rsqrt_bc2 = 1.f;
   if (KIND != GG_OPT_RMSPROP) {
@@ -120,7 +124,8 @@ __global__ void __launch_bounds__(256)
     if (write_g) g[i] = G;
   }
 }
-__global__ void bump_step_kernel(float* step_count) { step_count[0] += 1.f; }
+__global__ void bump_step_kernel(float* step_count) {
+  pdl_entry(); step_count[0] += 1.f; }
 
 int k_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, float lr, const float* coef_ptr,
                  float* step_count, cudaStream_t st) {
@@ -131,15 +136,15 @@ int k_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, fl
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   const unsigned gb = static_cast<unsigned>(blocks);
-  if (kind == GG_OPT_RMSPROP) optim_kernel<GG_OPT_RMSPROP><<<gb, 256, 0, st>>>(p, g, m, v, n, lr, coef_ptr, step_count);
-  else if (kind == GG_OPT_ADAM) optim_kernel<GG_OPT_ADAM><<<gb, 256, 0, st>>>(p, g, m, v, n, lr, coef_ptr, step_count);
-  else if (kind == GG_OPT_ADAMW) optim_kernel<GG_OPT_ADAMW><<<gb, 256, 0, st>>>(p, g, m, v, n, lr, coef_ptr, step_count);
+  if (kind == GG_OPT_RMSPROP) launch_k(optim_kernel<GG_OPT_RMSPROP>, gb, 256, 0, st, p, g, m, v, n, lr, coef_ptr, step_count);
+  else if (kind == GG_OPT_ADAM) launch_k(optim_kernel<GG_OPT_ADAM>, gb, 256, 0, st, p, g, m, v, n, lr, coef_ptr, step_count);
+  else if (kind == GG_OPT_ADAMW) launch_k(optim_kernel<GG_OPT_ADAMW>, gb, 256, 0, st, p, g, m, v, n, lr, coef_ptr, step_count);
   else {
     set_error("unknown optimizer kind %d", kind);
     return GG_ERR_ARG;
   }
   GG_LAUNCH_CHECK();
-  bump_step_kernel<<<1, 1, 0, st>>>(step_count);
+  launch_k(bump_step_kernel, 1, 1, 0, st, step_count);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -147,6 +152,7 @@ int k_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, fl
 // One (segment, 4-column run) per thread iteration: float4 load, 8-byte bf16x4 store, 32-bit index math.
 __global__ void __launch_bounds__(256)
     refresh_shadows_kernel(const float* __restrict__ p, bf16* __restrict__ shadow, const ShadowSeg* __restrict__ segs) {
+  pdl_entry();
   const ShadowSeg s = segs[blockIdx.y];
   const float* src = p + s.p_off + s.col0;
   bf16* dst = shadow + s.s_off;
@@ -178,7 +184,7 @@ int k_refresh_shadows(const float* p, bf16* shadow, const ShadowSeg* segs_dev, i
                       cudaStream_t st) {
   if (nseg <= 0) return GG_OK;
   dim3 grid(148, nseg);
-  refresh_shadows_kernel<<<grid, 256, 0, st>>>(p, shadow, segs_dev);
+  launch_k(refresh_shadows_kernel, grid, 256, 0, st, p, shadow, segs_dev);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -13,6 +13,7 @@
 // src/conditional_gan_cross_attention_with_film.py:108-123, 157-162 executed inside disc_loss.backward() /
 // gen_loss.backward() (:412, :455).
 #include "host_util.h"
+#include "pdl.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -115,6 +116,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
+  // everything above (barriers, TMEM, descriptor prefetch) touched no tensor: it overlaps the previous kernel
+  pdl_entry();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -410,7 +413,7 @@ int k_wgrad_group(const WgradItem* items, int n, void* workspace, int64_t worksp
   }
   P.total_work = work;
   const unsigned grid = static_cast<unsigned>(work < num_sms ? work : num_sms);
-  wgrad_group_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(P);
+  launch_k(wgrad_group_kernel, grid, THREADS, SMEM_BYTES, st, P);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -107,6 +107,8 @@ typedef struct gg_gemm_desc {
   int32_t impl;             /* GG_IMPL_* */
   int32_t force_splits;     /* 0 = heuristic */
   int32_t block_n;          /* 0 = heuristic; 64, 128 or 256 */
+  int32_t light;            /* 0 = heuristic; 1 = force, -1 = forbid the two-CTAs-per-SM configuration (128-wide
+                               tiles, no split-K) used for short-K products with many tiles */
 } gg_gemm_desc;
 
 int gg_gemm_bf16(const gg_gemm_desc* desc, void* stream);

@@ -97,6 +97,30 @@ def test_gemm_two_segments_row_map_and_film():
     assert (of - want).abs().max().item() <= 1e-4
 
 
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(27648, 768, 256, 0, 0), (18432, 256, 512, 0, 1), (1000, 200, 136, 0, 0),
+                                              (300, 264, 64, 1, 1)])
+def test_gemm_light_configuration(M, N, K, a_mn, b_mn):
+    """The two-CTAs-per-SM configuration (4 epilogue warps, 2-stage ring) computes the same thing."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _mk(K, M, g) if a_mn else _mk(M, K, g)
+    b = _mk(K, N, g) if b_mn else _mk(N, K, g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = _mk(M, N, g)
+    outs = []
+    for light in (1, -1):
+        ob = torch.zeros(M, (N + 7) // 8 * 8, device="cuda", dtype=torch.bfloat16)
+        of = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+        ops.gemm(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), bias=bias, act=_lib.ACT_LEAKY, slope=0.1, res=res,
+                 out_bf16=ob[:, :N], block_n=128, light=light)
+        ops.gemm(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), bias=bias, act=_lib.ACT_LEAKY, slope=0.1, res=res,
+                 out_f32=of, block_n=128, light=light)
+        outs.append((ob, of))
+    torch.cuda.synchronize()
+    want = _leaky(_ref(a, b, a_mn, b_mn) + bias, 0.1) + res.float()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert (outs[0][1] - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+
+
 @pytest.mark.parametrize("bn", [64, 128, 256])
 def test_gemm_dropout_matches_check_kernel(bn):
     """Dropout is a pure function of (seed, step, site, element index): the tensor-core kernel and the
