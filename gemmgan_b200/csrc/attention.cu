@@ -479,97 +479,100 @@ __global__ void __launch_bounds__(128) attn_small_kv_kernel(const AttnArgs a, co
 
 // ------------------------------------------------------- short self-attention, head_dim 64 (the tower)
 // S = Lq = Lk <= 16 tokens, hd = 64: the encoder layers of the paper / FiLM models at P = 8 patches.
-// One thread per (sequence, head, token) row with all 64 head dims in registers; a CTA owns SELF_GROUPS
-// (sequence, head) groups whose Q / K / V (/ dO) rows are staged in shared memory with coalesced 16-byte
-// loads (row pitch 144 B: conflict-free 16-byte reads). Scores never leave registers. The backward is one
-// kernel: pass A (thread = query row) recomputes the probabilities, writes dQ and leaves dS / dropped P in
-// shared memory; pass B (thread = key row) forms dK, dV from them (no atomics, deterministic).
+// One WARP per (sequence, head): the 16x16 score tile and the 16x64 outputs are m16n8k16 tensor-core
+// fragments (mma.sync, bf16 in / fp32 accumulate — a 9x9 problem is far below the 128-row tcgen05 tile; the
+// op is memory bound and this keeps it at a few hundred instructions per sequence). Q / K / V (/ dO) rows of
+// the CTA's four groups are staged with 16-byte cp.async (rows >= S zero-filled), fragments come from
+// ldmatrix. The backward is one kernel: S and P are recomputed, dP = dO V^T, dS = P o (dP - delta),
+// dQ = dS K, and dK = dS^T Q, dV = P^T dO go through a bf16 copy of dS / P in shared memory (ldmatrix.trans);
+// no atomics, deterministic.
 constexpr int SELF_HD = 64;
-constexpr int SELF_PITCH = SELF_HD + 8;  // bf16 elements
-constexpr int SELF_THREADS = 128;
+constexpr int SELF_PITCH = SELF_HD + 8;   // bf16 elements: 144-byte rows, conflict-free ldmatrix
+constexpr int SELF_GROUPS = 4;            // warps = (sequence, head) groups per CTA
+constexpr int SELF_THREADS = SELF_GROUPS * 32;
+constexpr int SELF_TILE = 16 * SELF_PITCH;  // one 16-row tile (elements)
+constexpr int SELF_SP = 24;               // pitch of the 16x16 bf16 dS / P tiles
 
-struct SelfGeom {
-  int G;       // groups per CTA
-  int rows;    // G * S
-};
-__host__ __device__ inline SelfGeom self_geom(int S) {
-  SelfGeom g;
-  g.G = SELF_THREADS / S;
-  g.rows = g.G * S;
-  return g;
-}
-
-// cooperative copy of nrows x 64 bf16 rows of up to four tensors into smem (pitch SELF_PITCH) with 16-byte
-// cp.async (no register staging: every load of the CTA is in flight at once). off(t, r) = element offset of
-// row r of tensor t (head column included), or -1 beyond the last group (zero-filled).
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
-template <int NT, class OffFn>
-__device__ __forceinline__ void self_stage(bf16* const* dst, const bf16* const* src, int nrows, OffFn off) {
-  const int n = nrows * 8;
-  for (int c = threadIdx.x; c < n; c += SELF_THREADS) {
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      const int64_t o = off(t, c >> 3);
-      cp_async16(dst[t] + (c >> 3) * SELF_PITCH + (c & 7) * 8, src[t] + (o >= 0 ? o : 0) + (c & 7) * 8, o >= 0);
-    }
-  }
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
-__device__ __forceinline__ void self_row_f32(const bf16* row, float* v) {
-#pragma unroll
-  for (int d = 0; d < SELF_HD; d += 8) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + d);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 f = __bfloat1622float2(h[q]);
-      v[d + 2 * q] = f.x;
-      v[d + 2 * q + 1] = f.y;
-    }
-  }
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
-__device__ __forceinline__ float self_dot(const float* q, const bf16* row) {
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains
-#pragma unroll
-  for (int d = 0; d < SELF_HD; d += 8) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + d);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 f = __bfloat1622float2(h[t]);
-      acc[t] = fmaf(q[d + 2 * t], f.x, acc[t]);
-      acc[t] = fmaf(q[d + 2 * t + 1], f.y, acc[t]);
-    }
-  }
-  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void self_axpy(float* acc, float w, const bf16* row) {
+__device__ __forceinline__ uint32_t pack_bf16(float x, float y) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_add(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// C[16 x 16] (2 n-tiles) = A[16 x 64] * B^T with B stored [16 rows (n)][64 (k)]: both row-major tiles in smem
+__device__ __forceinline__ void mma_ab_t(float (&c)[2][4], const bf16* A, const bf16* B, int lane) {
 #pragma unroll
-  for (int d = 0; d < SELF_HD; d += 8) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + d);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 f = __bfloat1622float2(h[t]);
-      acc[d + 2 * t] = fmaf(w, f.x, acc[d + 2 * t]);
-      acc[d + 2 * t + 1] = fmaf(w, f.y, acc[d + 2 * t + 1]);
-    }
+    for (int j = 0; j < 4; ++j) c[nt][j] = 0.f;
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
+  const int brow = (lane & 7) + (lane >> 4) * 8, bcol = ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int kk = 0; kk < SELF_HD / 16; ++kk) {
+    uint32_t a[4], b[4];
+    ldsm_x4(a, A + arow * SELF_PITCH + kk * 16 + acol);
+    ldsm_x4(b, B + brow * SELF_PITCH + kk * 16 + bcol);
+    mma16816(c[0], a, b[0], b[1]);
+    mma16816(c[1], a, b[2], b[3]);
   }
 }
-__device__ __forceinline__ void self_store_row(bf16* dst, const float* v, float scale) {
+// O[16 x 64] (8 n-tiles) = A[16 x 16] (fragments) * B with B stored [16 rows (k)][64 (n)] row-major in smem
+__device__ __forceinline__ void mma_frag_b(float (&o)[8][4], const uint32_t (&a)[4], const bf16* B, int lane) {
+  const int brow = (lane & 7) + ((lane >> 3) & 1) * 8, bcol = (lane >> 4) * 8;
 #pragma unroll
-  for (int d = 0; d < SELF_HD; d += 8) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+  for (int np = 0; np < 4; ++np) {
+    uint32_t b[4];
+    ldsm_x4_t(b, B + brow * SELF_PITCH + np * 16 + bcol);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[d + 2 * t] * scale, v[d + 2 * t + 1] * scale);
-    *reinterpret_cast<uint4*>(dst + d) = u;
+    for (int j = 0; j < 4; ++j) o[2 * np][j] = o[2 * np + 1][j] = 0.f;
+    mma16816(o[2 * np], a, b[0], b[1]);
+    mma16816(o[2 * np + 1], a, b[2], b[3]);
   }
+}
+// fragments (rows g / g+8, cols nt*8 + 2t) -> bf16 rows in a smem tile, then the first S rows -> global
+__device__ __forceinline__ void store_tile(bf16* stage, const float (&o)[8][4], float scale, bf16* gdst, int64_t ld,
+                                           int S, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t*>(stage + g * SELF_PITCH + nt * 8 + 2 * t) = pack_bf16(o[nt][0] * scale, o[nt][1] * scale);
+    *reinterpret_cast<uint32_t*>(stage + (g + 8) * SELF_PITCH + nt * 8 + 2 * t) = pack_bf16(o[nt][2] * scale, o[nt][3] * scale);
+  }
+  __syncwarp();
+  for (int c = lane; c < S * 8; c += 32) {
+    const int r = c >> 3, part = c & 7;
+    *reinterpret_cast<uint4*>(gdst + static_cast<int64_t>(r) * ld + part * 8) =
+        *reinterpret_cast<const uint4*>(stage + r * SELF_PITCH + part * 8);
+  }
+  __syncwarp();
 }
 
 // MODE 0: forward. MODE 1: backward (dq, dk, dv).
@@ -578,142 +581,165 @@ __global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const Att
   pdl_entry();
   extern __shared__ __align__(16) uint8_t smem_self[];
   const int S = a.Lq;
-  const SelfGeom geo = self_geom(S);
-  bf16* Qs = reinterpret_cast<bf16*>(smem_self);
-  bf16* Ks = Qs + geo.rows * SELF_PITCH;
-  bf16* Vs = Ks + geo.rows * SELF_PITCH;
-  bf16* Gs = Vs + geo.rows * SELF_PITCH;                                    // dO (backward only)
-  float* sc = reinterpret_cast<float*>(Gs + (MODE == 1 ? geo.rows * SELF_PITCH : 0));  // [2][SM_MAXL][threads]
-  float* dS = sc + 2 * SM_MAXL * SELF_THREADS;                                          // [G][S][S] x 2
+  constexpr int NT = MODE == 1 ? 4 : 3;               // staged tensors: Q, K, V (, dO)
+  bf16* tiles = reinterpret_cast<bf16*>(smem_self);   // [group][NT + 1 (staging)][16][SELF_PITCH]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ngroups = static_cast<int64_t>(a.nb) * a.H;
-  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * geo.G;
-  auto off = [&](int t, int r) -> int64_t {
-    const int64_t gid = g0 + r / S;
-    if (gid >= ngroups) return -1;
-    const int64_t bb = gid / a.H, col = (gid % a.H) * SELF_HD;
-    const int tok = r % S;
-    if (t == 0) return ((bb % a.q_mod) * S + tok) * a.ldq + col;
-    if (t == 3) return (bb * S + tok) * a.lddo + col;
-    return ((bb % a.kv_mod) * S + tok) * a.ldkv + col;
-  };
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * SELF_GROUPS;
+  constexpr int PER_GROUP = (NT + 1) * SELF_TILE + (MODE == 1 ? 2 * 16 * SELF_SP : 0);
+  // ---- stage: thread = (row, 16-byte part) of every (group, tensor) tile; rows >= S and groups beyond the
+  // end are zero-filled. (b, h) advance incrementally: no per-chunk integer division.
   {
-    bf16* dsts[4] = {Qs, Ks, Vs, Gs};
-    const bf16* srcs[4] = {a.q, a.k, a.v, a.dout};
-    if (MODE == 1) self_stage<4>(dsts, srcs, geo.rows, off);
-    else self_stage<3>(dsts, srcs, geo.rows, off);
-  }
-  __syncthreads();
-  const int r = threadIdx.x;
-  const int g = r / S, i = r % S;
-  const int64_t gid = g0 + g;
-  const bool active = r < geo.rows && gid < ngroups;
-  const int b = active ? static_cast<int>(gid / a.H) : 0;
-  const int h = active ? static_cast<int>(gid % a.H) : 0;
-  const uint8_t* mk = (a.mask && active) ? a.mask + static_cast<int64_t>(b % a.mask_mod) * S : nullptr;
-  const float scale = 0.125f;  // 1/sqrt(64)
-  uint64_t seed = 0, step = 0;
-  if (a.drop_p > 0.f) {
-    seed = a.rng[0];
-    step = a.rng[1];
-  }
-  const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-  const bf16* Kg = Ks + g * S * SELF_PITCH;
-  const bf16* Vg = Vs + g * S * SELF_PITCH;
-  // per-thread score rows live in shared memory (column = thread => conflict-free), so the key loops stay
-  // rolled: fully unrolled they are ~50 KB of SASS and thrash the instruction cache
-  float* pr = sc + threadIdx.x;   // p_j   at pr[j * SELF_THREADS]
-  float* pd = pr + SM_MAXL * SELF_THREADS;  // dropped p_j (forward weight) / dP_j (backward)
-  if (active) {
-    float q[SELF_HD];
-    self_row_f32(Qs + r * SELF_PITCH, q);
-    float m = -INFINITY;
-#pragma unroll 1
-    for (int j = 0; j < S; ++j) {
-      float t = -INFINITY;
-      if (!(mk && mk[j])) t = self_dot(q, Kg + j * SELF_PITCH) * scale;
-      pr[j * SELF_THREADS] = t;
-      m = fmaxf(m, t);
-    }
-    float l = 0.f;
-#pragma unroll 1
-    for (int j = 0; j < S; ++j) {
-      const float t = pr[j * SELF_THREADS];
-      const float e = (t == -INFINITY) ? 0.f : __expf(t - m);
-      pr[j * SELF_THREADS] = e;
-      l += e;
-    }
-    const float inv_l = l > 0.f ? 1.f / l : 0.f;
-    const uint64_t pbase = ((static_cast<uint64_t>(b) * a.H + h) * S + i) * static_cast<uint64_t>(S);
-#pragma unroll 1
-    for (int j = 0; j < S; ++j) {
-      const float pj = pr[j * SELF_THREADS] * inv_l;
-      const bool keep = a.drop_p > 0.f ? dropout_keep(seed, step, a.site, pbase + j, a.drop_p) : true;
-      pr[j * SELF_THREADS] = pj;
-      pd[j * SELF_THREADS] = keep ? keep_scale : 0.f;  // dropout multiplier
-    }
-  }
-  if (MODE == 0) {
-    if (active) {
-      float acc[SELF_HD];
+    const int row = threadIdx.x >> 3, part = threadIdx.x & 7;
+    const uint32_t H = static_cast<uint32_t>(a.H);
+    uint32_t bb = static_cast<uint32_t>(g0 / H), hh = static_cast<uint32_t>(g0 % H);
 #pragma unroll
-      for (int d = 0; d < SELF_HD; ++d) acc[d] = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < S; ++j) self_axpy(acc, pr[j * SELF_THREADS] * pd[j * SELF_THREADS], Vg + j * SELF_PITCH);
-      self_store_row(a.o + (static_cast<int64_t>(b) * S + i) * a.ldo + h * SELF_HD, acc, 1.f);
+    for (int gi = 0; gi < SELF_GROUPS; ++gi) {
+      const bool valid = g0 + gi < ngroups && row < S;
+      const int col = static_cast<int>(hh) * SELF_HD + part * 8;
+      const int64_t qr = static_cast<int64_t>(a.q_mod >= a.nb ? bb : bb % static_cast<uint32_t>(a.q_mod)) * S + row;
+      const int64_t kr = static_cast<int64_t>(a.kv_mod >= a.nb ? bb : bb % static_cast<uint32_t>(a.kv_mod)) * S + row;
+      bf16* dst = tiles + gi * PER_GROUP + row * SELF_PITCH + part * 8;
+      cp_async16(dst, valid ? a.q + qr * a.ldq + col : a.q, valid);
+      cp_async16(dst + SELF_TILE, valid ? a.k + kr * a.ldkv + col : a.q, valid);
+      cp_async16(dst + 2 * SELF_TILE, valid ? a.v + kr * a.ldkv + col : a.q, valid);
+      if (MODE == 1)
+        cp_async16(dst + 3 * SELF_TILE, valid ? a.dout + (static_cast<int64_t>(bb) * S + row) * a.lddo + col : a.q, valid);
+      if (++hh == H) {
+        hh = 0;
+        ++bb;
+      }
     }
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  const int64_t gid = g0 + warp;
+  if (gid >= ngroups) return;
+  const int b = static_cast<int>(gid / a.H), h = static_cast<int>(gid % a.H);
+  bf16* Qs = tiles + warp * PER_GROUP;
+  bf16* Ks = Qs + SELF_TILE;
+  bf16* Vs = Ks + SELF_TILE;
+  bf16* Gs = Vs + SELF_TILE;                       // dO (backward only)
+  bf16* stage = Qs + NT * SELF_TILE;
+  const uint8_t* mk = a.mask ? a.mask + static_cast<int64_t>(b % a.mask_mod) * S : nullptr;
+  const float scale = 0.125f;  // 1/sqrt(64)
+  const int g = lane >> 2, t = lane & 3;
+  // ---- scores and probabilities: thread holds rows g, g+8 x keys {2t, 2t+1, 8+2t, 9+2t}
+  float sc[2][4];
+  mma_ab_t(sc, Qs, Ks, lane);
+  bool kvalid[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = (e >> 1) * 8 + 2 * t + (e & 1);
+    kvalid[e] = j < S && !(mk && mk[j]);
+  }
+  float p[2][4];  // [row half][key e]
+#pragma unroll
+  for (int rh = 0; rh < 2; ++rh) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v = kvalid[e] ? sc[e >> 1][rh * 2 + (e & 1)] * scale : -INFINITY;
+      p[rh][e] = v;
+      m = fmaxf(m, v);
+    }
+    m = quad_max(m);
+    float l = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      p[rh][e] = kvalid[e] ? __expf(p[rh][e] - m) : 0.f;
+      l += p[rh][e];
+    }
+    l = quad_add(l);
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) p[rh][e] *= inv_l;
+  }
+  // dropout multipliers (0 or 1/(1-p)) on the probabilities, same element index as every other path
+  float mult[2][4];
+#pragma unroll
+  for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) mult[rh][e] = 1.f;
+  if (a.drop_p > 0.f) {
+    const uint64_t seed = a.rng[0], step = a.rng[1];
+    const float keep_scale = 1.f / (1.f - a.drop_p);
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const int i = g + rh * 8;
+      const uint64_t pbase = ((static_cast<uint64_t>(b) * a.H + h) * S + i) * static_cast<uint64_t>(S);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = (e >> 1) * 8 + 2 * t + (e & 1);
+        if (i < S && j < S) mult[rh][e] = dropout_keep(seed, step, a.site, pbase + j, a.drop_p) ? keep_scale : 0.f;
+      }
+    }
+  }
+  // A fragment of the (dropped) probabilities: a0 (row g, keys 2t..), a1 (row g+8), a2 (row g, keys 8+2t..), a3
+  uint32_t pa[4];
+  pa[0] = pack_bf16(p[0][0] * mult[0][0], p[0][1] * mult[0][1]);
+  pa[1] = pack_bf16(p[1][0] * mult[1][0], p[1][1] * mult[1][1]);
+  pa[2] = pack_bf16(p[0][2] * mult[0][2], p[0][3] * mult[0][3]);
+  pa[3] = pack_bf16(p[1][2] * mult[1][2], p[1][3] * mult[1][3]);
+  float o[8][4];
+  if (MODE == 0) {
+    mma_frag_b(o, pa, Vs, lane);
+    store_tile(stage, o, 1.f, a.o + static_cast<int64_t>(b) * S * a.ldo + h * SELF_HD, a.ldo, S, lane);
     return;
   }
-  // ---- backward pass A: thread = query row
-  float* dSg = dS + g * 2 * S * S;
-  if (active) {
-    float go[SELF_HD];
-    self_row_f32(Gs + r * SELF_PITCH, go);
+  // ---- backward
+  float dp[2][4];
+  mma_ab_t(dp, Gs, Vs, lane);  // dP = dO V^T
+  float ds[2][4];
+#pragma unroll
+  for (int rh = 0; rh < 2; ++rh) {
     float delta = 0.f;
-#pragma unroll 1
-    for (int j = 0; j < S; ++j) {
-      const float mult = pd[j * SELF_THREADS];
-      const float dpj = self_dot(go, Vg + j * SELF_PITCH) * mult;   // dP_ij through the dropout mask
-      delta = fmaf(pr[j * SELF_THREADS], dpj, delta);
-      dSg[S * S + i * S + j] = pr[j * SELF_THREADS] * mult;          // dropped probability (for dV)
-      pd[j * SELF_THREADS] = dpj;
-    }
-    float acc[SELF_HD];
 #pragma unroll
-    for (int d = 0; d < SELF_HD; ++d) acc[d] = 0.f;
-#pragma unroll 1
-    for (int j = 0; j < S; ++j) {
-      const float ds = pr[j * SELF_THREADS] * (pd[j * SELF_THREADS] - delta);
-      self_axpy(acc, ds, Kg + j * SELF_PITCH);
-      dSg[i * S + j] = ds;
+    for (int e = 0; e < 4; ++e) {
+      const float d = dp[e >> 1][rh * 2 + (e & 1)] * mult[rh][e];
+      ds[rh][e] = d;
+      delta = fmaf(p[rh][e], d, delta);
     }
-    self_store_row(a.dq + (static_cast<int64_t>(b) * S + i) * a.lddq + h * SELF_HD, acc, scale);
-  }
-  __syncthreads();
-  // ---- pass B: thread = key row j (= i)
-  if (active) {
-    const int j = i;
-    float dk[SELF_HD], dv[SELF_HD];
+    delta = quad_add(delta);
 #pragma unroll
-    for (int d = 0; d < SELF_HD; ++d) dk[d] = dv[d] = 0.f;
-    const bf16* Qg = Qs + g * S * SELF_PITCH;
-    const bf16* Gg = Gs + g * S * SELF_PITCH;
-#pragma unroll 1
-    for (int ii = 0; ii < S; ++ii) {
-      self_axpy(dk, dSg[ii * S + j], Qg + ii * SELF_PITCH);
-      self_axpy(dv, dSg[S * S + ii * S + j], Gg + ii * SELF_PITCH);
-    }
-    const int64_t row = static_cast<int64_t>(b) * S + j;
-    self_store_row(a.dk + row * a.lddkv + h * SELF_HD, dk, scale);
-    self_store_row(a.dv + row * a.lddkv + h * SELF_HD, dv, 1.f);
+    for (int e = 0; e < 4; ++e) ds[rh][e] = p[rh][e] * (ds[rh][e] - delta);
   }
+  uint32_t da[4];
+  da[0] = pack_bf16(ds[0][0], ds[0][1]);
+  da[1] = pack_bf16(ds[1][0], ds[1][1]);
+  da[2] = pack_bf16(ds[0][2], ds[0][3]);
+  da[3] = pack_bf16(ds[1][2], ds[1][3]);
+  // dQ = dS K * scale
+  mma_frag_b(o, da, Ks, lane);
+  store_tile(stage, o, scale, a.dq + static_cast<int64_t>(b) * S * a.lddq + h * SELF_HD, a.lddq, S, lane);
+  // bf16 copies of dS and P (dropped) for the transposed products
+  bf16* dSs = Qs + (NT + 1) * SELF_TILE;
+  bf16* Ps = dSs + 16 * SELF_SP;
+  *reinterpret_cast<uint32_t*>(dSs + g * SELF_SP + 2 * t) = da[0];
+  *reinterpret_cast<uint32_t*>(dSs + (g + 8) * SELF_SP + 2 * t) = da[1];
+  *reinterpret_cast<uint32_t*>(dSs + g * SELF_SP + 8 + 2 * t) = da[2];
+  *reinterpret_cast<uint32_t*>(dSs + (g + 8) * SELF_SP + 8 + 2 * t) = da[3];
+  *reinterpret_cast<uint32_t*>(Ps + g * SELF_SP + 2 * t) = pa[0];
+  *reinterpret_cast<uint32_t*>(Ps + (g + 8) * SELF_SP + 2 * t) = pa[1];
+  *reinterpret_cast<uint32_t*>(Ps + g * SELF_SP + 8 + 2 * t) = pa[2];
+  *reinterpret_cast<uint32_t*>(Ps + (g + 8) * SELF_SP + 8 + 2 * t) = pa[3];
+  __syncwarp();
+  // A fragments of X^T from the [query][key] tile: a0 = X[q 0-7][k 0-7]^T, a1 = X[q 0-7][k 8-15]^T,
+  // a2 = X[q 8-15][k 0-7]^T, a3 = X[q 8-15][k 8-15]^T
+  const int trow = (lane & 7) + (lane >> 4) * 8, tcol = ((lane >> 3) & 1) * 8;
+  uint32_t ta[4];
+  ldsm_x4_t(ta, dSs + trow * SELF_SP + tcol);
+  mma_frag_b(o, ta, Qs, lane);  // dK = dS^T Q * scale
+  store_tile(stage, o, scale, a.dk + static_cast<int64_t>(b) * S * a.lddkv + h * SELF_HD, a.lddkv, S, lane);
+  ldsm_x4_t(ta, Ps + trow * SELF_SP + tcol);
+  mma_frag_b(o, ta, Gs, lane);  // dV = P^T dO
+  store_tile(stage, o, 1.f, a.dv + static_cast<int64_t>(b) * S * a.lddkv + h * SELF_HD, a.lddkv, S, lane);
 }
 
-static size_t self_smem_bytes(int S, int mode) {
-  const SelfGeom geo = self_geom(S);
-  size_t b = static_cast<size_t>(mode == 1 ? 4 : 3) * geo.rows * SELF_PITCH * 2;
-  b += static_cast<size_t>(2) * SM_MAXL * SELF_THREADS * 4;
-  if (mode == 1) b += static_cast<size_t>(geo.G) * 2 * S * S * 4;
-  return b + 16;
+static size_t self_smem_bytes(int mode) {
+  const int nt = mode == 1 ? 4 : 3;
+  return static_cast<size_t>(SELF_GROUPS) * ((nt + 1) * SELF_TILE + (mode == 1 ? 2 * 16 * SELF_SP : 0)) * 2 + 16;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -761,16 +787,15 @@ static bool self_path(const AttnArgs& a) {
 }
 template <int MODE>
 static int launch_self(const AttnArgs& a, cudaStream_t st) {
-  const SelfGeom geo = self_geom(a.Lq);
-  const size_t smem = self_smem_bytes(a.Lq, MODE);
+  const size_t smem = self_smem_bytes(MODE);
   static bool configured = false;
   if (!configured) {
     GG_CUDA_CHECK(cudaFuncSetAttribute(attn_self_small_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(self_smem_bytes(SM_MAXL, MODE))));
+                                       static_cast<int>(smem)));
     configured = true;
   }
   const int64_t ngroups = static_cast<int64_t>(a.nb) * a.H;
-  const unsigned grid = static_cast<unsigned>((ngroups + geo.G - 1) / geo.G);
+  const unsigned grid = static_cast<unsigned>((ngroups + SELF_GROUPS - 1) / SELF_GROUPS);
   launch_k(attn_self_small_kernel<MODE>, grid, SELF_THREADS, smem, st, a);
   GG_LAUNCH_CHECK();
   return GG_OK;
