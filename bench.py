@@ -300,9 +300,15 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(w, args.workload, 1, 1, args.optimizer)
             line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the captured step graphs hold NCCL kernels: release them before the communicator goes away, and do not
+        # let a stuck teardown outlive the measurement
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -98,6 +98,8 @@ class TrainerBase:
         self.dropout_p = 0.1          # nn.TransformerEncoderLayer(dropout=0.1) in the reference towers
         self.dropout_seed = 0
         self.gemm_impl = _lib.IMPL_TCGEN05
+        self.dp_overlap = os.environ.get("GEMMGAN_DP_OVERLAP", "1") != "0"
+        self.dp_graph_collectives = os.environ.get("GEMMGAN_DP_GRAPH", "1") != "0"
         self.dp_global_noise = False   # draw z/alpha for the GLOBAL batch and slice (N-rank == 1-rank parity)
         self.use_cuda_graphs = os.environ.get("GEMMGAN_CUDA_GRAPHS", "1") != "0"
         self._engines = {}
@@ -209,11 +211,6 @@ class TrainerBase:
         return float(self._stats("d")[A.STAT_GP])
 
     # ---- the hot path -------------------------------------------------------------------
-    def _allreduce(self, flat: FlatNet):
-        d = _dist()
-        if d is not None:
-            d.all_reduce(flat.grads, op=d.ReduceOp.AVG)
-
     def _lr(self, opt):
         return opt.param_groups[0]["lr"]
 
@@ -241,17 +238,55 @@ class TrainerBase:
         g[0].replay()
         eng.lib.gg_launch_count_add(g[1])
 
+    def _buckets(self, flat: FlatNet):
+        """Trunk bucket (finished first by the hand-written backward) + tower bucket of one net's flat gradients."""
+        from .ddp import GradBuckets, plan_buckets
+
+        gb = getattr(flat, "_buckets", None)
+        if gb is None:
+            trunk = (A.P_TR0_W, A.P_TR0_B, A.P_TR1_W, A.P_TR1_B, A.P_FIN_W, A.P_FIN_B)
+            gb = flat._buckets = GradBuckets(flat.grads, plan_buckets(flat.offsets, flat.n_used, trunk))
+        return gb
+
     def _step(self, eng: Engine, tag, net, flat, lr, grads_fn):
+        """grads_fn(phase): phase 0 = whole backward, 1 = forward + trunk backward, 2 = tower backward."""
         lr = float(lr)
         if _dist() is None:
             def body():
-                grads_fn()
+                grads_fn(0)
                 eng.optim_step(net, lr)
             self._replay(eng, (tag, lr), body)
-        else:  # the gradient all-reduce sits between the backward and the optimizer kernel
-            self._replay(eng, (tag + "_grads",), grads_fn)
-            self._allreduce(flat)
-            self._replay(eng, (tag + "_optim", lr), lambda: eng.optim_step(net, lr))
+            return
+        # data parallel: the trunk bucket (over half of the net: one [H, G] matrix) is all-reduced on the
+        # communication stream while the fusion-tower backward runs; the tower bucket follows it; the
+        # optimizer kernel waits for both (SURVEY.md section 8e)
+        gb = self._buckets(flat)
+        split = len(gb.buckets) > 1 and self.dp_overlap
+        if self.dp_graph_collectives:
+            # one CUDA graph per step, the NCCL all-reduces captured inside it on the communication stream
+            def body():
+                if split:
+                    grads_fn(1)
+                    gb.reduce(0)
+                    grads_fn(2)
+                    gb.reduce(1)
+                else:
+                    grads_fn(0)
+                    gb.reduce_all()
+                gb.wait()
+                eng.optim_step(net, lr)
+            self._replay(eng, (tag + "_dp", lr, split), body)
+            return
+        if not split:
+            self._replay(eng, (tag + "_grads",), lambda: grads_fn(0))
+            gb.reduce_all()
+        else:
+            self._replay(eng, (tag + "_grads1",), lambda: grads_fn(1))
+            gb.reduce(0)
+            self._replay(eng, (tag + "_grads2",), lambda: grads_fn(2))
+            gb.reduce(1)
+        gb.wait()
+        self._replay(eng, (tag + "_optim", lr), lambda: eng.optim_step(net, lr))
 
     def _train_disc_staged(self, eng: Engine, z, alpha=None):
         """train_disc (:376-423) on the batch already staged in the engine."""
@@ -260,7 +295,7 @@ class TrainerBase:
         eng.z_in.copy_(z, non_blocking=True)
         eng.alpha_in.copy_(self._alpha(eng.B) if alpha is None else alpha.reshape(eng.B, 1), non_blocking=True)
         self._step(eng, "d", A.NET_DISC, self._flat_disc, self._lr(self.optimizer_disc),
-                   lambda: eng.disc_grads(eng.z_in, eng.alpha_in, training=True))
+                   lambda ph: eng.disc_grads(eng.z_in, eng.alpha_in, training=True, phase=ph))
         self._snapshot(eng, "d")
 
     def _train_gen_staged(self, eng: Engine, z):
@@ -273,7 +308,7 @@ class TrainerBase:
             w.requires_grad = True
         eng.z_in.copy_(z, non_blocking=True)
         self._step(eng, "g", A.NET_GEN, self._flat_gen, self._lr(self.optimizer_gen),
-                   lambda: eng.gen_grads(eng.z_in, training=True))
+                   lambda ph: eng.gen_grads(eng.z_in, training=True, phase=ph))
         self._snapshot(eng, "g")
 
     def _train_staged(self, eng: Engine, zs=None, alphas=None):
