@@ -77,6 +77,7 @@ class GemmDesc(C.Structure):
         ("force_splits", C.c_int32),
         ("block_n", C.c_int32),
         ("light", C.c_int32),
+        ("pair", C.c_int32),
     ]
 
 

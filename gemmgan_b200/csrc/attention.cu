@@ -665,6 +665,7 @@ __global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const Att
   if (a.drop_p > 0.f) {
     const uint64_t seed = a.rng[0], step = a.rng[1];
     const float keep_scale = 1.f / (1.f - a.drop_p);
+    DropoutStream ds(seed, step, a.site, a.drop_p);
 #pragma unroll
     for (int rh = 0; rh < 2; ++rh) {
       const int i = g + rh * 8;
@@ -672,7 +673,7 @@ __global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const Att
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = (e >> 1) * 8 + 2 * t + (e & 1);
-        if (i < S && j < S) mult[rh][e] = dropout_keep(seed, step, a.site, pbase + j, a.drop_p) ? keep_scale : 0.f;
+        if (i < S && j < S) mult[rh][e] = ds.keep(pbase + j) ? keep_scale : 0.f;
       }
     }
   }

@@ -88,14 +88,13 @@ __device__ __forceinline__ void epilogue_math(const gg_epilogue& e, int N, int m
     const uint64_t seed = e.rng[0], step = e.rng[1];
     const float keep_scale = 1.0f / (1.0f - e.drop_p);
     const uint64_t base = static_cast<uint64_t>(m) * static_cast<uint64_t>(N) + n0;
-    if ((base & 3) == 0) {  // one Philox call per 4 consecutive elements
+    if (W % 8 == 0 && (base & 7) == 0) {  // one Philox call per 8 consecutive elements
+      const uint32_t thr = dropout_thr(e.drop_p);
 #pragma unroll
-      for (int g = 0; g < W / 4; ++g) {
-        const u32x4 r = dropout_words(seed, step, e.site, (base >> 2) + g);
-        v[4 * g + 0] = keep_from_word(r.x, e.drop_p) ? v[4 * g + 0] * keep_scale : 0.f;
-        v[4 * g + 1] = keep_from_word(r.y, e.drop_p) ? v[4 * g + 1] * keep_scale : 0.f;
-        v[4 * g + 2] = keep_from_word(r.z, e.drop_p) ? v[4 * g + 2] * keep_scale : 0.f;
-        v[4 * g + 3] = keep_from_word(r.w, e.drop_p) ? v[4 * g + 3] * keep_scale : 0.f;
+      for (int g = 0; g < W / 8; ++g) {
+        const uint32_t kb = keep_bits8(dropout_words(seed, step, e.site, (base >> 3) + g), thr);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[8 * g + t] = ((kb >> t) & 1u) ? v[8 * g + t] * keep_scale : 0.f;
       }
     } else {
 #pragma unroll

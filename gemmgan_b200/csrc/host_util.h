@@ -66,6 +66,34 @@ static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through GG_LAUNCH_CHECK()
 }
 
+// Same, for kernels whose CTAs form clusters of `cluster` (1 = none) along x.
+template <class... KArgs, class... Args>
+static inline void launch_k_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through GG_LAUNCH_CHECK()
+}
+
 #define GG_TRY_RC(x)        \
   do {                      \
     int _rc = (x);          \

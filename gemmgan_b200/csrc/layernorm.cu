@@ -84,14 +84,9 @@ struct RowIO {
 #pragma unroll
       for (int k = 0; k < PER; ++k) {
         const uint64_t e0 = base + static_cast<uint64_t>((k * 32 + lane) * 8);  // multiple of 8
+        const uint32_t kb = keep_bits8(dropout_words(seed, step, site, e0 >> 3), dropout_thr(p));
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const u32x4 r = dropout_words(seed, step, site, (e0 >> 2) + g);
-          keep[k * 8 + 4 * g + 0] = keep_from_word(r.x, p);
-          keep[k * 8 + 4 * g + 1] = keep_from_word(r.y, p);
-          keep[k * 8 + 4 * g + 2] = keep_from_word(r.z, p);
-          keep[k * 8 + 4 * g + 3] = keep_from_word(r.w, p);
-        }
+        for (int t = 0; t < 8; ++t) keep[k * 8 + t] = ((kb >> t) & 1u) != 0;
       }
     } else {
 #pragma unroll

@@ -22,7 +22,7 @@ def gemm(
     bias=None, pre=None, act=_lib.ACT_NONE, slope=0.0, drop_p=0.0, rng=None, site=0,
     mask=None, mask_pos=1.0, mask_neg=0.0, res=None, alpha=1.0,
     out_bf16=None, out_f32=None, accum=False, row_map=None,
-    workspace=None, impl=_lib.IMPL_TCGEN05, splits=0, block_n=0, light=0,
+    workspace=None, impl=_lib.IMPL_TCGEN05, splits=0, block_n=0, light=0, pair=0,
 ):
     """D = epilogue(alpha * (A @ B^T [+ A2 @ B2^T])).
 
@@ -68,7 +68,7 @@ def gemm(
         e.row_div, e.row_mul, e.row_add = row_map
     if workspace is not None:
         d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
-    d.impl, d.force_splits, d.block_n, d.light = impl, splits, block_n, light
+    d.impl, d.force_splits, d.block_n, d.light, d.pair = impl, splits, block_n, light, pair
     _lib.check(L.gg_gemm_bf16(C.byref(d), _stream()))
 
 

@@ -77,7 +77,9 @@ typedef struct gg_epilogue {
   const void* res;       /* [M, res_ld] added AFTER everything else, or NULL */
   int64_t res_ld;
   int32_t res_f32;
-  void* out_bf16;        /* [*, ld_bf16] bf16 output or NULL */
+  void* out_bf16;        /* [*, ld_bf16] bf16 output or NULL. With a 16-byte aligned base and pitch the tile is written
+                            by TMA stores, which clip at 16-byte granularity: when N is not a multiple of 8 (4 for
+                            fp32) the row padding up to that multiple receives zeros */
   int64_t ld_bf16;
   float* out_f32;        /* [*, ld_f32] fp32 output or NULL */
   int64_t ld_f32;
@@ -109,6 +111,8 @@ typedef struct gg_gemm_desc {
   int32_t block_n;          /* 0 = heuristic; 64, 128 or 256 */
   int32_t light;            /* 0 = heuristic; 1 = force, -1 = forbid the two-CTAs-per-SM configuration (128-wide
                                tiles, no split-K) used for short-K products with many tiles */
+  int32_t pair;             /* 0 = heuristic; 1 = force, -1 = forbid the CTA-pair configuration (tcgen05 cta_group::2:
+                               256 x 256 tiles over the two SMs of a TPC, each CTA stages half of the B tile) */
 } gg_gemm_desc;
 
 int gg_gemm_bf16(const gg_gemm_desc* desc, void* stream);
@@ -119,6 +123,9 @@ void gg_launch_count_add(long long n); /* a replayed CUDA graph adds the launche
 int gg_gemm_profile_begin(void);
 int gg_gemm_profile_end(double* ms, double* flops, long long* launches);
 int gg_gemm_profile_dump(const char* csv_path); /* per-launch shapes and durations of the last region */
+/* Diagnostics: CTA `cta` of every following GEMM launch stamps clock64() per pipeline role into device_buf
+ * (6 x 512 int64: TMA issued / stage full / tile committed / accumulator full / tile stored / origin); NULL = off. */
+int gg_gemm_set_trace(void* device_buf, int cta);
 
 /* -------------------------------------------------------- training engine --
  * One engine = one (generator, critic) pair of one model variant at a fixed per-rank batch

@@ -11,7 +11,7 @@ from gemmgan_b200 import _lib, ops  # noqa: E402
 
 
 def bench(M, N, K, a_mn=False, b_mn=False, out="bf16", bias=True, bn=0, splits=0, iters=20, act=0, drop=0.0,
-          mask=False, res=False, ws=None, rng=None, flush=None, light=0):
+          mask=False, res=False, ws=None, rng=None, flush=None, light=0, pair=-1):
     """Device time per launch: `iters` launches over 4 rotating operand sets are captured in one CUDA graph and
     the replay is timed with CUDA events (no host launch overhead in the number; operands are L2-warm at best
     every 4th launch, as inside the training step)."""
@@ -26,7 +26,7 @@ def bench(M, N, K, a_mn=False, b_mn=False, out="bf16", bias=True, bn=0, splits=0
         mk = torch.randn(M, N, device=dev).to(torch.bfloat16) if mask else None
         rs = torch.randn(M, N, device=dev).to(torch.bfloat16) if res else None
         sets.append((a, b, dict(a_mn=a_mn, b_mn=b_mn, bias=bs, act=act, drop_p=drop, rng=rng, mask=mk, res=rs,
-                                out_bf16=ob, out_f32=of, workspace=ws, splits=splits, block_n=bn, light=light)))
+                                out_bf16=ob, out_f32=of, workspace=ws, splits=splits, block_n=bn, light=light, pair=pair)))
     for a, b, kw in sets:
         ops.gemm(a, b, **kw)
     torch.cuda.synchronize()
@@ -69,7 +69,7 @@ def main():
         ("wgrad ffn1", 512, 256, 18432, 1, 1, "f32", dict(bias=False)),
         ("wgrad qkv", 768, 256, 18432, 1, 1, "f32", dict(bias=False)),
         ("wgrad out", 256, 256, 18432, 1, 1, "f32", dict(bias=False)),
-        ("gen final", 1024, 18868, 256, 0, 0, "bf16", {}),
+        ("gen final", 1024, 18872, 256, 0, 0, "bf16", {}),
         ("critic L1 [2B,G]", 2048, 256, 18872, 0, 0, "f32", dict(bias=False)),
         ("dW1x", 256, 18872, 2048, 1, 1, "f32", dict(bias=False)),
         ("gram", 256, 256, 18872, 0, 0, "f32", dict(bias=False)),
@@ -79,11 +79,11 @@ def main():
         ("square 8192", 8192, 8192, 8192, 0, 0, "bf16", dict(bias=False)),
     ]
     for name, M, N, K, a_mn, b_mn, out, ex in cases:
-        for bn, light in ((128, -1), (128, 1), (256, 0)):
-            if (N < 256 and bn == 256) or (light == 1 and (K > 1024 or M * N > 40e6)):
+        for bn, pair in ((128, -1), (256, -1), (256, 1)):
+            if N < 256 and bn == 256:
                 continue
-            us, tf, gbs = bench(M, N, K, bool(a_mn), bool(b_mn), out, bn=bn, ws=ws, rng=rng, flush=flush, light=light, **ex)
-            print(f"{name:24s} M={M:6d} N={N:6d} K={K:6d} bn={bn:3d} light={light:2d} {us:8.1f} us  {tf:8.1f} TFLOP/s  {gbs:8.1f} GB/s",
+            us, tf, gbs = bench(M, N, K, bool(a_mn), bool(b_mn), out, bn=bn, ws=ws, rng=rng, flush=flush, pair=pair, **ex)
+            print(f"{name:24s} M={M:6d} N={N:6d} K={K:6d} bn={bn:3d} pair={pair:2d} {us:8.1f} us  {tf:8.1f} TFLOP/s  {gbs:8.1f} GB/s",
                   flush=True)
 
 

@@ -41,9 +41,24 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("M,N,K,a_mn,b_mn,bn,splits", CASES)
+PAIR_CASES = [
+    # the CTA-pair configuration (tcgen05 cta_group::2, 256 x 256 tiles): ragged M / N / K tails, both operand
+    # majors, split-K, the persistent multi-tile loop
+    (1000, 300, 256, 0, 0, 256, 0),
+    (256, 256, 64, 0, 0, 256, 0),
+    (300, 520, 136, 0, 1, 256, 0),
+    (260, 1000, 200, 1, 1, 256, 0),
+    (520, 264, 1000, 1, 0, 256, 3),
+    (27648, 768, 256, 0, 0, 256, 0),
+    (18432, 512, 256, 0, 1, 256, 0),
+    (256, 18872, 512, 1, 1, 256, 0),
+    (2048, 256, 18872, 0, 0, 256, 9),
+]
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,bn,splits,pair", [c + (-1,) for c in CASES] + [c + (1,) for c in PAIR_CASES])
 @pytest.mark.parametrize("aligned", [True, False])
-def test_gemm_epilogue_features(M, N, K, a_mn, b_mn, bn, splits, aligned):
+def test_gemm_epilogue_features(M, N, K, a_mn, b_mn, bn, splits, aligned, pair):
     torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 7 * K)
     a = _mk(K, M, g) if a_mn else _mk(M, K, g)
@@ -53,25 +68,29 @@ def test_gemm_epilogue_features(M, N, K, a_mn, b_mn, bn, splits, aligned):
     mask = _mk(M, N, g)
     res = torch.randn(M, N, device="cuda", generator=g)           # fp32 residual
     # aligned: pitches that allow TMA stores; unaligned: odd pitches force the direct-store path
-    ld_b = (N + 7) // 8 * 8 if aligned else (N + 7) // 8 * 8 + 2
-    ld_f = (N + 3) // 4 * 4 if aligned else (N + 3) // 4 * 4 + 1
+    ld_b = (N + 7) // 8 * 8 + 8 if aligned else (N + 7) // 8 * 8 + 2
+    ld_f = (N + 3) // 4 * 4 + 4 if aligned else (N + 3) // 4 * 4 + 1
     ob = torch.full((M, ld_b), 7.0, device="cuda", dtype=torch.bfloat16)
     of = torch.full((M, ld_f), 7.0, device="cuda", dtype=torch.float32)
     ws = torch.empty(max(1, splits) * M * N * 4 + 1024, device="cuda", dtype=torch.uint8)
     ops.gemm(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), bias=bias, pre=pre, act=_lib.ACT_LEAKY, slope=0.2,
              mask=mask, mask_pos=1.5, mask_neg=-0.5, res=res, alpha=0.5, out_bf16=ob[:, :N], out_f32=of[:, :N],
-             workspace=ws, splits=splits, block_n=bn)
+             workspace=ws, splits=splits, block_n=bn, pair=pair)
     torch.cuda.synchronize()
     want = _leaky(0.5 * _ref(a, b, a_mn, b_mn) + bias + pre.float(), 0.2)
     want = want * torch.where(mask.float() > 0, 1.5, -0.5) + res
     scale = want.abs().max().item()
     assert (of[:, :N] - want).abs().max().item() <= 1e-4 * scale
     assert (ob[:, :N].float() - want).abs().max().item() <= 5e-3 * scale
-    # nothing outside the [M, N] window was touched (clipped TMA boxes, guarded direct stores)
-    if ld_b > N:
-        assert (ob[:, N:] == 7.0).all()
-    if ld_f > N:
-        assert (of[:, N:] == 7.0).all()
+    # nothing outside the [M, N] window was touched (clipped TMA boxes, guarded direct stores). TMA stores clip
+    # at 16-byte granularity: with an aligned pitch the row padding up to the next multiple of 8 bf16 (4 fp32)
+    # columns may receive the zero accumulator tail (documented in include/gemmgan.h)
+    nb = (N + 7) // 8 * 8 if aligned else N
+    nf = (N + 3) // 4 * 4 if aligned else N
+    if ld_b > nb:
+        assert (ob[:, nb:] == 7.0).all()
+    if ld_f > nf:
+        assert (of[:, nf:] == 7.0).all()
 
 
 def test_gemm_two_segments_row_map_and_film():
@@ -82,7 +101,10 @@ def test_gemm_two_segments_row_map_and_film():
     a2, b2 = _mk(M, K2, g), _mk(E, K2, g)
     out = torch.zeros(Bn * S, E, device="cuda", dtype=torch.bfloat16)
     ops.gemm(a, b, a2=a2, b2=b2, out_bf16=out, row_map=(P, S, 1))
+    out2 = torch.zeros_like(out)
+    ops.gemm(a, b, a2=a2, b2=b2, out_bf16=out2, row_map=(P, S, 1), pair=1)   # same through a CTA pair
     torch.cuda.synchronize()
+    assert torch.equal(out, out2)
     want = (_ref(a, b, 0, 0) + _ref(a2, b2, 0, 0)).view(Bn, P, E)
     got = out.view(Bn, S, E)
     assert (got[:, 0] == 0).all()
@@ -121,7 +143,7 @@ def test_gemm_light_configuration(M, N, K, a_mn, b_mn):
     assert (outs[0][1] - want).abs().max().item() <= 1e-4 * want.abs().max().item()
 
 
-@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("bn", [64, 128, 256, -256])
 def test_gemm_dropout_matches_check_kernel(bn):
     """Dropout is a pure function of (seed, step, site, element index): the tensor-core kernel and the
     CUDA-core check kernel must drop exactly the same elements, whatever the tiling."""
@@ -131,7 +153,7 @@ def test_gemm_dropout_matches_check_kernel(bn):
     rng = torch.tensor([1234, 7], device="cuda", dtype=torch.int64)
     o1 = torch.empty(M, N, device="cuda", dtype=torch.float32)
     o2 = torch.empty(M, N, device="cuda", dtype=torch.float32)
-    ops.gemm(a, b, drop_p=0.25, rng=rng, site=3, out_f32=o1, block_n=bn)
+    ops.gemm(a, b, drop_p=0.25, rng=rng, site=3, out_f32=o1, block_n=abs(bn), pair=1 if bn < 0 else -1)  # -256: CTA pair
     ops.gemm(a, b, drop_p=0.25, rng=rng, site=3, out_f32=o2, impl=_lib.IMPL_SIMT_F32)
     torch.cuda.synchronize()
     assert ((o1 == 0) == (o2 == 0)).all()
