@@ -116,7 +116,7 @@ struct gg_engine {
   gg_net_buffers nets[2];
   NetShadow sh[2];
   int S_ = 1, Gp = 0, F = 0, hd = 0;
-  bool cond = false, paper = false;
+  bool cond = false, paper = false, film = false;  // paper: cross-attention tail; film: FiLM modulation of the patches
   // staged inputs
   bf16 *xfr, *patches, *text, *zbf, *xin;
   uint8_t *mask_s, *tpad;
@@ -463,7 +463,7 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
 }
 
 static int validate_cfg(const gg_model_cfg& c) {
-  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_PAPER, "unknown variant %d", c.variant);
+  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_CROSS, "unknown variant %d", c.variant);
   GG_REQUIRE(c.B > 0 && c.G > 0 && c.L > 0 && c.H > 0, "bad sizes B=%d G=%d L=%d H=%d", c.B, c.G, c.L, c.H);
   GG_REQUIRE(c.L % 8 == 0 && c.H % 8 == 0, "latent and hidden widths must be multiples of 8");
   if (c.variant != GG_VARIANT_VANILLA) {
@@ -481,7 +481,8 @@ static int validate_cfg(const gg_model_cfg& c) {
 static void derive(gg_engine& e) {
   const gg_model_cfg& c = e.cfg;
   e.cond = c.variant != GG_VARIANT_VANILLA;
-  e.paper = c.variant == GG_VARIANT_PAPER;
+  e.paper = c.variant == GG_VARIANT_PAPER || c.variant == GG_VARIANT_CROSS;
+  e.film = c.variant == GG_VARIANT_PAPER || c.variant == GG_VARIANT_FILM;
   e.S_ = e.cond ? c.P + 1 : 1;
   e.Gp = static_cast<int>(round_up64(c.G, 8));
   e.F = c.ffn;
@@ -498,15 +499,20 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
   const int B = c.B, S = e.S_, E = c.E, F = e.F, P = c.P, T = c.T, Dp = c.Dp, Dt = c.Dt;
   const int rows = R * B * S;
   const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
-  // FiLM parameters from the text CLS / text vector (:129-134)
-  GG_TRY(e.linear(ln, B, 2 * Dp, Dt, Op{e.text, static_cast<int64_t>(T) * Dt}, e.W(net, GG_P_FILM_W),
-                  Epi().bias(e.P(net, GG_P_FILM_B)).act(GG_ACT_FILM).of32(t.gb, 2 * Dp)));
-  GG_TRY(k_film_apply(e.patches, t.gb, t.mod, B, P, Dp, st));
+  // FiLM parameters from the text CLS / text vector (:129-134); conditional_gan_cross_attention.py has no FiLM
+  // (:128-130): its patch encoder reads the patch embeddings as they are
+  const bf16* pin = e.patches;
+  if (e.film) {
+    GG_TRY(e.linear(ln, B, 2 * Dp, Dt, Op{e.text, static_cast<int64_t>(T) * Dt}, e.W(net, GG_P_FILM_W),
+                    Epi().bias(e.P(net, GG_P_FILM_B)).act(GG_ACT_FILM).of32(t.gb, 2 * Dp)));
+    GG_TRY(k_film_apply(e.patches, t.gb, t.mod, B, P, Dp, st));
+    pin = t.mod;
+  }
   if (e.paper)
     GG_TRY(e.linear(ln, B * T, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W),
                     Epi().bias(e.P(net, GG_P_TEXT_B)).obf(t.te, E)));
   // patch projection written straight behind the CLS row of replica 0 (:139-142)
-  GG_TRY(e.linear(ln, B * P, E, Dp, Op{t.mod, Dp}, e.W(net, GG_P_PATCH_W),
+  GG_TRY(e.linear(ln, B * P, E, Dp, Op{pin, Dp}, e.W(net, GG_P_PATCH_W),
                   Epi().bias(e.P(net, GG_P_PATCH_B)).obf(t.X[0], E).rowmap(P, S, 1)));
   GG_TRY(k_assemble_tokens(t.X[0], e.P(net, GG_P_CLS), R, B, S, E, st));
   for (int l = 0; l < c.n_layers; ++l) {
@@ -705,13 +711,15 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
   // X0 = [cls | patch projections], replicas share the projections
   GG_TRY(e.bgrad(g.ga, static_cast<int64_t>(S) * E, n, E, e.Gr(net, GG_P_CLS)));  // d cls = sum over the CLS rows
   GG_TRY(k_unassemble_tokens(g.ga, g.dpe, nullptr, Rg, B, S, E, st));
-  GG_TRY(e.wgrad(E, Dp, B * P, Op{g.dpe, E}, Op{t.mod, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
+  GG_TRY(e.wgrad(E, Dp, B * P, Op{g.dpe, E}, Op{e.film ? t.mod : e.patches, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
   GG_TRY(e.bgrad(g.dpe, E, B * P, E, e.Gr(net, GG_P_PATCH_B)));
-  GG_TRY(e.dgrad(0, B * P, Dp, E, Op{g.dpe, E}, e.W(net, GG_P_PATCH_W), Epi().obf(g.dmod, Dp)));
-  GG_TRY(k_film_bwd(g.dmod, e.patches, t.gb, g.dgb, B, P, Dp, st));
-  GG_TRY(e.wgrad(2 * Dp, Dt, B, Op{g.dgb, 2 * Dp}, Op{e.text, static_cast<int64_t>(T) * Dt},
-                 e.Gr(net, GG_P_FILM_W), Dt));
-  GG_TRY(e.bgrad(g.dgb, 2 * Dp, B, 2 * Dp, e.Gr(net, GG_P_FILM_B)));
+  if (e.film) {  // without FiLM the patch embeddings are a plain input: nothing upstream needs a gradient
+    GG_TRY(e.dgrad(0, B * P, Dp, E, Op{g.dpe, E}, e.W(net, GG_P_PATCH_W), Epi().obf(g.dmod, Dp)));
+    GG_TRY(k_film_bwd(g.dmod, e.patches, t.gb, g.dgb, B, P, Dp, st));
+    GG_TRY(e.wgrad(2 * Dp, Dt, B, Op{g.dgb, 2 * Dp}, Op{e.text, static_cast<int64_t>(T) * Dt},
+                   e.Gr(net, GG_P_FILM_W), Dt));
+    GG_TRY(e.bgrad(g.dgb, 2 * Dp, B, 2 * Dp, e.Gr(net, GG_P_FILM_B)));
+  }
   return e.flush_grads();
 }
 
@@ -1099,6 +1107,38 @@ extern "C" int gg_engine_gradient_penalty(gg_engine* e, const float* real_f32, c
   GG_TRY(disc_forward_gp(*e, p > 0.f ? 3 : 1, p, alpha, 0));
   GG_TRY(e->join_all());
   GG_CUDA_CHECK(cudaMemcpyAsync(gp_out, e->stats + GG_STAT_GP, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return GG_OK;
+}
+
+// The gradient penalty alone, value AND gradients (BASELINE.json config 5, SURVEY.md section 8d "GP microbench"):
+// x_hat = alpha*real + (1-alpha)*fake, GP = mean((||dD/dx_hat|| - 1)^2) and gp_weight * dGP/d{W1, W2, w3} written
+// into the critic's gradient buffer — what autograd computes with a forward, torch.autograd.grad(create_graph)
+// and a double backward (reference :351-374 + the GP part of :412). fp32 inputs are cast to bf16 once (8*B*G
+// bytes read); no interpolated tensor, no [B,G] gradient tensor: the Gram-matrix formulation.
+extern "C" int gg_engine_gp_step(gg_engine* e, const float* real_f32, const float* fake_f32, const float* alpha,
+                                 float* gp_out, void* stream) {
+  GG_REQUIRE(e && real_f32 && fake_f32 && alpha, "null argument");
+  GG_REQUIRE(!e->cond, "gg_engine_gp_step is the unconditional-critic microbenchmark entry point");
+  e->begin(stream);
+  cudaStream_t st = e->S(0);
+  const gg_model_cfg& c = e->cfg;
+  TrunkBufs& t = e->tb;
+  const int B = c.B, H = c.H, G = c.G, net = GG_NET_DISC;
+  GG_TRY(k_cast_f32_bf16(fake_f32, G, e->xfr, e->Gp, B, G, st));
+  GG_TRY(k_cast_f32_bf16(real_f32, G, e->xfr + static_cast<int64_t>(B) * e->Gp, e->Gp, B, G, st));
+  GG_TRY(disc_forward_gp(*e, 1, 0.f, alpha, 0));
+  const Op W1x = e->W(net, GG_P_TR0_W), W2 = e->W(net, GG_P_TR1_W);
+  const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;
+  float* gw3 = e->Gr(net, GG_P_FIN_W);
+  // Q = (r u1)^T u1 ; du2 = dv1 W2^T masked by m2 -> d/dw3 ; dW2 = u2^T dv1 ; dW1 = Q W1x
+  GG_TRY(e->mm(0, H, H, B, Op{t.ru1, H}, 1, Op{t.u1b, H}, 1, Epi().obf(t.Qb, H)));
+  GG_TRY(e->linear(0, B, H, H, Op{t.dv1, H}, W2, Epi().mask(h2i, H, 1.f, c.slope).of32(t.du2f, H)));
+  GG_TRY(k_colsum(t.du2f, 1, H, B, H, nullptr, 1.f, gw3, 0, e->scratch_l[0], st));
+  GG_TRY(e->mm(0, H, H, B, Op{t.u2, H}, 1, Op{t.dv1, H}, 1, Epi().of32(e->Gr(net, GG_P_TR1_W), H)));
+  GG_TRY(e->mm(0, H, G, H, Op{t.Qb, H}, 0, W1x, 1, Epi().of32(e->Gr(net, GG_P_TR0_W), G)));
+  GG_TRY(e->join_all());
+  if (gp_out)
+    GG_CUDA_CHECK(cudaMemcpyAsync(gp_out, e->stats + GG_STAT_GP, sizeof(float), cudaMemcpyDeviceToDevice, st));
   return GG_OK;
 }
 

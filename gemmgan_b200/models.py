@@ -6,6 +6,7 @@ reference's initial weights and state_dict()s are interchangeable with reference
 (including the never-used prototype `patches_transformer_layer.*` entries):
   paper   generator/discriminator  src/conditional_gan_cross_attention_with_film.py:97-233
   film    generator/discriminator  src/conditional_gan_film.py:97-204
+  cross   generator/discriminator  src/conditional_gan_cross_attention.py:97-206
   vanilla generator_nocond/discriminator_nocond  src/vanilla_gan_unconditional.py:93-184
 
 forward() does not run torch kernels: it calls the engine (libgemmgan_sm100a.so) the trainer attached
@@ -19,7 +20,8 @@ from torch import nn
 
 from . import _abi_decl as A
 
-VARIANT_IDS = {"vanilla": A.VARIANT_VANILLA, "film": A.VARIANT_FILM, "paper": A.VARIANT_PAPER}
+VARIANT_IDS = {"vanilla": A.VARIANT_VANILLA, "film": A.VARIANT_FILM, "paper": A.VARIANT_PAPER,
+               "cross": A.VARIANT_CROSS}
 
 
 def build_linear_block(input_dims, output_dims, negative_slope=0.0, is_bn=False):
@@ -53,9 +55,10 @@ class _Net(nn.Module):
         self.negative_slope = negative_slope
         self.is_bn = is_bn
         E = embedding_dims
-        if v in ("paper", "film"):
-            self.film_generator = nn.Linear(text_embedding_dims, patches_embedding_dims * 2)
-            if v == "paper":
+        if v in ("paper", "film", "cross"):
+            if v != "cross":
+                self.film_generator = nn.Linear(text_embedding_dims, patches_embedding_dims * 2)
+            if v in ("paper", "cross"):
                 self.text_encoder = nn.Linear(text_embedding_dims, E)
             self.patches_encoder = nn.Linear(patches_embedding_dims, E)
             self.patches_transformer_layer = nn.TransformerEncoderLayer(
@@ -64,9 +67,10 @@ class _Net(nn.Module):
             self.patches_cls_token = nn.Parameter(torch.empty(1, 1, E))
             torch.nn.init.trunc_normal_(self.patches_cls_token, std=0.02)
             self.patches_transformer = nn.TransformerEncoder(self.patches_transformer_layer, num_layers=2)
-            if v == "paper":
-                self.patch2text_attention = nn.MultiheadAttention(embed_dim=E, num_heads=4, batch_first=True)
-                self.text2patch_attention = nn.MultiheadAttention(embed_dim=E, num_heads=4, batch_first=True)
+            if v in ("paper", "cross"):
+                ab = v == "paper"  # conditional_gan_cross_attention.py:118-121 builds its attentions with bias=False
+                self.patch2text_attention = nn.MultiheadAttention(embed_dim=E, num_heads=4, batch_first=True, bias=ab)
+                self.text2patch_attention = nn.MultiheadAttention(embed_dim=E, num_heads=4, batch_first=True, bias=ab)
         self.input_dims = first_dim + (0 if v == "vanilla" else E)
         stack = build_stack(self.input_dims, dims[:-1], negative_slope, is_bn)
         setattr(self, "generator" if self._role == "gen" else "discriminator", stack)
@@ -81,9 +85,10 @@ class _Net(nn.Module):
         """C-ABI parameter slot -> nn.Parameter (include/gemmgan.h enum gg_param_slot)."""
         t = {}
         v = self._variant
-        if v in ("paper", "film"):
-            t[A.P_FILM_W], t[A.P_FILM_B] = self.film_generator.weight, self.film_generator.bias
-            if v == "paper":
+        if v in ("paper", "film", "cross"):
+            if v != "cross":
+                t[A.P_FILM_W], t[A.P_FILM_B] = self.film_generator.weight, self.film_generator.bias
+            if v in ("paper", "cross"):
                 t[A.P_TEXT_W], t[A.P_TEXT_B] = self.text_encoder.weight, self.text_encoder.bias
             t[A.P_PATCH_W], t[A.P_PATCH_B] = self.patches_encoder.weight, self.patches_encoder.bias
             t[A.P_CLS] = self.patches_cls_token
@@ -95,7 +100,7 @@ class _Net(nn.Module):
                 t[b + A.L_FF2_W], t[b + A.L_FF2_B] = layer.linear2.weight, layer.linear2.bias
                 t[b + A.L_N1_W], t[b + A.L_N1_B] = layer.norm1.weight, layer.norm1.bias
                 t[b + A.L_N2_W], t[b + A.L_N2_B] = layer.norm2.weight, layer.norm2.bias
-            if v == "paper":
+            if v in ("paper", "cross"):
                 p2t, t2p = self.patch2text_attention, self.text2patch_attention
                 t[A.P_P2T_IN_W], t[A.P_P2T_IN_B] = p2t.in_proj_weight, p2t.in_proj_bias
                 t[A.P_P2T_OUT_W], t[A.P_P2T_OUT_B] = p2t.out_proj.weight, p2t.out_proj.bias
@@ -148,6 +153,15 @@ class PaperDiscriminator(_Net):
 
     def forward(self, gene_expression, patches, patches_padding_mask, text_tokens, text_padding_mask):
         return self._engine_forward(gene_expression, patches, patches_padding_mask, text_tokens, text_padding_mask)
+
+
+# ------------------------------------------------------------ cross-attention model (no FiLM)
+class CrossGenerator(PaperGenerator):
+    _role, _variant = "gen", "cross"
+
+
+class CrossDiscriminator(PaperDiscriminator):
+    _role, _variant = "disc", "cross"
 
 
 # ------------------------------------------------------------------------------ film model

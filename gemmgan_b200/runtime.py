@@ -240,6 +240,11 @@ class Engine:
                                                        _ptr(out), _stream()))
         return out
 
+    def gp_step(self, real, fake, alpha, out: Optional[torch.Tensor] = None) -> None:
+        """GP value + gp_weight * dGP/d{W1, W2, w3} into the critic's gradient buffer (gg_engine_gp_step)."""
+        r, f, a = self._f32(real), self._f32(fake), self._f32(alpha)
+        _lib.check(self.lib.gg_engine_gp_step(self.handle, _ptr(r), _ptr(f), _ptr(a), _ptr(out), _stream()))
+
     def critic(self, genes: torch.Tensor, training: bool = False) -> torch.Tensor:
         g = self._f32(genes)
         out = torch.empty(self.B, 1, device=self.device, dtype=torch.float32)

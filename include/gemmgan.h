@@ -141,6 +141,9 @@ int gg_gemm_set_trace(void* device_buf, int cta);
 #define GG_VARIANT_VANILLA 0 /* vanilla_gan_unconditional.py: trunk only                      */
 #define GG_VARIANT_FILM 1    /* conditional_gan_film.py: FiLM + encoder (no bias), CLS vector */
 #define GG_VARIANT_PAPER 2   /* conditional_gan_cross_attention_with_film.py (paper model)    */
+#define GG_VARIANT_CROSS 3   /* conditional_gan_cross_attention.py: the paper model's towers without FiLM and without
+                                tower biases (:97-206); only row 0 of its multi-query cross-attentions reaches the
+                                conditioning vector, so it runs as the same single-query tail */
 
 #define GG_OPT_RMSPROP 0
 #define GG_OPT_ADAM 1
@@ -245,6 +248,12 @@ int gg_engine_critic(gg_engine* e, const float* genes_f32, float* score_f32, int
  * the staged batch): gp_out[0] (device) = mean_b (||dD/dx_hat||_2 - 1)^2. */
 int gg_engine_gradient_penalty(gg_engine* e, const float* real_f32, const float* fake_f32, const float* alpha,
                                int training, float* gp_out, void* stream);
+/* The gradient penalty alone, value and gradients, on the unconditional critic (BASELINE.json config 5: the GP
+ * microbenchmark). Replaces WGAN_GP.gradient_penalty (src/vanilla_gan_unconditional.py:304-327) + the GP part of
+ * disc_loss.backward() (:381): gp_out[0] (device, may be NULL) = GP; gp_weight * dGP/dW1, dW2, dw3 are written
+ * into the critic's gradient buffer (biases get no GP gradient: the masks are piecewise constant). */
+int gg_engine_gp_step(gg_engine* e, const float* real_f32, const float* fake_f32, const float* alpha, float* gp_out,
+                      void* stream);
 float* gg_engine_stats(gg_engine* e);
 /* named internal device buffers for tests ("fake_bf16", "score", "gp_norms", "cond_disc", ...);
  * returns NULL for unknown names. rows/cols/ld (elements) are optional outputs. */

@@ -37,7 +37,7 @@ def _digest(sd):
 
 
 def ref_args(variant, x, cond):
-    if variant == "paper":
+    if variant in ("paper", "cross"):
         patches, ppad, text, tpad = cond
         return (x, text, tpad, patches, ppad)
     if variant == "film":
@@ -113,7 +113,7 @@ def make(variant, cfg, optimizer, slope, n_calls, full_tensors, name):
                 z = torch.normal(0, 1, size=(B, L))
                 if variant == "vanilla":
                     t.train_disc(xr, z)
-                elif variant == "paper":
+                elif variant in ("paper", "cross"):
                     t.train_disc(xr, z, *ref_args(variant, x, cond)[1:])
                 else:
                     t.train_disc(xr, z, *ref_args(variant, x, cond)[1:])
@@ -160,6 +160,7 @@ def main():
     make("film", SMALL, "adam", 0.0, 4, True, "film_small_adam")
     make("paper", FULL, "adam", 0.0, 3, False, "paper_fulldims_adam")
     make("film", FULL, "rms_prop", 0.0, 3, False, "film_fulldims_rmsprop")
+    make("cross", SMALL, "adam", 0.0, 4, True, "cross_small_adam")
 
 
 if __name__ == "__main__":

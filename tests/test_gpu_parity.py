@@ -78,7 +78,7 @@ def build_pair(variant, cfg, optimizer="adam", slope=0.0, seed=11, dropout=0.0):
         t.build_WGAN_GP_nocond()
     else:
         mod = importlib.import_module({"paper": "conditional_gan_cross_attention_with_film",
-                                       "film": "conditional_gan_film"}[variant])
+                                       "film": "conditional_gan_film", "cross": "conditional_gan_cross_attention"}[variant])
         t = mod.WGAN_GP(input_dims=G, latent_dims=cfg["latent"], embedding_dims=cfg["embed"],
                         generator_dims=[H, H, G], discriminator_dims=[H, H, 1], optimizer=optimizer,
                         negative_slope=slope, text_embedding_dims=cfg["text_dim"],
@@ -95,7 +95,7 @@ def build_pair(variant, cfg, optimizer="adam", slope=0.0, seed=11, dropout=0.0):
 
 def ref_order(variant, x, cond):
     """oracle cond tuple -> drop-in train()/train_disc() argument tuples (reference orders)."""
-    if variant == "paper":
+    if variant in ("paper", "cross"):
         patches, ppad, text, tpad = cond
         return (text, tpad, patches, ppad)
     if variant == "film":
@@ -110,7 +110,7 @@ MID = dict(B=64, G=1000, P=8, T=2, embed=256, hidden=256, latent=256, text_dim=7
 
 @pytest.mark.parametrize("variant,cfg,slope", [
     ("vanilla", SMALL, 0.0), ("vanilla", MID, 0.2), ("paper", SMALL, 0.0), ("paper", MID, 0.0),
-    ("film", SMALL, 0.0), ("film", MID, 0.0)])
+    ("film", SMALL, 0.0), ("film", MID, 0.0), ("cross", SMALL, 0.0), ("cross", MID, 0.0)])
 def test_critic_step_matches_oracle(variant, cfg, slope):
     o, t = build_pair(variant, cfg, "adam", slope)
     B, G, L = cfg["B"], cfg["G"], cfg["latent"]
@@ -139,7 +139,8 @@ def test_critic_step_matches_oracle(variant, cfg, slope):
         assert torch.equal(po.detach(), pt.detach().cpu()), k
 
 
-@pytest.mark.parametrize("variant,cfg", [("vanilla", SMALL), ("paper", SMALL), ("film", SMALL), ("paper", MID)])
+@pytest.mark.parametrize("variant,cfg", [("vanilla", SMALL), ("paper", SMALL), ("film", SMALL), ("paper", MID),
+                                         ("cross", SMALL), ("cross", MID)])
 def test_generator_step_matches_oracle(variant, cfg):
     o, t = build_pair(variant, cfg, "adam")
     B, G, L = cfg["B"], cfg["G"], cfg["latent"]

@@ -91,7 +91,8 @@ def test_oracle_matches_reference_golden(name):
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
-@pytest.mark.parametrize("variant,opt", [("vanilla", "rms_prop"), ("paper", "adam"), ("film", "adamw")])
+@pytest.mark.parametrize("variant,opt", [("vanilla", "rms_prop"), ("paper", "adam"), ("film", "adamw"),
+                                         ("cross", "rms_prop")])
 def test_oracle_matches_reference_live(variant, opt):
     G, B = 120, 6
     ref = ref_shim.make_trainer(variant, G, optimizer=opt, seed=3, dropout=0.0)
@@ -100,7 +101,7 @@ def test_oracle_matches_reference_live(variant, opt):
     assert _digest(ref.gen.state_dict()) == _digest(o.gen.state_dict())
     assert _digest(ref.disc.state_dict()) == _digest(o.disc.state_dict())
     x, cond = restated.synthetic_batch(variant, B, G, P=4, T=2, seed=9, ragged=True)
-    if variant == "paper":
+    if variant in ("paper", "cross"):
         patches, ppad, text, tpad = cond
         args = (x, text, tpad, patches, ppad)
     elif variant == "film":
