@@ -704,6 +704,7 @@ static int encode_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t 
 // Optional live profiler: CUDA-event pairs around every tcgen05 GEMM launch (bench.py roofline leg).
 struct GemmRecord {
   int M, N, K0, K1, bn, splits, a_mn, b_mn;
+  int out_bytes;  // bytes written per output element (2 = bf16, 4 = fp32, 6 = both)
 };
 struct GemmProfile {
   bool on = false;
@@ -711,6 +712,7 @@ struct GemmProfile {
   std::vector<GemmRecord> rec;  // one per pair
   size_t used = 0;
   double flops = 0.0;
+  double bytes = 0.0;  // algorithmic: every operand read once, every output written once
   long long launches = 0;
 };
 static GemmProfile g_prof;
@@ -752,7 +754,10 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
     g_prof.used += 2;
     g_prof.flops += 2.0 * args.M * args.N * (static_cast<double>(args.K0) + args.K1);
     g_prof.launches += 1;
-    g_prof.rec.push_back(GemmRecord{args.M, args.N, args.K0, args.K1, PAIR ? -BN : BN, args.splits, args.a_mn, args.b_mn});
+    const int ob = (args.epi.out_bf16 ? 2 : 0) + (args.epi.out_f32 ? 4 : 0);
+    g_prof.bytes += 2.0 * (static_cast<double>(args.M) + args.N) * (static_cast<double>(args.K0) + args.K1) +
+                    static_cast<double>(ob) * args.M * args.N;
+    g_prof.rec.push_back(GemmRecord{args.M, args.N, args.K0, args.K1, PAIR ? -BN : BN, args.splits, args.a_mn, args.b_mn, ob});
     GG_CUDA_CHECK(cudaEventRecord(e0, stream));
   }
   launch_k_cluster(gemm_tc_kernel<BN, STAGES, EPIW, PAIR>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, PAIR ? 2 : 1,
@@ -936,6 +941,7 @@ extern "C" int gg_gemm_profile_begin(void) {
   gg::g_prof.used = 0;
   gg::g_prof.rec.clear();
   gg::g_prof.flops = 0.0;
+  gg::g_prof.bytes = 0.0;
   gg::g_prof.launches = 0;
   return GG_OK;
 }
@@ -957,20 +963,25 @@ extern "C" int gg_gemm_profile_end(double* ms, double* flops, long long* launche
   return GG_OK;
 }
 
+// Algorithmic bytes (operands read once + outputs written once) of the launches of the last profiled region.
+extern "C" double gg_gemm_profile_bytes(void) { return gg::g_prof.bytes; }
+
 // Writes one CSV line per GEMM launch of the last profiled region (call after gg_gemm_profile_end).
 extern "C" int gg_gemm_profile_dump(const char* path) {
   using namespace gg;
   GG_REQUIRE(path, "null path");
   FILE* f = fopen(path, "w");
   GG_REQUIRE(f, "cannot open %s", path);
-  fprintf(f, "idx,M,N,K0,K1,block_n,splits,a_mn,b_mn,us,tflops\n");
+  fprintf(f, "idx,M,N,K0,K1,block_n,splits,a_mn,b_mn,us,tflops,gbs\n");
   for (size_t i = 0; i + 1 < g_prof.used && i / 2 < g_prof.rec.size(); i += 2) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]) != cudaSuccess) t = 0.f;
     const GemmRecord& r = g_prof.rec[i / 2];
     const double fl = 2.0 * r.M * r.N * (static_cast<double>(r.K0) + r.K1);
-    fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%d,%d,%.2f,%.1f\n", i / 2, r.M, r.N, r.K0, r.K1, r.bn, r.splits, r.a_mn,
-            r.b_mn, t * 1e3, t > 0.f ? fl / (t * 1e-3) / 1e12 : 0.0);
+    const double by = 2.0 * (static_cast<double>(r.M) + r.N) * (static_cast<double>(r.K0) + r.K1) +
+                      static_cast<double>(r.out_bytes) * r.M * r.N;
+    fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%d,%d,%.2f,%.1f,%.1f\n", i / 2, r.M, r.N, r.K0, r.K1, r.bn, r.splits, r.a_mn,
+            r.b_mn, t * 1e3, t > 0.f ? fl / (t * 1e-3) / 1e12 : 0.0, t > 0.f ? by / (t * 1e-3) / 1e9 : 0.0);
   }
   fclose(f);
   return GG_OK;

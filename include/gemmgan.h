@@ -122,6 +122,7 @@ long long gg_launch_count(int reset);
 void gg_launch_count_add(long long n); /* a replayed CUDA graph adds the launches it contains */
 int gg_gemm_profile_begin(void);
 int gg_gemm_profile_end(double* ms, double* flops, long long* launches);
+double gg_gemm_profile_bytes(void); /* algorithmic bytes (operands once + outputs once) of the last profiled region */
 int gg_gemm_profile_dump(const char* csv_path); /* per-launch shapes and durations of the last region */
 /* Diagnostics: CTA `cta` of every following GEMM launch stamps clock64() per pipeline role into device_buf
  * (6 x 512 int64: TMA issued / stage full / tile committed / accumulator full / tile stored / origin); NULL = off. */
