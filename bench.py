@@ -244,25 +244,26 @@ def main():
     value = world * w["B"] / (ms_per_step * 1e-3)
     losses = dict(d=[float(v) for v in t.d_batch_loss], g=float(t.g_batch_loss[0]))
 
-    # ---- live GEMM roofline leg: CUDA events around every tcgen05 GEMM launch of one more train() call
-    # (events need real launches, not a graph replay; one lane so that the bracketed kernel runs alone; a
-    # spin kernel in front keeps the GPU busy while the host enqueues, so no launch gap lands between events)
-    graphs_on, t.use_cuda_graphs = t.use_cuda_graphs, False
+    # ---- live GEMM roofline leg: CUDA events around every tcgen05 GEMM launch of one more train() call. The call
+    # is captured into CUDA graphs like the timed steps (the event records become external event nodes), on one
+    # lane so that the bracketed kernel runs alone; the graphs are dropped afterwards.
     for eng in t._engines.values():
-        eng.set_lanes(False)
-    t.train(*batch_dev)
+        eng.set_lanes(False)            # also drops the captured graphs
+    t.train(*batch_dev)                 # re-capture (single lane)
     torch.cuda.synchronize()
+    for eng in t._engines.values():
+        eng.graphs.clear()
+    t.unique_graphs = True              # every step its own capture: one event pair per launch of the whole call
     L.gg_gemm_profile_begin()
-    torch.cuda._sleep(int(30e-3 * 1.9e9))
-    t.train(*batch_dev)
+    t.train(*batch_dev)                 # capture with event nodes + replay
+    t.unique_graphs = False
     ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
     _lib.check(L.gg_gemm_profile_end(C.byref(ms), C.byref(fl), C.byref(nl)))
     if args.gemm_csv and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.gemm_csv)), exist_ok=True)
         _lib.check(L.gg_gemm_profile_dump(args.gemm_csv.encode()))
-    t.use_cuda_graphs = graphs_on
     for eng in t._engines.values():
-        eng.set_lanes(True)
+        eng.set_lanes(True)             # drops the profiling graphs
     # Roofline of the dominant kernel (gemm_tc_kernel): algorithmic work of the launches of one train() over their
     # summed CUDA-event durations. The step's products are skinny (K or N = 256): summed over the launches the
     # byte roofline (operands read once + outputs written once at the measured HBM copy bandwidth) is the larger
@@ -278,7 +279,7 @@ def main():
             traffic = float(json.load(f)["dram_bytes_per_launch"])
     except Exception:  # noqa: BLE001
         pass
-    common = dict(traffic=traffic, kernel="gemm_tc_kernel (tcgen05, all launches of one train(), each timed alone)",
+    common = dict(traffic=traffic, kernel="gemm_tc_kernel (tcgen05; every launch of one train(), CUDA-event pairs inside the replayed graph, one lane)",
                   gemm_launches_per_step=int(nl.value), gemm_ms_per_step=ms.value,
                   gemm_share_of_step=ms.value / ms_per_step, flops_per_step=fl.value, bytes_per_step=by,
                   algorithmic_bytes_per_launch=by / max(int(nl.value), 1), tensor_tflops=tf,

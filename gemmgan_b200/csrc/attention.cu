@@ -738,6 +738,258 @@ __global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const Att
   store_tile(stage, o, 1.f, a.dv + static_cast<int64_t>(b) * S * a.lddkv + h * SELF_HD, a.lddkv, S, lane);
 }
 
+// ------------------------------------------------- mid-size self-attention, head_dim 64 (17 <= S <= 128)
+// The encoder layers at P = 64 patches (BASELINE config 4: S = 65). One CTA per (sequence, head), NT = ceil(S/16)
+// tiles of 16 tokens; Q / K / V (/ dO) of the head are staged once with 16-byte cp.async (rows >= S zero-filled).
+// Forward: a warp owns 16 query rows: the whole 16 x S score row-block lives in m16n8k16 accumulator fragments
+// (softmax in registers, quad shuffles), P V accumulates over the key tiles. Backward: phase 1 (warp = query
+// tile) recomputes P, dP = dO V^T, dS = P o (dP - delta), dQ = dS K and leaves bf16 dS / P in shared memory;
+// phase 2 (warp = key tile) forms dK = dS^T Q and dV = P^T dO from them through ldmatrix.trans. No atomics.
+// (The CUDA-core kernels above took 2.6 ms forward / 10 ms backward per call at 12288 sequences x 65 tokens.)
+__device__ __forceinline__ void mma_frag_b_acc(float (&o)[8][4], const uint32_t (&a)[4], const bf16* B, int lane) {
+  const int brow = (lane & 7) + ((lane >> 3) & 1) * 8, bcol = (lane >> 4) * 8;
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    uint32_t b[4];
+    ldsm_x4_t(b, B + brow * SELF_PITCH + np * 16 + bcol);
+    mma16816(o[2 * np], a, b[0], b[1]);
+    mma16816(o[2 * np + 1], a, b[2], b[3]);
+  }
+}
+
+constexpr int MID_WARPS = 4;
+
+template <int MODE, int NT>
+__global__ void __launch_bounds__(MID_WARPS * 32) attn_self_mid_kernel(const AttnArgs a) {
+  pdl_entry();
+  extern __shared__ __align__(16) uint8_t smem_mid[];
+  constexpr int ROWS = NT * 16;
+  constexpr int SP = ROWS + 8;                       // pitch of the bf16 dS / P matrices
+  constexpr int NTEN = MODE == 1 ? 4 : 3;            // staged tensors: Q, K, V (, dO)
+  const int S = a.Lq;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_mid);
+  bf16* Ks = Qs + ROWS * SELF_PITCH;
+  bf16* Vs = Ks + ROWS * SELF_PITCH;
+  bf16* Gs = Vs + ROWS * SELF_PITCH;                 // dO (backward only)
+  bf16* stage_all = Qs + NTEN * ROWS * SELF_PITCH;   // one 16-row output staging tile per warp
+  bf16* dSs = stage_all + MID_WARPS * SELF_TILE;     // backward only: [ROWS][SP]
+  bf16* Ps = dSs + ROWS * SP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = static_cast<int>(blockIdx.x) / a.H, h = static_cast<int>(blockIdx.x) % a.H;
+  {
+    const int col = h * SELF_HD;
+    const int64_t qb = static_cast<int64_t>(a.q_mod >= a.nb ? b : b % a.q_mod) * S;
+    const int64_t kb = static_cast<int64_t>(a.kv_mod >= a.nb ? b : b % a.kv_mod) * S;
+    for (int idx = threadIdx.x; idx < ROWS * 8; idx += MID_WARPS * 32) {
+      const int row = idx >> 3, part = idx & 7;
+      const bool valid = row < S;
+      bf16* dst = Qs + row * SELF_PITCH + part * 8;
+      cp_async16(dst, valid ? a.q + (qb + row) * a.ldq + col + part * 8 : a.q, valid);
+      cp_async16(dst + ROWS * SELF_PITCH, valid ? a.k + (kb + row) * a.ldkv + col + part * 8 : a.q, valid);
+      cp_async16(dst + 2 * ROWS * SELF_PITCH, valid ? a.v + (kb + row) * a.ldkv + col + part * 8 : a.q, valid);
+      if (MODE == 1)
+        cp_async16(dst + 3 * ROWS * SELF_PITCH,
+                   valid ? a.dout + (static_cast<int64_t>(b) * S + row) * a.lddo + col + part * 8 : a.q, valid);
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  const uint8_t* mk = a.mask ? a.mask + static_cast<int64_t>(b % a.mask_mod) * S : nullptr;
+  const float scale = 0.125f;  // 1/sqrt(64)
+  const int g = lane >> 2, t = lane & 3;
+  bf16* stage = stage_all + warp * SELF_TILE;
+  const bool drop = a.drop_p > 0.f;
+  uint64_t seed = 0, step = 0;
+  if (drop) {
+    seed = a.rng[0];
+    step = a.rng[1];
+  }
+  const float keep_scale = drop ? 1.f / (1.f - a.drop_p) : 1.f;
+  // key validity of this thread's columns: key j = kt*16 + (e>>1)*8 + 2t + (e&1)
+  uint32_t kvalid = 0;  // bit kt*4 + e
+#pragma unroll
+  for (int kt = 0; kt < NT; ++kt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = kt * 16 + (e >> 1) * 8 + 2 * t + (e & 1);
+      if (j < S && !(mk && mk[j])) kvalid |= 1u << (kt * 4 + e);
+    }
+  for (int qt = warp; qt < NT; qt += MID_WARPS) {
+    const bf16* Qt = Qs + qt * SELF_TILE;
+    float p[NT][2][4];  // [key tile][row half][e]
+    {
+      float sc[NT][2][4];
+#pragma unroll
+      for (int kt = 0; kt < NT; ++kt) mma_ab_t(sc[kt], Qt, Ks + kt * SELF_TILE, lane);
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int kt = 0; kt < NT; ++kt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v = ((kvalid >> (kt * 4 + e)) & 1u) ? sc[kt][e >> 1][rh * 2 + (e & 1)] * scale : -INFINITY;
+            p[kt][rh][e] = v;
+            m = fmaxf(m, v);
+          }
+        m = quad_max(m);
+        float l = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < NT; ++kt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            p[kt][rh][e] = ((kvalid >> (kt * 4 + e)) & 1u) ? __expf(p[kt][rh][e] - m) : 0.f;
+            l += p[kt][rh][e];
+          }
+        l = quad_add(l);
+        const float inv_l = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+        for (int kt = 0; kt < NT; ++kt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) p[kt][rh][e] *= inv_l;
+      }
+    }
+    // dropout multipliers folded into a bit mask (bit kt*8 + rh*4 + e = dropped)
+    uint64_t dropped = 0;
+    if (drop) {
+      DropoutStream ds(seed, step, a.site, a.drop_p);
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const int i = qt * 16 + g + rh * 8;
+        const uint64_t pbase = ((static_cast<uint64_t>(b) * a.H + h) * S + i) * static_cast<uint64_t>(S);
+#pragma unroll
+        for (int kt = 0; kt < NT; ++kt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = kt * 16 + (e >> 1) * 8 + 2 * t + (e & 1);
+            if (i < S && j < S && !ds.keep(pbase + j)) dropped |= 1ull << (kt * 8 + rh * 4 + e);
+          }
+      }
+    }
+    auto mult = [&](int kt, int rh, int e) { return ((dropped >> (kt * 8 + rh * 4 + e)) & 1ull) ? 0.f : keep_scale; };
+    uint32_t pa[NT][4];  // A fragments of the (dropped) probabilities
+#pragma unroll
+    for (int kt = 0; kt < NT; ++kt) {
+      pa[kt][0] = pack_bf16(p[kt][0][0] * mult(kt, 0, 0), p[kt][0][1] * mult(kt, 0, 1));
+      pa[kt][1] = pack_bf16(p[kt][1][0] * mult(kt, 1, 0), p[kt][1][1] * mult(kt, 1, 1));
+      pa[kt][2] = pack_bf16(p[kt][0][2] * mult(kt, 0, 2), p[kt][0][3] * mult(kt, 0, 3));
+      pa[kt][3] = pack_bf16(p[kt][1][2] * mult(kt, 1, 2), p[kt][1][3] * mult(kt, 1, 3));
+    }
+    const int rows_valid = min(16, S - qt * 16);
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[n][j] = 0.f;
+    if (MODE == 0) {
+#pragma unroll
+      for (int kt = 0; kt < NT; ++kt) mma_frag_b_acc(o, pa[kt], Vs + kt * SELF_TILE, lane);
+      store_tile(stage, o, 1.f, a.o + (static_cast<int64_t>(b) * S + qt * 16) * a.ldo + h * SELF_HD, a.ldo, rows_valid,
+                 lane);
+      continue;
+    }
+    // ---- backward, phase 1
+    const bf16* Gt = Gs + qt * SELF_TILE;
+    float delta[2] = {0.f, 0.f};
+    float dsv[NT][2][4];
+#pragma unroll
+    for (int kt = 0; kt < NT; ++kt) {
+      float dp[2][4];
+      mma_ab_t(dp, Gt, Vs + kt * SELF_TILE, lane);  // dP~ = dO V^T
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d = dp[e >> 1][rh * 2 + (e & 1)] * mult(kt, rh, e);
+          dsv[kt][rh][e] = d;
+          delta[rh] = fmaf(p[kt][rh][e], d, delta[rh]);
+        }
+    }
+    delta[0] = quad_add(delta[0]);
+    delta[1] = quad_add(delta[1]);
+#pragma unroll
+    for (int kt = 0; kt < NT; ++kt) {
+      uint32_t da[4];
+      da[0] = pack_bf16(p[kt][0][0] * (dsv[kt][0][0] - delta[0]), p[kt][0][1] * (dsv[kt][0][1] - delta[0]));
+      da[1] = pack_bf16(p[kt][1][0] * (dsv[kt][1][0] - delta[1]), p[kt][1][1] * (dsv[kt][1][1] - delta[1]));
+      da[2] = pack_bf16(p[kt][0][2] * (dsv[kt][0][2] - delta[0]), p[kt][0][3] * (dsv[kt][0][3] - delta[0]));
+      da[3] = pack_bf16(p[kt][1][2] * (dsv[kt][1][2] - delta[1]), p[kt][1][3] * (dsv[kt][1][3] - delta[1]));
+      mma_frag_b_acc(o, da, Ks + kt * SELF_TILE, lane);  // dQ += dS K
+      bf16* dst = dSs + (qt * 16) * SP + kt * 16;
+      bf16* pst = Ps + (qt * 16) * SP + kt * 16;
+      *reinterpret_cast<uint32_t*>(dst + g * SP + 2 * t) = da[0];
+      *reinterpret_cast<uint32_t*>(dst + (g + 8) * SP + 2 * t) = da[1];
+      *reinterpret_cast<uint32_t*>(dst + g * SP + 8 + 2 * t) = da[2];
+      *reinterpret_cast<uint32_t*>(dst + (g + 8) * SP + 8 + 2 * t) = da[3];
+      *reinterpret_cast<uint32_t*>(pst + g * SP + 2 * t) = pa[kt][0];
+      *reinterpret_cast<uint32_t*>(pst + (g + 8) * SP + 2 * t) = pa[kt][1];
+      *reinterpret_cast<uint32_t*>(pst + g * SP + 8 + 2 * t) = pa[kt][2];
+      *reinterpret_cast<uint32_t*>(pst + (g + 8) * SP + 8 + 2 * t) = pa[kt][3];
+    }
+    store_tile(stage, o, scale, a.dq + (static_cast<int64_t>(b) * S + qt * 16) * a.lddq + h * SELF_HD, a.lddq,
+               rows_valid, lane);
+  }
+  if (MODE == 0) return;
+  __syncthreads();
+  // ---- backward, phase 2: A fragments of X^T from the [query][key] matrices
+  const int trow = (lane & 7) + (lane >> 4) * 8, tcol = ((lane >> 3) & 1) * 8;
+  for (int kt = warp; kt < NT; kt += MID_WARPS) {
+    const int rows_valid = min(16, S - kt * 16);
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[n][j] = 0.f;
+#pragma unroll
+    for (int qt = 0; qt < NT; ++qt) {
+      uint32_t ta[4];
+      ldsm_x4_t(ta, dSs + (qt * 16 + trow) * SP + kt * 16 + tcol);
+      mma_frag_b_acc(o, ta, Qs + qt * SELF_TILE, lane);  // dK += dS^T Q
+    }
+    store_tile(stage, o, scale, a.dk + (static_cast<int64_t>(b) * S + kt * 16) * a.lddkv + h * SELF_HD, a.lddkv,
+               rows_valid, lane);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[n][j] = 0.f;
+#pragma unroll
+    for (int qt = 0; qt < NT; ++qt) {
+      uint32_t ta[4];
+      ldsm_x4_t(ta, Ps + (qt * 16 + trow) * SP + kt * 16 + tcol);
+      mma_frag_b_acc(o, ta, Gs + qt * SELF_TILE, lane);  // dV += P^T dO
+    }
+    store_tile(stage, o, 1.f, a.dv + (static_cast<int64_t>(b) * S + kt * 16) * a.lddkv + h * SELF_HD, a.lddkv,
+               rows_valid, lane);
+  }
+}
+
+template <int MODE, int NT>
+static int launch_mid_nt(const AttnArgs& a, cudaStream_t st) {
+  constexpr int ROWS = NT * 16;
+  const size_t smem = (static_cast<size_t>((MODE == 1 ? 4 : 3) * ROWS * SELF_PITCH + MID_WARPS * SELF_TILE +
+                                           (MODE == 1 ? 2 * ROWS * (ROWS + 8) : 0))) * 2 + 16;
+  static bool configured = false;
+  if (!configured) {
+    GG_CUDA_CHECK(cudaFuncSetAttribute(attn_self_mid_kernel<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    configured = true;
+  }
+  launch_k(attn_self_mid_kernel<MODE, NT>, static_cast<unsigned>(a.nb) * a.H, MID_WARPS * 32, smem, st, a);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+template <int MODE>
+static int launch_mid(const AttnArgs& a, cudaStream_t st) {
+  const int nt = (a.Lq + 15) / 16;
+  if (nt <= 2) return launch_mid_nt<MODE, 2>(a, st);
+  if (nt <= 3) return launch_mid_nt<MODE, 3>(a, st);
+  if (nt <= 4) return launch_mid_nt<MODE, 4>(a, st);
+  if (nt <= 5) return launch_mid_nt<MODE, 5>(a, st);
+  if (nt <= 6) return launch_mid_nt<MODE, 6>(a, st);
+  return launch_mid_nt<MODE, 8>(a, st);
+}
+
 static size_t self_smem_bytes(int mode) {
   const int nt = mode == 1 ? 4 : 3;
   return static_cast<size_t>(SELF_GROUPS) * ((nt + 1) * SELF_TILE + (mode == 1 ? 2 * 16 * SELF_SP : 0)) * 2 + 16;
@@ -778,8 +1030,9 @@ static void launch_small_kv(const AttnArgs& a, const float* stat, cudaStream_t s
   }
 }
 
-static bool self_path(const AttnArgs& a) {
-  if (!(a.Lq == a.Lk && a.Lk <= SM_MAXL && a.hd == SELF_HD)) return false;
+constexpr int MID_MAXL = 128;
+static bool self_path(const AttnArgs& a, int maxl = SM_MAXL) {
+  if (!(a.Lq == a.Lk && a.Lk <= maxl && a.hd == SELF_HD)) return false;
   const bool ok = a.ldq % 8 == 0 && a.ldkv % 8 == 0 && aligned16(a.q) && aligned16(a.k) && aligned16(a.v) &&
                   (!a.o || (a.ldo % 8 == 0 && aligned16(a.o))) &&
                   (!a.dout || (a.lddo % 8 == 0 && aligned16(a.dout) && a.lddq % 8 == 0 && aligned16(a.dq) &&
@@ -814,6 +1067,7 @@ int k_attention_fwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_args(a);
   if (rc) return rc;
   if (self_path(a)) return launch_self<0>(a, st);
+  if (self_path(a, MID_MAXL)) return launch_mid<0>(a, st);
   if (small_path(a)) {
     launch_small_q<0>(a, nullptr, st);
     GG_LAUNCH_CHECK();
@@ -837,6 +1091,7 @@ int k_attention_bwd(const AttnArgs& a, cudaStream_t st) {
   int rc = check_args(a);
   if (rc) return rc;
   if (self_path(a)) return launch_self<1>(a, st);
+  if (self_path(a, MID_MAXL)) return launch_mid<1>(a, st);
   if (small_path(a)) {
     GG_REQUIRE(a.stat != nullptr, "short-sequence attention backward needs a stats scratch buffer");
     launch_small_q<1>(a, a.stat, st);

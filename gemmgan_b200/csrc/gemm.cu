@@ -719,6 +719,17 @@ static GemmProfile g_prof;
 static long long* g_trace_buf = nullptr;  // device buffer of 6 * TRACE_ROLE_STRIDE stamps, or null
 static int g_trace_cta = 0;
 
+// Event record that also works while the stream is being captured into a CUDA graph (an external event-record
+// node): the profiled train() call can then be replayed as a graph, so the event pairs bracket the kernels as
+// they run in the real step (no host launch gaps between them).
+static cudaError_t prof_record(cudaEvent_t ev, cudaStream_t stream) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaError_t rc = cudaStreamIsCapturing(stream, &cs);
+  if (rc != cudaSuccess) return rc;
+  return cs == cudaStreamCaptureStatusActive ? cudaEventRecordWithFlags(ev, stream, cudaEventRecordExternal)
+                                             : cudaEventRecord(ev, stream);
+}
+
 template <int BN, int STAGES, int EPIW, bool PAIR = false>
 static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = TileCfg<BN, STAGES, EPIW, PAIR>;
@@ -758,12 +769,12 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
     g_prof.bytes += 2.0 * (static_cast<double>(args.M) + args.N) * (static_cast<double>(args.K0) + args.K1) +
                     static_cast<double>(ob) * args.M * args.N;
     g_prof.rec.push_back(GemmRecord{args.M, args.N, args.K0, args.K1, PAIR ? -BN : BN, args.splits, args.a_mn, args.b_mn, ob});
-    GG_CUDA_CHECK(cudaEventRecord(e0, stream));
+    GG_CUDA_CHECK(prof_record(e0, stream));
   }
   launch_k_cluster(gemm_tc_kernel<BN, STAGES, EPIW, PAIR>, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, PAIR ? 2 : 1,
                    maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], args);
   GG_LAUNCH_CHECK();
-  if (e1) GG_CUDA_CHECK(cudaEventRecord(e1, stream));
+  if (e1) GG_CUDA_CHECK(prof_record(e1, stream));
   return GG_OK;
 }
 

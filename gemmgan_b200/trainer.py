@@ -102,6 +102,8 @@ class TrainerBase:
         self.dp_graph_collectives = os.environ.get("GEMMGAN_DP_GRAPH", "1") != "0"
         self.dp_global_noise = False   # draw z/alpha for the GLOBAL batch and slice (N-rank == 1-rank parity)
         self.use_cuda_graphs = os.environ.get("GEMMGAN_CUDA_GRAPHS", "1") != "0"
+        self.unique_graphs = False
+        self._graph_seq = 0
         self._engines = {}
         self._flat_gen = self._flat_disc = None
         self._pinned = None
@@ -222,6 +224,9 @@ class TrainerBase:
         if not self.use_cuda_graphs:
             body()
             return
+        if self.unique_graphs:  # diagnostics: one capture per step (bench.py's per-launch event timing)
+            self._graph_seq += 1
+            key = key + (self._graph_seq,)
         g = eng.graphs.get(key)
         if g is None:
             if key[0] not in eng.warmed:
