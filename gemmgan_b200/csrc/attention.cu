@@ -757,12 +757,12 @@ __device__ __forceinline__ void mma_frag_b_acc(float (&o)[8][4], const uint32_t 
   }
 }
 
-constexpr int MID_WARPS = 4;
 
 template <int MODE, int NT>
-__global__ void __launch_bounds__(MID_WARPS * 32) attn_self_mid_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(NT * 32) attn_self_mid_kernel(const AttnArgs a) {
   pdl_entry();
   extern __shared__ __align__(16) uint8_t smem_mid[];
+  constexpr int MID_WARPS = NT;  // one warp per 16-token tile (query tile in phase 1, key tile in phase 2)
   constexpr int ROWS = NT * 16;
   constexpr int SP = ROWS + 8;                       // pitch of the bf16 dS / P matrices
   constexpr int NTEN = MODE == 1 ? 4 : 3;            // staged tensors: Q, K, V (, dO)
@@ -967,6 +967,7 @@ __global__ void __launch_bounds__(MID_WARPS * 32) attn_self_mid_kernel(const Att
 template <int MODE, int NT>
 static int launch_mid_nt(const AttnArgs& a, cudaStream_t st) {
   constexpr int ROWS = NT * 16;
+  constexpr int MID_WARPS = NT;
   const size_t smem = (static_cast<size_t>((MODE == 1 ? 4 : 3) * ROWS * SELF_PITCH + MID_WARPS * SELF_TILE +
                                            (MODE == 1 ? 2 * ROWS * (ROWS + 8) : 0))) * 2 + 16;
   static bool configured = false;
@@ -988,6 +989,126 @@ static int launch_mid(const AttnArgs& a, cudaStream_t st) {
   if (nt <= 5) return launch_mid_nt<MODE, 5>(a, st);
   if (nt <= 6) return launch_mid_nt<MODE, 6>(a, st);
   return launch_mid_nt<MODE, 8>(a, st);
+}
+
+// ------------------------------------------------- single-query cross-attention, head_dim 64, Lk <= 128
+// patch2text / text2patch attention of the paper model (Lq = 1; :149-152) at 64 patches / 32 text tokens. One WARP
+// per (row, head): lane l scores keys l, l+32, ... from their own 128-byte K rows, softmax by warp shuffles, the
+// output accumulates the V rows coalesced (lane = 2 head dims). The backward is the same walk (p recomputed):
+// dv_j = p_j dO, dk_j = ds_j q / 8, dq = sum_j ds_j k_j / 8 with ds_j = p_j (dO.v_j - sum_i p_i dO.v_i).
+// No dropout on these attentions (nn.MultiheadAttention default, :120-123).
+constexpr int Q1_MAXK = 4;  // keys per lane
+
+__device__ __forceinline__ float dot64(const uint4 (&a)[8], const bf16* row) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 kv = __ldg(reinterpret_cast<const uint4*>(row) + c);
+    const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a[c]);
+    const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&kv);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 fx = __bfloat1622float2(x[t]), fy = __bfloat1622float2(y[t]);
+      acc = fmaf(fx.x, fy.x, acc);
+      acc = fmaf(fx.y, fy.y, acc);
+    }
+  }
+  return acc;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) attn_q1_kernel(const AttnArgs a) {
+  pdl_entry();
+  const int lane = threadIdx.x & 31;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (gid >= static_cast<int64_t>(a.nb) * a.H) return;
+  const int b = static_cast<int>(gid / a.H), h = static_cast<int>(gid % a.H);
+  const int Lk = a.Lk;
+  const int64_t qrow = a.q_mod >= a.nb ? b : b % a.q_mod;
+  const int64_t kb = static_cast<int64_t>(a.kv_mod >= a.nb ? b : b % a.kv_mod) * Lk;
+  const bf16* qp = a.q + qrow * a.ldq + h * 64;
+  const bf16* Kp = a.k + kb * a.ldkv + h * 64;
+  const bf16* Vp = a.v + kb * a.ldkv + h * 64;
+  const uint8_t* mk = a.mask ? a.mask + static_cast<int64_t>(b % a.mask_mod) * Lk : nullptr;
+  uint4 qv[8];  // the whole query row (and dO row) in every lane: 128 bytes each
+#pragma unroll
+  for (int c = 0; c < 8; ++c) qv[c] = __ldg(reinterpret_cast<const uint4*>(qp) + c);
+  float sc[Q1_MAXK];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < Q1_MAXK; ++i) {
+    const int j = lane + 32 * i;
+    sc[i] = -INFINITY;
+    if (j < Lk && !(mk && mk[j])) sc[i] = dot64(qv, Kp + static_cast<int64_t>(j) * a.ldkv) * 0.125f;
+    m = fmaxf(m, sc[i]);
+  }
+  m = wmax(m);
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < Q1_MAXK; ++i) {
+    sc[i] = sc[i] == -INFINITY ? 0.f : __expf(sc[i] - m);
+    l += sc[i];
+  }
+  l = wsum2(l);
+  const float inv_l = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+  for (int i = 0; i < Q1_MAXK; ++i) sc[i] *= inv_l;  // p_j of key lane + 32 i
+  if (MODE == 0) {
+    float2 acc = make_float2(0.f, 0.f);
+    for (int j = 0; j < Lk; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31);
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vp + static_cast<int64_t>(j) * a.ldkv + 2 * lane));
+      acc.x = fmaf(pj, v.x, acc.x);
+      acc.y = fmaf(pj, v.y, acc.y);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(a.o + static_cast<int64_t>(b) * a.ldo + h * 64 + 2 * lane) = __floats2bfloat162_rn(acc.x, acc.y);
+    return;
+  }
+  // ---- backward
+  const bf16* gp = a.dout + static_cast<int64_t>(b) * a.lddo + h * 64;
+  uint4 gv[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) gv[c] = __ldg(reinterpret_cast<const uint4*>(gp) + c);
+  float dp[Q1_MAXK];
+  float delta = 0.f;
+#pragma unroll
+  for (int i = 0; i < Q1_MAXK; ++i) {
+    const int j = lane + 32 * i;
+    dp[i] = (j < Lk && sc[i] != 0.f) ? dot64(gv, Vp + static_cast<int64_t>(j) * a.ldkv) : 0.f;
+    delta = fmaf(sc[i], dp[i], delta);
+  }
+  delta = wsum2(delta);
+#pragma unroll
+  for (int i = 0; i < Q1_MAXK; ++i) dp[i] = sc[i] * (dp[i] - delta) * 0.125f;  // ds_j / 8
+  const float2 g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gp + 2 * lane));
+  const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qp + 2 * lane));
+  bf16* dKp = a.dk + static_cast<int64_t>(b) * Lk * a.lddkv + h * 64;
+  bf16* dVp = a.dv + static_cast<int64_t>(b) * Lk * a.lddkv + h * 64;
+  float2 dq = make_float2(0.f, 0.f);
+  for (int j = 0; j < Lk; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31);
+    const float dsj = __shfl_sync(0xffffffffu, dp[j >> 5], j & 31);
+    const float2 kx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Kp + static_cast<int64_t>(j) * a.ldkv + 2 * lane));
+    dq.x = fmaf(dsj, kx.x, dq.x);
+    dq.y = fmaf(dsj, kx.y, dq.y);
+    *reinterpret_cast<__nv_bfloat162*>(dKp + static_cast<int64_t>(j) * a.lddkv + 2 * lane) = __floats2bfloat162_rn(dsj * q2.x, dsj * q2.y);
+    *reinterpret_cast<__nv_bfloat162*>(dVp + static_cast<int64_t>(j) * a.lddkv + 2 * lane) = __floats2bfloat162_rn(pj * g2.x, pj * g2.y);
+  }
+  *reinterpret_cast<__nv_bfloat162*>(a.dq + static_cast<int64_t>(b) * a.lddq + h * 64 + 2 * lane) = __floats2bfloat162_rn(dq.x, dq.y);
+}
+
+static bool aligned16(const void* p);
+static bool q1_path(const AttnArgs& a) {
+  if (!(a.Lq == 1 && a.Lk > SM_MAXL && a.Lk <= 32 * Q1_MAXK && a.hd == 64 && a.drop_p == 0.f)) return false;
+  return a.ldq % 8 == 0 && a.ldkv % 8 == 0 && aligned16(a.q) && aligned16(a.k) && aligned16(a.v) &&
+         (!a.dout || (a.lddo % 8 == 0 && aligned16(a.dout)));
+}
+template <int MODE>
+static int launch_q1(const AttnArgs& a, cudaStream_t st) {
+  const int64_t groups = static_cast<int64_t>(a.nb) * a.H;
+  launch_k(attn_q1_kernel<MODE>, static_cast<unsigned>((groups + 3) / 4), 128, 0, st, a);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
 }
 
 static size_t self_smem_bytes(int mode) {
@@ -1068,6 +1189,7 @@ int k_attention_fwd(const AttnArgs& a, cudaStream_t st) {
   if (rc) return rc;
   if (self_path(a)) return launch_self<0>(a, st);
   if (self_path(a, MID_MAXL)) return launch_mid<0>(a, st);
+  if (q1_path(a)) return launch_q1<0>(a, st);
   if (small_path(a)) {
     launch_small_q<0>(a, nullptr, st);
     GG_LAUNCH_CHECK();
@@ -1092,6 +1214,7 @@ int k_attention_bwd(const AttnArgs& a, cudaStream_t st) {
   if (rc) return rc;
   if (self_path(a)) return launch_self<1>(a, st);
   if (self_path(a, MID_MAXL)) return launch_mid<1>(a, st);
+  if (q1_path(a)) return launch_q1<1>(a, st);
   if (small_path(a)) {
     GG_REQUIRE(a.stat != nullptr, "short-sequence attention backward needs a stats scratch buffer");
     launch_small_q<1>(a, a.stat, st);

@@ -70,3 +70,74 @@ def test_attention_dropout_forward_backward_consistent(nb, L):
     # roughly 30 % of the probabilities are dropped: outputs differ from the dropout-free ones
     o0 = ops.attention(qkv, nb, H, L)
     assert (o0.float() - o1.float()).abs().mean().item() > 1e-3
+
+
+def _cross(q, kv, nb, H, Lk, mask=None, dout=None, kv_rows_shared=False):
+    """Single-query cross-attention through the C ABI: q [nb, E], kv [nb(or nb/2)*Lk, 2E] (k | v)."""
+    import ctypes as C
+
+    from gemmgan_b200 import _abi_decl as A
+    from gemmgan_b200 import _lib
+
+    L = _lib.lib()
+    E = q.shape[1]
+    a = A.AttnArgs()
+    a.q, a.ldq, a.q_mod = q.data_ptr(), q.stride(0), nb
+    a.k, a.v, a.ldkv = kv.data_ptr(), kv.data_ptr() + 2 * E, kv.stride(0)
+    a.kv_mod = kv.shape[0] // Lk
+    if mask is not None:
+        a.mask, a.mask_mod = mask.data_ptr(), mask.shape[0]
+    a.nb, a.H, a.hd, a.Lq, a.Lk = nb, H, E // H, 1, Lk
+    o = torch.empty(nb, E, device=q.device, dtype=torch.bfloat16)
+    a.o, a.ldo = o.data_ptr(), E
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.gg_attention_fwd(C.byref(a), st))
+    if dout is None:
+        return o
+    dq = torch.empty_like(q)
+    dkv = torch.empty(nb * Lk, 2 * E, device=q.device, dtype=torch.bfloat16)   # per-row gradients (replicas unsummed)
+    stat = torch.empty(2 * nb * H, device=q.device, dtype=torch.float32)
+    a.dout, a.lddo = dout.data_ptr(), dout.stride(0)
+    a.dq, a.lddq = dq.data_ptr(), dq.stride(0)
+    a.dk, a.dv, a.lddkv = dkv.data_ptr(), dkv.data_ptr() + 2 * E, dkv.stride(0)
+    a.stat = stat.data_ptr()
+    _lib.check(L.gg_attention_bwd(C.byref(a), st))
+    return o, dq, dkv
+
+
+@pytest.mark.parametrize("nb,Lk", [(33, 17), (40, 32), (24, 65), (10, 100), (6, 128), (12, 9), (4, 200)])
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("shared_kv", [False, True])
+def test_single_query_cross_attention(nb, Lk, masked, shared_kv):
+    """patch2text / text2patch attention (Lq = 1): the warp-per-head kernel (17 <= Lk <= 128) and its neighbours;
+    shared_kv: two replicas of the rows read the same keys / values (kv_mod = nb / 2), gradients stay per row."""
+    H, hd = 4, 64
+    E = H * hd
+    g = torch.Generator(device="cuda").manual_seed(nb * 100 + Lk)
+    nb -= nb % 2
+    nkv = nb // 2 if shared_kv else nb
+    q = torch.randn(nb, E, device="cuda", generator=g).to(torch.bfloat16)
+    kv = torch.randn(nkv * Lk, 2 * E, device="cuda", generator=g).to(torch.bfloat16)
+    dout = torch.randn(nb, E, device="cuda", generator=g).to(torch.bfloat16)
+    mask = None
+    if masked:
+        mask = (torch.rand(nkv, Lk, device="cuda", generator=g) < 0.3).to(torch.uint8)
+        mask[:, 0] = 0
+    o, dq, dkv = _cross(q, kv, nb, H, Lk, mask=mask, dout=dout)
+    torch.cuda.synchronize()
+    qf = q.float().requires_grad_(True)
+    kvf = kv.float().view(nkv, Lk, 2 * E)
+    kvf = (kvf.repeat(2, 1, 1) if shared_kv else kvf).clone().requires_grad_(True)     # row b reads kv[b % nkv]
+    qh = qf.view(nb, 1, H, hd).transpose(1, 2)
+    kh = kvf[:, :, :E].reshape(nb, Lk, H, hd).transpose(1, 2)
+    vh = kvf[:, :, E:].reshape(nb, Lk, H, hd).transpose(1, 2)
+    am = None
+    if mask is not None:
+        mm = mask.bool().repeat(2, 1) if shared_kv else mask.bool()
+        am = torch.zeros(nb, 1, 1, Lk, device="cuda").masked_fill_(mm.view(nb, 1, 1, Lk), float("-inf"))
+    oref = torch.nn.functional.scaled_dot_product_attention(qh, kh, vh, attn_mask=am).transpose(1, 2).reshape(nb, E)
+    oref.backward(dout.float())
+    assert (o.float() - oref).abs().max().item() <= 1e-2 * oref.abs().max().item()
+    assert (dq.float() - qf.grad).abs().max().item() <= 1.5e-2 * qf.grad.abs().max().item()
+    gref = kvf.grad.reshape(nb * Lk, 2 * E)
+    assert (dkv.float() - gref).abs().max().item() <= 1.5e-2 * gref.abs().max().item()
