@@ -255,6 +255,7 @@ def main():
         eng.graphs.clear()
     t.unique_graphs = True              # every step its own capture: one event pair per launch of the whole call
     L.gg_gemm_profile_begin()
+    t._replay_events.clear()
     t.train(*batch_dev)                 # capture with event nodes + replay
     t.unique_graphs = False
     ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
@@ -268,6 +269,10 @@ def main():
     # summed CUDA-event durations. The step's products are skinny (K or N = 256): summed over the launches the
     # byte roofline (operands read once + outputs written once at the measured HBM copy bandwidth) is the larger
     # of the two lower bounds, so that is the bound reported; the tensor-pipe view is given next to it.
+    # device time of the profiled call itself (the six graph replays; one lane, kernels serialised by the event
+    # nodes): the denominator that matches ncu's serialised launch list
+    torch.cuda.synchronize()
+    profiled_call_ms = sum(a.elapsed_time(b) for a, b in t._replay_events) or float("nan")
     by = float(L.gg_gemm_profile_bytes())
     secs = ms.value * 1e-3
     tf = fl.value / secs / 1e12 if secs > 0 else 0.0
@@ -281,7 +286,8 @@ def main():
         pass
     common = dict(traffic=traffic, kernel="gemm_tc_kernel (tcgen05; every launch of one train(), CUDA-event pairs inside the replayed graph, one lane)",
                   gemm_launches_per_step=int(nl.value), gemm_ms_per_step=ms.value,
-                  gemm_share_of_step=ms.value / ms_per_step, flops_per_step=fl.value, bytes_per_step=by,
+                  gemm_share_of_step=ms.value / ms_per_step, gemm_ms_over_profiled_call_ms=ms.value / profiled_call_ms,
+                  profiled_call_ms=profiled_call_ms, flops_per_step=fl.value, bytes_per_step=by,
                   algorithmic_bytes_per_launch=by / max(int(nl.value), 1), tensor_tflops=tf,
                   tensor_frac=tf / pk["tflops"], hbm_gbs=gbs, hbm_frac=gbs / pk["hbm"],
                   peak_source=f"{'hbm_gbs' if t_hbm >= t_tensor else 'bf16_tflops_sustained'} of {pk['src']} MEASURED_PEAKS.json")

@@ -46,7 +46,8 @@ class NetBuffers(C.Structure):
 
 class WgradItem(C.Structure):
     _fields_ = [("dy", C.c_void_p), ("ld_dy", C.c_int64), ("x", C.c_void_p), ("ld_x", C.c_int64),
-                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("out", C.c_void_p), ("ld", C.c_int64)]
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("out", C.c_void_p), ("ld", C.c_int64),
+                ("bias", C.c_void_p)]
 
 
 class AttnArgs(C.Structure):

@@ -167,6 +167,18 @@ struct gg_engine {
     forked[lane] = false;
     return GG_OK;
   }
+  // lane `dst` waits for everything enqueued on lane `src` so far (neither is lane 0's bookkeeping)
+  int wait_lane(int dst, int src) {
+    dst = L(dst);
+    src = L(src);
+    if (dst == src) return GG_OK;
+    cudaEvent_t ev = evs[ev_next];
+    ev_next = (ev_next + 1) % NEVENTS;
+    GG_CUDA_CHECK(cudaEventRecord(ev, cur[src]));
+    GG_CUDA_CHECK(cudaStreamWaitEvent(cur[dst], ev, 0));
+    if (dst != 0) forked[dst] = true;
+    return GG_OK;
+  }
   int join_all() {
     for (int l = 1; l < NLANES; ++l) {
       int rc = join(l);
@@ -225,6 +237,24 @@ struct gg_engine {
   }
   // launches what has been queued: ordered after everything lane 0 has enqueued so far
   int flush_grads() {
+    // a bias gradient whose dY is also the dY of a queued weight gradient is formed inside the grouped wgrad
+    // kernel (ones-column MMA); only the rest (CLS token, in-proj slices without a matching GEMM) needs a column sum
+    if (fuse_bias && !wq.empty()) {
+      size_t keep = 0;
+      for (size_t i = 0; i < bq.size(); ++i) {
+        const ColsumItem& b = bq[i];
+        bool fused = false;
+        for (WgradItem& w : wq) {
+          if (!w.bias && w.dy == b.in && w.ld_dy == b.ld && w.K == b.rows && w.M == b.N) {
+            w.bias = b.out;
+            fused = true;
+            break;
+          }
+        }
+        if (!fused) bq[keep++] = b;
+      }
+      bq.resize(keep);
+    }
     if (!wq.empty()) {
       GG_TRY(fork(1));
       GG_TRY(k_wgrad_group(wq.data(), static_cast<int>(wq.size()), wg_ws, wg_ws_bytes, S(1)));
@@ -240,6 +270,7 @@ struct gg_engine {
   std::vector<WgradItem> wq;
   std::vector<ColsumItem> bq;
   bool group_grads = true;
+  bool fuse_bias = true;  // GEMMGAN_FUSE_BIAS=0: keep every bias gradient in the grouped column-sum kernel
   // one workspace per flush in flight: flushes of one entry point run back to back on their lane, so
   // they rotate through GROUP_WS_SLOTS regions
   void *wg_ws = nullptr, *cs_ws = nullptr;
@@ -774,10 +805,9 @@ static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, 
 // matrix of W1x. Leaves u2, u1, y, dv1, ru1, norms, pen and the loss stats behind.
 // `fake_lane`: lane that is producing the fake rows of xfr (joined before the trunk reads them); the
 // critic tower (conditioning only) and the Gram matrix (weights only) do not wait for it.
-static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int fake_lane) {
+static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int fake_lane, int gp_lane = 0) {
   const gg_model_cfg& c = e.cfg;
   TrunkBufs& t = e.tb;
-  cudaStream_t st = e.S(0);
   const int B = c.B, H = c.H, G = c.G, net = GG_NET_DISC;
   const float inv_b = 1.f / static_cast<float>(B);
   const Op W1x = e.W(net, GG_P_TR0_W), W2 = e.W(net, GG_P_TR1_W);
@@ -786,13 +816,18 @@ static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int
   if (e.cond) GG_TRY(tower_forward(e, net, R, p, 0));
   GG_TRY(e.join(fake_lane));
   GG_TRY(critic_trunk_forward(e, e.xfr, 2, 3, R, alpha));
+  // The penalty's own chain (u2 -> u1 -> y = u1 M -> row norms -> losses) feeds only the loss statistics and the
+  // GP weight gradients: in the training step it runs on `gp_lane` next to the backward chain of lane 0.
+  if (gp_lane != 0) GG_TRY(e.fork(gp_lane));
+  cudaStream_t st = e.S(gp_lane);
   const float* w3 = e.P(net, GG_P_FIN_W);
   const bf16* h1i = t.h1 + static_cast<int64_t>(2) * B * H;
   const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;
   GG_TRY(k_gp_u2(h2i, w3, t.u2, B, H, c.slope, st));
-  GG_TRY(e.dgrad(0, B, H, H, Op{t.u2, H}, W2, Epi().mask(h1i, H, 1.f, c.slope).obf(t.u1b, H).of32(t.u1f, H)));
-  GG_TRY(e.join(2));
-  GG_TRY(e.linear(0, B, H, H, Op{t.u1b, H}, Op{t.Mgb, H}, Epi().of32(t.y, H)));
+  GG_TRY(e.dgrad(gp_lane, B, H, H, Op{t.u2, H}, W2, Epi().mask(h1i, H, 1.f, c.slope).obf(t.u1b, H).of32(t.u1f, H)));
+  if (gp_lane != 0) GG_TRY(e.wait_lane(gp_lane, 2));
+  else GG_TRY(e.join(2));
+  GG_TRY(e.linear(gp_lane, B, H, H, Op{t.u1b, H}, Op{t.Mgb, H}, Epi().of32(t.y, H)));
   GG_TRY(k_gp_rows(t.y, t.u1f, h1i, t.norms, t.pen, t.ru1, t.dv1, B, H, c.slope, c.gp_weight, inv_b, st));
   GG_TRY(k_disc_losses(t.score, t.pen, e.stats, B, c.gp_weight, inv_b, st));
   return GG_OK;
@@ -841,6 +876,8 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
     e->multi_lane = !(ml && ml[0] == '1' && ml[1] == 0);
     const char* gr = getenv("GEMMGAN_GROUP_GRADS");
     e->group_grads = !(gr && gr[0] == '0');
+    const char* fb = getenv("GEMMGAN_FUSE_BIAS");
+    e->fuse_bias = !(fb && fb[0] == '0');
   }
   for (int l = 1; l < gg_engine::NLANES; ++l)
     GG_CUDA_CHECK(cudaStreamCreateWithFlags(&e->cur[l], cudaStreamNonBlocking));
@@ -932,7 +969,7 @@ static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int
   // interpolated rows (:391-408), GP value (:351-374)
   GG_TRY(e->fork(1));
   GG_TRY(gen_forward(*e, z, p, nullptr, 1));
-  GG_TRY(disc_forward_gp(*e, R, p, alpha, 1));
+  GG_TRY(disc_forward_gp(*e, R, p, alpha, 1, 1));  // the GP chain continues on lane 1
   const Op W1x = e->W(net, GG_P_TR0_W), W2 = e->W(net, GG_P_TR1_W);
   const float* w3 = e->P(net, GG_P_FIN_W);
   const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;

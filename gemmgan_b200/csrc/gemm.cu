@@ -868,7 +868,9 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
       if (splits > total_kb / 4) splits = total_kb / 4;
       if (splits > 32) splits = 32;
     }
-  } else if (d->workspace && tiles < 100 && total_kb >= 8) {
+  } else if (d->workspace && tiles < 100 && total_kb >= 32) {
+    // (a split costs a second launch — ~6 us on a dependent chain — so K <= 1984 stays in one pass: the short
+    // [B, 256] x K <= 1024 products of the towers are latency-, not throughput-bound)
     splits = 296 / tiles;
     if (splits > total_kb / 2) splits = total_kb / 2;
     if (splits > 32) splits = 32;

@@ -233,6 +233,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
   return d;
 }
+// Same without swizzle (layout type 0): 8-row x 16-byte core matrices, `lbo` / `sbo` bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                             uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (sm_100)
+  return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
                                                              int b_mn_major) {

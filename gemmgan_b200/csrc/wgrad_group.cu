@@ -8,6 +8,10 @@
 // TMA pipeline as gemm.cu (both operands MN-major: the forward tensors are read in place, no transposes).
 // Problems whose K loop is much longer than the rest are split along K; the partial tiles of a split
 // problem are summed in split order by the last CTA to arrive (deterministic, no float atomics).
+// Bias gradients ride along: db[m] = sum_k dY[k, m] = (dY^T 1)[m]. For the first column tile of a problem with
+// a bias output the MMA thread issues one more N = 16 MMA per K step against a constant all-ones B tile into a
+// spare TMEM column block, and the epilogue reads it back as one value per row — the separate column-sum pass
+// (one more read of every dY, 1.2 ms of kernel time per cfg3 train() call) disappears.
 //
 // Replaces autograd's `grad_output.t().mm(input)` for every nn.Linear / in_proj / out_proj of
 // src/conditional_gan_cross_attention_with_film.py:108-123, 157-162 executed inside disc_loss.backward() /
@@ -35,10 +39,15 @@ constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int SLOT_BYTES = 4096;
 constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
 constexpr int STAGING_BYTES = EPI_WARPS * 2 * SLOT_BYTES;
-constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
+constexpr int ONES_OFFSET = STAGING_OFFSET + STAGING_BYTES;  // all-ones B operand of the bias-gradient MMAs
+constexpr int ONES_BYTES = 1024;
+constexpr int BAR_OFFSET = ONES_OFFSET + ONES_BYTES;
 constexpr int NUM_BARS = 2 * STAGES + 4;
 constexpr int SMEM_BYTES = BAR_OFFSET + NUM_BARS * 8 + 32 + 1024;
-constexpr int TMEM_COLS = 2 * BN;
+static_assert(SMEM_BYTES <= 232448, "grouped wgrad kernel exceeds 227 KB of shared memory");
+constexpr int BIAS_N = 16;                 // narrowest MMA for M = 128
+constexpr int BIAS_COL0 = 2 * BN;          // TMEM columns [256, 320): two 32-column bias accumulator stages
+constexpr int TMEM_COLS = 512;
 
 struct Problem {
   int M, N, K;
@@ -49,6 +58,8 @@ struct Problem {
   int64_t ld;
   float* partial;       // [splits][M][N] fp32 when splits > 1
   unsigned* counters;   // [tiles_m * tiles_n] arrival counters (zero between launches)
+  float* bias;          // [M] column sums of dY (bias gradient), or null
+  float* bias_partial;  // [splits][M] when splits > 1
 };
 
 struct Params {
@@ -112,6 +123,11 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
     tmem_alloc(tmem_holder, TMEM_COLS);
     tmem_relinquish();
   }
+  if (warp >= 2) {  // constant all-ones operand (bf16 1.0 = 0x3F80), read by the tensor core through the async proxy
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + ONES_OFFSET);
+    for (int i = threadIdx.x - 64; i < ONES_BYTES / 4; i += EPI_WARPS * 32) ones[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -147,6 +163,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
+      const uint32_t idesc_bias = make_idesc_bf16(BM, BIAS_N, 1, 0);  // A = dY tile (MN-major), B = ones (K-major)
+      // ones tile without swizzle: 8-row x 16-byte core matrices 256 bytes apart in either direction (all inside
+      // the 1 KB block, every element 1.0, so the exact walk is immaterial)
+      const uint64_t ones_desc = make_smem_desc_noswizzle(smem_u32(smem + ONES_OFFSET), 256, 256);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -156,6 +176,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        const bool with_bias = k.tn == 0 && P.p[k.pi].bias != nullptr;
+        const uint32_t d_bias = tmem_base + BIAS_COL0 + acc * 32;
         for (int kb = k.kb_begin; kb < k.kb_end; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after_sync();
@@ -166,6 +188,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
             const uint64_t ad = make_smem_desc(a_base + kk * 2048, ATOM_BYTES, 1024);
             const uint64_t bd = make_smem_desc(b_base + kk * 2048, ATOM_BYTES, 1024);
             tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > k.kb_begin || kk > 0) ? 1u : 0u);
+            if (with_bias) tc_mma_bf16(d_bias, ad, ones_desc, idesc_bias, (kb > k.kb_begin || kk > 0) ? 1u : 0u);
           }
           tc_commit(&empty[s]);
           if (++s == STAGES) {
@@ -197,6 +220,14 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
 #pragma unroll
       for (int c = 0; c < 2; ++c)
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + hsel * 64 + c * 32, v[c]);
+      const bool with_bias = k.tn == 0 && p.bias != nullptr && hsel == 0;  // four warps cover the tile's 128 rows
+      float bsum = 0.f;
+      if (with_bias) {
+        float vb[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BIAS_COL0 + acc * 32, vb);
+        tmem_ld_wait();
+        bsum = vb[0];  // the BIAS_N columns are identical: column 0 is sum_k dY[k, m]
+      }
       tmem_ld_wait();
       tc_fence_before_sync();
       __syncwarp();
@@ -223,6 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
             }
           }
         }
+        if (with_bias && m < p.M) __stcg(p.bias_partial + static_cast<int64_t>(k.z) * p.M + m, bsum);
         __threadfence();
         epi_bar();
         if (ew == 0 && lane == 0) {
@@ -235,6 +267,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
         }
         epi_bar();
         write_out = *last_flag != 0;
+        if (write_out && with_bias && m < p.M) {
+          bsum = 0.f;
+          for (int z = 0; z < p.splits; ++z) bsum += __ldcg(p.bias_partial + static_cast<int64_t>(z) * p.M + m);
+        }
         if (write_out) {
           // sum the partials in split order (fixed order => bit-reproducible)
 #pragma unroll
@@ -264,6 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
         epi_bar();  // last_flag is reused by the next tile
       }
       if (!write_out) continue;
+      if (with_bias && m < p.M) p.bias[m] = bsum;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int n0 = k.tn * BN + hsel * 64 + c * 32;
@@ -345,8 +382,9 @@ int encode2d(CUtensorMap* map, const void* ptr, bool f32, int64_t inner, int64_t
 // Workspace layout: [GROUP_COUNTER_BYTES of arrival counters | partial tiles]. Only the counter region has to
 // be zero when a launch starts, and every launch leaves it zero.
 int64_t wgrad_group_workspace_bytes(int64_t max_output_elems) {
+  // partial tiles + (generous) partial bias vectors: a bias has at most as many elements as its matrix has rows
   return GROUP_COUNTER_BYTES + static_cast<int64_t>(WGRAD_GROUP_MAX_SPLITS) * max_output_elems * 4 +
-         256LL * WGRAD_GROUP_MAX;
+         static_cast<int64_t>(WGRAD_GROUP_MAX_SPLITS) * max_output_elems * 4 / 8 + 512LL * WGRAD_GROUP_MAX;
 }
 
 // The first GROUP_COUNTER_BYTES of `workspace` must be zero-initialised once.
@@ -402,6 +440,9 @@ int k_wgrad_group(const WgradItem* items, int n, void* workspace, int64_t worksp
     p.tma_out = ((reinterpret_cast<uintptr_t>(it.out) & 15) == 0 && it.ld % 4 == 0) ? 1 : 0;
     p.partial = reinterpret_cast<float*>(ws + ws_off);
     if (splits > 1) ws_off = round_up64(ws_off + static_cast<int64_t>(splits) * it.M * it.N * 4, 256);
+    p.bias = it.bias;
+    p.bias_partial = reinterpret_cast<float*>(ws + ws_off);
+    if (it.bias && splits > 1) ws_off = round_up64(ws_off + static_cast<int64_t>(splits) * it.M * 4, 256);
     p.counters = reinterpret_cast<unsigned*>(ws + ctr_off);
     ctr_off += static_cast<int64_t>(p.tiles_m) * p.tiles_n * 4;
     GG_REQUIRE(ws_off <= workspace_bytes && ctr_off <= GROUP_COUNTER_BYTES,

@@ -73,20 +73,23 @@ def gemm(
 
 
 def wgrad_group(problems, workspace=None):
-    """problems: list of (dy [K, M] bf16, x [K, N] bf16, out [M, N] fp32). One launch (gg_wgrad_group)."""
+    """problems: list of (dy [K, M] bf16, x [K, N] bf16, out [M, N] fp32[, bias [M] fp32]). One launch (gg_wgrad_group)."""
     from . import _abi_decl as A
 
     L = _lib.lib()
     n = len(problems)
     items = (A.WgradItem * n)()
     total = 0
-    for i, (dy, x, out) in enumerate(problems):
+    for i, prob in enumerate(problems):
+        dy, x, out = prob[:3]
+        bias = prob[3] if len(prob) > 3 else None
         assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and out.dtype == torch.float32
         assert dy.shape[0] == x.shape[0] and out.shape == (dy.shape[1], x.shape[1])
         it = items[i]
         it.dy, it.ld_dy, it.x, it.ld_x = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0)
         it.M, it.N, it.K = dy.shape[1], x.shape[1], dy.shape[0]
         it.out, it.ld = out.data_ptr(), out.stride(0)
+        it.bias = None if bias is None else bias.data_ptr()
         total += it.M * it.N
     if workspace is None:
         workspace = torch.zeros(L.gg_wgrad_group_workspace_bytes(total), device=problems[0][0].device, dtype=torch.uint8)

@@ -104,6 +104,7 @@ class TrainerBase:
         self.use_cuda_graphs = os.environ.get("GEMMGAN_CUDA_GRAPHS", "1") != "0"
         self.unique_graphs = False
         self._graph_seq = 0
+        self._replay_events = []
         self._engines = {}
         self._flat_gen = self._flat_disc = None
         self._pinned = None
@@ -240,7 +241,14 @@ class TrainerBase:
             n_kernels = eng.lib.gg_launch_count(0) - n0
             eng.lib.gg_launch_count_add(-n_kernels)     # capture enqueues nothing
             g = eng.graphs[key] = (g, n_kernels)
-        g[0].replay()
+        if self.unique_graphs:  # diagnostics: device time of each replay (bench.py)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g[0].replay()
+            e1.record()
+            self._replay_events.append((e0, e1))
+        else:
+            g[0].replay()
         eng.lib.gg_launch_count_add(g[1])
 
     def _buckets(self, flat: FlatNet):

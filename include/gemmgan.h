@@ -297,6 +297,8 @@ typedef struct gg_wgrad_item {
   const void* x; int64_t ld_x;
   int32_t M, N, K;
   float* out; int64_t ld;
+  float* bias; /* optional [M] fp32: the bias gradient sum_k dY[k, m] (autograd's grad_output.sum(0)), formed by one
+                  extra N = 16 tensor-core MMA per K step against an all-ones operand; NULL = not wanted */
 } gg_wgrad_item;
 int64_t gg_wgrad_group_workspace_bytes(int64_t sum_output_elems);
 int gg_wgrad_group(const gg_wgrad_item* items, int n, void* workspace, int64_t workspace_bytes, void* stream);

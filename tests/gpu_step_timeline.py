@@ -1,0 +1,37 @@
+"""In-situ kernel timeline of one train() call (diagnostics; not a pytest file): torch.profiler (CUPTI) records the
+start / duration / stream of every kernel of the replayed CUDA graphs.
+
+    python tests/gpu_step_timeline.py [out.json] [workload]
+"""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+import bench  # noqa: E402
+
+out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/step_timeline.json"
+wl = sys.argv[2] if len(sys.argv) > 2 else "cfg3"
+w = dict(bench.WORKLOADS[wl])
+t = bench.build_trainer(w, "rms_prop")
+dev = torch.device("cuda", 0)
+batch = bench.make_batch(w, seed=42, device=dev)
+for _ in range(5):
+    t.train(*batch)
+torch.cuda.synchronize()
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    t.train(*batch)
+    torch.cuda.synchronize()
+ev = []
+for e in prof.events():
+    if e.device_type.name == "CUDA" and e.device_time_total > 0:
+        ev.append(dict(name=e.name[:80], start_us=e.time_range.start, dur_us=e.device_time_total))
+ev.sort(key=lambda x: x["start_us"])
+t0 = ev[0]["start_us"] if ev else 0
+for e in ev:
+    e["start_us"] -= t0
+json.dump(ev, open(out, "w"))
+print("kernels", len(ev), "span_us", (ev[-1]["start_us"] + ev[-1]["dur_us"]) if ev else 0)

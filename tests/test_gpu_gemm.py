@@ -172,28 +172,40 @@ def test_wgrad_group_matches_reference_and_is_deterministic():
         (18432, 256, 512, 512), (18432, 512, 256, 256), (18432, 768, 256, 256), (9216, 256, 256, 256),
         (1024, 2048, 768, 768), (2048, 256, 256, 19124), (1000, 200, 72, 75), (64, 128, 128, 128), (300, 40, 1000, 1000),
     ]
-    probs, refs = [], []
-    for K, M, N, ld in shapes:
+    probs, refs, brefs = [], [], []
+    for i, (K, M, N, ld) in enumerate(shapes):
         dy, x = _mk(K, M, g, scale=0.5), _mk(K, N, g, scale=0.5)
         buf = torch.full((M, ld), 3.0, device="cuda", dtype=torch.float32)
-        probs.append((dy, x, buf[:, :N]))
+        # every other problem also asks for its bias gradient (column sums of dY, fused as a ones-column MMA)
+        bias = torch.full((M + 3,), 9.0, device="cuda", dtype=torch.float32) if i % 2 == 0 else None
+        probs.append((dy, x, buf[:, :N]) + ((bias[:M],) if bias is not None else ()))
         refs.append(dy.float().t() @ x.float())
+        brefs.append(dy.double().sum(0))
     ws = ops.wgrad_group(probs)
     torch.cuda.synchronize()
     first = [p[2].clone() for p in probs]
-    for (dy, x, out), ref in zip(probs, refs):
+    first_b = [p[3].clone() if len(p) > 3 else None for p in probs]
+    for p, ref, bref in zip(probs, refs, brefs):
+        dy, x, out = p[:3]
         assert (out - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-3, (dy.shape, x.shape)
         buf = out._base if out._base is not None else out
         if buf.shape[1] > out.shape[1]:
             assert (buf[:, out.shape[1]:] == 3.0).all()
+        if len(p) > 3:
+            assert (p[3].double() - bref).abs().max().item() <= 1e-5 * dy.shape[0] ** 0.5 * 4 + 1e-3, dy.shape
+            assert (p[3]._base[dy.shape[1]:] == 9.0).all()      # nothing written behind the M bias elements
     # replay with the same workspace (counters must have been left at zero) -> bit-identical results
     for _ in range(3):
         for p in probs:
             p[2].fill_(-1.0)
+            if len(p) > 3:
+                p[3].fill_(-1.0)
         ops.wgrad_group(probs, workspace=ws)
         torch.cuda.synchronize()
-        for p, f in zip(probs, first):
+        for p, f, fb in zip(probs, first, first_b):
             assert torch.equal(p[2], f)
+            if fb is not None:
+                assert torch.equal(p[3], fb)
 
 
 def test_colsum_group_matches_reference_and_is_deterministic():
