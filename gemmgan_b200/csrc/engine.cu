@@ -172,6 +172,7 @@ struct gg_engine {
     dst = L(dst);
     src = L(src);
     if (dst == src) return GG_OK;
+    if (src != 0 && !forked[src]) return GG_OK;  // nothing enqueued on `src` in this entry point
     cudaEvent_t ev = evs[ev_next];
     ev_next = (ev_next + 1) % NEVENTS;
     GG_CUDA_CHECK(cudaEventRecord(ev, cur[src]));
@@ -257,6 +258,7 @@ struct gg_engine {
     }
     if (!wq.empty()) {
       GG_TRY(fork(1));
+      GG_TRY(wait_lane(1, 2));  // operands produced on lane 2 (text-side gradients)
       GG_TRY(k_wgrad_group(wq.data(), static_cast<int>(wq.size()), wg_ws, wg_ws_bytes, S(1)));
       wq.clear();
     }
@@ -270,6 +272,8 @@ struct gg_engine {
   std::vector<WgradItem> wq;
   std::vector<ColsumItem> bq;
   bool group_grads = true;
+  // text-side work on lane 2: measured on cfg3 (ms / train()): fwd+bwd 7.89, bwd only 7.96, fwd only 7.75, none 7.82
+  bool text_lane_fwd = true, text_lane_bwd = false;  // GEMMGAN_TEXT_LANE = <fwd><bwd> digits overrides
   bool fuse_bias = true;  // GEMMGAN_FUSE_BIAS=0: keep every bias gradient in the grouped column-sum kernel
   // one workspace per flush in flight: flushes of one entry point run back to back on their lane, so
   // they rotate through GROUP_WS_SLOTS regions
@@ -539,9 +543,20 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
     GG_TRY(k_film_apply(e.patches, t.gb, t.mod, B, P, Dp, st));
     pin = t.mod;
   }
-  if (e.paper)
-    GG_TRY(e.linear(ln, B * T, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W),
+  // text side of the paper model (:140, :149-152): token projection, the patch2text query and the text2patch
+  // keys / values depend on the text only — they run on lane 2 next to the patch encoder of lane `ln`
+  const int tl = e.text_lane_fwd ? 2 : ln;
+  if (e.paper) {
+    const Op Wp = e.W(net, GG_P_P2T_IN_W), Wt = e.W(net, GG_P_T2P_IN_W);
+    const float* bp = e.P(net, GG_P_P2T_IN_B);
+    const float* bt = e.P(net, GG_P_T2P_IN_B);
+    GG_TRY(e.wait_lane(tl, ln));
+    GG_TRY(e.linear(tl, B * T, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W),
                     Epi().bias(e.P(net, GG_P_TEXT_B)).obf(t.te, E)));
+    GG_TRY(e.linear(tl, B, E, E, Op{t.te, static_cast<int64_t>(T) * E}, Wp, Epi().bias(bp).obf(t.qp, E)));
+    GG_TRY(e.linear(tl, B * T, 2 * E, E, Op{t.te, E}, Op{Wt.p + static_cast<int64_t>(E) * Wt.ld, Wt.ld},
+                    Epi().bias(bt ? bt + E : nullptr).obf(t.kvt, 2 * E)));
+  }
   // patch projection written straight behind the CLS row of replica 0 (:139-142)
   GG_TRY(e.linear(ln, B * P, E, Dp, Op{pin, Dp}, e.W(net, GG_P_PATCH_W),
                   Epi().bias(e.P(net, GG_P_PATCH_B)).obf(t.X[0], E).rowmap(P, S, 1)));
@@ -577,8 +592,8 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
   const Op Wp = e.W(net, GG_P_P2T_IN_W), Wt = e.W(net, GG_P_T2P_IN_W);
   const float* bp = e.P(net, GG_P_P2T_IN_B);
   const float* bt = e.P(net, GG_P_T2P_IN_B);
-  // patch2text: query = encoded text CLS, keys/values = encoder output (:149-150)
-  GG_TRY(e.linear(ln, B, E, E, Op{t.te, static_cast<int64_t>(T) * E}, Wp, Epi().bias(bp).obf(t.qp, E)));
+  // patch2text: query = encoded text CLS (lane 2, above), keys/values = encoder output (:149-150)
+  GG_TRY(e.wait_lane(ln, tl));
   GG_TRY(e.linear(ln, rows, 2 * E, E, Op{Xf, E}, Op{Wp.p + static_cast<int64_t>(E) * Wp.ld, Wp.ld},
                   Epi().bias(bp ? bp + E : nullptr).obf(t.kvp, 2 * E)));
   AttnArgs a;
@@ -593,8 +608,6 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
                   Epi().bias(e.P(net, GG_P_P2T_OUT_B)).obf(t.pv, E)));
   // text2patch: query = that vector, keys/values = encoded text tokens (:151-152)
   GG_TRY(e.linear(ln, R * B, E, E, Op{t.pv, E}, Wt, Epi().bias(bt).obf(t.qt, E)));
-  GG_TRY(e.linear(ln, B * T, 2 * E, E, Op{t.te, E}, Op{Wt.p + static_cast<int64_t>(E) * Wt.ld, Wt.ld},
-                  Epi().bias(bt ? bt + E : nullptr).obf(t.kvt, 2 * E)));
   memset(&a, 0, sizeof(a));
   a.q = t.qt; a.ldq = E; a.q_mod = R * B;
   a.k = t.kvt; a.v = t.kvt + E; a.ldkv = 2 * E; a.kv_mod = B;
@@ -653,15 +666,18 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     GG_TRY(e.wgrad(E, E, n, Op{g.dqt, E}, Op{t.pv, E}, gWt, E));
     GG_TRY(e.bgrad(g.dqt, E, n, E, gbt));
     GG_TRY(e.dgrad(0, n, E, E, Op{g.dqt, E}, Wt, Epi().res(dc, E).obf(g.dp, E)));
-    // kvt = te Wkv_t^T + bkv_t (shared by the replicas)
+    // kvt = te Wkv_t^T + bkv_t (shared by the replicas). Everything that only flows back into the text encoder
+    // (dkvt -> dte, dqp -> dte0) leaves the dependent chain: lane 2
     const bf16* dkvt = g.dkvt;
+    const int bl = e.text_lane_bwd ? 2 : 0;
+    GG_TRY(e.wait_lane(bl, 0));
     if (Rg > 1) {
-      GG_TRY(k_sum_replicas(g.dkvt, g.dkvt_sum, Rg, static_cast<int64_t>(B) * T * 2 * E, st));
+      GG_TRY(k_sum_replicas(g.dkvt, g.dkvt_sum, Rg, static_cast<int64_t>(B) * T * 2 * E, e.S(bl)));
       dkvt = g.dkvt_sum;
     }
     GG_TRY(e.wgrad(2 * E, E, B * T, Op{dkvt, 2 * E}, Op{t.te, E}, gWt + static_cast<int64_t>(E) * E, E));
     GG_TRY(e.bgrad(dkvt, 2 * E, B * T, 2 * E, gbt ? gbt + E : nullptr));
-    GG_TRY(e.dgrad(0, B * T, E, 2 * E, Op{dkvt, 2 * E}, Wt_kv, Epi().obf(g.dte, E)));
+    GG_TRY(e.dgrad(bl, B * T, E, 2 * E, Op{dkvt, 2 * E}, Wt_kv, Epi().obf(g.dte, E)));
     // pv = ap Wo_p^T + bo_p
     GG_TRY(e.wgrad(E, E, n, Op{g.dp, E}, Op{t.ap, E}, e.Gr(net, GG_P_P2T_OUT_W), E));
     GG_TRY(e.bgrad(g.dp, E, n, E, e.Gr(net, GG_P_P2T_OUT_B)));
@@ -677,14 +693,15 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     GG_TRY(k_attention_bwd(a, st));
     // qp = te[:,0] Wq_p^T + bq_p (shared by the replicas)
     const bf16* dqp = g.dqp;
+    GG_TRY(e.wait_lane(bl, 0));
     if (Rg > 1) {
-      GG_TRY(k_sum_replicas(g.dqp, g.dqp_sum, Rg, static_cast<int64_t>(B) * E, st));
+      GG_TRY(k_sum_replicas(g.dqp, g.dqp_sum, Rg, static_cast<int64_t>(B) * E, e.S(bl)));
       dqp = g.dqp_sum;
     }
     GG_TRY(e.wgrad(E, E, B, Op{dqp, E}, Op{t.te, static_cast<int64_t>(T) * E}, gWp, E));
     GG_TRY(e.bgrad(dqp, E, B, E, gbp));
-    GG_TRY(e.dgrad(0, B, E, E, Op{dqp, E}, Wp, Epi().obf(g.dte0, E)));
-    GG_TRY(k_scatter_add_rows(g.dte, g.dte0, B, T, E, st));
+    GG_TRY(e.dgrad(bl, B, E, E, Op{dqp, E}, Wp, Epi().obf(g.dte0, E)));
+    GG_TRY(k_scatter_add_rows(g.dte, g.dte0, B, T, E, e.S(bl)));
     // kvp = Xf Wkv_p^T + bkv_p
     GG_TRY(e.wgrad(2 * E, E, rows, Op{g.dkvp, 2 * E}, Op{Xf, E}, gWp + static_cast<int64_t>(E) * E, E));
     GG_TRY(e.bgrad(g.dkvp, 2 * E, rows, 2 * E, gbp ? gbp + E : nullptr));
@@ -876,6 +893,10 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
     e->multi_lane = !(ml && ml[0] == '1' && ml[1] == 0);
     const char* gr = getenv("GEMMGAN_GROUP_GRADS");
     e->group_grads = !(gr && gr[0] == '0');
+    if (const char* tlv = getenv("GEMMGAN_TEXT_LANE")) {
+      e->text_lane_fwd = tlv[0] == '1';
+      e->text_lane_bwd = tlv[0] && tlv[1] == '1';
+    }
     const char* fb = getenv("GEMMGAN_FUSE_BIAS");
     e->fuse_bias = !(fb && fb[0] == '0');
   }
