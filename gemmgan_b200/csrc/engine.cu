@@ -274,6 +274,7 @@ struct gg_engine {
   bool group_grads = true;
   // text-side work on lane 2: measured on cfg3 (ms / train()): fwd+bwd 7.89, bwd only 7.96, fwd only 7.75, none 7.82
   bool text_lane_fwd = true, text_lane_bwd = false;  // GEMMGAN_TEXT_LANE = <fwd><bwd> digits overrides
+  bool split_tail_flush = false;  // measured: splitting the last flush costs 0.28 ms / train() (the grouped kernel occupies every SM)
   bool fuse_bias = true;  // GEMMGAN_FUSE_BIAS=0: keep every bias gradient in the grouped column-sum kernel
   // one workspace per flush in flight: flushes of one entry point run back to back on their lane, so
   // they rotate through GROUP_WS_SLOTS regions
@@ -761,7 +762,8 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
   GG_TRY(k_unassemble_tokens(g.ga, g.dpe, nullptr, Rg, B, S, E, st));
   GG_TRY(e.wgrad(E, Dp, B * P, Op{g.dpe, E}, Op{e.film ? t.mod : e.patches, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
   GG_TRY(e.bgrad(g.dpe, E, B * P, E, e.Gr(net, GG_P_PATCH_B)));
-  if (e.film) {  // without FiLM the patch embeddings are a plain input: nothing upstream needs a gradient
+  if (e.film) {
+    if (e.split_tail_flush) GG_TRY(e.flush_grads());  // patch-encoder gradients overlap the FiLM backward  // without FiLM the patch embeddings are a plain input: nothing upstream needs a gradient
     GG_TRY(e.dgrad(0, B * P, Dp, E, Op{g.dpe, E}, e.W(net, GG_P_PATCH_W), Epi().obf(g.dmod, Dp)));
     GG_TRY(k_film_bwd(g.dmod, e.patches, t.gb, g.dgb, B, P, Dp, st));
     GG_TRY(e.wgrad(2 * Dp, Dt, B, Op{g.dgb, 2 * Dp}, Op{e.text, static_cast<int64_t>(T) * Dt},
@@ -897,6 +899,7 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
       e->text_lane_fwd = tlv[0] == '1';
       e->text_lane_bwd = tlv[0] && tlv[1] == '1';
     }
+    if (const char* sf = getenv("GEMMGAN_SPLIT_TAIL_FLUSH")) e->split_tail_flush = sf[0] != '0';
     const char* fb = getenv("GEMMGAN_FUSE_BIAS");
     e->fuse_bias = !(fb && fb[0] == '0');
   }
@@ -1125,8 +1128,9 @@ extern "C" int gg_engine_optim_step(gg_engine* e, int net, float lr, void* strea
     coef = statp + 1;
   }
   GG_TRY(k_optim_step(e->cfg.optimizer, nb.params, nb.grads, nb.exp_avg, nb.exp_avg_sq, nb.n_used, lr, coef,
-                      nb.step_count, st));
-  return gg_engine_refresh_shadows(e, net, stream);
+                      nb.step_count, st, /*bump_step=*/false));
+  NetShadow& sh = e->sh[net];  // bf16 shadows of the new weights + the step-counter increment, one launch
+  return k_refresh_shadows(nb.params, sh.base, sh.segs_dev, static_cast<int>(sh.segs.size()), 0, st, nb.step_count);
 }
 
 extern "C" int gg_engine_generate(gg_engine* e, const float* z, float* out_f32, int training, void* stream) {

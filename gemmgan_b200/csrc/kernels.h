@@ -114,7 +114,7 @@ int k_grad_norm_clip(const float* g, int64_t n, float max_norm, float* norm_out,
                      cudaStream_t st);
 // One fused pass over the flat buffers: g *= coef (if coef_ptr), optimizer update, step counter in state.
 int k_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, float lr, const float* coef_ptr,
-                 float* step_count, cudaStream_t st);
+                 float* step_count, cudaStream_t st, bool bump_step = true);
 struct ShadowSeg {            // fp32 parameter sub-matrix -> bf16 shadow (padded pitch)
   int64_t p_off;              // offset of the parameter tensor in the flat buffer
   int32_t rows, cols;         // parameter shape [rows, cols]
@@ -122,7 +122,8 @@ struct ShadowSeg {            // fp32 parameter sub-matrix -> bf16 shadow (padde
   int64_t s_off;              // offset (elements) in the shadow buffer
   int64_t s_ld;
 };
+// bump_step (optional): step counter incremented by this launch (the engine's optimizer step folds it in here)
 int k_refresh_shadows(const float* p, bf16* shadow, const ShadowSeg* segs_dev, int nseg, int max_rows,
-                      cudaStream_t st);
+                      cudaStream_t st, float* bump_step = nullptr);
 
 }  // namespace gg

@@ -128,7 +128,7 @@ __global__ void bump_step_kernel(float* step_count) {
   pdl_entry(); step_count[0] += 1.f; }
 
 int k_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, float lr, const float* coef_ptr,
-                 float* step_count, cudaStream_t st) {
+                 float* step_count, cudaStream_t st, bool bump_step) {
   GG_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (!m || (reinterpret_cast<uintptr_t>(m) & 15) == 0),
              "optimizer buffers must be 16-byte aligned");
@@ -144,15 +144,19 @@ int k_optim_step(int kind, float* p, float* g, float* m, float* v, int64_t n, fl
     return GG_ERR_ARG;
   }
   GG_LAUNCH_CHECK();
-  launch_k(bump_step_kernel, 1, 1, 0, st, step_count);
-  GG_LAUNCH_CHECK();
+  if (bump_step) {  // the engine folds the increment into its shadow refresh instead (one launch less per step)
+    launch_k(bump_step_kernel, 1, 1, 0, st, step_count);
+    GG_LAUNCH_CHECK();
+  }
   return GG_OK;
 }
 
 // One (segment, 4-column run) per thread iteration: float4 load, 8-byte bf16x4 store, 32-bit index math.
 __global__ void __launch_bounds__(256)
-    refresh_shadows_kernel(const float* __restrict__ p, bf16* __restrict__ shadow, const ShadowSeg* __restrict__ segs) {
+    refresh_shadows_kernel(const float* __restrict__ p, bf16* __restrict__ shadow, const ShadowSeg* __restrict__ segs,
+                           float* bump) {
   pdl_entry();
+  if (bump && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) bump[0] += 1.f;  // optimizer step counter
   const ShadowSeg s = segs[blockIdx.y];
   const float* src = p + s.p_off + s.col0;
   bf16* dst = shadow + s.s_off;
@@ -181,10 +185,16 @@ __global__ void __launch_bounds__(256)
   }
 }
 int k_refresh_shadows(const float* p, bf16* shadow, const ShadowSeg* segs_dev, int nseg, int /*max_rows*/,
-                      cudaStream_t st) {
-  if (nseg <= 0) return GG_OK;
+                      cudaStream_t st, float* bump_step) {
+  if (nseg <= 0) {
+    if (bump_step) {
+      launch_k(bump_step_kernel, 1, 1, 0, st, bump_step);
+      GG_LAUNCH_CHECK();
+    }
+    return GG_OK;
+  }
   dim3 grid(148, nseg);
-  launch_k(refresh_shadows_kernel, grid, 256, 0, st, p, shadow, segs_dev);
+  launch_k(refresh_shadows_kernel, grid, 256, 0, st, p, shadow, segs_dev, bump_step);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

@@ -21,6 +21,8 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -453,7 +455,11 @@ int k_wgrad_group(const WgradItem* items, int n, void* workspace, int64_t worksp
     else P.mapO[oi] = P.mapA[oi];
   }
   P.total_work = work;
-  const unsigned grid = static_cast<unsigned>(work < num_sms ? work : num_sms);
+  // The kernel runs on a side lane next to the dependent chain; GEMMGAN_WGRAD_SMS caps how many SMs it takes.
+  static int sm_cap = [] { const char* v = getenv("GEMMGAN_WGRAD_SMS"); return v ? atoi(v) : 0; }();
+  int slots = num_sms;
+  if (sm_cap > 0 && sm_cap < slots) slots = sm_cap;
+  const unsigned grid = static_cast<unsigned>(work < slots ? work : slots);
   launch_k(wgrad_group_kernel, grid, THREADS, SMEM_BYTES, st, P);
   GG_LAUNCH_CHECK();
   return GG_OK;

@@ -144,7 +144,15 @@ class Engine:
         # fixed-address noise inputs so that a captured CUDA graph of the step can be replayed
         self.z_in = torch.empty(B, L, device=self.device, dtype=torch.float32)
         self.alpha_in = torch.empty(B, 1, device=self.device, dtype=torch.float32)
+        self.z_all = self.alpha_all = None
         self.graphs, self.warmed = {}, set()
+
+    def ensure_noise(self, n_critic: int) -> None:
+        """Per-step noise buffers of one train() call: z_all [n_critic + 1, B, L], alpha_all [n_critic, B, 1]."""
+        if self.z_all is None or self.z_all.shape[0] != n_critic + 1:
+            self.z_all = torch.empty(n_critic + 1, self.B, self.L, device=self.device, dtype=torch.float32)
+            self.alpha_all = torch.empty(n_critic, self.B, 1, device=self.device, dtype=torch.float32)
+            self.graphs.clear()
 
     def __del__(self):
         try:

@@ -102,6 +102,7 @@ class TrainerBase:
         self.dp_graph_collectives = os.environ.get("GEMMGAN_DP_GRAPH", "1") != "0"
         self.dp_global_noise = False   # draw z/alpha for the GLOBAL batch and slice (N-rank == 1-rank parity)
         self.use_cuda_graphs = os.environ.get("GEMMGAN_CUDA_GRAPHS", "1") != "0"
+        self.noise_upfront = os.environ.get("GEMMGAN_NOISE_UPFRONT", "1") != "0"
         self.unique_graphs = False
         self._graph_seq = 0
         self._replay_events = []
@@ -230,8 +231,9 @@ class TrainerBase:
             key = key + (self._graph_seq,)
         g = eng.graphs.get(key)
         if g is None:
-            if key[0] not in eng.warmed:
-                eng.warmed.add(key[0])
+            kind = key[0][:1]  # 'd' / 'g': the library's one-time lazy initialisation is per step kind
+            if kind not in eng.warmed:
+                eng.warmed.add(kind)
                 body()
                 return
             g = torch.cuda.CUDAGraph()
@@ -301,17 +303,23 @@ class TrainerBase:
         gb.wait()
         self._replay(eng, (tag + "_optim", lr), lambda: eng.optim_step(net, lr))
 
-    def _train_disc_staged(self, eng: Engine, z, alpha=None):
-        """train_disc (:376-423) on the batch already staged in the engine."""
+    def _train_disc_staged(self, eng: Engine, z, alpha=None, slot=None, snapshot=True):
+        """train_disc (:376-423) on the batch already staged in the engine. slot: index of pre-staged noise
+        (eng.z_all / eng.alpha_all, filled by _train_staged) instead of z / alpha."""
         self.disc.train()
         self._flat_disc.reattach_grads()
-        eng.z_in.copy_(z, non_blocking=True)
-        eng.alpha_in.copy_(self._alpha(eng.B) if alpha is None else alpha.reshape(eng.B, 1), non_blocking=True)
-        self._step(eng, "d", A.NET_DISC, self._flat_disc, self._lr(self.optimizer_disc),
-                   lambda ph: eng.disc_grads(eng.z_in, eng.alpha_in, training=True, phase=ph))
-        self._snapshot(eng, "d")
+        if slot is None:
+            eng.z_in.copy_(z, non_blocking=True)
+            eng.alpha_in.copy_(self._alpha(eng.B) if alpha is None else alpha.reshape(eng.B, 1), non_blocking=True)
+            zt, at, tag = eng.z_in, eng.alpha_in, "d"
+        else:
+            zt, at, tag = eng.z_all[slot], eng.alpha_all[slot], f"d{slot}"
+        self._step(eng, tag, A.NET_DISC, self._flat_disc, self._lr(self.optimizer_disc),
+                   lambda ph: eng.disc_grads(zt, at, training=True, phase=ph))
+        if snapshot:
+            self._snapshot(eng, "d")
 
-    def _train_gen_staged(self, eng: Engine, z):
+    def _train_gen_staged(self, eng: Engine, z, slot=None):
         """train_gen (:425-461) on the batch already staged in the engine."""
         self.gen.train()
         self._flat_gen.reattach_grads()
@@ -319,17 +327,44 @@ class TrainerBase:
             w.requires_grad = False
         for w in self.gen.parameters():
             w.requires_grad = True
-        eng.z_in.copy_(z, non_blocking=True)
-        self._step(eng, "g", A.NET_GEN, self._flat_gen, self._lr(self.optimizer_gen),
-                   lambda ph: eng.gen_grads(eng.z_in, training=True, phase=ph))
+        if slot is None:
+            eng.z_in.copy_(z, non_blocking=True)
+            zt, tag = eng.z_in, "g"
+        else:
+            zt, tag = eng.z_all[slot], f"g{slot}"
+        self._step(eng, tag, A.NET_GEN, self._flat_gen, self._lr(self.optimizer_gen),
+                   lambda ph: eng.gen_grads(zt, training=True, phase=ph))
         self._snapshot(eng, "g")
 
     def _train_staged(self, eng: Engine, zs=None, alphas=None):
-        for i in range(self.n_critic):
-            z = zs[i] if zs is not None else self._normal(eng.B)
-            self._train_disc_staged(eng, z, None if alphas is None else alphas[i])
-        z = zs[self.n_critic] if zs is not None else self._normal(eng.B)
-        self._train_gen_staged(eng, z)
+        """train() (:463-477): n_critic critic steps + one generator step. The noise of all steps is drawn up
+        front, in the reference's order (z, alpha, z, alpha, ..., z), straight into per-step buffers the captured
+        step graphs read — no RNG / copy kernels sit between the graph replays."""
+        n, B = self.n_critic, eng.B
+        if not self.noise_upfront:
+            for i in range(n):
+                z = zs[i] if zs is not None else self._normal(B)
+                self._train_disc_staged(eng, z, None if alphas is None else alphas[i])
+            self._train_gen_staged(eng, zs[n] if zs is not None else self._normal(B))
+            return
+        eng.ensure_noise(n)
+        for i in range(n + 1):
+            if zs is not None:
+                eng.z_all[i].copy_(zs[i], non_blocking=True)
+            elif _dist() is not None and self.dp_global_noise:
+                eng.z_all[i].copy_(self._normal(B))
+            else:
+                torch.normal(0, 1, size=(B, self.latent_dims), out=eng.z_all[i])
+            if i < n:
+                if alphas is not None:
+                    eng.alpha_all[i].copy_(alphas[i].reshape(B, 1), non_blocking=True)
+                elif _dist() is not None and self.dp_global_noise:
+                    eng.alpha_all[i].copy_(self._alpha(B))
+                else:
+                    torch.rand(B, 1, out=eng.alpha_all[i])
+        for i in range(n):
+            self._train_disc_staged(eng, None, slot=i, snapshot=(i == n - 1))
+        self._train_gen_staged(eng, None, slot=n)
 
     def set_requires_grad(self, nets, requires_grad=False):
         if not isinstance(nets, list):

@@ -25,10 +25,15 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     t.train(*batch)
     torch.cuda.synchronize()
+import os  # noqa: E402
+import tempfile  # noqa: E402
+
+tmp = os.path.join(tempfile.mkdtemp(), "trace.json")
+prof.export_chrome_trace(tmp)
 ev = []
-for e in prof.events():
-    if e.device_type.name == "CUDA" and e.device_time_total > 0:
-        ev.append(dict(name=e.name[:80], start_us=e.time_range.start, dur_us=e.device_time_total))
+for e in json.load(open(tmp))["traceEvents"]:
+    if e.get("cat") == "kernel":
+        ev.append(dict(name=e["name"][:80], start_us=e["ts"], dur_us=e["dur"], stream=e.get("args", {}).get("stream")))
 ev.sort(key=lambda x: x["start_us"])
 t0 = ev[0]["start_us"] if ev else 0
 for e in ev:
