@@ -631,4 +631,28 @@ int k_bump_rng(uint64_t* rng, cudaStream_t st) {
   return GG_OK;
 }
 
+__global__ void __launch_bounds__(256)
+    masked_mean_rows_kernel(const float* __restrict__ x, const uint8_t* __restrict__ pad, float* __restrict__ out,
+                            int P, int D) {
+  pdl_entry();
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const float* xb = x + static_cast<int64_t>(b) * P * D + d;
+  float acc = 0.f;
+  int cnt = 0;
+  for (int p = 0; p < P; ++p) {
+    if (pad && pad[static_cast<int64_t>(b) * P + p]) continue;
+    acc += xb[static_cast<int64_t>(p) * D];
+    ++cnt;
+  }
+  out[static_cast<int64_t>(b) * D + d] = acc / static_cast<float>(cnt);  // cnt = 0 -> inf/nan, as in the reference
+}
+int k_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>((D + 255) / 256), static_cast<unsigned>(B));
+  launch_k(masked_mean_rows_kernel, grid, 256, 0, st, x, pad, out, P, D);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 }  // namespace gg

@@ -116,6 +116,7 @@ struct gg_engine {
   gg_net_buffers nets[2];
   NetShadow sh[2];
   int S_ = 1, Gp = 0, F = 0, hd = 0;
+  bool concat = false;  // conditional_gan_concat.py: the conditioning is one Linear of the staged text / mean-patch vector
   bool cond = false, paper = false, film = false;  // paper: cross-attention tail; film: FiLM modulation of the patches
   // staged inputs
   bf16 *xfr, *patches, *text, *zbf, *xin;
@@ -392,7 +393,14 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
   e.opt_step[1] = ar.take<float>(4);
   e.normbuf = ar.take<float>(8);
   e.rng = ar.take<uint64_t>(2);
-  if (e.cond) {
+  if (e.concat) {
+    e.text = ar.take<bf16>(B * T * c.Dt);
+    for (int n = 0; n < 2; ++n) {
+      e.tw[n].Rmax = 1;
+      e.tw[n].c = ar.take<bf16>(B * E);
+    }
+    e.gs.dc = ar.take<bf16>(2 * B * E);
+  } else if (e.cond) {
     e.patches = ar.take<bf16>(B * P * c.Dp);
     e.text = ar.take<bf16>(B * T * c.Dt);
     e.mask_s = ar.take<uint8_t>(B * S);
@@ -499,7 +507,7 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
 }
 
 static int validate_cfg(const gg_model_cfg& c) {
-  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_CROSS, "unknown variant %d", c.variant);
+  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_CONCAT, "unknown variant %d", c.variant);
   GG_REQUIRE(c.B > 0 && c.G > 0 && c.L > 0 && c.H > 0, "bad sizes B=%d G=%d L=%d H=%d", c.B, c.G, c.L, c.H);
   GG_REQUIRE(c.L % 8 == 0 && c.H % 8 == 0, "latent and hidden widths must be multiples of 8");
   if (c.variant != GG_VARIANT_VANILLA) {
@@ -519,6 +527,7 @@ static void derive(gg_engine& e) {
   e.cond = c.variant != GG_VARIANT_VANILLA;
   e.paper = c.variant == GG_VARIANT_PAPER || c.variant == GG_VARIANT_CROSS;
   e.film = c.variant == GG_VARIANT_PAPER || c.variant == GG_VARIANT_FILM;
+  e.concat = c.variant == GG_VARIANT_CONCAT;
   e.S_ = e.cond ? c.P + 1 : 1;
   e.Gp = static_cast<int>(round_up64(c.G, 8));
   e.F = c.ffn;
@@ -535,6 +544,8 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
   const int B = c.B, S = e.S_, E = c.E, F = e.F, P = c.P, T = c.T, Dp = c.Dp, Dt = c.Dt;
   const int rows = R * B * S;
   const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
+  if (e.concat)  // conditional_gan_concat.py:135-139 / :182-186: c = encoder(text) (or of the masked mean patch)
+    return e.linear(ln, B, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W), Epi().bias(e.P(net, GG_P_TEXT_B)).obf(t.c, E));
   // FiLM parameters from the text CLS / text vector (:129-134); conditional_gan_cross_attention.py has no FiLM
   // (:128-130): its patch encoder reads the patch embeddings as they are
   const bf16* pin = e.patches;
@@ -624,7 +635,7 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
 
 static Op cond_vec(const gg_engine& e, int net) {
   const Tower& t = e.tw[net];
-  if (e.paper) return Op{t.c, e.cfg.E};
+  if (e.paper || e.concat) return Op{t.c, e.cfg.E};
   return Op{t.X[e.cfg.n_layers], static_cast<int64_t>(e.S_) * e.cfg.E};
 }
 
@@ -641,6 +652,11 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
   const int n = Rg * B, rows = n * S;
   const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (e.concat) {
+    GG_TRY(e.wgrad(E, Dt, B, Op{dc, E}, Op{e.text, Dt}, e.Gr(net, GG_P_TEXT_W), Dt));
+    GG_TRY(e.bgrad(dc, E, B, E, e.Gr(net, GG_P_TEXT_B)));
+    return e.flush_grads();
+  }
   bf16* Xf = t.X[c.n_layers];
   if (e.paper) {
     const Op Wp = e.W(net, GG_P_P2T_IN_W), Wt = e.W(net, GG_P_T2P_IN_W);
@@ -955,7 +971,10 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
   const gg_model_cfg& c = e->cfg;
   if (genes)  // real genes -> second half of the [fake; real] matrix
     GG_TRY(k_cast_f32_bf16(genes, c.G, e->xfr + static_cast<int64_t>(c.B) * e->Gp, e->Gp, c.B, c.G, st));
-  if (e->cond) {
+  if (e->concat) {
+    GG_REQUIRE(text, "the concat variant needs the conditioning vector (text embedding or masked mean patch)");
+    GG_TRY(k_cast_f32_bf16(text, c.Dt, e->text, c.Dt, static_cast<int64_t>(c.B) * c.T, c.Dt, st));
+  } else if (e->cond) {
     GG_REQUIRE(patches && text, "conditional variants need patches and text");
     GG_TRY(k_cast_f32_bf16(patches, c.Dp, e->patches, c.Dp, static_cast<int64_t>(c.B) * c.P, c.Dp, st));
     GG_TRY(k_cast_f32_bf16(text, c.Dt, e->text, c.Dt, static_cast<int64_t>(c.B) * c.T, c.Dt, st));
@@ -980,7 +999,7 @@ static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int
   const gg_model_cfg& c = e->cfg;
   TrunkBufs& t = e->tb;
   const int B = c.B, H = c.H, G = c.G, E = c.E, net = GG_NET_DISC;
-  const float p = (training && e->cond) ? c.dropout_p : 0.f;
+  const float p = (training && e->cond && !e->concat) ? c.dropout_p : 0.f;
   const int R = p > 0.f ? 3 : 1;   // independently-dropped tower passes: fake, real, interpolated
   const int Rg = p > 0.f ? 2 : 1;  // replicas that carry gradient (the GP's tower gradient is zero)
   const float inv_b = 1.f / static_cast<float>(B);
@@ -1059,7 +1078,7 @@ static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase,
   TrunkBufs& t = e->tb;
   const int B = c.B, H = c.H, G = c.G, E = c.E, L = c.L;
   const int Lp = static_cast<int>(round_up64(L, 8));
-  const float p = (training && e->cond) ? c.dropout_p : 0.f;
+  const float p = (training && e->cond && !e->concat) ? c.dropout_p : 0.f;
   const float inv_b = 1.f / static_cast<float>(B);
   const int D = GG_NET_DISC, Gn = GG_NET_GEN;
   if (phase == 2) {
@@ -1136,7 +1155,7 @@ extern "C" int gg_engine_optim_step(gg_engine* e, int net, float lr, void* strea
 extern "C" int gg_engine_generate(gg_engine* e, const float* z, float* out_f32, int training, void* stream) {
   GG_REQUIRE(e && z && out_f32, "null argument");
   e->begin(stream);
-  const float p = (training && e->cond) ? e->cfg.dropout_p : 0.f;
+  const float p = (training && e->cond && !e->concat) ? e->cfg.dropout_p : 0.f;
   if (p > 0.f) GG_TRY(k_bump_rng(e->rng, e->S(0)));
   return gen_forward(*e, z, p, out_f32, 0);
 }
@@ -1146,7 +1165,7 @@ extern "C" int gg_engine_critic(gg_engine* e, const float* genes_f32, float* sco
   e->begin(stream);
   cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
-  const float p = (training && e->cond) ? c.dropout_p : 0.f;
+  const float p = (training && e->cond && !e->concat) ? c.dropout_p : 0.f;
   if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
   GG_TRY(k_cast_f32_bf16(genes_f32, c.G, e->xin, e->Gp, c.B, c.G, st));
   if (e->cond) GG_TRY(tower_forward(*e, GG_NET_DISC, 1, p, 0));
@@ -1161,7 +1180,7 @@ extern "C" int gg_engine_gradient_penalty(gg_engine* e, const float* real_f32, c
   e->begin(stream);
   cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
-  const float p = (training && e->cond) ? c.dropout_p : 0.f;
+  const float p = (training && e->cond && !e->concat) ? c.dropout_p : 0.f;
   if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
   GG_TRY(k_cast_f32_bf16(fake_f32, c.G, e->xfr, e->Gp, c.B, c.G, st));
   if (real_f32)
@@ -1202,6 +1221,14 @@ extern "C" int gg_engine_gp_step(gg_engine* e, const float* real_f32, const floa
   if (gp_out)
     GG_CUDA_CHECK(cudaMemcpyAsync(gp_out, e->stats + GG_STAT_GP, sizeof(float), cudaMemcpyDeviceToDevice, st));
   return GG_OK;
+}
+
+// out[b, :] = sum over the non-padded rows p of x[b, p, :] / count_b  (conditional_gan_concat.py:137-138 /
+// :184-185 apply the Linear encoder to every patch and then take this masked mean; the encoder is affine, so
+// the mean is taken first and the encoder runs once per sample).
+extern "C" int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream) {
+  GG_REQUIRE(x && out && B > 0 && P > 0 && D > 0, "bad argument");
+  return k_masked_mean_rows(x, pad, out, B, P, D, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" float* gg_engine_stats(gg_engine* e) { return e ? e->stats : nullptr; }

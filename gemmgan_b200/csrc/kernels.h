@@ -45,6 +45,9 @@ constexpr int64_t GROUP_COUNTER_BYTES = 64 * 1024;  // zeroed arrival counters a
 int64_t colsum_group_workspace_bytes(int64_t max_total_columns);
 int k_colsum_group(const ColsumItem* items, int n, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
+// out[b, d] = mean over rows p with pad[b, p] == 0 of x[b, p, d]   (fp32 in / out; pad may be NULL)
+int k_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, cudaStream_t st);
+
 // ---- wgrad_group.cu: all single-segment weight gradients dW = dY^T X of one backward pass in one launch
 constexpr int WGRAD_GROUP_MAX = 32;
 constexpr int WGRAD_GROUP_MAX_SPLITS = 4;

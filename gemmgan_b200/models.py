@@ -7,6 +7,7 @@ reference's initial weights and state_dict()s are interchangeable with reference
   paper   generator/discriminator  src/conditional_gan_cross_attention_with_film.py:97-233
   film    generator/discriminator  src/conditional_gan_film.py:97-204
   cross   generator/discriminator  src/conditional_gan_cross_attention.py:97-206
+  concat  generator/discriminator  src/conditional_gan_concat.py:97-196
   vanilla generator_nocond/discriminator_nocond  src/vanilla_gan_unconditional.py:93-184
 
 forward() does not run torch kernels: it calls the engine (libgemmgan_sm100a.so) the trainer attached
@@ -21,7 +22,7 @@ from torch import nn
 from . import _abi_decl as A
 
 VARIANT_IDS = {"vanilla": A.VARIANT_VANILLA, "film": A.VARIANT_FILM, "paper": A.VARIANT_PAPER,
-               "cross": A.VARIANT_CROSS}
+               "cross": A.VARIANT_CROSS, "concat": A.VARIANT_CONCAT}
 
 
 def build_linear_block(input_dims, output_dims, negative_slope=0.0, is_bn=False):
@@ -195,6 +196,72 @@ class FilmDiscriminator(_Net):
 
     def forward(self, x, text_embedding, patches, padding_mask):
         return self._engine_forward(x, text_embedding, patches, padding_mask)
+
+
+# ---------------------------------------------------------------------------- concat model
+class _ConcatNet(_Net):
+    """conditional_gan_concat.py: conditioning vector = encoder(text embedding) ('text') or the masked mean over
+    the patches of encoder(patch embedding) ('image'). Construction order as in the reference: trunk blocks,
+    final_layer, then the encoder (:119-124 / :172-176)."""
+
+    _variant = "concat"
+
+    def _build_concat(self, first_dim, input_embedding_dims, embedding_dims, dims, condition_type, negative_slope,
+                      is_bn):
+        assert condition_type in ['text', 'image', 'both'], \
+            "Condition type must be either 'text' or 'image' or 'both'"
+        self.embedding_dims = embedding_dims
+        self.input_embedding_dims = input_embedding_dims
+        self.negative_slope = negative_slope
+        self.is_bn = is_bn
+        self.input_dims = first_dim + embedding_dims
+        stack = build_stack(self.input_dims, dims[:-1], negative_slope, is_bn)
+        setattr(self, "generator" if self._role == "gen" else "discriminator", stack)
+        self.final_layer = nn.Linear(dims[-2], dims[-1])
+        self.condition_type = condition_type
+        self._gg_owner = None
+
+    def slot_table(self):
+        blocks = self.trunk_blocks()
+        if len(blocks) != 2:
+            raise NotImplementedError("the engine implements the reference's 2-hidden-layer trunks")
+        return {A.P_TEXT_W: self.encoder.weight, A.P_TEXT_B: self.encoder.bias,
+                A.P_TR0_W: blocks[0][0].weight, A.P_TR0_B: blocks[0][0].bias,
+                A.P_TR1_W: blocks[1][0].weight, A.P_TR1_B: blocks[1][0].bias,
+                A.P_FIN_W: self.final_layer.weight, A.P_FIN_B: self.final_layer.bias}
+
+    def forward(self, x, text_embedding, patches, padding_mask):
+        return self._engine_forward(x, text_embedding, patches, padding_mask)
+
+
+class ConcatGenerator(_ConcatNet):
+    _role = "gen"
+
+    def __init__(self, latent_dims, input_embedding_dims, embedding_dims, generator_dims, condition_type='text',
+                 negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.latent_dims = latent_dims
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.generator_dims = generator_dims
+        self._build_concat(latent_dims, input_embedding_dims, embedding_dims, generator_dims, condition_type,
+                           negative_slope, is_bn)
+        self.final_activation = nn.ReLU()
+        self.relu = nn.ReLU()
+        self.encoder = nn.Linear(input_embedding_dims, embedding_dims)
+
+
+class ConcatDiscriminator(_ConcatNet):
+    _role = "disc"
+
+    def __init__(self, vector_dims, input_embedding_dims, embedding_dims, discriminator_dims, condition_type='text',
+                 negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.vector_dims = vector_dims
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.discriminator_dims = discriminator_dims
+        self._build_concat(vector_dims, input_embedding_dims, embedding_dims, discriminator_dims, condition_type,
+                           negative_slope, is_bn)
+        self.encoder = nn.Linear(input_embedding_dims, embedding_dims)
 
 
 # --------------------------------------------------------------------------- vanilla model

@@ -248,6 +248,14 @@ class Engine:
                                                        _ptr(out), _stream()))
         return out
 
+    def masked_mean_rows(self, x: torch.Tensor, pad: Optional[torch.Tensor]) -> torch.Tensor:
+        """[B, P, D] fp32 -> [B, D]: mean over the rows whose pad flag is False (gg_masked_mean_rows)."""
+        x, pm = self._f32(x), self._u8(pad)
+        B, P, D = x.shape
+        out = torch.empty(B, D, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.gg_masked_mean_rows(_ptr(x), _ptr(pm), _ptr(out), B, P, D, _stream()))
+        return out
+
     def gp_step(self, real, fake, alpha, out: Optional[torch.Tensor] = None) -> None:
         """GP value + gp_weight * dGP/d{W1, W2, w3} into the critic's gradient buffer (gg_engine_gp_step)."""
         r, f, a = self._f32(real), self._f32(fake), self._f32(alpha)

@@ -142,6 +142,8 @@ int gg_gemm_set_trace(void* device_buf, int cta);
 #define GG_VARIANT_VANILLA 0 /* vanilla_gan_unconditional.py: trunk only                      */
 #define GG_VARIANT_FILM 1    /* conditional_gan_film.py: FiLM + encoder (no bias), CLS vector */
 #define GG_VARIANT_PAPER 2   /* conditional_gan_cross_attention_with_film.py (paper model)    */
+#define GG_VARIANT_CONCAT 4  /* conditional_gan_concat.py: c = Linear(text embedding) ('text'), or Linear(masked mean
+                                patch embedding) ('image', :137-138); parameter slots GG_P_TEXT_W / GG_P_TEXT_B = encoder */
 #define GG_VARIANT_CROSS 3   /* conditional_gan_cross_attention.py: the paper model's towers without FiLM and without
                                 tower biases (:97-206); only row 0 of its multi-query cross-attentions reaches the
                                 conditioning vector, so it runs as the same single-query tail */
@@ -255,6 +257,9 @@ int gg_engine_gradient_penalty(gg_engine* e, const float* real_f32, const float*
  * into the critic's gradient buffer (biases get no GP gradient: the masks are piecewise constant). */
 int gg_engine_gp_step(gg_engine* e, const float* real_f32, const float* fake_f32, const float* alpha, float* gp_out,
                       void* stream);
+/* out[b, :] (fp32) = mean over the rows p with pad[b, p] == 0 of x[b, p, :] — the masked mean of
+ * conditional_gan_concat.py:137-138 ('image' conditioning), taken BEFORE the affine encoder. pad may be NULL. */
+int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream);
 float* gg_engine_stats(gg_engine* e);
 /* named internal device buffers for tests ("fake_bf16", "score", "gp_norms", "cond_disc", ...);
  * returns NULL for unknown names. rows/cols/ld (elements) are optional outputs. */

@@ -71,6 +71,16 @@ def make_trainer(variant: str, n_genes: int, *, optimizer: str = "adam", hidden:
                                    discriminator_dims=[hidden, hidden, 1], optimizer=optimizer,
                                    negative_slope=negative_slope, results_dire=out_dir, **kw)
             t.build_WGAN_GP_nocond()
+        elif variant in ("concat", "concat_image"):
+            ref = load("conditional_gan_concat")
+            torch.manual_seed(seed)
+            image = variant == "concat_image"
+            t = ref.WGAN_GP(input_dims=n_genes, latent_dims=latent, embedding_dims=embed,
+                            generator_dims=[hidden, hidden, n_genes], discriminator_dims=[hidden, hidden, 1],
+                            input_embedding_dims=patch_dim if image else text_dim,
+                            condition_on="image" if image else "text", optimizer=optimizer,
+                            negative_slope=negative_slope, results_dire=out_dir, **kw)
+            t.build_WGAN_GP()
         else:
             mod = {"paper": "conditional_gan_cross_attention_with_film",
                    "film": "conditional_gan_film", "cross": "conditional_gan_cross_attention"}[variant]

@@ -76,6 +76,14 @@ def build_pair(variant, cfg, optimizer="adam", slope=0.0, seed=11, dropout=0.0):
         t = mod.WGAN_GP_nocond(input_dims=G, latent_dims=cfg["latent"], vocab_sizes=[], generator_dims=[H, H, G],
                                discriminator_dims=[H, H, 1], optimizer=optimizer, negative_slope=slope)
         t.build_WGAN_GP_nocond()
+    elif variant in ("concat", "concat_image"):
+        mod = importlib.import_module("conditional_gan_concat")
+        image = variant == "concat_image"
+        t = mod.WGAN_GP(input_dims=G, latent_dims=cfg["latent"], embedding_dims=cfg["embed"], generator_dims=[H, H, G],
+                        discriminator_dims=[H, H, 1], optimizer=optimizer, negative_slope=slope,
+                        input_embedding_dims=cfg["patch_dim"] if image else cfg["text_dim"],
+                        condition_on="image" if image else "text")
+        t.build_WGAN_GP()
     else:
         mod = importlib.import_module({"paper": "conditional_gan_cross_attention_with_film",
                                        "film": "conditional_gan_film", "cross": "conditional_gan_cross_attention"}[variant])
@@ -98,7 +106,7 @@ def ref_order(variant, x, cond):
     if variant in ("paper", "cross"):
         patches, ppad, text, tpad = cond
         return (text, tpad, patches, ppad)
-    if variant == "film":
+    if variant in ("film", "concat", "concat_image"):
         text, patches, ppad = cond
         return (text, patches, ppad)
     return ()
@@ -110,7 +118,8 @@ MID = dict(B=64, G=1000, P=8, T=2, embed=256, hidden=256, latent=256, text_dim=7
 
 @pytest.mark.parametrize("variant,cfg,slope", [
     ("vanilla", SMALL, 0.0), ("vanilla", MID, 0.2), ("paper", SMALL, 0.0), ("paper", MID, 0.0),
-    ("film", SMALL, 0.0), ("film", MID, 0.0), ("cross", SMALL, 0.0), ("cross", MID, 0.0)])
+    ("film", SMALL, 0.0), ("film", MID, 0.0), ("cross", SMALL, 0.0), ("cross", MID, 0.0),
+    ("concat", SMALL, 0.0), ("concat", MID, 0.2), ("concat_image", SMALL, 0.0), ("concat_image", MID, 0.0)])
 def test_critic_step_matches_oracle(variant, cfg, slope):
     o, t = build_pair(variant, cfg, "adam", slope)
     B, G, L = cfg["B"], cfg["G"], cfg["latent"]
@@ -140,7 +149,7 @@ def test_critic_step_matches_oracle(variant, cfg, slope):
 
 
 @pytest.mark.parametrize("variant,cfg", [("vanilla", SMALL), ("paper", SMALL), ("film", SMALL), ("paper", MID),
-                                         ("cross", SMALL), ("cross", MID)])
+                                         ("cross", SMALL), ("cross", MID), ("concat", MID), ("concat_image", SMALL)])
 def test_generator_step_matches_oracle(variant, cfg):
     o, t = build_pair(variant, cfg, "adam")
     B, G, L = cfg["B"], cfg["G"], cfg["latent"]
