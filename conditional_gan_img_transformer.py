@@ -1,0 +1,192 @@
+"""Drop-in for the reference's src/conditional_gan_img_transformer.py (WGAN-GP conditioned on the CLS vector of a
+bias-free transformer encoder over the patch embeddings; patch encoder = Linear -> ReLU -> LayerNorm; the text
+embedding argument is accepted and ignored, as in the reference [:129-130]) backed by the sm_100a engine.
+
+Same public names and signatures as the reference (file:line of the reference in brackets):
+  losses [:32-46], build_* [:56-95], generator [:97-142], discriminator [:145-190], WGAN_GP_model, WGAN_GP [:213-...]
+  with init_train (RMSprop / Adam / AdamW), build_WGAN_GP, gradient_penalty [:305], train_disc [:330], train_gen,
+  train [:415], generate_samples(_all), fit. Model argument order: (x, text_embedding, patches, padding_mask)
+  [:128]; train() order: (gene, text, patches, pad) [:415]. No gradient clipping in this variant.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+
+import numpy as np
+import torch
+
+from gemmgan_b200.models import ImgDiscriminator, ImgGenerator, build_linear_block, build_stack  # noqa: F401
+from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, wasserstein_loss  # noqa: F401
+
+
+def build_generator(input_dims, generator_dims, negative_slope=0.0, is_bn=False):
+    return build_stack(input_dims, generator_dims, negative_slope, is_bn)
+
+
+def build_discriminator(input_dims, dicriminator_dims, negative_slope=0.0, is_bn=False):
+    return build_stack(input_dims, dicriminator_dims, negative_slope, is_bn)
+
+
+class generator(ImgGenerator):
+    pass
+
+
+class discriminator(ImgDiscriminator):
+    pass
+
+
+def WGAN_GP_model(latent_dims, vector_dims, embedding_dims, generator_dims, discriminator_dims,
+                  text_embedding_dims=768, patches_embedding_dims=1024, negative_slope=0.0, is_bn=False):
+    gen = generator(latent_dims, embedding_dims, generator_dims, text_embedding_dims, patches_embedding_dims,
+                    negative_slope, is_bn)
+    disc = discriminator(vector_dims, embedding_dims, discriminator_dims, text_embedding_dims,
+                         patches_embedding_dims, negative_slope, is_bn)
+    return gen, disc
+
+
+class WGAN_GP(TrainerBase):
+    variant = "img"
+
+    def __init__(self, input_dims, latent_dims, embedding_dims, generator_dims, discriminator_dims,
+                 text_embedding_dims=768, patches_embedding_dims=1024, negative_slope=0.0, is_bn=False,
+                 lr_d=5e-4, lr_g=5e-4, optimizer='rms_prop', gp_weight=10, p_aug=0, norm_scale=0.5, train=True,
+                 n_critic=5, freq_print=2, freq_compute_test=50, freq_visualize_test=100, patience=10,
+                 normalization='standardize', log2=False, rpm=False, results_dire=''):
+        self.embedding_dims = embedding_dims
+        self.text_embedding_dims = text_embedding_dims
+        self.patches_embedding_dims = patches_embedding_dims
+        self._init_common(input_dims, latent_dims, generator_dims, discriminator_dims, negative_slope, is_bn,
+                          lr_d, lr_g, optimizer, gp_weight, p_aug, norm_scale, train, n_critic, freq_print,
+                          freq_compute_test, freq_visualize_test, patience, normalization, log2, rpm,
+                          results_dire)
+        self._tokens = None
+
+    def _shape_cfg(self):
+        return dict(E=self.embedding_dims, H=self.generator_dims[0], Dt=self.text_embedding_dims,
+                    Dp=self.patches_embedding_dims, P=self._tokens, T=1, tower_bias=False)
+
+    def build_WGAN_GP(self):
+        self.numerical_dims = []
+        gen, disc = WGAN_GP_model(self.latent_dims, self.input_dims, self.embedding_dims, self.generator_dims,
+                                  self.discriminator_dims, self.text_embedding_dims, self.patches_embedding_dims,
+                                  self.negative_slope, self.is_bn)
+        self._attach(gen, disc)
+
+    def _stage(self, genes, text_embedding, patches, padding_mask):
+        dev = self.device
+        if patches.shape[1] != self._tokens:
+            self._tokens = patches.shape[1]
+            self._engines.clear()
+        eng = self._engine(patches.shape[0])
+        eng.set_batch(genes=None if genes is None else genes.to(dev, non_blocking=True), patches=patches.to(dev, non_blocking=True),
+                      patch_pad=padding_mask.to(dev, non_blocking=True), text=None, text_pad=None)
+        return eng
+
+    # ---- reference-signature entry points -------------------------------------------------
+    def gradient_penalty(self, real_data, fake_data, text_embedding, patches, padding_mask, alpha=None):
+        eng = self._stage(None, text_embedding, patches, padding_mask)
+        if alpha is None:
+            alpha = self._alpha(eng.B)
+        return eng.gradient_penalty(real_data.to(self.device), fake_data.to(self.device), alpha,
+                                    training=self.disc.training)
+
+    def train_disc(self, real_data, z, text_embedding, patches, padding_mask, alpha=None):
+        eng = self._stage(real_data, text_embedding, patches, padding_mask)
+        self._train_disc_staged(eng, z.to(self.device), alpha)
+
+    def train_gen(self, z, text_embedding, patches, padding_mask):
+        eng = self._stage(None, text_embedding, patches, padding_mask)
+        self._train_gen_staged(eng, z.to(self.device))
+
+    def train(self, gene_expression, text_embedding, patches, padding_mask, zs=None, alphas=None):
+        eng = self._stage(gene_expression, text_embedding, patches, padding_mask)
+        self._train_staged(eng, zs, alphas)
+
+    def _module_forward(self, module, x, text_embedding, patches, padding_mask):
+        eng = self._stage(None, text_embedding, patches, padding_mask)
+        if module is self.gen:
+            return eng.generate(x.to(self.device), training=module.training)
+        return eng.critic(x.to(self.device), training=module.training)
+
+    def generate_samples(self, gene_expression, text_embedding, patches, padding_mask):
+        with torch.no_grad():
+            self.gen.eval()
+            x_real = gene_expression.clone().to(torch.float32)
+            z = torch.normal(0, 1, size=(x_real.shape[0], self.latent_dims), device=self.device)
+            x_gen = self.gen(z, text_embedding, patches, padding_mask)
+        return x_real, x_gen
+
+    def generate_samples_all(self, data_loader, num_repeats=1):
+        """Batch tuple layout of multi_patch_gan_dataloader.py:48:
+        (text_embedding, gene_expression, patches, padding_mask, disease_type, primary_site)."""
+        real, gen, dt_r, dt_g, ps_r, ps_g = [], [], [], [], [], []
+        for i in range(num_repeats):
+            for batch in data_loader:
+                text, genes, patches, ppad, dtype_, psite = batch[:6]
+                x_real, x_gen = self.generate_samples(genes.to(self.device), text, patches, ppad)
+                gen.append(x_gen.cpu().numpy())
+                dt_g.append(dtype_.cpu().numpy())
+                ps_g.append(psite.cpu().numpy())
+                if i == 0:
+                    real.append(x_real.cpu().numpy())
+                    dt_r.append(dtype_.cpu().numpy())
+                    ps_r.append(psite.cpu().numpy())
+        return (np.vstack(real), np.vstack(gen), np.concatenate(dt_r), np.concatenate(dt_g), np.concatenate(ps_r),
+                np.concatenate(ps_g))
+
+    def fit(self, train_data, val_data=None, test_data=None, epochs=1, val=True):
+        """Training loop of the reference fit() without its evaluation / plotting."""
+        self.build_WGAN_GP()
+        if self.isTrain:
+            self.init_train()
+        for epoch in range(epochs):
+            self._epoch_lr_decay(epoch, 100)
+            self.epoch = epoch
+            d_sum, g_sum, n = 0.0, 0.0, 0
+            for i, data in enumerate(train_data):
+                self.train(data[1], data[0], data[2], data[3])
+                d_sum, g_sum, n = d_sum + self.d_batch_loss, g_sum + self.g_batch_loss, n + 1
+                if (i + 1) % self.freq_print == 0:
+                    print('[Epoch %d/%d] [Batch %d/%d] [D loss : %f] [G loss : %f]' %
+                          (epoch + 1, epochs, i + 1, len(train_data), self.disc_loss.item(), self.gen_loss.item()))
+            d_mean = d_sum / max(n, 1)
+            self.loss_dict['d loss'].append(d_mean[0])
+            self.loss_dict['d real loss'].append(d_mean[1])
+            self.loss_dict['d fake loss'].append(d_mean[2])
+            self.loss_dict['g loss'].append((g_sum / max(n, 1))[0])
+            last = epoch == epochs - 1
+            if self.result_dire and ((epoch + 1) % self.freq_compute_test == 0 or last):
+                tag = 'last_epoch' if last else f'epoch_{epoch + 1}'
+                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, f'gen_{tag}.pt'))
+                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, f'disc_{tag}.pt'))
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument('--seed', type=int, default=42)
+    p.add_argument('--num_epochs', type=int, default=1)
+    p.add_argument('--batch_size', type=int, default=8)
+    p.add_argument('--latent_dim', type=int, default=256)
+    p.add_argument('--hidden_dim', type=int, default=256)
+    p.add_argument('--embedding_dim', type=int, default=256)
+    p.add_argument('--num_patches', type=int, default=256)
+    p.add_argument('--n_genes', type=int, default=18868)
+    p.add_argument('--output_path', type=str, default='')
+    p.add_argument('--optimizer', type=str, default='rms_prop')
+    return p.parse_args()
+
+
+if __name__ == '__main__':
+    from gemmgan_b200.synthetic import synthetic_loader
+
+    args = parse_args()
+    torch.manual_seed(args.seed)
+    loader = synthetic_loader('film', n_samples=args.batch_size * 4, batch_size=args.batch_size,
+                              n_genes=args.n_genes, n_patches=args.num_patches, seed=args.seed)
+    model = WGAN_GP(input_dims=args.n_genes, latent_dims=args.latent_dim, embedding_dims=args.embedding_dim,
+                    generator_dims=[args.hidden_dim, args.hidden_dim, args.n_genes],
+                    discriminator_dims=[args.hidden_dim, args.hidden_dim, 1], optimizer=args.optimizer,
+                    results_dire=args.output_path)
+    model.fit(loader, None, None, epochs=args.num_epochs)
+    print(model.loss_dict)

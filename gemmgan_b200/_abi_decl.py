@@ -3,13 +3,14 @@ from __future__ import annotations
 
 import ctypes as C
 
-VARIANT_VANILLA, VARIANT_FILM, VARIANT_PAPER, VARIANT_CROSS, VARIANT_CONCAT = 0, 1, 2, 3, 4
+VARIANT_VANILLA, VARIANT_FILM, VARIANT_PAPER, VARIANT_CROSS, VARIANT_CONCAT, VARIANT_IMG = 0, 1, 2, 3, 4, 5
 OPT_RMSPROP, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 NET_GEN, NET_DISC = 0, 1
 
 # enum gg_param_slot
 P_FILM_W, P_FILM_B, P_TEXT_W, P_TEXT_B, P_PATCH_W, P_PATCH_B, P_CLS = range(7)
 P_LAYER0 = 7
+P_PENC_LN_W, P_PENC_LN_B = P_FILM_W, P_FILM_B   # GG_VARIANT_IMG: patch-encoder LayerNorm vectors
 (L_IN_W, L_IN_B, L_OUT_W, L_OUT_B, L_FF1_W, L_FF1_B, L_FF2_W, L_FF2_B,
  L_N1_W, L_N1_B, L_N2_W, L_N2_B) = range(12)
 L_COUNT = 12

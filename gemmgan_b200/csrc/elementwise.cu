@@ -127,7 +127,8 @@ int k_film_bwd(const bf16* dmod, const bf16* patches, const float* gb, bf16* dgb
 }
 
 // ----------------------------------------------------------------------------- token plumbing
-__global__ void assemble_tokens_kernel(bf16* x, const float* __restrict__ cls, int R, int B, int S, int E) {
+__global__ void assemble_tokens_kernel(bf16* x, const float* __restrict__ cls, int R, int B, int S, int E,
+                                       const bf16* __restrict__ src) {
   pdl_entry();
   const int64_t total = static_cast<int64_t>(R) * B * S * E;
   const int64_t rep = static_cast<int64_t>(B) * S * E;
@@ -136,11 +137,26 @@ __global__ void assemble_tokens_kernel(bf16* x, const float* __restrict__ cls, i
     const int e = static_cast<int>(i % E);
     const int s = static_cast<int>((i / E) % S);
     if (s == 0) x[i] = __float2bfloat16_rn(cls[e]);
-    else if (i >= rep) x[i] = x[i % rep];
+    else if (src) {
+      const int64_t b = (i % rep) / (static_cast<int64_t>(S) * E);
+      x[i] = src[(b * (S - 1) + (s - 1)) * E + e];
+    } else if (i >= rep) x[i] = x[i % rep];
   }
 }
-int k_assemble_tokens(bf16* x, const float* cls, int R, int B, int S, int E, cudaStream_t st) {
-  launch_k(assemble_tokens_kernel, grid_for(static_cast<int64_t>(R) * B * S * E, 256), 256, 0, st, x, cls, R, B, S, E);
+int k_assemble_tokens(bf16* x, const float* cls, int R, int B, int S, int E, cudaStream_t st, const bf16* src) {
+  launch_k(assemble_tokens_kernel, grid_for(static_cast<int64_t>(R) * B * S * E, 256), 256, 0, st, x, cls, R, B, S, E, src);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+__global__ void relu_bwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ h, bf16* __restrict__ out, int64_t n) {
+  pdl_entry();
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = __bfloat162float(h[i]) > 0.f ? g[i] : __float2bfloat16_rn(0.f);
+}
+int k_relu_bwd(const bf16* g, const bf16* h, bf16* out, int64_t n, cudaStream_t st) {
+  launch_k(relu_bwd_kernel, grid_for(n, 256), 256, 0, st, g, h, out, n);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

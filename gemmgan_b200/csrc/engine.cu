@@ -91,6 +91,8 @@ struct Tower {
   bf16 *mod, *te, *X[3];
   TowerLayer L[2];
   bf16 *qp, *kvp, *ap, *pv, *qt, *kvt, *at, *c, *tmpE;
+  bf16 *pe_h = nullptr, *pe_ln = nullptr, *zero = nullptr;  // IMG: relu(patch projection), its LayerNorm, zeros
+  float *pe_mean = nullptr, *pe_rstd = nullptr;
 };
 struct LayerGrads {  // per layer: side-lane weight-gradient GEMMs read these while lane 0 moves on
   bf16 *gz2, *gy2, *gz1, *gy1, *gh, *gqkv;
@@ -99,6 +101,8 @@ struct LayerGrads {  // per layer: side-lane weight-gradient GEMMs read these wh
 struct GradScratch {
   bf16 *dc, *dat, *dqt, *dkvt, *dkvt_sum, *dp, *dap, *dqp, *dqp_sum, *dkvp;
   bf16 *ga, *gb, *gao, *dte, *dte0, *dpe, *dmod, *dgb;
+  bf16 *dpe_z = nullptr, *dpe_h = nullptr;  // IMG: gradient before the patch LayerNorm / before the ReLU
+  float* lnp_pe = nullptr;
   LayerGrads L[2];
 };
 struct TrunkBufs {
@@ -116,6 +120,7 @@ struct gg_engine {
   gg_net_buffers nets[2];
   NetShadow sh[2];
   int S_ = 1, Gp = 0, F = 0, hd = 0;
+  bool img = false;     // conditional_gan_img_transformer.py: patch encoder = Linear + ReLU + LayerNorm, CLS conditioning
   bool concat = false;  // conditional_gan_concat.py: the conditioning is one Linear of the staged text / mean-patch vector
   bool cond = false, paper = false, film = false;  // paper: cross-attention tail; film: FiLM modulation of the patches
   // staged inputs
@@ -287,7 +292,10 @@ namespace gg {
 
 static bool slot_matrix_shape(const gg_model_cfg& c, int net, int slot, int* rows, int* cols) {
   const int E = c.E, F = c.ffn, condw = c.variant == GG_VARIANT_VANILLA ? 0 : E;
-  if (slot == GG_P_FILM_W) { *rows = 2 * c.Dp; *cols = c.Dt; return true; }
+  if (slot == GG_P_FILM_W) {  // (the IMG variant keeps its patch-encoder LayerNorm vectors in the FiLM slots)
+    if (c.variant == GG_VARIANT_IMG) return false;
+    *rows = 2 * c.Dp; *cols = c.Dt; return true;
+  }
   if (slot == GG_P_TEXT_W) { *rows = E; *cols = c.Dt; return true; }
   if (slot == GG_P_PATCH_W) { *rows = E; *cols = c.Dp; return true; }
   if (slot >= GG_P_LAYER0 && slot < GG_P_LAYER0 + 24) {
@@ -378,6 +386,13 @@ static void layout_tower(gg_engine& e, Tower& t, int Rmax, Arena& ar) {
   t.at = ar.take<bf16>(rb * E);
   t.c = ar.take<bf16>(rb * E);
   t.tmpE = ar.take<bf16>(rows * E);
+  if (e.img) {
+    t.pe_h = ar.take<bf16>(B * P * E);
+    t.pe_ln = ar.take<bf16>(B * P * E);
+    t.zero = ar.take<bf16>(B * P * E);
+    t.pe_mean = ar.take<float>(B * P);
+    t.pe_rstd = ar.take<float>(B * P);
+  }
 }
 
 static int64_t layout(gg_engine& e, uint8_t* base) {
@@ -442,6 +457,11 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
     g.dpe = ar.take<bf16>(B * P * E);
     g.dmod = ar.take<bf16>(B * P * c.Dp);
     g.dgb = ar.take<bf16>(B * 2 * c.Dp);
+    if (e.img) {
+      g.dpe_z = ar.take<bf16>(B * P * E);
+      g.dpe_h = ar.take<bf16>(B * P * E);
+      g.lnp_pe = ar.take<float>(ln_bwd_scratch_floats(B * P, static_cast<int>(E)));
+    }
   }
   TrunkBufs& t = e.tb;
   t.a1x = ar.take<float>(2 * B * H);
@@ -507,7 +527,7 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
 }
 
 static int validate_cfg(const gg_model_cfg& c) {
-  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_CONCAT, "unknown variant %d", c.variant);
+  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_IMG, "unknown variant %d", c.variant);
   GG_REQUIRE(c.B > 0 && c.G > 0 && c.L > 0 && c.H > 0, "bad sizes B=%d G=%d L=%d H=%d", c.B, c.G, c.L, c.H);
   GG_REQUIRE(c.L % 8 == 0 && c.H % 8 == 0, "latent and hidden widths must be multiples of 8");
   if (c.variant != GG_VARIANT_VANILLA) {
@@ -528,6 +548,7 @@ static void derive(gg_engine& e) {
   e.paper = c.variant == GG_VARIANT_PAPER || c.variant == GG_VARIANT_CROSS;
   e.film = c.variant == GG_VARIANT_PAPER || c.variant == GG_VARIANT_FILM;
   e.concat = c.variant == GG_VARIANT_CONCAT;
+  e.img = c.variant == GG_VARIANT_IMG;
   e.S_ = e.cond ? c.P + 1 : 1;
   e.Gp = static_cast<int>(round_up64(c.G, 8));
   e.F = c.ffn;
@@ -569,10 +590,20 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
     GG_TRY(e.linear(tl, B * T, 2 * E, E, Op{t.te, E}, Op{Wt.p + static_cast<int64_t>(E) * Wt.ld, Wt.ld},
                     Epi().bias(bt ? bt + E : nullptr).obf(t.kvt, 2 * E)));
   }
-  // patch projection written straight behind the CLS row of replica 0 (:139-142)
-  GG_TRY(e.linear(ln, B * P, E, Dp, Op{pin, Dp}, e.W(net, GG_P_PATCH_W),
-                  Epi().bias(e.P(net, GG_P_PATCH_B)).obf(t.X[0], E).rowmap(P, S, 1)));
-  GG_TRY(k_assemble_tokens(t.X[0], e.P(net, GG_P_CLS), R, B, S, E, st));
+  if (e.img) {
+    // conditional_gan_img_transformer.py:111-115: patches_encoder = Linear -> ReLU -> LayerNorm (no dropout: once
+    // for the B*P rows, shared by the replicas), then CLS + tokens
+    GG_TRY(e.linear(ln, B * P, E, Dp, Op{pin, Dp}, e.W(net, GG_P_PATCH_W),
+                    Epi().bias(e.P(net, GG_P_PATCH_B)).act(GG_ACT_LEAKY, 0.f).obf(t.pe_h, E)));
+    GG_TRY(k_add_ln_fwd(t.zero, t.pe_h, e.P(net, GG_P_PENC_LN_W), e.P(net, GG_P_PENC_LN_B), t.tmpE, t.pe_ln, t.pe_mean,
+                        t.pe_rstd, static_cast<int64_t>(B) * P, E, c.ln_eps, 0.f, e.rng, 0, st));
+    GG_TRY(k_assemble_tokens(t.X[0], e.P(net, GG_P_CLS), R, B, S, E, st, t.pe_ln));
+  } else {
+    // patch projection written straight behind the CLS row of replica 0 (:139-142)
+    GG_TRY(e.linear(ln, B * P, E, Dp, Op{pin, Dp}, e.W(net, GG_P_PATCH_W),
+                    Epi().bias(e.P(net, GG_P_PATCH_B)).obf(t.X[0], E).rowmap(P, S, 1)));
+    GG_TRY(k_assemble_tokens(t.X[0], e.P(net, GG_P_CLS), R, B, S, E, st));
+  }
   for (int l = 0; l < c.n_layers; ++l) {
     TowerLayer& L = t.L[l];
     const int ls = GG_P_LAYER0 + GG_L_COUNT * l;
@@ -776,6 +807,17 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
   // X0 = [cls | patch projections], replicas share the projections
   GG_TRY(e.bgrad(g.ga, static_cast<int64_t>(S) * E, n, E, e.Gr(net, GG_P_CLS)));  // d cls = sum over the CLS rows
   GG_TRY(k_unassemble_tokens(g.ga, g.dpe, nullptr, Rg, B, S, E, st));
+  if (e.img) {  // LayerNorm and ReLU of the patch encoder, then its Linear's gradients (the patches are inputs)
+    GG_TRY(k_add_ln_bwd(g.dpe, t.pe_h, t.pe_mean, t.pe_rstd, e.P(net, GG_P_PENC_LN_W), g.dpe_z, nullptr, nullptr,
+                        nullptr, static_cast<int64_t>(B) * P, E, 0.f, e.rng, 0, g.lnp_pe, st));
+    GG_TRY(e.fork(2));
+    GG_TRY(k_ln_bwd_finish(g.lnp_pe, static_cast<int64_t>(B) * P, E, e.Gr(net, GG_P_PENC_LN_W),
+                           e.Gr(net, GG_P_PENC_LN_B), e.S(2)));
+    GG_TRY(k_relu_bwd(g.dpe_z, t.pe_h, g.dpe_h, static_cast<int64_t>(B) * P * E, st));
+    GG_TRY(e.wgrad(E, Dp, B * P, Op{g.dpe_h, E}, Op{e.patches, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
+    GG_TRY(e.bgrad(g.dpe_h, E, B * P, E, e.Gr(net, GG_P_PATCH_B)));
+    return e.flush_grads();
+  }
   GG_TRY(e.wgrad(E, Dp, B * P, Op{g.dpe, E}, Op{e.film ? t.mod : e.patches, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
   GG_TRY(e.bgrad(g.dpe, E, B * P, E, e.Gr(net, GG_P_PATCH_B)));
   if (e.film) {
@@ -930,6 +972,9 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
                                     cudaMemcpyHostToDevice, st));
   }
   GG_CUDA_CHECK(cudaStreamSynchronize(st));  // segs vectors stay alive, but keep create() simple and safe
+  if (e->img)
+    for (int n = 0; n < 2; ++n)
+      GG_CUDA_CHECK(cudaMemsetAsync(e->tw[n].zero, 0, static_cast<size_t>(cfg->B) * cfg->P * cfg->E * sizeof(bf16), st));
   GG_CUDA_CHECK(cudaMemsetAsync(e->wg_ws, 0, GROUP_COUNTER_BYTES, st));
   GG_CUDA_CHECK(cudaMemsetAsync(e->cs_ws, 0, GROUP_COUNTER_BYTES, st));
   GG_CUDA_CHECK(cudaMemsetAsync(e->stats, 0, GG_STATS_COUNT * sizeof(float), st));
@@ -975,9 +1020,9 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
     GG_REQUIRE(text, "the concat variant needs the conditioning vector (text embedding or masked mean patch)");
     GG_TRY(k_cast_f32_bf16(text, c.Dt, e->text, c.Dt, static_cast<int64_t>(c.B) * c.T, c.Dt, st));
   } else if (e->cond) {
-    GG_REQUIRE(patches && text, "conditional variants need patches and text");
+    GG_REQUIRE(patches && (text || e->img), "conditional variants need patches and text");
     GG_TRY(k_cast_f32_bf16(patches, c.Dp, e->patches, c.Dp, static_cast<int64_t>(c.B) * c.P, c.Dp, st));
-    GG_TRY(k_cast_f32_bf16(text, c.Dt, e->text, c.Dt, static_cast<int64_t>(c.B) * c.T, c.Dt, st));
+    if (text) GG_TRY(k_cast_f32_bf16(text, c.Dt, e->text, c.Dt, static_cast<int64_t>(c.B) * c.T, c.Dt, st));
     if (patch_pad) {
       GG_TRY(k_mask_with_cls(patch_pad, e->mask_s, c.B, c.P, st));
     } else {

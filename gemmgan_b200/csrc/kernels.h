@@ -24,7 +24,11 @@ int k_film_apply(const bf16* patches, const float* gb, bf16* mod, int B, int P, 
 int k_film_bwd(const bf16* dmod, const bf16* patches, const float* gb, bf16* dgb, int B, int P, int Dp,
                cudaStream_t st);
 // x[r, b, 0, :] = cls; x[r, b, 1+j, :] = x[0, b, 1+j, :] for r >= 1 (replica 0 rows 1.. are already there)
-int k_assemble_tokens(bf16* x, const float* cls, int R, int B, int S, int E, cudaStream_t st);
+// src (optional) [B, S-1, E]: token rows of EVERY replica are taken from it instead
+int k_assemble_tokens(bf16* x, const float* cls, int R, int B, int S, int E, cudaStream_t st,
+                      const bf16* src = nullptr);
+// out[i] = h[i] > 0 ? g[i] : 0   (ReLU backward from the stored output)
+int k_relu_bwd(const bf16* g, const bf16* h, bf16* out, int64_t n, cudaStream_t st);
 // dpe[b, j, :] = sum_r dx[r, b, 1+j, :]; dcls[:] = sum_{r,b} dx[r, b, 0, :]  (fp32 out for dcls)
 int k_unassemble_tokens(const bf16* dx, bf16* dpe, float* dcls, int R, int B, int S, int E, cudaStream_t st);
 // out[i] = sum_r in[r * n + i]

@@ -8,6 +8,7 @@ reference's initial weights and state_dict()s are interchangeable with reference
   film    generator/discriminator  src/conditional_gan_film.py:97-204
   cross   generator/discriminator  src/conditional_gan_cross_attention.py:97-206
   concat  generator/discriminator  src/conditional_gan_concat.py:97-196
+  img     generator/discriminator  src/conditional_gan_img_transformer.py:97-190
   vanilla generator_nocond/discriminator_nocond  src/vanilla_gan_unconditional.py:93-184
 
 forward() does not run torch kernels: it calls the engine (libgemmgan_sm100a.so) the trainer attached
@@ -22,7 +23,7 @@ from torch import nn
 from . import _abi_decl as A
 
 VARIANT_IDS = {"vanilla": A.VARIANT_VANILLA, "film": A.VARIANT_FILM, "paper": A.VARIANT_PAPER,
-               "cross": A.VARIANT_CROSS, "concat": A.VARIANT_CONCAT}
+               "cross": A.VARIANT_CROSS, "concat": A.VARIANT_CONCAT, "img": A.VARIANT_IMG}
 
 
 def build_linear_block(input_dims, output_dims, negative_slope=0.0, is_bn=False):
@@ -56,12 +57,15 @@ class _Net(nn.Module):
         self.negative_slope = negative_slope
         self.is_bn = is_bn
         E = embedding_dims
-        if v in ("paper", "film", "cross"):
-            if v != "cross":
+        if v in ("paper", "film", "cross", "img"):
+            if v in ("paper", "film"):
                 self.film_generator = nn.Linear(text_embedding_dims, patches_embedding_dims * 2)
             if v in ("paper", "cross"):
                 self.text_encoder = nn.Linear(text_embedding_dims, E)
-            self.patches_encoder = nn.Linear(patches_embedding_dims, E)
+            if v == "img":  # conditional_gan_img_transformer.py:111-115
+                self.patches_encoder = nn.Sequential(nn.Linear(patches_embedding_dims, E), nn.ReLU(), nn.LayerNorm(E))
+            else:
+                self.patches_encoder = nn.Linear(patches_embedding_dims, E)
             self.patches_transformer_layer = nn.TransformerEncoderLayer(
                 d_model=E, nhead=4, dim_feedforward=E * 2, dropout=0.1, activation="relu", batch_first=True,
                 bias=(v == "paper"))
@@ -86,12 +90,17 @@ class _Net(nn.Module):
         """C-ABI parameter slot -> nn.Parameter (include/gemmgan.h enum gg_param_slot)."""
         t = {}
         v = self._variant
-        if v in ("paper", "film", "cross"):
-            if v != "cross":
+        if v in ("paper", "film", "cross", "img"):
+            if v in ("paper", "film"):
                 t[A.P_FILM_W], t[A.P_FILM_B] = self.film_generator.weight, self.film_generator.bias
             if v in ("paper", "cross"):
                 t[A.P_TEXT_W], t[A.P_TEXT_B] = self.text_encoder.weight, self.text_encoder.bias
-            t[A.P_PATCH_W], t[A.P_PATCH_B] = self.patches_encoder.weight, self.patches_encoder.bias
+            if v == "img":
+                lin, norm = self.patches_encoder[0], self.patches_encoder[2]
+                t[A.P_PATCH_W], t[A.P_PATCH_B] = lin.weight, lin.bias
+                t[A.P_PENC_LN_W], t[A.P_PENC_LN_B] = norm.weight, norm.bias
+            else:
+                t[A.P_PATCH_W], t[A.P_PATCH_B] = self.patches_encoder.weight, self.patches_encoder.bias
             t[A.P_CLS] = self.patches_cls_token
             for l, layer in enumerate(self.patches_transformer.layers):
                 b = A.P_LAYER0 + A.L_COUNT * l
@@ -196,6 +205,15 @@ class FilmDiscriminator(_Net):
 
     def forward(self, x, text_embedding, patches, padding_mask):
         return self._engine_forward(x, text_embedding, patches, padding_mask)
+
+
+# ------------------------------------------------- image-transformer model (no text, no FiLM)
+class ImgGenerator(FilmGenerator):
+    _role, _variant = "gen", "img"
+
+
+class ImgDiscriminator(FilmDiscriminator):
+    _role, _variant = "disc", "img"
 
 
 # ---------------------------------------------------------------------------- concat model

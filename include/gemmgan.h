@@ -144,6 +144,8 @@ int gg_gemm_set_trace(void* device_buf, int cta);
 #define GG_VARIANT_PAPER 2   /* conditional_gan_cross_attention_with_film.py (paper model)    */
 #define GG_VARIANT_CONCAT 4  /* conditional_gan_concat.py: c = Linear(text embedding) ('text'), or Linear(masked mean
                                 patch embedding) ('image', :137-138); parameter slots GG_P_TEXT_W / GG_P_TEXT_B = encoder */
+#define GG_VARIANT_IMG 5     /* conditional_gan_img_transformer.py: patch encoder Linear -> ReLU -> LayerNorm (:111-115), no
+                                text, bias-free encoder layers, CLS vector as conditioning (:131-133) */
 #define GG_VARIANT_CROSS 3   /* conditional_gan_cross_attention.py: the paper model's towers without FiLM and without
                                 tower biases (:97-206); only row 0 of its multi-query cross-attentions reaches the
                                 conditioning vector, so it runs as the same single-query tail */
@@ -160,7 +162,9 @@ enum gg_param_slot {
   GG_P_P2T_IN_W = GG_P_LAYER0 + 24, GG_P_P2T_IN_B, GG_P_P2T_OUT_W, GG_P_P2T_OUT_B,
   GG_P_T2P_IN_W, GG_P_T2P_IN_B, GG_P_T2P_OUT_W, GG_P_T2P_OUT_B,
   GG_P_TR0_W, GG_P_TR0_B, GG_P_TR1_W, GG_P_TR1_B, GG_P_FIN_W, GG_P_FIN_B,
-  GG_NSLOTS
+  GG_NSLOTS,
+  /* GG_VARIANT_IMG has no FiLM: its patch-encoder LayerNorm weight / bias [E] live in the FiLM slots */
+  GG_P_PENC_LN_W = GG_P_FILM_W, GG_P_PENC_LN_B = GG_P_FILM_B
 };
 enum gg_layer_slot {
   GG_L_IN_W = 0, GG_L_IN_B, GG_L_OUT_W, GG_L_OUT_B, GG_L_FF1_W, GG_L_FF1_B, GG_L_FF2_W, GG_L_FF2_B,

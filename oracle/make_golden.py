@@ -40,7 +40,7 @@ def ref_args(variant, x, cond):
     if variant in ("paper", "cross"):
         patches, ppad, text, tpad = cond
         return (x, text, tpad, patches, ppad)
-    if variant in ("film", "concat", "concat_image"):
+    if variant in ("film", "concat", "concat_image", "img"):
         text, patches, ppad = cond
         return (x, text, patches, ppad)
     return (x,)
@@ -161,6 +161,7 @@ def main():
     make("paper", FULL, "adam", 0.0, 3, False, "paper_fulldims_adam")
     make("film", FULL, "rms_prop", 0.0, 3, False, "film_fulldims_rmsprop")
     make("cross", SMALL, "adam", 0.0, 4, True, "cross_small_adam")
+    make("img", SMALL, "rms_prop", 0.0, 4, True, "img_small_rmsprop")
     make("concat", SMALL, "adam", 0.0, 4, True, "concat_small_adam")
     make("concat_image", SMALL, "rms_prop", 0.2, 4, True, "concat_image_small_rmsprop_leaky")
 
