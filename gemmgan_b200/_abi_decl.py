@@ -6,6 +6,7 @@ import ctypes as C
 VARIANT_VANILLA, VARIANT_FILM, VARIANT_PAPER, VARIANT_CROSS, VARIANT_CONCAT, VARIANT_IMG = 0, 1, 2, 3, 4, 5
 OPT_RMSPROP, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 NET_GEN, NET_DISC = 0, 1
+PHASE_STAGE0, PHASE_NO_JOIN = 16, 64
 
 # enum gg_param_slot
 P_FILM_W, P_FILM_B, P_TEXT_W, P_TEXT_B, P_PATCH_W, P_PATCH_B, P_CLS = range(7)
@@ -85,6 +86,7 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_critic.argtypes = [vp, vp, vp, i32, vp]
     L.gg_engine_gradient_penalty.argtypes = [vp, vp, vp, vp, i32, vp, vp]
     L.gg_engine_gp_step.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.gg_engine_lanes_signal.argtypes = [vp, vp]
     L.gg_masked_mean_rows.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.gg_engine_stats.argtypes = [vp]
     L.gg_engine_stats.restype = vp
@@ -115,7 +117,7 @@ EXPORTS = [
     "gg_last_error", "gg_abi_version", "gg_check_device", "gg_gemm_bf16", "gg_engine_workspace_bytes",
     "gg_engine_create", "gg_engine_destroy", "gg_engine_set_lanes", "gg_engine_refresh_shadows", "gg_engine_set_batch",
     "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_disc_grads_phase", "gg_engine_gen_grads_phase", "gg_engine_optim_step", "gg_engine_generate",
-    "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_gp_step", "gg_masked_mean_rows", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
+    "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_gp_step", "gg_masked_mean_rows", "gg_engine_lanes_signal", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes",
     "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

@@ -674,7 +674,10 @@ static Op cond_vec(const gg_engine& e, int net) {
 // dc: [Rg*B, E] gradient of the loss w.r.t. the conditioning vectors of the first Rg replicas.
 // The dependent chain (dgrads, attention / LayerNorm backward) runs on lane 0; every weight- and
 // bias-gradient reduction is forked onto the side lanes (e.wgrad / e.bgrad).
-static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc) {
+// Stages (data parallel: the trainer all-reduces a stage's gradients while the next stages run): 0 = head (the
+// cross-attention tail / CLS scatter), 1 .. n_layers = encoder layers from the last to the first, n_layers + 1 =
+// embedding tail (CLS, patch encoder, FiLM). Runs the stages in [s0, s1).
+static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc, int s0 = 0, int s1 = 1 << 20) {
   const gg_model_cfg& c = e.cfg;
   Tower& t = e.tw[net];
   GradScratch& g = e.gs;
@@ -684,12 +687,16 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
   const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   if (e.concat) {
+    if (s0 > 0) return GG_OK;
     GG_TRY(e.wgrad(E, Dt, B, Op{dc, E}, Op{e.text, Dt}, e.Gr(net, GG_P_TEXT_W), Dt));
     GG_TRY(e.bgrad(dc, E, B, E, e.Gr(net, GG_P_TEXT_B)));
     return e.flush_grads();
   }
   bf16* Xf = t.X[c.n_layers];
-  if (e.paper) {
+  const bool head = s0 <= 0 && 0 < s1;
+  const int tail_stage = c.n_layers + 1;
+  if (!head) {
+  } else if (e.paper) {
     const Op Wp = e.W(net, GG_P_P2T_IN_W), Wt = e.W(net, GG_P_T2P_IN_W);
     const Op Wp_kv{Wp.p + static_cast<int64_t>(E) * Wp.ld, Wp.ld}, Wt_kv{Wt.p + static_cast<int64_t>(E) * Wt.ld, Wt.ld};
     float* gWp = e.Gr(net, GG_P_P2T_IN_W);
@@ -762,6 +769,8 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     GG_TRY(k_scatter_cls(g.ga, dc, n, S, E, st));
   }
   for (int l = c.n_layers - 1; l >= 0; --l) {
+    const int stage = c.n_layers - l;
+    if (stage < s0 || stage >= s1) continue;
     TowerLayer& L = t.L[l];
     LayerGrads& lg = g.L[l];
     const int ls = GG_P_LAYER0 + GG_L_COUNT * l;
@@ -804,6 +813,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     GG_TRY(e.dgrad(0, rows, E, 3 * E, Op{lg.gqkv, 3 * E}, e.W(net, ls + GG_L_IN_W), Epi().res(lg.gz1, E).obf(g.ga, E)));
     GG_TRY(e.flush_grads());
   }
+  if (tail_stage < s0 || tail_stage >= s1) return e.flush_grads();
   // X0 = [cls | patch projections], replicas share the projections
   GG_TRY(e.bgrad(g.ga, static_cast<int64_t>(S) * E, n, E, e.Gr(net, GG_P_CLS)));  // d cls = sum over the CLS rows
   GG_TRY(k_unassemble_tokens(g.ga, g.dpe, nullptr, Rg, B, S, E, st));
@@ -1038,7 +1048,9 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
 // phase 0: whole step; 1: forward + trunk backward (trunk gradients final on return); 2: tower backward
 static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int training, int phase, void* stream) {
   GG_REQUIRE(e && z && alpha, "null argument");
-  GG_REQUIRE(phase >= 0 && phase <= 2, "bad phase %d", phase);
+  const bool no_join = (phase & GG_PHASE_NO_JOIN) != 0;  // side lanes stay open: a later call joins them
+  phase &= ~GG_PHASE_NO_JOIN;
+  GG_REQUIRE((phase >= 0 && phase <= 2) || (phase >= GG_PHASE_STAGE0 && phase < GG_PHASE_STAGE0 + 16), "bad phase %d", phase);
   e->begin(stream);
   cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
@@ -1048,9 +1060,10 @@ static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int
   const int R = p > 0.f ? 3 : 1;   // independently-dropped tower passes: fake, real, interpolated
   const int Rg = p > 0.f ? 2 : 1;  // replicas that carry gradient (the GP's tower gradient is zero)
   const float inv_b = 1.f / static_cast<float>(B);
-  if (phase == 2) {
-    if (e->cond) GG_TRY(tower_backward(*e, net, Rg, p, e->gs.dc));
-    return e->join_all();
+  if (phase >= 2) {
+    const int s0 = phase == 2 ? 0 : phase - GG_PHASE_STAGE0;
+    if (e->cond) GG_TRY(tower_backward(*e, net, Rg, p, e->gs.dc, s0, phase == 2 ? (1 << 20) : s0 + 1));
+    return no_join ? GG_OK : e->join_all();
   }
   GG_TRY(k_bump_rng(e->rng, st));
   // ---- forward: G(z) (no graph) on lane 1 next to the critic tower on lane 0; D on fake / real /
@@ -1102,7 +1115,7 @@ static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int
   GG_TRY(e->bgrad(t.da1, H, 2 * B, H, e->Gr(net, GG_P_TR0_B)));
   GG_TRY(e->flush_grads());
   if (phase == 0 && e->cond) GG_TRY(tower_backward(*e, net, Rg, p, e->gs.dc));
-  return e->join_all();
+  return no_join ? GG_OK : e->join_all();
 }
 
 extern "C" int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream) {
@@ -1110,13 +1123,15 @@ extern "C" int gg_engine_disc_grads(gg_engine* e, const float* z, const float* a
 }
 extern "C" int gg_engine_disc_grads_phase(gg_engine* e, const float* z, const float* alpha, int training, int phase,
                                           void* stream) {
-  GG_REQUIRE(phase == 1 || phase == 2, "phase must be 1 or 2");
+  GG_REQUIRE(phase != 0, "phase 0 is gg_engine_disc_grads");
   return disc_grads_impl(e, z, alpha, training, phase, stream);
 }
 
 static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase, void* stream) {
   GG_REQUIRE(e && z, "null argument");
-  GG_REQUIRE(phase >= 0 && phase <= 2, "bad phase %d", phase);
+  const bool no_join = (phase & GG_PHASE_NO_JOIN) != 0;
+  phase &= ~GG_PHASE_NO_JOIN;
+  GG_REQUIRE((phase >= 0 && phase <= 2) || (phase >= GG_PHASE_STAGE0 && phase < GG_PHASE_STAGE0 + 16), "bad phase %d", phase);
   e->begin(stream);
   cudaStream_t st = e->S(0);
   const gg_model_cfg& c = e->cfg;
@@ -1126,9 +1141,10 @@ static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase,
   const float p = (training && e->cond && !e->concat) ? c.dropout_p : 0.f;
   const float inv_b = 1.f / static_cast<float>(B);
   const int D = GG_NET_DISC, Gn = GG_NET_GEN;
-  if (phase == 2) {
-    if (e->cond) GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc));
-    return e->join_all();
+  if (phase >= 2) {
+    const int s0 = phase == 2 ? 0 : phase - GG_PHASE_STAGE0;
+    if (e->cond) GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc, s0, phase == 2 ? (1 << 20) : s0 + 1));
+    return no_join ? GG_OK : e->join_all();
   }
   GG_TRY(k_bump_rng(e->rng, st));
   // ---- forward: fake = G(z) on lane 0, the critic's tower (conditioning only) next to it on lane 1,
@@ -1168,14 +1184,30 @@ static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase,
   }
   GG_TRY(e->flush_grads());
   if (e->cond && phase == 0) GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc));
-  return e->join_all();
+  return no_join ? GG_OK : e->join_all();
+}
+
+// Makes `stream` (the trainer's communication stream) wait for everything enqueued so far on the engine's side
+// lanes — the weight- / bias-gradient work of the stages run with GG_PHASE_NO_JOIN — without joining them into the
+// caller's stream: the all-reduce of a finished bucket then starts behind its producers while lane 0 moves on.
+extern "C" int gg_engine_lanes_signal(gg_engine* e, void* stream) {
+  GG_REQUIRE(e && stream, "null argument");
+  cudaStream_t dst = reinterpret_cast<cudaStream_t>(stream);
+  for (int l = 1; l < gg_engine::NLANES; ++l) {
+    if (!e->forked[e->L(l)] || e->L(l) == 0) continue;
+    cudaEvent_t ev = e->evs[e->ev_next];
+    e->ev_next = (e->ev_next + 1) % gg_engine::NEVENTS;
+    GG_CUDA_CHECK(cudaEventRecord(ev, e->cur[l]));
+    GG_CUDA_CHECK(cudaStreamWaitEvent(dst, ev, 0));
+  }
+  return GG_OK;
 }
 
 extern "C" int gg_engine_gen_grads(gg_engine* e, const float* z, int training, void* stream) {
   return gen_grads_impl(e, z, training, 0, stream);
 }
 extern "C" int gg_engine_gen_grads_phase(gg_engine* e, const float* z, int training, int phase, void* stream) {
-  GG_REQUIRE(phase == 1 || phase == 2, "phase must be 1 or 2");
+  GG_REQUIRE(phase != 0, "phase 0 is gg_engine_gen_grads");
   return gen_grads_impl(e, z, training, phase, stream);
 }
 

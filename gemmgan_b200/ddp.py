@@ -69,6 +69,41 @@ def plan_buckets(offsets: dict, n_used: int, first_slots: Sequence[int], names=(
     return out
 
 
+def plan_stage_buckets(offsets: dict, n_used: int, trunk_slots: Sequence[int], layer0: int, layer_count: int,
+                       n_layers: int, cross_slots: Sequence[int]) -> List[Tuple[int, Bucket]]:
+    """Buckets in the order the staged backward finishes them, as (stage, bucket) pairs: stage -1 = trunk (after
+    phase 1), 0 = cross-attention tail, 1 .. n_layers = encoder layers from the last to the first, n_layers + 1 =
+    the embedding tensors (slots below the first layer: FiLM / text / patch encoders, CLS). Slots are laid out in
+    increasing slot order, so each group is one contiguous range; groups a variant does not have are skipped."""
+    def span(slots):
+        present = sorted(offsets[s] for s in slots if s in offsets)
+        return (present[0], present[-1]) if present else None
+
+    starts = sorted(set(offsets.values())) + [n_used]
+
+    def end_of(last_start):
+        return starts[starts.index(last_start) + 1]
+
+    out: List[Tuple[int, Bucket]] = []
+    sp = span(trunk_slots)
+    if sp:
+        out.append((-1, Bucket("trunk", sp[0], end_of(sp[1]))))
+    sp = span(cross_slots)
+    if sp:
+        out.append((0, Bucket("cross", sp[0], end_of(sp[1]))))
+    for k in range(1, n_layers + 1):
+        layer = n_layers - k
+        sp = span(range(layer0 + layer_count * layer, layer0 + layer_count * (layer + 1)))
+        if sp:
+            out.append((k, Bucket(f"layer{layer}", sp[0], end_of(sp[1]))))
+    sp = span(range(0, layer0))
+    if sp:
+        out.append((n_layers + 1, Bucket("embed", sp[0], end_of(sp[1]))))
+    covered = sum(b.stop - b.start for _, b in out)
+    assert covered == n_used, f"stage buckets cover {covered} of {n_used} gradient elements"
+    return out
+
+
 class GradBuckets:
     """All-reduce(mean) of contiguous slices of one flat gradient tensor, asynchronously.
 
@@ -88,8 +123,9 @@ class GradBuckets:
     def bytes(self) -> List[int]:
         return [v.numel() * v.element_size() for v in self.views]
 
-    def reduce(self, i: int) -> None:
-        """Start the all-reduce of bucket i; everything enqueued so far on the current stream produces it."""
+    def reduce(self, i: int, also_wait: Optional[Callable[[object], None]] = None) -> None:
+        """Start the all-reduce of bucket i; everything enqueued so far on the current stream produces it.
+        also_wait(comm_stream): extra producers the communication stream has to wait for (the engine's side lanes)."""
         d = dist_or_none()
         if d is None:
             return
@@ -98,6 +134,8 @@ class GradBuckets:
             ready = torch.cuda.Event()
             ready.record()
             self.comm_stream.wait_event(ready)
+            if also_wait is not None:
+                also_wait(self.comm_stream)
             with torch.cuda.stream(self.comm_stream):
                 d.all_reduce(v, op=d.ReduceOp.AVG, group=self.group)
                 done = torch.cuda.Event()

@@ -232,6 +232,10 @@ class Engine:
         else:
             _lib.check(self.lib.gg_engine_gen_grads_phase(self.handle, _ptr(z), int(training), phase, _stream()))
 
+    def lanes_signal(self, stream: torch.cuda.Stream) -> None:
+        """`stream` waits for the engine's side lanes (gg_engine_lanes_signal)."""
+        _lib.check(self.lib.gg_engine_lanes_signal(self.handle, C.c_void_p(stream.cuda_stream)))
+
     def optim_step(self, net: int, lr: float) -> None:
         _lib.check(self.lib.gg_engine_optim_step(self.handle, net, float(lr), _stream()))
 

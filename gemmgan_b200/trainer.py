@@ -100,6 +100,7 @@ class TrainerBase:
         self.gemm_impl = _lib.IMPL_TCGEN05
         self.dp_overlap = os.environ.get("GEMMGAN_DP_OVERLAP", "1") != "0"
         self.dp_graph_collectives = os.environ.get("GEMMGAN_DP_GRAPH", "1") != "0"
+        self.dp_stage_buckets = os.environ.get("GEMMGAN_DP_STAGES", "1") != "0"
         self.dp_global_noise = False   # draw z/alpha for the GLOBAL batch and slice (N-rank == 1-rank parity)
         self.use_cuda_graphs = os.environ.get("GEMMGAN_CUDA_GRAPHS", "1") != "0"
         self.noise_upfront = os.environ.get("GEMMGAN_NOISE_UPFRONT", "1") != "0"
@@ -263,6 +264,18 @@ class TrainerBase:
             gb = flat._buckets = GradBuckets(flat.grads, plan_buckets(flat.offsets, flat.n_used, trunk))
         return gb
 
+    def _stage_buckets(self, flat: FlatNet):
+        from .ddp import GradBuckets, plan_stage_buckets
+
+        sb = getattr(flat, "_stage_buckets", None)
+        if sb is None:
+            trunk = (A.P_TR0_W, A.P_TR0_B, A.P_TR1_W, A.P_TR1_B, A.P_FIN_W, A.P_FIN_B)
+            cross = tuple(range(A.P_P2T_IN_W, A.P_T2P_OUT_B + 1))
+            plan = plan_stage_buckets(flat.offsets, flat.n_used, trunk, A.P_LAYER0, A.L_COUNT, 2, cross)
+            sb = flat._stage_buckets = GradBuckets(flat.grads, [b for _, b in plan])
+            sb.plan = plan
+        return sb
+
     def _step(self, eng: Engine, tag, net, flat, lr, grads_fn):
         """grads_fn(phase): phase 0 = whole backward, 1 = forward + trunk backward, 2 = tower backward."""
         lr = float(lr)
@@ -275,6 +288,28 @@ class TrainerBase:
         # data parallel: the trunk bucket (over half of the net: one [H, G] matrix) is all-reduced on the
         # communication stream while the fusion-tower backward runs; the tower bucket follows it; the
         # optimizer kernel waits for both
+        if self.dp_overlap and self.dp_graph_collectives and self.dp_stage_buckets and self.variant != "vanilla":
+            # staged backward: trunk, cross-attention tail, each encoder layer and the embedding tensors are reduced
+            # as soon as their producers have been enqueued; the side lanes are not joined in between (the
+            # communication stream waits for them directly), only the last, small bucket is exposed
+            sb = self._stage_buckets(flat)
+            stages = {st: i for i, (st, _) in enumerate(sb.plan)}
+            n_stages = 2 + 2   # head, two encoder layers, embedding tail
+
+            def body():
+                nj = A.PHASE_NO_JOIN
+                grads_fn(1 | nj)
+                if -1 in stages:
+                    sb.reduce(stages[-1], eng.lanes_signal)
+                for st in range(n_stages):
+                    last = st == n_stages - 1
+                    grads_fn((A.PHASE_STAGE0 + st) | (0 if last else nj))
+                    if st in stages:
+                        sb.reduce(stages[st], None if last else eng.lanes_signal)
+                sb.wait()
+                eng.optim_step(net, lr)
+            self._replay(eng, (tag + "_dps", lr), body)
+            return
         gb = self._buckets(flat)
         split = len(gb.buckets) > 1 and self.dp_overlap
         if self.dp_graph_collectives:

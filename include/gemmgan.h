@@ -240,10 +240,18 @@ int gg_engine_gen_grads(gg_engine* e, const float* z, int training, void* stream
 /* The same steps in two halves, for data-parallel runs that overlap the gradient all-reduce with the rest of
  * the backward: phase 1 = forward + trunk backward (on return every trunk gradient — slots GG_P_TR0_W ..
  * GG_P_FIN_B, one contiguous range at the end of `grads` — is final), phase 2 = fusion-tower backward (the
- * remaining slots). Phase 2 must follow phase 1 of the same step on the same stream. */
+ * remaining slots). Phase 2 must follow phase 1 of the same step on the same stream.
+ * Finer cut: phase GG_PHASE_STAGE0 + s runs stage s of the tower backward alone (s = 0: cross-attention tail — slots
+ * GG_P_P2T_* / GG_P_T2P_* and the text encoder final; s = 1 .. n_layers: encoder layers from the last to the first
+ * — that layer's 12 slots final; s = n_layers + 1: CLS / patch encoder / FiLM — slots 0..6 final). OR-ing
+ * GG_PHASE_NO_JOIN leaves the side lanes open when the call returns (a later call without it joins them); the
+ * trainer then orders its communication stream behind them with gg_engine_lanes_signal and lets lane 0 run on. */
+#define GG_PHASE_STAGE0 16
+#define GG_PHASE_NO_JOIN 64
 int gg_engine_disc_grads_phase(gg_engine* e, const float* z, const float* alpha, int training, int phase,
                                void* stream);
 int gg_engine_gen_grads_phase(gg_engine* e, const float* z, int training, int phase, void* stream);
+int gg_engine_lanes_signal(gg_engine* e, void* stream);
 /* clip_grad_norm_ (if configured) + optimizer.step() on the flat buffers + shadow refresh.
  * In data-parallel runs the caller all-reduces `grads` between *_grads and this call. */
 int gg_engine_optim_step(gg_engine* e, int net, float lr, void* stream);

@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from gemmgan_b200 import _abi_decl as A
-from gemmgan_b200.ddp import Bucket, GradBuckets, global_noise, plan_buckets
+from gemmgan_b200.ddp import Bucket, GradBuckets, global_noise, plan_buckets, plan_stage_buckets
 
 TRUNK = (A.P_TR0_W, A.P_TR0_B, A.P_TR1_W, A.P_TR1_B, A.P_FIN_W, A.P_FIN_B)
 
@@ -30,6 +30,30 @@ def test_plan_buckets_trunk_first():
     # vanilla: trunk tensors only -> one bucket covering everything
     b = plan_buckets({A.P_TR0_W: 0, A.P_FIN_B: 512}, 576, TRUNK)
     assert [(x.start, x.stop) for x in b] == [(0, 576)]
+
+
+def test_plan_stage_buckets_paper_and_film_layouts():
+    cross = tuple(range(A.P_P2T_IN_W, A.P_T2P_OUT_B + 1))
+    # paper-like layout: every slot present, 64 elements each
+    offsets = {s: 64 * i for i, s in enumerate(range(A.NSLOTS))}
+    plan = plan_stage_buckets(offsets, 64 * A.NSLOTS, TRUNK, A.P_LAYER0, A.L_COUNT, 2, cross)
+    assert [st for st, _ in plan] == [-1, 0, 1, 2, 3]
+    assert [b.name for _, b in plan] == ["trunk", "cross", "layer1", "layer0", "embed"]
+    spans = sorted((b.start, b.stop) for _, b in plan)
+    assert spans[0][0] == 0 and spans[-1][1] == 64 * A.NSLOTS
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))          # contiguous, disjoint, complete
+    by = {b.name: b for _, b in plan}
+    assert by["layer1"].start == offsets[A.P_LAYER0 + A.L_COUNT] and by["cross"].start == offsets[A.P_P2T_IN_W]
+    # film-like layout: no text encoder, no cross-attention, bias-free layers (only the weight slots present)
+    slots = [A.P_FILM_W, A.P_FILM_B, A.P_PATCH_W, A.P_PATCH_B, A.P_CLS]
+    for layer in range(2):
+        base = A.P_LAYER0 + A.L_COUNT * layer
+        slots += [base + A.L_IN_W, base + A.L_OUT_W, base + A.L_FF1_W, base + A.L_FF2_W, base + A.L_N1_W, base + A.L_N2_W]
+    slots += list(TRUNK)
+    offsets = {s: 128 * i for i, s in enumerate(sorted(slots))}
+    plan = plan_stage_buckets(offsets, 128 * len(slots), TRUNK, A.P_LAYER0, A.L_COUNT, 2, cross)
+    assert [st for st, _ in plan] == [-1, 1, 2, 3]
+    assert sum(b.stop - b.start for _, b in plan) == 128 * len(slots)
 
 
 def test_plan_buckets_rejects_tower_behind_trunk():
