@@ -89,9 +89,9 @@ class WGAN_GP(TrainerBase):
         dev = self.device
         B = patches.shape[0]
         eng = self._engine_for(B, patches, text_token)
-        eng.set_batch(genes=None if genes is None else genes.to(dev, non_blocking=True), patches=patches.to(dev, non_blocking=True),
-                      patch_pad=padding_mask.to(dev, non_blocking=True), text=text_token.to(dev, non_blocking=True),
-                      text_pad=text_token_padding.to(dev, non_blocking=True))
+        eng.set_batch(genes=None if genes is None else self._dev(genes), patches=self._dev(patches),
+                      patch_pad=self._dev(padding_mask), text=self._dev(text_token),
+                      text_pad=self._dev(text_token_padding))
         return eng
 
     # ---- reference-signature entry points -------------------------------------------------
@@ -111,9 +111,11 @@ class WGAN_GP(TrainerBase):
         eng = self._stage(None, text_token, text_token_padding, patches, padding_mask)
         self._train_gen_staged(eng, z.to(self.device))
 
-    def train(self, gene_expression, text_token, text_token_padding, patches, padding_mask, zs=None, alphas=None):
+    def train(self, gene_expression, text_token, text_token_padding, patches, padding_mask, zs=None, alphas=None, prefetch=None):
         eng = self._stage(gene_expression, text_token, text_token_padding, patches, padding_mask)
         self._train_staged(eng, zs, alphas)
+        if prefetch is not None:   # host tensors of the NEXT batch: their H2D copies overlap this step
+            self.prefetch(*prefetch)
 
     def _module_forward(self, module, x, patches, patches_padding_mask, text_tokens, text_padding_mask):
         eng = self._stage(None, text_tokens, text_padding_mask, patches, patches_padding_mask)
@@ -158,8 +160,8 @@ class WGAN_GP(TrainerBase):
             self._epoch_lr_decay(epoch, 100)  # both LRs halve every 100 epochs [:649-657]
             self.epoch = epoch
             d_sum, g_sum, n = 0.0, 0.0, 0
-            for i, data in enumerate(train_data):
-                self.train(data[2], data[0], data[1], data[3], data[4])
+            for i, (data, nxt) in enumerate(self._lookahead(train_data)):
+                self.train(data[2], data[0], data[1], data[3], data[4], prefetch=None if nxt is None else (nxt[2], nxt[0], nxt[1], nxt[3], nxt[4]))
                 d_sum, g_sum, n = d_sum + self.d_batch_loss, g_sum + self.g_batch_loss, n + 1
                 if (i + 1) % self.freq_print == 0:
                     print('[Epoch %d/%d] [Batch %d/%d] [D loss : %f] [G loss : %f]' %
@@ -172,8 +174,8 @@ class WGAN_GP(TrainerBase):
             last = epoch == epochs - 1
             if self.result_dire and ((epoch + 1) % self.freq_compute_test == 0 or last):
                 tag = 'last_epoch' if last else f'epoch_{epoch + 1}'
-                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, f'gen_{tag}.pt'))
-                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, f'disc_{tag}.pt'))
+                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, f'generator_{tag}.pt'))
+                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, f'discriminator_{tag}.pt'))
 
 
 def parse_args():

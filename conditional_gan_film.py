@@ -79,8 +79,8 @@ class WGAN_GP(TrainerBase):
             self._tokens = patches.shape[1]
             self._engines.clear()
         eng = self._engine(patches.shape[0])
-        eng.set_batch(genes=None if genes is None else genes.to(dev, non_blocking=True), patches=patches.to(dev, non_blocking=True),
-                      patch_pad=padding_mask.to(dev, non_blocking=True), text=text_embedding.to(dev, non_blocking=True),
+        eng.set_batch(genes=None if genes is None else self._dev(genes), patches=self._dev(patches),
+                      patch_pad=self._dev(padding_mask), text=self._dev(text_embedding),
                       text_pad=None)
         return eng
 
@@ -100,9 +100,11 @@ class WGAN_GP(TrainerBase):
         eng = self._stage(None, text_embedding, patches, padding_mask)
         self._train_gen_staged(eng, z.to(self.device))
 
-    def train(self, gene_expression, text_embedding, patches, padding_mask, zs=None, alphas=None):
+    def train(self, gene_expression, text_embedding, patches, padding_mask, zs=None, alphas=None, prefetch=None):
         eng = self._stage(gene_expression, text_embedding, patches, padding_mask)
         self._train_staged(eng, zs, alphas)
+        if prefetch is not None:   # host tensors of the NEXT batch: their H2D copies overlap this step
+            self.prefetch(*prefetch)
 
     def _module_forward(self, module, x, text_embedding, patches, padding_mask):
         eng = self._stage(None, text_embedding, patches, padding_mask)
@@ -145,8 +147,8 @@ class WGAN_GP(TrainerBase):
             self._epoch_lr_decay(epoch, 100)
             self.epoch = epoch
             d_sum, g_sum, n = 0.0, 0.0, 0
-            for i, data in enumerate(train_data):
-                self.train(data[1], data[0], data[2], data[3])
+            for i, (data, nxt) in enumerate(self._lookahead(train_data)):
+                self.train(data[1], data[0], data[2], data[3], prefetch=None if nxt is None else (nxt[1], nxt[0], nxt[2], nxt[3]))
                 d_sum, g_sum, n = d_sum + self.d_batch_loss, g_sum + self.g_batch_loss, n + 1
                 if (i + 1) % self.freq_print == 0:
                     print('[Epoch %d/%d] [Batch %d/%d] [D loss : %f] [G loss : %f]' %
@@ -159,8 +161,8 @@ class WGAN_GP(TrainerBase):
             last = epoch == epochs - 1
             if self.result_dire and ((epoch + 1) % self.freq_compute_test == 0 or last):
                 tag = 'last_epoch' if last else f'epoch_{epoch + 1}'
-                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, f'gen_{tag}.pt'))
-                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, f'disc_{tag}.pt'))
+                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, f'generator_{tag}.pt'))
+                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, f'discriminator_{tag}.pt'))
 
 
 def parse_args():

@@ -107,6 +107,7 @@ class TrainerBase:
         self.unique_graphs = False
         self._graph_seq = 0
         self._replay_events = []
+        self._copy_stream, self._prefetched, self._prefetch_event = None, {}, None
         self._engines = {}
         self._flat_gen = self._flat_disc = None
         self._pinned = None
@@ -158,6 +159,43 @@ class TrainerBase:
         else:
             eng.sync_external_param_writes()
         return eng
+
+    # ---- host -> device staging ----------------------------------------------------------
+    def prefetch(self, *tensors):
+        """Starts the host->device copies of the NEXT batch's tensors on a copy stream, so that they overlap the
+        step that is running; the next train() / train_disc() call that receives these same host tensors picks the
+        device copies up (pass pinned tensors: pageable ones are copied synchronously by CUDA)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._prefetched.clear()
+        with torch.cuda.stream(self._copy_stream):
+            for t in tensors:
+                if isinstance(t, torch.Tensor) and not t.is_cuda:
+                    self._prefetched[(t.data_ptr(), tuple(t.shape), t.dtype)] = t.to(self.device, non_blocking=True)
+            self._prefetch_event = torch.cuda.Event()
+            self._prefetch_event.record()
+
+    @staticmethod
+    def _lookahead(loader):
+        """(batch, next batch or None) pairs: fit() hands the next batch to train(prefetch=...)."""
+        it = iter(loader)
+        cur = next(it, None)
+        while cur is not None:
+            nxt = next(it, None)
+            yield cur, nxt
+            cur = nxt
+
+    def _dev(self, t):
+        """Device copy of one batch tensor: the prefetched copy when there is one, else an async copy now."""
+        if t is None or t.is_cuda:
+            return t
+        hit = self._prefetched.pop((t.data_ptr(), tuple(t.shape), t.dtype), None)
+        if hit is None:
+            return t.to(self.device, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._prefetch_event)
+        hit.record_stream(cur)
+        return hit
 
     # ---- noise --------------------------------------------------------------------------
     def _normal(self, B):

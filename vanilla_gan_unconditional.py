@@ -12,6 +12,7 @@ hot path and not reproduced here.
 from __future__ import annotations
 
 import argparse
+import os
 
 import numpy as np
 import torch
@@ -85,11 +86,13 @@ class WGAN_GP_nocond(TrainerBase):
         eng = self._engine(z.shape[0])
         self._train_gen_staged(eng, z.to(self.device))
 
-    def train(self, x_GE, zs=None, alphas=None):
-        x_real = x_GE.to(self.device, non_blocking=True)
+    def train(self, x_GE, zs=None, alphas=None, prefetch=None):
+        x_real = self._dev(x_GE)
         eng = self._engine(x_real.shape[0])
         eng.set_batch(genes=x_real)
         self._train_staged(eng, zs, alphas)
+        if prefetch is not None:   # host tensors of the NEXT batch: their H2D copies overlap this step
+            self.prefetch(*prefetch)
 
     def _module_forward(self, module, x):
         eng = self._engine(x.shape[0])
@@ -123,9 +126,9 @@ class WGAN_GP_nocond(TrainerBase):
             self._epoch_lr_decay(epoch, 50)  # vanilla halves both LRs every 50 epochs (:558)
             self.epoch = epoch
             d_sum, g_sum, n = 0.0, 0.0, 0
-            for i, data in enumerate(train_data):
-                x = data[0] if isinstance(data, (list, tuple)) else data
-                self.train(x.to(self.device))
+            first = lambda d: d[0] if isinstance(d, (list, tuple)) else d  # noqa: E731
+            for i, (data, nxt) in enumerate(self._lookahead(train_data)):
+                self.train(first(data), prefetch=None if nxt is None else (first(nxt),))
                 d_sum, g_sum, n = d_sum + self.d_batch_loss, g_sum + self.g_batch_loss, n + 1
                 if (i + 1) % self.freq_print == 0:
                     print('[Epoch %d/%d] [Batch %d/%d] [D loss : %f] [G loss : %f]' %
@@ -135,6 +138,9 @@ class WGAN_GP_nocond(TrainerBase):
             self.loss_dict['d real loss'].append(d_mean[1])
             self.loss_dict['d fake loss'].append(d_mean[2])
             self.loss_dict['g loss'].append((g_sum / max(n, 1))[0])
+            if self.result_dire and epoch == epochs - 1:   # reference :614-615
+                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, 'generator_last_epoch.pt'))
+                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, 'discriminator_last_epoch.pt'))
 
 
 def parse_args():
