@@ -991,6 +991,284 @@ static int launch_mid(const AttnArgs& a, cudaStream_t st) {
   return launch_mid_nt<MODE, 8>(a, st);
 }
 
+// ------------------------------------------------- long self-attention, head_dim 64 (129 <= S <= 320)
+// The encoder layers at the scripts' default of 256 patches (BASELINE config 2: S = 257). Same one-CTA-per-(sequence,
+// head) staging as the mid-size kernel, but a 16 x S score row-block no longer fits in registers: the key tiles are
+// streamed with an online softmax (running row maximum / sum, output rescaled), flash-attention style. Backward,
+// everything recomputed from Q, K, V, dO, O: phase 1 (warp = query tile) re-derives the row statistics, forms
+// delta_i = dO_i . O_i (valid with dropout: O already carries the mask) and accumulates dQ; phase 2 (warp = key
+// tile) walks the query tiles with the transposed products S^T = K Q^T, dP^T = V dO^T straight in accumulator
+// fragments, so dK = dS^T Q and dV = P^T dO need no shared-memory copies of dS / P. No atomics, deterministic.
+constexpr int LONG_WARPS = 8;
+constexpr int LONG_MAXT = 20;  // S <= 320
+
+template <int MODE>
+__global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const AttnArgs a) {
+  pdl_entry();
+  extern __shared__ __align__(16) uint8_t smem_long[];
+  const int S = a.Lq;
+  const int NT = (S + 15) / 16;
+  const int ROWS = NT * 16;
+  constexpr int NTEN = MODE == 1 ? 4 : 3;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_long);
+  bf16* Ks = Qs + ROWS * SELF_PITCH;
+  bf16* Vs = Ks + ROWS * SELF_PITCH;
+  bf16* Gs = Vs + ROWS * SELF_PITCH;                   // dO (backward only)
+  bf16* stage_all = Qs + NTEN * ROWS * SELF_PITCH;     // one 16-row staging tile per warp
+  float* row_m = reinterpret_cast<float*>(stage_all + LONG_WARPS * SELF_TILE);  // backward: per query row
+  float* row_il = row_m + ROWS;
+  float* row_delta = row_il + ROWS;
+  uint8_t* kval = reinterpret_cast<uint8_t*>(row_delta + ROWS);                 // key j usable (in range, not padded)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = static_cast<int>(blockIdx.x) / a.H, h = static_cast<int>(blockIdx.x) % a.H;
+  const uint8_t* mk = a.mask ? a.mask + static_cast<int64_t>(b % a.mask_mod) * S : nullptr;
+  {
+    const int col = h * SELF_HD;
+    const int64_t qb = static_cast<int64_t>(a.q_mod >= a.nb ? b : b % a.q_mod) * S;
+    const int64_t kb = static_cast<int64_t>(a.kv_mod >= a.nb ? b : b % a.kv_mod) * S;
+    for (int idx = threadIdx.x; idx < ROWS * 8; idx += LONG_WARPS * 32) {
+      const int row = idx >> 3, part = idx & 7;
+      const bool valid = row < S;
+      bf16* dst = Qs + row * SELF_PITCH + part * 8;
+      cp_async16(dst, valid ? a.q + (qb + row) * a.ldq + col + part * 8 : a.q, valid);
+      cp_async16(dst + ROWS * SELF_PITCH, valid ? a.k + (kb + row) * a.ldkv + col + part * 8 : a.q, valid);
+      cp_async16(dst + 2 * ROWS * SELF_PITCH, valid ? a.v + (kb + row) * a.ldkv + col + part * 8 : a.q, valid);
+      if (MODE == 1)
+        cp_async16(dst + 3 * ROWS * SELF_PITCH,
+                   valid ? a.dout + (static_cast<int64_t>(b) * S + row) * a.lddo + col + part * 8 : a.q, valid);
+    }
+    for (int j = threadIdx.x; j < ROWS; j += LONG_WARPS * 32) kval[j] = (j < S && !(mk && mk[j])) ? 1 : 0;
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  const float scale = 0.125f;
+  const int g = lane >> 2, t = lane & 3;
+  bf16* stage = stage_all + warp * SELF_TILE;
+  const bool drop = a.drop_p > 0.f;
+  uint64_t seed = 0, step = 0;
+  if (drop) {
+    seed = a.rng[0];
+    step = a.rng[1];
+  }
+  const float keep_scale = drop ? 1.f / (1.f - a.drop_p) : 1.f;
+  const uint64_t head_base = (static_cast<uint64_t>(b) * a.H + h) * static_cast<uint64_t>(S);  // + i -> row of P
+  // this thread's 4 key columns of a key tile: j = kt*16 + (e>>1)*8 + 2t + (e&1)
+  auto key_of = [&](int kt, int e) { return kt * 16 + (e >> 1) * 8 + 2 * t + (e & 1); };
+
+  for (int qt = warp; qt < NT; qt += LONG_WARPS) {
+    const bf16* Qt = Qs + qt * SELF_TILE;
+    const int rows_valid = min(16, S - qt * 16);
+    // ---- online softmax statistics (and, forward, the output) over the key tiles
+    float m_run[2] = {-INFINITY, -INFINITY}, l_thr[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[n][j] = 0.f;
+    for (int kt = 0; kt < NT; ++kt) {
+      float sc[2][4];
+      mma_ab_t(sc, Qt, Ks + kt * SELF_TILE, lane);
+      float pv[2][4];
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        float tm = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v = kval[key_of(kt, e)] ? sc[e >> 1][rh * 2 + (e & 1)] * scale : -INFINITY;
+          pv[rh][e] = v;
+          tm = fmaxf(tm, v);
+        }
+        tm = quad_max(tm);
+        const float m_new = fmaxf(m_run[rh], tm);
+        const float corr = m_new == -INFINITY ? 1.f : __expf(m_run[rh] - m_new);  // m_run = -inf -> 0
+        m_run[rh] = m_new;
+        float ls = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          pv[rh][e] = pv[rh][e] == -INFINITY ? 0.f : __expf(pv[rh][e] - m_new);
+          ls += pv[rh][e];
+        }
+        l_thr[rh] = l_thr[rh] * corr + ls;
+        if (MODE == 0) {
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            o[n][rh * 2] *= corr;
+            o[n][rh * 2 + 1] *= corr;
+          }
+        }
+      }
+      if (MODE == 0) {
+        if (drop) {
+          DropoutStream ds(seed, step, a.site, a.drop_p);
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const int i = qt * 16 + g + rh * 8;
+            const uint64_t pbase = (head_base + i) * static_cast<uint64_t>(S);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = key_of(kt, e);
+              if (i < S && j < S) pv[rh][e] = ds.keep(pbase + j) ? pv[rh][e] * keep_scale : 0.f;
+            }
+          }
+        }
+        uint32_t pa[4];
+        pa[0] = pack_bf16(pv[0][0], pv[0][1]);
+        pa[1] = pack_bf16(pv[1][0], pv[1][1]);
+        pa[2] = pack_bf16(pv[0][2], pv[0][3]);
+        pa[3] = pack_bf16(pv[1][2], pv[1][3]);
+        mma_frag_b_acc(o, pa, Vs + kt * SELF_TILE, lane);
+      }
+    }
+    float inv_l[2];
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const float l = quad_add(l_thr[rh]);
+      inv_l[rh] = l > 0.f ? 1.f / l : 0.f;
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        o[n][0] *= inv_l[0]; o[n][1] *= inv_l[0];
+        o[n][2] *= inv_l[1]; o[n][3] *= inv_l[1];
+      }
+      store_tile(stage, o, 1.f, a.o + (static_cast<int64_t>(b) * S + qt * 16) * a.ldo + h * SELF_HD, a.ldo, rows_valid,
+                 lane);
+      continue;
+    }
+    // ---- backward, phase 1: delta_i = dO_i . O_i, then dQ
+    const bf16* Gt = Gs + qt * SELF_TILE;
+    {
+      const int r = lane >> 1, hf = lane & 1;  // row of the tile, half of the 64 head dims
+      float acc = 0.f;
+      if (r < rows_valid) {
+        const bf16* orow = a.o + (static_cast<int64_t>(b) * S + qt * 16 + r) * a.ldo + h * SELF_HD + hf * 32;
+        const bf16* grow = Gt + r * SELF_PITCH + hf * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 ov = __ldg(reinterpret_cast<const uint4*>(orow) + c);
+          const uint4 gv = *reinterpret_cast<const uint4*>(grow + c * 8);
+          const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&ov);
+          const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&gv);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 fx = __bfloat1622float2(x[q]), fy = __bfloat1622float2(y[q]);
+            acc = fmaf(fx.x, fy.x, acc);
+            acc = fmaf(fx.y, fy.y, acc);
+          }
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (hf == 0) row_delta[qt * 16 + r] = acc;
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const int i = qt * 16 + g + rh * 8;
+        row_m[i] = m_run[rh] == -INFINITY ? 0.f : m_run[rh];
+        row_il[i] = i < S ? inv_l[rh] : 0.f;  // rows beyond S contribute nothing in phase 2
+      }
+    }
+    __syncwarp();
+    const float delta[2] = {row_delta[qt * 16 + g], row_delta[qt * 16 + g + 8]};
+    for (int kt = 0; kt < NT; ++kt) {
+      float sc[2][4], dp[2][4];
+      mma_ab_t(sc, Qt, Ks + kt * SELF_TILE, lane);
+      mma_ab_t(dp, Gt, Vs + kt * SELF_TILE, lane);  // dP~ = dO V^T
+      float dsv[2][4];
+      DropoutStream ds(seed, step, a.site, a.drop_p);
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const int i = qt * 16 + g + rh * 8;
+        const uint64_t pbase = (head_base + i) * static_cast<uint64_t>(S);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = key_of(kt, e);
+          const float pij = kval[j] ? __expf(sc[e >> 1][rh * 2 + (e & 1)] * scale - m_run[rh]) * inv_l[rh] : 0.f;
+          float mult = 1.f;
+          if (drop && i < S && j < S) mult = ds.keep(pbase + j) ? keep_scale : 0.f;
+          dsv[rh][e] = pij * (dp[e >> 1][rh * 2 + (e & 1)] * mult - delta[rh]);
+        }
+      }
+      uint32_t da[4];
+      da[0] = pack_bf16(dsv[0][0], dsv[0][1]);
+      da[1] = pack_bf16(dsv[1][0], dsv[1][1]);
+      da[2] = pack_bf16(dsv[0][2], dsv[0][3]);
+      da[3] = pack_bf16(dsv[1][2], dsv[1][3]);
+      mma_frag_b_acc(o, da, Ks + kt * SELF_TILE, lane);  // dQ += dS K
+    }
+    store_tile(stage, o, scale, a.dq + (static_cast<int64_t>(b) * S + qt * 16) * a.lddq + h * SELF_HD, a.lddq,
+               rows_valid, lane);
+  }
+  if (MODE == 0) return;
+  __syncthreads();
+  // ---- backward, phase 2: warp = key tile; rows of the fragments are KEYS, columns are QUERIES
+  for (int kt = warp; kt < NT; kt += LONG_WARPS) {
+    const int rows_valid = min(16, S - kt * 16);
+    const bool kv0 = kval[kt * 16 + g] != 0, kv1 = kval[kt * 16 + g + 8] != 0;
+    float ok[8][4], ov[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ok[n][j] = ov[n][j] = 0.f;
+    for (int qt = 0; qt < NT; ++qt) {
+      float st[2][4], dpt[2][4];
+      mma_ab_t(st, Ks + kt * SELF_TILE, Qs + qt * SELF_TILE, lane);   // S^T = K Q^T
+      mma_ab_t(dpt, Vs + kt * SELF_TILE, Gs + qt * SELF_TILE, lane);  // dP~^T = V dO^T
+      float pT[2][4], dsT[2][4];  // [key row half][e]: query column i = qt*16 + (e>>1)*8 + 2t + (e&1)
+      DropoutStream ds(seed, step, a.site, a.drop_p);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = qt * 16 + (e >> 1) * 8 + 2 * t + (e & 1);
+        const float mi = row_m[i], il = row_il[i], dl = row_delta[i];
+        const uint64_t pbase = (head_base + i) * static_cast<uint64_t>(S);
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          const int j = kt * 16 + g + rh * 8;
+          const bool kv = rh == 0 ? kv0 : kv1;
+          const float pij = kv ? __expf(st[e >> 1][rh * 2 + (e & 1)] * scale - mi) * il : 0.f;
+          float mult = 1.f;
+          if (drop && i < S && j < S) mult = ds.keep(pbase + j) ? keep_scale : 0.f;
+          pT[rh][e] = pij * mult;
+          dsT[rh][e] = pij * (dpt[e >> 1][rh * 2 + (e & 1)] * mult - dl);
+        }
+      }
+      uint32_t fa[4];
+      fa[0] = pack_bf16(dsT[0][0], dsT[0][1]);
+      fa[1] = pack_bf16(dsT[1][0], dsT[1][1]);
+      fa[2] = pack_bf16(dsT[0][2], dsT[0][3]);
+      fa[3] = pack_bf16(dsT[1][2], dsT[1][3]);
+      mma_frag_b_acc(ok, fa, Qs + qt * SELF_TILE, lane);  // dK += dS^T Q
+      fa[0] = pack_bf16(pT[0][0], pT[0][1]);
+      fa[1] = pack_bf16(pT[1][0], pT[1][1]);
+      fa[2] = pack_bf16(pT[0][2], pT[0][3]);
+      fa[3] = pack_bf16(pT[1][2], pT[1][3]);
+      mma_frag_b_acc(ov, fa, Gs + qt * SELF_TILE, lane);  // dV += P~^T dO
+    }
+    store_tile(stage, ok, scale, a.dk + (static_cast<int64_t>(b) * S + kt * 16) * a.lddkv + h * SELF_HD, a.lddkv,
+               rows_valid, lane);
+    store_tile(stage, ov, 1.f, a.dv + (static_cast<int64_t>(b) * S + kt * 16) * a.lddkv + h * SELF_HD, a.lddkv,
+               rows_valid, lane);
+  }
+}
+
+template <int MODE>
+static int launch_long(const AttnArgs& a, cudaStream_t st) {
+  GG_REQUIRE(MODE == 0 || a.o != nullptr, "long self-attention backward needs the forward output (a.o)");
+  const int rows = (a.Lq + 15) / 16 * 16;
+  const size_t smem = static_cast<size_t>((MODE == 1 ? 4 : 3) * rows * SELF_PITCH + LONG_WARPS * SELF_TILE) * 2 +
+                      static_cast<size_t>(rows) * (3 * 4 + 1) + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    GG_CUDA_CHECK(cudaFuncSetAttribute(attn_self_long_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    configured = smem;
+  }
+  launch_k(attn_self_long_kernel<MODE>, static_cast<unsigned>(a.nb) * a.H, LONG_WARPS * 32, smem, st, a);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 // ------------------------------------------------- single-query cross-attention, head_dim 64, Lk <= 128
 // patch2text / text2patch attention of the paper model (Lq = 1; :149-152) at 64 patches / 32 text tokens. One WARP
 // per (row, head): lane l scores keys l, l+32, ... from their own 128-byte K rows, softmax by warp shuffles, the
@@ -1189,6 +1467,7 @@ int k_attention_fwd(const AttnArgs& a, cudaStream_t st) {
   if (rc) return rc;
   if (self_path(a)) return launch_self<0>(a, st);
   if (self_path(a, MID_MAXL)) return launch_mid<0>(a, st);
+  if (self_path(a, 16 * LONG_MAXT)) return launch_long<0>(a, st);
   if (q1_path(a)) return launch_q1<0>(a, st);
   if (small_path(a)) {
     launch_small_q<0>(a, nullptr, st);
@@ -1214,6 +1493,7 @@ int k_attention_bwd(const AttnArgs& a, cudaStream_t st) {
   if (rc) return rc;
   if (self_path(a)) return launch_self<1>(a, st);
   if (self_path(a, MID_MAXL)) return launch_mid<1>(a, st);
+  if (self_path(a, 16 * LONG_MAXT) && a.o) return launch_long<1>(a, st);  // needs the forward output for delta
   if (q1_path(a)) return launch_q1<1>(a, st);
   if (small_path(a)) {
     GG_REQUIRE(a.stat != nullptr, "short-sequence attention backward needs a stats scratch buffer");

@@ -804,6 +804,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     a.mask = e.mask_s; a.mask_mod = B;
     a.nb = n; a.H = c.n_heads; a.hd = e.hd; a.Lq = S; a.Lk = S;
     a.drop_p = p; a.rng = e.rng; a.site = site + 0;
+    a.o = L.ao; a.ldo = E;  // forward output (kept for the out-projection's weight gradient): delta_i = dO_i . O_i
     a.dout = g.gao; a.lddo = E; a.dq = lg.gqkv; a.lddq = 3 * E;
     a.dk = lg.gqkv + E; a.dv = lg.gqkv + 2 * E; a.lddkv = 3 * E;
     a.stat = e.attn_stat;
