@@ -999,7 +999,7 @@ static int launch_mid(const AttnArgs& a, cudaStream_t st) {
 // delta_i = dO_i . O_i (valid with dropout: O already carries the mask) and accumulates dQ; phase 2 (warp = key
 // tile) walks the query tiles with the transposed products S^T = K Q^T, dP^T = V dO^T straight in accumulator
 // fragments, so dK = dS^T Q and dV = P^T dO need no shared-memory copies of dS / P. No atomics, deterministic.
-constexpr int LONG_WARPS = 8;
+constexpr int LONG_WARPS = 16;  // 1 CTA per SM (shared memory): 16 warps hide the ldmatrix / mma latencies (8 warps: 1.24 / 3.08 ms at cfg2)
 constexpr int LONG_MAXT = 20;  // S <= 320
 
 template <int MODE>
