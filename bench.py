@@ -266,6 +266,47 @@ def main():
         _lib.check(L.gg_gemm_profile_dump(args.gemm_csv.encode()))
     for eng in t._engines.values():
         eng.set_lanes(True)             # drops the profiling graphs
+    # ---- supplement: the same launches timed from INSIDE the kernels (%globaltimer at body start / after the
+    # stores), in the real three-lane graphs. An event pair costs ~6 us around a ~6 us launch, so the event-based
+    # figure above understates the in-step efficiency of the ~250 one-tile launches; this one has no such overhead
+    # (but includes whatever the concurrently running lanes take away).
+    in_situ = None
+    try:
+        cap = 4096
+        stamps = torch.empty(cap, 2, dtype=torch.int64, device=dev)
+
+        def reset():
+            stamps[:, 0] = torch.iinfo(torch.int64).max
+            stamps[:, 1] = 0
+
+        for eng in t._engines.values():
+            eng.graphs.clear()
+        reset()
+        L.gg_gemm_set_timer(C.c_void_p(stamps.data_ptr()), cap)
+        t.train(*batch_dev)                  # capture (with stamp slots) + first replay
+        fl_a, by_a = (C.c_double * cap)(), (C.c_double * cap)()
+        n_slots = int(L.gg_gemm_timer_slots(fl_a, by_a, cap))
+        torch.cuda.synchronize()
+        reset()
+        t.train(*batch_dev)                  # replay only
+        torch.cuda.synchronize()
+        L.gg_gemm_set_timer(None, 0)
+        for eng in t._engines.values():
+            eng.graphs.clear()
+        st = stamps[:n_slots].cpu()
+        dur_ns = (st[:, 1] - st[:, 0]).clamp(min=0).double()
+        ok = (st[:, 1] > 0)
+        tot_s = float(dur_ns[ok].sum()) * 1e-9
+        fl_s = sum(fl_a[i] for i in range(n_slots) if ok[i])
+        by_s = sum(by_a[i] for i in range(n_slots) if ok[i])
+        if tot_s > 0:
+            in_situ = dict(launches=int(ok.sum()), gemm_ms=tot_s * 1e3, hbm_gbs=by_s / tot_s / 1e9,
+                           hbm_frac=by_s / tot_s / 1e9 / pk["hbm"], tensor_tflops=fl_s / tot_s / 1e12,
+                           tensor_frac=fl_s / tot_s / 1e12 / pk["tflops"],
+                           how="%globaltimer inside gemm_tc_kernel (body start -> stores issued), replayed three-lane graphs")
+    except Exception as exc:  # noqa: BLE001 - a diagnostic must not cost the bench line
+        in_situ = dict(error=repr(exc))
+
     # Roofline of the dominant kernel (gemm_tc_kernel): algorithmic work of the launches of one train() over their
     # summed CUDA-event durations. The step's products are skinny (K or N = 256): summed over the launches the
     # byte roofline (operands read once + outputs written once at the measured HBM copy bandwidth) is the larger
@@ -285,7 +326,7 @@ def main():
             traffic = float(json.load(f)["dram_bytes_per_launch"])
     except Exception:  # noqa: BLE001
         pass
-    common = dict(traffic=traffic, kernel="gemm_tc_kernel (tcgen05; every launch of one train(), CUDA-event pairs inside the replayed graph, one lane)",
+    common = dict(in_situ=in_situ, traffic=traffic, kernel="gemm_tc_kernel (tcgen05; every launch of one train(), CUDA-event pairs inside the replayed graph, one lane)",
                   gemm_launches_per_step=int(nl.value), gemm_ms_per_step=ms.value,
                   gemm_share_of_step=ms.value / ms_per_step, gemm_ms_over_profiled_call_ms=ms.value / profiled_call_ms,
                   profiled_call_ms=profiled_call_ms, flops_per_step=fl.value, bytes_per_step=by,

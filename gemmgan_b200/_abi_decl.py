@@ -108,6 +108,8 @@ def declare(L: C.CDLL) -> None:
     L.gg_gemm_profile_begin.argtypes = []
     L.gg_gemm_profile_dump.argtypes = [C.c_char_p]
     L.gg_gemm_set_trace.argtypes = [vp, i32]
+    L.gg_gemm_set_timer.argtypes = [vp, i32]
+    L.gg_gemm_timer_slots.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), i32]
     L.gg_gemm_profile_bytes.argtypes = []
     L.gg_gemm_profile_bytes.restype = C.c_double
     L.gg_gemm_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
@@ -118,6 +120,6 @@ EXPORTS = [
     "gg_engine_create", "gg_engine_destroy", "gg_engine_set_lanes", "gg_engine_refresh_shadows", "gg_engine_set_batch",
     "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_disc_grads_phase", "gg_engine_gen_grads_phase", "gg_engine_optim_step", "gg_engine_generate",
     "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_gp_step", "gg_masked_mean_rows", "gg_engine_lanes_signal", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
-    "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes",
+    "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",
     "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

@@ -39,6 +39,7 @@ struct GemmArgs {
   int lean;                       // >= 0: feature set of the compact epilogue (see lean_tile_epilogue); -1: generic
   long long* trace;               // diagnostics: per-role clock64() stamps of CTA `trace_cta` (gg_gemm_set_trace)
   int trace_cta;
+  unsigned long long* stamp;      // measurement: {min start, max end} of this launch in %globaltimer ns, or null
   float* partial;
   gg_epilogue epi;
 };
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(TileCfg<BN, STAGES, EPIW, PAIR>::THREADS, Tile
   if (tr && threadIdx.x == 0) tr[5 * TRACE_ROLE_STRIDE] = clock64();  // kernel-relative origin
   // everything above (barriers, TMEM, descriptor prefetch) touched no tensor: it overlaps the previous kernel
   pdl_entry();
+  if (g.stamp && threadIdx.x == 0) atomicMin(g.stamp, globaltimer_ns());  // body start (the predecessor has finished)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -566,6 +568,10 @@ __global__ void __launch_bounds__(TileCfg<BN, STAGES, EPIW, PAIR>::THREADS, Tile
   }
 
   tc_fence_before_sync();
+  if (g.stamp && threadIdx.x == 64) {  // first epilogue thread: its stores have been issued
+    tma_store_wait_all<0>();
+    atomicMax(g.stamp + 1, globaltimer_ns());
+  }
   if (PAIR) {
     cluster_sync_all();  // neither CTA may leave (or free tensor memory) while the other still signals / reads it
     if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
@@ -716,6 +722,12 @@ struct GemmProfile {
   long long launches = 0;
 };
 static GemmProfile g_prof;
+struct StampRecord {
+  double flops, bytes;
+};
+static std::vector<StampRecord> g_stamp_rec;
+static unsigned long long* g_stamp_buf = nullptr;  // device: 2 x capacity uint64 (gg_gemm_set_timer)
+static int g_stamp_cap = 0, g_stamp_next = 0;
 static long long* g_trace_buf = nullptr;  // device buffer of 6 * TRACE_ROLE_STRIDE stamps, or null
 static int g_trace_cta = 0;
 
@@ -856,6 +868,14 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
   args.partial = reinterpret_cast<float*>(d->workspace);
   args.trace = g_trace_buf;
   args.trace_cta = g_trace_cta;
+  args.stamp = nullptr;
+  if (g_stamp_buf && g_stamp_next < g_stamp_cap) {
+    args.stamp = g_stamp_buf + 2 * g_stamp_next;
+    g_stamp_rec.push_back(StampRecord{2.0 * d->M * d->N * (static_cast<double>(d->seg[0].K) + (d->nseg > 1 ? d->seg[1].K : 0)),
+                                      2.0 * (static_cast<double>(d->M) + d->N) * (static_cast<double>(d->seg[0].K) + (d->nseg > 1 ? d->seg[1].K : 0)) +
+                                          static_cast<double>((d->epi.out_bf16 ? 2 : 0) + (d->epi.out_f32 ? 4 : 0)) * d->M * d->N});
+    ++g_stamp_next;
+  }
 
   const int total_kb = ceil_div(args.K0, BK) + ceil_div(args.K1, BK);
   const int tiles = ceil_div(d->M, pair ? 2 * BM : BM) * ceil_div(d->N, bn);
@@ -947,6 +967,27 @@ extern "C" int gg_gemm_set_trace(void* device_buf, int cta) {
   gg::g_trace_buf = reinterpret_cast<long long*>(device_buf);
   gg::g_trace_cta = cta;
   return GG_OK;
+}
+
+// In-kernel timing (supplement to the CUDA-event profile: an event pair adds ~6 us to a ~6 us launch). Every
+// following tcgen05 GEMM launch gets a slot of `device_buf` (2 x capacity uint64, the caller presets every slot to
+// {UINT64_MAX, 0} before each run): thread 0 of every CTA does atomicMin(start) after griddepcontrol.wait, the first
+// epilogue thread atomicMax(end) after its stores — also inside replayed CUDA graphs. NULL switches it off.
+extern "C" int gg_gemm_set_timer(void* device_buf, int capacity) {
+  gg::g_stamp_buf = reinterpret_cast<unsigned long long*>(device_buf);
+  gg::g_stamp_cap = device_buf ? capacity : 0;
+  gg::g_stamp_next = 0;
+  gg::g_stamp_rec.clear();
+  return GG_OK;
+}
+// Slots handed out since gg_gemm_set_timer; flops[i] / bytes[i] (optional, length >= count) = algorithmic work of slot i.
+extern "C" int gg_gemm_timer_slots(double* flops, double* bytes, int n) {
+  const int count = static_cast<int>(gg::g_stamp_rec.size());
+  for (int i = 0; i < count && i < n; ++i) {
+    if (flops) flops[i] = gg::g_stamp_rec[i].flops;
+    if (bytes) bytes[i] = gg::g_stamp_rec[i].bytes;
+  }
+  return count;
 }
 
 extern "C" int gg_gemm_profile_begin(void) {

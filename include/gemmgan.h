@@ -127,6 +127,11 @@ int gg_gemm_profile_dump(const char* csv_path); /* per-launch shapes and duratio
 /* Diagnostics: CTA `cta` of every following GEMM launch stamps clock64() per pipeline role into device_buf
  * (6 x 512 int64: TMA issued / stage full / tile committed / accumulator full / tile stored / origin); NULL = off. */
 int gg_gemm_set_trace(void* device_buf, int cta);
+/* In-kernel timing of every following GEMM launch (also inside replayed CUDA graphs): slot i of device_buf
+ * (2 x capacity uint64, preset to {UINT64_MAX, 0} by the caller before each run) receives {min start, max end} in
+ * %globaltimer ns. gg_gemm_timer_slots returns the number of slots handed out and their algorithmic FLOPs / bytes. */
+int gg_gemm_set_timer(void* device_buf, int capacity);
+int gg_gemm_timer_slots(double* flops, double* bytes, int n);
 
 /* -------------------------------------------------------- training engine --
  * One engine = one (generator, critic) pair of one model variant at a fixed per-rank batch
