@@ -74,77 +74,109 @@ int k_mask_with_cls(const uint8_t* in, uint8_t* out, int B, int P, cudaStream_t 
 }
 
 // ----------------------------------------------------------------------------------- FiLM
-__global__ void film_apply_kernel(const bf16* __restrict__ patches, const float* __restrict__ gb,
-                                  bf16* __restrict__ mod, int B, int P, int Dp) {
+// 8 consecutive features per thread: one 16-byte load of the patch row, four 16-byte loads of gamma / beta.
+__global__ void __launch_bounds__(256)
+    film_apply_kernel(const bf16* __restrict__ patches, const float* __restrict__ gb, bf16* __restrict__ mod, int B,
+                      int P, int Dp) {
   pdl_entry();
-  const int d2 = Dp >> 1;
-  const int64_t total = static_cast<int64_t>(B) * P * d2;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % d2) * 2;
-    const int64_t bj = i / d2;
-    const int b = static_cast<int>(bj / P);
-    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(patches + bj * Dp + k));
-    const float2 g = *reinterpret_cast<const float2*>(gb + static_cast<int64_t>(b) * 2 * Dp + k);
-    const float2 be = *reinterpret_cast<const float2*>(gb + static_cast<int64_t>(b) * 2 * Dp + Dp + k);
-    *reinterpret_cast<__nv_bfloat162*>(mod + bj * Dp + k) =
-        __floats2bfloat162_rn(fmaf(g.x, x.x, be.x), fmaf(g.y, x.y, be.y));
+  const unsigned d8 = static_cast<unsigned>(Dp) >> 3;
+  const unsigned rows = static_cast<unsigned>(B) * P;
+  const unsigned total = rows * d8;  // < 2^32 for every supported shape (checked on the host)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned bj = i / d8, k = (i - bj * d8) * 8;
+    const unsigned b = bj / static_cast<unsigned>(P);
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(patches + static_cast<int64_t>(bj) * Dp + k));
+    const float* gp = gb + static_cast<int64_t>(b) * 2 * Dp + k;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp)), g1 = __ldg(reinterpret_cast<const float4*>(gp) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(gp + Dp)), b1 = __ldg(reinterpret_cast<const float4*>(gp + Dp) + 1);
+    const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&xv);
+    const float2 x0 = __bfloat1622float2(x[0]), x1 = __bfloat1622float2(x[1]), x2 = __bfloat1622float2(x[2]),
+                 x3 = __bfloat1622float2(x[3]);
+    uint4 ov;
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&ov);
+    o[0] = __floats2bfloat162_rn(fmaf(g0.x, x0.x, b0.x), fmaf(g0.y, x0.y, b0.y));
+    o[1] = __floats2bfloat162_rn(fmaf(g0.z, x1.x, b0.z), fmaf(g0.w, x1.y, b0.w));
+    o[2] = __floats2bfloat162_rn(fmaf(g1.x, x2.x, b1.x), fmaf(g1.y, x2.y, b1.y));
+    o[3] = __floats2bfloat162_rn(fmaf(g1.z, x3.x, b1.z), fmaf(g1.w, x3.y, b1.w));
+    *reinterpret_cast<uint4*>(mod + static_cast<int64_t>(bj) * Dp + k) = ov;
   }
 }
 int k_film_apply(const bf16* patches, const float* gb, bf16* mod, int B, int P, int Dp, cudaStream_t st) {
-  GG_REQUIRE(Dp % 2 == 0, "patch feature dim must be even");
-  launch_k(film_apply_kernel, grid_for(static_cast<int64_t>(B) * P * Dp / 2, 256), 256, 0, st, patches, gb, mod, B,
-                                                                                        P, Dp);
+  GG_REQUIRE(Dp % 8 == 0 && static_cast<int64_t>(B) * P * (Dp / 8) < (1LL << 32), "FiLM: unsupported shape");
+  launch_k(film_apply_kernel, grid_for(static_cast<int64_t>(B) * P * Dp / 8, 256), 256, 0, st, patches, gb, mod, B, P, Dp);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
-__global__ void film_bwd_kernel(const bf16* __restrict__ dmod, const bf16* __restrict__ patches,
-                                const float* __restrict__ gb, bf16* __restrict__ dgb, int B, int P, int Dp) {
+// thread = (sample, pair of features): walks the P patch rows with 4-byte loads (a warp covers 128 contiguous bytes)
+__global__ void __launch_bounds__(256)
+    film_bwd_kernel(const bf16* __restrict__ dmod, const bf16* __restrict__ patches, const float* __restrict__ gb,
+                    bf16* __restrict__ dgb, int B, int P, int Dp) {
   pdl_entry();
-  const int64_t total = static_cast<int64_t>(B) * Dp;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(i / Dp), k = static_cast<int>(i % Dp);
-    float dg = 0.f, db = 0.f;
+  const unsigned d2 = static_cast<unsigned>(Dp) >> 1;
+  const unsigned total = static_cast<unsigned>(B) * d2;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned b = i / d2, k = (i - b * d2) * 2;
+    const bf16* dm = dmod + static_cast<int64_t>(b) * P * Dp + k;
+    const bf16* pa = patches + static_cast<int64_t>(b) * P * Dp + k;
+    float dgx = 0.f, dgy = 0.f, dbx = 0.f, dby = 0.f;
+#pragma unroll 4
     for (int j = 0; j < P; ++j) {
-      const int64_t o = (static_cast<int64_t>(b) * P + j) * Dp + k;
-      const float d = __bfloat162float(dmod[o]);
-      dg = fmaf(d, __bfloat162float(patches[o]), dg);
-      db += d;
+      const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dm + static_cast<int64_t>(j) * Dp));
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pa + static_cast<int64_t>(j) * Dp));
+      dgx = fmaf(d.x, x.x, dgx);
+      dgy = fmaf(d.y, x.y, dgy);
+      dbx += d.x;
+      dby += d.y;
     }
-    const float gamma = gb[static_cast<int64_t>(b) * 2 * Dp + k];
-    const float beta = gb[static_cast<int64_t>(b) * 2 * Dp + Dp + k];
-    dgb[static_cast<int64_t>(b) * 2 * Dp + k] = __float2bfloat16_rn(dg * (1.f - gamma * gamma));
-    dgb[static_cast<int64_t>(b) * 2 * Dp + Dp + k] = __float2bfloat16_rn(fabsf(beta) < 5.0f ? db : 0.f);
+    const float* gp = gb + static_cast<int64_t>(b) * 2 * Dp + k;
+    const float2 gamma = *reinterpret_cast<const float2*>(gp), beta = *reinterpret_cast<const float2*>(gp + Dp);
+    bf16* o = dgb + static_cast<int64_t>(b) * 2 * Dp + k;
+    *reinterpret_cast<__nv_bfloat162*>(o) =
+        __floats2bfloat162_rn(dgx * (1.f - gamma.x * gamma.x), dgy * (1.f - gamma.y * gamma.y));
+    *reinterpret_cast<__nv_bfloat162*>(o + Dp) =
+        __floats2bfloat162_rn(fabsf(beta.x) < 5.0f ? dbx : 0.f, fabsf(beta.y) < 5.0f ? dby : 0.f);
   }
 }
 int k_film_bwd(const bf16* dmod, const bf16* patches, const float* gb, bf16* dgb, int B, int P, int Dp,
                cudaStream_t st) {
-  launch_k(film_bwd_kernel, grid_for(static_cast<int64_t>(B) * Dp, 256), 256, 0, st, dmod, patches, gb, dgb, B, P, Dp);
+  launch_k(film_bwd_kernel, grid_for(static_cast<int64_t>(B) * Dp / 2, 256), 256, 0, st, dmod, patches, gb, dgb, B, P, Dp);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
 
 // ----------------------------------------------------------------------------- token plumbing
-__global__ void assemble_tokens_kernel(bf16* x, const float* __restrict__ cls, int R, int B, int S, int E,
-                                       const bf16* __restrict__ src) {
+// 8 consecutive features (16 bytes) per thread
+__global__ void __launch_bounds__(256)
+    assemble_tokens_kernel(bf16* x, const float* __restrict__ cls, int R, int B, int S, int E, const bf16* __restrict__ src) {
   pdl_entry();
-  const int64_t total = static_cast<int64_t>(R) * B * S * E;
-  const int64_t rep = static_cast<int64_t>(B) * S * E;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int e = static_cast<int>(i % E);
-    const int s = static_cast<int>((i / E) % S);
-    if (s == 0) x[i] = __float2bfloat16_rn(cls[e]);
-    else if (src) {
-      const int64_t b = (i % rep) / (static_cast<int64_t>(S) * E);
-      x[i] = src[(b * (S - 1) + (s - 1)) * E + e];
-    } else if (i >= rep) x[i] = x[i % rep];
+  const unsigned e8 = static_cast<unsigned>(E) >> 3;
+  const unsigned rows_rep = static_cast<unsigned>(B) * S;
+  const unsigned total = static_cast<unsigned>(R) * rows_rep * e8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned row = i / e8, e = (i - row * e8) * 8;   // row = (r * B + b) * S + s
+    const unsigned rr = row % rows_rep;                      // b * S + s
+    const unsigned s = rr % static_cast<unsigned>(S);
+    uint4 v;
+    if (s == 0) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls + e)), c1 = __ldg(reinterpret_cast<const float4*>(cls + e) + 1);
+      __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&v);
+      o[0] = __floats2bfloat162_rn(c0.x, c0.y); o[1] = __floats2bfloat162_rn(c0.z, c0.w);
+      o[2] = __floats2bfloat162_rn(c1.x, c1.y); o[3] = __floats2bfloat162_rn(c1.z, c1.w);
+    } else if (src) {
+      const unsigned b = rr / static_cast<unsigned>(S);
+      v = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<int64_t>(b) * (S - 1) + (s - 1)) * E + e));
+    } else if (row >= rows_rep) {
+      v = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(rr) * E + e);  // replica 0's row (not a CLS row)
+    } else {
+      continue;  // replica 0: the patch projection wrote this row already
+    }
+    *reinterpret_cast<uint4*>(x + static_cast<int64_t>(row) * E + e) = v;
   }
 }
 int k_assemble_tokens(bf16* x, const float* cls, int R, int B, int S, int E, cudaStream_t st, const bf16* src) {
-  launch_k(assemble_tokens_kernel, grid_for(static_cast<int64_t>(R) * B * S * E, 256), 256, 0, st, x, cls, R, B, S, E, src);
+  GG_REQUIRE(E % 8 == 0 && static_cast<int64_t>(R) * B * S * (E / 8) < (1LL << 32), "token assembly: unsupported shape");
+  launch_k(assemble_tokens_kernel, grid_for(static_cast<int64_t>(R) * B * S * E / 8, 256), 256, 0, st, x, cls, R, B, S, E, src);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
@@ -161,27 +193,39 @@ int k_relu_bwd(const bf16* g, const bf16* h, bf16* out, int64_t n, cudaStream_t 
   return GG_OK;
 }
 
-__global__ void unassemble_tokens_kernel(const bf16* __restrict__ dx, bf16* __restrict__ dpe, int R, int B,
-                                         int S, int E) {
+__global__ void __launch_bounds__(256)
+    unassemble_tokens_kernel(const bf16* __restrict__ dx, bf16* __restrict__ dpe, int R, int B, int S, int E) {
   pdl_entry();
-  const int P = S - 1;
-  const int64_t total = static_cast<int64_t>(B) * P * E;
+  const unsigned P = static_cast<unsigned>(S) - 1;
+  const unsigned e8 = static_cast<unsigned>(E) >> 3;
+  const unsigned total = static_cast<unsigned>(B) * P * e8;
   const int64_t rep = static_cast<int64_t>(B) * S * E;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int e = static_cast<int>(i % E);
-    const int j = static_cast<int>((i / E) % P);
-    const int64_t b = i / (static_cast<int64_t>(E) * P);
-    const int64_t src = (b * S + 1 + j) * E + e;
-    float acc = 0.f;
-    for (int r = 0; r < R; ++r) acc += __bfloat162float(dx[r * rep + src]);
-    dpe[i] = __float2bfloat16_rn(acc);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned row = i / e8, e = (i - row * e8) * 8;  // row = b * P + j
+    const unsigned b = row / P, j = row - b * P;
+    const int64_t src = (static_cast<int64_t>(b) * S + 1 + j) * E + e;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < R; ++r) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(dx + r * rep + src));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        acc[2 * q] += f.x;
+        acc[2 * q + 1] += f.y;
+      }
+    }
+    uint4 ov;
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+    *reinterpret_cast<uint4*>(dpe + static_cast<int64_t>(row) * E + e) = ov;
   }
 }
 int k_unassemble_tokens(const bf16* dx, bf16* dpe, float* /*unused*/, int R, int B, int S, int E,
                         cudaStream_t st) {
   if (S <= 1) return GG_OK;
-  launch_k(unassemble_tokens_kernel, grid_for(static_cast<int64_t>(B) * (S - 1) * E, 256), 256, 0, st, dx, dpe, R, B, S, E);
+  launch_k(unassemble_tokens_kernel, grid_for(static_cast<int64_t>(B) * (S - 1) * E / 8, 256), 256, 0, st, dx, dpe, R, B, S, E);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }
