@@ -223,11 +223,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`)
+    sampler = ClockSampler(local)   # nvidia-smi needs ~0.3 s to produce its first line: started before the warm-up,
+                                    # stopped right after the timed region (it covers both)
     for _ in range(max(args.warmup, 3)):
         t.train(*batch_dev)
     barrier()
     L.gg_launch_count(1)
-    sampler = ClockSampler(local)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                # evict L2 between timed iterations (outside the events)
