@@ -593,21 +593,33 @@ __global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const Att
     const int row = threadIdx.x >> 3, part = threadIdx.x & 7;
     const uint32_t H = static_cast<uint32_t>(a.H);
     uint32_t bb = static_cast<uint32_t>(g0 / H), hh = static_cast<uint32_t>(g0 % H);
-#pragma unroll
-    for (int gi = 0; gi < SELF_GROUPS; ++gi) {
-      const bool valid = g0 + gi < ngroups && row < S;
-      const int col = static_cast<int>(hh) * SELF_HD + part * 8;
+    // row pointers of sequence bb (recomputed only when the group walk crosses into the next sequence: with 4 heads
+    // and 4 groups per CTA that is never, and the four heads' slices are 128 bytes apart in the same rows)
+    const bf16 *qrow = nullptr, *krow = nullptr, *vrow = nullptr, *grow = nullptr;
+    auto row_ptrs = [&]() {
       const int64_t qr = static_cast<int64_t>(a.q_mod >= a.nb ? bb : bb % static_cast<uint32_t>(a.q_mod)) * S + row;
       const int64_t kr = static_cast<int64_t>(a.kv_mod >= a.nb ? bb : bb % static_cast<uint32_t>(a.kv_mod)) * S + row;
-      bf16* dst = tiles + gi * PER_GROUP + row * SELF_PITCH + part * 8;
-      cp_async16(dst, valid ? a.q + qr * a.ldq + col : a.q, valid);
-      cp_async16(dst + SELF_TILE, valid ? a.k + kr * a.ldkv + col : a.q, valid);
-      cp_async16(dst + 2 * SELF_TILE, valid ? a.v + kr * a.ldkv + col : a.q, valid);
-      if (MODE == 1)
-        cp_async16(dst + 3 * SELF_TILE, valid ? a.dout + (static_cast<int64_t>(bb) * S + row) * a.lddo + col : a.q, valid);
+      qrow = a.q + qr * a.ldq + part * 8;
+      krow = a.k + kr * a.ldkv + part * 8;
+      vrow = a.v + kr * a.ldkv + part * 8;
+      if (MODE == 1) grow = a.dout + (static_cast<int64_t>(bb) * S + row) * a.lddo + part * 8;
+    };
+    row_ptrs();
+    const bool row_ok = row < S;
+    bf16* dst = tiles + row * SELF_PITCH + part * 8;
+#pragma unroll
+    for (int gi = 0; gi < SELF_GROUPS; ++gi) {
+      const bool valid = row_ok && g0 + gi < ngroups;
+      const int col = static_cast<int>(hh) * SELF_HD;
+      cp_async16(dst, valid ? qrow + col : a.q, valid);
+      cp_async16(dst + SELF_TILE, valid ? krow + col : a.q, valid);
+      cp_async16(dst + 2 * SELF_TILE, valid ? vrow + col : a.q, valid);
+      if (MODE == 1) cp_async16(dst + 3 * SELF_TILE, valid ? grow + col : a.q, valid);
+      dst += PER_GROUP;
       if (++hh == H) {
         hh = 0;
         ++bb;
+        if (gi + 1 < SELF_GROUPS) row_ptrs();
       }
     }
   }
