@@ -37,15 +37,18 @@ def test_struct_layouts_match_header_sizes(tmp_path):
     src = tmp_path / "probe.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "gemmgan.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %d\\n", sizeof(gg_epilogue), sizeof(gg_gemm_seg),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %d %zu %zu %zu %zu %zu\\n", sizeof(gg_epilogue), sizeof(gg_gemm_seg),'
         'sizeof(gg_gemm_desc), sizeof(gg_net_buffers), sizeof(gg_model_cfg), offsetof(gg_gemm_desc, epi),'
-        'offsetof(gg_net_buffers, off), (int)GG_NSLOTS);return 0;}\n')
+        'offsetof(gg_net_buffers, off), (int)GG_NSLOTS, sizeof(gg_wgrad_item), offsetof(gg_wgrad_item, bias),'
+        'sizeof(gg_colsum_item), sizeof(gg_attn_args), offsetof(gg_gemm_desc, pair));return 0;}\n')
     exe = tmp_path / "probe"
     subprocess.check_call([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert vals == [C.sizeof(_lib.Epilogue), C.sizeof(_lib.GemmSeg), C.sizeof(_lib.GemmDesc),
                     C.sizeof(_abi_decl.NetBuffers), C.sizeof(_abi_decl.ModelCfg), _lib.GemmDesc.epi.offset,
-                    _abi_decl.NetBuffers.off.offset, _abi_decl.NSLOTS]
+                    _abi_decl.NetBuffers.off.offset, _abi_decl.NSLOTS, C.sizeof(_abi_decl.WgradItem),
+                    _abi_decl.WgradItem.bias.offset, C.sizeof(_abi_decl.ColsumItem), C.sizeof(_abi_decl.AttnArgs),
+                    _lib.GemmDesc.pair.offset]
 
 
 def test_no_cpu_fallback_in_product_path():
@@ -55,7 +58,8 @@ def test_no_cpu_fallback_in_product_path():
         if fn.endswith(".py"):
             text = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in text and "from oracle" not in text, fn
-    for fn in ("vanilla_gan_unconditional.py", "conditional_gan_film.py",
-               "conditional_gan_cross_attention_with_film.py"):
+    for fn in ("vanilla_gan_unconditional.py", "conditional_gan_film.py", "conditional_gan_cross_attention_with_film.py",
+               "conditional_gan_cross_attention.py", "conditional_gan_img_transformer.py", "conditional_gan_concat.py",
+               "multi_patch_gan_dataloader.py", "multi_patch_multi_token_gan_dataloader.py"):
         text = open(os.path.join(ROOT, fn)).read()
         assert "oracle" not in text.replace("oracle/", ""), fn
