@@ -514,6 +514,16 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// 2^x on the SFU (ex2.approx.ftz: one instruction; 2^-inf = 0). The softmaxes below work in the log2 domain:
+// score * (log2(e) / sqrt(hd)) + key bias (0, or -inf for padded / out-of-range keys), so that a probability is
+// ex2(v - max) with no select around it (__expf cost ~12 issued instructions per element with its range handling).
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float SCALE_LOG2E = 0.125f * 1.4426950408889634f;  // log2(e) / sqrt(64)
+
 __device__ __forceinline__ uint32_t pack_bf16(float x, float y) {
   __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -640,11 +650,11 @@ __global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const Att
   // ---- scores and probabilities: thread holds rows g, g+8 x keys {2t, 2t+1, 8+2t, 9+2t}
   float sc[2][4];
   mma_ab_t(sc, Qs, Ks, lane);
-  bool kvalid[4];
+  float kbias[4];  // 0, or -inf for a padded / out-of-range key
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int j = (e >> 1) * 8 + 2 * t + (e & 1);
-    kvalid[e] = j < S && !(mk && mk[j]);
+    kbias[e] = (j < S && !(mk && mk[j])) ? 0.f : -INFINITY;
   }
   float p[2][4];  // [row half][key e]
 #pragma unroll
@@ -652,15 +662,15 @@ __global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const Att
     float m = -INFINITY;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float v = kvalid[e] ? sc[e >> 1][rh * 2 + (e & 1)] * scale : -INFINITY;
-      p[rh][e] = v;
-      m = fmaxf(m, v);
+      p[rh][e] = fmaf(sc[e >> 1][rh * 2 + (e & 1)], SCALE_LOG2E, kbias[e]);
+      m = fmaxf(m, p[rh][e]);
     }
     m = quad_max(m);
+    m = m == -INFINITY ? 0.f : m;  // every key masked: all probabilities 0
     float l = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      p[rh][e] = kvalid[e] ? __expf(p[rh][e] - m) : 0.f;
+      p[rh][e] = fast_ex2(p[rh][e] - m);
       l += p[rh][e];
     }
     l = quad_add(l);
@@ -819,13 +829,13 @@ __global__ void __launch_bounds__(NT * 32) attn_self_mid_kernel(const AttnArgs a
   }
   const float keep_scale = drop ? 1.f / (1.f - a.drop_p) : 1.f;
   // key validity of this thread's columns: key j = kt*16 + (e>>1)*8 + 2t + (e&1)
-  uint32_t kvalid = 0;  // bit kt*4 + e
+  float kbias[NT][4];  // 0, or -inf for a padded / out-of-range key
 #pragma unroll
   for (int kt = 0; kt < NT; ++kt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = kt * 16 + (e >> 1) * 8 + 2 * t + (e & 1);
-      if (j < S && !(mk && mk[j])) kvalid |= 1u << (kt * 4 + e);
+      kbias[kt][e] = (j < S && !(mk && mk[j])) ? 0.f : -INFINITY;
     }
   for (int qt = warp; qt < NT; qt += MID_WARPS) {
     const bf16* Qt = Qs + qt * SELF_TILE;
@@ -841,17 +851,17 @@ __global__ void __launch_bounds__(NT * 32) attn_self_mid_kernel(const AttnArgs a
         for (int kt = 0; kt < NT; ++kt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float v = ((kvalid >> (kt * 4 + e)) & 1u) ? sc[kt][e >> 1][rh * 2 + (e & 1)] * scale : -INFINITY;
-            p[kt][rh][e] = v;
-            m = fmaxf(m, v);
+            p[kt][rh][e] = fmaf(sc[kt][e >> 1][rh * 2 + (e & 1)], SCALE_LOG2E, kbias[kt][e]);
+            m = fmaxf(m, p[kt][rh][e]);
           }
         m = quad_max(m);
+        m = m == -INFINITY ? 0.f : m;
         float l = 0.f;
 #pragma unroll
         for (int kt = 0; kt < NT; ++kt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            p[kt][rh][e] = ((kvalid >> (kt * 4 + e)) & 1u) ? __expf(p[kt][rh][e] - m) : 0.f;
+            p[kt][rh][e] = fast_ex2(p[kt][rh][e] - m);
             l += p[kt][rh][e];
           }
         l = quad_add(l);
@@ -1087,18 +1097,19 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
         float tm = -INFINITY;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float v = kval[key_of(kt, e)] ? sc[e >> 1][rh * 2 + (e & 1)] * scale : -INFINITY;
+          const float v = kval[key_of(kt, e)] ? sc[e >> 1][rh * 2 + (e & 1)] * SCALE_LOG2E : -INFINITY;
           pv[rh][e] = v;
           tm = fmaxf(tm, v);
         }
         tm = quad_max(tm);
-        const float m_new = fmaxf(m_run[rh], tm);
-        const float corr = m_new == -INFINITY ? 1.f : __expf(m_run[rh] - m_new);  // m_run = -inf -> 0
+        const float m_new = fmaxf(m_run[rh], tm);  // running maximum, log2 domain
+        const float m_use = m_new == -INFINITY ? 0.f : m_new;
+        const float corr = fast_ex2(m_run[rh] - m_use);  // m_run = -inf -> 0
         m_run[rh] = m_new;
         float ls = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          pv[rh][e] = pv[rh][e] == -INFINITY ? 0.f : __expf(pv[rh][e] - m_new);
+          pv[rh][e] = fast_ex2(pv[rh][e] - m_use);
           ls += pv[rh][e];
         }
         l_thr[rh] = l_thr[rh] * corr + ls;
@@ -1182,6 +1193,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
       }
     }
     __syncwarp();
+    const float m_safe[2] = {m_run[0] == -INFINITY ? 0.f : m_run[0], m_run[1] == -INFINITY ? 0.f : m_run[1]};
     const float delta[2] = {row_delta[qt * 16 + g], row_delta[qt * 16 + g + 8]};
     for (int kt = 0; kt < NT; ++kt) {
       float sc[2][4], dp[2][4];
@@ -1196,7 +1208,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = key_of(kt, e);
-          const float pij = kval[j] ? __expf(sc[e >> 1][rh * 2 + (e & 1)] * scale - m_run[rh]) * inv_l[rh] : 0.f;
+          const float pij = kval[j] ? fast_ex2(fmaf(sc[e >> 1][rh * 2 + (e & 1)], SCALE_LOG2E, -m_safe[rh])) * inv_l[rh] : 0.f;
           float mult = 1.f;
           if (drop && i < S && j < S) mult = ds.keep(pbase + j) ? keep_scale : 0.f;
           dsv[rh][e] = pij * (dp[e >> 1][rh * 2 + (e & 1)] * mult - delta[rh]);
@@ -1238,7 +1250,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
         for (int rh = 0; rh < 2; ++rh) {
           const int j = kt * 16 + g + rh * 8;
           const bool kv = rh == 0 ? kv0 : kv1;
-          const float pij = kv ? __expf(st[e >> 1][rh * 2 + (e & 1)] * scale - mi) * il : 0.f;
+          const float pij = kv ? fast_ex2(fmaf(st[e >> 1][rh * 2 + (e & 1)], SCALE_LOG2E, -mi)) * il : 0.f;
           float mult = 1.f;
           if (drop && i < S && j < S) mult = ds.keep(pbase + j) ? keep_scale : 0.f;
           pT[rh][e] = pij * mult;
