@@ -245,6 +245,67 @@ int k_sum_replicas(const bf16* in, bf16* out, int R, int64_t n, cudaStream_t st)
   return GG_OK;
 }
 
+// Label-conditioned baseline (benchmark_generative_model.py:138-150): the conditioning vector of sample b is the
+// concatenation of one row of each embedding table. Tables are the fp32 master parameters (a few KB: L2 resident).
+__global__ void embed_gather_kernel(const float* __restrict__ emb0, const float* __restrict__ emb1,
+                                    const int64_t* __restrict__ y0, const int64_t* __restrict__ y1, int V0, int V1,
+                                    bf16* __restrict__ c, int B, int Eh) {
+  pdl_entry();
+  const int64_t total = static_cast<int64_t>(B) * 2 * Eh;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / (2 * Eh));
+    const int col = static_cast<int>(i % (2 * Eh));
+    const bool second = col >= Eh;
+    int64_t y = second ? y1[b] : y0[b];
+    const int V = second ? V1 : V0;
+    y = y < 0 ? 0 : (y >= V ? V - 1 : y);
+    const float* tab = second ? emb1 : emb0;
+    c[i] = __float2bfloat16_rn(tab[y * Eh + (second ? col - Eh : col)]);
+  }
+}
+int k_embed_gather(const float* emb0, const float* emb1, const int64_t* y0, const int64_t* y1, int V0, int V1, bf16* c,
+                   int B, int Eh, cudaStream_t st) {
+  launch_k(embed_gather_kernel, grid_for(static_cast<int64_t>(B) * 2 * Eh, 256), 256, 0, st, emb0, emb1, y0, y1, V0, V1,
+           c, B, Eh);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+// Gradient of the tables: g_t[v, :] = sum over the samples with y_t[b] = v of dc[b, t*Eh : (t+1)*Eh]. One thread per
+// table element walks the batch in order (fixed summation order: deterministic, no atomics); the threads of a warp
+// share v, so the label read is a broadcast and the dc read is coalesced. Every element is written (0 for unused rows).
+__global__ void embed_grad_kernel(const bf16* __restrict__ dc, const int64_t* __restrict__ y0,
+                                  const int64_t* __restrict__ y1, int V0, int V1, float* __restrict__ g0,
+                                  float* __restrict__ g1, int B, int Eh) {
+  pdl_entry();
+  const int64_t total = static_cast<int64_t>(V0 + V1) * Eh;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int v = static_cast<int>(i / Eh);
+    const int col = static_cast<int>(i % Eh);
+    const bool second = v >= V0;
+    if (second) v -= V0;
+    const int V = second ? V1 : V0;
+    const int64_t* y = second ? y1 : y0;
+    const bf16* src = dc + (second ? Eh : 0) + col;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      int64_t yb = y[b];
+      yb = yb < 0 ? 0 : (yb >= V ? V - 1 : yb);
+      if (yb == v) acc += __bfloat162float(src[static_cast<int64_t>(b) * 2 * Eh]);
+    }
+    (second ? g1 : g0)[static_cast<int64_t>(v) * Eh + col] = acc;
+  }
+}
+int k_embed_grad(const bf16* dc, const int64_t* y0, const int64_t* y1, int V0, int V1, float* g0, float* g1, int B,
+                 int Eh, cudaStream_t st) {
+  launch_k(embed_grad_kernel, grid_for(static_cast<int64_t>(V0 + V1) * Eh, 128), 128, 0, st, dc, y0, y1, V0, V1, g0, g1,
+           B, Eh);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 __global__ void scatter_add_rows_kernel(bf16* dst, const bf16* __restrict__ src, int B, int stride_rows, int E) {
   pdl_entry();
   const int64_t total = static_cast<int64_t>(B) * E;

@@ -122,6 +122,9 @@ struct gg_engine {
   int S_ = 1, Gp = 0, F = 0, hd = 0;
   bool img = false;     // conditional_gan_img_transformer.py: patch encoder = Linear + ReLU + LayerNorm, CLS conditioning
   bool concat = false;  // conditional_gan_concat.py: the conditioning is one Linear of the staged text / mean-patch vector
+  bool label = false;   // benchmark_generative_model.py: the conditioning is two gathered embedding rows (a concat-style
+                        // engine: `concat` is set too; the staged vector / encoder GEMM become labels / a gather)
+  int64_t* labels = nullptr;  // [2, B]
   bool cond = false, paper = false, film = false;  // paper: cross-attention tail; film: FiLM modulation of the patches
   // staged inputs
   bf16 *xfr, *patches, *text, *zbf, *xin;
@@ -292,6 +295,7 @@ namespace gg {
 
 static bool slot_matrix_shape(const gg_model_cfg& c, int net, int slot, int* rows, int* cols) {
   const int E = c.E, F = c.ffn, condw = c.variant == GG_VARIANT_VANILLA ? 0 : E;
+  if (c.variant == GG_VARIANT_LABEL && slot < GG_P_TR0_W) return false;  // embedding tables are gathered in fp32
   if (slot == GG_P_FILM_W) {  // (the IMG variant keeps its patch-encoder LayerNorm vectors in the FiLM slots)
     if (c.variant == GG_VARIANT_IMG) return false;
     *rows = 2 * c.Dp; *cols = c.Dt; return true;
@@ -409,7 +413,11 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
   e.normbuf = ar.take<float>(8);
   e.rng = ar.take<uint64_t>(2);
   if (e.concat) {
-    e.text = ar.take<bf16>(B * T * c.Dt);
+    if (e.label) {
+      e.labels = ar.take<int64_t>(2 * B);
+    } else {
+      e.text = ar.take<bf16>(B * T * c.Dt);
+    }
     for (int n = 0; n < 2; ++n) {
       e.tw[n].Rmax = 1;
       e.tw[n].c = ar.take<bf16>(B * E);
@@ -527,10 +535,13 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
 }
 
 static int validate_cfg(const gg_model_cfg& c) {
-  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_IMG, "unknown variant %d", c.variant);
+  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_LABEL, "unknown variant %d", c.variant);
   GG_REQUIRE(c.B > 0 && c.G > 0 && c.L > 0 && c.H > 0, "bad sizes B=%d G=%d L=%d H=%d", c.B, c.G, c.L, c.H);
   GG_REQUIRE(c.L % 8 == 0 && c.H % 8 == 0, "latent and hidden widths must be multiples of 8");
-  if (c.variant != GG_VARIANT_VANILLA) {
+  if (c.variant == GG_VARIANT_LABEL) {
+    GG_REQUIRE(c.E % 16 == 0 && c.E <= 1024, "conditioning width %d must be a multiple of 16 (<= 1024)", c.E);
+    GG_REQUIRE(c.Dt >= 1 && c.Dp >= 1, "vocabulary sizes must be positive (Dt=%d Dp=%d)", c.Dt, c.Dp);
+  } else if (c.variant != GG_VARIANT_VANILLA) {
     GG_REQUIRE(c.E % 32 == 0 && c.E <= 1024, "embedding width %d must be a multiple of 32 (<= 1024)", c.E);
     GG_REQUIRE(c.n_heads > 0 && c.E % c.n_heads == 0 && (c.E / c.n_heads) % 2 == 0 && c.E / c.n_heads <= 64,
                "unsupported head configuration E=%d heads=%d", c.E, c.n_heads);
@@ -547,12 +558,13 @@ static void derive(gg_engine& e) {
   e.cond = c.variant != GG_VARIANT_VANILLA;
   e.paper = c.variant == GG_VARIANT_PAPER || c.variant == GG_VARIANT_CROSS;
   e.film = c.variant == GG_VARIANT_PAPER || c.variant == GG_VARIANT_FILM;
-  e.concat = c.variant == GG_VARIANT_CONCAT;
+  e.label = c.variant == GG_VARIANT_LABEL;
+  e.concat = c.variant == GG_VARIANT_CONCAT || e.label;
   e.img = c.variant == GG_VARIANT_IMG;
   e.S_ = e.cond ? c.P + 1 : 1;
   e.Gp = static_cast<int>(round_up64(c.G, 8));
   e.F = c.ffn;
-  e.hd = e.cond ? c.E / c.n_heads : 0;
+  e.hd = (e.cond && !e.label) ? c.E / c.n_heads : 0;
 }
 
 // ------------------------------------------------------------------------------- tower forward
@@ -565,6 +577,8 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
   const int B = c.B, S = e.S_, E = c.E, F = e.F, P = c.P, T = c.T, Dp = c.Dp, Dt = c.Dt;
   const int rows = R * B * S;
   const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
+  if (e.label)  // benchmark_generative_model.py:138-157 / :204-224: c = [emb0[y0] | emb1[y1]]
+    return k_embed_gather(e.P(net, GG_P_EMB0), e.P(net, GG_P_EMB1), e.labels, e.labels + B, Dt, Dp, t.c, B, E / 2, st);
   if (e.concat)  // conditional_gan_concat.py:135-139 / :182-186: c = encoder(text) (or of the masked mean patch)
     return e.linear(ln, B, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W), Epi().bias(e.P(net, GG_P_TEXT_B)).obf(t.c, E));
   // FiLM parameters from the text CLS / text vector (:129-134); conditional_gan_cross_attention.py has no FiLM
@@ -686,6 +700,10 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
   const int n = Rg * B, rows = n * S;
   const uint32_t site0 = static_cast<uint32_t>(net) * 64u;
   const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  if (e.label) {  // rows of the two tables: sums of the dc rows that carry each label
+    if (s0 > 0) return GG_OK;
+    return k_embed_grad(dc, e.labels, e.labels + B, Dt, Dp, e.Gr(net, GG_P_EMB0), e.Gr(net, GG_P_EMB1), B, E / 2, st);
+  }
   if (e.concat) {
     if (s0 > 0) return GG_OK;
     GG_TRY(e.wgrad(E, Dt, B, Op{dc, E}, Op{e.text, Dt}, e.Gr(net, GG_P_TEXT_W), Dt));
@@ -1027,7 +1045,9 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
   const gg_model_cfg& c = e->cfg;
   if (genes)  // real genes -> second half of the [fake; real] matrix
     GG_TRY(k_cast_f32_bf16(genes, c.G, e->xfr + static_cast<int64_t>(c.B) * e->Gp, e->Gp, c.B, c.G, st));
-  if (e->concat) {
+  if (e->label) {
+    // labels arrive through gg_engine_set_labels
+  } else if (e->concat) {
     GG_REQUIRE(text, "the concat variant needs the conditioning vector (text embedding or masked mean patch)");
     GG_TRY(k_cast_f32_bf16(text, c.Dt, e->text, c.Dt, static_cast<int64_t>(c.B) * c.T, c.Dt, st));
   } else if (e->cond) {
@@ -1043,6 +1063,16 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
     if (e->has_tpad)
       GG_CUDA_CHECK(cudaMemcpyAsync(e->tpad, text_pad, static_cast<size_t>(c.B) * c.T, cudaMemcpyDeviceToDevice, st));
   }
+  return GG_OK;
+}
+
+extern "C" int gg_engine_set_labels(gg_engine* e, const int64_t* labels0, const int64_t* labels1, void* stream) {
+  GG_REQUIRE(e && labels0 && labels1, "null argument");
+  GG_REQUIRE(e->label, "gg_engine_set_labels is for GG_VARIANT_LABEL engines");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t bytes = sizeof(int64_t) * static_cast<size_t>(e->cfg.B);
+  GG_CUDA_CHECK(cudaMemcpyAsync(e->labels, labels0, bytes, cudaMemcpyDeviceToDevice, st));
+  GG_CUDA_CHECK(cudaMemcpyAsync(e->labels + e->cfg.B, labels1, bytes, cudaMemcpyDeviceToDevice, st));
   return GG_OK;
 }
 

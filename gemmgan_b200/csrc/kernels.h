@@ -50,6 +50,11 @@ int64_t colsum_group_workspace_bytes(int64_t max_total_columns);
 int k_colsum_group(const ColsumItem* items, int n, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
 // out[b, d] = mean over rows p with pad[b, p] == 0 of x[b, p, d]   (fp32 in / out; pad may be NULL)
+// label-conditioned baseline: c[b] = [emb0[y0[b]] | emb1[y1[b]]] (bf16), and its gradient (deterministic row sums)
+int k_embed_gather(const float* emb0, const float* emb1, const int64_t* y0, const int64_t* y1, int V0, int V1, bf16* c,
+                   int B, int Eh, cudaStream_t st);
+int k_embed_grad(const bf16* dc, const int64_t* y0, const int64_t* y1, int V0, int V1, float* g0, float* g1, int B,
+                 int Eh, cudaStream_t st);
 int k_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, cudaStream_t st);
 
 // ---- wgrad_group.cu: all single-segment weight gradients dW = dY^T X of one backward pass in one launch

@@ -10,6 +10,7 @@ reference's initial weights and state_dict()s are interchangeable with reference
   concat  generator/discriminator  src/conditional_gan_concat.py:97-196
   img     generator/discriminator  src/conditional_gan_img_transformer.py:97-190
   vanilla generator_nocond/discriminator_nocond  src/vanilla_gan_unconditional.py:93-184
+  label   generator/discriminator  src/benchmark_generative_model.py:101-236 (label-conditioned baseline)
 
 forward() does not run torch kernels: it calls the engine (libgemmgan_sm100a.so) the trainer attached
 to the module. It is an inference forward (no autograd graph); the training step uses the engine's
@@ -23,7 +24,7 @@ from torch import nn
 from . import _abi_decl as A
 
 VARIANT_IDS = {"vanilla": A.VARIANT_VANILLA, "film": A.VARIANT_FILM, "paper": A.VARIANT_PAPER,
-               "cross": A.VARIANT_CROSS, "concat": A.VARIANT_CONCAT, "img": A.VARIANT_IMG}
+               "cross": A.VARIANT_CROSS, "concat": A.VARIANT_CONCAT, "img": A.VARIANT_IMG, "label": A.VARIANT_LABEL}
 
 
 def build_linear_block(input_dims, output_dims, negative_slope=0.0, is_bn=False):
@@ -280,6 +281,77 @@ class ConcatDiscriminator(_ConcatNet):
         self._build_concat(vector_dims, input_embedding_dims, embedding_dims, discriminator_dims, condition_type,
                            negative_slope, is_bn)
         self.encoder = nn.Linear(input_embedding_dims, embedding_dims)
+
+
+# ------------------------------------------------------ label-conditioned baseline model
+LABEL_EMBEDDING_DIMS = 128  # benchmark_generative_model.py:32 (hard-coded; 2 variables -> the 256 of :119 / :185)
+
+
+def categorical_embedding(vocab_sizes):
+    """One nn.Embedding(vs, 128) per categorical variable (reference :27-35)."""
+    return nn.ModuleList(nn.Embedding(vs, LABEL_EMBEDDING_DIMS) for vs in vocab_sizes)
+
+
+class _LabelNet(_Net):
+    """benchmark_generative_model.py: conditioning vector = [emb0[disease type] | emb1[primary site]], concatenated
+    to the trunk input. Construction order as in the reference: trunk blocks, final_layer, then the embedding
+    tables (:122-126 / :190-196). `categorical_embedded_dims` is hard-coded to 256 there while every table is 128
+    wide, so only two categorical variables give consistent shapes; anything else fails in the reference's first
+    forward (mat1 / mat2 shape mismatch) and is rejected here at construction."""
+
+    _variant = "label"
+
+    def _build_label(self, first_dim, numerical_dims, vocab_sizes, dims, negative_slope, is_bn):
+        self.numerical_dims = len(numerical_dims)
+        self.vocab_sizes = vocab_sizes
+        self.negative_slope = negative_slope
+        self.n_cat_vars = len(vocab_sizes)
+        self.categorical_embedded_dims = 256
+        if self.n_cat_vars * LABEL_EMBEDDING_DIMS != self.categorical_embedded_dims or self.numerical_dims != 0:
+            raise NotImplementedError("the reference's shapes are only consistent for two categorical variables and "
+                                      "no numerical covariates (128-wide tables vs a hard-coded 256: :32, :119)")
+        self.input_dims = first_dim + self.numerical_dims + self.categorical_embedded_dims
+        stack = build_stack(self.input_dims, dims[:-1], negative_slope, is_bn)
+        setattr(self, "generator" if self._role == "gen" else "discriminator", stack)
+        self.final_layer = nn.Linear(dims[-2], dims[-1])
+        self._gg_owner = None
+
+    def slot_table(self):
+        blocks = self.trunk_blocks()
+        if len(blocks) != 2:
+            raise NotImplementedError("the engine implements the reference's 2-hidden-layer trunks")
+        return {A.P_EMB0: self.categorical_embedding[0].weight, A.P_EMB1: self.categorical_embedding[1].weight,
+                A.P_TR0_W: blocks[0][0].weight, A.P_TR0_B: blocks[0][0].bias,
+                A.P_TR1_W: blocks[1][0].weight, A.P_TR1_B: blocks[1][0].bias,
+                A.P_FIN_W: self.final_layer.weight, A.P_FIN_B: self.final_layer.bias}
+
+    def forward(self, x, categorical_covariates, categorical_covariates_2):
+        return self._engine_forward(x, categorical_covariates, categorical_covariates_2)
+
+
+class LabelGenerator(_LabelNet):
+    _role = "gen"
+
+    def __init__(self, latent_dims, numerical_dims, vocab_sizes, generator_dims, negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.latent_dims = latent_dims
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.generator_dims = generator_dims
+        self._build_label(latent_dims, numerical_dims, vocab_sizes, generator_dims, negative_slope, is_bn)
+        self.final_activation = nn.ReLU()
+        self.relu = nn.ReLU()
+        self.categorical_embedding = categorical_embedding(vocab_sizes)
+
+
+class LabelDiscriminator(_LabelNet):
+    _role = "disc"
+
+    def __init__(self, vector_dims, numerical_dims, vocab_sizes, discriminator_dims, negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.vector_dims = vector_dims
+        self.discriminator_dims = discriminator_dims
+        self._build_label(vector_dims, numerical_dims, vocab_sizes, discriminator_dims, negative_slope, is_bn)
+        self.categorical_embedding = categorical_embedding(vocab_sizes)
 
 
 # --------------------------------------------------------------------------- vanilla model

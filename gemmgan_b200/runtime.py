@@ -214,6 +214,14 @@ class Engine:
         self._keep = (g, p, t, pm, tm)  # keep alive until the enqueued casts have run
         _lib.check(self.lib.gg_engine_set_batch(self.handle, _ptr(g), _ptr(p), _ptr(pm), _ptr(t), _ptr(tm), _stream()))
 
+    def set_labels(self, labels0: torch.Tensor, labels1: torch.Tensor) -> None:
+        """Label-conditioned baseline: the two categorical covariates of the batch, int64 [B] on the device."""
+        y0 = labels0.reshape(-1).to(device=self.device, dtype=torch.int64).contiguous()
+        y1 = labels1.reshape(-1).to(device=self.device, dtype=torch.int64).contiguous()
+        assert y0.numel() == self.B and y1.numel() == self.B
+        self._keep_labels = (y0, y1)
+        _lib.check(self.lib.gg_engine_set_labels(self.handle, _ptr(y0), _ptr(y1), _stream()))
+
     def disc_grads(self, z: torch.Tensor, alpha: torch.Tensor, training: bool = True, phase: int = 0) -> None:
         """phase 0 = whole step; 1 = forward + trunk backward; 2 = tower backward (gg_engine_disc_grads_phase)."""
         z, alpha = self._f32(z), self._f32(alpha)

@@ -7,6 +7,7 @@ Layouts (reference file:line):
   film    (text_embedding[Dt], gene_expression[G], patches[P,Dp], padding_mask[P], disease_type,
            primary_site)   src/multi_patch_gan_dataloader.py:48
   vanilla (gene_expression[G],)   src/data_loader.py:160 (TensorDataset)
+  label   (gene_expression[G] f32, disease_type i64, primary_site i64)   src/benchmark_gan_dataloader.py:37
 Masks: True = padding; token 0 is never padded. Data ~ N(0,1) (the real genes are z-scored log2(TPM+1)).
 """
 from __future__ import annotations
@@ -21,6 +22,8 @@ def synthetic_tensors(variant, n, n_genes, n_patches=8, n_tokens=1, text_dim=768
     genes = torch.randn(n, n_genes, generator=g)
     if variant == "vanilla":
         return (genes,)
+    if variant == "label":
+        return (genes, torch.randint(0, 10, (n,), generator=g), torch.randint(0, 10, (n,), generator=g))
     patches = torch.randn(n, n_patches, patch_dim, generator=g)
     ppad = torch.zeros(n, n_patches, dtype=torch.bool)
     if ragged and n_patches > 1:

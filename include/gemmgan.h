@@ -151,6 +151,9 @@ int gg_gemm_timer_slots(double* flops, double* bytes, int n);
                                 patch embedding) ('image', :137-138); parameter slots GG_P_TEXT_W / GG_P_TEXT_B = encoder */
 #define GG_VARIANT_IMG 5     /* conditional_gan_img_transformer.py: patch encoder Linear -> ReLU -> LayerNorm (:111-115), no
                                 text, bias-free encoder layers, CLS vector as conditioning (:131-133) */
+#define GG_VARIANT_LABEL 6   /* benchmark_generative_model.py (label-conditioned baseline, :101-236): c = [emb0[y0] | emb1[y1]],
+                                two nn.Embedding tables of width E/2 per net; cfg.Dt / cfg.Dp = their vocabulary sizes;
+                                labels staged with gg_engine_set_labels; no dropout, no attention                      */
 #define GG_VARIANT_CROSS 3   /* conditional_gan_cross_attention.py: the paper model's towers without FiLM and without
                                 tower biases (:97-206); only row 0 of its multi-query cross-attentions reaches the
                                 conditioning vector, so it runs as the same single-query tail */
@@ -169,7 +172,9 @@ enum gg_param_slot {
   GG_P_TR0_W, GG_P_TR0_B, GG_P_TR1_W, GG_P_TR1_B, GG_P_FIN_W, GG_P_FIN_B,
   GG_NSLOTS,
   /* GG_VARIANT_IMG has no FiLM: its patch-encoder LayerNorm weight / bias [E] live in the FiLM slots */
-  GG_P_PENC_LN_W = GG_P_FILM_W, GG_P_PENC_LN_B = GG_P_FILM_B
+  GG_P_PENC_LN_W = GG_P_FILM_W, GG_P_PENC_LN_B = GG_P_FILM_B,
+  /* GG_VARIANT_LABEL: the two embedding tables [vocab_i, E/2] (fp32, gathered directly: no bf16 shadow) */
+  GG_P_EMB0 = GG_P_TEXT_W, GG_P_EMB1 = GG_P_PATCH_W
 };
 enum gg_layer_slot {
   GG_L_IN_W = 0, GG_L_IN_B, GG_L_OUT_W, GG_L_OUT_B, GG_L_FF1_W, GG_L_FF1_B, GG_L_FF2_W, GG_L_FF2_B,
@@ -237,6 +242,10 @@ int gg_engine_refresh_shadows(gg_engine* e, int net, void* stream);
  * casts to bf16 once per train() call (:465-469). Unused pointers may be NULL per variant. */
 int gg_engine_set_batch(gg_engine* e, const float* genes, const float* patches, const uint8_t* patch_pad,
                         const float* text, const uint8_t* text_pad, void* stream);
+/* GG_VARIANT_LABEL: stages the two categorical covariates of the batch (device int64 [B] each, the dataloader's
+ * disease_type / primary_site columns; benchmark_generative_model.py:138-150). Values must lie in [0, vocab_i):
+ * nn.Embedding raises on anything else, the caller checks (the kernel clamps instead of faulting). */
+int gg_engine_set_labels(gg_engine* e, const int64_t* labels0, const int64_t* labels1, void* stream);
 /* train_disc minus optimizer: fills critic grads + stats. z [B,L], alpha [B,1] fp32. training=1
  * uses dropout_p (three independently-dropped critic tower passes, as the reference). */
 int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream);

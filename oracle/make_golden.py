@@ -43,6 +43,8 @@ def ref_args(variant, x, cond):
     if variant in ("film", "concat", "concat_image", "img"):
         text, patches, ppad = cond
         return (x, text, patches, ppad)
+    if variant == "label":
+        return (x,) + tuple(cond)
     return (x,)
 
 
@@ -68,10 +70,10 @@ def make(variant, cfg, optimizer, slope, n_calls, full_tensors, name):
     B, G, L = c["B"], c["G"], c["latent"]
     kw = dict(optimizer=optimizer, hidden=c["hidden"], latent=L, embed=c["embed"], seed=11,
               dropout=0.0, negative_slope=slope)
-    if variant != "vanilla":
+    if variant not in ("vanilla", "label"):
         kw.update(text_dim=c["text_dim"], patch_dim=c["patch_dim"])
     else:
-        kw.pop("embed")
+        kw.pop("embed")   # (label: two 128-wide tables, hard-coded in the reference)
     t = ref_shim.make_trainer(variant, G, **kw) if variant != "vanilla" else \
         ref_shim.make_trainer(variant, G, optimizer=optimizer, hidden=c["hidden"], latent=L, seed=11,
                               dropout=0.0, negative_slope=slope)
@@ -152,6 +154,11 @@ def make(variant, cfg, optimizer, slope, n_calls, full_tensors, name):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]   # optional: variant names to (re)generate, e.g. `python -m oracle.make_golden label`
+    if only:
+        global make
+        _make = make
+        make = lambda v, *a: _make(v, *a) if v in only else None  # noqa: E731
     make("vanilla", SMALL, "adam", 0.0, 4, True, "vanilla_small_adam")
     make("vanilla", SMALL, "rms_prop", 0.2, 4, True, "vanilla_small_rmsprop_leaky")
     make("paper", SMALL, "adam", 0.0, 4, True, "paper_small_adam")
@@ -164,6 +171,8 @@ def main():
     make("img", SMALL, "rms_prop", 0.0, 4, True, "img_small_rmsprop")
     make("concat", SMALL, "adam", 0.0, 4, True, "concat_small_adam")
     make("concat_image", SMALL, "rms_prop", 0.2, 4, True, "concat_image_small_rmsprop_leaky")
+    make("label", SMALL, "rms_prop", 0.0, 4, True, "label_small_rmsprop")
+    make("label", SMALL, "adam", 0.2, 4, True, "label_small_adam_leaky")
 
 
 if __name__ == "__main__":

@@ -32,23 +32,52 @@ def available() -> bool:
     return os.path.isdir(REF_SRC)
 
 
+_loaded = {}        # reference scripts imported so far, by name
+_ref_modules = {}   # every module that came from REF_SRC (kept out of sys.modules between loads)
+
+
+def _from_reference(mod) -> bool:
+    f = getattr(mod, "__file__", None)
+    return bool(f) and os.path.abspath(f).startswith(os.path.abspath(REF_SRC) + os.sep)
+
+
 def load(module_name: str):
     """Imports one reference script (e.g. 'conditional_gan_cross_attention_with_film').
+
+    The drop-in modules at the repo root carry the reference's file names on purpose, and the reference scripts
+    import each other by bare name, so both sets cannot sit in sys.modules together: while a reference script is
+    being imported the same-named drop-ins are set aside (and REF_SRC leads sys.path); afterwards the drop-ins are
+    put back and the reference's modules live only in this shim's cache.
 
     NB: importing reseeds torch / numpy / random to 42 (reference generative_model_utils.py:22-26).
     """
     if not available():
         raise RuntimeError(f"reference sources not found at {REF_SRC}")
+    if module_name in _loaded:
+        return _loaded[module_name]
     for name in _STUBS:
         if name not in sys.modules:
             m = MagicMock(name=name)
             m.__path__ = []
             m.__all__ = []
             sys.modules[name] = m
-    if REF_SRC not in sys.path:
-        sys.path.insert(0, REF_SRC)
-    with contextlib.redirect_stdout(io.StringIO()):
-        return importlib.import_module(module_name)
+    ref_names = {f[:-3] for f in os.listdir(REF_SRC) if f.endswith(".py")}
+    aside = {n: sys.modules.pop(n) for n in list(sys.modules)
+             if n in ref_names and not _from_reference(sys.modules[n])}
+    sys.modules.update(_ref_modules)
+    sys.path.insert(0, REF_SRC)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod = importlib.import_module(module_name)
+    finally:
+        sys.path.remove(REF_SRC)
+        for n in list(sys.modules):
+            if n in ref_names and _from_reference(sys.modules[n]):
+                _ref_modules[n] = sys.modules.pop(n)
+        sys.modules.update(aside)
+    assert _from_reference(mod), f"{module_name} resolved to {getattr(mod, '__file__', None)}, not to the reference"
+    _loaded[module_name] = mod
+    return mod
 
 
 def make_trainer(variant: str, n_genes: int, *, optimizer: str = "adam", hidden: int = 256,
@@ -71,6 +100,14 @@ def make_trainer(variant: str, n_genes: int, *, optimizer: str = "adam", hidden:
                                    discriminator_dims=[hidden, hidden, 1], optimizer=optimizer,
                                    negative_slope=negative_slope, results_dire=out_dir, **kw)
             t.build_WGAN_GP_nocond()
+        elif variant == "label":
+            ref = load("benchmark_generative_model")
+            torch.manual_seed(seed)
+            t = ref.WGAN_GP_benchmark(input_dims=n_genes, latent_dims=latent, vocab_sizes=[10, 10],
+                                      generator_dims=[hidden, hidden, n_genes],
+                                      discriminator_dims=[hidden, hidden, 1], optimizer=optimizer,
+                                      negative_slope=negative_slope, results_dire=out_dir, **kw)
+            t.build_WGAN_GP()
         elif variant in ("concat", "concat_image"):
             ref = load("conditional_gan_concat")
             torch.manual_seed(seed)

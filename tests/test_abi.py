@@ -63,3 +63,30 @@ def test_no_cpu_fallback_in_product_path():
                "multi_patch_gan_dataloader.py", "multi_patch_multi_token_gan_dataloader.py"):
         text = open(os.path.join(ROOT, fn)).read()
         assert "oracle" not in text.replace("oracle/", ""), fn
+
+
+def test_label_conditioned_nets_mirror_the_oracle_layout():
+    """benchmark_generative_model drop-in (CPU part): same state_dict keys / shapes / initial values as the oracle
+    restatement (itself pinned to the reference), and the C-ABI slot table covers every parameter."""
+    import torch
+
+    import benchmark_generative_model as bm
+    from oracle import restated
+
+    torch.manual_seed(4)
+    gen, disc = bm.WGAN_GP_model_benchmark(16, 203, [], [10, 7], [32, 32, 203], [32, 32, 1])
+    torch.manual_seed(4)
+    o_gen = restated.Net("gen", "label", 203, 16, 0, [32, 32, 203], vocab_sizes=(10, 7))
+    o_disc = restated.Net("disc", "label", 203, 16, 0, [32, 32, 1], vocab_sizes=(10, 7))
+    for mine, ref in ((gen, o_gen), (disc, o_disc)):
+        a, b = mine.state_dict(), ref.state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+        slots = mine.slot_table()
+        assert {id(p) for p in slots.values()} == {id(p) for p in mine.parameters()}
+        assert slots[_abi_decl.P_EMB0].shape == (10, 128) and slots[_abi_decl.P_EMB1].shape == (7, 128)
+    assert gen.input_dims == 16 + 256 and disc.input_dims == 203 + 256
+    import pytest
+    with pytest.raises(NotImplementedError):
+        bm.generator(16, [], [10], [32, 32, 203])   # one variable: 128 != the hard-coded 256 (reference shape error)

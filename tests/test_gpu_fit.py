@@ -51,6 +51,36 @@ def test_fit_runs_and_saves_checkpoints(variant, tmp_path):
         assert out[0].shape == (3 * B, G) and out[1].shape == (3 * B, G) and np.isfinite(out[1]).all()
 
 
+def test_label_conditioned_baseline_fit(tmp_path):
+    """benchmark_generative_model.WGAN_GP_benchmark.fit(train, test, epochs) over (genes, disease type, primary site)
+    batches; checkpoints only at the last epoch when it is a freq_compute_test multiple (reference :643-656)."""
+    m = importlib.import_module("benchmark_generative_model")
+    torch.manual_seed(0)
+    t = m.WGAN_GP_benchmark(input_dims=G, latent_dims=32, vocab_sizes=[10, 10], generator_dims=[32, 32, G],
+                            discriminator_dims=[32, 32, 1], optimizer="rms_prop", freq_compute_test=1,
+                            results_dire=str(tmp_path))
+    loader = synthetic_loader("label", n_samples=3 * B, batch_size=B, n_genes=G, seed=1)
+    t.fit(loader, None, epochs=2)
+    for k in ("d loss", "d real loss", "d fake loss", "g loss"):
+        assert len(t.loss_dict[k]) == 2 and np.isfinite(t.loss_dict[k]).all(), (k, t.loss_dict[k])
+    sd = torch.load(tmp_path / "generator_last_epoch.pt")
+    assert list(sd.keys()) == list(t.gen.state_dict().keys()) and "categorical_embedding.1.weight" in sd
+    real, gen, cats, _, sites, _ = t.generate_samples_all(loader)
+    assert real.shape == (3 * B, G) and gen.shape == (3 * B, G) and np.isfinite(gen).all()
+    assert len(cats) == 3 * B and len(sites) == 3 * B
+    # the embedding rows of labels that occur in the data have moved, the others have not
+    e0 = t.gen.categorical_embedding[0].weight.detach().cpu()
+    torch.manual_seed(0)
+    fresh, _ = m.WGAN_GP_model_benchmark(32, G, [], [10, 10], [32, 32, G], [32, 32, 1])
+    seen = torch.zeros(10, dtype=torch.bool)
+    for b in loader:
+        seen[b[1]] = True
+    moved = (e0 - fresh.categorical_embedding[0].weight.detach()).abs().amax(dim=1) > 0
+    assert torch.equal(moved, seen)
+    with pytest.raises(IndexError):
+        t.train(torch.zeros(B, G), torch.full((B,), 10), torch.zeros(B, dtype=torch.long))
+
+
 def test_prefetch_gives_identical_training(tmp_path):
     """train(batch, prefetch=next batch) must be a pure scheduling change."""
     batches = [synthetic_tensors("paper", B, G, 5, 3, text_dim=24, patch_dim=40, seed=s, ragged=True) for s in (1, 2, 3)]

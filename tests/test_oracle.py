@@ -92,7 +92,8 @@ def test_oracle_matches_reference_golden(name):
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
 @pytest.mark.parametrize("variant,opt", [("vanilla", "rms_prop"), ("paper", "adam"), ("film", "adamw"),
-                                         ("cross", "rms_prop"), ("concat", "adam"), ("concat_image", "rms_prop"), ("img", "rms_prop")])
+                                         ("cross", "rms_prop"), ("concat", "adam"), ("concat_image", "rms_prop"), ("img", "rms_prop"),
+                                         ("label", "rms_prop"), ("label", "adam")])
 def test_oracle_matches_reference_live(variant, opt):
     G, B = 120, 6
     ref = ref_shim.make_trainer(variant, G, optimizer=opt, seed=3, dropout=0.0)
@@ -107,6 +108,8 @@ def test_oracle_matches_reference_live(variant, opt):
     elif variant in ("film", "concat", "concat_image", "img"):
         text, patches, ppad = cond
         args = (x, text, patches, ppad)
+    elif variant == "label":
+        args = (x,) + tuple(cond)
     else:
         args = (x,)
     torch.manual_seed(21)
