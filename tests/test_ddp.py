@@ -56,6 +56,20 @@ def test_plan_stage_buckets_paper_and_film_layouts():
     assert sum(b.stop - b.start for _, b in plan) == 128 * len(slots)
 
 
+def test_plan_stage_buckets_label_and_concat_layouts():
+    """Trunk-plus-one-tensor-group variants: the label-conditioned baseline (two embedding tables in the EMB0 / EMB1
+    slots) and the concat model (one encoder): trunk bucket first, everything else in the stage-3 'embed' bucket,
+    which the staged step reduces after the stage that produced it (stage 0)."""
+    cross = tuple(range(A.P_P2T_IN_W, A.P_T2P_OUT_B + 1))
+    for slots in ([A.P_EMB0, A.P_EMB1], [A.P_TEXT_W, A.P_TEXT_B]):
+        offsets, off = {}, 0
+        for s_ in sorted(slots) + list(TRUNK):
+            offsets[s_] = off
+            off += 192
+        plan = plan_stage_buckets(offsets, off, TRUNK, A.P_LAYER0, A.L_COUNT, 2, cross)
+        assert [(st, b.name, b.start, b.stop) for st, b in plan] == [(-1, "trunk", 384, off), (3, "embed", 0, 384)]
+
+
 def test_plan_buckets_rejects_tower_behind_trunk():
     with pytest.raises(AssertionError):
         plan_buckets({A.P_TR0_W: 0, A.P_FILM_W: 512}, 1024, TRUNK)
