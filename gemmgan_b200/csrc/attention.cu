@@ -1021,11 +1021,16 @@ static int launch_mid(const AttnArgs& a, cudaStream_t st) {
 // delta_i = dO_i . O_i (valid with dropout: O already carries the mask) and accumulates dQ; phase 2 (warp = key
 // tile) walks the query tiles with the transposed products S^T = K Q^T, dP^T = V dO^T straight in accumulator
 // fragments, so dK = dS^T Q and dV = P^T dO need no shared-memory copies of dS / P. No atomics, deterministic.
-constexpr int LONG_WARPS = 16;  // 1 CTA per SM (shared memory): 16 warps hide the ldmatrix / mma latencies (8 warps: 1.24 / 3.08 ms at cfg2)
+// 1 CTA per SM (shared memory): 16 warps hide the ldmatrix / mma latencies (8 warps: 1.24 / 3.08 ms at cfg2).
+// Warp w owns tiles w, w + WARPS, ...: with 16 warps a sequence of 17 .. 19 tiles (S = 257 = 256 patches + CLS is
+// the reference's film configuration) would leave one to three warps a second tile while the others idle -- twice
+// the time for one more row -- so those lengths run with one warp per tile (17 .. 19 warps; the register cap of the
+// launch bound falls to 120 / 112 / 104). 20 tiles (S > 304) stay on 16 warps: 20 staging tiles no longer fit.
+constexpr int LONG_WARPS = 16;
 constexpr int LONG_MAXT = 20;  // S <= 320
 
-template <int MODE>
-__global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const AttnArgs a) {
+template <int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnArgs a) {
   pdl_entry();
   extern __shared__ __align__(16) uint8_t smem_long[];
   const int S = a.Lq;
@@ -1037,7 +1042,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
   bf16* Vs = Ks + ROWS * SELF_PITCH;
   bf16* Gs = Vs + ROWS * SELF_PITCH;                   // dO (backward only)
   bf16* stage_all = Qs + NTEN * ROWS * SELF_PITCH;     // one 16-row staging tile per warp
-  float* row_m = reinterpret_cast<float*>(stage_all + LONG_WARPS * SELF_TILE);  // backward: per query row
+  float* row_m = reinterpret_cast<float*>(stage_all + WARPS * SELF_TILE);  // backward: per query row
   float* row_il = row_m + ROWS;
   float* row_delta = row_il + ROWS;
   uint8_t* kval = reinterpret_cast<uint8_t*>(row_delta + ROWS);                 // key j usable (in range, not padded)
@@ -1048,7 +1053,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
     const int col = h * SELF_HD;
     const int64_t qb = static_cast<int64_t>(a.q_mod >= a.nb ? b : b % a.q_mod) * S;
     const int64_t kb = static_cast<int64_t>(a.kv_mod >= a.nb ? b : b % a.kv_mod) * S;
-    for (int idx = threadIdx.x; idx < ROWS * 8; idx += LONG_WARPS * 32) {
+    for (int idx = threadIdx.x; idx < ROWS * 8; idx += WARPS * 32) {
       const int row = idx >> 3, part = idx & 7;
       const bool valid = row < S;
       bf16* dst = Qs + row * SELF_PITCH + part * 8;
@@ -1059,7 +1064,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
         cp_async16(dst + 3 * ROWS * SELF_PITCH,
                    valid ? a.dout + (static_cast<int64_t>(b) * S + row) * a.lddo + col + part * 8 : a.q, valid);
     }
-    for (int j = threadIdx.x; j < ROWS; j += LONG_WARPS * 32) kval[j] = (j < S && !(mk && mk[j])) ? 1 : 0;
+    for (int j = threadIdx.x; j < ROWS; j += WARPS * 32) kval[j] = (j < S && !(mk && mk[j])) ? 1 : 0;
   }
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -1078,7 +1083,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
   // this thread's 4 key columns of a key tile: j = kt*16 + (e>>1)*8 + 2t + (e&1)
   auto key_of = [&](int kt, int e) { return kt * 16 + (e >> 1) * 8 + 2 * t + (e & 1); };
 
-  for (int qt = warp; qt < NT; qt += LONG_WARPS) {
+  for (int qt = warp; qt < NT; qt += WARPS) {
     const bf16* Qt = Qs + qt * SELF_TILE;
     const int rows_valid = min(16, S - qt * 16);
     // ---- online softmax statistics (and, forward, the output) over the key tiles
@@ -1227,7 +1232,7 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
   if (MODE == 0) return;
   __syncthreads();
   // ---- backward, phase 2: warp = key tile; rows of the fragments are KEYS, columns are QUERIES
-  for (int kt = warp; kt < NT; kt += LONG_WARPS) {
+  for (int kt = warp; kt < NT; kt += WARPS) {
     const int rows_valid = min(16, S - kt * 16);
     const bool kv0 = kval[kt * 16 + g] != 0, kv1 = kval[kt * 16 + g + 8] != 0;
     float ok[8][4], ov[8][4];
@@ -1276,21 +1281,31 @@ __global__ void __launch_bounds__(LONG_WARPS * 32) attn_self_long_kernel(const A
   }
 }
 
-template <int MODE>
-static int launch_long(const AttnArgs& a, cudaStream_t st) {
-  GG_REQUIRE(MODE == 0 || a.o != nullptr, "long self-attention backward needs the forward output (a.o)");
+template <int MODE, int WARPS>
+static int launch_long_w(const AttnArgs& a, cudaStream_t st) {
   const int rows = (a.Lq + 15) / 16 * 16;
-  const size_t smem = static_cast<size_t>((MODE == 1 ? 4 : 3) * rows * SELF_PITCH + LONG_WARPS * SELF_TILE) * 2 +
+  const size_t smem = static_cast<size_t>((MODE == 1 ? 4 : 3) * rows * SELF_PITCH + WARPS * SELF_TILE) * 2 +
                       static_cast<size_t>(rows) * (3 * 4 + 1) + 16;
   static size_t configured = 0;
   if (smem > configured) {
-    GG_CUDA_CHECK(cudaFuncSetAttribute(attn_self_long_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GG_CUDA_CHECK(cudaFuncSetAttribute(attn_self_long_kernel<MODE, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
     configured = smem;
   }
-  launch_k(attn_self_long_kernel<MODE>, static_cast<unsigned>(a.nb) * a.H, LONG_WARPS * 32, smem, st, a);
+  launch_k(attn_self_long_kernel<MODE, WARPS>, static_cast<unsigned>(a.nb) * a.H, WARPS * 32, smem, st, a);
   GG_LAUNCH_CHECK();
   return GG_OK;
+}
+
+template <int MODE>
+static int launch_long(const AttnArgs& a, cudaStream_t st) {
+  GG_REQUIRE(MODE == 0 || a.o != nullptr, "long self-attention backward needs the forward output (a.o)");
+  switch ((a.Lq + 15) / 16) {  // one warp per tile where a 17th .. 19th tile would otherwise cost a second round
+    case 17: return launch_long_w<MODE, 17>(a, st);
+    case 18: return launch_long_w<MODE, 18>(a, st);
+    case 19: return launch_long_w<MODE, 19>(a, st);
+    default: return launch_long_w<MODE, LONG_WARPS>(a, st);
+  }
 }
 
 // ------------------------------------------------- single-query cross-attention, head_dim 64, Lk <= 128

@@ -1,7 +1,8 @@
 """GPU tests of the attention core (gg_attention_fwd / gg_attention_bwd) against torch SDPA + autograd in fp32 on
 the same bf16 inputs, for the code paths: register-resident short self-attention (S <= 16, hd = 64: the tower at
 8 patches), the tensor-core mid-size self-attention (17 <= S <= 128, hd = 64: the tower at 64 patches), the
-flash-style long self-attention (129 <= S <= 320, hd = 64: the tower at 256 patches), the generic
+flash-style long self-attention (129 <= S <= 320, hd = 64: the tower at 256 patches; 17 .. 19 tiles run with one warp
+per tile), the generic
 short-sequence path, and the shared-memory path for long sequences."""
 import pytest
 import torch
@@ -29,7 +30,8 @@ def _reference(qkv, nb, H, L, mask, dout):
 @pytest.mark.parametrize("nb,H,hd,L", [(37, 4, 64, 9), (129, 4, 64, 16), (5, 4, 64, 3), (21, 4, 8, 6), (3, 4, 64, 65),
                                        (2, 2, 32, 257), (7, 4, 64, 17), (5, 4, 64, 32), (3, 4, 64, 48), (9, 4, 64, 80),
                                        (3, 4, 64, 96), (2, 4, 64, 128), (2, 4, 64, 129), (300, 4, 64, 65), (3, 4, 64, 257),
-                                       (2, 4, 64, 200), (1, 4, 64, 320), (40, 4, 64, 257)])
+                                       (2, 4, 64, 200), (1, 4, 64, 320), (40, 4, 64, 257), (2, 4, 64, 280),
+                                       (3, 4, 64, 300), (2, 4, 64, 272), (2, 4, 64, 305)])
 @pytest.mark.parametrize("masked", [False, True])
 def test_attention_matches_sdpa(nb, H, hd, L, masked):
     g = torch.Generator(device="cuda").manual_seed(nb * 1000 + L)
@@ -47,7 +49,7 @@ def test_attention_matches_sdpa(nb, H, hd, L, masked):
     assert (dqkv.float() - g_ref).abs().max().item() <= 1.5e-2 * g_ref.abs().max().item()
 
 
-@pytest.mark.parametrize("nb,L", [(64, 9), (16, 65), (8, 100), (4, 257)])
+@pytest.mark.parametrize("nb,L", [(64, 9), (16, 65), (8, 100), (4, 257), (3, 290)])
 def test_attention_dropout_forward_backward_consistent(nb, L):
     """With dropout the backward must regenerate the forward's mask: d(sum o * w)/dv checked by linearity in v."""
     H, hd = 4, 64
