@@ -68,6 +68,20 @@ class ColsumItem(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int64), ("N", C.c_int32), ("out", C.c_void_p)]
 
 
+def declare_evalmetrics(L: C.CDLL) -> None:
+    """Entry points of csrc/evalmetrics.cu (kept apart so that tests can bind the host-emulated build of that file)."""
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.gg_pairwise_distance.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp, i64, vp]
+    L.gg_row_kth_smallest.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp]
+    L.gg_row_membership.argtypes = [vp, i64, i32, i32, vp, i32, f32, vp, vp, vp, vp, vp]
+    L.gg_col_hits.argtypes = [vp, i64, i32, i32, vp, i32, vp, vp]
+    L.gg_standardize_columns.argtypes = [vp, i64, i32, i32, vp, i64, vp]
+    L.gg_gene_correlation.argtypes = [vp, i64, vp, i64, i32, i32, i32, vp, i64, vp]
+    L.gg_gamma_moments_workspace_bytes.argtypes = [i32]
+    L.gg_gamma_moments_workspace_bytes.restype = i64
+    L.gg_gamma_moments.argtypes = [vp, i64, i32, vp, i64, i32, i32, vp, i64, vp, vp]
+
+
 def declare(L: C.CDLL) -> None:
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     L.gg_engine_workspace_bytes.argtypes = [C.POINTER(ModelCfg), C.POINTER(i64)]
@@ -103,6 +117,7 @@ def declare(L: C.CDLL) -> None:
     L.gg_colsum_group_workspace_bytes.argtypes = [i64]
     L.gg_colsum_group_workspace_bytes.restype = i64
     L.gg_colsum_group.argtypes = [C.POINTER(ColsumItem), i32, vp, i64, vp]
+    declare_evalmetrics(L)
     L.gg_launch_count.argtypes = [i32]
     L.gg_launch_count.restype = C.c_longlong
     L.gg_launch_count_add.argtypes = [C.c_longlong]
@@ -123,5 +138,7 @@ EXPORTS = [
     "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_disc_grads_phase", "gg_engine_gen_grads_phase", "gg_engine_optim_step", "gg_engine_generate",
     "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_gp_step", "gg_masked_mean_rows", "gg_engine_lanes_signal", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",
+    "gg_pairwise_distance", "gg_row_kth_smallest", "gg_row_membership", "gg_col_hits", "gg_standardize_columns",
+    "gg_gene_correlation", "gg_gamma_moments_workspace_bytes", "gg_gamma_moments",
     "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

@@ -342,6 +342,59 @@ typedef struct gg_colsum_item {
 int64_t gg_colsum_group_workspace_bytes(int64_t sum_columns);
 int gg_colsum_group(const gg_colsum_item* items, int n, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------- evaluation metrics --
+ * The sample-quality metrics fit() computes every 50 epochs on the generated profiles. fp32 row-major tensors,
+ * fp32 CUDA-core arithmetic (nearest-neighbour comparisons do not survive bf16 operands); see
+ * gemmgan_b200/csrc/evalmetrics.cu and the host mirror gemmgan_b200/evalmetrics.py.
+ *
+ * out[i, j] (pitch ldo) = distance between x[i, 0:d] and y[j, 0:d]:
+ *   GG_DIST_L1   sum |a-b|      sklearn pairwise_distances(metric='l1') of compute_pairwise_distance
+ *                               (src/distribution_distances.py:51-66)
+ *   GG_DIST_SQL2 sum (a-b)^2    batch_pairwise_distances (src/unsupervised_metrics.py:114-138; the reference's
+ *                               |u|^2 - 2uv + |v|^2 clamped at 0 -- formed here from the differences, which is the
+ *                               same number without the cancellation)
+ *   GG_DIST_L2   sqrt of it     (a[:, None] - b).pow(2).sum(2).sqrt() of dcr / nndr (src/privacy_evaluator.py:23-24,
+ *                               :48, :55) without the [128, N, G] intermediate */
+#define GG_DIST_L1 0
+#define GG_DIST_SQL2 1
+#define GG_DIST_L2 2
+int gg_pairwise_distance(const float* x, int64_t ldx, const float* y, int64_t ldy, int32_t n, int32_t m, int32_t d,
+                         int32_t metric, float* out, int64_t ldo, void* stream);
+/* kth[i] = sorted(dist[i, 0:m])[k] (0-based rank, duplicates counted): get_kth_value(dist, k + 1)
+ * (src/distribution_distances.py:69-83), np.partition(dist, seq)[:, k] (src/unsupervised_metrics.py:186-187), and
+ * with k = 0 / 1 the first / second neighbour of dcr / nndr (src/privacy_evaluator.py:23-24, :49-52).
+ * argmin (optional) [n] = first index of the row minimum (np.argmin, src/unsupervised_metrics.py:236-237). */
+int gg_row_kth_smallest(const float* dist, int64_t ld, int32_t n, int32_t m, int32_t k, float* kth, int32_t* argmin,
+                        void* stream);
+/* Per row i of dist [n, m] (outputs may be NULL):
+ *   row_any[i]    = any_j dist[i,j] < col_radius[j] (inclusive: <=)  -- recall of compute_prdc
+ *                   (src/distribution_distances.py:124-127), np.any(distance <= D) of ManifoldEstimator.evaluate
+ *                   (src/unsupervised_metrics.py:229-232)
+ *   row_min[i], row_argmin[i] = min_j dist[i,j] and its first index -- coverage (:134-137), nearest_indices (:236)
+ *   row_ratio[i]  = max_j col_radius[j] / (dist[i,j] + eps)          -- realism score (:234-235) */
+int gg_row_membership(const float* dist, int64_t ld, int32_t n, int32_t m, const float* col_radius, int32_t inclusive,
+                      float eps, uint8_t* row_any, float* row_min, int32_t* row_argmin, float* row_ratio, void* stream);
+/* col_hits[j] += #{ i < n : dist[i,j] < row_radius[i] } (inclusive: <=): precision (.any(axis=0)) and density
+ * (.sum(axis=0)) of compute_prdc (src/distribution_distances.py:119-132). Accumulates, so that the caller can feed
+ * the rows in chunks; zero col_hits first. */
+int gg_col_hits(const float* dist, int64_t ld, int32_t n, int32_t m, const float* row_radius, int32_t inclusive,
+                int32_t* col_hits, void* stream);
+/* out[s, c] = (x[s, c] - mean_c) / std_c over the n rows (population std); constant columns give 0
+ * (standardize() inside pearson_correlation, src/corr_score.py:55-61). */
+int gg_standardize_columns(const float* x, int64_t ldx, int32_t n, int32_t g, float* out, int64_t ldo, void* stream);
+/* out[i, j] (pitch ldo) = sum_s a[s, i] * b[s, j] / n for standardised a [n, ga], b [n, gb]:
+ * np.dot(x_.T, y_) / x.shape[0] of pearson_correlation (src/corr_score.py:63-68). */
+int gg_gene_correlation(const float* a, int64_t lda, const float* b, int64_t ldb, int32_t n, int32_t ga, int32_t gb,
+                        float* out, int64_t ldo, void* stream);
+/* Fused gamma coefficient (gamma_coef / gamma_coeff_score, src/corr_score.py:71-120): over all gene pairs i < j with
+ * cx = corr of genes i, j in xs [nx, g] and cy = the same in ys [ny, g] (both standardised), sums[0..5] (fp64,
+ * device) = count, sum cx, sum cy, sum cx^2, sum cy^2, sum cx*cy. The Pearson correlation of the two
+ * upper_diag_list()s of 1 - corr follows on the host (1 - c flips both lists, so the sign survives). Neither
+ * [g, g] matrix is written. workspace: gg_gamma_moments_workspace_bytes(g) bytes. Deterministic. */
+int64_t gg_gamma_moments_workspace_bytes(int32_t g);
+int gg_gamma_moments(const float* xs, int64_t ldx, int32_t nx, const float* ys, int64_t ldy, int32_t ny, int32_t g,
+                     void* workspace, int64_t workspace_bytes, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,90 @@
+"""Evaluation-metric kernels on the B200 through the C ABI: the shared cases of tests/eval_cases.py
+(oracle + reference goldens) and size-independent properties at the reference's real shapes (18 868 genes).
+
+Named to sort after the hot-path GPU tests: these kernels were written after the round's GPU minutes were spent and
+had only been run through the host emulation (tests/test_eval_kernels_emulated.py) when they were committed."""
+import numpy as np
+import pytest
+import torch
+
+import eval_cases
+from eval_cases import *  # noqa: F401,F403  (the shared test functions)
+from gemmgan_b200 import _lib
+from gemmgan_b200 import evalmetrics as em
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def host(monkeypatch):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    _lib.require_device(torch.cuda.current_device())      # fails loudly off sm_100: there is no fallback
+    monkeypatch.setitem(eval_cases.DEV, "device", "cuda")
+    return em
+
+
+def _profiles(n, g, seed, shift=0.0, scale=1.0):
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    centres = torch.randn(8, g, device="cuda", generator=gen) * 1.5
+    pick = torch.randint(0, 8, (n,), device="cuda", generator=gen)
+    return centres[pick] + scale * torch.randn(n, g, device="cuda", generator=gen) + shift
+
+
+def test_distances_at_full_gene_count_against_torch_fp64(host):
+    x, y = _profiles(300, 18868, 1), _profiles(257, 18868, 2, shift=0.1)
+    for metric, p in ((em.DIST_L1, 1.0), (em.DIST_L2, 2.0)):
+        got = host.pairwise_distance(x, y, metric)
+        want = torch.cdist(x.double(), y.double(), p=p)   # independent check only (tests may use torch math)
+        assert torch.allclose(got.double(), want, rtol=1e-4, atol=0)   # 18 868 sequential fp32 additions per pair
+    sq = host.pairwise_distance(x, y, em.DIST_SQL2)
+    assert torch.allclose(sq.double(), torch.cdist(x.double(), y.double()) ** 2, rtol=1e-4)
+    self_d = host.pairwise_distance(x, x, em.DIST_L1)
+    assert torch.all(torch.diagonal(self_d) == 0) and torch.equal(self_d, self_d.T.contiguous())
+
+
+def test_rank_selection_matches_a_sort_at_scale(host):
+    d = host.pairwise_distance(_profiles(513, 512, 3), _profiles(2049, 512, 4), em.DIST_L1)
+    s, idx = torch.sort(d, dim=1, stable=True)
+    for k in (0, 1, 10, 2048):
+        kth, arg = host.row_kth_smallest(d, k, want_argmin=True)
+        assert torch.equal(kth, s[:, k])
+        assert torch.equal(arg.long(), idx[:, 0])
+
+
+def test_prdc_properties_at_scale(host, monkeypatch):
+    real = _profiles(1500, 18868, 5)
+    same = host.compute_prdc(real, real, 10)               # a set against itself: everything is covered
+    assert same["precision"] == 1.0 and same["recall"] == 1.0 and same["coverage"] == 1.0
+    fake = _profiles(1100, 18868, 6, shift=0.05, scale=1.1)
+    whole = host.compute_prdc(real, fake, 10)
+    assert all(0.0 <= whole[k] <= 1.0 for k in ("precision", "recall", "coverage")) and whole["density"] >= 0.0
+    monkeypatch.setattr(em, "CHUNK_BYTES", 256 * 4 * 1100)  # 256 distance rows at a time
+    assert host.compute_prdc(real, fake, 10) == whole       # chunking does not change a single count
+    far = host.compute_prdc(real, fake + 50.0, 10)           # disjoint supports
+    assert far["precision"] == 0.0 and far["recall"] == 0.0 and far["coverage"] == 0.0 and far["density"] == 0.0
+
+
+def test_privacy_scores_properties(host):
+    real, test = _profiles(800, 18868, 7), _profiles(300, 18868, 8)
+    copies = real[:200] + 1e-3 * _profiles(200, 18868, 9, scale=1.0)
+    assert host.dcr(real, copies, test) == 1.0              # near copies of training rows are closer to train
+    assert host.nndr(real, copies, test) == 1.0             # and their first neighbour is far closer than the second
+    assert host.dcr(test, copies, real) == 0.0
+
+
+def test_gamma_at_full_gene_count(host):
+    x = _profiles(256, 18868, 10)
+    assert host.gamma_coef(x, x) == pytest.approx(1.0, abs=1e-9)
+    m = host.gamma_moments(x, x)
+    g = 18868
+    assert m[0] == g * (g - 1) // 2 and m[3] == pytest.approx(m[4]) and m[3] == pytest.approx(m[5])
+    # against the unfused kernels: full [G, G] correlation of a gene subset, then the list statistics in fp64
+    sub_x, sub_y = x[:, :700].contiguous(), _profiles(300, 700, 11)
+    cx = torch.from_numpy(host.pearson_correlation(sub_x, sub_x)).double()
+    cy = torch.from_numpy(host.pearson_correlation(sub_y, sub_y)).double()
+    iu = torch.triu_indices(700, 700, offset=1)
+    a, b = cx[iu[0], iu[1]], cy[iu[0], iu[1]]
+    want = torch.corrcoef(torch.stack([a, b]))[0, 1].item()
+    assert host.gamma_coef(sub_x, sub_y) == pytest.approx(want, abs=1e-6)
+    assert torch.allclose(cx, torch.corrcoef(sub_x.double().T), atol=5e-6)
