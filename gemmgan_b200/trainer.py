@@ -486,6 +486,23 @@ class TrainerBase:
         idx = np.argmax(list(d.values()))
         print("Best epoch " + name + ":", list(d.keys())[idx], "score:", list(d.values())[idx])
 
+    def evaluate_generated(self, data_real, data_gen, test_real, test_gen, nn=10, privacy=True) -> dict:
+        """The GPU-computable part of the evaluation the reference's fit() runs on the arrays that
+        generate_samples_all returns (src/conditional_gan_cross_attention_with_film.py:732-734, :808-811, :983-984):
+        gamma_coef(test_real, test_gen), compute_prdc on the train and test pairs (the `precision` .. `coverage` and
+        `*_test` entries of compute_evaluation_metrics, src/unsupervised_metrics.py:52-62) and the DCR / NNDR privacy
+        scores. The sklearn classifiers, PCA and UMAP plots of the reference stay on the host and are out of scope."""
+        from . import evalmetrics as em
+
+        out = {"gamma": em.gamma_coef(test_real, test_gen)}
+        train, test = em.compute_prdc(data_real, data_gen, nearest_k=nn), em.compute_prdc(test_real, test_gen, nearest_k=nn)
+        for key in train:
+            out[key], out[key + "_test"] = train[key], test[key]
+        if privacy:
+            out["dcr"] = em.dcr(data_real, data_gen, test_real)
+            out["nndr"] = em.nndr(data_real, data_gen, test_real)
+        return out
+
     def _epoch_lr_decay(self, epoch, every):
         if epoch > 0 and epoch % every == 0:
             for opt in (self.optimizer_disc, self.optimizer_gen):

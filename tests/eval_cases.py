@@ -184,3 +184,19 @@ def test_argument_errors_are_reported(host):
     assert L.gg_gamma_moments(p, 4, 4, p, 4, 4, 4, None, 0, p, None) == -4        # GG_ERR_WORKSPACE
     with pytest.raises(ValueError):
         host.pairwise_distance(t(np.zeros((2, 3))), t(np.zeros((2, 4))), 0)
+
+
+def test_evaluate_generated_composition(host):
+    """TrainerBase.evaluate_generated (what fit()'s evaluation block computes on the GPU) against the oracle."""
+    from gemmgan_b200.trainer import TrainerBase
+
+    fx = load("eval_privacy")
+    real, gen, test = fx["real"], fx["fake"], fx["test"]
+    test_gen = gen[:35]
+    got = TrainerBase.evaluate_generated(None, real, gen, test, test_gen, nn=4)
+    train_want, test_want = ref.compute_prdc(real, gen, 4), ref.compute_prdc(test, test_gen, 4)
+    for key in ("precision", "recall", "density", "coverage"):
+        assert got[key] == pytest.approx(train_want[key], abs=1e-9), key
+        assert got[key + "_test"] == pytest.approx(test_want[key], abs=1e-9), key
+    assert got["gamma"] == pytest.approx(float(ref.gamma_coef(test, test_gen)), abs=5e-6)
+    assert got["dcr"] == pytest.approx(float(fx["dcr"]), abs=1e-12) and got["nndr"] == pytest.approx(float(fx["nndr"]), abs=1e-12)

@@ -88,3 +88,30 @@ def test_gamma_at_full_gene_count(host):
     want = torch.corrcoef(torch.stack([a, b]))[0, 1].item()
     assert host.gamma_coef(sub_x, sub_y) == pytest.approx(want, abs=1e-6)
     assert torch.allclose(cx, torch.corrcoef(sub_x.double().T), atol=5e-6)
+
+
+def test_evaluate_generated_after_fit(host, tmp_path):
+    """fit() -> generate_samples_all (train and test loaders) -> TrainerBase.evaluate_generated: the arrays the
+    reference hands to gamma_coef / compute_evaluation_metrics / dcr / nndr (…with_film.py:716-734, :983-984)."""
+    import conditional_gan_cross_attention_with_film as paper
+    from gemmgan_b200.synthetic import synthetic_loader
+
+    G, B = 300, 16
+    torch.manual_seed(0)
+    t = paper.WGAN_GP(input_dims=G, optimizer="adam", results_dire=str(tmp_path), latent_dims=32, embedding_dims=32,
+                      generator_dims=[32, 32, G], discriminator_dims=[32, 32, 1], text_embedding_dims=24,
+                      patches_embedding_dims=40)
+    mk = lambda n, seed: synthetic_loader("paper", n_samples=n, batch_size=B, n_genes=G, n_patches=5, n_tokens=3,
+                                          seed=seed, text_dim=24, patch_dim=40, ragged=True)
+    train, test = mk(4 * B, 1), mk(2 * B, 2)
+    t.fit(train, None, None, epochs=1)
+    data_real, data_gen = t.generate_samples_all(train)[:2]
+    test_real, test_gen = t.generate_samples_all(test)[:2]
+    got = t.evaluate_generated(data_real, data_gen, test_real, test_gen, nn=5)
+    want = ref.compute_prdc(test_real, test_gen, 5)
+    for key in ("precision", "recall", "density", "coverage"):
+        assert got[key + "_test"] == pytest.approx(want[key], abs=1e-9), key
+        assert 0.0 <= got[key]
+    assert got["gamma"] == pytest.approx(float(ref.gamma_coef(test_real, test_gen)), abs=1e-5)
+    assert got["dcr"] == pytest.approx(ref.dcr(data_real, data_gen, test_real), abs=1e-9)
+    assert got["nndr"] == pytest.approx(ref.nndr(data_real, data_gen, test_real), abs=1e-9)
