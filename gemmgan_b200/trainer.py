@@ -503,8 +503,80 @@ class TrainerBase:
             out["nndr"] = em.nndr(data_real, data_gen, test_real)
         return out
 
+    def save_generated_run(self, train_data, test_data, run: int, epoch: int, evaluate: bool = True) -> dict:
+        """One run of the reference's final test block (…with_film.py:786-811): generate_samples_all over the training
+        and the test loader, the twelve arrays written under <results_dire>/test_<run>_epoch_<epoch+1>/ with the
+        reference's file names (what UtilityEvaluatorPrimary and the privacy block read back, :962-990), and the GPU
+        metrics of evaluate_generated. Returns {"folder": ..., **metrics}."""
+        train_out = self.generate_samples_all(train_data)
+        test_out = self.generate_samples_all(test_data)
+        folder = os.path.join(self.result_dire, f"test_{run}_epoch_{epoch + 1}")
+        save_generated_arrays(folder, train_out, test_out)
+        out = {"folder": folder}
+        if evaluate:
+            out.update(self.evaluate_generated(train_out[0], train_out[1], test_out[0], test_out[1]))
+        return out
+
+    def _fit_evaluation(self, epoch, epochs, train_data, val_data, test_data, val=True, n_runs=2) -> None:
+        """Evaluation block of the reference's fit() (…with_film.py:702-811), GPU-computable part. Nothing happens
+        unless the caller hands fit() a validation / test loader and a results directory:
+          * every freq_compute_test epochs, with val_data: generate on the training and validation loaders, record
+            precision_test / recall_test (:732-734) and the gamma coefficient per epoch in `precision_scores`,
+            `recall_scores`, `corr_scores` (the dicts print_best_epoch reads);
+          * at the last epoch, with test_data: n_runs x save_generated_run (:786-811) -> `self.test_runs`."""
+        if not (val and self.result_dire):
+            return
+        if val_data is not None and (epoch + 1) % self.freq_compute_test == 0:
+            tr_out, va_out = self.generate_samples_all(train_data), self.generate_samples_all(val_data)
+            m = self.evaluate_generated(tr_out[0], tr_out[1], va_out[0], va_out[1], privacy=False)
+            self.precision_scores[epoch + 1] = m["precision_test"]
+            self.recall_scores[epoch + 1] = m["recall_test"]
+            self.corr_scores[epoch + 1] = m["gamma"]
+        if test_data is not None and epoch + 1 == epochs:
+            self.test_runs = [self.save_generated_run(train_data, test_data, run, epoch) for run in range(n_runs)]
+
     def _epoch_lr_decay(self, epoch, every):
         if epoch > 0 and epoch % every == 0:
             for opt in (self.optimizer_disc, self.optimizer_gen):
                 for g in opt.param_groups:
                     g["lr"] *= 0.5
+
+
+# ---- the .npy layout fit() leaves behind for the utility / privacy evaluation (…with_film.py:793-806, :970-976)
+GENERATED_FILES = ("data_real", "data_gen", "train_labels_real", "train_labels_gen", "train_primary_site_real",
+                   "train_primary_site_gen")
+GENERATED_TEST_FILES = ("test_real", "test_gen", "test_labels_real", "test_labels_gen", "test_primary_site_real",
+                        "test_primary_site_gen")
+
+
+def save_generated_arrays(folder: str, train_out, test_out) -> None:
+    """Writes what generate_samples_all returned for the training loader (real, gen, disease type real / gen, primary
+    site real / gen) and for the test loader under the reference's twelve file names (:793-806)."""
+    os.makedirs(folder, exist_ok=True)
+    for names, arrays in ((GENERATED_FILES, train_out), (GENERATED_TEST_FILES, test_out)):
+        if len(arrays) != len(names):
+            raise ValueError(f"expected the 6-tuple of generate_samples_all, got {len(arrays)} arrays")
+        for name, a in zip(names, arrays):
+            with open(os.path.join(folder, name + ".npy"), "wb") as f:
+                np.save(f, np.asarray(a))
+
+
+def load_generated_arrays(folder: str) -> dict:
+    """load_data of the reference's privacy block (:970-976)."""
+    return {k: np.load(os.path.join(folder, k + ".npy")) for k in ("data_real", "data_gen", "test_real", "test_gen")}
+
+
+def privacy_report(output_path: str) -> dict:
+    """DCR / NNDR over every <output_path>/test_* folder, mean and std (:978-995), on the GPU kernels."""
+    from glob import glob
+
+    from . import evalmetrics as em
+
+    dcr_scores, nndr_scores = [], []
+    for folder in sorted(glob(os.path.join(output_path, "test_*"))):
+        data = load_generated_arrays(folder)
+        dcr_scores.append(em.dcr(data["data_real"], data["data_gen"], data["test_real"]))
+        nndr_scores.append(em.nndr(data["data_real"], data["data_gen"], data["test_real"]))
+    return {"dcr": dcr_scores, "nndr": nndr_scores, "mean_dcr": float(np.mean(dcr_scores)),
+            "std_dcr": float(np.std(dcr_scores)), "mean_nndr": float(np.mean(nndr_scores)),
+            "std_nndr": float(np.std(nndr_scores))}

@@ -200,3 +200,66 @@ def test_evaluate_generated_composition(host):
         assert got[key + "_test"] == pytest.approx(test_want[key], abs=1e-9), key
     assert got["gamma"] == pytest.approx(float(ref.gamma_coef(test, test_gen)), abs=5e-6)
     assert got["dcr"] == pytest.approx(float(fx["dcr"]), abs=1e-12) and got["nndr"] == pytest.approx(float(fx["nndr"]), abs=1e-12)
+
+
+def test_generated_array_layout_and_privacy_report(host, tmp_path):
+    """The twelve .npy files of the reference's test block and the DCR / NNDR report read back from them."""
+    from gemmgan_b200 import trainer as tr
+
+    fx = load("eval_privacy")
+    real, gen, test = fx["real"], fx["fake"], fx["test"]
+    lab = lambda a: np.arange(len(a)) % 7
+    for run in range(2):
+        tr.save_generated_arrays(os.path.join(tmp_path, f"test_{run}_epoch_5"),
+                                 (real, gen[: len(real)], lab(real), lab(real), lab(real), lab(real)),
+                                 (test, gen[:len(test)], lab(test), lab(test), lab(test), lab(test)))
+    names = sorted(os.listdir(os.path.join(tmp_path, "test_0_epoch_5")))
+    assert names == sorted(n + ".npy" for n in (
+        "data_real", "data_gen", "test_real", "test_gen", "train_labels_real", "train_labels_gen", "test_labels_real",
+        "test_labels_gen", "train_primary_site_real", "train_primary_site_gen", "test_primary_site_real",
+        "test_primary_site_gen"))                                    # …with_film.py:795-806
+    back = tr.load_generated_arrays(os.path.join(tmp_path, "test_1_epoch_5"))
+    assert np.array_equal(back["data_real"], real) and np.array_equal(back["test_gen"], gen[:len(test)])
+    rep = tr.privacy_report(str(tmp_path))
+    want = ref.dcr(real, gen[: len(real)], test)
+    assert rep["dcr"] == [want, want] and rep["std_dcr"] == 0.0
+    assert rep["mean_nndr"] == pytest.approx(ref.nndr(real, gen[: len(real)], test), abs=1e-12)
+    with pytest.raises(ValueError):
+        tr.save_generated_arrays(str(tmp_path / "bad"), (real, gen), (test, gen))
+
+
+def test_fit_evaluation_block(host, tmp_path):
+    """TrainerBase._fit_evaluation (the GPU part of the reference fit()'s evaluation, …with_film.py:702-811) on a stub
+    trainer whose generate_samples_all returns fixed arrays: per-epoch precision / recall / gamma at the test
+    frequency, and the two saved runs with their metrics at the last epoch."""
+    from gemmgan_b200.trainer import TrainerBase
+
+    fx = load("eval_privacy")
+    lab = lambda a: np.arange(len(a)) % 5
+    six = lambda real, gen: (real, gen, lab(real), lab(real), lab(real), lab(real))
+    loaders = {"train": six(fx["real"], fx["fake"][:70]), "val": six(fx["test"], fx["fake"][70:110]),
+               "test": six(fx["test"], fx["fake"][110:150])}
+
+    class Stub(TrainerBase):
+        def __init__(self):
+            self.result_dire, self.freq_compute_test = str(tmp_path), 2
+            self.precision_scores, self.recall_scores, self.corr_scores = {}, {}, {}
+
+        def generate_samples_all(self, loader):
+            return loaders[loader]
+
+    t = Stub()
+    for epoch in range(4):
+        t._fit_evaluation(epoch, 4, "train", "val", "test", val=True)
+    assert sorted(t.precision_scores) == [2, 4] and sorted(t.corr_scores) == [2, 4]
+    want = ref.compute_prdc(fx["test"], fx["fake"][70:110], 10)
+    assert t.precision_scores[2] == pytest.approx(want["precision"], abs=1e-9)
+    assert t.recall_scores[4] == pytest.approx(want["recall"], abs=1e-9)
+    assert t.corr_scores[2] == pytest.approx(float(ref.gamma_coef(fx["test"], fx["fake"][70:110])), abs=5e-6)
+    assert [os.path.basename(r["folder"]) for r in t.test_runs] == ["test_0_epoch_4", "test_1_epoch_4"]
+    assert t.test_runs[0]["dcr"] == pytest.approx(ref.dcr(fx["real"], fx["fake"][:70], fx["test"]), abs=1e-12)
+    assert np.array_equal(np.load(os.path.join(t.test_runs[1]["folder"], "test_gen.npy")), fx["fake"][110:150])
+    quiet = Stub()
+    quiet._fit_evaluation(3, 4, "train", None, None, val=True)        # no loaders: nothing happens
+    quiet._fit_evaluation(3, 4, "train", "val", "test", val=False)
+    assert quiet.precision_scores == {} and not hasattr(quiet, "test_runs")

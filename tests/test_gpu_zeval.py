@@ -104,7 +104,12 @@ def test_evaluate_generated_after_fit(host, tmp_path):
     mk = lambda n, seed: synthetic_loader("paper", n_samples=n, batch_size=B, n_genes=G, n_patches=5, n_tokens=3,
                                           seed=seed, text_dim=24, patch_dim=40, ragged=True)
     train, test = mk(4 * B, 1), mk(2 * B, 2)
-    t.fit(train, None, None, epochs=1)
+    t.freq_compute_test = 1
+    t.fit(train, test, test, epochs=1)                   # validation + test loaders: the evaluation block runs
+    assert sorted(t.precision_scores) == [1] and sorted(t.corr_scores) == [1] and len(t.test_runs) == 2
+    assert (tmp_path / "test_1_epoch_1" / "train_primary_site_gen.npy").exists()
+    assert np.load(tmp_path / "test_0_epoch_1" / "test_real.npy").shape == (2 * B, G)
+    assert 0.0 <= t.test_runs[0]["dcr"] <= 1.0 and -1.0 <= t.test_runs[0]["gamma"] <= 1.0
     data_real, data_gen = t.generate_samples_all(train)[:2]
     test_real, test_gen = t.generate_samples_all(test)[:2]
     got = t.evaluate_generated(data_real, data_gen, test_real, test_gen, nn=5)
