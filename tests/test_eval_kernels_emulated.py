@@ -32,7 +32,10 @@ def emu(tmp_path_factory):
     if gxx is None or not os.path.isfile(os.path.join(CUDA_INC, "cuda_runtime.h")):
         pytest.skip("g++ or the CUDA headers are not available")
     out = tmp_path_factory.mktemp("cuda_emu") / "libevalmetrics_emu.so"
-    subprocess.check_call([gxx, "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-I", CUDA_INC,
+    # GEMMGAN_EMU_ASAN=1 (with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0): the kernels'
+    # global-memory accesses are checked against the redzones of the numpy / torch allocations
+    extra = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("GEMMGAN_EMU_ASAN") == "1" else []
+    subprocess.check_call([gxx, "-std=c++20", "-O1", *extra, "-shared", "-fPIC", "-pthread", "-I", CUDA_INC,
                            "-I", os.path.join(ROOT, "include"), EMU_SRC, "-o", str(out)])
     L = C.CDLL(str(out))
     L.gg_last_error.restype = C.c_char_p
