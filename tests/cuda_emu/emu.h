@@ -1,0 +1,242 @@
+#pragma once
+// TEST INFRASTRUCTURE ONLY -- lets g++ compile a gemmgan_b200/csrc/*.cu file UNCHANGED and run its (tensor-core-free)
+// kernels on the host, so that the build container (no GPU) can check index arithmetic, reductions, tails and argument
+// handling against the oracle / torch, optionally under AddressSanitizer (tests/test_*_emulated.py). Usage: a
+// translation unit includes this header and then the .cu file. It is not a CPU path of the product: nothing under
+// gemmgan_b200/ can load the result, and it is orders of magnitude too slow to be one.
+//
+// Execution model: the threads of a CTA are fibers (ucontext) scheduled round-robin on one host thread, the CTAs of a
+// launch are spread over the host's cores. `__shared__` becomes `static thread_local` (one copy per host thread = per
+// CTA in flight), __syncthreads() a counting barrier that exited threads leave (as on the GPU), __shfl_down_sync an
+// exchange through a per-warp slot array. What this cannot show: data races inside a CTA (fibers never run
+// concurrently), performance, anything about the real launch.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <algorithm>
+#include <atomic>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+using std::max;
+using std::min;
+
+namespace emu {
+// One CTA = up to 256 fibers (ucontext) scheduled round-robin on ONE host thread; CTAs of a launch are spread over the
+// host's cores. A barrier is "count arrivals, yield until the generation changes"; threads that leave the kernel stop
+// counting (as exited threads do on the GPU).
+constexpr int MAX_THREADS = 256;
+constexpr size_t STACK_BYTES = 64 * 1024;
+struct Barrier {
+  int live = 0, arrived = 0;
+  long gen = 0;
+};
+struct Warp {
+  Barrier bar;
+  alignas(8) unsigned char slot[32][8];
+};
+struct Cta {
+  Barrier bar;
+  Warp warps[MAX_THREADS / 32];
+};
+struct Fiber {
+  ucontext_t ctx;
+  bool done = false;
+  uint3 tid;
+};
+struct Worker {  // per host thread
+  ucontext_t sched;
+  std::vector<Fiber> fibers;
+  std::vector<char> stacks;
+  int cur = 0;
+  Cta cta;
+  std::function<void()> body;
+};
+thread_local Worker* t_worker = nullptr;
+thread_local uint3 t_thread, t_block;
+thread_local dim3 t_block_dim, t_grid_dim;
+
+inline void yield() {
+  Worker* w = t_worker;
+  swapcontext(&w->fibers[w->cur].ctx, &w->sched);
+}
+inline void barrier_wait(Barrier& b) {
+  const long g = b.gen;
+  if (++b.arrived == b.live) {
+    b.arrived = 0;
+    ++b.gen;
+    return;
+  }
+  while (b.gen == g) yield();
+}
+inline void barrier_leave(Barrier& b) {
+  --b.live;
+  if (b.live > 0 && b.arrived == b.live) {
+    b.arrived = 0;
+    ++b.gen;
+  }
+}
+inline void fiber_entry() {
+  Worker* w = t_worker;
+  w->body();
+  const int t = w->cur;
+  barrier_leave(w->cta.warps[t / 32].bar);
+  barrier_leave(w->cta.bar);
+  w->fibers[t].done = true;
+  swapcontext(&w->fibers[t].ctx, &w->sched);  // never resumed
+}
+
+// Runs one CTA of `nthreads` threads on the calling host thread.
+inline void run_cta(int nthreads, dim3 block, const std::function<void()>& body) {
+  static thread_local Worker worker;
+  Worker* w = &worker;
+  t_worker = w;
+  w->body = body;
+  w->fibers.assign(nthreads, Fiber());
+  w->stacks.resize(static_cast<size_t>(nthreads) * STACK_BYTES);
+  w->cta = Cta();
+  w->cta.bar.live = nthreads;
+  for (int q = 0; q < (nthreads + 31) / 32; ++q) w->cta.warps[q].bar.live = std::min(32, nthreads - 32 * q);
+  for (int t = 0; t < nthreads; ++t) {
+    Fiber& f = w->fibers[t];
+    f.tid = uint3{static_cast<unsigned>(t) % block.x, (static_cast<unsigned>(t) / block.x) % block.y,
+                  static_cast<unsigned>(t) / (block.x * block.y)};
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = w->stacks.data() + static_cast<size_t>(t) * STACK_BYTES;
+    f.ctx.uc_stack.ss_size = STACK_BYTES;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, fiber_entry, 0);
+  }
+  for (int remaining = nthreads; remaining > 0;) {
+    for (int t = 0; t < nthreads; ++t) {
+      Fiber& f = w->fibers[t];
+      if (f.done) continue;
+      w->cur = t;
+      t_thread = f.tid;
+      swapcontext(&w->sched, &f.ctx);
+      if (f.done) --remaining;
+    }
+  }
+}
+
+template <class... KArgs>
+cudaError_t launch(const cudaLaunchConfig_t* cfg, void (*kern)(KArgs...), KArgs... args) {
+  const dim3 grid = cfg->gridDim, block = cfg->blockDim;
+  const int nthreads = static_cast<int>(block.x * block.y * block.z);
+  if (nthreads < 1 || nthreads > MAX_THREADS) return cudaErrorInvalidConfiguration;
+  const long n_cta = static_cast<long>(grid.x) * grid.y * grid.z;
+  std::atomic<long> next{0};
+  auto host_thread = [&] {
+    for (long c = next.fetch_add(1); c < n_cta; c = next.fetch_add(1)) {
+      t_block = uint3{static_cast<unsigned>(c % grid.x), static_cast<unsigned>((c / grid.x) % grid.y),
+                      static_cast<unsigned>(c / (static_cast<long>(grid.x) * grid.y))};
+      t_block_dim = block;
+      t_grid_dim = grid;
+      run_cta(nthreads, block, [&] { kern(args...); });
+    }
+  };
+  const int n_host = static_cast<int>(std::min<long>(n_cta, std::max(1u, std::thread::hardware_concurrency())));
+  std::vector<std::thread> hosts;
+  for (int i = 1; i < n_host; ++i) hosts.emplace_back(host_thread);
+  host_thread();
+  for (auto& h : hosts) h.join();
+  return cudaSuccess;
+}
+}  // namespace emu
+
+static inline void __syncthreads() { emu::barrier_wait(emu::t_worker->cta.bar); }
+template <class T>
+static inline T __shfl_down_sync(unsigned, T v, int offset) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  emu::Worker* w = emu::t_worker;
+  const int t = w->cur, lane = t % 32;
+  emu::Warp& warp = w->cta.warps[t / 32];
+  memcpy(warp.slot[lane], &v, sizeof(T));
+  emu::barrier_wait(warp.bar);
+  T r = v;
+  if (lane + offset < 32) memcpy(&r, warp.slot[lane + offset], sizeof(T));
+  emu::barrier_wait(warp.bar);
+  return r;
+}
+template <class T>
+static inline T emu_shfl_from(T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  emu::Worker* w = emu::t_worker;
+  const int t = w->cur, lane = t % 32;
+  emu::Warp& warp = w->cta.warps[t / 32];
+  memcpy(warp.slot[lane], &v, sizeof(T));
+  emu::barrier_wait(warp.bar);
+  T r = v;
+  if (src_lane >= 0 && src_lane < 32) memcpy(&r, warp.slot[src_lane], sizeof(T));
+  emu::barrier_wait(warp.bar);
+  return r;
+}
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int mask) { return emu_shfl_from(v, (emu::t_worker->cur % 32) ^ mask); }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl_from(v, src & 31); }
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+template <class T>
+static inline T __ldcg(const T* p) { return *p; }
+template <class T>
+static inline void __stcg(T* p, T v) { *p = v; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline float atomicAdd(float* p, float v) {
+  float old = *p, want;
+  do want = old + v;
+  while (!__atomic_compare_exchange(p, &old, &want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+  return old;
+}
+static inline float __int_as_float(int v) {
+  float f;
+  memcpy(&f, &v, 4);
+  return f;
+}
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+
+static inline cudaError_t emu_get_device(int* d) {
+  *d = 0;
+  return cudaSuccess;
+}
+// runtime calls made by host_util.h's launch helpers / check macros and by the entry points
+#define cudaLaunchKernelEx emu::launch
+#define cudaGetLastError() cudaSuccess
+#define cudaGetErrorString(e) "emulated"
+#define cudaGetDevice emu_get_device
+
+// ---- what abi.cu provides in the real library
+#include "../../gemmgan_b200/csrc/host_util.h"
+namespace gg {
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launch_count{0};
+bool pdl_enabled() { return true; }
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace gg
+extern "C" const char* gg_last_error(void) { return gg::g_err; }
+extern "C" int gg_check_device(int) { return GG_OK; }
+
+// ---- rebind the CUDA spellings the kernel source uses, then compile it as it is
+#undef __shared__
+#define __shared__ static thread_local
+#define __launch_bounds__(...)
+#define threadIdx emu::t_thread
+#define blockIdx emu::t_block
+#define blockDim emu::t_block_dim
+#define gridDim emu::t_grid_dim
+#define asm
+#define volatile(...) ((void)0)  // pdl.cuh: asm volatile("griddepcontrol...") -> no-op

@@ -1,0 +1,29 @@
+"""Builds one host-emulation translation unit of tests/cuda_emu/ (see tests/cuda_emu/emu.h) into a shared library.
+TEST INFRASTRUCTURE ONLY: the product binds libgemmgan_sm100a.so and nothing else."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+
+
+def build(unit: str, outdir) -> C.CDLL:
+    """unit = 'evalmetrics' -> tests/cuda_emu/emu_evalmetrics.cpp. GEMMGAN_EMU_ASAN=1 (with
+    LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0) adds AddressSanitizer, so the kernels'
+    global-memory accesses are checked against the redzones of the numpy / torch allocations."""
+    gxx = shutil.which("g++")
+    if gxx is None or not os.path.isfile(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("g++ or the CUDA headers are not available")
+    src = os.path.join(ROOT, "tests", "cuda_emu", f"emu_{unit}.cpp")
+    out = os.path.join(str(outdir), f"lib{unit}_emu.so")
+    extra = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("GEMMGAN_EMU_ASAN") == "1" else []
+    subprocess.check_call([gxx, "-std=c++20", "-O1", *extra, "-shared", "-fPIC", "-pthread", "-I", CUDA_INC,
+                           "-I", os.path.join(ROOT, "include"), src, "-o", out])
+    L = C.CDLL(out)
+    L.gg_last_error.restype = C.c_char_p
+    return L
