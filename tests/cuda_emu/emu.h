@@ -6,7 +6,7 @@
 // gemmgan_b200/ can load the result, and it is orders of magnitude too slow to be one.
 //
 // Execution model: the threads of a CTA are fibers (ucontext) scheduled round-robin on one host thread, the CTAs of a
-// launch are spread over the host's cores. `__shared__` becomes `static thread_local` (one copy per host thread = per
+// launch are spread over the host's cores. `__shared__` becomes `thread_local` (one copy per host thread = per
 // CTA in flight), __syncthreads() a counting barrier that exited threads leave (as on the GPU), __shfl_down_sync an
 // exchange through a per-warp slot array. What this cannot show: data races inside a CTA (fibers never run
 // concurrently), performance, anything about the real launch.
@@ -232,7 +232,11 @@ extern "C" int gg_check_device(int) { return GG_OK; }
 
 // ---- rebind the CUDA spellings the kernel source uses, then compile it as it is
 #undef __shared__
-#define __shared__ static thread_local
+// block-scope `thread_local` is implicitly static: one copy per host thread = per CTA in flight. Dynamic shared memory
+// (`extern __shared__ T name[];`) becomes a block-scope extern declaration of a thread_local array that the including
+// translation unit defines at namespace scope, with the name and type the .cu uses and the largest size it launches.
+#define __shared__ thread_local
+#define cudaFuncSetAttribute(...) cudaSuccess
 #define __launch_bounds__(...)
 #define threadIdx emu::t_thread
 #define blockIdx emu::t_block

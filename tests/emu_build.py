@@ -22,7 +22,7 @@ def build(unit: str, outdir) -> C.CDLL:
     src = os.path.join(ROOT, "tests", "cuda_emu", f"emu_{unit}.cpp")
     out = os.path.join(str(outdir), f"lib{unit}_emu.so")
     extra = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("GEMMGAN_EMU_ASAN") == "1" else []
-    subprocess.check_call([gxx, "-std=c++20", "-O1", *extra, "-shared", "-fPIC", "-pthread", "-I", CUDA_INC,
+    subprocess.check_call([gxx, "-std=c++20", "-O1", "-fno-extern-tls-init", *extra, "-shared", "-fPIC", "-pthread", "-I", CUDA_INC,
                            "-I", os.path.join(ROOT, "include"), src, "-o", out])
     L = C.CDLL(out)
     L.gg_last_error.restype = C.c_char_p
