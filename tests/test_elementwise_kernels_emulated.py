@@ -268,3 +268,35 @@ def test_embedding_gather_and_deterministic_table_gradient(k):
     k.embed_grad(dc, y0, y1, V0, V1, g0, g1, B, Eh)
     close(g0, e0.grad, 1e-6)
     close(g1, e1.grad, 1e-6)
+
+
+class ColsumItem(C.Structure):   # gg_colsum_item, include/gemmgan.h
+    _fields_ = [("inp", vp), ("ld", i64), ("rows", i64), ("N", i32), ("out", vp)]
+
+
+def test_grouped_column_sums_are_exact_and_deterministic(k):
+    """Every bias gradient of one backward pass in one launch (gg_colsum_group): problems of different shapes, the
+    16-byte and the scalar path, one chunk and several (last-arriver reduction in chunk order), arrival counters left
+    at zero so that the next launch can reuse the workspace."""
+    L = k.L
+    L.emu_colsum_group.argtypes = [vp, i32, vp, i64]
+    L.emu_colsum_group_workspace_bytes.argtypes = [i64]
+    L.emu_colsum_group_workspace_bytes.restype = i64
+    g = torch.Generator().manual_seed(9)
+    shapes = [(300, 256, 256), (5000, 70, 72), (4100, 64, 67), (9, 1, 8), (2049, 130, 136)]   # rows, N, pitch
+    xs = [torch.randn(r, ld, generator=g).bfloat16() for r, _, ld in shapes]
+    outs = [torch.full((n,), -3.0) for _, n, _ in shapes]
+    items = (ColsumItem * len(shapes))(*[ColsumItem(x.data_ptr(), ld, r, n, o.data_ptr())
+                                         for x, o, (r, n, ld) in zip(xs, outs, shapes)])
+    nbytes = int(L.emu_colsum_group_workspace_bytes(sum(n for _, n, _ in shapes)))
+    ws = torch.zeros(nbytes, dtype=torch.uint8)
+    assert L.emu_colsum_group(C.addressof(items), len(shapes), ws.data_ptr(), nbytes) == 0, L.gg_last_error()
+    first = [o.clone() for o in outs]
+    for x, o, (r, n, ld) in zip(xs, outs, shapes):
+        close(o, x.float()[:, :n].sum(0), 2e-5)
+    assert torch.all(ws[: 64 * 1024] == 0)                       # counters are back at zero
+    for o in outs:
+        o.fill_(7.0)
+    assert L.emu_colsum_group(C.addressof(items), len(shapes), ws.data_ptr(), nbytes) == 0
+    assert all(torch.equal(a, b) for a, b in zip(first, outs))   # bit-identical on the second launch
+    assert L.emu_colsum_group(C.addressof(items), 41, ws.data_ptr(), nbytes) == -1   # more than COLSUM_GROUP_MAX
