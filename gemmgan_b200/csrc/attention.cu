@@ -493,6 +493,10 @@ constexpr int SELF_THREADS = SELF_GROUPS * 32;
 constexpr int SELF_TILE = 16 * SELF_PITCH;  // one 16-row tile (elements)
 constexpr int SELF_SP = 24;               // pitch of the 16x16 bf16 dS / P tiles
 
+// The five PTX wrappers below are the only inline assembly the kernels of this file depend on for their results;
+// tests/cuda_emu/emu_attention.cpp defines GG_EMULATED_PTX and supplies host versions of them (cp.async as a copy,
+// ldmatrix / mma.sync as warp-collective exchanges), so that the kernels themselves run unchanged on the CPU suite.
+#ifndef GG_EMULATED_PTX
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   const int sz = valid ? 16 : 0;
@@ -522,6 +526,7 @@ __device__ __forceinline__ float fast_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
 }
+#endif  // GG_EMULATED_PTX
 constexpr float SCALE_LOG2E = 0.125f * 1.4426950408889634f;  // log2(e) / sqrt(64)
 
 __device__ __forceinline__ uint32_t pack_bf16(float x, float y) {

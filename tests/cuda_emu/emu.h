@@ -32,7 +32,7 @@ namespace emu {
 // One CTA = up to 256 fibers (ucontext) scheduled round-robin on ONE host thread; CTAs of a launch are spread over the
 // host's cores. A barrier is "count arrivals, yield until the generation changes"; threads that leave the kernel stop
 // counting (as exited threads do on the GPU).
-constexpr int MAX_THREADS = 256;
+constexpr int MAX_THREADS = 1024;
 constexpr size_t STACK_BYTES = 64 * 1024;
 struct Barrier {
   int live = 0, arrived = 0;
@@ -40,7 +40,7 @@ struct Barrier {
 };
 struct Warp {
   Barrier bar;
-  alignas(8) unsigned char slot[32][8];
+  alignas(8) unsigned char slot[32][32];
 };
 struct Cta {
   Barrier bar;
@@ -178,6 +178,23 @@ static inline T emu_shfl_from(T v, int src_lane) {
   emu::barrier_wait(warp.bar);
   return r;
 }
+// every lane contributes `mine`; all lanes receive the 32 contributions (warp-collective instructions are built on this)
+template <class T>
+static inline void emu_warp_all_gather(const T& mine, T (&all)[32]) {
+  static_assert(sizeof(T) <= 32, "gather payload");
+  emu::Worker* w = emu::t_worker;
+  const int t = w->cur, lane = t % 32;
+  emu::Warp& warp = w->cta.warps[t / 32];
+  memcpy(warp.slot[lane], &mine, sizeof(T));
+  emu::barrier_wait(warp.bar);
+  for (int l = 0; l < 32; ++l) memcpy(&all[l], warp.slot[l], sizeof(T));
+  emu::barrier_wait(warp.bar);
+}
+static inline int emu_lane() { return emu::t_worker->cur % 32; }
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+  emu::Worker* w = emu::t_worker;
+  emu::barrier_wait(w->cta.warps[w->cur / 32].bar);
+}
 template <class T>
 static inline T __shfl_xor_sync(unsigned, T v, int mask) { return emu_shfl_from(v, (emu::t_worker->cur % 32) ^ mask); }
 template <class T>
@@ -190,6 +207,9 @@ template <class T>
 static inline void __stcg(T* p, T v) { *p = v; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+// CUDA's fast-math intrinsics share their names with glibc-internal aliases that <math.h> declares but libm does not export
+extern "C" __attribute__((weak)) float __expf(float x) noexcept { return expf(x); }
+extern "C" __attribute__((weak)) float __logf(float x) noexcept { return logf(x); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline float atomicAdd(float* p, float v) {
   float old = *p, want;
