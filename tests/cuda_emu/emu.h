@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <ucontext.h>
 
@@ -205,6 +206,23 @@ template <class T>
 static inline T __ldcg(const T* p) { return *p; }
 template <class T>
 static inline void __stcg(T* p, T v) { *p = v; }
+template <class T>
+static inline T __ldcs(const T* p) { return *p; }
+static inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
+static inline long long clock64() { return 0; }
+static inline void __trap() { abort(); }
+template <class T>
+static inline T atomicMin(T* p, T v) {
+  T old = *p;
+  while (v < old && !__atomic_compare_exchange(p, &old, &v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+template <class T>
+static inline T atomicMax(T* p, T v) {
+  T old = *p;
+  while (old < v && !__atomic_compare_exchange(p, &old, &v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 // CUDA's fast-math intrinsics share their names with glibc-internal aliases that <math.h> declares but libm does not export
@@ -258,6 +276,7 @@ extern "C" int gg_check_device(int) { return GG_OK; }
 #define __shared__ thread_local
 #define cudaFuncSetAttribute(...) cudaSuccess
 #define __launch_bounds__(...)
+#define __noinline__
 #define threadIdx emu::t_thread
 #define blockIdx emu::t_block
 #define blockDim emu::t_block_dim

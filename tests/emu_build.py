@@ -10,9 +10,10 @@ import pytest
 from conftest import ROOT
 
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+CUDA_LIB = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/lib64"
 
 
-def build(unit: str, outdir) -> C.CDLL:
+def build(unit: str, outdir, cudart: bool = False) -> C.CDLL:
     """unit = 'evalmetrics' -> tests/cuda_emu/emu_evalmetrics.cpp. GEMMGAN_EMU_ASAN=1 (with
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0) adds AddressSanitizer, so the kernels'
     global-memory accesses are checked against the redzones of the numpy / torch allocations."""
@@ -23,7 +24,9 @@ def build(unit: str, outdir) -> C.CDLL:
     out = os.path.join(str(outdir), f"lib{unit}_emu.so")
     extra = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("GEMMGAN_EMU_ASAN") == "1" else []
     subprocess.check_call([gxx, "-std=c++20", "-O1", "-fno-extern-tls-init", *extra, "-shared", "-fPIC", "-pthread", "-I", CUDA_INC,
-                           "-I", os.path.join(ROOT, "include"), src, "-o", out])
+                           "-I", os.path.join(ROOT, "include"), src, "-o", out] + (
+        # host-side runtime symbols some files reference but the emulated paths never call
+        ["-L", CUDA_LIB, "-Wl,-rpath," + CUDA_LIB, "-lcudart"] if cudart else []))
     L = C.CDLL(out)
     L.gg_last_error.restype = C.c_char_p
     return L
