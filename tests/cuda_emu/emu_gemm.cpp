@@ -11,4 +11,8 @@
 
 #include "emu.h"
 
+namespace gg {
+thread_local uint8_t smem_raw[1024];  // `extern __shared__` of gemm_tc_kernel (declared, never run here)
+}
+
 #include "../../gemmgan_b200/csrc/gemm.cu"
