@@ -68,9 +68,11 @@ def reference(qkv, nb, H, S, mask, dout):
 
 
 # short register kernel (S <= 16), mma.sync mid kernel (17..128), flash-style long kernel (129..320; 257 = the
-# reference's 256 patches + CLS runs with 17 warps), generic paths (hd != 64)
+# reference's 256 patches + CLS runs with 17 warps, 288 / 304 with 18 / 19, 305 and 320 = 20 tiles on 16 warps),
+# generic paths (hd != 64)
 @pytest.mark.parametrize("nb,H,hd,S", [(5, 4, 64, 9), (3, 4, 64, 16), (2, 4, 64, 3), (3, 4, 8, 6), (2, 4, 64, 17),
                                        (2, 4, 64, 65), (1, 4, 64, 128), (1, 2, 64, 129), (1, 2, 64, 257),
+                                       (1, 1, 64, 288), (1, 1, 64, 304), (1, 1, 64, 305), (1, 1, 64, 320),
                                        (1, 2, 32, 40)])
 @pytest.mark.parametrize("masked", [False, True])
 def test_self_attention_matches_sdpa(emu, nb, H, hd, S, masked):
