@@ -131,7 +131,11 @@ class Engine:
         self.gen, self.disc = gen, disc
         nbytes = C.c_int64(0)
         _lib.check(self.lib.gg_engine_workspace_bytes(C.byref(cfg), C.byref(nbytes)))
-        self.workspace = torch.empty(nbytes.value, device=self.device, dtype=torch.uint8)
+        # the engine wants a 256-byte aligned workspace: CUDA allocations are (offset 0), host allocations of the
+        # emulated test build are not
+        raw = torch.empty(nbytes.value + 256, device=self.device, dtype=torch.uint8)
+        off = (-raw.data_ptr()) % 256
+        self.workspace = raw[off:off + nbytes.value]
         self._gen_c, self._disc_c = gen.c_struct(), disc.c_struct()
         h = C.c_void_p()
         with torch.cuda.device(self.device):

@@ -246,6 +246,36 @@ static inline cudaError_t emu_get_device(int* d) {
   *d = 0;
   return cudaSuccess;
 }
+// Streams and events: every emulated launch completes before it returns, so streams are opaque tokens, event record /
+// wait are no-ops and the asynchronous copies are plain copies ("device" memory is host memory).
+static inline cudaError_t emu_stream_create(cudaStream_t* s, unsigned = 0) {
+  static int token;
+  *s = reinterpret_cast<cudaStream_t>(&token);
+  return cudaSuccess;
+}
+static inline cudaError_t emu_event_create(cudaEvent_t* e, unsigned = 0) {
+  static int token;
+  *e = reinterpret_cast<cudaEvent_t>(&token);
+  return cudaSuccess;
+}
+static inline cudaError_t emu_ok(...) { return cudaSuccess; }
+static inline cudaError_t emu_memcpy(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) {
+  memmove(dst, src, n);
+  return cudaSuccess;
+}
+static inline cudaError_t emu_memset(void* dst, int v, size_t n, cudaStream_t = nullptr) {
+  memset(dst, v, n);
+  return cudaSuccess;
+}
+#define cudaStreamCreateWithFlags emu_stream_create
+#define cudaEventCreateWithFlags emu_event_create
+#define cudaStreamDestroy emu_ok
+#define cudaEventDestroy emu_ok
+#define cudaEventRecord emu_ok
+#define cudaStreamWaitEvent emu_ok
+#define cudaStreamSynchronize emu_ok
+#define cudaMemcpyAsync emu_memcpy
+#define cudaMemsetAsync emu_memset
 // runtime calls made by host_util.h's launch helpers / check macros and by the entry points
 #define cudaLaunchKernelEx emu::launch
 #define cudaGetLastError() cudaSuccess

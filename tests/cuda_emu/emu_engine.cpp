@@ -1,0 +1,42 @@
+// Host build of the WHOLE engine (see emu.h): engine.cu with every kernel file it sequences, in its all-CUDA-core
+// configuration (gg_model_cfg.gemm_impl = GG_IMPL_SIMT_F32: every GEMM of the step runs on the check kernel of gemm.cu
+// with the shared epilogue; weight gradients take the per-problem path instead of the grouped tcgen05 kernel). One
+// critic step / generator step / optimizer step of any variant then runs on the CPU through the same gg_engine_* C
+// ABI and gemmgan_b200/runtime.py, and is compared with the oracle (tests/test_engine_emulated.py).
+// Not emulated: the tcgen05 / TMA main loops (gemm_tc_kernel, wgrad_group_kernel) — k_wgrad_group is a stub that
+// reports GG_ERR_ARCH — and everything about streams (launches complete synchronously, lanes are tokens).
+#define GG_EMULATED_PTX 1
+#include <cuda.h>
+
+#include <mutex>
+#include <vector>
+
+#include "emu.h"
+#include "emu_attention_ptx.h"
+
+namespace gg {
+thread_local float sm[64 * 1024 / 4];  // layernorm.cu: add_ln_bwd_kernel
+thread_local uint8_t smem_raw[1024];   // gemm.cu: gemm_tc_kernel (declared, never run here)
+}  // namespace gg
+
+#include "../../gemmgan_b200/csrc/elementwise.cu"
+#include "../../gemmgan_b200/csrc/optim.cu"
+#include "../../gemmgan_b200/csrc/layernorm.cu"
+#include "../../gemmgan_b200/csrc/attention.cu"
+#include "../../gemmgan_b200/csrc/gemm.cu"
+#include "../../gemmgan_b200/csrc/evalmetrics.cu"
+
+namespace gg {
+int64_t wgrad_group_workspace_bytes(int64_t max_output_elems) { return GROUP_COUNTER_BYTES + 4 * max_output_elems; }
+int k_wgrad_group(const WgradItem*, int, void*, int64_t, cudaStream_t) {
+  set_error("the grouped weight-gradient kernel is tcgen05 only (not available in the host emulation)");
+  return GG_ERR_ARCH;
+}
+}  // namespace gg
+
+#include "../../gemmgan_b200/csrc/engine.cu"
+
+// the three entry points of abi.cu that are not already in emu.h
+extern "C" int gg_abi_version(void) { return GG_ABI_VERSION; }
+extern "C" void gg_launch_count_add(long long n) { gg::g_launch_count.fetch_add(n); }
+extern "C" long long gg_launch_count(int reset) { return reset ? gg::g_launch_count.exchange(0) : gg::g_launch_count.load(); }

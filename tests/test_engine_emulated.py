@@ -1,0 +1,183 @@
+"""The WHOLE training step on the CPU suite: gg_engine_* (gemmgan_b200/csrc/engine.cu and every kernel file it
+sequences) compiled for the host (tests/cuda_emu/emu_engine.cpp) in the engine's all-CUDA-core configuration
+(gemm_impl = GG_IMPL_SIMT_F32), driven through gemmgan_b200/runtime.py exactly as the trainer drives it
+(set_batch -> disc_grads -> optim_step, gen_grads -> optim_step), against the oracle (oracle/restated.py, pinned to the
+unmodified reference) on the same weights, batch and noise: WGAN_GP.train_disc / train_gen of
+src/conditional_gan_cross_attention_with_film.py:376-461 and src/vanilla_gan_unconditional.py.
+
+What this covers that the per-kernel emulation tests do not: the hand-written backward / double backward as the engine
+sequences it (Gram-matrix gradient penalty, shared [fake; real] GEMM, replica batching, FiLM and tower backward, two
+post-norm encoder layers, both single-query attentions), the parameter slot tables, the clip + optimizer update on the
+flat buffers. What it cannot cover: the tcgen05 / TMA GEMMs and the grouped weight-gradient kernel (GPU only; on the
+B200 tests/test_gpu_parity.py makes the same comparisons through the drop-in trainers), lanes, graphs, NCCL.
+
+Tolerances are those of tests/test_gpu_parity.py (bf16 operands, fp32 accumulation): 2e-2 of the tensor's scale on
+outputs / scores / GP, relative Frobenius on gradients (ReLU mask flips).
+"""
+import contextlib
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import emu_build
+from gemmgan_b200 import _abi_decl as A
+from gemmgan_b200 import _lib, runtime
+from oracle import restated
+
+TOL = 2e-2
+SMALL = dict(B=8, G=203, P=5, T=3, embed=32, hidden=32, latent=16, text_dim=24, patch_dim=32)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    L = emu_build.build("engine", tmp_path_factory.mktemp("cuda_emu"), cudart=True)
+    A.declare(L)
+    return L
+
+
+@pytest.fixture()
+def rt(emu, monkeypatch):
+    monkeypatch.setattr(_lib, "lib", lambda: emu)
+    monkeypatch.setattr(_lib, "require_device", lambda dev=0: None)
+    monkeypatch.setattr(runtime, "_stream", lambda: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    return runtime
+
+
+def rel(a, b):
+    a, b = a.detach().float(), b.detach().float()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+def fro(a, b):
+    a, b = a.detach().float(), b.detach().float()
+    return (a - b).norm().item() / max(b.norm().item(), 1e-12)
+
+
+def build(rt, variant, cfg, optimizer, slope, seed=11):
+    """(oracle, generator, critic, engine) with identical initial weights; nets from the drop-in modules."""
+    torch.manual_seed(seed)
+    o = restated.OracleWGANGP(variant, cfg["G"], latent=cfg["latent"], embed=cfg["embed"], hidden=cfg["hidden"],
+                              optimizer=optimizer, negative_slope=slope, dropout=0.0, text_dim=cfg["text_dim"],
+                              patch_dim=cfg["patch_dim"])
+    torch.manual_seed(seed)
+    H, G = cfg["hidden"], cfg["G"]
+    if variant == "vanilla":
+        import vanilla_gan_unconditional as m
+        gen, disc = m.WGAN_GP_model_nocond(cfg["latent"], G, [], [], [H, H, G], [H, H, 1], slope, False)
+        shape = dict(E=0, H=H, Dt=0, Dp=0, P=0, T=0)
+        clip_d = clip_g = 0.0
+    else:
+        import conditional_gan_cross_attention_with_film as m
+        gen, disc = m.WGAN_GP_model(cfg["latent"], G, cfg["embed"], [H, H, G], [H, H, 1], cfg["text_dim"],
+                                    cfg["patch_dim"], slope, False)
+        shape = dict(E=cfg["embed"], H=H, Dt=cfg["text_dim"], Dp=cfg["patch_dim"], P=cfg["P"], T=cfg["T"], tower_bias=True)
+        clip_d, clip_g = m.WGAN_GP.clip_d, m.WGAN_GP.clip_g
+    for (k1, v1), (k2, v2) in zip(o.gen.state_dict().items(), gen.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2), k1
+    for (k1, v1), (k2, v2) in zip(o.disc.state_dict().items(), disc.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2), k1
+    dev = torch.device("cpu")
+    fg, fd = rt.FlatNet(gen, dev, optimizer), rt.FlatNet(disc, dev, optimizer)
+    eng = rt.Engine(variant=variant, B=cfg["B"], G=G, L=cfg["latent"], gen=fg, disc=fd, slope=slope, dropout_p=0.0,
+                    gp_weight=10.0, clip_d=clip_d, clip_g=clip_g, optimizer=optimizer, gemm_impl=_lib.IMPL_SIMT_F32,
+                    device=dev, **shape)
+    eng.set_lanes(False)
+    return o, gen, disc, eng
+
+
+def stage(eng, variant, x, cond):
+    if variant == "vanilla":
+        eng.set_batch(genes=x)
+    else:
+        patches, ppad, text, tpad = cond
+        eng.set_batch(genes=x, patches=patches, patch_pad=ppad, text=text, text_pad=tpad)
+
+
+def check_grads(named_ref, named_got, total):
+    num = den = 0.0
+    for (k, gref), (_, pt) in zip(named_ref, named_got):
+        if gref is None:
+            assert pt.grad is None, k
+            continue
+        got = pt.grad.detach().float()
+        assert torch.isfinite(got).all(), k
+        d, n = (got - gref).norm().item(), gref.norm().item()
+        num, den = num + d * d, den + n * n
+        if n > 1e-7:
+            assert d / n <= (0.15 if gref.numel() >= 4096 else 0.35), (k, d / n)
+    assert (num / max(den, 1e-30)) ** 0.5 <= total
+
+
+@pytest.mark.parametrize("variant,optimizer,slope", [("vanilla", "adam", 0.0), ("vanilla", "rms_prop", 0.2),
+                                                     ("paper", "adam", 0.0), ("paper", "rms_prop", 0.0)])
+def test_critic_and_generator_step_match_the_oracle(rt, variant, optimizer, slope):
+    cfg = SMALL
+    o, gen, disc, eng = build(rt, variant, cfg, optimizer, slope)
+    B, G, L = cfg["B"], cfg["G"], cfg["latent"]
+    x, cond = restated.synthetic_batch(variant, B, G, cfg["P"], cfg["T"], seed=5, ragged=True,
+                                       text_dim=cfg["text_dim"], patch_dim=cfg["patch_dim"])
+    g = torch.Generator().manual_seed(99)
+    z, alpha, z2 = torch.randn(B, L, generator=g), torch.rand(B, 1, generator=g), torch.randn(B, L, generator=g)
+    lr = 5e-4
+
+    # ---- critic step (train_disc, :376-423)
+    o.train_disc(x, z, cond, alpha)
+    stage(eng, variant, x, cond)
+    eng.disc_grads(z, alpha, training=True)
+    assert rel(eng.buffer("fake_bf16"), o.last["fake"]) < TOL
+    score = eng.buffer("score")[:, 0]
+    assert rel(score[:B], o.last["d_fake"][:, 0]) < TOL
+    assert rel(score[B:2 * B], o.last["d_true"][:, 0]) < TOL
+    assert fro(eng.buffer("gp_norms")[:, 0], o.last["grad_norm"]) < TOL          # per-row ||dD/dx_hat||
+    st = eng.stats
+    assert abs(st[A.STAT_GP].item() - o.last["gp"].item()) <= TOL * max(abs(o.last["gp"].item()), 1e-3)
+    got_d = np.array([st[A.STAT_LOSS_REAL].item() + st[A.STAT_LOSS_FAKE].item(), st[A.STAT_LOSS_REAL].item(),
+                      st[A.STAT_LOSS_FAKE].item()])
+    np.testing.assert_allclose(got_d, o.d_batch_loss, rtol=TOL, atol=TOL * 0.05)
+    before = {k: p.detach().clone() for k, p in disc.named_parameters()}
+    eng.optim_step(A.NET_DISC, lr)                                               # clip (:414) + optimizer (:415)
+    check_grads([(k, p.grad) for k, p in o.disc.named_parameters()], list(disc.named_parameters()), total=0.08)
+    # post-step weights: the update vectors of both sides (Adam / RMSprop steps are sign-like: an element whose tiny
+    # gradient differs in sign moves by 2 lr, so the updates are compared as vectors, not element by element)
+    dot = nr = ng = 0.0
+    for (k, po), (_, pt) in zip(o.disc.named_parameters(), disc.named_parameters()):
+        if po.grad is None:                                                      # the unused prototype layer (:114)
+            assert torch.equal(pt.detach(), before[k]), k
+            continue
+        ur, ug = (po.detach() - before[k]).flatten(), (pt.detach() - before[k]).flatten()
+        assert ug.abs().max().item() <= 1.01 * max(ur.abs().max().item(), lr), k
+        dot, nr, ng = dot + (ur @ ug).item(), nr + (ur @ ur).item(), ng + (ug @ ug).item()
+    assert dot / (nr * ng) ** 0.5 > 0.97 and 0.9 < (ng / nr) ** 0.5 < 1.1
+    for (k, po), (_, pt) in zip(o.gen.named_parameters(), gen.named_parameters()):
+        assert torch.equal(po.detach(), pt.detach()), k                          # generator untouched
+
+    # ---- generator step (train_gen, :425-461), on the critic the kernels have just updated
+    with torch.no_grad():                                                        # same critic on both sides
+        for po, pt in zip(o.disc.parameters(), disc.parameters()):
+            po.copy_(pt)
+    o.train_gen(z2, cond)
+    eng.sync_external_param_writes()
+    eng.gen_grads(z2, training=True)
+    assert st[A.STAT_G_LOSS].item() == pytest.approx(float(np.asarray(o.g_batch_loss).reshape(-1)[0]), rel=TOL, abs=TOL * 0.05)
+    eng.optim_step(A.NET_GEN, lr)
+    check_grads([(k, p.grad) for k, p in o.gen.named_parameters()], list(gen.named_parameters()), total=0.08)
+
+
+def test_generate_and_critic_entry_points(rt):
+    """generate_samples (:601-608) and discriminator.forward as stand-alone calls (eval mode)."""
+    cfg = SMALL
+    o, gen, disc, eng = build(rt, "paper", cfg, "adam", 0.0)
+    B, G, L = cfg["B"], cfg["G"], cfg["latent"]
+    x, cond = restated.synthetic_batch("paper", B, G, cfg["P"], cfg["T"], seed=6, ragged=True,
+                                       text_dim=cfg["text_dim"], patch_dim=cfg["patch_dim"])
+    z = torch.randn(B, L, generator=torch.Generator().manual_seed(3))
+    stage(eng, "paper", x, cond)
+    fake = eng.generate(z)
+    with torch.no_grad():
+        want = o.gen(z, *cond)
+        want_score = o.disc(x, *cond)
+    assert rel(fake, want) < TOL
+    assert rel(eng.critic(x), want_score) < TOL
