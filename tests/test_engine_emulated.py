@@ -3,7 +3,8 @@ sequences) compiled for the host (tests/cuda_emu/emu_engine.cpp) in the engine's
 (gemm_impl = GG_IMPL_SIMT_F32), driven through gemmgan_b200/runtime.py exactly as the trainer drives it
 (set_batch -> disc_grads -> optim_step, gen_grads -> optim_step), against the oracle (oracle/restated.py, pinned to the
 unmodified reference) on the same weights, batch and noise: WGAN_GP.train_disc / train_gen of
-src/conditional_gan_cross_attention_with_film.py:376-461 and src/vanilla_gan_unconditional.py.
+src/conditional_gan_cross_attention_with_film.py:376-461 and the same steps of every other variant (vanilla, film,
+cross, img, concat text / image, label).
 
 What this covers that the per-kernel emulation tests do not: the hand-written backward / double backward as the engine
 sequences it (Gram-matrix gradient penalty, shared [fake; real] GEMM, replica batching, FiLM and tower backward, two
@@ -69,6 +70,19 @@ def build(rt, variant, cfg, optimizer, slope, seed=11):
         gen, disc = m.WGAN_GP_model_nocond(cfg["latent"], G, [], [], [H, H, G], [H, H, 1], slope, False)
         shape = dict(E=0, H=H, Dt=0, Dp=0, P=0, T=0)
         clip_d = clip_g = 0.0
+    elif variant in ("concat", "concat_image"):
+        import conditional_gan_concat as m
+        image = variant == "concat_image"
+        din = cfg["patch_dim"] if image else cfg["text_dim"]
+        gen, disc = m.WGAN_GP_model(cfg["latent"], G, din, cfg["embed"], [H, H, G], [H, H, 1],
+                                    "image" if image else "text", slope, False)
+        shape = dict(E=cfg["embed"], H=H, Dt=din, Dp=din, P=1, T=1, tower_bias=True)
+        clip_d, clip_g = float(m.WGAN_GP.clip_d or 0.0), float(m.WGAN_GP.clip_g or 0.0)
+    elif variant == "label":
+        import benchmark_generative_model as m
+        gen, disc = m.WGAN_GP_model_benchmark(cfg["latent"], G, [], [10, 10], [H, H, G], [H, H, 1], slope, False)
+        shape = dict(E=gen.categorical_embedded_dims, H=H, Dt=10, Dp=10, P=1, T=1)
+        clip_d, clip_g = float(m.WGAN_GP_benchmark.clip_d or 0.0), float(m.WGAN_GP_benchmark.clip_g or 0.0)
     else:
         import importlib
         m = importlib.import_module({"paper": "conditional_gan_cross_attention_with_film", "film": "conditional_gan_film",
@@ -86,7 +100,7 @@ def build(rt, variant, cfg, optimizer, slope, seed=11):
         assert k1 == k2 and torch.equal(v1, v2), k1
     dev = torch.device("cpu")
     fg, fd = rt.FlatNet(gen, dev, optimizer), rt.FlatNet(disc, dev, optimizer)
-    eng = rt.Engine(variant=variant, B=cfg["B"], G=G, L=cfg["latent"], gen=fg, disc=fd, slope=slope, dropout_p=0.0,
+    eng = rt.Engine(variant="concat" if variant.startswith("concat") else variant, B=cfg["B"], G=G, L=cfg["latent"], gen=fg, disc=fd, slope=slope, dropout_p=0.0,
                     gp_weight=10.0, clip_d=clip_d, clip_g=clip_g, optimizer=optimizer, gemm_impl=_lib.IMPL_SIMT_F32,
                     device=dev, **shape)
     eng.set_lanes(False)
@@ -96,6 +110,13 @@ def build(rt, variant, cfg, optimizer, slope, seed=11):
 def stage(eng, variant, x, cond):
     if variant == "vanilla":
         eng.set_batch(genes=x)
+    elif variant == "label":
+        eng.set_batch(genes=x)
+        eng.set_labels(cond[0], cond[1])
+    elif variant == "concat":
+        eng.set_batch(genes=x, text=cond[0])
+    elif variant == "concat_image":     # masked mean of the patch embeddings first, then ONE encoder GEMM
+        eng.set_batch(genes=x, text=eng.masked_mean_rows(cond[1], cond[2]))
     elif variant in ("paper", "cross"):
         patches, ppad, text, tpad = cond
         eng.set_batch(genes=x, patches=patches, patch_pad=ppad, text=text, text_pad=tpad)
@@ -121,7 +142,9 @@ def check_grads(named_ref, named_got, total):
 
 @pytest.mark.parametrize("variant,optimizer,slope", [("vanilla", "adam", 0.0), ("vanilla", "rms_prop", 0.2),
                                                      ("paper", "adam", 0.0), ("paper", "rms_prop", 0.0),
-                                                     ("film", "adam", 0.0), ("cross", "adam", 0.0), ("img", "adam", 0.0)])
+                                                     ("film", "adam", 0.0), ("cross", "adam", 0.0), ("img", "adam", 0.0),
+                                                     ("concat", "adam", 0.2), ("concat_image", "rms_prop", 0.0),
+                                                     ("label", "adam", 0.0)])
 def test_critic_and_generator_step_match_the_oracle(rt, variant, optimizer, slope):
     cfg = SMALL
     o, gen, disc, eng = build(rt, variant, cfg, optimizer, slope)
