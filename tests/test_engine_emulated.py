@@ -217,3 +217,51 @@ def test_generate_and_critic_entry_points(rt):
         want_score = o.disc(x, *cond)
     assert rel(fake, want) < TOL
     assert rel(eng.critic(x), want_score) < TOL
+
+
+@pytest.mark.parametrize("name", ["vanilla_small_adam", "paper_small_adam", "film_small_adam", "label_small_rmsprop"])
+def test_against_reference_golden_loss_curves(rt, name):
+    """Replays the recorded noise of a run of the UNMODIFIED reference (tests/golden, oracle/make_golden.py) through
+    the emulated engine: first critic step against the recorded internals, then whole train() calls (n_critic critic
+    steps + one generator step, :463-477) against the reference's loss curves."""
+    from conftest import load_golden
+
+    fx = load_golden(name)
+    cfg, variant = fx["cfg"], fx["variant"]
+    o, gen, disc, eng = build(rt, variant, cfg, fx["optimizer"], fx["negative_slope"], seed=fx["init_seed"])
+    x, cond, zs, alphas = fx["x"], fx["cond"], fx["zs"], fx["alphas"]
+    B, nc, lr = cfg["B"], o.n_critic, 5e-4
+    st = eng.stats
+    stage(eng, variant, x, cond)
+
+    def critic_step(z, alpha):
+        eng.disc_grads(z, alpha, training=True)
+        d = np.array([st[A.STAT_LOSS_REAL].item() + st[A.STAT_LOSS_FAKE].item(), st[A.STAT_LOSS_REAL].item(),
+                      st[A.STAT_LOSS_FAKE].item()])
+        eng.optim_step(A.NET_DISC, lr)
+        return d
+
+    def gen_step(z):
+        eng.gen_grads(z, training=True)
+        g_loss = np.array([st[A.STAT_G_LOSS].item()])
+        eng.optim_step(A.NET_GEN, lr)
+        return g_loss
+
+    eng.disc_grads(zs[0], alphas[0], training=True)
+    assert rel(eng.buffer("fake_bf16"), fx["step0"]["fake"]) < TOL
+    assert rel(eng.buffer("score")[:B, 0], fx["step0"]["d_fake"][:, 0]) < TOL
+    assert rel(eng.buffer("score")[B:2 * B, 0], fx["step0"]["d_true"][:, 0]) < TOL
+    d_curve, g_curve = [], []
+    for call in range(fx["n_calls"]):
+        d = None
+        for i in range(nc):
+            d = critic_step(zs[call * (nc + 1) + i], alphas[call * nc + i])
+        d_curve.append(d)                              # d_batch_loss of the LAST critic step of the call (:421-423)
+        g_curve.append(gen_step(zs[call * (nc + 1) + nc]))
+    d_ref, g_ref = fx["curves"]["d"].numpy(), fx["curves"]["g"].numpy()
+    rms = fx["optimizer"] == "rms_prop"
+    for call in range(fx["n_calls"]):
+        tol = (0.05 if call == 0 else 0.35) if rms else 0.05      # as in tests/test_gpu_parity.py
+        scale = max(np.abs(d_ref[call]).max(), np.abs(g_ref[call]).max(), 0.25 if rms else 0.05)
+        assert np.abs(d_curve[call] - d_ref[call]).max() <= tol * scale + 2e-3, (call, d_curve[call], d_ref[call])
+        assert np.abs(g_curve[call] - g_ref[call]).max() <= tol * scale + 2e-3, (call, g_curve[call], g_ref[call])
