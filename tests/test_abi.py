@@ -58,6 +58,9 @@ def test_no_cpu_fallback_in_product_path():
         if fn.endswith(".py"):
             text = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in text and "from oracle" not in text, fn
+            # the host emulation of the kernels (tests/cuda_emu) is test infrastructure: the product binds exactly one
+            # library, libgemmgan_sm100a.so, and never an emulated build
+            assert "cuda_emu" not in text and "_emu.so" not in text and "emu_build" not in text, fn
     for fn in ("vanilla_gan_unconditional.py", "conditional_gan_film.py", "conditional_gan_cross_attention_with_film.py",
                "conditional_gan_cross_attention.py", "conditional_gan_img_transformer.py", "conditional_gan_concat.py",
                "multi_patch_gan_dataloader.py", "multi_patch_multi_token_gan_dataloader.py"):
