@@ -304,3 +304,33 @@ def test_against_reference_golden_loss_curves(rt, name):
         scale = max(np.abs(d_ref[call]).max(), np.abs(g_ref[call]).max(), 0.25 if rms else 0.05)
         assert np.abs(d_curve[call] - d_ref[call]).max() <= tol * scale + 2e-3, (call, d_curve[call], d_ref[call])
         assert np.abs(g_curve[call] - g_ref[call]).max() <= tol * scale + 2e-3, (call, g_curve[call], g_ref[call])
+
+
+def test_staged_backward_of_the_data_parallel_path_equals_the_whole_step(rt):
+    """The data-parallel trainer cuts the backward into phases (trunk, cross-attention tail, encoder layers, embedding
+    tail: gg_engine_*_grads_phase) so that each gradient bucket can be all-reduced while the next stage runs. The
+    staged sequences must leave exactly the gradients of the one-call step."""
+    cfg = SMALL
+    B, G, L = cfg["B"], cfg["G"], cfg["latent"]
+    x, cond = restated.synthetic_batch("paper", B, G, cfg["P"], cfg["T"], seed=5, ragged=True,
+                                       text_dim=cfg["text_dim"], patch_dim=cfg["patch_dim"])
+    g = torch.Generator().manual_seed(2)
+    z, alpha = torch.randn(B, L, generator=g), torch.rand(B, 1, generator=g)
+
+    def grads(schedule):
+        _, gen, disc, eng = build(rt, "paper", cfg, "adam", 0.0)
+        stage(eng, "paper", x, cond)
+        for ph in schedule:
+            eng.disc_grads(z, alpha, training=True, phase=ph)
+        d = eng.disc.grads.clone()
+        for ph in schedule:
+            eng.gen_grads(z, training=True, phase=ph)
+        return d, eng.gen.grads.clone()
+
+    whole_d, whole_g = grads([0])
+    two_d, two_g = grads([1, 2])                                             # trunk | tower
+    nj = A.PHASE_NO_JOIN
+    staged = [1 | nj] + [(A.PHASE_STAGE0 + s) | (0 if s == 3 else nj) for s in range(4)]
+    st_d, st_g = grads(staged)                                               # trunk | head | layer | layer | embedding
+    assert torch.equal(whole_d, two_d) and torch.equal(whole_g, two_g)
+    assert torch.equal(whole_d, st_d) and torch.equal(whole_g, st_g)
