@@ -29,6 +29,9 @@ from oracle import restated
 
 TOL = 2e-2
 SMALL = dict(B=8, G=203, P=5, T=3, embed=32, hidden=32, latent=16, text_dim=24, patch_dim=32)
+# the reference's feature widths (768-d text, 1024-d patches, E = H = 256 -> 4 heads of 64): the production kernel paths
+# (register-resident / mma.sync attention, vectorised LayerNorm and FiLM) instead of the generic small-width ones
+FULL = dict(B=16, G=1000, P=8, T=2, embed=256, hidden=256, latent=256, text_dim=768, patch_dim=1024)
 
 
 @pytest.fixture(scope="module")
@@ -146,7 +149,17 @@ def check_grads(named_ref, named_got, total):
                                                      ("concat", "adam", 0.2), ("concat_image", "rms_prop", 0.0),
                                                      ("label", "adam", 0.0)])
 def test_critic_and_generator_step_match_the_oracle(rt, variant, optimizer, slope):
-    cfg = SMALL
+    run_steps(rt, variant, optimizer, slope, SMALL)
+
+
+@pytest.mark.parametrize("variant,P", [("paper", 8), ("film", 20)])
+def test_steps_at_the_reference_feature_widths(rt, variant, P):
+    """paper: 8 patches + CLS = 9 tokens (short attention kernel, cfg3's shape); film: 20 patches + CLS = 21 tokens
+    (mma.sync mid kernel)."""
+    run_steps(rt, variant, "adam", 0.0, dict(FULL, P=P))
+
+
+def run_steps(rt, variant, optimizer, slope, cfg):
     o, gen, disc, eng = build(rt, variant, cfg, optimizer, slope)
     B, G, L = cfg["B"], cfg["G"], cfg["latent"]
     x, cond = restated.synthetic_batch(variant, B, G, cfg["P"], cfg["T"], seed=5, ragged=True,
