@@ -159,6 +159,12 @@ def test_steps_at_the_reference_feature_widths(rt, variant, P):
     run_steps(rt, variant, "adam", 0.0, dict(FULL, P=P))
 
 
+def test_cfg4_like_token_counts(rt):
+    """64 patches + CLS = 65 tokens (mma.sync mid kernel) and 32 text tokens (single-query attention over 65 / 32 keys):
+    BASELINE config 4's sequence lengths at a batch the emulation finishes quickly."""
+    run_steps(rt, "paper", "adam", 0.0, dict(FULL, B=8, P=64, T=32))
+
+
 def run_steps(rt, variant, optimizer, slope, cfg):
     o, gen, disc, eng = build(rt, variant, cfg, optimizer, slope)
     B, G, L = cfg["B"], cfg["G"], cfg["latent"]
