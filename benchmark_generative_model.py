@@ -166,8 +166,7 @@ class WGAN_GP_benchmark(TrainerBase):
             self.loss_dict['d fake loss'].append(d_mean[2])
             self.loss_dict["g loss"].append(np.atleast_1d(g_sum)[0])   # summed, not averaged, in the reference (:638)
             if self.result_dire and val and (epoch + 1) % self.freq_compute_test == 0 and epoch + 1 == epochs:
-                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, 'generator_last_epoch.pt'))
-                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, 'discriminator_last_epoch.pt'))
+                self._save_checkpoints('last_epoch')
 
 
 def parse_args():

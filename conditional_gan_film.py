@@ -161,8 +161,7 @@ class WGAN_GP(TrainerBase):
             last = epoch == epochs - 1
             if self.result_dire and ((epoch + 1) % self.freq_compute_test == 0 or last):
                 tag = 'last_epoch' if last else f'epoch_{epoch + 1}'
-                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, f'generator_{tag}.pt'))
-                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, f'discriminator_{tag}.pt'))
+                self._save_checkpoints(tag)
             self._fit_evaluation(epoch, epochs, train_data, val_data, test_data, val)
 
 

@@ -13,6 +13,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libgemmgan_sm100a.so"
 
 GG_OK = 0
+ABI_VERSION = 2   # must equal GG_ABI_VERSION of include/gemmgan.h: bumped with every struct / signature change
 ACT_NONE, ACT_LEAKY, ACT_FILM = 0, 1, 2
 IMPL_TCGEN05, IMPL_SIMT_F32 = 0, 1
 
@@ -102,6 +103,11 @@ def lib() -> C.CDLL:
         L = C.CDLL(str(path))
         L.gg_last_error.restype = C.c_char_p
         L.gg_abi_version.restype = C.c_int
+        got = L.gg_abi_version()
+        if got != ABI_VERSION:
+            # a stale git-ignored .so after a header change would be called with mismatched ctypes layouts
+            raise GGError(f"{path} was built for ABI version {got}, the Python bindings declare {ABI_VERSION}: "
+                          "rebuild it (python gemmgan_b200/build.py, or GEMMGAN_REBUILD=1)")
         L.gg_check_device.argtypes = [C.c_int]
         L.gg_gemm_bf16.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
         _declare_rest(L)

@@ -67,18 +67,69 @@ class FlatNet:
                 p.grad = None
         # buffers (none in these models) and anything else follow the module to the device
         self._versions = self._version_sum()
+        # Generation of the fp32 master weights. Every engine keeps its own bf16 shadows of them
+        # (engine.cu::layout_shadows); an optimizer step run by ONE engine, or a write through PyTorch,
+        # bumps this counter, and every engine refreshes its shadows when the generation it last saw
+        # lags (Engine.sync_params) — engines of other batch sizes (last partial batch of an epoch, a
+        # validation loader with its own batch size) must never run on stale matrices.
+        self.generation = 0
 
     def _version_sum(self) -> int:
         return sum(p._version for p in self.slots.values())
 
-    def externally_modified(self) -> bool:
-        """True when someone wrote to the parameters through PyTorch (load_state_dict, manual
-        edits) since the last call: the bf16 weight shadows then need a refresh."""
+    def poll_external_writes(self) -> int:
+        """Bumps `generation` when someone wrote to the parameters through PyTorch (load_state_dict,
+        manual edits, a broadcast) since the last poll; returns the current generation."""
         v = self._version_sum()
         if v != self._versions:
             self._versions = v
-            return True
-        return False
+            self.generation += 1
+        return self.generation
+
+    def bump(self) -> int:
+        """An engine's optimizer kernel has rewritten the master weights (the C kernels do not touch
+        torch's version counters)."""
+        self.generation += 1
+        return self.generation
+
+    def attach_optimizer(self, opt: "torch.optim.Optimizer") -> None:
+        """Makes `opt.state_dict()` / `opt.load_state_dict()` meaningful although `opt.step()` is never called: the
+        per-parameter state entries torch's RMSprop / Adam / AdamW keep (`square_avg` / `exp_avg`, `exp_avg_sq`,
+        `step`; torch/optim/rmsprop.py, adam.py) become VIEWS of the flat state buffers the optimizer kernel
+        updates, so torch.save(optimizer.state_dict()) captures the live state; load_state_dict copies the loaded
+        tensors back into the flat buffers (torch replaces the state tensors on load) and re-attaches the views.
+        Tensors the forward never uses (grad is None in the reference too) have no state, as in torch."""
+        adam = self.exp_avg is not None
+
+        def attach():
+            opt.state.clear()
+            for slot, p in self.slots.items():
+                o, n = self.offsets[slot], p.numel()
+                st = {"step": self.step_count[0:1].view(())}
+                if adam:
+                    st["exp_avg"] = self.exp_avg[o:o + n].view(p.shape)
+                    st["exp_avg_sq"] = self.exp_avg_sq[o:o + n].view(p.shape)
+                else:
+                    st["square_avg"] = self.exp_avg_sq[o:o + n].view(p.shape)
+                opt.state[p] = st
+
+        def after_load(optimizer):
+            with torch.no_grad():
+                for slot, p in self.slots.items():
+                    st = optimizer.state.get(p)
+                    if not st:
+                        continue
+                    o, n = self.offsets[slot], p.numel()
+                    if adam:
+                        self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                        self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    else:
+                        self.exp_avg_sq[o:o + n].copy_(st["square_avg"].reshape(-1))
+                    self.step_count[0:1].copy_(torch.as_tensor(st["step"], dtype=torch.float32).reshape(1))
+            attach()
+
+        attach()
+        opt.register_load_state_dict_post_hook(after_load)
 
     def reattach_grads(self) -> None:
         """optimizer.zero_grad(set_to_none=True) drops p.grad; point it back at the flat buffer."""
@@ -150,6 +201,8 @@ class Engine:
         self.alpha_in = torch.empty(B, 1, device=self.device, dtype=torch.float32)
         self.z_all = self.alpha_all = None
         self.graphs, self.warmed = {}, set()
+        # generation of each net's master weights this engine's bf16 shadows were made from (create refreshes both)
+        self.seen = {A.NET_GEN: gen.poll_external_writes(), A.NET_DISC: disc.poll_external_writes()}
 
     def ensure_noise(self, n_critic: int) -> None:
         """Per-step noise buffers of one train() call: z_all [n_critic + 1, B, L], alpha_all [n_critic, B, 1]."""
@@ -193,11 +246,21 @@ class Engine:
         for n in ((A.NET_GEN, A.NET_DISC) if net is None else (net,)):
             _lib.check(self.lib.gg_engine_refresh_shadows(self.handle, n, _stream()))
 
-    def sync_external_param_writes(self) -> None:
-        if self.gen.externally_modified():
-            self.refresh_shadows(A.NET_GEN)
-        if self.disc.externally_modified():
-            self.refresh_shadows(A.NET_DISC)
+    def sync_params(self) -> None:
+        """Refreshes the bf16 shadows of every net whose master weights changed since this engine last saw
+        them: by another engine's optimizer step, or by a write through PyTorch."""
+        for net, flat in ((A.NET_GEN, self.gen), (A.NET_DISC, self.disc)):
+            g = flat.poll_external_writes()
+            if self.seen[net] != g:
+                self.refresh_shadows(net)
+                self.seen[net] = g
+
+    sync_external_param_writes = sync_params
+
+    def stepped(self, net: int) -> None:
+        """This engine's optimizer kernel has updated `net` (and refreshed ITS shadows): the other engines lag."""
+        flat = self.gen if net == A.NET_GEN else self.disc
+        self.seen[net] = flat.bump()
 
     @staticmethod
     def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:

@@ -130,8 +130,11 @@ class TrainerBase:
             raise ValueError(f"unknown optimizer {self.optimizer!r}")
         self.optimizer_disc = mk(self.disc.parameters(), self.lr_d)
         self.optimizer_gen = mk(self.gen.parameters(), self.lr_g)
-        # the update itself is the engine's kernel; optimizer state lives in the flat buffers
+        # the update itself is the engine's kernel; optimizer state lives in the flat buffers, which
+        # optimizer.state_dict() / load_state_dict() see through views (FlatNet.attach_optimizer)
         self._flatten()
+        self._flat_disc.attach_optimizer(self.optimizer_disc)
+        self._flat_gen.attach_optimizer(self.optimizer_gen)
 
     def _attach(self, gen, disc):
         self.gen, self.disc = gen.to(self.device), disc.to(self.device)
@@ -144,6 +147,14 @@ class TrainerBase:
             self._flat_gen = FlatNet(self.gen, self.device, opt)
             self._flat_disc = FlatNet(self.disc, self.device, opt)
             self._engines.clear()
+            d = _dist()
+            if d is not None:
+                # replicas must start from the same weights whatever each rank's torch seed was: rank 0's go to all
+                # (optimizer state starts at zero everywhere). The flat buffers are written in place, so the
+                # nn.Parameter views follow; engines are created afterwards and build their shadows from them.
+                for flat in (self._flat_gen, self._flat_disc):
+                    d.broadcast(flat.params, src=0)
+                    flat.bump()
 
     def _shape_cfg(self):
         raise NotImplementedError
@@ -160,8 +171,17 @@ class TrainerBase:
                          clip_g=float(self.clip_g or 0.0), optimizer=self.optimizer.lower(),
                          seed=int(self.dropout_seed), gemm_impl=self.gemm_impl, device=self.device, **s)
             self._engines[B] = eng
+            d = _dist()
+            if d is not None:
+                # the all-reduce averages per-rank gradient MEANS with equal weight: that is the global-batch
+                # gradient only when every rank holds the same number of rows (e.g. DistributedSampler(drop_last=True))
+                sizes = torch.zeros(d.get_world_size(), dtype=torch.int64, device=self.device)
+                sizes[d.get_rank()] = B
+                d.all_reduce(sizes)
+                if int(sizes.min()) != int(sizes.max()):
+                    raise ValueError(f"data-parallel ranks must use equal per-rank batch sizes, got {sizes.tolist()}")
         else:
-            eng.sync_external_param_writes()
+            eng.sync_params()
         return eng
 
     # ---- host -> device staging ----------------------------------------------------------
@@ -325,6 +345,12 @@ class TrainerBase:
     def _step(self, eng: Engine, tag, net, flat, lr, grads_fn):
         """grads_fn(phase): phase 0 = whole backward, 1 = forward + trunk backward, 2 = tower backward."""
         lr = float(lr)
+        try:
+            self._step_inner(eng, tag, net, flat, lr, grads_fn)
+        finally:
+            eng.stepped(net)    # master weights moved: engines of other batch sizes refresh their shadows
+
+    def _step_inner(self, eng: Engine, tag, net, flat, lr, grads_fn):
         if _dist() is None:
             def body():
                 grads_fn(0)
@@ -389,6 +415,10 @@ class TrainerBase:
         (eng.z_all / eng.alpha_all, filled by _train_staged) instead of z / alpha."""
         self.disc.train()
         self._flat_disc.reattach_grads()
+        for w in self.disc.parameters():  # observable side effect of the reference (:384-389)
+            w.requires_grad = True
+        for w in self.gen.parameters():
+            w.requires_grad = False
         if slot is None:
             eng.z_in.copy_(z, non_blocking=True)
             eng.alpha_in.copy_(self._alpha(eng.B) if alpha is None else alpha.reshape(eng.B, 1), non_blocking=True)
@@ -471,6 +501,8 @@ class TrainerBase:
             w.requires_grad = True
         self._flat_disc.reattach_grads()
         self._flat_gen.reattach_grads()
+        eng.stepped(A.NET_DISC)   # (a replay does not re-run the Python of the steps)
+        eng.stepped(A.NET_GEN)
         self._mark("d")
         self._mark("g")
 
@@ -524,7 +556,7 @@ class TrainerBase:
             precision_test / recall_test (:732-734) and the gamma coefficient per epoch in `precision_scores`,
             `recall_scores`, `corr_scores` (the dicts print_best_epoch reads);
           * at the last epoch, with test_data: n_runs x save_generated_run (:786-811) -> `self.test_runs`."""
-        if not (val and self.result_dire):
+        if not (val and self.result_dire and self._is_main_rank()):
             return
         if val_data is not None and (epoch + 1) % self.freq_compute_test == 0:
             tr_out, va_out = self.generate_samples_all(train_data), self.generate_samples_all(val_data)
@@ -534,6 +566,20 @@ class TrainerBase:
             self.corr_scores[epoch + 1] = m["gamma"]
         if test_data is not None and epoch + 1 == epochs:
             self.test_runs = [self.save_generated_run(train_data, test_data, run, epoch) for run in range(n_runs)]
+
+    @staticmethod
+    def _is_main_rank() -> bool:
+        """Data-parallel replicas hold identical weights: only rank 0 writes files (checkpoints, .npy dumps)."""
+        d = _dist()
+        return d is None or d.get_rank() == 0
+
+    def _save_checkpoints(self, tag: str) -> None:
+        """generator_<tag>.pt / discriminator_<tag>.pt under results_dire — the reference's file names
+        (…with_film.py:710-711, :743-744). Rank 0 only in data-parallel runs."""
+        if not (self.result_dire and self._is_main_rank()):
+            return
+        torch.save(self.gen.state_dict(), os.path.join(self.result_dire, f"generator_{tag}.pt"))
+        torch.save(self.disc.state_dict(), os.path.join(self.result_dire, f"discriminator_{tag}.pt"))
 
     def _epoch_lr_decay(self, epoch, every):
         if epoch > 0 and epoch % every == 0:

@@ -34,7 +34,7 @@ extern "C" {
 #define GG_ERR_CUDA (-3)
 #define GG_ERR_WORKSPACE (-4)
 
-#define GG_ABI_VERSION 1
+#define GG_ABI_VERSION 2
 
 const char* gg_last_error(void);
 int gg_abi_version(void);

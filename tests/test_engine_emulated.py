@@ -353,3 +353,60 @@ def test_staged_backward_of_the_data_parallel_path_equals_the_whole_step(rt):
     st_d, st_g = grads(staged)                                               # trunk | head | layer | layer | embedding
     assert torch.equal(whole_d, two_d) and torch.equal(whole_g, two_g)
     assert torch.equal(whole_d, st_d) and torch.equal(whole_g, st_g)
+
+
+def test_engines_of_other_batch_sizes_see_optimizer_updates(rt):
+    """The reference's loaders have no drop_last (multi_patch_multi_token_gan_dataloader.py:178-185): the last partial
+    batch of an epoch, and a validation loader with its own batch size, run on an engine of another B than the one
+    whose optimizer kernel last moved the weights. Every engine keeps its own bf16 weight shadows: after a step on
+    engine A, engine B must refresh (FlatNet.generation / Engine.sync_params) — compared with a fresh engine built
+    from the updated weights, bit for bit."""
+    cfg = SMALL
+    o, gen, disc, eng = build(rt, "paper", cfg, "adam", 0.0)
+    B, G, L = cfg["B"], cfg["G"], cfg["latent"]
+    shape = dict(E=cfg["embed"], H=cfg["hidden"], Dt=cfg["text_dim"], Dp=cfg["patch_dim"], P=cfg["P"], T=cfg["T"],
+                 tower_bias=True)
+
+    def engine_at(b):
+        e = rt.Engine(variant="paper", B=b, G=G, L=L, gen=eng.gen, disc=eng.disc, slope=0.0, dropout_p=0.0,
+                      gp_weight=10.0, clip_d=10.0, clip_g=2.0, optimizer="adam", gemm_impl=_lib.IMPL_SIMT_F32,
+                      device=torch.device("cpu"), **shape)
+        e.set_lanes(False)
+        return e
+
+    small = engine_at(5)                                   # created BEFORE the updates: its shadows are the old weights
+    x, cond = restated.synthetic_batch("paper", B, G, cfg["P"], cfg["T"], seed=5, ragged=True,
+                                       text_dim=cfg["text_dim"], patch_dim=cfg["patch_dim"])
+    g = torch.Generator().manual_seed(99)
+    z, alpha, z2 = torch.randn(B, L, generator=g), torch.rand(B, 1, generator=g), torch.randn(B, L, generator=g)
+    stage(eng, "paper", x, cond)
+    eng.disc_grads(z, alpha, training=True)
+    eng.optim_step(A.NET_DISC, 5e-2)                       # a large step: stale shadows would be far off
+    eng.stepped(A.NET_DISC)
+    eng.gen_grads(z2, training=True)
+    eng.optim_step(A.NET_GEN, 5e-2)
+    eng.stepped(A.NET_GEN)
+    assert small.seen[A.NET_DISC] != eng.disc.generation and small.seen[A.NET_GEN] != eng.gen.generation
+    xs, conds = x[:5], tuple(c[:5] for c in cond)
+    zs = z[:5].contiguous()
+    stage(small, "paper", xs, conds)
+    stale_fake, stale_score = small.generate(zs).clone(), small.critic(xs).clone()
+    small.sync_params()                                    # what TrainerBase._engine does for a cached engine
+    assert small.seen[A.NET_DISC] == eng.disc.generation and small.seen[A.NET_GEN] == eng.gen.generation
+    fresh = engine_at(5)
+    stage(fresh, "paper", xs, conds)
+    want_fake, want_score = fresh.generate(zs), fresh.critic(xs)
+    got_fake, got_score = small.generate(zs), small.critic(xs)
+    assert torch.equal(got_fake, want_fake) and torch.equal(got_score, want_score)
+    assert not torch.equal(stale_fake, want_fake) and not torch.equal(stale_score, want_score)
+    # a write through PyTorch (load_state_dict) is seen by every engine, not only the first one that asks
+    with torch.no_grad():
+        gen.final_layer.bias.add_(1.0)
+        gen.final_layer.weight.mul_(0.5)
+    for e in (eng, small, fresh):
+        e.sync_params()
+    stage(eng, "paper", x, cond)
+    a = eng.generate(z)[:5]
+    stage(small, "paper", xs, conds)
+    b = small.generate(zs)
+    assert torch.allclose(a, b, atol=0, rtol=0)

@@ -87,7 +87,9 @@ def test_gamma_at_full_gene_count(host):
     a, b = cx[iu[0], iu[1]], cy[iu[0], iu[1]]
     want = torch.corrcoef(torch.stack([a, b]))[0, 1].item()
     assert host.gamma_coef(sub_x, sub_y) == pytest.approx(want, abs=1e-6)
-    assert torch.allclose(cx, torch.corrcoef(sub_x.double().T), atol=5e-6)
+    # fp32 standardised values and a 256-term fp32 FMA dot per entry against fp64 corrcoef: |err| <= ~n * eps32 / 2
+    # in the worst case (1.5e-5 at n = 256), a few 1e-6 in practice
+    assert torch.allclose(cx, torch.corrcoef(sub_x.double().T).cpu(), atol=2e-5)
 
 
 def test_evaluate_generated_after_fit(host, tmp_path):

@@ -139,8 +139,7 @@ class WGAN_GP_nocond(TrainerBase):
             self.loss_dict['d fake loss'].append(d_mean[2])
             self.loss_dict['g loss'].append((g_sum / max(n, 1))[0])
             if self.result_dire and epoch == epochs - 1:   # reference :614-615
-                torch.save(self.gen.state_dict(), os.path.join(self.result_dire, 'generator_last_epoch.pt'))
-                torch.save(self.disc.state_dict(), os.path.join(self.result_dire, 'discriminator_last_epoch.pt'))
+                self._save_checkpoints('last_epoch')
 
 
 def parse_args():
