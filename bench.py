@@ -38,7 +38,10 @@ WORKLOADS = {
 }
 METRIC = "wgan_gp_train_samples_per_sec"
 UNIT = "samples/s"
-CPU_SAMPLE_BATCH = {"cfg1": 64, "cfg2": 8, "cfg3": 256, "cfg4": 16}
+# CPU arm: cfg1 / cfg3 run the FULL workload batch (cfg3: ~6 s per train() on 16 cores); cfg2 / cfg4 (10^2..10^3 s per
+# call at full batch) run a reduced batch, which `sample` and `config.cpu_sample_batch` state
+CPU_SAMPLE_BATCH = {"cfg1": 64, "cfg2": 8, "cfg3": 1024, "cfg4": 16}
+GP_SHAPE = dict(B=16384, G=20000, H=256)   # cfg5 headline point (0.67 TFLOP dense, 2.6 GB)
 
 
 def peaks():
@@ -158,9 +161,99 @@ def cpu_reference_run(w, name, steps, warmup, optimizer):
         o.train(x, cond)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return dict(value=Bs / dt, unit=UNIT, cores=cores, threads=torch.get_num_threads(), kind="port",
-                sample=f"{steps} train() call(s) of {w['variant']} at B={Bs} (full workload B={w['B']}), "
+                sample=f"{steps} train() call(s) of {w['variant']} at B={Bs} "
+                       f"({'the full workload batch' if Bs == w['B'] else 'REDUCED from the workload batch B=' + str(w['B'])}), "
                        f"G={w['G']}, P={w['P']}, T={w['T']}, fp32, {optimizer}, dropout 0.1; samples/s = B/t",
                 ms_per_step=dt * 1e3)
+
+
+def eager_b200_run(w, optimizer, dev, autocast, steps=5, warmup=3):
+    """Stock PyTorch eager on THIS B200: the reference's step (oracle port with stock_modules=True, i.e. the
+    nn.TransformerEncoder / nn.MultiheadAttention / autograd / torch.optim calls the reference makes, reference
+    :144-152, :351-477) with device-resident inputs, fp32 as the reference runs it or under torch.autocast(bf16).
+    This is the 'beat this' number of SURVEY.md section 8d: the reference ships no native kernels."""
+    import contextlib
+
+    import torch
+    from oracle import restated
+
+    torch.manual_seed(42)
+    o = restated.OracleWGANGP(w["variant"], w["G"], optimizer=optimizer, dropout=None, device=str(dev),
+                              stock_modules=True)
+    x, cond = restated.synthetic_batch(w["variant"], w["B"], w["G"], max(w["P"], 1), max(w["T"], 1), seed=42,
+                                       device=str(dev))
+    ctx = (lambda: torch.autocast(device_type="cuda", dtype=torch.bfloat16)) if autocast else contextlib.nullcontext
+    for _ in range(warmup):
+        with ctx():
+            o.train(x, cond)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        with ctx():
+            o.train(x, cond)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del o
+    torch.cuda.empty_cache()
+    return dict(value=w["B"] / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, warmup=warmup,
+                precision="autocast-bf16" if autocast else "fp32 (TF32 off, torch default)",
+                how="oracle port with torch's stock modules (cuBLASLt + SDPA + autograd + torch.optim), device-resident "
+                    "inputs, CUDA events, includes the per-step .item() syncs the reference makes")
+
+
+def gp_microbench(dev, pk, iters=10):
+    """BASELINE.json config 5, the 'GP-kernel TFLOP/s' half of the metric, at its headline point: the whole gradient
+    penalty of the unconditional critic (value + gp_weight * dGP/d{W1, W2, w3}) through gg_engine_gp_step, CUDA-graph
+    replay, CUDA events, L2 flushed between iterations. The full sweep is bench_gp.py."""
+    import torch
+
+    import vanilla_gan_unconditional as m
+
+    B, G, H = GP_SHAPE["B"], GP_SHAPE["G"], GP_SHAPE["H"]
+    torch.manual_seed(42)
+    t = m.WGAN_GP_nocond(input_dims=G, latent_dims=256, vocab_sizes=[], generator_dims=[H, H, G],
+                         discriminator_dims=[H, H, 1], optimizer="rms_prop")
+    t.build_WGAN_GP_nocond()
+    t.init_train()
+    eng = t._engine(B)
+    g = torch.Generator(device=dev).manual_seed(1)
+    real = torch.randn(B, G, device=dev, generator=g)
+    fake = torch.randn(B, G, device=dev, generator=g)
+    alpha = torch.rand(B, 1, device=dev, generator=g)
+    gp = torch.zeros((), device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        eng.gp_step(real, fake, alpha, gp)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.gp_step(real, fake, alpha, gp)
+    ts = []
+    for i in range(iters):
+        flush.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    dense = 8.0 * B * G * H + 8.0 * B * H * H
+    executed = 2.0 * (2 * B) * G * H + 2.0 * H * H * G * 2 + 14.0 * B * H * H
+    byts = 8.0 * B * G + 4.0 * G * H + 4.0 * G * H
+    out = dict(workload=f"cfg5: gradient penalty of the unconditional critic, B={B} G={G} H={H}", ms=ms,
+               dense_equivalent_tflops=dense / ms / 1e9, executed_tflops=executed / ms / 1e9,
+               hbm_gbs=byts / ms / 1e6, hbm_frac=byts / ms / 1e6 / pk["hbm"],
+               tensor_frac_dense_equivalent=dense / ms / 1e9 / pk["tflops"], gp=float(gp.item()),
+               note="Gram-matrix formulation: executes fewer FLOPs than the dense count 8BGH + 8BH^2 (SURVEY 8d), "
+                    "so the figure that bounds it is HBM: 8BG bytes of fp32 real + fake read once")
+    del eng, graph, real, fake, flush
+    t._engines.clear()
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -168,15 +261,34 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--optimizer", default="rms_prop", choices=["rms_prop", "adam", "adamw"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (diagnostics only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the Adam leg, the stock-PyTorch-eager-on-B200 legs and the GP microbenchmark")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg without the next-batch H2D prefetch")
     ap.add_argument("--gemm-csv", default="", help="write per-launch GEMM shapes / durations of one train() here")
     args = ap.parse_args()
+    if args.workload == "cfg5":     # the GP-kernel half of the metric as its own line
+        import torch
+        from gemmgan_b200 import _lib
+
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        torch.cuda.set_device(0)
+        _lib.require_device(0)
+        pk = peaks()
+        r = gp_microbench(torch.device("cuda", 0), pk, iters=max(args.steps, 5))
+        print(json.dumps(dict(metric="gp_kernel_dense_equivalent_tflops", value=r["dense_equivalent_tflops"],
+                              unit="TFLOP/s (dense-equivalent)", n_gpus=1, steps=max(args.steps, 5), warmup=3,
+                              ms_per_step=r["ms"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                              data="synthetic", config=dict(workload=r["workload"], l2="flushed between timed steps"),
+                              roofline=dict(bound="hbm", achieved=r["hbm_gbs"], peak=pk["hbm"], unit="GB/s",
+                                            frac=r["hbm_frac"], traffic=None), gp_microbench=r)))
+        return
     w = dict(WORKLOADS[args.workload])
     if args.batch:
         w["B"] = args.batch
@@ -186,6 +298,7 @@ def main():
     cfg = dict(workload=f"{args.workload}: {w['desc']}", per_gpu_batch=w["B"], genes=w["G"], patch_tokens=w["P"],
                text_tokens=w["T"], optimizer=args.optimizer, n_critic=5, dropout=0.1,
                parallelism=f"dp{world}", l2="flushed between timed steps (512 MB write)",
+               cpu_sample_batch=min(w["B"], CPU_SAMPLE_BATCH[args.workload]),
                cuda_graphs=os.environ.get("GEMMGAN_CUDA_GRAPHS", "1") != "0")
 
     if args.impl == "reference":
@@ -323,7 +436,8 @@ def main():
     t_tensor, t_hbm = fl.value / (pk["tflops"] * 1e12), by / (pk["hbm"] * 1e9)
     traffic = None
     try:  # DRAM bytes per launch of the same launches under ncu (profiles/, committed with the launch list)
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+        tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+        with open(tp if os.path.exists(tp) else os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
             traffic = float(json.load(f)["dram_bytes_per_launch"])
     except Exception:  # noqa: BLE001
         pass
@@ -366,11 +480,55 @@ def main():
                    d2h_bytes_per_step=2 * 16 * 4, ms_per_step=te.item() / args.steps,
                    h2d_overlapped_with_previous_step=pre is not None)
 
+    # ---- extras (N=1, rank 0; each guarded: a diagnostic must not cost the bench line)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        del batch_dev
+        t._engines.clear()
+        t = None
+        torch.cuda.empty_cache()
+        other = "adam" if args.optimizer != "adam" else "rms_prop"
+        try:    # the same workload under the other optimizer the report asks for (north_star names Adam, the script
+                # default is RMSprop): device-resident value only
+            t2 = build_trainer(w, other)
+            b2 = make_batch(w, seed=42, device=dev)
+            for _ in range(3):
+                t2.train(*b2)
+            torch.cuda.synchronize()
+            n2 = max(5, min(args.steps, 10))
+            tot = 0.0
+            for i in range(n2):
+                flush.fill_(i & 0xFF)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                t2.train(*b2)
+                b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            extras["optimizers"] = {args.optimizer: dict(value=value, ms_per_step=ms_per_step),
+                                    other: dict(value=w["B"] / (tot / n2 * 1e-3), ms_per_step=tot / n2, steps=n2)}
+            t2._engines.clear()
+            del t2, b2
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001
+            extras["optimizers"] = dict(error=repr(exc))
+        for key, ac in (("fp32", False), ("autocast_bf16", True)):
+            try:
+                r = eager_b200_run(w, args.optimizer, dev, ac)
+                r["speedup_ours_over_it"] = value / r["value"]
+                extras.setdefault("torch_eager_b200", {})[key] = r
+            except Exception as exc:  # noqa: BLE001
+                extras.setdefault("torch_eager_b200", {})[key] = dict(error=repr(exc))
+        try:
+            extras["gp_microbench"] = gp_microbench(dev, pk)
+        except Exception as exc:  # noqa: BLE001
+            extras["gp_microbench"] = dict(error=repr(exc))
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                     data="synthetic", config=cfg, clocks=clocks, e2e=e2e, gpu_launches=launches,
-                    roofline=roofline, last_losses=losses)
+                    roofline=roofline, last_losses=losses, **extras)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(w, args.workload, 1, 1, args.optimizer)
             line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])

@@ -3,6 +3,7 @@ oracle/make_golden.py produced by running the UNMODIFIED reference, (2) live aga
 when /root/reference is present (build container only)."""
 import hashlib
 
+import numpy as np
 import pytest
 import torch
 
@@ -118,3 +119,28 @@ def test_oracle_matches_reference_live(variant, opt):
     o.train(x, cond)
     torch.testing.assert_close(torch.tensor(o.d_batch_loss), torch.tensor(ref.d_batch_loss), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(torch.tensor(o.g_batch_loss), torch.tensor(ref.g_batch_loss), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("variant", ["paper", "film", "cross"])
+def test_stock_module_mode_equals_the_explicit_math(variant):
+    """OracleWGANGP(stock_modules=True) runs nn.TransformerEncoder / nn.MultiheadAttention forwards as the reference
+    does (:144-152); bench.py times that mode on the B200 as the stock-PyTorch-eager baseline. Same step, same
+    numbers as the explicit restatement."""
+    cfg = dict(G=97, latent=16, embed=32, hidden=32, text_dim=24, patch_dim=40)
+    outs = []
+    for stock in (False, True):
+        torch.manual_seed(3)
+        o = restated.OracleWGANGP(variant, cfg["G"], latent=16, embed=32, hidden=32, optimizer="adam", dropout=0.0,
+                                  text_dim=24, patch_dim=40, stock_modules=stock)
+        x, cond = restated.synthetic_batch(variant, 6, cfg["G"], 5, 3, seed=1, ragged=True, text_dim=24, patch_dim=40)
+        g = torch.Generator().manual_seed(2)
+        zs = [torch.randn(6, 16, generator=g) for _ in range(6)]
+        alphas = [torch.rand(6, 1, generator=g) for _ in range(5)]
+        o.train(x, cond, zs, alphas)
+        outs.append((o.d_batch_loss.copy(), o.g_batch_loss.copy(),
+                     torch.cat([p.detach().flatten() for p in o.disc.parameters()])))
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(outs[0][1], outs[1][1], rtol=2e-5, atol=2e-6)
+    # Adam's first steps are lr * sign(g)-like: an entry whose ~0 gradient rounds to the other sign moves by 2 lr
+    d = (outs[0][2] - outs[1][2]).abs()
+    assert d.max().item() <= 2 * 5 * 5e-4 and d.mean().item() < 2e-5, (d.max().item(), d.mean().item())
