@@ -64,6 +64,21 @@ class AttnArgs(C.Structure):
                 ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddkv", C.c_int64), ("stat", C.c_void_p)]
 
 
+class EncLayerParams(C.Structure):
+    """gg_enc_layer_params (include/gemmgan.h)."""
+    _fields_ = [("nb", C.c_int32), ("S", C.c_int32), ("E", C.c_int32), ("F", C.c_int32), ("n_heads", C.c_int32),
+                ("save_rows", C.c_int64), ("x", C.c_void_p),
+                ("w_in", C.c_void_p), ("ld_in", C.c_int64), ("w_out", C.c_void_p), ("ld_out", C.c_int64),
+                ("w_ff1", C.c_void_p), ("ld_ff1", C.c_int64), ("w_ff2", C.c_void_p), ("ld_ff2", C.c_int64),
+                ("b_in", C.c_void_p), ("b_out", C.c_void_p), ("b_ff1", C.c_void_p), ("b_ff2", C.c_void_p),
+                ("g1", C.c_void_p), ("be1", C.c_void_p), ("g2", C.c_void_p), ("be2", C.c_void_p),
+                ("mask", C.c_void_p), ("mask_mod", C.c_int32), ("drop_p", C.c_float), ("eps", C.c_float),
+                ("rng", C.c_void_p), ("site", C.c_uint32),
+                ("qkv", C.c_void_p), ("ao", C.c_void_p), ("z1", C.c_void_p), ("x1", C.c_void_p), ("h", C.c_void_p),
+                ("z2", C.c_void_p), ("out", C.c_void_p),
+                ("mean1", C.c_void_p), ("rstd1", C.c_void_p), ("mean2", C.c_void_p), ("rstd2", C.c_void_p)]
+
+
 class ColsumItem(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int64), ("N", C.c_int32), ("out", C.c_void_p)]
 
@@ -117,6 +132,7 @@ def declare(L: C.CDLL) -> None:
     L.gg_colsum_group_workspace_bytes.argtypes = [i64]
     L.gg_colsum_group_workspace_bytes.restype = i64
     L.gg_colsum_group.argtypes = [C.POINTER(ColsumItem), i32, vp, i64, vp]
+    L.gg_encoder_layer_fwd.argtypes = [C.POINTER(EncLayerParams), vp]
     declare_evalmetrics(L)
     L.gg_launch_count.argtypes = [i32]
     L.gg_launch_count.restype = C.c_longlong
@@ -140,5 +156,5 @@ EXPORTS = [
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",
     "gg_pairwise_distance", "gg_row_kth_smallest", "gg_row_membership", "gg_col_hits", "gg_standardize_columns",
     "gg_gene_correlation", "gg_gamma_moments_workspace_bytes", "gg_gamma_moments",
-    "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
+    "gg_encoder_layer_fwd", "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

@@ -1,0 +1,654 @@
+// gg_encoder_layer_fwd: one post-norm nn.TransformerEncoderLayer forward as ONE kernel (short sequences).
+//
+//   sa  = out_proj(softmax(q k^T / 8 + key_padding_mask) v),  [q | k | v] = x Win^T + b_in      (4 heads x 64)
+//   x1  = LayerNorm1(x + dropout(sa))
+//   out = LayerNorm2(x1 + dropout(W2 dropout(relu(W1 x1 + b1)) + b2))
+//
+// Replaces, per layer and pass, the seven launches qkv GEMM -> attention -> out-proj GEMM -> add+LN -> ffn1 GEMM ->
+// ffn2 GEMM -> add+LN of the unfused path (reference: nn.TransformerEncoder at
+// src/conditional_gan_cross_attention_with_film.py:114-119, :144; torch/nn/modules/transformer.py post-norm branch)
+// and their HBM round trips: at the paper model's 9 tokens (8 patches + CLS) those launches are 10-30 us each on a
+// dependent chain, i.e. latency bound (profiles/r02_timeline_cfg3_a.json: 183 us per layer for the critic's 3B rows).
+//
+// sm_100a design. One CTA per SM, persistent over tiles of SPT = floor(128 / S) whole sequences (S <= 16 tokens;
+// 14 x 9 = 126 of 128 rows at the paper model's shape). Per tile everything stays on chip:
+//   warp 0   TMA producer: the X tile (4 swizzled [rows][64] boxes) and ALL weights of the layer (1 MB of bf16 from L2)
+//            streamed through a 2-slot ring in the order the MMAs consume them
+//   warp 1   one thread issues tcgen05.mma (M = 128, N = 192 / 256, K = 16 per instruction), accumulators in TMEM:
+//            per head [Q_h | K_h | V_h] (double-buffered), then out-proj, ffn1 (two 256-wide halves), ffn2
+//   warps 2-9  epilogues (thread = accumulator row, two warps share a row and split its columns):
+//            tcgen05.ld -> bias -> bf16 -> swizzled shared memory = the A operand of the next MMA (attention output,
+//            x1, relu hidden) — never HBM; the 9 x 9 attention itself runs per (sequence, head) on mma.sync
+//            fragments from the staged Q / K / V tiles; LayerNorm statistics in fp32 registers (two-pass),
+//            Philox dropout with the element indexing of the unfused kernels, so the existing backward regenerates
+//            the same masks.
+// Tensors the hand-written backward needs (qkv, attention output, pre-LN sums, x1, hidden, LN statistics) are written
+// for rows < save_rows only: the generator tower inside a critic step and the critic's interpolated replica are
+// never back-propagated and write nothing but their output.
+#include "host_util.h"
+#include "kernels.h"
+#include "pdl.cuh"
+#include "philox.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace gg {
+
+int encode_tma_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer,
+                   bool f32);
+
+namespace el {
+
+constexpr int E = 256, F = 512, HD = 64, NH = 4;
+constexpr int THREADS = 320;
+constexpr int BLK = 128 * 128;          // one [128 rows][64 bf16] block, 128B-swizzled (TMA / UMMA K-major layout)
+constexpr int OFF_BUF0 = 0;             // X tile, later x1                         (4 blocks)
+constexpr int OFF_BUF1 = 4 * BLK;       // Q_h / attention output, later relu hidden (4 blocks)
+constexpr int OFF_KV = 8 * BLK;         // K_h, V_h of the current head; later LayerNorm partial sums
+constexpr int OFF_RING = 10 * BLK;      // 2 weight slots
+constexpr int SLOT = 32768;
+constexpr int OFF_BAR = OFF_RING + 2 * SLOT;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+static_assert(SMEM_BYTES <= 232448, "encoder-layer kernel exceeds 227 KB of shared memory");
+
+enum Bar {
+  B_XFULL = 0, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, B_ACCFULL0, B_ACCFULL1, B_ACCEMPTY0, B_ACCEMPTY1, B_AOFULL,
+  B_ACC2FULL, B_X1FULL, B_F1AFULL, B_F1BFULL, B_HAFULL, B_F2ADONE, B_HBFULL, B_OUTFULL, B_TILEDONE, B_COUNT
+};
+
+struct Args {
+  int nb, S, spt, rows_pt, num_tiles;
+  int64_t rows_total, save_rows;
+  const bf16* x;
+  const float *b_in, *b_out, *b_ff1, *b_ff2, *g1, *be1, *g2, *be2;
+  const uint8_t* mask;
+  int mask_mod;
+  float drop_p, eps;
+  const uint64_t* rng;
+  uint32_t site;
+  bf16 *qkv, *ao, *z1, *x1, *h, *z2, *out;
+  float *mean1, *rstd1, *mean2, *rstd2;
+};
+
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {
+  return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float x, float y) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 u;
+  u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]); u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
+  return u;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __bfloat1622float2(h[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_add(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// 32 values of one row: inverted dropout with the flat element index of the unfused kernels
+// (group = (row * width + col) / 8, eight 16-bit uniforms per Philox call).
+__device__ __forceinline__ void dropout32(float* v, uint64_t seed, uint64_t step, uint32_t site, uint64_t elem0,
+                                          uint32_t thr, float keep_scale) {
+#pragma unroll
+  for (int gq = 0; gq < 4; ++gq) {
+    const uint32_t kb = keep_bits8(dropout_words(seed, step, site, (elem0 >> 3) + gq), thr);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[8 * gq + t] = ((kb >> t) & 1u) ? v[8 * gq + t] * keep_scale : 0.f;
+  }
+}
+
+// softmax(q k^T / 8 + mask) v of one (sequence, head) on m16n8k16 fragments: rows [r0, r0 + S) of the swizzled
+// Q / K / V blocks (S <= 16; window rows beyond S belong to the next sequence: their keys get a -inf bias, their
+// values meet exact-zero probabilities, their query rows are not stored). The output overwrites the Q rows.
+__device__ __forceinline__ void attention_task(uint8_t* qblk, const uint8_t* kblk, const uint8_t* vblk, int r0, int S,
+                                               const uint8_t* mk, float drop_p, uint64_t seed, uint64_t step,
+                                               uint32_t site, uint64_t pbase, int lane) {
+  constexpr float SCALE_LOG2E = 0.125f * 1.4426950408889634f;
+  float sc[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sc[nt][j] = 0.f;
+  {
+    const int ra = min(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, 127), ca = lane >> 4;
+    const int rb = min(r0 + (lane & 7) + (lane >> 4) * 8, 127), cb = (lane >> 3) & 1;
+#pragma unroll
+    for (int kk = 0; kk < HD / 16; ++kk) {
+      uint32_t a[4], b[4];
+      ldsm_x4(a, qblk + swz(ra, kk * 2 + ca));
+      ldsm_x4(b, kblk + swz(rb, kk * 2 + cb));
+      mma16816(sc[0], a, b[0], b[1]);
+      mma16816(sc[1], a, b[2], b[3]);
+    }
+  }
+  const int g = lane >> 2, t = lane & 3;
+  float kbias[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = (e >> 1) * 8 + 2 * t + (e & 1);
+    kbias[e] = (j < S && !(mk && mk[j])) ? 0.f : -INFINITY;
+  }
+  float p[2][4];
+#pragma unroll
+  for (int rh = 0; rh < 2; ++rh) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      p[rh][e] = fmaf(sc[e >> 1][rh * 2 + (e & 1)], SCALE_LOG2E, kbias[e]);
+      m = fmaxf(m, p[rh][e]);
+    }
+    m = quad_max(m);
+    m = m == -INFINITY ? 0.f : m;
+    float l = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      p[rh][e] = fast_ex2(p[rh][e] - m);
+      l += p[rh][e];
+    }
+    l = quad_add(l);
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) p[rh][e] *= inv_l;
+  }
+  if (drop_p > 0.f) {
+    const float keep_scale = 1.f / (1.f - drop_p);
+    DropoutStream ds(seed, step, site, drop_p);
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const int i = g + rh * 8;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = (e >> 1) * 8 + 2 * t + (e & 1);
+        if (i < S && j < S) p[rh][e] *= ds.keep(pbase + static_cast<uint64_t>(i) * S + j) ? keep_scale : 0.f;
+      }
+    }
+  }
+  uint32_t pa[4];
+  pa[0] = pack2(p[0][0], p[0][1]);
+  pa[1] = pack2(p[1][0], p[1][1]);
+  pa[2] = pack2(p[0][2], p[0][3]);
+  pa[3] = pack2(p[1][2], p[1][3]);
+  float o[8][4];
+  {
+    const int rv = min(r0 + (lane & 7) + ((lane >> 3) & 1) * 8, 127), cv = lane >> 4;
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, vblk + swz(rv, np * 2 + cv));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[2 * np][j] = o[2 * np + 1][j] = 0.f;
+      mma16816(o[2 * np], pa, b[0], b[1]);
+      mma16816(o[2 * np + 1], pa, b[2], b[3]);
+    }
+  }
+  __syncwarp();  // every lane has read its Q fragments: the output may overwrite the Q rows
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (g < S) *reinterpret_cast<uint32_t*>(qblk + swz(r0 + g, nt) + 4 * t) = pack2(o[nt][0], o[nt][1]);
+    if (g + 8 < S) *reinterpret_cast<uint32_t*>(qblk + swz(r0 + g + 8, nt) + 4 * t) = pack2(o[nt][2], o[nt][3]);
+  }
+}
+
+// issue the four K = 16 steps of one 64-wide k-block
+__device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t idesc,
+                                           bool accumulate_first) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t ad = make_smem_desc(a_base + k * 32, 16, 1024);
+    const uint64_t bd = make_smem_desc(b_base + k * 32, 16, 1024);
+    tc_mma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || k > 0) ? 1u : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+    enc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWin,
+                         const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmW1,
+                         const __grid_constant__ CUtensorMap tmW2, const Args a) {
+  extern __shared__ uint8_t el_smem_raw[];
+  uint8_t* smem = el_smem_raw + ((1024 - (smem_u32(el_smem_raw) & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWin);
+    tma_prefetch_desc(&tmWo);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int i = 0; i < B_COUNT; ++i) {
+      const bool by_warps = i == B_ACCEMPTY0 || i == B_ACCEMPTY1 || i == B_AOFULL || i == B_X1FULL || i == B_HAFULL ||
+                            i == B_HBFULL || i == B_TILEDONE;
+      mbar_init(&bars[i], by_warps ? 8 : 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  // rows the X box never fills (rows_pt .. 127) must hold finite numbers: they flow through every MMA as
+  // independent accumulator rows, and the attention's 16-row windows read (and zero-weight) them
+  for (int i = threadIdx.x; i < 4 * (128 - a.rows_pt) * 8; i += THREADS) {
+    const int blk = i / ((128 - a.rows_pt) * 8), rem = i % ((128 - a.rows_pt) * 8);
+    const int row = a.rows_pt + rem / 8, chunk = rem % 8;
+    *reinterpret_cast<uint4*>(smem + OFF_BUF0 + blk * BLK + swz(row, chunk)) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_entry();
+
+  const uint32_t buf0 = smem_u32(smem + OFF_BUF0), buf1 = smem_u32(smem + OFF_BUF1), ring = smem_u32(smem + OFF_RING);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      auto next_slot = [&]() {
+        if (++s == 2) { s = 0; ph ^= 1; }
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(&bars[B_TILEDONE], (it & 1) ^ 1);  // the previous tile's last reader of BUF0 (x1 residual) is done
+        mbar_arrive_expect_tx(&bars[B_XFULL], 4u * static_cast<uint32_t>(a.rows_pt) * 128u);
+        for (int kb = 0; kb < 4; ++kb)
+          tma_load_2d(smem + OFF_BUF0 + kb * BLK, &tmX, &bars[B_XFULL], kb * 64, tile * a.rows_pt);
+        // in-proj: per head the Q / K / V row slices (64 rows each) of Win, k-block by k-block
+        for (int h = 0; h < NH; ++h)
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&bars[B_EMPTY0 + s], ph ^ 1);
+            mbar_arrive_expect_tx(&bars[B_FULL0 + s], 3u * 8192u);
+            uint8_t* dst = smem + OFF_RING + s * SLOT;
+            for (int t = 0; t < 3; ++t)
+              tma_load_2d(dst + t * 8192, &tmWin, &bars[B_FULL0 + s], kb * 64, t * E + h * HD);
+            next_slot();
+          }
+        // out-proj, ffn1 (two halves of 256 hidden units), ffn2 (two K halves)
+        for (int blk = 0; blk < 5; ++blk)
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&bars[B_EMPTY0 + s], ph ^ 1);
+            mbar_arrive_expect_tx(&bars[B_FULL0 + s], 32768u);
+            uint8_t* dst = smem + OFF_RING + s * SLOT;
+            if (blk == 0) tma_load_2d(dst, &tmWo, &bars[B_FULL0 + s], kb * 64, 0);
+            else if (blk <= 2) tma_load_2d(dst, &tmW1, &bars[B_FULL0 + s], kb * 64, (blk - 1) * 256);
+            else tma_load_2d(dst, &tmW2, &bars[B_FULL0 + s], (blk - 3) * 256 + kb * 64, 0);
+            next_slot();
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_qkv = make_idesc_bf16(128, 192, 0, 0);
+      const uint32_t idesc_256 = make_idesc_bf16(128, 256, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      auto kblocks = [&](uint32_t d_tmem, uint32_t a_base, uint32_t idesc, bool accumulate) {
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&bars[B_FULL0 + s], ph);
+          tc_fence_after_sync();
+          mma_kblock(d_tmem, a_base + kb * BLK, ring + s * SLOT, idesc, accumulate || kb > 0);
+          tc_commit(&bars[B_EMPTY0 + s]);
+          if (++s == 2) { s = 0; ph ^= 1; }
+        }
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1;
+        mbar_wait(&bars[B_XFULL], par);
+        tc_fence_after_sync();
+        for (int h = 0; h < NH; ++h) {
+          const int b = h & 1, use = 2 * it + (h >> 1);
+          mbar_wait(&bars[B_ACCEMPTY0 + b], (use & 1) ^ 1);
+          tc_fence_after_sync();
+          kblocks(tmem_base + b * 256, buf0, idesc_qkv, false);
+          tc_commit(&bars[B_ACCFULL0 + b]);
+        }
+        mbar_wait(&bars[B_AOFULL], par);
+        tc_fence_after_sync();
+        kblocks(tmem_base, buf1, idesc_256, false);
+        tc_commit(&bars[B_ACC2FULL]);
+        mbar_wait(&bars[B_X1FULL], par);
+        tc_fence_after_sync();
+        kblocks(tmem_base + 256, buf0, idesc_256, false);
+        tc_commit(&bars[B_F1AFULL]);
+        kblocks(tmem_base, buf0, idesc_256, false);
+        tc_commit(&bars[B_F1BFULL]);
+        mbar_wait(&bars[B_HAFULL], par);
+        tc_fence_after_sync();
+        kblocks(tmem_base + 256, buf1, idesc_256, false);
+        tc_commit(&bars[B_F2ADONE]);
+        mbar_wait(&bars[B_HBFULL], par);
+        tc_fence_after_sync();
+        kblocks(tmem_base + 256, buf1, idesc_256, true);
+        tc_commit(&bars[B_OUTFULL]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;      // 0..7
+    const int q = warp & 3;       // TMEM lane quarter this warp may touch
+    const int hf = ew >> 2;       // which half of an accumulator's columns this warp drains
+    const int row = q * 32 + lane;
+    const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const bool drop = a.drop_p > 0.f;
+    uint64_t seed = 0, step = 0;
+    float keep_scale = 1.f;
+    uint32_t thr = 0;
+    if (drop) {
+      seed = a.rng[0];
+      step = a.rng[1];
+      keep_scale = 1.f / (1.f - a.drop_p);
+      thr = dropout_thr(a.drop_p);
+    }
+    float* red = reinterpret_cast<float*>(smem + OFF_KV);  // [2 halves][128 rows] partial sums (LayerNorm phases)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
+      const int seq_l = row / a.S;
+      const int64_t gseq = static_cast<int64_t>(tile) * a.spt + seq_l;
+      const bool valid = seq_l < a.spt && gseq < a.nb;
+      const int64_t grow = static_cast<int64_t>(tile) * a.rows_pt + row;
+      const bool save = valid && grow < a.save_rows;
+
+      // ------------------------------------------------------------ in-proj + attention, head by head
+      for (int h = 0; h < NH; ++h) {
+        const int b = h & 1, use = 2 * it + (h >> 1);
+        mbar_wait(&bars[B_ACCFULL0 + b], use & 1);
+        tc_fence_after_sync();
+        bar_sync_epi();  // the previous head's attention has finished with the K / V staging tiles
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+          const int cc = hf * 3 + c;         // 0..5: 32-column chunk of [Q_h | K_h | V_h]
+          const int t = cc >> 1, sub = cc & 1;
+          float v[32];
+          tmem_ld_32x32(tm_lane + b * 256 + cc * 32, v);
+          tmem_ld_wait();
+          if (a.b_in) {
+            const float4* bp = reinterpret_cast<const float4*>(a.b_in + t * E + h * HD + sub * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(bp + j);
+              v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
+            }
+          }
+          uint8_t* blk = t == 0 ? smem + OFF_BUF1 + h * BLK : smem + OFF_KV + (t - 1) * BLK;
+          bf16* gdst = a.qkv + grow * (3 * E) + t * E + h * HD + sub * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 pk = pack8(v + 8 * j);
+            *reinterpret_cast<uint4*>(blk + swz(row, sub * 4 + j)) = pk;
+            if (save) *reinterpret_cast<uint4*>(gdst + 8 * j) = pk;
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY0 + b]);
+        bar_sync_epi();  // Q / K / V tiles of this head are complete
+        for (int sl = ew; sl < a.spt; sl += 8) {
+          const int64_t gs = static_cast<int64_t>(tile) * a.spt + sl;
+          if (gs >= a.nb) break;
+          const uint8_t* mk = a.mask ? a.mask + (gs % a.mask_mod) * a.S : nullptr;
+          attention_task(smem + OFF_BUF1 + h * BLK, smem + OFF_KV, smem + OFF_KV + BLK, sl * a.S, a.S, mk, a.drop_p,
+                         seed, step, a.site, (static_cast<uint64_t>(gs) * NH + h) * a.S * a.S, lane);
+        }
+      }
+      fence_proxy_async_smem();  // attention outputs (generic-proxy stores) -> visible to the MMA's operand reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_AOFULL]);
+      // the attention output is also an input of the backward (out-proj weight gradient, softmax delta)
+      bar_sync_epi();
+      if (save) {
+#pragma unroll 1
+        for (int j = 0; j < 16; ++j) {
+          const int col8 = hf * 16 + j;  // 16-byte chunk of the row
+          *reinterpret_cast<uint4*>(a.ao + grow * E + col8 * 8) =
+              *reinterpret_cast<const uint4*>(smem + OFF_BUF1 + (col8 >> 3) * BLK + swz(row, col8 & 7));
+        }
+      }
+
+      // ------------------------------------------------------------ out-proj epilogue: x1 = LN1(x + drop(sa))
+      // and, further down with the same code, out = LN2(x1 + drop(ff)); thread = (row, 128 columns)
+      // Sweep 1 (per 32-column chunk): accumulator + bias -> dropout -> + residual = z; fp32 sum / sum of squares;
+      // z kept as packed bf16 (what the backward reads back as the pre-LayerNorm tensor). Sweep 2 normalises the
+      // stored z with the fp32 statistics of the unrounded values.
+      uint4 zq[16];
+      auto layer_norm_epilogue = [&](uint32_t tm_acc, const float* bias, uint32_t site, bool res_from_smem,
+                                     const float* gamma, const float* beta, bf16* zdst, bf16* ydst, bool ysave,
+                                     float* mean_out, float* rstd_out, bool to_smem) {
+        float s = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = hf * 128 + c * 32;
+          float v[32];
+          tmem_ld_32x32(tm_acc + col0, v);
+          tmem_ld_wait();
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);
+              v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
+            }
+          }
+          if (drop) dropout32(v, seed, step, site, static_cast<uint64_t>(grow) * E + col0, thr, keep_scale);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (res_from_smem) {
+              const int col8 = (col0 >> 3) + j;
+              r = *reinterpret_cast<const uint4*>(smem + OFF_BUF0 + (col8 >> 3) * BLK + swz(row, col8 & 7));
+            } else if (valid) {
+              r = __ldg(reinterpret_cast<const uint4*>(a.x + grow * E + col0) + j);
+            }
+            float rf[8];
+            unpack8(r, rf);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const float z = v[8 * j + t] + rf[t];
+              v[8 * j + t] = z;
+              s += z;
+              s2 = fmaf(z, z, s2);
+            }
+            zq[4 * c + j] = pack8(v + 8 * j);
+          }
+        }
+        red[hf * 128 + row] = s;
+        red[256 + hf * 128 + row] = s2;
+        bar_sync_epi();
+        const float mu = (red[row] + red[128 + row]) * (1.f / E);
+        const float var = fmaxf((red[256 + row] + red[384 + row]) * (1.f / E) - mu * mu, 0.f);
+        const float rs = rsqrtf(var + a.eps);
+        bar_sync_epi();  // (the partial sums may be overwritten by the next LayerNorm / the next tile's staging)
+        if (hf == 0 && save) {
+          mean_out[grow] = mu;
+          rstd_out[grow] = rs;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = hf * 128 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (save) *reinterpret_cast<uint4*>(zdst + grow * E + col0 + 8 * j) = zq[4 * c + j];
+            float zz[8], y[8];
+            unpack8(zq[4 * c + j], zz);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col0 + 8 * j));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col0 + 8 * j) + 1);
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (beta) {
+              b0 = __ldg(reinterpret_cast<const float4*>(beta + col0 + 8 * j));
+              b1 = __ldg(reinterpret_cast<const float4*>(beta + col0 + 8 * j) + 1);
+            }
+            y[0] = (zz[0] - mu) * rs * g0.x + b0.x; y[1] = (zz[1] - mu) * rs * g0.y + b0.y;
+            y[2] = (zz[2] - mu) * rs * g0.z + b0.z; y[3] = (zz[3] - mu) * rs * g0.w + b0.w;
+            y[4] = (zz[4] - mu) * rs * g1.x + b1.x; y[5] = (zz[5] - mu) * rs * g1.y + b1.y;
+            y[6] = (zz[6] - mu) * rs * g1.z + b1.z; y[7] = (zz[7] - mu) * rs * g1.w + b1.w;
+            const uint4 pk = pack8(y);
+            const int col8 = (col0 >> 3) + j;
+            if (to_smem) *reinterpret_cast<uint4*>(smem + OFF_BUF0 + (col8 >> 3) * BLK + swz(row, col8 & 7)) = pk;
+            if (ysave) *reinterpret_cast<uint4*>(ydst + grow * E + col0 + 8 * j) = pk;
+          }
+        }
+      };
+      mbar_wait(&bars[B_ACC2FULL], par);
+      tc_fence_after_sync();
+      layer_norm_epilogue(tm_lane, a.b_out, a.site + 1, false, a.g1, a.be1, a.z1, a.x1, save, a.mean1, a.rstd1, true);
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_X1FULL]);
+
+      // ------------------------------------------------------------ ffn1 epilogues: h = drop(relu(x1 W1^T + b1))
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&bars[half == 0 ? B_F1AFULL : B_F1BFULL], par);
+        if (half == 1) mbar_wait(&bars[B_F2ADONE], par);  // the first half's ffn2 MMAs have finished reading BUF1
+        tc_fence_after_sync();
+        const uint32_t tm_acc = tm_lane + (half == 0 ? 256 : 0);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = hf * 128 + c * 32;  // within this half
+          const int hcol = half * 256 + col0;  // hidden unit
+          float w[32];
+          tmem_ld_32x32(tm_acc + col0, w);
+          tmem_ld_wait();
+          if (a.b_ff1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(a.b_ff1 + hcol) + j);
+              w[4 * j] += bv.x; w[4 * j + 1] += bv.y; w[4 * j + 2] += bv.z; w[4 * j + 3] += bv.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w[j] = fmaxf(w[j], 0.f);
+          if (drop) dropout32(w, seed, step, a.site + 2, static_cast<uint64_t>(grow) * F + hcol, thr, keep_scale);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 pk = pack8(w + 8 * j);
+            const int col8 = (col0 >> 3) + j;
+            *reinterpret_cast<uint4*>(smem + OFF_BUF1 + (col8 >> 3) * BLK + swz(row, col8 & 7)) = pk;
+            if (save) *reinterpret_cast<uint4*>(a.h + grow * F + hcol + 8 * j) = pk;
+          }
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[half == 0 ? B_HAFULL : B_HBFULL]);
+      }
+
+      // ------------------------------------------------------------ ffn2 epilogue: out = LN2(x1 + drop(ff))
+      mbar_wait(&bars[B_OUTFULL], par);
+      tc_fence_after_sync();
+      layer_norm_epilogue(tm_lane + 256, a.b_ff2, a.site + 3, true, a.g2, a.be2, a.z2, a.out, valid, a.mean2, a.rstd2,
+                          false);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_TILEDONE]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace el
+
+// x [nb * S, 256] bf16 -> the layer's output and (rows < save_rows) the tensors the backward reads.
+int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
+  using namespace el;
+  GG_REQUIRE(p.E == E && p.F == F && p.n_heads == NH, "fused encoder layer: E=256, ffn=512, 4 heads only");
+  GG_REQUIRE(p.S >= 1 && p.S <= 16 && p.nb >= 1, "fused encoder layer: 1..16 tokens per sequence");
+  GG_REQUIRE(p.x && p.out && p.w_in && p.w_out && p.w_ff1 && p.w_ff2 && p.g1 && p.g2, "fused encoder layer: null tensor");
+  GG_REQUIRE(p.drop_p == 0.f || p.rng, "dropout needs an rng state pointer");
+  Args a;
+  a.nb = p.nb; a.S = p.S;
+  a.spt = 128 / p.S;
+  a.rows_pt = a.spt * p.S;
+  a.num_tiles = ceil_div(p.nb, a.spt);
+  a.rows_total = static_cast<int64_t>(p.nb) * p.S;
+  a.save_rows = p.save_rows < 0 ? a.rows_total : (p.save_rows > a.rows_total ? a.rows_total : p.save_rows);
+  if (a.save_rows > 0)
+    GG_REQUIRE(p.qkv && p.ao && p.z1 && p.x1 && p.h && p.z2 && p.mean1 && p.rstd1 && p.mean2 && p.rstd2,
+               "fused encoder layer: save_rows > 0 needs every backward tensor");
+  a.x = static_cast<const bf16*>(p.x);
+  a.b_in = p.b_in; a.b_out = p.b_out; a.b_ff1 = p.b_ff1; a.b_ff2 = p.b_ff2;
+  a.g1 = p.g1; a.be1 = p.be1; a.g2 = p.g2; a.be2 = p.be2;
+  a.mask = p.mask; a.mask_mod = p.mask_mod > 0 ? p.mask_mod : p.nb;
+  a.drop_p = p.drop_p; a.eps = p.eps; a.rng = p.rng; a.site = p.site;
+  a.qkv = static_cast<bf16*>(p.qkv); a.ao = static_cast<bf16*>(p.ao); a.z1 = static_cast<bf16*>(p.z1);
+  a.x1 = static_cast<bf16*>(p.x1); a.h = static_cast<bf16*>(p.h); a.z2 = static_cast<bf16*>(p.z2);
+  a.out = static_cast<bf16*>(p.out);
+  a.mean1 = p.mean1; a.rstd1 = p.rstd1; a.mean2 = p.mean2; a.rstd2 = p.rstd2;
+  CUtensorMap mX, mWin, mWo, mW1, mW2;
+  GG_TRY_RC(encode_tma_map(&mX, p.x, E, a.rows_total, E, a.rows_pt, false));
+  GG_TRY_RC(encode_tma_map(&mWin, p.w_in, E, 3 * E, p.ld_in, 64, false));
+  GG_TRY_RC(encode_tma_map(&mWo, p.w_out, E, E, p.ld_out, 256, false));
+  GG_TRY_RC(encode_tma_map(&mW1, p.w_ff1, E, F, p.ld_ff1, 256, false));
+  GG_TRY_RC(encode_tma_map(&mW2, p.w_ff2, F, E, p.ld_ff2, 256, false));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(enc_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  GG_CUDA_CHECK(attr_err);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    GG_CUDA_CHECK(cudaGetDevice(&dev));
+    GG_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+  launch_k(enc_layer_fwd_kernel, static_cast<unsigned>(grid), THREADS, SMEM_BYTES, st, mX, mWin, mWo, mW1, mW2, a);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
+}  // namespace gg
+
+extern "C" int gg_encoder_layer_fwd(const gg_enc_layer_params* p, void* stream) {
+  GG_REQUIRE(p != nullptr, "null argument");
+  int dev = 0;
+  GG_CUDA_CHECK(cudaGetDevice(&dev));
+  GG_TRY_RC(gg_check_device(dev));
+  return gg::k_enc_layer_fwd(*p, reinterpret_cast<cudaStream_t>(stream));
+}

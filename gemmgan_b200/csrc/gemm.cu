@@ -679,8 +679,14 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D tensor [outer, inner] of bf16 (or fp32) with row pitch ld (elements); box = {box_inner, box_outer},
 // 128B swizzle (box_inner * element size = 128 bytes).
+int encode_tma_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer,
+                   bool f32);
 static int encode_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld,
                       int box_outer, bool f32 = false) {
+  return encode_tma_map(map, ptr, inner, outer, ld, box_outer, f32);
+}
+int encode_tma_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer,
+                   bool f32) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (driver too old?)");

@@ -57,6 +57,10 @@ int k_embed_grad(const bf16* dc, const int64_t* y0, const int64_t* y1, int V0, i
                  int Eh, cudaStream_t st);
 int k_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, cudaStream_t st);
 
+// ---- enc_layer.cu: one encoder layer forward as one tcgen05 kernel (S <= 16 tokens, E = 256, ffn = 512, 4 heads)
+typedef gg_enc_layer_params EncLayerParams;
+int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st);
+
 // ---- wgrad_group.cu: all single-segment weight gradients dW = dY^T X of one backward pass in one launch
 constexpr int WGRAD_GROUP_MAX = 32;
 constexpr int WGRAD_GROUP_MAX_SPLITS = 4;

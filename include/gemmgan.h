@@ -317,6 +317,35 @@ typedef struct gg_attn_args {
 int gg_attention_fwd(const gg_attn_args* a, void* stream);
 int gg_attention_bwd(const gg_attn_args* a, void* stream);
 
+/* One post-norm nn.TransformerEncoderLayer forward (d_model 256, 4 heads x 64, ffn 512, relu, dropout p) as ONE kernel
+ * for short sequences (S <= 16 tokens: the paper model's 8 patches + CLS): in-proj, masked softmax attention, out-proj,
+ * residual + dropout + LayerNorm, ffn1 + relu + dropout, ffn2, residual + dropout + LayerNorm
+ * (src/conditional_gan_cross_attention_with_film.py:114-119, :144; torch/nn/modules/transformer.py post-norm branch,
+ * F.multi_head_attention_forward). x [nb * S, 256] bf16 (row = sequence * S + token); weights bf16 [out, in] with
+ * pitches that are multiples of 8; biases / LayerNorm vectors fp32 (b_* and be* may be NULL: bias=False variants).
+ * mask [mask_mod, S] uint8 (1 = padded key), sequence b uses row b % mask_mod; may be NULL. Dropout: sites
+ * site .. site + 3 (attention probabilities, after out-proj, after relu, after ffn2) of the {seed, step} stream at
+ * `rng`, indexed exactly as gg_attention_fwd / the GEMM epilogue / the LayerNorm kernel index them, so the unfused
+ * backward regenerates the same masks. Rows < save_rows (negative: all) also write what the backward reads: qkv
+ * [rows, 768], ao (attention output), z1 / z2 (pre-LayerNorm sums), x1, h [rows, 512], mean / rstd (fp32 [rows]);
+ * with save_rows = 0 those pointers may be NULL and only `out` is written. */
+typedef struct gg_enc_layer_params {
+  int32_t nb, S, E, F, n_heads;
+  int64_t save_rows;
+  const void* x;
+  const void* w_in; int64_t ld_in;
+  const void* w_out; int64_t ld_out;
+  const void* w_ff1; int64_t ld_ff1;
+  const void* w_ff2; int64_t ld_ff2;
+  const float *b_in, *b_out, *b_ff1, *b_ff2, *g1, *be1, *g2, *be2;
+  const uint8_t* mask; int32_t mask_mod;
+  float drop_p, eps;
+  const uint64_t* rng; uint32_t site;
+  void *qkv, *ao, *z1, *x1, *h, *z2, *out;
+  float *mean1, *rstd1, *mean2, *rstd2;
+} gg_enc_layer_params;
+int gg_encoder_layer_fwd(const gg_enc_layer_params* p, void* stream);
+
 /* Grouped weight gradients: out_i[M_i, N_i] (fp32, pitch ld) = dY_i^T X_i for up to 32 problems in ONE launch
  * (autograd's grad_output.t().mm(input) of every Linear of one backward pass, :412 / :455). dY_i is stored
  * [K_i rows, M_i], X_i [K_i rows, N_i], both bf16 with 16-byte aligned bases and pitches that are multiples of

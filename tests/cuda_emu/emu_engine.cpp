@@ -32,7 +32,12 @@ int k_wgrad_group(const WgradItem*, int, void*, int64_t, cudaStream_t) {
   set_error("the grouped weight-gradient kernel is tcgen05 only (not available in the host emulation)");
   return GG_ERR_ARCH;
 }
+int k_enc_layer_fwd(const EncLayerParams&, cudaStream_t) {
+  set_error("the fused encoder-layer kernel is tcgen05 only (not available in the host emulation)");
+  return GG_ERR_ARCH;
+}
 }  // namespace gg
+extern "C" int gg_encoder_layer_fwd(const gg_enc_layer_params*, void*) { return GG_ERR_ARCH; }
 
 #include "../../gemmgan_b200/csrc/engine.cu"
 
