@@ -69,7 +69,13 @@ struct Args {
   uint32_t site;
   bf16 *qkv, *ao, *z1, *x1, *h, *z2, *out;
   float *mean1, *rstd1, *mean2, *rstd2;
+  long long* trace;  // diagnostics (gg_enc_layer_set_trace): clock64() stamps of CTA 0's first tile, 3 roles x 64
 };
+constexpr int TRACE_SLOTS = 64;
+#define EL_STAMP(role, idx)                                                                  \
+  do {                                                                                       \
+    if (tr && (idx) < TRACE_SLOTS) tr[(role) * TRACE_SLOTS + (idx)] = clock64();             \
+  } while (0)
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk) {
   return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
@@ -290,7 +296,11 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (++s == 2) { s = 0; ph ^= 1; }
       };
       int it = 0;
+      long long* tr = blockIdx.x == 0 ? a.trace : nullptr;
+      int ts = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        if (it > 0) tr = nullptr;
+        EL_STAMP(0, ts++);
         mbar_wait(&bars[B_TILEDONE], (it & 1) ^ 1);  // the previous tile's last reader of BUF0 (x1 residual) is done
         mbar_arrive_expect_tx(&bars[B_XFULL], 4u * static_cast<uint32_t>(a.rows_pt) * 128u);
         for (int kb = 0; kb < 4; ++kb)
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int h = 0; h < NH; ++h)
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(&bars[B_EMPTY0 + s], ph ^ 1);
+            EL_STAMP(0, ts++);
             mbar_arrive_expect_tx(&bars[B_FULL0 + s], 3u * 8192u);
             uint8_t* dst = smem + OFF_RING + s * SLOT;
             for (int t = 0; t < 3; ++t)
@@ -309,6 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int blk = 0; blk < 5; ++blk)
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(&bars[B_EMPTY0 + s], ph ^ 1);
+            EL_STAMP(0, ts++);
             mbar_arrive_expect_tx(&bars[B_FULL0 + s], 32768u);
             uint8_t* dst = smem + OFF_RING + s * SLOT;
             if (blk == 0) tma_load_2d(dst, &tmWo, &bars[B_FULL0 + s], kb * 64, 0);
@@ -334,35 +346,51 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       };
       int it = 0;
+      long long* tr = blockIdx.x == 0 ? a.trace : nullptr;
+      int ts = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        if (it > 0) tr = nullptr;
         const uint32_t par = it & 1;
+        EL_STAMP(1, ts++);
         mbar_wait(&bars[B_XFULL], par);
+        EL_STAMP(1, ts++);
         tc_fence_after_sync();
         for (int h = 0; h < NH; ++h) {
           const int b = h & 1, use = 2 * it + (h >> 1);
           mbar_wait(&bars[B_ACCEMPTY0 + b], (use & 1) ^ 1);
           tc_fence_after_sync();
+          EL_STAMP(1, ts++);
           kblocks(tmem_base + b * 256, buf0, idesc_qkv, false);
           tc_commit(&bars[B_ACCFULL0 + b]);
+          EL_STAMP(1, ts++);
         }
         mbar_wait(&bars[B_AOFULL], par);
+        EL_STAMP(1, ts++);
         tc_fence_after_sync();
         kblocks(tmem_base, buf1, idesc_256, false);
         tc_commit(&bars[B_ACC2FULL]);
+        EL_STAMP(1, ts++);
         mbar_wait(&bars[B_X1FULL], par);
+        EL_STAMP(1, ts++);
         tc_fence_after_sync();
         kblocks(tmem_base + 256, buf0, idesc_256, false);
         tc_commit(&bars[B_F1AFULL]);
+        EL_STAMP(1, ts++);
         kblocks(tmem_base, buf0, idesc_256, false);
         tc_commit(&bars[B_F1BFULL]);
+        EL_STAMP(1, ts++);
         mbar_wait(&bars[B_HAFULL], par);
+        EL_STAMP(1, ts++);
         tc_fence_after_sync();
         kblocks(tmem_base + 256, buf1, idesc_256, false);
         tc_commit(&bars[B_F2ADONE]);
+        EL_STAMP(1, ts++);
         mbar_wait(&bars[B_HBFULL], par);
+        EL_STAMP(1, ts++);
         tc_fence_after_sync();
         kblocks(tmem_base + 256, buf1, idesc_256, true);
         tc_commit(&bars[B_OUTFULL]);
+        EL_STAMP(1, ts++);
       }
     }
   } else {
@@ -383,7 +411,10 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     float* red = reinterpret_cast<float*>(smem + OFF_KV);  // [2 halves][128 rows] partial sums (LayerNorm phases)
     int it = 0;
+    long long* tr = (blockIdx.x == 0 && ew == 0 && lane == 0) ? a.trace : nullptr;
+    int ts = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      if (it > 0) tr = nullptr;
       const uint32_t par = it & 1;
       const int seq_l = row / a.S;
       const int64_t gseq = static_cast<int64_t>(tile) * a.spt + seq_l;
@@ -394,7 +425,9 @@ __global__ void __launch_bounds__(THREADS, 1)
       // ------------------------------------------------------------ in-proj + attention, head by head
       for (int h = 0; h < NH; ++h) {
         const int b = h & 1, use = 2 * it + (h >> 1);
+        EL_STAMP(2, ts++);
         mbar_wait(&bars[B_ACCFULL0 + b], use & 1);
+        EL_STAMP(2, ts++);
         tc_fence_after_sync();
         bar_sync_epi();  // the previous head's attention has finished with the K / V staging tiles
 #pragma unroll 1
@@ -425,6 +458,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY0 + b]);
         bar_sync_epi();  // Q / K / V tiles of this head are complete
+        EL_STAMP(2, ts++);
         for (int sl = ew; sl < a.spt; sl += 8) {
           const int64_t gs = static_cast<int64_t>(tile) * a.spt + sl;
           if (gs >= a.nb) break;
@@ -433,6 +467,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                          seed, step, a.site, (static_cast<uint64_t>(gs) * NH + h) * a.S * a.S, lane);
         }
       }
+      EL_STAMP(2, ts++);
       fence_proxy_async_smem();  // attention outputs (generic-proxy stores) -> visible to the MMA's operand reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_AOFULL]);
@@ -529,19 +564,23 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
         }
       };
+      EL_STAMP(2, ts++);
       mbar_wait(&bars[B_ACC2FULL], par);
+      EL_STAMP(2, ts++);
       tc_fence_after_sync();
       layer_norm_epilogue(tm_lane, a.b_out, a.site + 1, false, a.g1, a.be1, a.z1, a.x1, save, a.mean1, a.rstd1, true);
       tc_fence_before_sync();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_X1FULL]);
+      EL_STAMP(2, ts++);
 
       // ------------------------------------------------------------ ffn1 epilogues: h = drop(relu(x1 W1^T + b1))
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         mbar_wait(&bars[half == 0 ? B_F1AFULL : B_F1BFULL], par);
         if (half == 1) mbar_wait(&bars[B_F2ADONE], par);  // the first half's ffn2 MMAs have finished reading BUF1
+        EL_STAMP(2, ts++);
         tc_fence_after_sync();
         const uint32_t tm_acc = tm_lane + (half == 0 ? 256 : 0);
 #pragma unroll 1
@@ -573,16 +612,19 @@ __global__ void __launch_bounds__(THREADS, 1)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[half == 0 ? B_HAFULL : B_HBFULL]);
+        EL_STAMP(2, ts++);
       }
 
       // ------------------------------------------------------------ ffn2 epilogue: out = LN2(x1 + drop(ff))
       mbar_wait(&bars[B_OUTFULL], par);
+      EL_STAMP(2, ts++);
       tc_fence_after_sync();
       layer_norm_epilogue(tm_lane + 256, a.b_ff2, a.site + 3, true, a.g2, a.be2, a.z2, a.out, valid, a.mean2, a.rstd2,
                           false);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_TILEDONE]);
+      EL_STAMP(2, ts++);
     }
   }
 
@@ -592,6 +634,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 }  // namespace el
+
+static long long* g_el_trace = nullptr;
 
 // x [nb * S, 256] bf16 -> the layer's output and (rows < save_rows) the tensors the backward reads.
 int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
@@ -619,6 +663,7 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
   a.x1 = static_cast<bf16*>(p.x1); a.h = static_cast<bf16*>(p.h); a.z2 = static_cast<bf16*>(p.z2);
   a.out = static_cast<bf16*>(p.out);
   a.mean1 = p.mean1; a.rstd1 = p.rstd1; a.mean2 = p.mean2; a.rstd2 = p.rstd2;
+  a.trace = g_el_trace;
   CUtensorMap mX, mWin, mWo, mW1, mW2;
   GG_TRY_RC(encode_tma_map(&mX, p.x, E, a.rows_total, E, a.rows_pt, false));
   GG_TRY_RC(encode_tma_map(&mWin, p.w_in, E, 3 * E, p.ld_in, 64, false));
@@ -644,6 +689,13 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
 }
 
 }  // namespace gg
+
+// Diagnostics: CTA 0 of every following launch stamps clock64() per role for its first tile into device_buf
+// (3 x 64 int64: TMA producer / MMA issuer / epilogue warp 0); NULL switches it off.
+extern "C" int gg_enc_layer_set_trace(void* device_buf) {
+  gg::g_el_trace = reinterpret_cast<long long*>(device_buf);
+  return GG_OK;
+}
 
 extern "C" int gg_encoder_layer_fwd(const gg_enc_layer_params* p, void* stream) {
   GG_REQUIRE(p != nullptr, "null argument");

@@ -285,6 +285,7 @@ struct gg_engine {
   bool text_lane_fwd = true, text_lane_bwd = false;  // GEMMGAN_TEXT_LANE = <fwd><bwd> digits overrides
   bool split_tail_flush = false;  // measured: splitting the last flush costs 0.28 ms / train() (the grouped kernel occupies every SM)
   bool fuse_bias = true;  // GEMMGAN_FUSE_BIAS=0: keep every bias gradient in the grouped column-sum kernel
+  bool fused_layer = true;  // GEMMGAN_FUSED_LAYER=0: encoder layers as seven launches instead of enc_layer.cu's one
   // one workspace per flush in flight: flushes of one entry point run back to back on their lane, so
   // they rotate through GROUP_WS_SLOTS regions
   void *wg_ws = nullptr, *cs_ws = nullptr;
@@ -567,9 +568,17 @@ static void derive(gg_engine& e) {
   e.hd = (e.cond && !e.label) ? c.E / c.n_heads : 0;
 }
 
+// the fused encoder-layer kernel covers the reference's layer shape (d_model 256, 4 heads, ffn 512) at <= 16 tokens
+static bool cfg_fused_layer_ok(const gg_engine& e) {
+  const gg_model_cfg& c = e.cfg;
+  return c.gemm_impl == GG_IMPL_TCGEN05 && c.E == 256 && c.ffn == 512 && c.n_heads == 4 && e.S_ <= 16;
+}
+
 // ------------------------------------------------------------------------------- tower forward
 // Runs entirely on lane `ln` (the generator's tower runs next to the critic's on another lane).
-static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
+// save_reps: replicas (leading row blocks) whose backward tensors are kept; the fused layer kernel writes nothing but
+// its output for the others (the generator's tower inside a critic step, the critic's interpolated replica, inference)
+static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save_reps) {
   const gg_model_cfg& c = e.cfg;
   Tower& t = e.tw[net];
   cudaStream_t st = e.S(ln);
@@ -622,6 +631,28 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln) {
     TowerLayer& L = t.L[l];
     const int ls = GG_P_LAYER0 + GG_L_COUNT * l;
     const uint32_t site = site0 + 8u * l;
+    if (e.fused_layer && cfg_fused_layer_ok(e)) {
+      // the whole post-norm layer as one tcgen05 kernel (enc_layer.cu): same tensors, same dropout streams
+      EncLayerParams q;
+      memset(&q, 0, sizeof(q));
+      q.nb = R * B; q.S = S; q.E = E; q.F = F; q.n_heads = c.n_heads;
+      q.save_rows = static_cast<int64_t>(save_reps < R ? save_reps : R) * B * S;
+      q.x = t.X[l];
+      const Op wi = e.W(net, ls + GG_L_IN_W), wo = e.W(net, ls + GG_L_OUT_W), w1 = e.W(net, ls + GG_L_FF1_W),
+               w2 = e.W(net, ls + GG_L_FF2_W);
+      q.w_in = wi.p; q.ld_in = wi.ld; q.w_out = wo.p; q.ld_out = wo.ld;
+      q.w_ff1 = w1.p; q.ld_ff1 = w1.ld; q.w_ff2 = w2.p; q.ld_ff2 = w2.ld;
+      q.b_in = e.P(net, ls + GG_L_IN_B); q.b_out = e.P(net, ls + GG_L_OUT_B);
+      q.b_ff1 = e.P(net, ls + GG_L_FF1_B); q.b_ff2 = e.P(net, ls + GG_L_FF2_B);
+      q.g1 = e.P(net, ls + GG_L_N1_W); q.be1 = e.P(net, ls + GG_L_N1_B);
+      q.g2 = e.P(net, ls + GG_L_N2_W); q.be2 = e.P(net, ls + GG_L_N2_B);
+      q.mask = e.mask_s; q.mask_mod = B;
+      q.drop_p = p; q.eps = c.ln_eps; q.rng = e.rng; q.site = site;
+      q.qkv = L.qkv; q.ao = L.ao; q.z1 = L.z1; q.x1 = L.x1; q.h = L.h; q.z2 = L.z2; q.out = t.X[l + 1];
+      q.mean1 = L.mean1; q.rstd1 = L.rstd1; q.mean2 = L.mean2; q.rstd2 = L.rstd2;
+      GG_TRY(k_enc_layer_fwd(q, st));
+      continue;
+    }
     GG_TRY(e.linear(ln, rows, 3 * E, E, Op{t.X[l], E}, e.W(net, ls + GG_L_IN_W),
                     Epi().bias(e.P(net, ls + GG_L_IN_B)).obf(L.qkv, 3 * E)));
     AttnArgs a;
@@ -861,7 +892,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
 }
 
 // --------------------------------------------------------------------------- generator forward
-static int gen_forward(gg_engine& e, const float* z, float p, float* out_f32, int ln) {
+static int gen_forward(gg_engine& e, const float* z, float p, float* out_f32, int ln, bool need_bwd) {
   const gg_model_cfg& c = e.cfg;
   TrunkBufs& t = e.tb;
   cudaStream_t st = e.S(ln);
@@ -871,7 +902,7 @@ static int gen_forward(gg_engine& e, const float* z, float p, float* out_f32, in
   const int net = GG_NET_GEN;
   Epi e1 = Epi().bias(e.P(net, GG_P_TR0_B)).act(GG_ACT_LEAKY, c.slope).obf(t.hg1, H);
   if (e.cond) {
-    GG_TRY(tower_forward(e, net, 1, p, ln));
+    GG_TRY(tower_forward(e, net, 1, p, ln, need_bwd ? 1 : 0));
     const Op cv = cond_vec(e, net);
     GG_TRY(e.mm(ln, B, H, L, Op{e.zbf, Lp}, 0, e.W(net, GG_P_TR0_W), 0, e1, E, cv,
                 Op{e.sh[net].tr0_c.p, e.sh[net].tr0_c.ld}));
@@ -911,7 +942,8 @@ static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, 
 // matrix of W1x. Leaves u2, u1, y, dv1, ru1, norms, pen and the loss stats behind.
 // `fake_lane`: lane that is producing the fake rows of xfr (joined before the trunk reads them); the
 // critic tower (conditioning only) and the Gram matrix (weights only) do not wait for it.
-static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int fake_lane, int gp_lane = 0) {
+static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int fake_lane, int gp_lane = 0,
+                           int save_reps = 0) {
   const gg_model_cfg& c = e.cfg;
   TrunkBufs& t = e.tb;
   const int B = c.B, H = c.H, G = c.G, net = GG_NET_DISC;
@@ -919,7 +951,7 @@ static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int
   const Op W1x = e.W(net, GG_P_TR0_W), W2 = e.W(net, GG_P_TR1_W);
   GG_TRY(e.fork(2));
   GG_TRY(e.mm(2, H, H, G, W1x, 0, W1x, 0, Epi().of32(t.Mg, H).obf(t.Mgb, H)));
-  if (e.cond) GG_TRY(tower_forward(e, net, R, p, 0));
+  if (e.cond) GG_TRY(tower_forward(e, net, R, p, 0, save_reps));
   GG_TRY(e.join(fake_lane));
   GG_TRY(critic_trunk_forward(e, e.xfr, 2, 3, R, alpha));
   // The penalty's own chain (u2 -> u1 -> y = u1 M -> row norms -> losses) feeds only the loss statistics and the
@@ -989,6 +1021,8 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
     if (const char* sf = getenv("GEMMGAN_SPLIT_TAIL_FLUSH")) e->split_tail_flush = sf[0] != '0';
     const char* fb = getenv("GEMMGAN_FUSE_BIAS");
     e->fuse_bias = !(fb && fb[0] == '0');
+    const char* fl = getenv("GEMMGAN_FUSED_LAYER");
+    e->fused_layer = !(fl && fl[0] == '0');
   }
   for (int l = 1; l < gg_engine::NLANES; ++l)
     GG_CUDA_CHECK(cudaStreamCreateWithFlags(&e->cur[l], cudaStreamNonBlocking));
@@ -1100,8 +1134,8 @@ static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int
   // ---- forward: G(z) (no graph) on lane 1 next to the critic tower on lane 0; D on fake / real /
   // interpolated rows (:391-408), GP value (:351-374)
   GG_TRY(e->fork(1));
-  GG_TRY(gen_forward(*e, z, p, nullptr, 1));
-  GG_TRY(disc_forward_gp(*e, R, p, alpha, 1, 1));  // the GP chain continues on lane 1
+  GG_TRY(gen_forward(*e, z, p, nullptr, 1, false));      // (no graph: the generator is not trained here)
+  GG_TRY(disc_forward_gp(*e, R, p, alpha, 1, 1, Rg));  // the GP chain continues on lane 1
   const Op W1x = e->W(net, GG_P_TR0_W), W2 = e->W(net, GG_P_TR1_W);
   const float* w3 = e->P(net, GG_P_FIN_W);
   const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;
@@ -1182,9 +1216,9 @@ static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase,
   // then D(fake) (:441-452)
   if (e->cond) {
     GG_TRY(e->fork(1));
-    GG_TRY(tower_forward(*e, D, 1, p, 1));
+    GG_TRY(tower_forward(*e, D, 1, p, 1, 0));  // (the critic is frozen: nothing of its tower is back-propagated)
   }
-  GG_TRY(gen_forward(*e, z, p, nullptr, 0));
+  GG_TRY(gen_forward(*e, z, p, nullptr, 0, true));
   GG_TRY(e->join(1));
   GG_TRY(critic_trunk_forward(*e, e->xfr, 1, 1, 1, nullptr));
   GG_TRY(k_gen_loss(t.score, e->stats, B, inv_b, st));
@@ -1265,7 +1299,7 @@ extern "C" int gg_engine_generate(gg_engine* e, const float* z, float* out_f32, 
   e->begin(stream);
   const float p = (training && e->cond && !e->concat) ? e->cfg.dropout_p : 0.f;
   if (p > 0.f) GG_TRY(k_bump_rng(e->rng, e->S(0)));
-  return gen_forward(*e, z, p, out_f32, 0);
+  return gen_forward(*e, z, p, out_f32, 0, false);
 }
 
 extern "C" int gg_engine_critic(gg_engine* e, const float* genes_f32, float* score_f32, int training, void* stream) {
@@ -1276,7 +1310,7 @@ extern "C" int gg_engine_critic(gg_engine* e, const float* genes_f32, float* sco
   const float p = (training && e->cond && !e->concat) ? c.dropout_p : 0.f;
   if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
   GG_TRY(k_cast_f32_bf16(genes_f32, c.G, e->xin, e->Gp, c.B, c.G, st));
-  if (e->cond) GG_TRY(tower_forward(*e, GG_NET_DISC, 1, p, 0));
+  if (e->cond) GG_TRY(tower_forward(*e, GG_NET_DISC, 1, p, 0, 0));
   GG_TRY(critic_trunk_forward(*e, e->xin, 1, 1, 1, nullptr));
   GG_CUDA_CHECK(cudaMemcpyAsync(score_f32, e->tb.score, sizeof(float) * c.B, cudaMemcpyDeviceToDevice, st));
   return GG_OK;

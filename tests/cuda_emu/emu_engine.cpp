@@ -38,6 +38,7 @@ int k_enc_layer_fwd(const EncLayerParams&, cudaStream_t) {
 }
 }  // namespace gg
 extern "C" int gg_encoder_layer_fwd(const gg_enc_layer_params*, void*) { return GG_ERR_ARCH; }
+extern "C" int gg_enc_layer_set_trace(void*) { return GG_ERR_ARCH; }
 
 #include "../../gemmgan_b200/csrc/engine.cu"
 
