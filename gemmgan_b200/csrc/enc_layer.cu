@@ -16,7 +16,8 @@
 //            streamed through a 2-slot ring in the order the MMAs consume them
 //   warp 1   one thread issues tcgen05.mma (M = 128, N = 192 / 256, K = 16 per instruction), accumulators in TMEM:
 //            per head [Q_h | K_h | V_h] (double-buffered), then out-proj, ffn1 (two 256-wide halves), ffn2
-//   warps 2-9  epilogues (thread = accumulator row, two warps share a row and split its columns):
+//   warps 2-17 epilogues (thread = accumulator row, FOUR warps share a row and split its columns — the epilogues are
+//            chains of dependent TMEM / shared-memory accesses, so they want warps per scheduler, not registers):
 //            tcgen05.ld -> bias -> bf16 -> swizzled shared memory = the A operand of the next MMA (attention output,
 //            x1, relu hidden) — never HBM; the 9 x 9 attention itself runs per (sequence, head) on mma.sync
 //            fragments from the staged Q / K / V tiles; LayerNorm statistics in fp32 registers (two-pass),
@@ -41,11 +42,16 @@ int encode_tma_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t out
 namespace el {
 
 constexpr int E = 256, F = 512, HD = 64, NH = 4;
-constexpr int THREADS = 320;
+constexpr int EPI_WARPS = 16;           // 4 per TMEM lane quarter: each thread owns 64 of an accumulator row's 256 columns
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int BLK = 128 * 128;          // one [128 rows][64 bf16] block, 128B-swizzled (TMA / UMMA K-major layout)
 constexpr int OFF_BUF0 = 0;             // X tile, later x1                         (4 blocks)
 constexpr int OFF_BUF1 = 4 * BLK;       // Q_h / attention output, later relu hidden (4 blocks)
-constexpr int OFF_KV = 8 * BLK;         // K_h, V_h of the current head; later LayerNorm partial sums
+constexpr int OFF_KV = 8 * BLK;         // K_h, V_h of the current head; later LayerNorm partial sums + per-column vectors
+constexpr int OFF_RED = OFF_KV;         // [2 (sum, sum of squares)][4 parts][128 rows] floats
+constexpr int OFF_VEC = OFF_KV + 4096;  // b_out, g1, be1, b_ff1 (512), b_ff2, g2, be2: 2304 floats
+constexpr int V_BOUT = 0, V_G1 = 256, V_BE1 = 512, V_BFF1 = 768, V_BFF2 = 1280, V_G2 = 1536, V_BE2 = 1792, V_COUNT = 2048;
 constexpr int OFF_RING = 10 * BLK;      // 2 weight slots
 constexpr int SLOT = 32768;
 constexpr int OFF_BAR = OFF_RING + 2 * SLOT;
@@ -80,7 +86,18 @@ constexpr int TRACE_SLOTS = 64;
 __device__ __forceinline__ uint32_t swz(int row, int chunk) {
   return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
 }
-__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_epi() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
   const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -130,6 +147,13 @@ __device__ __forceinline__ float quad_add(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
+// keep bits of one group of eight elements, out of line: the Philox rounds are ~100 instructions, and inlining them
+// at every call site of the unrolled epilogues tripled the kernel's code size (instruction-cache misses were 13 % of
+// the stall samples of the first version)
+__device__ __noinline__ uint32_t keep8(uint64_t seed, uint64_t step, uint32_t site, uint64_t group, uint32_t thr) {
+  return keep_bits8(dropout_words(seed, step, site, group), thr);
+}
+
 // 32 values of one row: inverted dropout with the flat element index of the unfused kernels
 // (group = (row * width + col) / 8, eight 16-bit uniforms per Philox call).
 __device__ __forceinline__ void dropout32(float* v, uint64_t seed, uint64_t step, uint32_t site, uint64_t elem0,
@@ -144,11 +168,22 @@ __device__ __forceinline__ void dropout32(float* v, uint64_t seed, uint64_t step
 
 // softmax(q k^T / 8 + mask) v of one (sequence, head) on m16n8k16 fragments: rows [r0, r0 + S) of the swizzled
 // Q / K / V blocks (S <= 16; window rows beyond S belong to the next sequence: their keys get a -inf bias, their
-// values meet exact-zero probabilities, their query rows are not stored). The output overwrites the Q rows.
-__device__ __forceinline__ void attention_task(uint8_t* qblk, const uint8_t* kblk, const uint8_t* vblk, int r0, int S,
-                                               const uint8_t* mk, float drop_p, uint64_t seed, uint64_t step,
-                                               uint32_t site, uint64_t pbase, int lane) {
+// values meet exact-zero probabilities, their query rows are not stored).
+__device__ __forceinline__ void attention_compute(const uint8_t* qblk, const uint8_t* kblk, const uint8_t* vblk, int r0,
+                                                  int S, const uint8_t* mk, float drop_p, uint64_t seed, uint64_t step,
+                                                  uint32_t site, uint64_t pbase, int lane, uint32_t (&op)[8][2]) {
   constexpr float SCALE_LOG2E = 0.125f * 1.4426950408889634f;
+  // keep bits of the S x S probabilities (flat index pbase + i * S + j, eight per Philox call): lane l draws group
+  // g0 + l (and g0 + 32 + l when 33 groups are touched) FIRST — the bits do not depend on the scores, so the Philox
+  // rounds overlap the latency of the QK^T fragment chain; every thread later fetches its eight decisions by shuffle
+  const uint64_t g0 = pbase >> 3;
+  const int ngroups = static_cast<int>(((pbase + static_cast<uint64_t>(S) * S + 7) >> 3) - g0);
+  uint32_t bits0 = 0, bits1 = 0;
+  if (drop_p > 0.f) {
+    const uint32_t thr = dropout_thr(drop_p);
+    if (lane < ngroups) bits0 = keep8(seed, step, site, g0 + lane, thr);
+    if (lane + 32 < ngroups) bits1 = keep8(seed, step, site, g0 + 32 + lane, thr);
+  }
   float sc[2][4];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt)
@@ -197,14 +232,21 @@ __device__ __forceinline__ void attention_task(uint8_t* qblk, const uint8_t* kbl
   }
   if (drop_p > 0.f) {
     const float keep_scale = 1.f / (1.f - drop_p);
-    DropoutStream ds(seed, step, site, drop_p);
 #pragma unroll
     for (int rh = 0; rh < 2; ++rh) {
       const int i = g + rh * 8;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = (e >> 1) * 8 + 2 * t + (e & 1);
-        if (i < S && j < S) p[rh][e] *= ds.keep(pbase + static_cast<uint64_t>(i) * S + j) ? keep_scale : 0.f;
+        const bool live = i < S && j < S;
+        const uint64_t idx = pbase + static_cast<uint64_t>(live ? i * S + j : 0);
+        const int gl = static_cast<int>((idx >> 3) - g0);
+        uint32_t w = __shfl_sync(0xffffffffu, bits0, gl & 31);
+        if (ngroups > 32) {
+          const uint32_t w1 = __shfl_sync(0xffffffffu, bits1, gl & 31);
+          w = gl >= 32 ? w1 : w;
+        }
+        if (live) p[rh][e] *= ((w >> (idx & 7)) & 1u) ? keep_scale : 0.f;
       }
     }
   }
@@ -226,11 +268,19 @@ __device__ __forceinline__ void attention_task(uint8_t* qblk, const uint8_t* kbl
       mma16816(o[2 * np + 1], pa, b[2], b[3]);
     }
   }
-  __syncwarp();  // every lane has read its Q fragments: the output may overwrite the Q rows
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    if (g < S) *reinterpret_cast<uint32_t*>(qblk + swz(r0 + g, nt) + 4 * t) = pack2(o[nt][0], o[nt][1]);
-    if (g + 8 < S) *reinterpret_cast<uint32_t*>(qblk + swz(r0 + g + 8, nt) + 4 * t) = pack2(o[nt][2], o[nt][3]);
+    op[nt][0] = pack2(o[nt][0], o[nt][1]);
+    op[nt][1] = pack2(o[nt][2], o[nt][3]);
+  }
+}
+// the task's output rows over its Q rows (rows g / g + 8 of the window, columns nt * 8 + 2t)
+__device__ __forceinline__ void attention_write(uint8_t* qblk, int r0, int S, int lane, const uint32_t (&op)[8][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (g < S) *reinterpret_cast<uint32_t*>(qblk + swz(r0 + g, nt) + 4 * t) = op[nt][0];
+    if (g + 8 < S) *reinterpret_cast<uint32_t*>(qblk + swz(r0 + g + 8, nt) + 4 * t) = op[nt][1];
   }
 }
 
@@ -248,7 +298,11 @@ __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_base, uin
 __global__ void __launch_bounds__(THREADS, 1)
     enc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWin,
                          const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmW1,
-                         const __grid_constant__ CUtensorMap tmW2, const Args a) {
+                         const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmQKV,
+                         const __grid_constant__ CUtensorMap tmAO, const __grid_constant__ CUtensorMap tmZ1,
+                         const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmH,
+                         const __grid_constant__ CUtensorMap tmZ2, const __grid_constant__ CUtensorMap tmOut,
+                         const Args a) {
   extern __shared__ uint8_t el_smem_raw[];
   uint8_t* smem = el_smem_raw + ((1024 - (smem_u32(el_smem_raw) & 1023)) & 1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -261,10 +315,15 @@ __global__ void __launch_bounds__(THREADS, 1)
     tma_prefetch_desc(&tmWo);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmOut);
+    if (a.save_rows > 0) {
+      tma_prefetch_desc(&tmQKV); tma_prefetch_desc(&tmAO); tma_prefetch_desc(&tmZ1); tma_prefetch_desc(&tmX1);
+      tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmZ2);
+    }
     for (int i = 0; i < B_COUNT; ++i) {
       const bool by_warps = i == B_ACCEMPTY0 || i == B_ACCEMPTY1 || i == B_AOFULL || i == B_X1FULL || i == B_HAFULL ||
-                            i == B_HBFULL || i == B_TILEDONE;
-      mbar_init(&bars[i], by_warps ? 8 : 1);
+                            i == B_HBFULL;
+      mbar_init(&bars[i], by_warps ? EPI_WARPS : 1);
     }
     fence_mbar_init();
   }
@@ -394,10 +453,11 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else {
-    const int ew = warp - 2;      // 0..7
+    const int ew = warp - 2;      // 0..15
     const int q = warp & 3;       // TMEM lane quarter this warp may touch
-    const int hf = ew >> 2;       // which half of an accumulator's columns this warp drains
+    const int part = ew >> 2;     // which quarter of an accumulator's columns this warp drains
     const int row = q * 32 + lane;
+    const bool t0 = ew == 0 && lane == 0;  // issues (and tracks) every TMA store of the CTA
     const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const bool drop = a.drop_p > 0.f;
     uint64_t seed = 0, step = 0;
@@ -409,9 +469,10 @@ __global__ void __launch_bounds__(THREADS, 1)
       keep_scale = 1.f / (1.f - a.drop_p);
       thr = dropout_thr(a.drop_p);
     }
-    float* red = reinterpret_cast<float*>(smem + OFF_KV);  // [2 halves][128 rows] partial sums (LayerNorm phases)
+    float* red = reinterpret_cast<float*>(smem + OFF_RED);
+    const float* vec = reinterpret_cast<const float*>(smem + OFF_VEC);
     int it = 0;
-    long long* tr = (blockIdx.x == 0 && ew == 0 && lane == 0) ? a.trace : nullptr;
+    long long* tr = (blockIdx.x == 0 && t0) ? a.trace : nullptr;
     int ts = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       if (it > 0) tr = nullptr;
@@ -421,6 +482,9 @@ __global__ void __launch_bounds__(THREADS, 1)
       const bool valid = seq_l < a.spt && gseq < a.nb;
       const int64_t grow = static_cast<int64_t>(tile) * a.rows_pt + row;
       const bool save = valid && grow < a.save_rows;
+      const int trow = tile * a.rows_pt;                                   // first row of the tile (TMA coordinate)
+      const bool tile_save = t0 && static_cast<int64_t>(trow) < a.save_rows;  // (rows >= save_rows: clipped by the maps)
+      mbar_wait(&bars[B_XFULL], par);  // the X tile (the LayerNorm-1 residual is read from it) has landed
 
       // ------------------------------------------------------------ in-proj + attention, head by head
       for (int h = 0; h < NH; ++h) {
@@ -429,203 +493,279 @@ __global__ void __launch_bounds__(THREADS, 1)
         mbar_wait(&bars[B_ACCFULL0 + b], use & 1);
         EL_STAMP(2, ts++);
         tc_fence_after_sync();
-        bar_sync_epi();  // the previous head's attention has finished with the K / V staging tiles
-#pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
-          const int cc = hf * 3 + c;         // 0..5: 32-column chunk of [Q_h | K_h | V_h]
-          const int t = cc >> 1, sub = cc & 1;
-          float v[32];
-          tmem_ld_32x32(tm_lane + b * 256 + cc * 32, v);
-          tmem_ld_wait();
-          if (a.b_in) {
-            const float4* bp = reinterpret_cast<const float4*>(a.b_in + t * E + h * HD + sub * 32);
+        // this thread's 48 of the 192 columns [Q_h | K_h | V_h]: three 16-column groups
+        float v[48];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bv = __ldg(bp + j);
-              v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
-            }
-          }
-          uint8_t* blk = t == 0 ? smem + OFF_BUF1 + h * BLK : smem + OFF_KV + (t - 1) * BLK;
-          bf16* gdst = a.qkv + grow * (3 * E) + t * E + h * HD + sub * 32;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 pk = pack8(v + 8 * j);
-            *reinterpret_cast<uint4*>(blk + swz(row, sub * 4 + j)) = pk;
-            if (save) *reinterpret_cast<uint4*>(gdst + 8 * j) = pk;
-          }
-        }
+        for (int c = 0; c < 3; ++c) tmem_ld_32x16(tm_lane + b * 256 + part * 48 + c * 16, v + 16 * c);
+        tmem_ld_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_ACCEMPTY0 + b]);
-        bar_sync_epi();  // Q / K / V tiles of this head are complete
+        // (the K / V staging tiles are free: every task of the previous head passed its second barrier)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int col = part * 48 + c * 16;  // 0..191
+          const int t = col >> 6, hc = col & 63;
+          if (a.b_in) {
+            const float4* bp = reinterpret_cast<const float4*>(a.b_in + t * E + h * HD + hc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 bv = __ldg(bp + j);
+              v[16 * c + 4 * j] += bv.x; v[16 * c + 4 * j + 1] += bv.y;
+              v[16 * c + 4 * j + 2] += bv.z; v[16 * c + 4 * j + 3] += bv.w;
+            }
+          }
+          uint8_t* blk = t == 0 ? smem + OFF_BUF1 + h * BLK : smem + OFF_KV + (t - 1) * BLK;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) *reinterpret_cast<uint4*>(blk + swz(row, (hc >> 3) + j)) = pack8(v + 16 * c + 8 * j);
+        }
+        fence_proxy_async_smem();  // (the staged tiles are also the source of the q / k / v TMA stores)
+        bar_sync_epi();            // Q / K / V tiles of this head are complete
         EL_STAMP(2, ts++);
-        for (int sl = ew; sl < a.spt; sl += 8) {
+        if (tile_save) {  // q, k, v of this head -> HBM for the backward, straight from the staged tiles
+          tma_store_2d(&tmQKV, smem + OFF_BUF1 + h * BLK, h * HD, trow);
+          tma_store_2d(&tmQKV, smem + OFF_KV, E + h * HD, trow);
+          tma_store_2d(&tmQKV, smem + OFF_KV + BLK, 2 * E + h * HD, trow);
+          tma_store_commit();
+        }
+        // first round of tasks: outputs stay in registers until the Q tile has been read by its TMA store
+        uint32_t op[8][2];
+        const int sl0 = ew;
+        const int64_t gs0 = static_cast<int64_t>(tile) * a.spt + sl0;
+        const bool task0 = sl0 < a.spt && gs0 < a.nb;
+        if (task0) {
+          const uint8_t* mk = a.mask ? a.mask + (gs0 % a.mask_mod) * a.S : nullptr;
+          attention_compute(smem + OFF_BUF1 + h * BLK, smem + OFF_KV, smem + OFF_KV + BLK, sl0 * a.S, a.S, mk, a.drop_p,
+                            seed, step, a.site, (static_cast<uint64_t>(gs0) * NH + h) * a.S * a.S, lane, op);
+        }
+        if (tile_save) tma_store_wait_read<0>();
+        bar_sync_epi();
+        if (task0) attention_write(smem + OFF_BUF1 + h * BLK, sl0 * a.S, a.S, lane, op);
+        for (int sl = ew + EPI_WARPS; sl < a.spt; sl += EPI_WARPS) {  // (more than 16 sequences per tile: S <= 7)
           const int64_t gs = static_cast<int64_t>(tile) * a.spt + sl;
           if (gs >= a.nb) break;
           const uint8_t* mk = a.mask ? a.mask + (gs % a.mask_mod) * a.S : nullptr;
-          attention_task(smem + OFF_BUF1 + h * BLK, smem + OFF_KV, smem + OFF_KV + BLK, sl * a.S, a.S, mk, a.drop_p,
-                         seed, step, a.site, (static_cast<uint64_t>(gs) * NH + h) * a.S * a.S, lane);
+          attention_compute(smem + OFF_BUF1 + h * BLK, smem + OFF_KV, smem + OFF_KV + BLK, sl * a.S, a.S, mk, a.drop_p,
+                            seed, step, a.site, (static_cast<uint64_t>(gs) * NH + h) * a.S * a.S, lane, op);
+          __syncwarp();
+          attention_write(smem + OFF_BUF1 + h * BLK, sl * a.S, a.S, lane, op);
         }
+        if (a.spt > EPI_WARPS) bar_sync_epi();  // later rounds still read K / V: the next head must not restage yet
       }
       EL_STAMP(2, ts++);
       fence_proxy_async_smem();  // attention outputs (generic-proxy stores) -> visible to the MMA's operand reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_AOFULL]);
+      bar_sync_epi();  // every attention task is done: the K / V staging area is free, the attention output complete
       // the attention output is also an input of the backward (out-proj weight gradient, softmax delta)
-      bar_sync_epi();
-      if (save) {
-#pragma unroll 1
-        for (int j = 0; j < 16; ++j) {
-          const int col8 = hf * 16 + j;  // 16-byte chunk of the row
-          *reinterpret_cast<uint4*>(a.ao + grow * E + col8 * 8) =
-              *reinterpret_cast<const uint4*>(smem + OFF_BUF1 + (col8 >> 3) * BLK + swz(row, col8 & 7));
+      if (tile_save) {
+        for (int kb = 0; kb < 4; ++kb) tma_store_2d(&tmAO, smem + OFF_BUF1 + kb * BLK, kb * 64, trow);
+        tma_store_commit();
+      }
+      // per-column vectors of the remaining epilogues -> shared memory (broadcast reads instead of global loads)
+      {
+        float* vw = reinterpret_cast<float*>(smem + OFF_VEC);
+        for (int i = threadIdx.x - 64; i < V_COUNT / 4; i += EPI_THREADS) {
+          const int o = i * 4;
+          const float* src;
+          int off;
+          float fill = 0.f;
+          if (o < V_G1) { src = a.b_out; off = o - V_BOUT; }
+          else if (o < V_BE1) { src = a.g1; off = o - V_G1; fill = 1.f; }
+          else if (o < V_BFF1) { src = a.be1; off = o - V_BE1; }
+          else if (o < V_BFF2) { src = a.b_ff1; off = o - V_BFF1; }
+          else if (o < V_G2) { src = a.b_ff2; off = o - V_BFF2; }
+          else if (o < V_BE2) { src = a.g2; off = o - V_G2; fill = 1.f; }
+          else { src = a.be2; off = o - V_BE2; }
+          const float4 val = src ? __ldg(reinterpret_cast<const float4*>(src + off)) : make_float4(fill, fill, fill, fill);
+          *reinterpret_cast<float4*>(vw + o) = val;
         }
       }
+      if (tile_save) tma_store_wait_read<0>();  // the attention output has left BUF1: LayerNorm 1 parks z there
+      bar_sync_epi();
 
-      // ------------------------------------------------------------ out-proj epilogue: x1 = LN1(x + drop(sa))
-      // and, further down with the same code, out = LN2(x1 + drop(ff)); thread = (row, 128 columns)
-      // Sweep 1 (per 32-column chunk): accumulator + bias -> dropout -> + residual = z; fp32 sum / sum of squares;
-      // z kept as packed bf16 (what the backward reads back as the pre-LayerNorm tensor). Sweep 2 normalises the
-      // stored z with the fp32 statistics of the unrounded values.
-      uint4 zq[16];
-      auto layer_norm_epilogue = [&](uint32_t tm_acc, const float* bias, uint32_t site, bool res_from_smem,
-                                     const float* gamma, const float* beta, bf16* zdst, bf16* ydst, bool ysave,
-                                     float* mean_out, float* rstd_out, bool to_smem) {
+      // ------------------------------------------------------------ LayerNorm epilogues. Thread = (row, 64 columns =
+      // block `part`). Sweep 1: accumulator + bias -> dropout -> + residual (read from BUF0: X for LN1, x1 for LN2) = z;
+      // fp32 sum / sum of squares; bf16 z into BUF1 (free in both phases: its last MMA reader and its last TMA store are
+      // done), from where one TMA store takes it to HBM. Sweep 2 normalises the stored z with the statistics of the
+      // unrounded values into BUF0: x1 (the next MMA's A operand) or the layer output.
+      // (the dropout keep bits of a phase are drawn BEFORE waiting for its accumulator: the epilogue warps idle there
+      // while the MMA waits for its weight stages, and the Philox rounds are a third of the epilogue's instructions)
+      auto draw_masks = [&](uint32_t site, uint64_t elem0, uint32_t (&km)[2]) {
+        km[0] = km[1] = 0;
+        if (drop) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            km[j >> 2] |= keep8(seed, step, site, (elem0 >> 3) + j, thr) << (8 * (j & 3));
+        }
+      };
+      auto layer_norm_epilogue = [&](uint32_t tm_acc, int vb, const uint32_t (&km)[2], int vg, int vbe,
+                                     const CUtensorMap* tmZ, float* mean_out, float* rstd_out) {
+        uint8_t* rblk = smem + OFF_BUF0 + part * BLK;
+        uint8_t* zblk = smem + OFF_BUF1 + part * BLK;
         float s = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int col0 = hf * 128 + c * 32;
+#pragma unroll 1
+        for (int hs = 0; hs < 2; ++hs) {  // 32 columns at a time: half the live registers
           float v[32];
-          tmem_ld_32x32(tm_acc + col0, v);
+          tmem_ld_32x32(tm_acc + part * 64 + hs * 32, v);
           tmem_ld_wait();
-          if (bias) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);
-              v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
-            }
-          }
-          if (drop) dropout32(v, seed, step, site, static_cast<uint64_t>(grow) * E + col0, thr, keep_scale);
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = hs * 4 + jj;
+            const int col = part * 64 + 8 * j;
+            const float4 b0 = *reinterpret_cast<const float4*>(vec + vb + col);
+            const float4 b1 = *reinterpret_cast<const float4*>(vec + vb + col + 4);
+            float* w = v + 8 * jj;
+            w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w;
+            w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+            if (drop) {
+              const uint32_t kb = km[j >> 2] >> (8 * (j & 3));
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 r = make_uint4(0, 0, 0, 0);
-            if (res_from_smem) {
-              const int col8 = (col0 >> 3) + j;
-              r = *reinterpret_cast<const uint4*>(smem + OFF_BUF0 + (col8 >> 3) * BLK + swz(row, col8 & 7));
-            } else if (valid) {
-              r = __ldg(reinterpret_cast<const uint4*>(a.x + grow * E + col0) + j);
+              for (int t = 0; t < 8; ++t) w[t] = ((kb >> t) & 1u) ? w[t] * keep_scale : 0.f;
             }
             float rf[8];
-            unpack8(r, rf);
+            unpack8(*reinterpret_cast<const uint4*>(rblk + swz(row, j)), rf);
+            float sa = 0.f, sb = 0.f, qa = 0.f, qb = 0.f;  // (two short chains instead of one 64-long dependency)
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const float z = v[8 * j + t] + rf[t];
-              v[8 * j + t] = z;
-              s += z;
-              s2 = fmaf(z, z, s2);
+            for (int t = 0; t < 8; t += 2) {
+              w[t] += rf[t];
+              w[t + 1] += rf[t + 1];
+              sa += w[t];
+              sb += w[t + 1];
+              qa = fmaf(w[t], w[t], qa);
+              qb = fmaf(w[t + 1], w[t + 1], qb);
             }
-            zq[4 * c + j] = pack8(v + 8 * j);
+            s += sa + sb;
+            s2 += qa + qb;
+            *reinterpret_cast<uint4*>(zblk + swz(row, j)) = pack8(w);
           }
         }
-        red[hf * 128 + row] = s;
-        red[256 + hf * 128 + row] = s2;
+        red[part * 128 + row] = s;
+        red[512 + part * 128 + row] = s2;
+        EL_STAMP(2, ts++);
+        fence_proxy_async_smem();
+        EL_STAMP(2, ts++);
         bar_sync_epi();
-        const float mu = (red[row] + red[128 + row]) * (1.f / E);
-        const float var = fmaxf((red[256 + row] + red[384 + row]) * (1.f / E) - mu * mu, 0.f);
-        const float rs = rsqrtf(var + a.eps);
-        bar_sync_epi();  // (the partial sums may be overwritten by the next LayerNorm / the next tile's staging)
-        if (hf == 0 && save) {
+        EL_STAMP(2, ts++);
+        if (tile_save) {
+          for (int kb = 0; kb < 4; ++kb) tma_store_2d(tmZ, smem + OFF_BUF1 + kb * BLK, kb * 64, trow);
+          tma_store_commit();
+        }
+        const float mu = (red[row] + red[128 + row] + red[256 + row] + red[384 + row]) * (1.f / E);
+        const float ex2 = (red[512 + row] + red[640 + row] + red[768 + row] + red[896 + row]) * (1.f / E);
+        const float rs = rsqrtf(fmaxf(ex2 - mu * mu, 0.f) + a.eps);
+        if (part == 0 && save) {
           mean_out[grow] = mu;
           rstd_out[grow] = rs;
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int col0 = hf * 128 + c * 32;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (save) *reinterpret_cast<uint4*>(zdst + grow * E + col0 + 8 * j) = zq[4 * c + j];
-            float zz[8], y[8];
-            unpack8(zq[4 * c + j], zz);
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col0 + 8 * j));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col0 + 8 * j) + 1);
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (beta) {
-              b0 = __ldg(reinterpret_cast<const float4*>(beta + col0 + 8 * j));
-              b1 = __ldg(reinterpret_cast<const float4*>(beta + col0 + 8 * j) + 1);
-            }
-            y[0] = (zz[0] - mu) * rs * g0.x + b0.x; y[1] = (zz[1] - mu) * rs * g0.y + b0.y;
-            y[2] = (zz[2] - mu) * rs * g0.z + b0.z; y[3] = (zz[3] - mu) * rs * g0.w + b0.w;
-            y[4] = (zz[4] - mu) * rs * g1.x + b1.x; y[5] = (zz[5] - mu) * rs * g1.y + b1.y;
-            y[6] = (zz[6] - mu) * rs * g1.z + b1.z; y[7] = (zz[7] - mu) * rs * g1.w + b1.w;
-            const uint4 pk = pack8(y);
-            const int col8 = (col0 >> 3) + j;
-            if (to_smem) *reinterpret_cast<uint4*>(smem + OFF_BUF0 + (col8 >> 3) * BLK + swz(row, col8 & 7)) = pk;
-            if (ysave) *reinterpret_cast<uint4*>(ydst + grow * E + col0 + 8 * j) = pk;
-          }
+        for (int j = 0; j < 8; ++j) {
+          const int col = part * 64 + 8 * j;
+          float zz[8], y[8];
+          unpack8(*reinterpret_cast<const uint4*>(zblk + swz(row, j)), zz);
+          const float4 g0 = *reinterpret_cast<const float4*>(vec + vg + col);
+          const float4 g1 = *reinterpret_cast<const float4*>(vec + vg + col + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(vec + vbe + col);
+          const float4 b1 = *reinterpret_cast<const float4*>(vec + vbe + col + 4);
+          y[0] = (zz[0] - mu) * rs * g0.x + b0.x; y[1] = (zz[1] - mu) * rs * g0.y + b0.y;
+          y[2] = (zz[2] - mu) * rs * g0.z + b0.z; y[3] = (zz[3] - mu) * rs * g0.w + b0.w;
+          y[4] = (zz[4] - mu) * rs * g1.x + b1.x; y[5] = (zz[5] - mu) * rs * g1.y + b1.y;
+          y[6] = (zz[6] - mu) * rs * g1.z + b1.z; y[7] = (zz[7] - mu) * rs * g1.w + b1.w;
+          *reinterpret_cast<uint4*>(rblk + swz(row, j)) = pack8(y);
         }
+        EL_STAMP(2, ts++);
+        fence_proxy_async_smem();
+        EL_STAMP(2, ts++);
       };
+      uint32_t km[2];
+      draw_masks(a.site + 1, static_cast<uint64_t>(grow) * E + part * 64, km);
       EL_STAMP(2, ts++);
       mbar_wait(&bars[B_ACC2FULL], par);
       EL_STAMP(2, ts++);
       tc_fence_after_sync();
-      layer_norm_epilogue(tm_lane, a.b_out, a.site + 1, false, a.g1, a.be1, a.z1, a.x1, save, a.mean1, a.rstd1, true);
+      layer_norm_epilogue(tm_lane, V_BOUT, km, V_G1, V_BE1, &tmZ1, a.mean1, a.rstd1);
       tc_fence_before_sync();
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_X1FULL]);
+      if (tile_save) {  // x1 -> HBM once every warp has written its part (it stays in BUF0 until LayerNorm 2)
+        mbar_wait(&bars[B_X1FULL], par);
+        for (int kb = 0; kb < 4; ++kb) tma_store_2d(&tmX1, smem + OFF_BUF0 + kb * BLK, kb * 64, trow);
+        tma_store_commit();
+      }
       EL_STAMP(2, ts++);
 
       // ------------------------------------------------------------ ffn1 epilogues: h = drop(relu(x1 W1^T + b1))
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
+        draw_masks(a.site + 2, static_cast<uint64_t>(grow) * F + half * 256 + part * 64, km);
         mbar_wait(&bars[half == 0 ? B_F1AFULL : B_F1BFULL], par);
-        if (half == 1) mbar_wait(&bars[B_F2ADONE], par);  // the first half's ffn2 MMAs have finished reading BUF1
-        EL_STAMP(2, ts++);
         tc_fence_after_sync();
         const uint32_t tm_acc = tm_lane + (half == 0 ? 256 : 0);
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int col0 = hf * 128 + c * 32;  // within this half
-          const int hcol = half * 256 + col0;  // hidden unit
-          float w[32];
-          tmem_ld_32x32(tm_acc + col0, w);
+        uint8_t* myblk = smem + OFF_BUF1 + part * BLK;
+        uint4 pk[8];
+#pragma unroll
+        for (int hs = 0; hs < 2; ++hs) {
+          float v[32];
+          tmem_ld_32x32(tm_acc + part * 64 + hs * 32, v);
           tmem_ld_wait();
-          if (a.b_ff1) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(a.b_ff1 + hcol) + j);
-              w[4 * j] += bv.x; w[4 * j + 1] += bv.y; w[4 * j + 2] += bv.z; w[4 * j + 3] += bv.w;
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = hs * 4 + jj;
+            const int hcol = half * 256 + part * 64 + 8 * j;  // hidden unit
+            const float4 b0 = *reinterpret_cast<const float4*>(vec + V_BFF1 + hcol);
+            const float4 b1 = *reinterpret_cast<const float4*>(vec + V_BFF1 + hcol + 4);
+            float* w = v + 8 * jj;
+            w[0] = fmaxf(w[0] + b0.x, 0.f); w[1] = fmaxf(w[1] + b0.y, 0.f);
+            w[2] = fmaxf(w[2] + b0.z, 0.f); w[3] = fmaxf(w[3] + b0.w, 0.f);
+            w[4] = fmaxf(w[4] + b1.x, 0.f); w[5] = fmaxf(w[5] + b1.y, 0.f);
+            w[6] = fmaxf(w[6] + b1.z, 0.f); w[7] = fmaxf(w[7] + b1.w, 0.f);
+            if (drop) {
+              const uint32_t kb = km[j >> 2] >> (8 * (j & 3));
+#pragma unroll
+              for (int t = 0; t < 8; ++t) w[t] = ((kb >> t) & 1u) ? w[t] * keep_scale : 0.f;
             }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) w[j] = fmaxf(w[j], 0.f);
-          if (drop) dropout32(w, seed, step, a.site + 2, static_cast<uint64_t>(grow) * F + hcol, thr, keep_scale);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 pk = pack8(w + 8 * j);
-            const int col8 = (col0 >> 3) + j;
-            *reinterpret_cast<uint4*>(smem + OFF_BUF1 + (col8 >> 3) * BLK + swz(row, col8 & 7)) = pk;
-            if (save) *reinterpret_cast<uint4*>(a.h + grow * F + hcol + 8 * j) = pk;
+            pk[j] = pack8(w);
           }
         }
+        EL_STAMP(2, ts++);
+        // BUF1 must be free: (first half) LayerNorm 1's z has been stored from it; (second half) the first half's ffn2
+        // MMAs and its TMA store have finished reading it
+        if (half == 1) mbar_wait(&bars[B_F2ADONE], par);
+        if (tile_save) tma_store_wait_read<0>();
+        bar_sync_epi();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(myblk + swz(row, j)) = pk[j];
         tc_fence_before_sync();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[half == 0 ? B_HAFULL : B_HBFULL]);
+        if (tile_save) {  // this half of the hidden activations -> HBM
+          mbar_wait(&bars[half == 0 ? B_HAFULL : B_HBFULL], par);
+          for (int kb = 0; kb < 4; ++kb) tma_store_2d(&tmH, smem + OFF_BUF1 + kb * BLK, half * 256 + kb * 64, trow);
+          tma_store_commit();
+        }
         EL_STAMP(2, ts++);
       }
 
       // ------------------------------------------------------------ ffn2 epilogue: out = LN2(x1 + drop(ff))
+      draw_masks(a.site + 3, static_cast<uint64_t>(grow) * E + part * 64, km);
       mbar_wait(&bars[B_OUTFULL], par);
       EL_STAMP(2, ts++);
       tc_fence_after_sync();
-      layer_norm_epilogue(tm_lane + 256, a.b_ff2, a.site + 3, true, a.g2, a.be2, a.z2, a.out, valid, a.mean2, a.rstd2,
-                          false);
+      if (tile_save) tma_store_wait_read<0>();  // the hidden activations have left BUF1: LayerNorm 2 parks z there
+      bar_sync_epi();
+      layer_norm_epilogue(tm_lane + 256, V_BFF2, km, V_G2, V_BE2, &tmZ2, a.mean2, a.rstd2);
       tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_TILEDONE]);
+      bar_sync_epi();  // the layer output is complete in BUF0
+      if (t0) {
+        for (int kb = 0; kb < 4; ++kb) tma_store_2d(&tmOut, smem + OFF_BUF0 + kb * BLK, kb * 64, trow);
+        tma_store_commit();
+        tma_store_wait_read<0>();  // (also the hidden activations' store out of BUF1): the next tile may overwrite both
+        mbar_arrive(&bars[B_TILEDONE]);
+      }
       EL_STAMP(2, ts++);
     }
+    if (t0) tma_store_wait_all<0>();
   }
 
   tc_fence_before_sync();
@@ -664,12 +804,22 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
   a.out = static_cast<bf16*>(p.out);
   a.mean1 = p.mean1; a.rstd1 = p.rstd1; a.mean2 = p.mean2; a.rstd2 = p.rstd2;
   a.trace = g_el_trace;
-  CUtensorMap mX, mWin, mWo, mW1, mW2;
+  CUtensorMap mX, mWin, mWo, mW1, mW2, mQKV, mAO, mZ1, mX1, mH, mZ2, mOut;
   GG_TRY_RC(encode_tma_map(&mX, p.x, E, a.rows_total, E, a.rows_pt, false));
   GG_TRY_RC(encode_tma_map(&mWin, p.w_in, E, 3 * E, p.ld_in, 64, false));
   GG_TRY_RC(encode_tma_map(&mWo, p.w_out, E, E, p.ld_out, 256, false));
   GG_TRY_RC(encode_tma_map(&mW1, p.w_ff1, E, F, p.ld_ff1, 256, false));
   GG_TRY_RC(encode_tma_map(&mW2, p.w_ff2, F, E, p.ld_ff2, 256, false));
+  GG_TRY_RC(encode_tma_map(&mOut, p.out, E, a.rows_total, E, a.rows_pt, false));
+  mQKV = mAO = mZ1 = mX1 = mH = mZ2 = mX;  // (unused without a save range)
+  if (a.save_rows > 0) {  // rows >= save_rows are clipped by the maps' extents
+    GG_TRY_RC(encode_tma_map(&mQKV, p.qkv, 3 * E, a.save_rows, 3 * E, a.rows_pt, false));
+    GG_TRY_RC(encode_tma_map(&mAO, p.ao, E, a.save_rows, E, a.rows_pt, false));
+    GG_TRY_RC(encode_tma_map(&mZ1, p.z1, E, a.save_rows, E, a.rows_pt, false));
+    GG_TRY_RC(encode_tma_map(&mX1, p.x1, E, a.save_rows, E, a.rows_pt, false));
+    GG_TRY_RC(encode_tma_map(&mH, p.h, F, a.save_rows, F, a.rows_pt, false));
+    GG_TRY_RC(encode_tma_map(&mZ2, p.z2, E, a.save_rows, E, a.rows_pt, false));
+  }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -683,7 +833,7 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
     GG_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
-  launch_k(enc_layer_fwd_kernel, static_cast<unsigned>(grid), THREADS, SMEM_BYTES, st, mX, mWin, mWo, mW1, mW2, a);
+  launch_k(enc_layer_fwd_kernel, static_cast<unsigned>(grid), THREADS, SMEM_BYTES, st, mX, mWin, mWo, mW1, mW2, mQKV, mAO, mZ1, mX1, mH, mZ2, mOut, a);
   GG_LAUNCH_CHECK();
   return GG_OK;
 }

