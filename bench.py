@@ -375,6 +375,8 @@ def main():
     t.unique_graphs = False
     ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
     _lib.check(L.gg_gemm_profile_end(C.byref(ms), C.byref(fl), C.byref(nl)))
+    el_ms, el_fl, el_by, el_n = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
+    _lib.check(L.gg_enc_layer_profile(C.byref(el_ms), C.byref(el_fl), C.byref(el_by), C.byref(el_n)))
     if args.gemm_csv and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.gemm_csv)), exist_ok=True)
         _lib.check(L.gg_gemm_profile_dump(args.gemm_csv.encode()))
@@ -452,6 +454,25 @@ def main():
         roofline = dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], **common)
     else:
         roofline = dict(bound="tensor", achieved=tf, peak=pk["tflops"], unit="TFLOP/s", frac=tf / pk["tflops"], **common)
+    # the fused encoder-layer kernel (enc_layer.cu: in-proj + attention + out-proj + LN + ffn + LN of one layer pass as one
+    # tcgen05 launch) — the other tensor-core kernel of the step, same event-pair method, its own lower bounds
+    if el_n.value > 0 and el_ms.value > 0:
+        es = el_ms.value * 1e-3
+        e_tf, e_gbs = el_fl.value / es / 1e12, el_by.value / es / 1e9
+        e_t_tensor, e_t_hbm = el_fl.value / (pk["tflops"] * 1e12), el_by.value / (pk["hbm"] * 1e9)
+        enc = dict(kernel="enc_layer_fwd_kernel (tcgen05 + TMEM + TMA, one launch per encoder layer pass)",
+                   launches_per_step=int(el_n.value), ms_per_step=el_ms.value, flops_per_step=el_fl.value,
+                   bytes_per_step=el_by.value, tensor_tflops=e_tf, tensor_frac=e_tf / pk["tflops"], hbm_gbs=e_gbs,
+                   hbm_frac=e_gbs / pk["hbm"], bound="hbm" if e_t_hbm >= e_t_tensor else "tensor",
+                   frac=max(e_tf / pk["tflops"], e_gbs / pk["hbm"]), share_of_profiled_call=el_ms.value / profiled_call_ms)
+        roofline["enc_layer"] = enc
+        # both tensor-core kernels together: the figure that describes the step's tcgen05 work as a whole
+        tot_s = secs + es
+        roofline["all_tcgen05"] = dict(launches=int(nl.value + el_n.value), ms=ms.value + el_ms.value,
+                                       tensor_tflops=(fl.value + el_fl.value) / tot_s / 1e12,
+                                       tensor_frac=(fl.value + el_fl.value) / tot_s / 1e12 / pk["tflops"],
+                                       hbm_gbs=(by + el_by.value) / tot_s / 1e9,
+                                       hbm_frac=(by + el_by.value) / tot_s / 1e9 / pk["hbm"])
 
     # ---- end-to-end through the public API with pinned host tensors
     e2e = None

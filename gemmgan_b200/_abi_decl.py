@@ -134,6 +134,8 @@ def declare(L: C.CDLL) -> None:
     L.gg_colsum_group.argtypes = [C.POINTER(ColsumItem), i32, vp, i64, vp]
     L.gg_encoder_layer_fwd.argtypes = [C.POINTER(EncLayerParams), vp]
     L.gg_enc_layer_set_trace.argtypes = [vp]
+    L.gg_enc_layer_profile.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_longlong)]
     declare_evalmetrics(L)
     L.gg_launch_count.argtypes = [i32]
     L.gg_launch_count.restype = C.c_longlong
@@ -157,5 +159,5 @@ EXPORTS = [
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",
     "gg_pairwise_distance", "gg_row_kth_smallest", "gg_row_membership", "gg_col_hits", "gg_standardize_columns",
     "gg_gene_correlation", "gg_gamma_moments_workspace_bytes", "gg_gamma_moments",
-    "gg_encoder_layer_fwd", "gg_enc_layer_set_trace", "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
+    "gg_encoder_layer_fwd", "gg_enc_layer_set_trace", "gg_enc_layer_profile", "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

@@ -38,6 +38,8 @@ namespace gg {
 
 int encode_tma_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_outer,
                    bool f32);
+int prof_aux_begin(double flops, double bytes, cudaStream_t stream);
+int prof_aux_end(cudaStream_t stream);
 
 namespace el {
 
@@ -833,8 +835,16 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
     GG_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+  {  // live profiler (bench.py): algorithmic work of this launch. FLOPs: the four projections + the attention core;
+     // bytes: X and the weights read once, the output and (rows < save_rows) the backward tensors written once
+    const double rows = static_cast<double>(a.rows_total), srows = static_cast<double>(a.save_rows);
+    const double fl = rows * (2.0 * E * 3 * E + 2.0 * E * E + 4.0 * E * F + 4.0 * p.S * E);
+    const double by = rows * E * 2 * 2 + (3.0 * E * E + E * E + 2.0 * E * F) * 2 + srows * (3 * E + 4 * E + F) * 2 + srows * 16;
+    GG_TRY_RC(prof_aux_begin(fl, by, st));
+  }
   launch_k(enc_layer_fwd_kernel, static_cast<unsigned>(grid), THREADS, SMEM_BYTES, st, mX, mWin, mWo, mW1, mW2, mQKV, mAO, mZ1, mX1, mH, mZ2, mOut, a);
   GG_LAUNCH_CHECK();
+  GG_TRY_RC(prof_aux_end(st));
   return GG_OK;
 }
 

@@ -728,6 +728,14 @@ struct GemmProfile {
   long long launches = 0;
 };
 static GemmProfile g_prof;
+// second record set for the fused encoder-layer kernel (same begin / end switch): bench.py reports both kernels
+struct AuxProfile {
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  double flops = 0.0, bytes = 0.0;
+  long long launches = 0;
+};
+static AuxProfile g_aux;
 struct StampRecord {
   double flops, bytes;
 };
@@ -746,6 +754,30 @@ static cudaError_t prof_record(cudaEvent_t ev, cudaStream_t stream) {
   if (rc != cudaSuccess) return rc;
   return cs == cudaStreamCaptureStatusActive ? cudaEventRecordWithFlags(ev, stream, cudaEventRecordExternal)
                                              : cudaEventRecord(ev, stream);
+}
+
+// Event pair around a launch of another tensor-core kernel of the library while the live profiler is on:
+// prof_aux_begin before the launch (records its algorithmic flops / bytes), prof_aux_end after it.
+int prof_aux_begin(double flops, double bytes, cudaStream_t stream) {
+  if (!g_prof.on) return GG_OK;
+  if (g_aux.used + 2 > g_aux.ev.size()) {
+    cudaEvent_t a, b;
+    GG_CUDA_CHECK(cudaEventCreate(&a));
+    GG_CUDA_CHECK(cudaEventCreate(&b));
+    g_aux.ev.push_back(a);
+    g_aux.ev.push_back(b);
+  }
+  g_aux.flops += flops;
+  g_aux.bytes += bytes;
+  g_aux.launches += 1;
+  GG_CUDA_CHECK(prof_record(g_aux.ev[g_aux.used], stream));
+  return GG_OK;
+}
+int prof_aux_end(cudaStream_t stream) {
+  if (!g_prof.on) return GG_OK;
+  GG_CUDA_CHECK(prof_record(g_aux.ev[g_aux.used + 1], stream));
+  g_aux.used += 2;
+  return GG_OK;
 }
 
 template <int BN, int STAGES, int EPIW, bool PAIR = false>
@@ -1003,6 +1035,24 @@ extern "C" int gg_gemm_profile_begin(void) {
   gg::g_prof.flops = 0.0;
   gg::g_prof.bytes = 0.0;
   gg::g_prof.launches = 0;
+  gg::g_aux.used = 0;
+  gg::g_aux.flops = gg::g_aux.bytes = 0.0;
+  gg::g_aux.launches = 0;
+  return GG_OK;
+}
+// The fused encoder-layer launches of the last profiled region (call after gg_gemm_profile_end).
+extern "C" int gg_enc_layer_profile(double* ms, double* flops, double* bytes, long long* launches) {
+  using namespace gg;
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < g_aux.used; i += 2) {
+    float t = 0.f;
+    GG_CUDA_CHECK(cudaEventElapsedTime(&t, g_aux.ev[i], g_aux.ev[i + 1]));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (flops) *flops = g_aux.flops;
+  if (bytes) *bytes = g_aux.bytes;
+  if (launches) *launches = g_aux.launches;
   return GG_OK;
 }
 // Synchronises the device and returns the summed duration (ms), FLOPs (2*M*N*K) and count of the

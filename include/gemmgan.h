@@ -348,6 +348,9 @@ int gg_encoder_layer_fwd(const gg_enc_layer_params* p, void* stream);
 /* Diagnostics: CTA 0 of every following gg_encoder_layer_fwd launch stamps clock64() per pipeline role for its first
  * tile into device_buf (3 x 64 int64: TMA producer / MMA issuer / first epilogue warp); NULL = off. */
 int gg_enc_layer_set_trace(void* device_buf);
+/* Live profile (bench.py): summed CUDA-event duration, algorithmic FLOPs / bytes and count of the fused encoder-layer
+ * launches between gg_gemm_profile_begin and gg_gemm_profile_end (call after the latter). */
+int gg_enc_layer_profile(double* ms, double* flops, double* bytes, long long* launches);
 
 /* Grouped weight gradients: out_i[M_i, N_i] (fp32, pitch ld) = dY_i^T X_i for up to 32 problems in ONE launch
  * (autograd's grad_output.t().mm(input) of every Linear of one backward pass, :412 / :455). dY_i is stored

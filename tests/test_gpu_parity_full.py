@@ -301,3 +301,39 @@ def test_dropout_on_loss_curves_inside_the_oracle_spread():
     assert np.all(np.abs(got.mean(0) - mean.mean(0)) <= 4.0 * sd.mean(0) / np.sqrt(n_seeds) + TOL * scale + 5e-3)
     # and dropout really is on: the dropout-free oracle sits measurably elsewhere or the spread is non-zero
     assert sd.mean() > 0
+
+
+@pytest.mark.parametrize("variant,dropout", [("paper", 0.1), ("paper", 0.0), ("film", 0.1)])
+def test_fused_encoder_layer_engine_matches_the_seven_launch_path(variant, dropout, monkeypatch):
+    """The engine with the fused encoder-layer kernel (enc_layer.cu, default) against the same engine running every
+    layer as seven launches (GEMMGAN_FUSED_LAYER=0), DROPOUT ON: both draw the same Philox masks (same seed, step,
+    site and element indices), so the critic step must agree to bf16 rounding — conditioning vectors of all three
+    replicas, scores, GP, losses and every gradient."""
+    cfg = dict(MID, B=48)
+    B, G, L = cfg["B"], cfg["G"], cfg["latent"]
+    x, cond = restated.synthetic_batch(variant, B, G, cfg["P"], cfg["T"], seed=5, ragged=True)
+    z, alpha, z2 = _noise(B, L, 99)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("GEMMGAN_FUSED_LAYER", fused)
+        _, t = build_pair(variant, cfg, "adam", dropout=dropout)
+        dev = t.device
+        args = [c.to(dev) for c in ref_order(variant, x, cond)]
+        eng = t._stage(x.to(dev), *args)
+        eng.disc_grads(z.to(dev), alpha.to(dev), training=True)
+        torch.cuda.synchronize()
+        rec = dict(cond=eng.buffer("cond_disc").float().clone(), score=eng.buffer("score")[:, 0].clone(),
+                   norms=eng.buffer("gp_norms")[:, 0].clone(), stats=eng.stats.clone(), dg=t._flat_disc.grads.clone())
+        eng.gen_grads(z2.to(dev), training=True)
+        torch.cuda.synchronize()
+        rec["gg"] = t._flat_gen.grads.clone()
+        rec["gstats"] = eng.stats.clone()
+        out[fused] = rec
+    a, b = out["1"], out["0"]
+    m = {k: rel(a[k], b[k]) for k in ("cond", "score", "norms")}
+    m["dgrads"], m["ggrads"] = fro(a["dg"], b["dg"]), fro(a["gg"], b["gg"])
+    print(f"{variant} p={dropout}: fused vs seven-launch engine {m}")
+    assert m["cond"] < 2e-2 and m["score"] < 2e-2 and m["norms"] < 6e-2, m
+    assert m["dgrads"] < 5e-2 and m["ggrads"] < 8e-2, m   # (0.014 - 0.028 / 0.036 - 0.058 measured)
+    assert torch.allclose(a["stats"][:5], b["stats"][:5], rtol=2e-2, atol=2e-3)
+    assert torch.allclose(a["gstats"][4], b["gstats"][4], rtol=3e-2, atol=3e-3)
