@@ -119,6 +119,7 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_gp_step.argtypes = [vp, vp, vp, vp, vp, vp]
     L.gg_engine_lanes_signal.argtypes = [vp, vp]
     L.gg_masked_mean_rows.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.gg_gather_rows.argtypes = [vp, i64, vp, vp, i64, i64, i32, vp]
     L.gg_engine_stats.argtypes = [vp]
     L.gg_engine_stats.restype = vp
     L.gg_engine_buffer.argtypes = [vp, C.c_char_p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
@@ -155,7 +156,7 @@ EXPORTS = [
     "gg_last_error", "gg_abi_version", "gg_check_device", "gg_gemm_bf16", "gg_engine_workspace_bytes",
     "gg_engine_create", "gg_engine_destroy", "gg_engine_set_lanes", "gg_engine_refresh_shadows", "gg_engine_set_batch", "gg_engine_set_labels",
     "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_disc_grads_phase", "gg_engine_gen_grads_phase", "gg_engine_optim_step", "gg_engine_generate",
-    "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_gp_step", "gg_masked_mean_rows", "gg_engine_lanes_signal", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
+    "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_gp_step", "gg_masked_mean_rows", "gg_gather_rows", "gg_engine_lanes_signal", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",
     "gg_pairwise_distance", "gg_row_kth_smallest", "gg_row_membership", "gg_col_hits", "gg_standardize_columns",
     "gg_gene_correlation", "gg_gamma_moments_workspace_bytes", "gg_gamma_moments",

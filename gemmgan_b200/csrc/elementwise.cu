@@ -776,4 +776,38 @@ int k_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, in
   return GG_OK;
 }
 
+// dst[r, 0:cols] = index[r] >= 0 ? src[index[r], 0:cols] : 0 -- batch assembly on the device: the
+// rows of one batch (patch embeddings picked / zero-padded per case, gene profiles, token embeddings) are gathered
+// from a dataset that stays resident in HBM instead of being np.load-ed, collated and copied per step
+// (src/multi_patch_multi_token_gan_dataloader.py:25-55). One warp per row, 16-byte accesses when aligned. HBM bound.
+__global__ void __launch_bounds__(256)
+    gather_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int64_t* __restrict__ index,
+                       float* __restrict__ dst, int64_t ld_dst, int64_t rows, int cols) {
+  pdl_entry();
+  const int lane = threadIdx.x & 31;
+  const bool vec = (cols % 4 == 0) && (ld_src % 4 == 0) && (ld_dst % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); r < rows;
+       r += static_cast<int64_t>(gridDim.x) * 8) {
+    const int64_t s = index[r];
+    float* d = dst + r * ld_dst;
+    if (vec) {
+      const float4* sp = s >= 0 ? reinterpret_cast<const float4*>(src + s * ld_src) : nullptr;
+      for (int c = lane; c < cols / 4; c += 32)
+        reinterpret_cast<float4*>(d)[c] = sp ? __ldg(sp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int c = lane; c < cols; c += 32) d[c] = s >= 0 ? src[s * ld_src + c] : 0.f;
+    }
+  }
+}
+int k_gather_rows(const float* src, int64_t ld_src, const int64_t* index, float* dst, int64_t ld_dst, int64_t rows,
+                  int cols, cudaStream_t st) {
+  if (rows <= 0) return GG_OK;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_k(gather_rows_kernel, static_cast<unsigned>(blocks), 256, 0, st, src, ld_src, index, dst, ld_dst, rows, cols);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 }  // namespace gg

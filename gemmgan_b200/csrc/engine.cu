@@ -1373,6 +1373,12 @@ extern "C" int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* ou
   return k_masked_mean_rows(x, pad, out, B, P, D, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int gg_gather_rows(const float* src, int64_t ld_src, const int64_t* index, float* dst, int64_t ld_dst,
+                              int64_t rows, int32_t cols, void* stream) {
+  GG_REQUIRE(src && index && dst && rows >= 0 && cols > 0 && ld_src >= cols && ld_dst >= cols, "gg_gather_rows: bad argument");
+  return k_gather_rows(src, ld_src, index, dst, ld_dst, rows, cols, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" float* gg_engine_stats(gg_engine* e) { return e ? e->stats : nullptr; }
 
 extern "C" void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows, int64_t* cols, int64_t* ld,

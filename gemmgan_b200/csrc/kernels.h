@@ -56,6 +56,9 @@ int k_embed_gather(const float* emb0, const float* emb1, const int64_t* y0, cons
 int k_embed_grad(const bf16* dc, const int64_t* y0, const int64_t* y1, int V0, int V1, float* g0, float* g1, int B,
                  int Eh, cudaStream_t st);
 int k_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, cudaStream_t st);
+// dst[r, :] = index[r] >= 0 ? src[index[r], :] : 0   (fp32 rows; device-side batch assembly)
+int k_gather_rows(const float* src, int64_t ld_src, const int64_t* index, float* dst, int64_t ld_dst, int64_t rows,
+                  int cols, cudaStream_t st);
 
 // ---- enc_layer.cu: one encoder layer forward as one tcgen05 kernel (S <= 16 tokens, E = 256, ffn = 512, 4 heads)
 typedef gg_enc_layer_params EncLayerParams;

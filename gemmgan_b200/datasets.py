@@ -232,3 +232,102 @@ def multi_patch_multi_token_loaders(dataset_path, normalize=True, percentage_to_
                                          dataset_path / patch_embeddings_folder, p.genes[i], p.disease[i], p.site[i],
                                          num_patches=num_patches) for i in range(3)]
     return (*_loaders(ds, batch_size, num_workers, g), p.n_genes)
+
+
+# ------------------------------------------------------------------- device-resident datasets
+class DeviceResidentLoader:
+    """The batches of MultiPatchMultiTokenGANDataset / MultiPatchGANDataset + DataLoader, assembled ON THE GPU.
+
+    The reference's loader np.load()s two or three files per sample in worker processes, collates and copies ~110 KB
+    per sample to the device every step (src/multi_patch_multi_token_gan_dataloader.py:25-55, :178-185): at a few
+    milliseconds per training step that loader, not the step, bounds fit(). Here every case's patch embeddings (one
+    ragged [sum n_i, 1024] matrix), token embeddings / text vectors, masks, gene profiles and labels are uploaded
+    ONCE; per batch the host only draws the indices — the same np.random.choice(n, num_patches, replace=False) per
+    over-long case, in batch order, so that a seeded run picks the same patches as the reference dataset read with
+    num_workers=0 — and three gg_gather_rows launches build the fp32 batch tuple in HBM (padding rows are zero rows,
+    mask True = padding, as the reference :37-38, :46-47).
+
+    Iterating yields the reference's tuples with CUDA tensors: multi-token datasets
+    (tokens [B,T,768], token_pad [B,T] bool, genes [B,G], patches [B,P,1024], patch_pad [B,P] bool, disease, site),
+    single-vector datasets (text [B,768], genes, patches, patch_pad, disease, site). No drop_last, like the reference.
+    """
+
+    def __init__(self, dataset, batch_size, shuffle=False, generator=None, device=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self._C, self._lib = C, _lib.lib()
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        _lib.require_device(self.device.index or 0)
+        self.batch_size, self.shuffle, self.generator = batch_size, shuffle, generator
+        self.num_patches = dataset.num_patches
+        self.multi_token = isinstance(dataset, MultiPatchMultiTokenGANDataset)
+        n = len(dataset)
+        self.n = n
+        counts, chunks = [], []
+        for i in range(n):
+            pch = np.load(dataset.patches_path / f"{dataset.case_ids[i]}.npy").astype(np.float32, copy=False)
+            counts.append(pch.shape[0])
+            chunks.append(pch)
+        self.counts = np.asarray(counts, dtype=np.int64)
+        self.offsets = np.concatenate(([0], np.cumsum(self.counts)))
+        dev = self.device
+        self.patch_store = torch.from_numpy(np.ascontiguousarray(np.concatenate(chunks, axis=0))).to(dev)   # [sum n_i, Dp]
+        self.genes = torch.from_numpy(np.ascontiguousarray(dataset.gene_expressions, dtype=np.float32)).to(dev)  # (C order: pandas hands out F-ordered blocks)
+        self.disease = torch.as_tensor(np.asarray(dataset.disease_types), dtype=torch.long).to(dev)
+        self.site = torch.as_tensor(np.asarray(dataset.primary_site), dtype=torch.long).to(dev)
+        if self.multi_token:
+            toks, pads = [], []
+            for i in range(n):
+                case = dataset.case_ids[i]
+                tk = np.load(dataset.tokens_path / f"{case}.npy").astype(np.float32, copy=False)
+                toks.append(tk.reshape(-1, tk.shape[-1]))                                  # [1, T, Dt] -> [T, Dt]
+                pads.append(~np.load(dataset.tokens_path / f"{case}_attention_mask.npy").astype(bool).reshape(-1))
+            self.text = torch.from_numpy(np.stack(toks)).to(dev)                          # [n, T, Dt]
+            self.text_pad = torch.from_numpy(np.stack(pads)).to(dev)                      # [n, T] True = padding
+        else:
+            self.text = torch.from_numpy(np.ascontiguousarray(dataset.text_embeddings, dtype=np.float32)).to(dev)
+            self.text_pad = None
+
+    def __len__(self):
+        return (self.n + self.batch_size - 1) // self.batch_size
+
+    def _gather(self, src2d, index):
+        rows, cols = index.numel(), src2d.shape[1]
+        assert src2d.stride(1) == 1 and src2d.stride(0) >= cols, "device stores are row-major"
+        out = torch.empty(rows, cols, device=self.device, dtype=torch.float32)
+        C = self._C
+        from . import _lib
+        _lib.check(self._lib.gg_gather_rows(C.c_void_p(src2d.data_ptr()), src2d.stride(0), C.c_void_p(index.data_ptr()),
+                                            C.c_void_p(out.data_ptr()), cols, rows, cols,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
+
+    def __iter__(self):
+        order = torch.randperm(self.n, generator=self.generator).numpy() if self.shuffle else np.arange(self.n)
+        P = self.num_patches
+        for b0 in range(0, self.n, self.batch_size):
+            ids = order[b0:b0 + self.batch_size]
+            B = len(ids)
+            rows = np.full((B, P), -1, dtype=np.int64)
+            pad = np.zeros((B, P), dtype=bool)
+            for j, i in enumerate(ids):       # the reference's per-sample logic (:32-40), indices only
+                cnt, off = int(self.counts[i]), int(self.offsets[i])
+                if cnt > P:
+                    rows[j] = off + np.random.choice(cnt, P, replace=False)
+                else:
+                    rows[j, :cnt] = off + np.arange(cnt)
+                    pad[j, cnt:] = MASK_ZERO_PADDING
+            dev = self.device
+            sample = torch.from_numpy(np.ascontiguousarray(ids)).to(dev)
+            patches = self._gather(self.patch_store, torch.from_numpy(rows.reshape(-1)).to(dev)).view(B, P, -1)
+            genes = self._gather(self.genes, sample)
+            ppad = torch.from_numpy(pad).to(dev)
+            if self.multi_token:
+                T, Dt = self.text.shape[1], self.text.shape[2]
+                text = self._gather(self.text.view(self.n, T * Dt), sample).view(B, T, Dt)
+                yield (text, self.text_pad[sample], genes, patches, ppad, self.disease[sample], self.site[sample])
+            else:
+                text = self._gather(self.text, sample)
+                yield (text, genes, patches, ppad, self.disease[sample], self.site[sample])

@@ -286,6 +286,13 @@ int gg_engine_gp_step(gg_engine* e, const float* real_f32, const float* fake_f32
 /* out[b, :] (fp32) = mean over the rows p with pad[b, p] == 0 of x[b, p, :] — the masked mean of
  * conditional_gan_concat.py:137-138 ('image' conditioning), taken BEFORE the affine encoder. pad may be NULL. */
 int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream);
+/* Device-side batch assembly: dst[r, 0:cols] = index[r] >= 0 ? src[index[r], 0:cols] : 0 (fp32 rows,
+ * pitches in elements, index: device int64 [rows]). With the dataset resident in HBM (patch embeddings of every case
+ * as one ragged matrix, gene profiles, token embeddings) one call per tensor builds the batch tuple of
+ * MultiPatchMultiTokenGANDataset.__getitem__ + the DataLoader collation
+ * (src/multi_patch_multi_token_gan_dataloader.py:25-55: the picked / zero-padded patch rows, -1 = padding row). */
+int gg_gather_rows(const float* src, int64_t ld_src, const int64_t* index, float* dst, int64_t ld_dst, int64_t rows,
+                   int32_t cols, void* stream);
 float* gg_engine_stats(gg_engine* e);
 /* named internal device buffers for tests ("fake_bf16", "score", "gp_norms", "cond_disc", ...);
  * returns NULL for unknown names. rows/cols/ld (elements) are optional outputs. */

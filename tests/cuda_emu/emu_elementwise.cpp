@@ -46,3 +46,5 @@ W(embed_gather, (const float* e0, const float* e1, const int64_t* y0, const int6
 W(embed_grad, (const bf16* dc, const int64_t* y0, const int64_t* y1, int V0, int V1, float* g0, float* g1, int B, int Eh),
   (dc, y0, y1, V0, V1, g0, g1, B, Eh, nullptr))
 W(masked_mean_rows, (const float* x, const uint8_t* pad, float* out, int B, int P, int D), (x, pad, out, B, P, D, nullptr))
+W(gather_rows, (const float* src, int64_t ld_src, const int64_t* index, float* dst, int64_t ld_dst, int64_t rows, int cols),
+  (src, ld_src, index, dst, ld_dst, rows, cols, nullptr))

@@ -11,21 +11,34 @@ import torch
 sys.path.insert(0, ".")
 import bench  # noqa: E402
 
+import os  # noqa: E402
+
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/step_timeline.json"
 wl = sys.argv[2] if len(sys.argv) > 2 else "cfg3"
 w = dict(bench.WORKLOADS[wl])
+# under torchrun (data parallel): every rank trains, rank 0 records its own timeline (NCCL kernels included)
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 t = bench.build_trainer(w, "rms_prop")
-dev = torch.device("cuda", 0)
-batch = bench.make_batch(w, seed=42, device=dev)
+batch = bench.make_batch(w, seed=42 + rank, device=dev)
 for _ in range(5):
     t.train(*batch)
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
+if world > 1:
+    dist.barrier()
+    torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     t.train(*batch)
     torch.cuda.synchronize()
-import os  # noqa: E402
+if rank != 0:
+    dist.barrier()
+    os._exit(0)
 import tempfile  # noqa: E402
 
 tmp = os.path.join(tempfile.mkdtemp(), "trace.json")
@@ -40,3 +53,7 @@ for e in ev:
     e["start_us"] -= t0
 json.dump(ev, open(out, "w"))
 print("kernels", len(ev), "span_us", (ev[-1]["start_us"] + ev[-1]["dur_us"]) if ev else 0)
+if world > 1:
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)

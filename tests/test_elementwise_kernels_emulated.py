@@ -37,6 +37,7 @@ SIGS = {
     "embed_gather": [vp, vp, vp, vp, i32, i32, vp, i32, i32],
     "embed_grad": [vp, vp, vp, i32, i32, vp, vp, i32, i32],
     "masked_mean_rows": [vp, vp, vp, i32, i32, i32],
+    "gather_rows": [vp, i64, vp, vp, i64, i64, i32],
 }
 
 
@@ -300,3 +301,19 @@ def test_grouped_column_sums_are_exact_and_deterministic(k):
     assert L.emu_colsum_group(C.addressof(items), len(shapes), ws.data_ptr(), nbytes) == 0
     assert all(torch.equal(a, b) for a, b in zip(first, outs))   # bit-identical on the second launch
     assert L.emu_colsum_group(C.addressof(items), 41, ws.data_ptr(), nbytes) == -1   # more than COLSUM_GROUP_MAX
+
+
+@pytest.mark.parametrize("cols,ld_src,ld_dst", [(1024, 1024, 1024), (203, 203, 211), (768, 772, 768)])
+def test_gather_rows_builds_a_batch(k, cols, ld_src, ld_dst):
+    """gg_gather_rows (device-side batch assembly): picked rows are copied, -1 rows are the zero
+    padding of src/multi_patch_multi_token_gan_dataloader.py:37-38; vector and scalar paths, pitched tensors."""
+    g = torch.Generator().manual_seed(0)
+    n_src, rows = 57, 40
+    src = torch.randn(n_src, ld_src, generator=g)
+    index = torch.randint(-1, n_src, (rows,), generator=g, dtype=torch.int64)
+    index[3] = -1
+    dst = torch.full((rows, ld_dst), 7.0)
+    k.gather_rows(src, ld_src, index, dst, ld_dst, rows, cols)
+    want = torch.where((index >= 0)[:, None], src[index.clamp(min=0), :cols], torch.zeros(rows, cols))
+    assert torch.equal(dst[:, :cols], want)
+    assert torch.all(dst[:, cols:] == 7.0)            # the pitch padding is left alone
