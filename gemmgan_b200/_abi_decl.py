@@ -79,6 +79,14 @@ class EncLayerParams(C.Structure):
                 ("mean1", C.c_void_p), ("rstd1", C.c_void_p), ("mean2", C.c_void_p), ("rstd2", C.c_void_p)]
 
 
+class EncFfnBwdParams(C.Structure):
+    """gg_enc_ffn_bwd_params (include/gemmgan.h)."""
+    _fields_ = [("rows", C.c_int64), ("dout", C.c_void_p), ("z2", C.c_void_p), ("mean2", C.c_void_p),
+                ("rstd2", C.c_void_p), ("gamma2", C.c_void_p), ("h", C.c_void_p), ("w2t", C.c_void_p),
+                ("ld_w2t", C.c_int64), ("w1t", C.c_void_p), ("ld_w1t", C.c_int64), ("drop_p", C.c_float),
+                ("rng", C.c_void_p), ("site", C.c_uint32), ("gh", C.c_void_p), ("gb", C.c_void_p)]
+
+
 class ColsumItem(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("ld", C.c_int64), ("rows", C.c_int64), ("N", C.c_int32), ("out", C.c_void_p)]
 
@@ -135,6 +143,7 @@ def declare(L: C.CDLL) -> None:
     L.gg_colsum_group.argtypes = [C.POINTER(ColsumItem), i32, vp, i64, vp]
     L.gg_encoder_layer_fwd.argtypes = [C.POINTER(EncLayerParams), vp]
     L.gg_enc_layer_set_trace.argtypes = [vp]
+    L.gg_encoder_ffn_bwd.argtypes = [C.POINTER(EncFfnBwdParams), vp]
     L.gg_enc_layer_profile.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_longlong)]
     declare_evalmetrics(L)
@@ -160,5 +169,5 @@ EXPORTS = [
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",
     "gg_pairwise_distance", "gg_row_kth_smallest", "gg_row_membership", "gg_col_hits", "gg_standardize_columns",
     "gg_gene_correlation", "gg_gamma_moments_workspace_bytes", "gg_gamma_moments",
-    "gg_encoder_layer_fwd", "gg_enc_layer_set_trace", "gg_enc_layer_profile", "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
+    "gg_encoder_layer_fwd", "gg_encoder_ffn_bwd", "gg_enc_layer_set_trace", "gg_enc_layer_profile", "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

@@ -848,6 +848,358 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
   return GG_OK;
 }
 
+
+// ===================================================================================================================
+// gg_encoder_ffn_bwd: the feed-forward half of one encoder layer's BACKWARD as one kernel (the dependent chain only).
+//
+//   gz = LayerNorm2-backward(dout; z2, mean2, rstd2, gamma2)          (gradient w.r.t. the pre-LayerNorm sum)
+//   gy = dropout-mask(gz)                                              (site + 3, regenerated)
+//   gh = (gy W2) * [h > 0] * keep_scale                                (through ffn2, relu and the ffn dropout: h is the
+//                                                                       stored post-dropout activation)
+//   gb = gz + gh W1                                                    (through ffn1, plus the residual branch)
+//
+// replaces add_ln_bwd -> dgrad(ffn2) -> dgrad(ffn1) on the step's dependent chain (90 us per layer at the paper
+// model's shape, profiles/r02_timeline_cfg3_n1_two_critic_steps.json); the LayerNorm parameter gradients and the
+// bf16 gz / gy tensors the weight-gradient GEMMs read are still produced by add_ln_bwd_kernel, now on a side lane.
+// Both dgrads are K-major products against TRANSPOSED bf16 shadows (W2^T [512, 256], W1^T [256, 512]), i.e. exactly
+// the forward's ffn1 / ffn2 pipeline: same producer / MMA / epilogue roles, same ring, same 128-row tiles (no
+// sequence alignment needed here). gz never leaves the SM: the prologue parks it in fp32 in the tensor-memory
+// columns of the second product's accumulator (tcgen05.st), so the residual add is the MMA's own accumulation.
+namespace el {
+
+enum BBar { BB_XFULL = 0, BB_FULL0, BB_FULL1, BB_EMPTY0, BB_EMPTY1, BB_GYFULL, BB_F1AFULL, BB_ACCAEMPTY, BB_F1BFULL,
+            BB_HAFULL, BB_F2ADONE, BB_HBFULL, BB_OUTFULL, BB_TILEDONE, BB_COUNT };
+
+struct BArgs {
+  int64_t rows;
+  int num_tiles;
+  const float *mean, *rstd, *gamma;
+  const bf16* h;     // [rows, 512] stored post-dropout relu activations (mask source)
+  float drop_p;
+  const uint64_t* rng;
+  uint32_t site;     // dropout site of the LayerNorm-2 residual branch (layer site + 3)
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+    enc_ffn_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmZ,
+                       const __grid_constant__ CUtensorMap tmW2T, const __grid_constant__ CUtensorMap tmW1T,
+                       const __grid_constant__ CUtensorMap tmGH, const __grid_constant__ CUtensorMap tmGB,
+                       const BArgs a) {
+  extern __shared__ uint8_t el_smem_raw[];
+  uint8_t* smem = el_smem_raw + ((1024 - (smem_u32(el_smem_raw) & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + BB_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmW2T); tma_prefetch_desc(&tmW1T);
+    tma_prefetch_desc(&tmGH); tma_prefetch_desc(&tmGB);
+    for (int i = 0; i < BB_COUNT; ++i) {
+      const bool by_warps = i == BB_GYFULL || i == BB_ACCAEMPTY || i == BB_HAFULL || i == BB_HBFULL;
+      mbar_init(&bars[i], by_warps ? EPI_WARPS : 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_entry();
+  const uint32_t buf0 = smem_u32(smem + OFF_BUF0), buf1 = smem_u32(smem + OFF_BUF1), ring = smem_u32(smem + OFF_RING);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(&bars[BB_TILEDONE], (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[BB_XFULL], 8u * BLK);
+        for (int kb = 0; kb < 4; ++kb) {
+          tma_load_2d(smem + OFF_BUF0 + kb * BLK, &tmG, &bars[BB_XFULL], kb * 64, tile * 128);
+          tma_load_2d(smem + OFF_BUF1 + kb * BLK, &tmZ, &bars[BB_XFULL], kb * 64, tile * 128);
+        }
+        // W2^T rows [0, 256) / [256, 512) (the two halves of the hidden units), then W1^T K halves
+        for (int blk = 0; blk < 4; ++blk)
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&bars[BB_EMPTY0 + s], ph ^ 1);
+            mbar_arrive_expect_tx(&bars[BB_FULL0 + s], 32768u);
+            uint8_t* dst = smem + OFF_RING + s * SLOT;
+            // consumption order: product 1 half a, product 1 half b, product 2 half a, product 2 half b
+            if (blk == 0) tma_load_2d(dst, &tmW2T, &bars[BB_FULL0 + s], kb * 64, 0);
+            else if (blk == 1) tma_load_2d(dst, &tmW1T, &bars[BB_FULL0 + s], kb * 64, 0);           // (see MMA order)
+            else if (blk == 2) tma_load_2d(dst, &tmW2T, &bars[BB_FULL0 + s], kb * 64, 256);
+            else tma_load_2d(dst, &tmW1T, &bars[BB_FULL0 + s], 256 + kb * 64, 0);
+            if (++s == 2) { s = 0; ph ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_256 = make_idesc_bf16(128, 256, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      auto kblocks = [&](uint32_t d_tmem, uint32_t a_base, bool accumulate) {
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&bars[BB_FULL0 + s], ph);
+          tc_fence_after_sync();
+          mma_kblock(d_tmem, a_base + kb * BLK, ring + s * SLOT, idesc_256, accumulate || kb > 0);
+          tc_commit(&bars[BB_EMPTY0 + s]);
+          if (++s == 2) { s = 0; ph ^= 1; }
+        }
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1;
+        // weight order in the ring: W2^T half a | W1^T K half a | W2^T half b | W1^T K half b
+        mbar_wait(&bars[BB_GYFULL], par);        // gy in BUF0, gz parked in TMEM [256, 512)
+        tc_fence_after_sync();
+        kblocks(tmem_base, buf0, false);         // (gy W2)[:, 0:256] -> TMEM [0, 256)
+        tc_commit(&bars[BB_F1AFULL]);
+        mbar_wait(&bars[BB_HAFULL], par);        // gh half a in BUF1
+        tc_fence_after_sync();
+        kblocks(tmem_base + 256, buf1, true);    // gz += gh_a W1[0:256, :]
+        tc_commit(&bars[BB_F2ADONE]);
+        mbar_wait(&bars[BB_ACCAEMPTY], par);     // (long since true: the epilogue drained TMEM [0, 256) before HAFULL)
+        tc_fence_after_sync();
+        kblocks(tmem_base, buf0, false);         // (gy W2)[:, 256:512] -> TMEM [0, 256)
+        tc_commit(&bars[BB_F1BFULL]);
+        mbar_wait(&bars[BB_HBFULL], par);
+        tc_fence_after_sync();
+        kblocks(tmem_base + 256, buf1, true);    // += gh_b W1[256:512, :]
+        tc_commit(&bars[BB_OUTFULL]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int part = ew >> 2;
+    const int row = q * 32 + lane;
+    const bool t0 = ew == 0 && lane == 0;
+    const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const bool drop = a.drop_p > 0.f;
+    uint64_t seed = 0, step = 0;
+    float keep_scale = 1.f;
+    uint32_t thr = 0;
+    if (drop) {
+      seed = a.rng[0];
+      step = a.rng[1];
+      keep_scale = 1.f / (1.f - a.drop_p);
+      thr = dropout_thr(a.drop_p);
+    }
+    float* red = reinterpret_cast<float*>(smem + OFF_RED);
+    float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
+    // gamma -> shared memory once per CTA (the K / V staging area of the forward is unused here)
+    for (int i = threadIdx.x - 64; i < E / 4; i += EPI_THREADS)
+      reinterpret_cast<float4*>(vec)[i] = __ldg(reinterpret_cast<const float4*>(a.gamma) + i);
+    bar_sync_epi();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
+      const int64_t grow = static_cast<int64_t>(tile) * 128 + row;
+      const bool valid = grow < a.rows;
+      const int trow = tile * 128;
+      uint32_t km[2] = {0, 0};
+      if (drop) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          km[j >> 2] |= keep8(seed, step, a.site, ((static_cast<uint64_t>(grow) * E + part * 64) >> 3) + j, thr) << (8 * (j & 3));
+      }
+      const float mu = valid ? __ldg(a.mean + grow) : 0.f, rs = valid ? __ldg(a.rstd + grow) : 0.f;
+      mbar_wait(&bars[BB_XFULL], par);
+      uint8_t* gblk = smem + OFF_BUF0 + part * BLK;
+      uint8_t* zblk = smem + OFF_BUF1 + part * BLK;
+      // ---- LayerNorm backward, sweep 1: the two row means
+      float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d[8], z[8];
+        unpack8(*reinterpret_cast<const uint4*>(gblk + swz(row, j)), d);
+        unpack8(*reinterpret_cast<const uint4*>(zblk + swz(row, j)), z);
+        const float4 g0 = *reinterpret_cast<const float4*>(vec + part * 64 + 8 * j);
+        const float4 g1 = *reinterpret_cast<const float4*>(vec + part * 64 + 8 * j + 4);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float g = d[t] * gm[t];
+          c1 += g;
+          c2 = fmaf(g, (z[t] - mu) * rs, c2);
+        }
+      }
+      red[part * 128 + row] = c1;
+      red[512 + part * 128 + row] = c2;
+      bar_sync_epi();
+      c1 = (red[row] + red[128 + row] + red[256 + row] + red[384 + row]) * (1.f / E);
+      c2 = (red[512 + row] + red[640 + row] + red[768 + row] + red[896 + row]) * (1.f / E);
+      // ---- sweep 2: gz (fp32) -> tensor memory [256 + part * 64, +64) = the accumulator the second product adds to;
+      // gy = dropout-mask(gz) (bf16) over dout in BUF0 = the A operand of the first product
+#pragma unroll 1
+      for (int hs = 0; hs < 2; ++hs) {
+        float gz[32];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = hs * 4 + jj;
+          float d[8], z[8], y[8];
+          uint4* slot = reinterpret_cast<uint4*>(gblk + swz(row, j));
+          unpack8(*slot, d);
+          unpack8(*reinterpret_cast<const uint4*>(zblk + swz(row, j)), z);
+          const float4 g0 = *reinterpret_cast<const float4*>(vec + part * 64 + 8 * j);
+          const float4 g1 = *reinterpret_cast<const float4*>(vec + part * 64 + 8 * j + 4);
+          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const uint32_t kb = km[j >> 2] >> (8 * (j & 3));
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float v = rs * (d[t] * gm[t] - c1 - (z[t] - mu) * rs * c2);
+            gz[8 * jj + t] = v;
+            y[t] = drop ? (((kb >> t) & 1u) ? v * keep_scale : 0.f) : v;
+          }
+          *slot = pack8(y);
+        }
+        tmem_st_32x32(tm_lane + 256 + part * 64 + hs * 32, gz);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BB_GYFULL]);
+
+      // ---- first product's epilogues: gh = acc * [h > 0] * keep_scale -> BUF1 (z2 is dead) -> HBM
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&bars[half == 0 ? BB_F1AFULL : BB_F1BFULL], par);
+        tc_fence_after_sync();
+        if (half == 1) {
+          mbar_wait(&bars[BB_F2ADONE], par);  // the second product's first half has finished reading BUF1
+          if (t0) tma_store_wait_read<0>();
+          bar_sync_epi();
+        }
+        uint8_t* myblk = smem + OFF_BUF1 + part * BLK;
+#pragma unroll 1
+        for (int hs = 0; hs < 2; ++hs) {
+          float v[32];
+          tmem_ld_32x32(tm_lane + part * 64 + hs * 32, v);
+          uint4 hm[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            hm[jj] = valid ? __ldg(reinterpret_cast<const uint4*>(a.h + grow * F + half * 256 + part * 64 + hs * 32) + jj)
+                           : make_uint4(0, 0, 0, 0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float hv[8];
+            unpack8(hm[jj], hv);
+            float* w = v + 8 * jj;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) w[t] = hv[t] > 0.f ? w[t] * keep_scale : 0.f;
+            *reinterpret_cast<uint4*>(myblk + swz(row, hs * 4 + jj)) = pack8(w);
+          }
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (half == 0) mbar_arrive(&bars[BB_ACCAEMPTY]);  // TMEM [0, 256) may take the second half of product 1
+          mbar_arrive(&bars[half == 0 ? BB_HAFULL : BB_HBFULL]);
+        }
+        if (t0) {
+          mbar_wait(&bars[half == 0 ? BB_HAFULL : BB_HBFULL], par);
+          for (int kb = 0; kb < 4; ++kb) tma_store_2d(&tmGH, smem + OFF_BUF1 + kb * BLK, half * 256 + kb * 64, trow);
+          tma_store_commit();
+        }
+      }
+
+      // ---- gb = gz + gh W1 (the accumulator) -> BUF0 (gy is dead: both halves of product 1 are complete) -> HBM
+      mbar_wait(&bars[BB_OUTFULL], par);
+      tc_fence_after_sync();
+      {
+        uint8_t* oblk = smem + OFF_BUF0 + part * BLK;
+#pragma unroll 1
+        for (int hs = 0; hs < 2; ++hs) {
+          float v[32];
+          tmem_ld_32x32(tm_lane + 256 + part * 64 + hs * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) *reinterpret_cast<uint4*>(oblk + swz(row, hs * 4 + jj)) = pack8(v + 8 * jj);
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      bar_sync_epi();
+      if (t0) {
+        for (int kb = 0; kb < 4; ++kb) tma_store_2d(&tmGB, smem + OFF_BUF0 + kb * BLK, kb * 64, trow);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(&bars[BB_TILEDONE]);
+      }
+    }
+    if (t0) tma_store_wait_all<0>();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace el
+
+int k_enc_ffn_bwd(const EncFfnBwdParams& p, cudaStream_t st) {
+  using namespace el;
+  GG_REQUIRE(p.rows > 0 && p.dout && p.z2 && p.mean2 && p.rstd2 && p.gamma2 && p.h && p.w2t && p.w1t && p.gh && p.gb,
+             "fused ffn backward: null tensor");
+  GG_REQUIRE(p.drop_p == 0.f || p.rng, "dropout needs an rng state pointer");
+  BArgs a;
+  a.rows = p.rows;
+  a.num_tiles = static_cast<int>((p.rows + 127) / 128);
+  a.mean = p.mean2; a.rstd = p.rstd2; a.gamma = p.gamma2;
+  a.h = static_cast<const bf16*>(p.h);
+  a.drop_p = p.drop_p; a.rng = p.rng; a.site = p.site;
+  CUtensorMap mG, mZ, mW2T, mW1T, mGH, mGB;
+  GG_TRY_RC(encode_tma_map(&mG, p.dout, E, p.rows, E, 128, false));
+  GG_TRY_RC(encode_tma_map(&mZ, p.z2, E, p.rows, E, 128, false));
+  GG_TRY_RC(encode_tma_map(&mW2T, p.w2t, E, F, p.ld_w2t, 256, false));   // W2^T [512, 256]
+  GG_TRY_RC(encode_tma_map(&mW1T, p.w1t, F, E, p.ld_w1t, 256, false));   // W1^T [256, 512]
+  GG_TRY_RC(encode_tma_map(&mGH, p.gh, F, p.rows, F, 128, false));
+  GG_TRY_RC(encode_tma_map(&mGB, p.gb, E, p.rows, E, 128, false));
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(enc_ffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  GG_CUDA_CHECK(attr_err);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    GG_CUDA_CHECK(cudaGetDevice(&dev));
+    GG_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+  {
+    const double rows = static_cast<double>(p.rows);
+    GG_TRY_RC(prof_aux_begin(rows * 4.0 * E * F, rows * (E * 2 * 3 + F * 2 * 2) + 2.0 * E * F * 2, st));
+  }
+  launch_k(enc_ffn_bwd_kernel, static_cast<unsigned>(grid), THREADS, SMEM_BYTES, st, mG, mZ, mW2T, mW1T, mGH, mGB, a);
+  GG_LAUNCH_CHECK();
+  GG_TRY_RC(prof_aux_end(st));
+  return GG_OK;
+}
+
 }  // namespace gg
 
 // Diagnostics: CTA 0 of every following launch stamps clock64() per role for its first tile into device_buf
@@ -855,6 +1207,14 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
 extern "C" int gg_enc_layer_set_trace(void* device_buf) {
   gg::g_el_trace = reinterpret_cast<long long*>(device_buf);
   return GG_OK;
+}
+
+extern "C" int gg_encoder_ffn_bwd(const gg_enc_ffn_bwd_params* p, void* stream) {
+  GG_REQUIRE(p != nullptr, "null argument");
+  int dev = 0;
+  GG_CUDA_CHECK(cudaGetDevice(&dev));
+  GG_TRY_RC(gg_check_device(dev));
+  return gg::k_enc_ffn_bwd(*p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gg_encoder_layer_fwd(const gg_enc_layer_params* p, void* stream) {

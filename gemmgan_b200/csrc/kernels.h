@@ -63,6 +63,8 @@ int k_gather_rows(const float* src, int64_t ld_src, const int64_t* index, float*
 // ---- enc_layer.cu: one encoder layer forward as one tcgen05 kernel (S <= 16 tokens, E = 256, ffn = 512, 4 heads)
 typedef gg_enc_layer_params EncLayerParams;
 int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st);
+typedef gg_enc_ffn_bwd_params EncFfnBwdParams;
+int k_enc_ffn_bwd(const EncFfnBwdParams& p, cudaStream_t st);
 
 // ---- wgrad_group.cu: all single-segment weight gradients dW = dY^T X of one backward pass in one launch
 constexpr int WGRAD_GROUP_MAX = 32;

@@ -352,6 +352,27 @@ typedef struct gg_enc_layer_params {
   float *mean1, *rstd1, *mean2, *rstd2;
 } gg_enc_layer_params;
 int gg_encoder_layer_fwd(const gg_enc_layer_params* p, void* stream);
+/* The feed-forward half of the same layer's BACKWARD, dependent chain only, as one kernel: LayerNorm-2 backward of
+ * dout -> dropout mask (site) -> x W2 -> relu / ffn-dropout mask from the stored activation h -> x W1 -> + residual:
+ *   gz = LN2'(dout; z2, mean2, rstd2, gamma2); gh = (mask(gz) W2) * [h > 0] / (1 - p); gb = gz + gh W1.
+ * Replaces autograd's LayerNormBackward / AddmmBackward / ReluBackward nodes of linear2 / linear1 inside
+ * disc_loss.backward() / gen_loss.backward() (:412, :455; torch/nn/modules/transformer.py _ff_block). w2t / w1t are
+ * TRANSPOSED bf16 copies of linear2.weight ([512, 256]) and linear1.weight ([256, 512]) (pitches multiples of 8).
+ * Outputs: gh [rows, 512] (the weight gradient of linear1 reads it), gb [rows, 256] (gradient w.r.t. x1). The
+ * LayerNorm parameter gradients and the tensors linear2's weight gradient reads stay with the unfused kernels. */
+typedef struct gg_enc_ffn_bwd_params {
+  int64_t rows;
+  const void* dout;
+  const void* z2;
+  const float *mean2, *rstd2, *gamma2;
+  const void* h;
+  const void* w2t; int64_t ld_w2t;
+  const void* w1t; int64_t ld_w1t;
+  float drop_p; const uint64_t* rng; uint32_t site;
+  void* gh;
+  void* gb;
+} gg_enc_ffn_bwd_params;
+int gg_encoder_ffn_bwd(const gg_enc_ffn_bwd_params* p, void* stream);
 /* Diagnostics: CTA 0 of every following gg_encoder_layer_fwd launch stamps clock64() per pipeline role for its first
  * tile into device_buf (3 x 64 int64: TMA producer / MMA issuer / first epilogue warp); NULL = off. */
 int gg_enc_layer_set_trace(void* device_buf);

@@ -32,6 +32,10 @@ int k_wgrad_group(const WgradItem*, int, void*, int64_t, cudaStream_t) {
   set_error("the grouped weight-gradient kernel is tcgen05 only (not available in the host emulation)");
   return GG_ERR_ARCH;
 }
+int k_enc_ffn_bwd(const EncFfnBwdParams&, cudaStream_t) {
+  set_error("the fused ffn-backward kernel is tcgen05 only (not available in the host emulation)");
+  return GG_ERR_ARCH;
+}
 int k_enc_layer_fwd(const EncLayerParams&, cudaStream_t) {
   set_error("the fused encoder-layer kernel is tcgen05 only (not available in the host emulation)");
   return GG_ERR_ARCH;
@@ -39,6 +43,7 @@ int k_enc_layer_fwd(const EncLayerParams&, cudaStream_t) {
 }  // namespace gg
 extern "C" int gg_encoder_layer_fwd(const gg_enc_layer_params*, void*) { return GG_ERR_ARCH; }
 extern "C" int gg_enc_layer_set_trace(void*) { return GG_ERR_ARCH; }
+extern "C" int gg_encoder_ffn_bwd(const gg_enc_ffn_bwd_params*, void*) { return GG_ERR_ARCH; }
 
 #include "../../gemmgan_b200/csrc/engine.cu"
 

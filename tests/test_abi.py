@@ -37,11 +37,12 @@ def test_struct_layouts_match_header_sizes(tmp_path):
     src = tmp_path / "probe.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "gemmgan.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %d %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gg_epilogue), sizeof(gg_gemm_seg),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %d %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gg_epilogue), sizeof(gg_gemm_seg),'
         'sizeof(gg_gemm_desc), sizeof(gg_net_buffers), sizeof(gg_model_cfg), offsetof(gg_gemm_desc, epi),'
         'offsetof(gg_net_buffers, off), (int)GG_NSLOTS, sizeof(gg_wgrad_item), offsetof(gg_wgrad_item, bias),'
         'sizeof(gg_colsum_item), sizeof(gg_attn_args), offsetof(gg_gemm_desc, pair), sizeof(gg_enc_layer_params),'
-        'offsetof(gg_enc_layer_params, mask_mod), offsetof(gg_enc_layer_params, mean1));return 0;}\n')
+        'offsetof(gg_enc_layer_params, mask_mod), offsetof(gg_enc_layer_params, mean1), sizeof(gg_enc_ffn_bwd_params),'
+        'offsetof(gg_enc_ffn_bwd_params, site));return 0;}\n')
     exe = tmp_path / "probe"
     subprocess.check_call([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
@@ -50,7 +51,8 @@ def test_struct_layouts_match_header_sizes(tmp_path):
                     _abi_decl.NetBuffers.off.offset, _abi_decl.NSLOTS, C.sizeof(_abi_decl.WgradItem),
                     _abi_decl.WgradItem.bias.offset, C.sizeof(_abi_decl.ColsumItem), C.sizeof(_abi_decl.AttnArgs),
                     _lib.GemmDesc.pair.offset, C.sizeof(_abi_decl.EncLayerParams), _abi_decl.EncLayerParams.mask_mod.offset,
-                    _abi_decl.EncLayerParams.mean1.offset]
+                    _abi_decl.EncLayerParams.mean1.offset, C.sizeof(_abi_decl.EncFfnBwdParams),
+                    _abi_decl.EncFfnBwdParams.site.offset]
 
 
 def test_no_cpu_fallback_in_product_path():

@@ -173,3 +173,49 @@ def test_fused_layer_is_deterministic_and_dropout_changes_with_the_step():
     for k in a:
         assert torch.equal(a[k], b[k]), k
     assert not torch.equal(a["out"], c["out"])
+
+
+# ------------------------------------------------------------------ fused ffn-half backward (gg_encoder_ffn_bwd)
+@pytest.mark.parametrize("rows,p", [(1000, 0.0), (18432, 0.1), (333, 0.1), (128, 0.0)])
+def test_fused_ffn_backward_matches_torch(rows, p):
+    """gz = LN2'(dout), gy = mask(gz), gh = (gy W2) * [h > 0] / (1 - p), gb = gz + gh W1 against fp32 torch math on the
+    same bf16 operands (dropout mask of the residual branch regenerated on the host; the ffn dropout acts through the
+    stored activation h, whose zeros are dropped or relu-inactive units)."""
+    _lib.require_device(0)
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    r = lambda *s, scale=1.0: torch.randn(*s, device="cuda", generator=g) * scale
+    dout, z2 = r(rows, E).bfloat16(), r(rows, E).bfloat16()
+    gamma = 1 + 0.1 * r(E)
+    w1, w2 = r(F, E, scale=E ** -0.5).bfloat16(), r(E, F, scale=F ** -0.5).bfloat16()
+    h = torch.relu(r(rows, F))
+    h = (h * (torch.rand(rows, F, device="cuda", generator=g) > 0.1)).bfloat16()      # zeros = inactive or dropped
+    zf = z2.float()
+    mean, var = zf.mean(1), zf.var(1, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-5)
+    seed, step, site = 0xABCDEF12345, 5, 19
+    w2t, w1t = w2.t().contiguous(), w1.t().contiguous()
+    gh = torch.full((rows, F), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gb = torch.full((rows, E), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rng = torch.tensor([seed, step], dtype=torch.int64, device="cuda")
+    P = A.EncFfnBwdParams()
+    P.rows, P.dout, P.z2, P.mean2, P.rstd2, P.gamma2 = rows, dout.data_ptr(), z2.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()
+    P.h, P.w2t, P.ld_w2t, P.w1t, P.ld_w1t = h.data_ptr(), w2t.data_ptr(), E, w1t.data_ptr(), F
+    P.drop_p, P.rng, P.site, P.gh, P.gb = p, rng.data_ptr(), site, gh.data_ptr(), gb.data_ptr()
+    _lib.check(L.gg_encoder_ffn_bwd(C.byref(P), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    # reference
+    d = dout.float() * gamma
+    xh = (zf - mean[:, None]) * rstd[:, None]
+    gz = rstd[:, None] * (d - d.mean(1, keepdim=True) - xh * (d * xh).mean(1, keepdim=True))
+    keep_scale = 1.0 / (1.0 - p) if p > 0 else 1.0
+    if p > 0:
+        idx = np.arange(rows * E, dtype=np.int64).reshape(rows, E)
+        keep = torch.from_numpy(philox_keep(seed, step, site, idx, p)).cuda().float() * keep_scale
+    else:
+        keep = torch.ones(rows, E, device="cuda")
+    gy = (gz * keep).bfloat16().float()
+    gh_ref = (gy @ w2.float()) * (h.float() > 0) * keep_scale
+    gb_ref = gz + gh_ref.bfloat16().float() @ w1.float()
+    assert rel(gh, gh_ref) < 1.5e-2, rel(gh, gh_ref)
+    assert rel(gb, gb_ref) < 1.5e-2, rel(gb, gb_ref)
