@@ -74,6 +74,7 @@ struct WShadow {
 };
 struct NetShadow {
   WShadow w[GG_NSLOTS];
+  WShadow wt[GG_NSLOTS];  // transposed copies (ffn weights of the encoder layers: dgrad operands of enc_ffn_bwd)
   WShadow tr0_c;  // conditioning column block of the first trunk layer
   bf16* base = nullptr;
   int64_t elems = 0;
@@ -330,17 +331,19 @@ static void layout_shadows(gg_engine& e, Arena& ar) {
       int rows, cols;
       if (e.nets[net].off[slot] < 0 || !slot_matrix_shape(c, net, slot, &rows, &cols)) continue;
       if (slot == GG_P_FIN_W && net == GG_NET_DISC) continue;  // used as an fp32 vector
-      auto add = [&](int col0, int ncols, WShadow* dst) {
-        const int64_t ld = round_up64(ncols, 8);
+      auto add = [&](int col0, int ncols, WShadow* dst, bool transpose = false) {
+        const int64_t ld = round_up64(transpose ? rows : ncols, 8);
         elems = round_up64(elems, 128);
         ShadowSeg sg;
+        memset(&sg, 0, sizeof(sg));
         sg.p_off = e.nets[net].off[slot];
         sg.rows = rows; sg.cols = cols; sg.col0 = col0; sg.ncols = ncols;
         sg.s_off = elems; sg.s_ld = ld;
+        sg.transpose = transpose ? 1 : 0;
         s.segs.push_back(sg);
         dst->ld = ld;
         dst->p = reinterpret_cast<bf16*>(static_cast<uintptr_t>(elems));  // offset for now
-        elems += static_cast<int64_t>(rows) * ld;
+        elems += static_cast<int64_t>(transpose ? ncols : rows) * ld;
       };
       if (slot == GG_P_TR0_W && c.variant != GG_VARIANT_VANILLA) {
         const int first = cols - c.E;
@@ -349,11 +352,18 @@ static void layout_shadows(gg_engine& e, Arena& ar) {
       } else {
         add(0, cols, &s.w[slot]);
       }
+      if (slot >= GG_P_LAYER0 && slot < GG_P_LAYER0 + 24) {
+        const int k = (slot - GG_P_LAYER0) % GG_L_COUNT;
+        if (k == GG_L_FF1_W || k == GG_L_FF2_W) add(0, cols, &s.wt[slot], true);
+      }
     }
     s.elems = elems;
     s.base = ar.take<bf16>(elems);
-    for (int slot = 0; slot < GG_NSLOTS; ++slot)
+    for (int slot = 0; slot < GG_NSLOTS; ++slot) {
       if (s.w[slot].ld) s.w[slot].p = s.base + reinterpret_cast<uintptr_t>(s.w[slot].p);
+      if (s.wt[slot].ld) s.wt[slot].p = s.base + reinterpret_cast<uintptr_t>(s.wt[slot].p);
+    }
+
     if (s.tr0_c.ld) s.tr0_c.p = s.base + reinterpret_cast<uintptr_t>(s.tr0_c.p);
     s.segs_dev = ar.take<ShadowSeg>(static_cast<int64_t>(s.segs.size()) + 1);
   }
@@ -569,9 +579,9 @@ static void derive(gg_engine& e) {
 }
 
 // the fused encoder-layer kernel covers the reference's layer shape (d_model 256, 4 heads, ffn 512) at <= 16 tokens
-static bool cfg_fused_layer_ok(const gg_engine& e) {
+static bool cfg_fused_layer_ok(const gg_engine& e, bool any_tokens = false) {
   const gg_model_cfg& c = e.cfg;
-  return c.gemm_impl == GG_IMPL_TCGEN05 && c.E == 256 && c.ffn == 512 && c.n_heads == 4 && e.S_ <= 16;
+  return c.gemm_impl == GG_IMPL_TCGEN05 && c.E == 256 && c.ffn == 512 && c.n_heads == 4 && (any_tokens || e.S_ <= 16);
 }
 
 // ------------------------------------------------------------------------------- tower forward
@@ -825,18 +835,43 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     const int ls = GG_P_LAYER0 + GG_L_COUNT * l;
     const uint32_t site = site0 + 8u * l;
     // x_out = LN2(x1 + drop(ff))
-    GG_TRY(k_add_ln_bwd(g.ga, L.z2, L.mean2, L.rstd2, e.P(net, ls + GG_L_N2_W), lg.gz2, p > 0.f ? lg.gy2 : nullptr,
-                        nullptr, nullptr, rows, E, p, e.rng, site + 3, lg.lnp2, st));
-    GG_TRY(e.fork(2));
-    GG_TRY(k_ln_bwd_finish(lg.lnp2, rows, E, e.Gr(net, ls + GG_L_N2_W), e.Gr(net, ls + GG_L_N2_B), e.S(2)));
     const bf16* dff = p > 0.f ? lg.gy2 : lg.gz2;
-    GG_TRY(e.wgrad(E, F, rows, Op{dff, E}, Op{L.h, F}, e.Gr(net, ls + GG_L_FF2_W), F));
-    GG_TRY(e.bgrad(dff, E, rows, E, e.Gr(net, ls + GG_L_FF2_B)));
-    GG_TRY(e.dgrad(0, rows, F, E, Op{dff, E}, e.W(net, ls + GG_L_FF2_W),
-                   Epi().mask(L.h, F, keep_scale, 0.f).obf(lg.gh, F)));
-    GG_TRY(e.wgrad(F, E, rows, Op{lg.gh, F}, Op{L.x1, E}, e.Gr(net, ls + GG_L_FF1_W), E));
-    GG_TRY(e.bgrad(lg.gh, F, rows, F, e.Gr(net, ls + GG_L_FF1_B)));
-    GG_TRY(e.dgrad(0, rows, E, F, Op{lg.gh, F}, e.W(net, ls + GG_L_FF1_W), Epi().res(lg.gz2, E).obf(g.gb, E)));
+    const bool fused_ffn = e.fused_layer && cfg_fused_layer_ok(e, /*any_tokens=*/true);
+    if (fused_ffn) {
+      // dependent chain: ONE kernel (enc_layer.cu::enc_ffn_bwd_kernel) LayerNorm-2 backward -> dgrad ffn2 -> masks ->
+      // dgrad ffn1 -> + residual. The LayerNorm parameter gradients and the bf16 gz / gy tensors the weight-gradient
+      // GEMMs read come from the unfused LayerNorm-backward kernel, which now runs next to it on lane 2.
+      GG_TRY(e.fork(2));
+      GG_TRY(k_add_ln_bwd(g.ga, L.z2, L.mean2, L.rstd2, e.P(net, ls + GG_L_N2_W), lg.gz2, p > 0.f ? lg.gy2 : nullptr,
+                          nullptr, nullptr, rows, E, p, e.rng, site + 3, lg.lnp2, e.S(2)));
+      GG_TRY(k_ln_bwd_finish(lg.lnp2, rows, E, e.Gr(net, ls + GG_L_N2_W), e.Gr(net, ls + GG_L_N2_B), e.S(2)));
+      EncFfnBwdParams q;
+      memset(&q, 0, sizeof(q));
+      q.rows = rows;
+      q.dout = g.ga; q.z2 = L.z2; q.mean2 = L.mean2; q.rstd2 = L.rstd2; q.gamma2 = e.P(net, ls + GG_L_N2_W);
+      q.h = L.h;
+      q.w2t = e.sh[net].wt[ls + GG_L_FF2_W].p; q.ld_w2t = e.sh[net].wt[ls + GG_L_FF2_W].ld;
+      q.w1t = e.sh[net].wt[ls + GG_L_FF1_W].p; q.ld_w1t = e.sh[net].wt[ls + GG_L_FF1_W].ld;
+      q.drop_p = p; q.rng = e.rng; q.site = site + 3;
+      q.gh = lg.gh; q.gb = g.gb;
+      GG_TRY(k_enc_ffn_bwd(q, st));
+      GG_TRY(e.wgrad(E, F, rows, Op{dff, E}, Op{L.h, F}, e.Gr(net, ls + GG_L_FF2_W), F));
+      GG_TRY(e.bgrad(dff, E, rows, E, e.Gr(net, ls + GG_L_FF2_B)));
+      GG_TRY(e.wgrad(F, E, rows, Op{lg.gh, F}, Op{L.x1, E}, e.Gr(net, ls + GG_L_FF1_W), E));
+      GG_TRY(e.bgrad(lg.gh, F, rows, F, e.Gr(net, ls + GG_L_FF1_B)));
+    } else {
+      GG_TRY(k_add_ln_bwd(g.ga, L.z2, L.mean2, L.rstd2, e.P(net, ls + GG_L_N2_W), lg.gz2, p > 0.f ? lg.gy2 : nullptr,
+                          nullptr, nullptr, rows, E, p, e.rng, site + 3, lg.lnp2, st));
+      GG_TRY(e.fork(2));
+      GG_TRY(k_ln_bwd_finish(lg.lnp2, rows, E, e.Gr(net, ls + GG_L_N2_W), e.Gr(net, ls + GG_L_N2_B), e.S(2)));
+      GG_TRY(e.wgrad(E, F, rows, Op{dff, E}, Op{L.h, F}, e.Gr(net, ls + GG_L_FF2_W), F));
+      GG_TRY(e.bgrad(dff, E, rows, E, e.Gr(net, ls + GG_L_FF2_B)));
+      GG_TRY(e.dgrad(0, rows, F, E, Op{dff, E}, e.W(net, ls + GG_L_FF2_W),
+                     Epi().mask(L.h, F, keep_scale, 0.f).obf(lg.gh, F)));
+      GG_TRY(e.wgrad(F, E, rows, Op{lg.gh, F}, Op{L.x1, E}, e.Gr(net, ls + GG_L_FF1_W), E));
+      GG_TRY(e.bgrad(lg.gh, F, rows, F, e.Gr(net, ls + GG_L_FF1_B)));
+      GG_TRY(e.dgrad(0, rows, E, F, Op{lg.gh, F}, e.W(net, ls + GG_L_FF1_W), Epi().res(lg.gz2, E).obf(g.gb, E)));
+    }
     // x1 = LN1(x_in + drop(sa))
     GG_TRY(k_add_ln_bwd(g.gb, L.z1, L.mean1, L.rstd1, e.P(net, ls + GG_L_N1_W), lg.gz1, p > 0.f ? lg.gy1 : nullptr,
                         nullptr, nullptr, rows, E, p, e.rng, site + 1, lg.lnp1, st));
@@ -860,6 +895,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     GG_TRY(k_attention_bwd(a, st));
     GG_TRY(e.wgrad(3 * E, E, rows, Op{lg.gqkv, 3 * E}, Op{t.X[l], E}, e.Gr(net, ls + GG_L_IN_W), E));
     GG_TRY(e.bgrad(lg.gqkv, 3 * E, rows, 3 * E, e.Gr(net, ls + GG_L_IN_B)));
+    if (fused_ffn) GG_TRY(e.wait_lane(0, 2));  // lane 2's LayerNorm-2 backward has read g.ga: it may be overwritten
     GG_TRY(e.dgrad(0, rows, E, 3 * E, Op{lg.gqkv, 3 * E}, e.W(net, ls + GG_L_IN_W), Epi().res(lg.gz1, E).obf(g.ga, E)));
     GG_TRY(e.flush_grads());
   }

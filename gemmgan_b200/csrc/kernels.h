@@ -142,6 +142,8 @@ struct ShadowSeg {            // fp32 parameter sub-matrix -> bf16 shadow (padde
   int32_t col0, ncols;        // column range copied
   int64_t s_off;              // offset (elements) in the shadow buffer
   int64_t s_ld;
+  int32_t transpose;          // 1: the shadow holds the TRANSPOSE ([ncols, rows], pitch s_ld >= rows): K-major operand of
+  int32_t pad_;               //    the dgrad products of the fused backward kernels
 };
 // bump_step (optional): step counter incremented by this launch (the engine's optimizer step folds it in here)
 int k_refresh_shadows(const float* p, bf16* shadow, const ShadowSeg* segs_dev, int nseg, int max_rows,

@@ -160,6 +160,16 @@ __global__ void __launch_bounds__(256)
   const ShadowSeg s = segs[blockIdx.y];
   const float* src = p + s.p_off + s.col0;
   bf16* dst = shadow + s.s_off;
+  if (s.transpose) {  // dst[c, r] = src[r, c]: consecutive threads walk r (coalesced bf16 writes; the reads hit L2)
+    const int64_t total = static_cast<int64_t>(s.rows) * s.ncols;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t c = i / s.rows;
+      const int r = static_cast<int>(i % s.rows);
+      dst[c * s.s_ld + r] = __float2bfloat16_rn(src[static_cast<int64_t>(r) * s.cols + c]);
+    }
+    return;
+  }
   const bool vec = (s.ncols % 4 == 0) && (s.cols % 4 == 0) && (s.s_ld % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
   if (vec) {

@@ -85,6 +85,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3-D tiled load: c0 innermost. Used for MN-major operands viewed as [mn / 64][k][64]: ONE instruction fetches
+// several 64 x 64 atoms (each TMA instruction costs its issuing thread a few hundred cycles).
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // Same load issued by either CTA of a cta_group::2 pair: the data lands in the executing CTA's shared memory,
 // the transaction bytes are counted on the LEADER CTA's mbarrier (same offset, peer bit of the shared::cluster
 // address cleared), on which the leader's MMA thread waits for both halves of the stage.

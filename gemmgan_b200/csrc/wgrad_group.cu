@@ -62,6 +62,7 @@ struct Problem {
   unsigned* counters;   // [tiles_m * tiles_n] arrival counters (zero between launches)
   float* bias;          // [M] column sums of dY (bias gradient), or null
   float* bias_partial;  // [splits][M] when splits > 1
+  int a3d, b3d;         // operand map is the 3-D [mn / 64][k][64] view: one TMA instruction per tile instead of two
 };
 
 struct Params {
@@ -151,10 +152,18 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_group_kernel(const __grid_co
           uint8_t* a_dst = smem + s * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_TILE_BYTES;
           mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          if (P.p[k.pi].a3d) {
+            tma_load_3d(a_dst, ma, &full[s], 0, kb * BK, m0 / 64);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * ATOM_BYTES, ma, &full[s], m0 + 64 * j, kb * BK);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * ATOM_BYTES, ma, &full[s], m0 + 64 * j, kb * BK);
+          }
+          if (P.p[k.pi].b3d) {
+            tma_load_3d(b_dst, mb, &full[s], 0, kb * BK, n0 / 64);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * ATOM_BYTES, mb, &full[s], n0 + 64 * j, kb * BK);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * ATOM_BYTES, mb, &full[s], n0 + 64 * j, kb * BK);
+          }
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -379,6 +388,24 @@ int encode2d(CUtensorMap* map, const void* ptr, bool f32, int64_t inner, int64_t
   return GG_OK;
 }
 
+// MN-major operand [K rows, mn columns] (pitch ld) viewed as [mn / 64 blocks][K][64]: box = (64, 64, blocks_per_tile),
+// i.e. the 64 x 64 atoms of one tile in one instruction, laid out ATOM_BYTES apart. Needs mn % 64 == 0.
+int encode3d(CUtensorMap* map, const void* ptr, int64_t mn, int64_t k_rows, int64_t ld, int blocks_per_tile) {
+  EncodeTiledFn fn = encode_fn();
+  GG_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable");
+  GG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0 && ld >= mn && mn % 64 == 0,
+             "grouped wgrad operand %p (ld %lld) does not fit the 3-D view", ptr, (long long)ld);
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(k_rows), static_cast<cuuint64_t>(mn / 64)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(blocks_per_tile)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+  return GG_OK;
+}
+
 }  // namespace
 
 // Workspace layout: [GROUP_COUNTER_BYTES of arrival counters | partial tiles]. Only the counter region has to
@@ -449,8 +476,13 @@ int k_wgrad_group(const WgradItem* items, int n, void* workspace, int64_t worksp
     ctr_off += static_cast<int64_t>(p.tiles_m) * p.tiles_n * 4;
     GG_REQUIRE(ws_off <= workspace_bytes && ctr_off <= GROUP_COUNTER_BYTES,
                "grouped wgrad workspace too small (%lld > %lld)", (long long)ws_off, (long long)workspace_bytes);
-    GG_TRY_RC(encode2d(&P.mapA[oi], it.dy, false, it.M, it.K, it.ld_dy, BK));
-    GG_TRY_RC(encode2d(&P.mapB[oi], it.x, false, it.N, it.K, it.ld_x, BK));
+    static const bool use3d = [] { const char* v = getenv("GEMMGAN_WGRAD_3D"); return !(v && v[0] == '0'); }();
+    p.a3d = use3d && it.M % 64 == 0;
+    p.b3d = use3d && it.N % 64 == 0;
+    if (p.a3d) GG_TRY_RC(encode3d(&P.mapA[oi], it.dy, it.M, it.K, it.ld_dy, BM / 64));
+    else GG_TRY_RC(encode2d(&P.mapA[oi], it.dy, false, it.M, it.K, it.ld_dy, BK));
+    if (p.b3d) GG_TRY_RC(encode3d(&P.mapB[oi], it.x, it.N, it.K, it.ld_x, BN / 64));
+    else GG_TRY_RC(encode2d(&P.mapB[oi], it.x, false, it.N, it.K, it.ld_x, BK));
     if (p.tma_out) GG_TRY_RC(encode2d(&P.mapO[oi], it.out, true, it.N, it.M, it.ld, 32));
     else P.mapO[oi] = P.mapA[oi];
   }

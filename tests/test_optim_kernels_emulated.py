@@ -70,7 +70,8 @@ def test_optimizer_rejects_misaligned_buffers_and_unknown_kind(emu):
 
 class ShadowSeg(C.Structure):   # gemmgan_b200/csrc/kernels.h
     _fields_ = [("p_off", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("col0", C.c_int32),
-                ("ncols", C.c_int32), ("s_off", C.c_int64), ("s_ld", C.c_int64)]
+                ("ncols", C.c_int32), ("s_off", C.c_int64), ("s_ld", C.c_int64), ("transpose", C.c_int32),
+                ("pad_", C.c_int32)]
 
 
 def test_shadow_refresh_vector_and_scalar_paths(emu):
@@ -86,3 +87,10 @@ def test_shadow_refresh_vector_and_scalar_paths(emu):
     b = shadow[6 * 24:].view(5, 8)
     assert torch.equal(b[:, :7], flat[96:].view(5, 11)[:, 3:10].bfloat16()) and torch.all(b[:, 7:] == 7.0)
     assert bump.item() == 1.0
+    # transposed shadow (the K-major dgrad operands of the fused backward kernels): [5, 11] -> [11, 8-pitch]
+    flat2 = torch.randn(5 * 11)
+    sh2 = torch.full((11 * 8,), 7.0, dtype=torch.bfloat16)
+    seg2 = (ShadowSeg * 1)(ShadowSeg(0, 5, 11, 0, 11, 0, 8, 1, 0))
+    check(emu, emu.emu_refresh_shadows(flat2.data_ptr(), sh2.data_ptr(), C.addressof(seg2), 1, None))
+    t = sh2.view(11, 8)
+    assert torch.equal(t[:, :5], flat2.view(5, 11).t().bfloat16()) and torch.all(t[:, 5:] == 7.0)
