@@ -225,6 +225,21 @@ struct gg_engine {
   int dgrad(int lane, int rows, int in, int out, Op dY, Op Wt, const Epi& epi) const {
     return mm(lane, rows, in, out, dY, 0, Wt, 1, epi);
   }
+  // Y = X W^T with FP32 operands read in place and multiplied as TF32 (gg_gemm_desc.tf32_operands): X [rows, in]
+  // (pitch ldx), W [out, in] (pitch ldw) -- the gradient-penalty microbenchmark's fp32 profiles against the fp32 master
+  // weights: no bf16 copy of either
+  int linear_tf32(int lane, int rows, int out, int in, const float* X, int64_t ldx, const float* Wt, int64_t ldw,
+                  const Epi& epi) const {
+    gg_gemm_desc d;
+    memset(&d, 0, sizeof(d));
+    d.M = rows; d.N = out; d.nseg = 1;
+    d.seg[0].a = X; d.seg[0].b = Wt; d.seg[0].lda = ldx; d.seg[0].ldb = ldw; d.seg[0].K = in;
+    d.epi = epi.e;
+    d.workspace = splitk_l[L(lane)]; d.workspace_bytes = splitk_bytes;
+    d.impl = cfg.gemm_impl;
+    d.tf32_operands = 1;
+    return gemm_dispatch(&d, S(lane));
+  }
   // Weight / bias gradients feed nothing but the optimizer: they run on side lanes, ordered after
   // everything lane 0 has enqueued so far (their operands), and are joined at the end of the entry point.
   // dW[out, in] = dY^T X, fp32 into the gradient buffer (pitch ldw)
@@ -954,12 +969,22 @@ static int gen_forward(gg_engine& e, const float* z, float p, float* out_f32, in
 }
 
 // critic trunk forward on npass row groups; nx = number of gene matrices in xfr (1: fake, 2: fake+real)
-static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, int R, const float* alpha) {
+// fake_f32 / real_f32 (both non-null): the first layer reads those fp32 [B, G] tensors directly (TF32) instead of the bf16
+// [fake; real] matrix x
+static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, int R, const float* alpha,
+                                const float* fake_f32 = nullptr, const float* real_f32 = nullptr) {
   const gg_model_cfg& c = e.cfg;
   TrunkBufs& t = e.tb;
   cudaStream_t st = e.S(0);
   const int B = c.B, H = c.H, G = c.G, E = c.E, net = GG_NET_DISC;
-  GG_TRY(e.linear(0, nx * B, H, G, Op{x, e.Gp}, e.W(net, GG_P_TR0_W), Epi().of32(t.a1x, H)));
+  if (fake_f32 && real_f32) {
+    const int64_t ldw = static_cast<int64_t>(G) + (e.cond ? E : 0);
+    GG_TRY(e.linear_tf32(0, B, H, G, fake_f32, G, e.P(net, GG_P_TR0_W), ldw, Epi().of32(t.a1x, H)));
+    GG_TRY(e.linear_tf32(0, B, H, G, real_f32, G, e.P(net, GG_P_TR0_W), ldw,
+                         Epi().of32(t.a1x + static_cast<int64_t>(B) * H, H)));
+  } else {
+    GG_TRY(e.linear(0, nx * B, H, G, Op{x, e.Gp}, e.W(net, GG_P_TR0_W), Epi().of32(t.a1x, H)));
+  }
   const float* a1c = nullptr;
   if (e.cond) {
     const Op cv = cond_vec(e, net);
@@ -979,7 +1004,7 @@ static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, 
 // `fake_lane`: lane that is producing the fake rows of xfr (joined before the trunk reads them); the
 // critic tower (conditioning only) and the Gram matrix (weights only) do not wait for it.
 static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int fake_lane, int gp_lane = 0,
-                           int save_reps = 0) {
+                           int save_reps = 0, const float* fake_f32 = nullptr, const float* real_f32 = nullptr) {
   const gg_model_cfg& c = e.cfg;
   TrunkBufs& t = e.tb;
   const int B = c.B, H = c.H, G = c.G, net = GG_NET_DISC;
@@ -989,7 +1014,7 @@ static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int
   GG_TRY(e.mm(2, H, H, G, W1x, 0, W1x, 0, Epi().of32(t.Mg, H).obf(t.Mgb, H)));
   if (e.cond) GG_TRY(tower_forward(e, net, R, p, 0, save_reps));
   GG_TRY(e.join(fake_lane));
-  GG_TRY(critic_trunk_forward(e, e.xfr, 2, 3, R, alpha));
+  GG_TRY(critic_trunk_forward(e, e.xfr, 2, 3, R, alpha, fake_f32, real_f32));
   // The penalty's own chain (u2 -> u1 -> y = u1 M -> row norms -> losses) feeds only the loss statistics and the
   // GP weight gradients: in the training step it runs on `gp_lane` next to the backward chain of lane 0.
   if (gp_lane != 0) GG_TRY(e.fork(gp_lane));
@@ -1383,9 +1408,22 @@ extern "C" int gg_engine_gp_step(gg_engine* e, const float* real_f32, const floa
   const gg_model_cfg& c = e->cfg;
   TrunkBufs& t = e->tb;
   const int B = c.B, H = c.H, G = c.G, net = GG_NET_DISC;
-  GG_TRY(k_cast_f32_bf16(fake_f32, G, e->xfr, e->Gp, B, G, st));
-  GG_TRY(k_cast_f32_bf16(real_f32, G, e->xfr + static_cast<int64_t>(B) * e->Gp, e->Gp, B, G, st));
-  GG_TRY(disc_forward_gp(*e, 1, 0.f, alpha, 0));
+  // The only [B, G] work of the penalty is critic layer 1 on real and fake. Default: cast both to bf16 once (as the
+  // training step does with its resident bf16 [fake; real] matrix), then one bf16 GEMM. GEMMGAN_GP_TF32=1: read both
+  // fp32 tensors in place with TF32 tensor-core GEMMs against the fp32 master weights -- no cast pass, 8 B G bytes of
+  // HBM traffic in all, but MEASURED SLOWER (B = 16384, G = 20000: 1.47 ms vs 1.15 ms): every 128-row tile re-streams
+  // the fp32 weight matrix (20 MB) from L2, and the L2 -> shared-memory fabric (~7 TB/s), not HBM, becomes the bound;
+  // it needs the weight k-blocks multicast across a cluster of M-tiles to pay off.
+  static const bool gp_tf32 = [] { const char* v = getenv("GEMMGAN_GP_TF32"); return v && v[0] == '1'; }();
+  const bool direct = gp_tf32 && c.gemm_impl == GG_IMPL_TCGEN05 && G % 4 == 0 &&
+                      ((reinterpret_cast<uintptr_t>(real_f32) | reinterpret_cast<uintptr_t>(fake_f32)) & 15) == 0;
+  if (direct) {
+    GG_TRY(disc_forward_gp(*e, 1, 0.f, alpha, 0, 0, 0, fake_f32, real_f32));
+  } else {
+    GG_TRY(k_cast_f32_bf16(fake_f32, G, e->xfr, e->Gp, B, G, st));
+    GG_TRY(k_cast_f32_bf16(real_f32, G, e->xfr + static_cast<int64_t>(B) * e->Gp, e->Gp, B, G, st));
+    GG_TRY(disc_forward_gp(*e, 1, 0.f, alpha, 0));
+  }
   const Op W1x = e->W(net, GG_P_TR0_W), W2 = e->W(net, GG_P_TR1_W);
   const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;
   float* gw3 = e->Gr(net, GG_P_FIN_W);

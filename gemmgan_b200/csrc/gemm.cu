@@ -37,6 +37,7 @@ struct GemmArgs {
   int splits;
   int tma_out_bf16, tma_out_f32;  // outputs written by TMA stores (alignment permitting)
   int lean;                       // >= 0: feature set of the compact epilogue (see lean_tile_epilogue); -1: generic
+  int tf32;                       // operands are fp32 in memory, multiplied as TF32 (K-major only): a k-block is 32 elements
   long long* trace;               // diagnostics: per-role clock64() stamps of CTA `trace_cta` (gg_gemm_set_trace)
   int trace_cta;
   unsigned long long* stamp;      // measurement: {min start, max end} of this launch in %globaltimer ns, or null
@@ -290,8 +291,9 @@ __global__ void __launch_bounds__(TileCfg<BN, STAGES, EPIW, PAIR>::THREADS, Tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kb0 = (g.K0 + BK - 1) / BK;
-  const int kb1 = (g.K1 + BK - 1) / BK;
+  const int BKe = g.tf32 ? BK / 2 : BK;  // elements per 128-byte k-block row
+  const int kb0 = (g.K0 + BKe - 1) / BKe;
+  const int kb1 = (g.K1 + BKe - 1) / BKe;
   const int total_kb = kb0 + kb1;
   const int tiles_n = (g.N + BN - 1) / BN;
   const int tiles_m = (g.M + TILE_M - 1) / TILE_M;
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(TileCfg<BN, STAGES, EPIW, PAIR>::THREADS, Tile
           mbar_wait(&empty[s], ph ^ 1);
           if (tr && tn_p < TRACE_ROLE_STRIDE) tr[0 * TRACE_ROLE_STRIDE + tn_p++] = clock64();
           const bool second = kb >= kb0;
-          const int kloc = (second ? kb - kb0 : kb) * BK;
+          const int kloc = (second ? kb - kb0 : kb) * BKe;
           const CUtensorMap* ma = second ? &tmA1 : &tmA0;
           const CUtensorMap* mb = second ? &tmB1 : &tmB0;
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(TileCfg<BN, STAGES, EPIW, PAIR>::THREADS, Tile
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {  // PAIR: the leader CTA issues the MMAs of both
-      const uint32_t idesc = make_idesc_bf16(TILE_M, BN, g.a_mn, g.b_mn);
+      const uint32_t idesc = g.tf32 ? make_idesc_tf32(TILE_M, BN) : make_idesc_bf16(TILE_M, BN, g.a_mn, g.b_mn);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -419,6 +421,7 @@ __global__ void __launch_bounds__(TileCfg<BN, STAGES, EPIW, PAIR>::THREADS, Tile
             const uint64_t bd = g.b_mn ? make_smem_desc(b_base + k * 2048, ATOM_BYTES, 1024)
                                        : make_smem_desc(b_base + k * 32, 16, 1024);
             if (PAIR) tc_mma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            else if (g.tf32) tc_mma_tf32(d_tmem, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
             else tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           if (PAIR) tc_commit_pair(&empty[s]);  // frees the stage in both CTAs
@@ -816,7 +819,7 @@ static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t
     g_prof.flops += 2.0 * args.M * args.N * (static_cast<double>(args.K0) + args.K1);
     g_prof.launches += 1;
     const int ob = (args.epi.out_bf16 ? 2 : 0) + (args.epi.out_f32 ? 4 : 0);
-    g_prof.bytes += 2.0 * (static_cast<double>(args.M) + args.N) * (static_cast<double>(args.K0) + args.K1) +
+    g_prof.bytes += (args.tf32 ? 4.0 : 2.0) * (static_cast<double>(args.M) + args.N) * (static_cast<double>(args.K0) + args.K1) +
                     static_cast<double>(ob) * args.M * args.N;
     g_prof.rec.push_back(GemmRecord{args.M, args.N, args.K0, args.K1, PAIR ? -BN : BN, args.splits, args.a_mn, args.b_mn, ob});
     GG_CUDA_CHECK(prof_record(e0, stream));
@@ -848,6 +851,7 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
   GG_REQUIRE(d->epi.drop_p == 0.f || d->epi.rng, "dropout needs an rng state pointer");
 
   if (d->impl == GG_IMPL_SIMT_F32) {
+    GG_REQUIRE(!d->tf32_operands, "the CUDA-core check path takes bf16 operands");
     const gg_gemm_seg& s0 = d->seg[0];
     const gg_gemm_seg& s1 = d->seg[1];
     const int chunks = ceil_div(d->N, 32);
@@ -861,6 +865,9 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
     return GG_OK;
   }
   GG_REQUIRE(d->impl == GG_IMPL_TCGEN05, "unknown GEMM impl %d", d->impl);
+  const bool tf32 = d->tf32_operands != 0;
+  const int BKh = tf32 ? BK / 2 : BK;
+  GG_REQUIRE(!tf32 || (!d->a_mn_major && !d->b_mn_major), "fp32 (TF32) operands must be K-major");
 
   int bn = d->block_n;
   // Tile configuration (measured on B200, tests/gpu_gemm_bench.py -> profiles/r01_gemm_shapes_v6.log). A stage of
@@ -870,9 +877,9 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
   //  * N >= 512 with enough 128 x 256 tiles for every SM: 256-wide single-CTA tiles;
   //  * otherwise 128-wide tiles (more, smaller tiles for the short / narrow problems).
   bool pair = false;
-  const int kb_all = ceil_div(d->seg[0].K, BK) + (d->nseg > 1 ? ceil_div(d->seg[1].K, BK) : 0);
-  if (d->pair > 0) pair = true;
-  else if (d->pair == 0 && pair_enabled() && (bn == 0 || bn == 256) && d->N >= 256 && d->M >= 256 && kb_all >= 32) {
+  const int kb_all = ceil_div(d->seg[0].K, BKh) + (d->nseg > 1 ? ceil_div(d->seg[1].K, BKh) : 0);
+  if (d->pair > 0 && !tf32) pair = true;
+  else if (d->pair == 0 && !tf32 && pair_enabled() && (bn == 0 || bn == 256) && d->N >= 256 && d->M >= 256 && kb_all >= 32) {
     const int64_t tiles2 = static_cast<int64_t>(ceil_div(d->M, 256)) * ceil_div(d->N, 256);
     pair = tiles2 >= 56 || (d->workspace != nullptr && tiles2 * (kb_all / 4) >= 56);
   }
@@ -887,10 +894,10 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
   for (int s = 0; s < 2; ++s) {
     const gg_gemm_seg& sg = d->seg[s < d->nseg ? s : 0];
     int rc;
-    if (!d->a_mn_major) rc = encode_map(&maps[2 * s], sg.a, sg.K, d->M, sg.lda, BM);
+    if (!d->a_mn_major) rc = encode_map(&maps[2 * s], sg.a, sg.K, d->M, sg.lda, BM, tf32);
     else rc = encode_map(&maps[2 * s], sg.a, d->M, sg.K, sg.lda, BK);
     if (rc) return rc;
-    if (!d->b_mn_major) rc = encode_map(&maps[2 * s + 1], sg.b, sg.K, d->N, sg.ldb, pair ? bn / 2 : bn);
+    if (!d->b_mn_major) rc = encode_map(&maps[2 * s + 1], sg.b, sg.K, d->N, sg.ldb, pair ? bn / 2 : bn, tf32);
     else rc = encode_map(&maps[2 * s + 1], sg.b, d->N, sg.K, sg.ldb, BK);
     if (rc) return rc;
   }
@@ -903,6 +910,7 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
   args.a_mn = d->a_mn_major;
   args.b_mn = d->b_mn_major;
   args.epi = d->epi;
+  args.tf32 = tf32 ? 1 : 0;
   args.partial = reinterpret_cast<float*>(d->workspace);
   args.trace = g_trace_buf;
   args.trace_cta = g_trace_cta;
@@ -915,7 +923,7 @@ int gemm_dispatch(const gg_gemm_desc* d, cudaStream_t stream) {
     ++g_stamp_next;
   }
 
-  const int total_kb = ceil_div(args.K0, BK) + ceil_div(args.K1, BK);
+  const int total_kb = ceil_div(args.K0, BKh) + ceil_div(args.K1, BKh);
   const int tiles = ceil_div(d->M, pair ? 2 * BM : BM) * ceil_div(d->N, bn);
   int splits = 1;
   if (d->force_splits > 0) {

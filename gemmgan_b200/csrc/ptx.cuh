@@ -216,6 +216,17 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with fp32 operands in shared memory read as TF32 (kind::tf32: K = 8 per instruction = the same 32 bytes of a
+// 128-byte swizzle row as 16 bf16), fp32 accumulate.
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -258,6 +269,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_noswizzle(uint32_t smem_addr,
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (sm_100)
+  return d;
+}
+// Instruction descriptor for kind::tf32 (A / B format code 2 = tf32), fp32 D, both operands K-major.
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;   // D format: f32
+  d |= 2u << 7;   // A format: tf32
+  d |= 2u << 10;  // B format: tf32
+  d |= static_cast<uint32_t>(N >> 3) << 17;
+  d |= static_cast<uint32_t>(M >> 4) << 24;
   return d;
 }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.

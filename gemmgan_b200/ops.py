@@ -37,8 +37,9 @@ def gemm(
     d.M, d.N = M, N
     segs = [(a, b)] + ([(a2, b2)] if a2 is not None else [])
     d.nseg = len(segs)
+    tf32 = a.dtype == torch.float32     # fp32 operands are multiplied as TF32 (gg_gemm_desc.tf32_operands)
     for i, (x, w) in enumerate(segs):
-        assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+        assert x.dtype == w.dtype and x.dtype in (torch.bfloat16, torch.float32) and (x.dtype == torch.float32) == tf32
         assert x.stride(-1) == 1 and w.stride(-1) == 1
         K = x.shape[0] if a_mn else x.shape[1]
         Kb = w.shape[0] if b_mn else w.shape[1]
@@ -69,6 +70,7 @@ def gemm(
     if workspace is not None:
         d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     d.impl, d.force_splits, d.block_n, d.light, d.pair = impl, splits, block_n, light, pair
+    d.tf32_operands = int(tf32)
     _lib.check(L.gg_gemm_bf16(C.byref(d), _stream()))
 
 

@@ -34,7 +34,7 @@ extern "C" {
 #define GG_ERR_CUDA (-3)
 #define GG_ERR_WORKSPACE (-4)
 
-#define GG_ABI_VERSION 2
+#define GG_ABI_VERSION 3
 
 const char* gg_last_error(void);
 int gg_abi_version(void);
@@ -113,6 +113,9 @@ typedef struct gg_gemm_desc {
                                tiles, no split-K) used for short-K products with many tiles */
   int32_t pair;             /* 0 = heuristic; 1 = force, -1 = forbid the CTA-pair configuration (tcgen05 cta_group::2:
                                256 x 256 tiles over the two SMs of a TPC, each CTA stages half of the B tile) */
+  int32_t tf32_operands;    /* 1: A and B are FP32 in memory (pitches in fp32 elements, multiples of 4, both K-major) and
+                               are multiplied as TF32 (tcgen05.mma kind::tf32, fp32 accumulate): fp32 tensors are read
+                               once, with no bf16 copy (the gradient-penalty microbenchmark's real / fake profiles) */
 } gg_gemm_desc;
 
 int gg_gemm_bf16(const gg_gemm_desc* desc, void* stream);

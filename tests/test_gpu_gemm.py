@@ -228,3 +228,24 @@ def test_colsum_group_matches_reference_and_is_deterministic():
         torch.cuda.synchronize()
         for p, f in zip(probs, first):
             assert torch.equal(p[1], f)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 1000, 0), (2048, 256, 18868, 256), (300, 130, 97 * 4, 128),
+                                      (128, 64, 36, 64)])
+def test_gemm_with_fp32_operands_runs_as_tf32(M, N, K, bn):
+    """gg_gemm_desc.tf32_operands: fp32 A / B read in place (no bf16 copy), multiplied on the tensor cores as TF32
+    (10-bit mantissa), fp32 accumulate. Against fp64 torch: relative error of the TF32 rounding of the operands."""
+    import torch
+    from gemmgan_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g) * K ** -0.5
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ws = torch.empty(64 << 20, device="cuda", dtype=torch.uint8)
+    ops.gemm(a, b, bias=bias, out_f32=out, block_n=bn, workspace=ws)
+    torch.cuda.synchronize()
+    want = (a.double() @ b.double().t() + bias.double()).float()
+    err = (out - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-3, err                       # (bf16 operands give ~1e-2 here)

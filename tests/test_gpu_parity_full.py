@@ -337,3 +337,46 @@ def test_fused_encoder_layer_engine_matches_the_seven_launch_path(variant, dropo
     assert m["dgrads"] < 5e-2 and m["ggrads"] < 8e-2, m   # (0.014 - 0.028 / 0.036 - 0.058 measured)
     assert torch.allclose(a["stats"][:5], b["stats"][:5], rtol=2e-2, atol=2e-3)
     assert torch.allclose(a["gstats"][4], b["gstats"][4], rtol=3e-2, atol=3e-3)
+
+
+@pytest.mark.parametrize("B,G", [(256, 1000), (512, 5000)])
+def test_gp_step_value_and_gradients_match_autograd(B, G):
+    """gg_engine_gp_step (BASELINE config 5: the gradient penalty alone, value + gp_weight * dGP/d{W1, W2, w3}) on the
+    unconditional critic against float64 autograd (gradient_penalty + the GP part of disc_loss.backward(),
+    src/vanilla_gan_unconditional.py:304-327, :381). Critic layer 1 reads the fp32 real / fake profiles in place on the
+    tensor cores as TF32; everything downstream is the Gram-matrix formulation on bf16 operands."""
+    import vanilla_gan_unconditional as m
+
+    torch.manual_seed(3)
+    t = m.WGAN_GP_nocond(input_dims=G, latent_dims=256, vocab_sizes=[], generator_dims=[256, 256, G],
+                         discriminator_dims=[256, 256, 1], optimizer="adam")
+    t.build_WGAN_GP_nocond()
+    t.init_train()
+    dev = t.device
+    g = torch.Generator(device=dev).manual_seed(1)
+    real = torch.randn(B, G, device=dev, generator=g)
+    fake = torch.randn(B, G, device=dev, generator=g)
+    alpha = torch.rand(B, 1, device=dev, generator=g)
+    eng = t._engine(B)
+    gp = torch.zeros((), device=dev)
+    t._flat_disc.grads.zero_()
+    eng.gp_step(real, fake, alpha, gp)
+    torch.cuda.synchronize()
+    d = t.disc
+    W1 = d.discriminator[0][0].weight.detach().double().requires_grad_(True)
+    b1 = d.discriminator[0][0].bias.detach().double()
+    W2 = d.discriminator[1][0].weight.detach().double().requires_grad_(True)
+    b2 = d.discriminator[1][0].bias.detach().double()
+    w3 = d.final_layer.weight.detach().double().requires_grad_(True)
+    a = alpha.double()
+    xh = (a * real.double() + (1 - a) * fake.double()).requires_grad_(True)
+    out = torch.relu(torch.relu(xh @ W1.t() + b1) @ W2.t() + b2) @ w3.t()
+    (gr,) = torch.autograd.grad(out.sum(), xh, create_graph=True)
+    ref = ((gr.norm(dim=1) - 1) ** 2).mean()
+    (10.0 * ref).backward()
+    assert abs(gp.item() - ref.item()) <= 1e-2 * abs(ref.item())
+    for name, p_ref, p_got in (("W1", W1, d.discriminator[0][0].weight), ("W2", W2, d.discriminator[1][0].weight),
+                               ("w3", w3, d.final_layer.weight)):
+        e = fro(p_got.grad, p_ref.grad.float())
+        print(f"gp_step B={B} G={G} {name}: rel fro {e:.4f}")
+        assert e < 6e-2, (name, e)          # ReLU mask flips at bf16 / TF32 precision, as in check_grads
