@@ -144,7 +144,7 @@ class WGAN_GP(TrainerBase):
         if self.isTrain:
             self.init_train()
         for epoch in range(epochs):
-            self._epoch_lr_decay(epoch, 100)
+            self._epoch_lr_decay(epoch, getattr(self, '_lr_decay_every', 100))
             self.epoch = epoch
             d_sum, g_sum, n = 0.0, 0.0, 0
             for i, (data, nxt) in enumerate(self._lookahead(train_data)):

@@ -4,6 +4,7 @@ from __future__ import annotations
 import ctypes as C
 
 VARIANT_VANILLA, VARIANT_FILM, VARIANT_PAPER, VARIANT_CROSS, VARIANT_CONCAT, VARIANT_IMG, VARIANT_LABEL = 0, 1, 2, 3, 4, 5, 6
+VARIANT_ATTN = 7   # conditional_gan_attention.py
 OPT_RMSPROP, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 NET_GEN, NET_DISC = 0, 1
 PHASE_STAGE0, PHASE_NO_JOIN = 16, 64
@@ -13,6 +14,7 @@ P_FILM_W, P_FILM_B, P_TEXT_W, P_TEXT_B, P_PATCH_W, P_PATCH_B, P_CLS = range(7)
 P_LAYER0 = 7
 P_PENC_LN_W, P_PENC_LN_B = P_FILM_W, P_FILM_B   # GG_VARIANT_IMG: patch-encoder LayerNorm vectors
 P_EMB0, P_EMB1 = P_TEXT_W, P_PATCH_W             # GG_VARIANT_LABEL: the two embedding tables
+P_BN_W, P_BN_B = P_FILM_W, P_FILM_B              # GG_VARIANT_ATTN (generator): BatchNorm1d weight / bias
 (L_IN_W, L_IN_B, L_OUT_W, L_OUT_B, L_FF1_W, L_FF1_B, L_FF2_W, L_FF2_B,
  L_N1_W, L_N1_B, L_N2_W, L_N2_B) = range(12)
 L_COUNT = 12
@@ -116,6 +118,7 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_set_lanes.argtypes = [vp, i32]
     L.gg_engine_set_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.gg_engine_set_labels.argtypes = [vp, vp, vp, vp]
+    L.gg_engine_set_batchnorm.argtypes = [vp, vp, vp, C.c_float, C.c_float]
     L.gg_engine_disc_grads.argtypes = [vp, vp, vp, i32, vp]
     L.gg_engine_gen_grads.argtypes = [vp, vp, i32, vp]
     L.gg_engine_disc_grads_phase.argtypes = [vp, vp, vp, i32, i32, vp]
@@ -163,7 +166,7 @@ def declare(L: C.CDLL) -> None:
 
 EXPORTS = [
     "gg_last_error", "gg_abi_version", "gg_check_device", "gg_gemm_bf16", "gg_engine_workspace_bytes",
-    "gg_engine_create", "gg_engine_destroy", "gg_engine_set_lanes", "gg_engine_refresh_shadows", "gg_engine_set_batch", "gg_engine_set_labels",
+    "gg_engine_create", "gg_engine_destroy", "gg_engine_set_lanes", "gg_engine_refresh_shadows", "gg_engine_set_batch", "gg_engine_set_labels", "gg_engine_set_batchnorm",
     "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_disc_grads_phase", "gg_engine_gen_grads_phase", "gg_engine_optim_step", "gg_engine_generate",
     "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_gp_step", "gg_masked_mean_rows", "gg_gather_rows", "gg_engine_lanes_signal", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",

@@ -810,4 +810,111 @@ int k_gather_rows(const float* src, int64_t ld_src, const int64_t* index, float*
   return GG_OK;
 }
 
+// ---------------------------------------------------------------------------------------- BatchNorm1d over the batch
+// conditional_gan_attention.py:108, :126 (generator only): y = (x - mean_B) / sqrt(var_B + eps) * gamma + beta over the
+// rows of x [B, E] in training mode (biased batch variance; the running statistics take the UNBIASED one, torch
+// nn.BatchNorm1d), the running statistics in eval mode. One block per 32 columns, the 8 warps stride over the rows and
+// meet in shared memory in a fixed order (deterministic); x is a few hundred KB and stays in L2 between the passes.
+__device__ __forceinline__ float bn_block_sum(float v, float (*red)[33]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  red[w][lane] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i][lane];
+  return s;
+}
+
+__global__ void __launch_bounds__(256)
+    bn_fwd_kernel(const bf16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float* __restrict__ run_mean, float* __restrict__ run_var, float momentum, float eps, int training,
+                  bf16* __restrict__ y, int64_t ldy, float* __restrict__ mean_out, float* __restrict__ rstd_out, int B,
+                  int E) {
+  pdl_entry();
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const bool ok = col < E;
+  float mean, rstd;
+  if (training) {
+    float s = 0.f;
+    if (ok)
+      for (int r = w; r < B; r += 8) s += __bfloat162float(x[r * ldx + col]);
+    mean = bn_block_sum(s, red) / static_cast<float>(B);
+    float ss = 0.f;
+    if (ok)
+      for (int r = w; r < B; r += 8) {
+        const float d = __bfloat162float(x[r * ldx + col]) - mean;
+        ss += d * d;
+      }
+    ss = bn_block_sum(ss, red);
+    rstd = rsqrtf(ss / static_cast<float>(B) + eps);
+    if (ok && w == 0 && run_mean) {
+      run_mean[col] = (1.f - momentum) * run_mean[col] + momentum * mean;
+      run_var[col] = (1.f - momentum) * run_var[col] + momentum * ss / static_cast<float>(B - 1);
+    }
+  } else {
+    mean = ok ? run_mean[col] : 0.f;
+    rstd = ok ? rsqrtf(run_var[col] + eps) : 0.f;
+  }
+  if (!ok) return;
+  if (w == 0) {
+    mean_out[col] = mean;
+    rstd_out[col] = rstd;
+  }
+  const float g = gamma[col] * rstd, b = beta[col];
+  for (int r = w; r < B; r += 8) y[r * ldy + col] = __float2bfloat16((__bfloat162float(x[r * ldx + col]) - mean) * g + b);
+}
+
+// dx = gamma * rstd * (dy - mean_B(dy) - xhat * mean_B(dy * xhat)), dgamma = sum dy * xhat, dbeta = sum dy (training mode)
+__global__ void __launch_bounds__(256)
+    bn_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                  bf16* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int E) {
+  pdl_entry();
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const bool ok = col < E;
+  const float mu = ok ? mean[col] : 0.f, rs = ok ? rstd[col] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  if (ok)
+    for (int r = w; r < B; r += 8) {
+      const float d = __bfloat162float(dy[r * lddy + col]);
+      s1 += d;
+      s2 += d * (__bfloat162float(x[r * ldx + col]) - mu) * rs;
+    }
+  s1 = bn_block_sum(s1, red);
+  s2 = bn_block_sum(s2, red);
+  if (!ok) return;
+  if (w == 0) {
+    dgamma[col] = s2;
+    dbeta[col] = s1;
+  }
+  const float inv_b = 1.f / static_cast<float>(B), g = gamma[col] * rs;
+  for (int r = w; r < B; r += 8) {
+    const float xh = (__bfloat162float(x[r * ldx + col]) - mu) * rs;
+    dx[r * lddx + col] = __float2bfloat16(g * (__bfloat162float(dy[r * lddy + col]) - s1 * inv_b - xh * s2 * inv_b));
+  }
+}
+
+int k_bn_fwd(const bf16* x, int64_t ldx, const float* gamma, const float* beta, float* run_mean, float* run_var,
+             float momentum, float eps, int training, bf16* y, int64_t ldy, float* mean_out, float* rstd_out, int B, int E,
+             cudaStream_t st) {
+  GG_REQUIRE(!training || B > 1, "BatchNorm1d in training mode needs more than one row per channel (torch raises too)");
+  GG_REQUIRE(training || (run_mean && run_var), "eval-mode BatchNorm needs the running statistics");
+  launch_k(bn_fwd_kernel, static_cast<unsigned>((E + 31) / 32), 256, 0, st, x, ldx, gamma, beta, run_mean, run_var, momentum,
+           eps, training, y, ldy, mean_out, rstd_out, B, E);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+int k_bn_bwd(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, const float* mean, const float* rstd,
+             const float* gamma, bf16* dx, int64_t lddx, float* dgamma, float* dbeta, int B, int E, cudaStream_t st) {
+  launch_k(bn_bwd_kernel, static_cast<unsigned>((E + 31) / 32), 256, 0, st, dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx,
+           dgamma, dbeta, B, E);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 }  // namespace gg

@@ -126,6 +126,12 @@ struct gg_engine {
   bool label = false;   // benchmark_generative_model.py: the conditioning is two gathered embedding rows (a concat-style
                         // engine: `concat` is set too; the staged vector / encoder GEMM become labels / a gather)
   int64_t* labels = nullptr;  // [2, B]
+  // conditional_gan_attention.py: c = single-query MHA(text vector -> patches) [+ BatchNorm1d in the generator]
+  bool attn = false;
+  float *bn_run_mean = nullptr, *bn_run_var = nullptr;  // caller-owned running statistics (gg_engine_set_batchnorm)
+  float bn_momentum = 0.1f, bn_eps = 1e-5f;
+  float *bn_mean = nullptr, *bn_rstd = nullptr;  // statistics the last generator forward normalised with
+  int bn_training = 1;
   bool cond = false, paper = false, film = false;  // paper: cross-attention tail; film: FiLM modulation of the patches
   // staged inputs
   bf16 *xfr, *patches, *text, *zbf, *xin;
@@ -314,7 +320,7 @@ static bool slot_matrix_shape(const gg_model_cfg& c, int net, int slot, int* row
   const int E = c.E, F = c.ffn, condw = c.variant == GG_VARIANT_VANILLA ? 0 : E;
   if (c.variant == GG_VARIANT_LABEL && slot < GG_P_TR0_W) return false;  // embedding tables are gathered in fp32
   if (slot == GG_P_FILM_W) {  // (the IMG variant keeps its patch-encoder LayerNorm vectors in the FiLM slots)
-    if (c.variant == GG_VARIANT_IMG) return false;
+    if (c.variant == GG_VARIANT_IMG || c.variant == GG_VARIANT_ATTN) return false;
     *rows = 2 * c.Dp; *cols = c.Dt; return true;
   }
   if (slot == GG_P_TEXT_W) { *rows = E; *cols = c.Dt; return true; }
@@ -491,6 +497,10 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
     g.dpe = ar.take<bf16>(B * P * E);
     g.dmod = ar.take<bf16>(B * P * c.Dp);
     g.dgb = ar.take<bf16>(B * 2 * c.Dp);
+    if (e.attn) {
+      e.bn_mean = ar.take<float>(E);
+      e.bn_rstd = ar.take<float>(E);
+    }
     if (e.img) {
       g.dpe_z = ar.take<bf16>(B * P * E);
       g.dpe_h = ar.take<bf16>(B * P * E);
@@ -561,7 +571,9 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
 }
 
 static int validate_cfg(const gg_model_cfg& c) {
-  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_LABEL, "unknown variant %d", c.variant);
+  GG_REQUIRE(c.variant >= GG_VARIANT_VANILLA && c.variant <= GG_VARIANT_ATTN, "unknown variant %d", c.variant);
+  GG_REQUIRE(c.variant != GG_VARIANT_ATTN || (c.dropout_p == 0.f && c.T == 1),
+             "the attention variant has no dropout and one text vector per sample");
   GG_REQUIRE(c.B > 0 && c.G > 0 && c.L > 0 && c.H > 0, "bad sizes B=%d G=%d L=%d H=%d", c.B, c.G, c.L, c.H);
   GG_REQUIRE(c.L % 8 == 0 && c.H % 8 == 0, "latent and hidden widths must be multiples of 8");
   if (c.variant == GG_VARIANT_LABEL) {
@@ -587,6 +599,7 @@ static void derive(gg_engine& e) {
   e.label = c.variant == GG_VARIANT_LABEL;
   e.concat = c.variant == GG_VARIANT_CONCAT || e.label;
   e.img = c.variant == GG_VARIANT_IMG;
+  e.attn = c.variant == GG_VARIANT_ATTN;
   e.S_ = e.cond ? c.P + 1 : 1;
   e.Gp = static_cast<int>(round_up64(c.G, 8));
   e.F = c.ffn;
@@ -615,6 +628,35 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
     return k_embed_gather(e.P(net, GG_P_EMB0), e.P(net, GG_P_EMB1), e.labels, e.labels + B, Dt, Dp, t.c, B, E / 2, st);
   if (e.concat)  // conditional_gan_concat.py:135-139 / :182-186: c = encoder(text) (or of the masked mean patch)
     return e.linear(ln, B, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W), Epi().bias(e.P(net, GG_P_TEXT_B)).obf(t.c, E));
+  if (e.attn) {
+    // conditional_gan_attention.py:113-126 / :154-161: query = text_encoder(text) [B, 1, E], keys / values =
+    // patches_encoder(patches) [B, P, E] under the key-padding mask, one MultiheadAttention; BatchNorm1d in the generator
+    const Op Wa = e.W(net, GG_P_P2T_IN_W);
+    const float* ba = e.P(net, GG_P_P2T_IN_B);
+    GG_TRY(e.linear(ln, B, E, Dt, Op{e.text, Dt}, e.W(net, GG_P_TEXT_W), Epi().bias(e.P(net, GG_P_TEXT_B)).obf(t.te, E)));
+    GG_TRY(e.linear(ln, B * P, E, Dp, Op{e.patches, Dp}, e.W(net, GG_P_PATCH_W),
+                    Epi().bias(e.P(net, GG_P_PATCH_B)).obf(t.X[0], E)));
+    GG_TRY(e.linear(ln, B, E, E, Op{t.te, E}, Wa, Epi().bias(ba).obf(t.qp, E)));
+    GG_TRY(e.linear(ln, B * P, 2 * E, E, Op{t.X[0], E}, Op{Wa.p + static_cast<int64_t>(E) * Wa.ld, Wa.ld},
+                    Epi().bias(ba ? ba + E : nullptr).obf(t.kvp, 2 * E)));
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = t.qp; a.ldq = E; a.q_mod = B;
+    a.k = t.kvp; a.v = t.kvp + E; a.ldkv = 2 * E; a.kv_mod = B;
+    a.mask = e.mask_s; a.mask_mod = B;  // [B, P]: the padding flags as they came (no CLS column in this variant)
+    a.nb = B; a.H = c.n_heads; a.hd = e.hd; a.Lq = 1; a.Lk = P;
+    a.o = t.ap; a.ldo = E;
+    GG_TRY(k_attention_fwd(a, st));
+    const bool bn = net == GG_NET_GEN;
+    GG_TRY(e.linear(ln, B, E, E, Op{t.ap, E}, e.W(net, GG_P_P2T_OUT_W),
+                    Epi().bias(e.P(net, GG_P_P2T_OUT_B)).obf(bn ? t.pv : t.c, E)));
+    if (bn) {
+      GG_REQUIRE(e.bn_run_mean && e.bn_run_var, "gg_engine_set_batchnorm has not been called");
+      GG_TRY(k_bn_fwd(t.pv, E, e.P(net, GG_P_BN_W), e.P(net, GG_P_BN_B), e.bn_run_mean, e.bn_run_var, e.bn_momentum,
+                      e.bn_eps, e.bn_training, t.c, E, e.bn_mean, e.bn_rstd, B, E, st));
+    }
+    return GG_OK;
+  }
   // FiLM parameters from the text CLS / text vector (:129-134); conditional_gan_cross_attention.py has no FiLM
   // (:128-130): its patch encoder reads the patch embeddings as they are
   const bf16* pin = e.patches;
@@ -736,7 +778,7 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
 
 static Op cond_vec(const gg_engine& e, int net) {
   const Tower& t = e.tw[net];
-  if (e.paper || e.concat) return Op{t.c, e.cfg.E};
+  if (e.paper || e.concat || e.attn) return Op{t.c, e.cfg.E};
   return Op{t.X[e.cfg.n_layers], static_cast<int64_t>(e.S_) * e.cfg.E};
 }
 
@@ -764,6 +806,47 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     if (s0 > 0) return GG_OK;
     GG_TRY(e.wgrad(E, Dt, B, Op{dc, E}, Op{e.text, Dt}, e.Gr(net, GG_P_TEXT_W), Dt));
     GG_TRY(e.bgrad(dc, E, B, E, e.Gr(net, GG_P_TEXT_B)));
+    return e.flush_grads();
+  }
+  if (e.attn) {
+    if (s0 > 0) return GG_OK;
+    GG_REQUIRE(Rg == 1, "the attention variant has one tower pass");
+    const Op Wa = e.W(net, GG_P_P2T_IN_W);
+    const Op Wa_kv{Wa.p + static_cast<int64_t>(E) * Wa.ld, Wa.ld};
+    float* gWa = e.Gr(net, GG_P_P2T_IN_W);
+    float* gba = e.Gr(net, GG_P_P2T_IN_B);
+    const bf16* dpv = dc;
+    if (net == GG_NET_GEN) {  // c = attn_bn(pv)
+      GG_TRY(k_bn_bwd(dc, E, t.pv, E, e.bn_mean, e.bn_rstd, e.P(net, GG_P_BN_W), g.dp, E, e.Gr(net, GG_P_BN_W),
+                      e.Gr(net, GG_P_BN_B), B, E, st));
+      dpv = g.dp;
+    }
+    // pv = ap Wo^T + bo
+    GG_TRY(e.wgrad(E, E, B, Op{dpv, E}, Op{t.ap, E}, e.Gr(net, GG_P_P2T_OUT_W), E));
+    GG_TRY(e.bgrad(dpv, E, B, E, e.Gr(net, GG_P_P2T_OUT_B)));
+    GG_TRY(e.dgrad(0, B, E, E, Op{dpv, E}, e.W(net, GG_P_P2T_OUT_W), Epi().obf(g.dap, E)));
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = t.qp; a.ldq = E; a.q_mod = B;
+    a.k = t.kvp; a.v = t.kvp + E; a.ldkv = 2 * E; a.kv_mod = B;
+    a.mask = e.mask_s; a.mask_mod = B;
+    a.nb = B; a.H = c.n_heads; a.hd = e.hd; a.Lq = 1; a.Lk = P;
+    a.dout = g.dap; a.lddo = E; a.dq = g.dqp; a.lddq = E;
+    a.dk = g.dkvp; a.dv = g.dkvp + E; a.lddkv = 2 * E;
+    a.stat = e.attn_stat;
+    GG_TRY(k_attention_bwd(a, st));
+    // q = te Wq^T + bq ; te = text Wt^T + bt
+    GG_TRY(e.wgrad(E, E, B, Op{g.dqp, E}, Op{t.te, E}, gWa, E));
+    GG_TRY(e.bgrad(g.dqp, E, B, E, gba));
+    GG_TRY(e.dgrad(0, B, E, E, Op{g.dqp, E}, Wa, Epi().obf(g.dte0, E)));
+    GG_TRY(e.wgrad(E, Dt, B, Op{g.dte0, E}, Op{e.text, Dt}, e.Gr(net, GG_P_TEXT_W), Dt));
+    GG_TRY(e.bgrad(g.dte0, E, B, E, e.Gr(net, GG_P_TEXT_B)));
+    // kv = pe Wkv^T + bkv ; pe = patches Wp^T + bp
+    GG_TRY(e.wgrad(2 * E, E, B * P, Op{g.dkvp, 2 * E}, Op{t.X[0], E}, gWa + static_cast<int64_t>(E) * E, E));
+    GG_TRY(e.bgrad(g.dkvp, 2 * E, B * P, 2 * E, gba ? gba + E : nullptr));
+    GG_TRY(e.dgrad(0, B * P, E, 2 * E, Op{g.dkvp, 2 * E}, Wa_kv, Epi().obf(g.dpe, E)));
+    GG_TRY(e.wgrad(E, Dp, B * P, Op{g.dpe, E}, Op{e.patches, Dp}, e.Gr(net, GG_P_PATCH_W), Dp));
+    GG_TRY(e.bgrad(g.dpe, E, B * P, E, e.Gr(net, GG_P_PATCH_B)));
     return e.flush_grads();
   }
   bf16* Xf = t.X[c.n_layers];
@@ -1149,7 +1232,9 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
     GG_REQUIRE(patches && (text || e->img), "conditional variants need patches and text");
     GG_TRY(k_cast_f32_bf16(patches, c.Dp, e->patches, c.Dp, static_cast<int64_t>(c.B) * c.P, c.Dp, st));
     if (text) GG_TRY(k_cast_f32_bf16(text, c.Dt, e->text, c.Dt, static_cast<int64_t>(c.B) * c.T, c.Dt, st));
-    if (patch_pad) {
+    if (patch_pad && e->attn) {
+      GG_CUDA_CHECK(cudaMemcpyAsync(e->mask_s, patch_pad, static_cast<size_t>(c.B) * c.P, cudaMemcpyDeviceToDevice, st));
+    } else if (patch_pad) {
       GG_TRY(k_mask_with_cls(patch_pad, e->mask_s, c.B, c.P, st));
     } else {
       GG_CUDA_CHECK(cudaMemsetAsync(e->mask_s, 0, static_cast<size_t>(c.B) * e->S_, st));
@@ -1158,6 +1243,17 @@ extern "C" int gg_engine_set_batch(gg_engine* e, const float* genes, const float
     if (e->has_tpad)
       GG_CUDA_CHECK(cudaMemcpyAsync(e->tpad, text_pad, static_cast<size_t>(c.B) * c.T, cudaMemcpyDeviceToDevice, st));
   }
+  return GG_OK;
+}
+
+extern "C" int gg_engine_set_batchnorm(gg_engine* e, float* running_mean, float* running_var, float momentum, float eps) {
+  GG_REQUIRE(e && running_mean && running_var, "null argument");
+  GG_REQUIRE(e->attn, "gg_engine_set_batchnorm is for GG_VARIANT_ATTN engines");
+  GG_REQUIRE(momentum >= 0.f && momentum <= 1.f && eps > 0.f, "bad BatchNorm momentum / eps");
+  e->bn_run_mean = running_mean;
+  e->bn_run_var = running_var;
+  e->bn_momentum = momentum;
+  e->bn_eps = eps;
   return GG_OK;
 }
 
@@ -1195,6 +1291,7 @@ static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int
   // ---- forward: G(z) (no graph) on lane 1 next to the critic tower on lane 0; D on fake / real /
   // interpolated rows (:391-408), GP value (:351-374)
   GG_TRY(e->fork(1));
+  e->bn_training = training;
   GG_TRY(gen_forward(*e, z, p, nullptr, 1, false));      // (no graph: the generator is not trained here)
   GG_TRY(disc_forward_gp(*e, R, p, alpha, 1, 1, Rg));  // the GP chain continues on lane 1
   const Op W1x = e->W(net, GG_P_TR0_W), W2 = e->W(net, GG_P_TR1_W);
@@ -1279,6 +1376,8 @@ static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase,
     GG_TRY(e->fork(1));
     GG_TRY(tower_forward(*e, D, 1, p, 1, 0));  // (the critic is frozen: nothing of its tower is back-propagated)
   }
+  GG_REQUIRE(training || !e->attn, "the BatchNorm backward of the attention variant is the training-mode one");
+  e->bn_training = training;
   GG_TRY(gen_forward(*e, z, p, nullptr, 0, true));
   GG_TRY(e->join(1));
   GG_TRY(critic_trunk_forward(*e, e->xfr, 1, 1, 1, nullptr));
@@ -1360,6 +1459,7 @@ extern "C" int gg_engine_generate(gg_engine* e, const float* z, float* out_f32, 
   e->begin(stream);
   const float p = (training && e->cond && !e->concat) ? e->cfg.dropout_p : 0.f;
   if (p > 0.f) GG_TRY(k_bump_rng(e->rng, e->S(0)));
+  e->bn_training = training;
   return gen_forward(*e, z, p, out_f32, 0, false);
 }
 

@@ -60,6 +60,13 @@ int k_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, in
 int k_gather_rows(const float* src, int64_t ld_src, const int64_t* index, float* dst, int64_t ld_dst, int64_t rows,
                   int cols, cudaStream_t st);
 
+// BatchNorm1d over the rows of x [B, E] (conditional_gan_attention.py:108, :126); training: batch statistics + running update
+int k_bn_fwd(const bf16* x, int64_t ldx, const float* gamma, const float* beta, float* run_mean, float* run_var,
+             float momentum, float eps, int training, bf16* y, int64_t ldy, float* mean_out, float* rstd_out, int B, int E,
+             cudaStream_t st);
+int k_bn_bwd(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, const float* mean, const float* rstd,
+             const float* gamma, bf16* dx, int64_t lddx, float* dgamma, float* dbeta, int B, int E, cudaStream_t st);
+
 // ---- enc_layer.cu: one encoder layer forward as one tcgen05 kernel (S <= 16 tokens, E = 256, ffn = 512, 4 heads)
 typedef gg_enc_layer_params EncLayerParams;
 int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st);

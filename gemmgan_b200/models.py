@@ -11,6 +11,7 @@ reference's initial weights and state_dict()s are interchangeable with reference
   img     generator/discriminator  src/conditional_gan_img_transformer.py:97-190
   vanilla generator_nocond/discriminator_nocond  src/vanilla_gan_unconditional.py:93-184
   label   generator/discriminator  src/benchmark_generative_model.py:101-236 (label-conditioned baseline)
+  attn    generator/discriminator  src/conditional_gan_attention.py:92-170 (one MultiheadAttention, BatchNorm1d in G)
 
 forward() does not run torch kernels: it calls the engine (libgemmgan_sm100a.so) the trainer attached
 to the module. It is an inference forward (no autograd graph); the training step uses the engine's
@@ -24,7 +25,8 @@ from torch import nn
 from . import _abi_decl as A
 
 VARIANT_IDS = {"vanilla": A.VARIANT_VANILLA, "film": A.VARIANT_FILM, "paper": A.VARIANT_PAPER,
-               "cross": A.VARIANT_CROSS, "concat": A.VARIANT_CONCAT, "img": A.VARIANT_IMG, "label": A.VARIANT_LABEL}
+               "cross": A.VARIANT_CROSS, "concat": A.VARIANT_CONCAT, "img": A.VARIANT_IMG, "label": A.VARIANT_LABEL,
+               "attn": A.VARIANT_ATTN}
 
 
 def build_linear_block(input_dims, output_dims, negative_slope=0.0, is_bn=False):
@@ -281,6 +283,79 @@ class ConcatDiscriminator(_ConcatNet):
         self._build_concat(vector_dims, input_embedding_dims, embedding_dims, discriminator_dims, condition_type,
                            negative_slope, is_bn)
         self.encoder = nn.Linear(input_embedding_dims, embedding_dims)
+
+
+# ----------------------------------------------------------------- single-attention model
+class _AttnNet(_Net):
+    """conditional_gan_attention.py: conditioning vector = MultiheadAttention(query = text_encoder(text embedding),
+    keys / values = patches_encoder(patches), key_padding_mask) (:113-120 / :154-159); the generator normalises it with
+    BatchNorm1d over the batch (`attn_bn`, :108, :126). Construction order as in the reference: text_encoder,
+    patches_encoder, attention, (attn_bn), trunk blocks, final_layer."""
+
+    _variant = "attn"
+
+    def _build_attn(self, first_dim, embedding_dims, dims, text_embedding_dims, patches_embedding_dims, negative_slope,
+                    is_bn):
+        E = embedding_dims
+        self.embedding_dims = E
+        self.text_embedding_dims = text_embedding_dims
+        self.patches_embedding_dims = patches_embedding_dims
+        self.is_bn = is_bn
+        self.negative_slope = negative_slope
+        self.text_encoder = nn.Linear(text_embedding_dims, E)
+        self.patches_encoder = nn.Linear(patches_embedding_dims, E)
+        self.attention = nn.MultiheadAttention(embed_dim=E, num_heads=4, batch_first=True)
+        self.input_dims = first_dim + E
+        if self._role == "gen":
+            self.attn_bn = nn.BatchNorm1d(E)
+        stack = build_stack(self.input_dims, dims[:-1], negative_slope, is_bn)
+        setattr(self, "generator" if self._role == "gen" else "discriminator", stack)
+        self.final_layer = nn.Linear(dims[-2], dims[-1])
+        self._gg_owner = None
+
+    def slot_table(self):
+        blocks = self.trunk_blocks()
+        if len(blocks) != 2:
+            raise NotImplementedError("the engine implements the reference's 2-hidden-layer trunks")
+        att = self.attention
+        t = {A.P_TEXT_W: self.text_encoder.weight, A.P_TEXT_B: self.text_encoder.bias,
+             A.P_PATCH_W: self.patches_encoder.weight, A.P_PATCH_B: self.patches_encoder.bias,
+             A.P_P2T_IN_W: att.in_proj_weight, A.P_P2T_IN_B: att.in_proj_bias,
+             A.P_P2T_OUT_W: att.out_proj.weight, A.P_P2T_OUT_B: att.out_proj.bias,
+             A.P_TR0_W: blocks[0][0].weight, A.P_TR0_B: blocks[0][0].bias,
+             A.P_TR1_W: blocks[1][0].weight, A.P_TR1_B: blocks[1][0].bias,
+             A.P_FIN_W: self.final_layer.weight, A.P_FIN_B: self.final_layer.bias}
+        if self._role == "gen":
+            t[A.P_BN_W], t[A.P_BN_B] = self.attn_bn.weight, self.attn_bn.bias
+        return t
+
+    def forward(self, x, text_embedding, patches, padding_mask):
+        return self._engine_forward(x, text_embedding, patches, padding_mask)
+
+
+class AttnGenerator(_AttnNet):
+    _role = "gen"
+
+    def __init__(self, latent_dims, embedding_dims, generator_dims, text_embedding_dims=768,
+                 patches_embedding_dims=1024, negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.latent_dims = latent_dims
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.generator_dims = generator_dims
+        self._build_attn(latent_dims, embedding_dims, generator_dims, text_embedding_dims, patches_embedding_dims,
+                         negative_slope, is_bn)
+
+
+class AttnDiscriminator(_AttnNet):
+    _role = "disc"
+
+    def __init__(self, vector_dims, embedding_dims, discriminator_dims, text_embedding_dims=768,
+                 patches_embedding_dims=1024, negative_slope=0.0, is_bn=False):
+        super().__init__()
+        self.vector_dims = vector_dims
+        self.discriminator_dims = discriminator_dims
+        self._build_attn(vector_dims, embedding_dims, discriminator_dims, text_embedding_dims, patches_embedding_dims,
+                         negative_slope, is_bn)
 
 
 # ------------------------------------------------------ label-conditioned baseline model

@@ -193,6 +193,15 @@ class Engine:
             _lib.check(self.lib.gg_engine_create(C.byref(cfg), C.byref(self._gen_c), C.byref(self._disc_c),
                                                  _ptr(self.workspace), nbytes.value, _stream(), C.byref(h)))
         self.handle = h
+        if variant == "attn":
+            # the generator's BatchNorm1d buffers stay torch's (state_dict / checkpoints); the kernel updates them in place
+            bn = gen.module.attn_bn
+            rm, rv = bn.running_mean, bn.running_var
+            assert rm.device == self.device and rm.dtype == torch.float32 and rm.is_contiguous() and rv.is_contiguous()
+            assert bn.momentum is not None and bn.track_running_stats and bn.affine
+            _lib.check(self.lib.gg_engine_set_batchnorm(self.handle, _ptr(rm), _ptr(rv), float(bn.momentum),
+                                                        float(bn.eps)))
+            self._keep_bn = (rm, rv)
         sp = self.lib.gg_engine_stats(self.handle)
         self.stats = self._view(sp, A.STATS_COUNT, torch.float32)
         self._keep = None

@@ -157,6 +157,11 @@ int gg_gemm_timer_slots(double* flops, double* bytes, int n);
 #define GG_VARIANT_LABEL 6   /* benchmark_generative_model.py (label-conditioned baseline, :101-236): c = [emb0[y0] | emb1[y1]],
                                 two nn.Embedding tables of width E/2 per net; cfg.Dt / cfg.Dp = their vocabulary sizes;
                                 labels staged with gg_engine_set_labels; no dropout, no attention                      */
+#define GG_VARIANT_ATTN 7    /* conditional_gan_attention.py (:92-170): c = MultiheadAttention(query = text_encoder(text
+                                embedding) [B, 1, E], keys / values = patches_encoder(patches), key_padding_mask),
+                                no encoder layers, no dropout; the generator passes c through BatchNorm1d (attn_bn, :108,
+                                :126). Slots: GG_P_TEXT_*, GG_P_PATCH_*, GG_P_P2T_* = `attention`, GG_P_BN_* = attn_bn;
+                                running statistics through gg_engine_set_batchnorm                                     */
 #define GG_VARIANT_CROSS 3   /* conditional_gan_cross_attention.py: the paper model's towers without FiLM and without
                                 tower biases (:97-206); only row 0 of its multi-query cross-attentions reaches the
                                 conditioning vector, so it runs as the same single-query tail */
@@ -177,7 +182,9 @@ enum gg_param_slot {
   /* GG_VARIANT_IMG has no FiLM: its patch-encoder LayerNorm weight / bias [E] live in the FiLM slots */
   GG_P_PENC_LN_W = GG_P_FILM_W, GG_P_PENC_LN_B = GG_P_FILM_B,
   /* GG_VARIANT_LABEL: the two embedding tables [vocab_i, E/2] (fp32, gathered directly: no bf16 shadow) */
-  GG_P_EMB0 = GG_P_TEXT_W, GG_P_EMB1 = GG_P_PATCH_W
+  GG_P_EMB0 = GG_P_TEXT_W, GG_P_EMB1 = GG_P_PATCH_W,
+  /* GG_VARIANT_ATTN (generator only): BatchNorm1d weight / bias [E] in the FiLM slots */
+  GG_P_BN_W = GG_P_FILM_W, GG_P_BN_B = GG_P_FILM_B
 };
 enum gg_layer_slot {
   GG_L_IN_W = 0, GG_L_IN_B, GG_L_OUT_W, GG_L_OUT_B, GG_L_FF1_W, GG_L_FF1_B, GG_L_FF2_W, GG_L_FF2_B,
@@ -249,6 +256,11 @@ int gg_engine_set_batch(gg_engine* e, const float* genes, const float* patches, 
  * disease_type / primary_site columns; benchmark_generative_model.py:138-150). Values must lie in [0, vocab_i):
  * nn.Embedding raises on anything else, the caller checks (the kernel clamps instead of faulting). */
 int gg_engine_set_labels(gg_engine* e, const int64_t* labels0, const int64_t* labels1, void* stream);
+/* GG_VARIANT_ATTN: the generator's BatchNorm1d buffers (device fp32 [E] each, torch's running_mean / running_var, updated
+ * in place by every training-mode generator forward exactly like nn.BatchNorm1d: running = (1 - momentum) * running +
+ * momentum * batch statistic, the variance unbiased), its momentum and eps (torch defaults 0.1 / 1e-5). Must be called
+ * before the first forward of an ATTN engine. */
+int gg_engine_set_batchnorm(gg_engine* e, float* running_mean, float* running_var, float momentum, float eps);
 /* train_disc minus optimizer: fills critic grads + stats. z [B,L], alpha [B,1] fp32. training=1
  * uses dropout_p (three independently-dropped critic tower passes, as the reference). */
 int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream);

@@ -40,7 +40,7 @@ def ref_args(variant, x, cond):
     if variant in ("paper", "cross"):
         patches, ppad, text, tpad = cond
         return (x, text, tpad, patches, ppad)
-    if variant in ("film", "concat", "concat_image", "img"):
+    if variant in ("film", "concat", "concat_image", "img", "attn"):
         text, patches, ppad = cond
         return (x, text, patches, ppad)
     if variant == "label":
@@ -66,6 +66,17 @@ def draw_noise(seed, n_calls, n_critic, B, L):
 
 
 def make(variant, cfg, optimizer, slope, n_calls, full_tensors, name):
+    if variant == "attn":  # the reference's generator.forward prints its BatchNorm input / output on every call
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            _make(variant, cfg, optimizer, slope, n_calls, full_tensors, name)
+        print(f"{name}: written")
+        return
+    _make(variant, cfg, optimizer, slope, n_calls, full_tensors, name)
+
+
+def _make(variant, cfg, optimizer, slope, n_calls, full_tensors, name):
     c = dict(cfg)
     B, G, L = c["B"], c["G"], c["latent"]
     kw = dict(optimizer=optimizer, hidden=c["hidden"], latent=L, embed=c["embed"], seed=11,
@@ -88,6 +99,9 @@ def make(variant, cfg, optimizer, slope, n_calls, full_tensors, name):
 
     # --- first critic step, instrumented with the reference's own functions ---------------
     z0, a0 = zs[0], alphas[0]
+    # (attn: the probes below are extra training-mode forwards the replayed train() calls do not contain; the
+    # generator's BatchNorm running statistics are put back afterwards so that the fixture's final state is train()'s)
+    buffers0 = {k: v.clone() for k, v in t.gen.named_buffers()}
     with torch.no_grad():
         fake = t.gen(z0, *margs)
         d_fake = t.disc(fake, *margs)
@@ -100,6 +114,9 @@ def make(variant, cfg, optimizer, slope, n_calls, full_tensors, name):
         w.requires_grad = True
     gp_probe = t.gradient_penalty(x, fake, *margs)
     fx["step0"] = dict(fake=fake, d_fake=d_fake, d_true=d_true, gp_alpha=probe, gp=gp_probe.detach())
+    with torch.no_grad():
+        for k, v in t.gen.named_buffers():
+            v.copy_(buffers0[k])
 
     # --- the real thing: replay train() with the recorded noise ---------------------------
     torch.manual_seed(77)
@@ -157,8 +174,8 @@ def main():
     only = sys.argv[1:]   # optional: variant names to (re)generate, e.g. `python -m oracle.make_golden label`
     if only:
         global make
-        _make = make
-        make = lambda v, *a: _make(v, *a) if v in only else None  # noqa: E731
+        make_all = make
+        make = lambda v, *a: make_all(v, *a) if v in only else None  # noqa: E731
     make("vanilla", SMALL, "adam", 0.0, 4, True, "vanilla_small_adam")
     make("vanilla", SMALL, "rms_prop", 0.2, 4, True, "vanilla_small_rmsprop_leaky")
     make("paper", SMALL, "adam", 0.0, 4, True, "paper_small_adam")
@@ -173,6 +190,8 @@ def main():
     make("concat_image", SMALL, "rms_prop", 0.2, 4, True, "concat_image_small_rmsprop_leaky")
     make("label", SMALL, "rms_prop", 0.0, 4, True, "label_small_rmsprop")
     make("label", SMALL, "adam", 0.2, 4, True, "label_small_adam_leaky")
+    make("attn", SMALL, "adam", 0.0, 4, True, "attn_small_adam")
+    make("attn", SMALL, "rms_prop", 0.2, 4, True, "attn_small_rmsprop_leaky")
 
 
 if __name__ == "__main__":

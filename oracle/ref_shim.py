@@ -121,7 +121,7 @@ def make_trainer(variant: str, n_genes: int, *, optimizer: str = "adam", hidden:
         else:
             mod = {"paper": "conditional_gan_cross_attention_with_film",
                    "film": "conditional_gan_film", "cross": "conditional_gan_cross_attention",
-                   "img": "conditional_gan_img_transformer"}[variant]
+                   "img": "conditional_gan_img_transformer", "attn": "conditional_gan_attention"}[variant]
             ref = load(mod)
             torch.manual_seed(seed)
             t = ref.WGAN_GP(input_dims=n_genes, latent_dims=latent, embedding_dims=embed,

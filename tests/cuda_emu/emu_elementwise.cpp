@@ -48,3 +48,9 @@ W(embed_grad, (const bf16* dc, const int64_t* y0, const int64_t* y1, int V0, int
 W(masked_mean_rows, (const float* x, const uint8_t* pad, float* out, int B, int P, int D), (x, pad, out, B, P, D, nullptr))
 W(gather_rows, (const float* src, int64_t ld_src, const int64_t* index, float* dst, int64_t ld_dst, int64_t rows, int cols),
   (src, ld_src, index, dst, ld_dst, rows, cols, nullptr))
+W(bn_fwd, (const bf16* x, int64_t ldx, const float* gamma, const float* beta, float* run_mean, float* run_var, float momentum,
+           float eps, int training, bf16* y, int64_t ldy, float* mean_out, float* rstd_out, int B, int E),
+  (x, ldx, gamma, beta, run_mean, run_var, momentum, eps, training, y, ldy, mean_out, rstd_out, B, E, nullptr))
+W(bn_bwd, (const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+           bf16* dx, int64_t lddx, float* dgamma, float* dbeta, int B, int E),
+  (dy, lddy, x, ldx, mean, rstd, gamma, dx, lddx, dgamma, dbeta, B, E, nullptr))

@@ -38,6 +38,8 @@ SIGS = {
     "embed_grad": [vp, vp, vp, i32, i32, vp, vp, i32, i32],
     "masked_mean_rows": [vp, vp, vp, i32, i32, i32],
     "gather_rows": [vp, i64, vp, vp, i64, i64, i32],
+    "bn_fwd": [vp, i64, vp, vp, vp, vp, f32, f32, i32, vp, i64, vp, vp, i32, i32],
+    "bn_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, i32],
 }
 
 
@@ -317,3 +319,41 @@ def test_gather_rows_builds_a_batch(k, cols, ld_src, ld_dst):
     want = torch.where((index >= 0)[:, None], src[index.clamp(min=0), :cols], torch.zeros(rows, cols))
     assert torch.equal(dst[:, :cols], want)
     assert torch.all(dst[:, cols:] == 7.0)            # the pitch padding is left alone
+
+
+@pytest.mark.parametrize("B,E", [(8, 32), (37, 100), (64, 256)])
+def test_batchnorm_forward_backward_and_running_statistics(k, B, E):
+    """k_bn_fwd / k_bn_bwd against nn.BatchNorm1d (the generator's attn_bn of src/conditional_gan_attention.py:108, :126):
+    training-mode output, in-place running_mean / running_var update (unbiased variance, momentum 0.1), eval-mode output
+    from the running statistics, and the training-mode backward (dx, dweight, dbias) against autograd."""
+    g = torch.Generator().manual_seed(B + E)
+    x = (torch.randn(B, E, generator=g) * 2 + 0.5).bfloat16()
+    bn = torch.nn.BatchNorm1d(E)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(E, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(E, generator=g))
+        bn.running_mean.copy_(torch.randn(E, generator=g))
+        bn.running_var.copy_(torch.rand(E, generator=g) + 0.5)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    xr = x.float().requires_grad_(True)
+    want = bn(xr)
+    y = torch.empty(B, E, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(E), torch.empty(E)
+    k.bn_fwd(x, E, bn.weight.detach(), bn.bias.detach(), rm, rv, 0.1, 1e-5, 1, y, E, mean, rstd, B, E)
+    assert torch.allclose(y.float(), want.detach(), atol=2e-2, rtol=1e-2)          # bf16 output
+    assert torch.allclose(mean, x.float().mean(0), atol=1e-5)
+    assert torch.allclose(rm, bn.running_mean, atol=1e-5) and torch.allclose(rv, bn.running_var, rtol=1e-5, atol=1e-6)
+    dy = torch.randn(B, E, generator=g).bfloat16()
+    want.backward(dy.float())
+    dx = torch.empty(B, E, dtype=torch.bfloat16)
+    dgamma, dbeta = torch.empty(E), torch.empty(E)
+    k.bn_bwd(dy, E, x, E, mean, rstd, bn.weight.detach(), dx, E, dgamma, dbeta, B, E)
+    assert torch.allclose(dgamma, bn.weight.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(dbeta, bn.bias.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(dx.float(), xr.grad, atol=2e-2 * xr.grad.abs().max().item())
+    # eval mode: the running statistics, untouched
+    bn.eval()
+    rm2, rv2 = rm.clone(), rv.clone()
+    k.bn_fwd(x, E, bn.weight.detach(), bn.bias.detach(), rm2, rv2, 0.1, 1e-5, 0, y, E, mean, rstd, B, E)
+    assert torch.allclose(y.float(), bn(x.float()).detach(), atol=2e-2, rtol=1e-2)
+    assert torch.equal(rm2, rm) and torch.equal(rv2, rv)

@@ -90,12 +90,13 @@ def build(rt, variant, cfg, optimizer, slope, seed=11):
         import importlib
         m = importlib.import_module({"paper": "conditional_gan_cross_attention_with_film", "film": "conditional_gan_film",
                                      "cross": "conditional_gan_cross_attention",
-                                     "img": "conditional_gan_img_transformer"}[variant])
+                                     "img": "conditional_gan_img_transformer",
+                                     "attn": "conditional_gan_attention"}[variant])
         gen, disc = m.WGAN_GP_model(cfg["latent"], G, cfg["embed"], [H, H, G], [H, H, 1], cfg["text_dim"],
                                     cfg["patch_dim"], slope, False)
         tokens = variant in ("paper", "cross")           # text tokens [B, T, Dt] vs one text embedding [B, Dt]
         shape = dict(E=cfg["embed"], H=H, Dt=cfg["text_dim"], Dp=cfg["patch_dim"], P=cfg["P"],
-                     T=cfg["T"] if tokens else 1, tower_bias=variant == "paper")
+                     T=cfg["T"] if tokens else 1, tower_bias=variant in ("paper", "attn"))
         clip_d, clip_g = float(m.WGAN_GP.clip_d or 0.0), float(m.WGAN_GP.clip_g or 0.0)
     for (k1, v1), (k2, v2) in zip(o.gen.state_dict().items(), gen.state_dict().items()):
         assert k1 == k2 and torch.equal(v1, v2), k1
@@ -147,7 +148,8 @@ def check_grads(named_ref, named_got, total):
                                                      ("paper", "adam", 0.0), ("paper", "rms_prop", 0.0),
                                                      ("film", "adam", 0.0), ("cross", "adam", 0.0), ("img", "adam", 0.0),
                                                      ("concat", "adam", 0.2), ("concat_image", "rms_prop", 0.0),
-                                                     ("label", "adam", 0.0)])
+                                                     ("label", "adam", 0.0), ("attn", "adam", 0.0),
+                                                     ("attn", "rms_prop", 0.2)])
 def test_critic_and_generator_step_match_the_oracle(rt, variant, optimizer, slope):
     run_steps(rt, variant, optimizer, slope, SMALL)
 
@@ -219,6 +221,11 @@ def run_steps(rt, variant, optimizer, slope, cfg):
     # (tests/test_gpu_parity.py makes the same exception and runs its generator step at the larger configuration)
     check_grads([(k, p.grad) for k, p in o.gen.named_parameters()], list(gen.named_parameters()),
                 total=0.2 if variant == "img" else 0.08)
+    if variant == "attn":   # BatchNorm1d running statistics after the two training-mode generator forwards (:108, :126)
+        bo, bt = o.gen.attn_bn, gen.attn_bn
+        assert not torch.equal(bt.running_mean, torch.zeros_like(bt.running_mean))
+        torch.testing.assert_close(bt.running_mean, bo.running_mean, rtol=TOL, atol=2e-3)
+        torch.testing.assert_close(bt.running_var, bo.running_var, rtol=TOL, atol=2e-3)
 
 
 def test_generate_and_critic_entry_points(rt):
@@ -242,6 +249,35 @@ def test_generate_and_critic_entry_points(rt):
     o.disc.eval()
     gp_ref = o.gradient_penalty(x, want, cond, alpha)
     assert gp.item() == pytest.approx(gp_ref.item(), rel=TOL)
+
+
+def test_attention_variant_generates_from_the_running_statistics_in_eval_mode(rt):
+    """generate_samples of conditional_gan_attention.py (:505-512, gen.eval()): BatchNorm1d normalises with the running
+    statistics the training-mode forwards have accumulated and leaves them alone; a training-mode forward of the same
+    call uses the batch statistics and updates them."""
+    cfg = SMALL
+    o, gen, disc, eng = build(rt, "attn", cfg, "adam", 0.0)
+    B, G, L = cfg["B"], cfg["G"], cfg["latent"]
+    x, cond = restated.synthetic_batch("attn", B, G, cfg["P"], cfg["T"], seed=6, ragged=True,
+                                       text_dim=cfg["text_dim"], patch_dim=cfg["patch_dim"])
+    g = torch.Generator().manual_seed(3)
+    stage(eng, "attn", x, cond)
+    for _ in range(3):                                   # accumulate running statistics on both sides
+        z = torch.randn(B, L, generator=g)
+        with torch.no_grad():
+            want = o.gen(z, *cond)
+        assert rel(eng.generate(z, training=True), want) < TOL
+    bo, bt = o.gen.attn_bn, gen.attn_bn
+    torch.testing.assert_close(bt.running_mean, bo.running_mean, rtol=TOL, atol=2e-3)
+    torch.testing.assert_close(bt.running_var, bo.running_var, rtol=TOL, atol=2e-3)
+    frozen = (bt.running_mean.clone(), bt.running_var.clone())
+    o.gen.eval()
+    z = torch.randn(B, L, generator=g)
+    with torch.no_grad():
+        want = o.gen(z, *cond)
+    assert rel(eng.generate(z, training=False), want) < TOL
+    assert torch.equal(bt.running_mean, frozen[0]) and torch.equal(bt.running_var, frozen[1])
+    assert rel(eng.critic(x), o.disc(x, *cond).detach()) < TOL
 
 
 def test_dropout_is_deterministic_in_the_seed_and_close_in_expectation(rt):
@@ -277,7 +313,8 @@ def test_dropout_is_deterministic_in_the_seed_and_close_in_expectation(rt):
     assert rel(f1, f0) < 0.5 and fro(g1, g0) < 0.6           # perturbed, not different in kind
 
 
-@pytest.mark.parametrize("name", ["vanilla_small_adam", "paper_small_adam", "film_small_adam", "label_small_rmsprop"])
+@pytest.mark.parametrize("name", ["vanilla_small_adam", "paper_small_adam", "film_small_adam", "label_small_rmsprop",
+                                  "attn_small_adam"])
 def test_against_reference_golden_loss_curves(rt, name):
     """Replays the recorded noise of a run of the UNMODIFIED reference (tests/golden, oracle/make_golden.py) through
     the emulated engine: first critic step against the recorded internals, then whole train() calls (n_critic critic

@@ -28,18 +28,25 @@ def _make(variant, tmp):
         image = variant == "concat_image"
         return m.WGAN_GP(input_embedding_dims=40 if image else 24, condition_on="image" if image else "text", **kw), "film"
     mod = {"paper": "conditional_gan_cross_attention_with_film", "cross": "conditional_gan_cross_attention",
-           "film": "conditional_gan_film", "img": "conditional_gan_img_transformer"}[variant]
+           "film": "conditional_gan_film", "img": "conditional_gan_img_transformer",
+           "attn": "conditional_gan_attention"}[variant]
     m = importlib.import_module(mod)
     return m.WGAN_GP(**kw, **SMALLF), ("paper" if variant in ("paper", "cross") else "film")
 
 
-@pytest.mark.parametrize("variant", ["paper", "cross", "film", "img", "concat", "concat_image", "vanilla"])
+@pytest.mark.parametrize("variant", ["paper", "cross", "film", "img", "concat", "concat_image", "vanilla", "attn"])
 def test_fit_runs_and_saves_checkpoints(variant, tmp_path):
     torch.manual_seed(0)
     t, layout = _make(variant, tmp_path)
     loader = synthetic_loader(layout, n_samples=3 * B, batch_size=B, n_genes=G, n_patches=5, n_tokens=3, seed=1,
                               text_dim=24, patch_dim=40, ragged=True)
-    t.fit(loader, None, None, epochs=2)
+    if variant == "attn":   # conditional_gan_attention.py:523: fit(train_data, test_data, epochs, val)
+        t.fit(loader, None, epochs=2)
+        bn = t.gen.attn_bn   # 2 epochs x 3 batches x (5 critic + 1 generator) training-mode generator forwards
+        assert int(bn.num_batches_tracked) == 36 and bn.running_var.min().item() > 0
+        assert not torch.equal(bn.running_mean, torch.zeros_like(bn.running_mean))
+    else:
+        t.fit(loader, None, None, epochs=2)
     for k in ("d loss", "d real loss", "d fake loss", "g loss"):
         assert len(t.loss_dict[k]) == 2 and np.isfinite(t.loss_dict[k]).all(), (k, t.loss_dict[k])
     # the reference's checkpoint names (conditional_gan_cross_attention_with_film.py:743-744, vanilla :614-615)
