@@ -119,6 +119,10 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_set_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.gg_engine_set_labels.argtypes = [vp, vp, vp, vp]
     L.gg_engine_set_batchnorm.argtypes = [vp, vp, vp, C.c_float, C.c_float]
+    L.gg_engine_generate_keep.argtypes = [vp, vp, vp, i32, vp]
+    L.gg_engine_generate_backward.argtypes = [vp, vp, vp, vp]
+    L.gg_engine_critic_keep.argtypes = [vp, vp, vp, i32, vp]
+    L.gg_engine_critic_backward.argtypes = [vp, vp, vp, vp]
     L.gg_engine_disc_grads.argtypes = [vp, vp, vp, i32, vp]
     L.gg_engine_gen_grads.argtypes = [vp, vp, i32, vp]
     L.gg_engine_disc_grads_phase.argtypes = [vp, vp, vp, i32, i32, vp]
@@ -166,7 +170,8 @@ def declare(L: C.CDLL) -> None:
 
 EXPORTS = [
     "gg_last_error", "gg_abi_version", "gg_check_device", "gg_gemm_bf16", "gg_engine_workspace_bytes",
-    "gg_engine_create", "gg_engine_destroy", "gg_engine_set_lanes", "gg_engine_refresh_shadows", "gg_engine_set_batch", "gg_engine_set_labels", "gg_engine_set_batchnorm",
+    "gg_engine_create", "gg_engine_destroy", "gg_engine_set_lanes", "gg_engine_refresh_shadows", "gg_engine_set_batch", "gg_engine_set_labels", "gg_engine_set_batchnorm", "gg_engine_generate_keep", "gg_engine_generate_backward",
+    "gg_engine_critic_keep", "gg_engine_critic_backward",
     "gg_engine_disc_grads", "gg_engine_gen_grads", "gg_engine_disc_grads_phase", "gg_engine_gen_grads_phase", "gg_engine_optim_step", "gg_engine_generate",
     "gg_engine_critic", "gg_engine_gradient_penalty", "gg_engine_gp_step", "gg_masked_mean_rows", "gg_gather_rows", "gg_engine_lanes_signal", "gg_engine_stats", "gg_engine_buffer", "gg_optim_step",
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",

@@ -130,3 +130,11 @@ def check(rc: int) -> None:
 
 def require_device(dev: int = 0) -> None:
     check(lib().gg_check_device(dev))
+
+
+def require_cuda_tensor_device(dev, what: str) -> None:
+    """Free-standing modules: the parameters must already live on the sm_100a device (no CPU fallback path)."""
+    if dev.type != "cuda":
+        raise RuntimeError(f"{what} runs on the sm_100a engine: move the module to a CUDA device first "
+                           "(there is no PyTorch / CPU fallback path)")
+    require_device(dev.index or 0)

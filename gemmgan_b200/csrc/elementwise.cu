@@ -677,6 +677,26 @@ int k_score_bwd(const bf16* h2, const float* w3, bf16* da2, float* roww, int row
   return GG_OK;
 }
 
+// da2[m, o] = drow[m] * w3[o] * LeakyReLU'(h2[m, o]): the critic's last layer backward for an arbitrary upstream
+// gradient of the scores (module-level autograd: discriminator(x, ...).backward(dscore))
+__global__ void score_bwd_rows_kernel(const bf16* __restrict__ h2, const float* __restrict__ w3,
+                                      const float* __restrict__ drow, bf16* __restrict__ da2, int rows, int H, float slope) {
+  pdl_entry();
+  const int64_t total = static_cast<int64_t>(rows) * H;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i % H);
+    const float mk = __bfloat162float(h2[i]) > 0.f ? 1.f : slope;
+    da2[i] = __float2bfloat16_rn(drow[i / H] * w3[o] * mk);
+  }
+}
+int k_score_bwd_rows(const bf16* h2, const float* w3, const float* drow, bf16* da2, int rows, int H, float slope,
+                     cudaStream_t st) {
+  launch_k(score_bwd_rows_kernel, grid_for(static_cast<int64_t>(rows) * H, 256), 256, 0, st, h2, w3, drow, da2, rows, H, slope);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 __device__ float block_sum_ordered(float v, float* sm) {
   // fixed-order tree: deterministic for a fixed block size
   const int t = threadIdx.x;

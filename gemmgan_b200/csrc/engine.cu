@@ -132,6 +132,8 @@ struct gg_engine {
   float bn_momentum = 0.1f, bn_eps = 1e-5f;
   float *bn_mean = nullptr, *bn_rstd = nullptr;  // statistics the last generator forward normalised with
   int bn_training = 1;
+  float kept_p[2] = {-1.f, -1.f};  // dropout probability of the last *_keep forward per net (< 0: none yet)
+  int kept_training[2] = {0, 0};
   bool cond = false, paper = false, film = false;  // paper: cross-attention tail; film: FiLM modulation of the patches
   // staged inputs
   bf16 *xfr, *patches, *text, *zbf, *xin;
@@ -1350,6 +1352,36 @@ extern "C" int gg_engine_disc_grads_phase(gg_engine* e, const float* z, const fl
   return disc_grads_impl(e, z, alpha, training, phase, stream);
 }
 
+// Generator trunk backward from d loss / d fake (t.dfake, bf16 [B, Gp]): every trunk gradient, gs.dc for the tower, and
+// (optionally) the gradient w.r.t. the latent input z (fp32 [B, L])
+static int gen_trunk_backward(gg_engine& e, float* dz_f32) {
+  const gg_model_cfg& c = e.cfg;
+  TrunkBufs& t = e.tb;
+  const int B = c.B, H = c.H, G = c.G, E = c.E, L = c.L, Gn = GG_NET_GEN;
+  const int Lp = static_cast<int>(round_up64(L, 8));
+  const Op Wf = e.W(Gn, GG_P_FIN_W), Wg2 = e.W(Gn, GG_P_TR1_W);
+  GG_TRY(e.wgrad(G, H, B, Op{t.dfake, e.Gp}, Op{t.hg2, H}, e.Gr(Gn, GG_P_FIN_W), H));
+  GG_TRY(e.bgrad(t.dfake, e.Gp, B, G, e.Gr(Gn, GG_P_FIN_B)));
+  GG_TRY(e.dgrad(0, B, H, G, Op{t.dfake, e.Gp}, Wf, Epi().mask(t.hg2, H, 1.f, c.slope).obf(t.dag2, H)));
+  GG_TRY(e.wgrad(H, H, B, Op{t.dag2, H}, Op{t.hg1, H}, e.Gr(Gn, GG_P_TR1_W), H));
+  GG_TRY(e.bgrad(t.dag2, H, B, H, e.Gr(Gn, GG_P_TR1_B)));
+  GG_TRY(e.dgrad(0, B, H, H, Op{t.dag2, H}, Wg2, Epi().mask(t.hg1, H, 1.f, c.slope).obf(t.dag1, H)));
+  const int64_t ldw = static_cast<int64_t>(L) + (e.cond ? E : 0);
+  float* gW1 = e.Gr(Gn, GG_P_TR0_W);
+  if (e.cond) {
+    const Op Wc{e.sh[Gn].tr0_c.p, e.sh[Gn].tr0_c.ld};
+    GG_TRY(e.dgrad(0, B, E, H, Op{t.dag1, H}, Wc, Epi().obf(e.gs.dc, E)));
+  }
+  if (dz_f32) GG_TRY(e.dgrad(0, B, L, H, Op{t.dag1, H}, e.W(Gn, GG_P_TR0_W), Epi().of32(dz_f32, L)));
+  GG_TRY(e.wgrad(H, L, B, Op{t.dag1, H}, Op{e.zbf, Lp}, gW1, ldw));
+  GG_TRY(e.bgrad(t.dag1, H, B, H, e.Gr(Gn, GG_P_TR0_B)));
+  if (e.cond) {
+    const Op cv = cond_vec(e, Gn);
+    GG_TRY(e.wgrad(H, E, B, Op{t.dag1, H}, cv, gW1 + L, ldw));
+  }
+  return e.flush_grads();
+}
+
 static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase, void* stream) {
   GG_REQUIRE(e && z, "null argument");
   const bool no_join = (phase & GG_PHASE_NO_JOIN) != 0;
@@ -1387,27 +1419,7 @@ static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase,
   GG_TRY(k_score_bwd(t.h2, e->P(D, GG_P_FIN_W), t.da2, nullptr, B, B, H, c.slope, -1.f, -1.f, inv_b, st));
   GG_TRY(e->dgrad(0, B, H, H, Op{t.da2, H}, W2, Epi().mask(t.h1, H, 1.f, c.slope).obf(t.da1, H)));
   GG_TRY(e->dgrad(0, B, G, H, Op{t.da1, H}, W1x, Epi().obf(t.dfake, e->Gp)));
-  // ---- generator trunk backward
-  const Op Wf = e->W(Gn, GG_P_FIN_W), Wg2 = e->W(Gn, GG_P_TR1_W);
-  GG_TRY(e->wgrad(G, H, B, Op{t.dfake, e->Gp}, Op{t.hg2, H}, e->Gr(Gn, GG_P_FIN_W), H));
-  GG_TRY(e->bgrad(t.dfake, e->Gp, B, G, e->Gr(Gn, GG_P_FIN_B)));
-  GG_TRY(e->dgrad(0, B, H, G, Op{t.dfake, e->Gp}, Wf, Epi().mask(t.hg2, H, 1.f, c.slope).obf(t.dag2, H)));
-  GG_TRY(e->wgrad(H, H, B, Op{t.dag2, H}, Op{t.hg1, H}, e->Gr(Gn, GG_P_TR1_W), H));
-  GG_TRY(e->bgrad(t.dag2, H, B, H, e->Gr(Gn, GG_P_TR1_B)));
-  GG_TRY(e->dgrad(0, B, H, H, Op{t.dag2, H}, Wg2, Epi().mask(t.hg1, H, 1.f, c.slope).obf(t.dag1, H)));
-  const int64_t ldw = static_cast<int64_t>(L) + (e->cond ? E : 0);
-  float* gW1 = e->Gr(Gn, GG_P_TR0_W);
-  if (e->cond) {
-    const Op Wc{e->sh[Gn].tr0_c.p, e->sh[Gn].tr0_c.ld};
-    GG_TRY(e->dgrad(0, B, E, H, Op{t.dag1, H}, Wc, Epi().obf(e->gs.dc, E)));
-  }
-  GG_TRY(e->wgrad(H, L, B, Op{t.dag1, H}, Op{e->zbf, Lp}, gW1, ldw));
-  GG_TRY(e->bgrad(t.dag1, H, B, H, e->Gr(Gn, GG_P_TR0_B)));
-  if (e->cond) {
-    const Op cv = cond_vec(*e, Gn);
-    GG_TRY(e->wgrad(H, E, B, Op{t.dag1, H}, cv, gW1 + L, ldw));
-  }
-  GG_TRY(e->flush_grads());
+  GG_TRY(gen_trunk_backward(*e, nullptr));
   if (e->cond && phase == 0) GG_TRY(tower_backward(*e, Gn, 1, p, e->gs.dc));
   return no_join ? GG_OK : e->join_all();
 }
@@ -1461,6 +1473,79 @@ extern "C" int gg_engine_generate(gg_engine* e, const float* z, float* out_f32, 
   if (p > 0.f) GG_TRY(k_bump_rng(e->rng, e->S(0)));
   e->bn_training = training;
   return gen_forward(*e, z, p, out_f32, 0, false);
+}
+
+// ---- module-level autograd (SURVEY.md section 8 b "who calls it": generator.forward / discriminator.forward as
+// free-standing differentiable modules). *_keep = the same forward, keeping what the backward reads; *_backward = the
+// first-order backward from an arbitrary upstream gradient (the trainers' fused steps never come through here).
+extern "C" int gg_engine_generate_keep(gg_engine* e, const float* z, float* out_f32, int training, void* stream) {
+  GG_REQUIRE(e && z && out_f32, "null argument");
+  e->begin(stream);
+  const float p = (training && e->cond && !e->concat) ? e->cfg.dropout_p : 0.f;
+  if (p > 0.f) GG_TRY(k_bump_rng(e->rng, e->S(0)));
+  e->bn_training = training;
+  e->kept_p[GG_NET_GEN] = p;
+  e->kept_training[GG_NET_GEN] = training;
+  return gen_forward(*e, z, p, out_f32, 0, true);
+}
+
+extern "C" int gg_engine_generate_backward(gg_engine* e, const float* dout_f32, float* dz_f32, void* stream) {
+  GG_REQUIRE(e && dout_f32, "null argument");
+  GG_REQUIRE(e->kept_p[GG_NET_GEN] >= 0.f, "gg_engine_generate_backward without a gg_engine_generate_keep forward");
+  GG_REQUIRE(e->kept_training[GG_NET_GEN] || !e->attn, "the BatchNorm backward is the training-mode one");
+  e->begin(stream);
+  const gg_model_cfg& c = e->cfg;
+  GG_TRY(k_cast_f32_bf16(dout_f32, c.G, e->tb.dfake, e->Gp, c.B, c.G, e->S(0)));
+  GG_TRY(gen_trunk_backward(*e, dz_f32));
+  if (e->cond) GG_TRY(tower_backward(*e, GG_NET_GEN, 1, e->kept_p[GG_NET_GEN], e->gs.dc));
+  return e->join_all();
+}
+
+extern "C" int gg_engine_critic_keep(gg_engine* e, const float* genes_f32, float* score_f32, int training, void* stream) {
+  GG_REQUIRE(e && genes_f32 && score_f32, "null argument");
+  e->begin(stream);
+  cudaStream_t st = e->S(0);
+  const gg_model_cfg& c = e->cfg;
+  const float p = (training && e->cond && !e->concat) ? c.dropout_p : 0.f;
+  if (p > 0.f) GG_TRY(k_bump_rng(e->rng, st));
+  e->kept_p[GG_NET_DISC] = p;
+  GG_TRY(k_cast_f32_bf16(genes_f32, c.G, e->xin, e->Gp, c.B, c.G, st));
+  if (e->cond) GG_TRY(tower_forward(*e, GG_NET_DISC, 1, p, 0, 1));
+  GG_TRY(critic_trunk_forward(*e, e->xin, 1, 1, 1, nullptr));
+  GG_CUDA_CHECK(cudaMemcpyAsync(score_f32, e->tb.score, sizeof(float) * c.B, cudaMemcpyDeviceToDevice, st));
+  return GG_OK;
+}
+
+extern "C" int gg_engine_critic_backward(gg_engine* e, const float* dscore_f32, float* dgenes_f32, void* stream) {
+  GG_REQUIRE(e && dscore_f32, "null argument");
+  GG_REQUIRE(e->kept_p[GG_NET_DISC] >= 0.f, "gg_engine_critic_backward without a gg_engine_critic_keep forward");
+  e->begin(stream);
+  cudaStream_t st = e->S(0);
+  const gg_model_cfg& c = e->cfg;
+  TrunkBufs& t = e->tb;
+  const int B = c.B, H = c.H, G = c.G, E = c.E, net = GG_NET_DISC;
+  const Op W1x = e->W(net, GG_P_TR0_W), W2 = e->W(net, GG_P_TR1_W);
+  // score = h2 . w3 + b3
+  GG_TRY(k_score_bwd_rows(t.h2, e->P(net, GG_P_FIN_W), dscore_f32, t.da2, B, H, c.slope, st));
+  GG_TRY(e->dgrad(0, B, H, H, Op{t.da2, H}, W2, Epi().mask(t.h1, H, 1.f, c.slope).obf(t.da1, H)));
+  const int64_t ldw1 = static_cast<int64_t>(G) + (e->cond ? E : 0);
+  float* gW1 = e->Gr(net, GG_P_TR0_W);
+  if (e->cond) {
+    const Op W1c{e->sh[net].tr0_c.p, e->sh[net].tr0_c.ld};
+    GG_TRY(e->dgrad(0, B, E, H, Op{t.da1, H}, W1c, Epi().obf(e->gs.dc, E)));
+  }
+  if (dgenes_f32) GG_TRY(e->dgrad(0, B, G, H, Op{t.da1, H}, W1x, Epi().of32(dgenes_f32, G)));
+  GG_TRY(e->fork(1));
+  GG_TRY(k_colsum(t.h2f, 1, H, B, H, dscore_f32, 1.f, e->Gr(net, GG_P_FIN_W), 0, e->scratch_l[e->L(1)], e->S(1)));
+  GG_TRY(k_colsum(dscore_f32, 1, 1, B, 1, nullptr, 1.f, e->Gr(net, GG_P_FIN_B), 0, e->scratch_l[e->L(1)], e->S(1)));
+  GG_TRY(e->wgrad(H, H, B, Op{t.da2, H}, Op{t.h1, H}, e->Gr(net, GG_P_TR1_W), H));
+  GG_TRY(e->bgrad(t.da2, H, B, H, e->Gr(net, GG_P_TR1_B)));
+  GG_TRY(e->wgrad(H, G, B, Op{t.da1, H}, Op{e->xin, e->Gp}, gW1, ldw1));
+  GG_TRY(e->bgrad(t.da1, H, B, H, e->Gr(net, GG_P_TR0_B)));
+  if (e->cond) GG_TRY(e->wgrad(H, E, B, Op{t.da1, H}, cond_vec(*e, net), gW1 + G, ldw1));
+  GG_TRY(e->flush_grads());
+  if (e->cond) GG_TRY(tower_backward(*e, net, 1, e->kept_p[net], e->gs.dc));
+  return e->join_all();
 }
 
 extern "C" int gg_engine_critic(gg_engine* e, const float* genes_f32, float* score_f32, int training, void* stream) {

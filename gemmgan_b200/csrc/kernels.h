@@ -97,6 +97,8 @@ int k_gp_rows(const float* y, const float* u1f, const bf16* h1i, float* norms, f
 // da2[m, o] = sign(m)/B * w3[o] * (h2[m, o] > 0 ? 1 : slope); rows [0,B): sign_fake, rows [B,2B): sign_real
 int k_score_bwd(const bf16* h2, const float* w3, bf16* da2, float* roww, int rows, int B, int H, float slope,
                 float sign_first, float sign_second, float inv_batch, cudaStream_t st);
+int k_score_bwd_rows(const bf16* h2, const float* w3, const float* drow, bf16* da2, int rows, int H, float slope,
+                     cudaStream_t st);
 // stats: [0]=loss_real=-mean(score_real) [1]=loss_fake=mean(score_fake) [2]=gp=mean(pen) [3]=d_loss total
 int k_disc_losses(const float* score, const float* pen, float* stats, int B, float gp_weight, float inv_batch,
                   cudaStream_t st);

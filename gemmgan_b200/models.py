@@ -13,9 +13,10 @@ reference's initial weights and state_dict()s are interchangeable with reference
   label   generator/discriminator  src/benchmark_generative_model.py:101-236 (label-conditioned baseline)
   attn    generator/discriminator  src/conditional_gan_attention.py:92-170 (one MultiheadAttention, BatchNorm1d in G)
 
-forward() does not run torch kernels: it calls the engine (libgemmgan_sm100a.so) the trainer attached
-to the module. It is an inference forward (no autograd graph); the training step uses the engine's
-hand-written backward instead (gemmgan_b200/trainer.py).
+forward() does not run torch kernels: it calls the engine (libgemmgan_sm100a.so). Inside a drop-in trainer it is the
+trainer's engine (an inference forward: the training step uses the engine's fused, hand-written backward instead,
+gemmgan_b200/trainer.py). A free-standing module (no trainer) is differentiable: its forward goes through one
+torch.autograd.Function over the engine's forward / backward entry points (gemmgan_b200/standalone.py), first order.
 """
 from __future__ import annotations
 
@@ -129,10 +130,9 @@ class _Net(nn.Module):
         return {k: p for k, p in t.items() if p is not None}
 
     def _engine_forward(self, *args):
-        if self._gg_owner is None:
-            raise RuntimeError(
-                f"{type(self).__name__}.forward needs the sm_100a engine: build the model through "
-                "WGAN_GP.build_WGAN_GP() (there is no PyTorch/CPU fallback path)")
+        if self._gg_owner is None:   # free-standing module: autograd over the engine (raises off a CUDA device)
+            from .standalone import owner_of
+            return owner_of(self)._module_forward(self, *args)
         return self._gg_owner._module_forward(self, *args)
 
 

@@ -31,8 +31,11 @@ class FlatNet:
     (the prototype encoder layer the reference registers at :114) are placed behind `n_used`:
     they get no gradient (`grad is None`, as in the reference) and are never updated."""
 
-    def __init__(self, module: nn.Module, device: torch.device, optimizer: str):
+    def __init__(self, module: nn.Module, device: torch.device, optimizer: str, bind_grads: bool = True):
+        # bind_grads=False (free-standing modules driven by autograd): p.grad stays autograd's; the engine's gradient
+        # buffer is only the place the backward kernels write to
         self.module = module
+        self.bind_grads = bind_grads
         slots: Dict[int, nn.Parameter] = module.slot_table()
         used_ids = {id(p) for p in slots.values()}
         unused = [p for p in module.parameters() if id(p) not in used_ids]
@@ -58,7 +61,7 @@ class FlatNet:
                 view = self.params[o:o + p.numel()].view(p.shape)
                 view.copy_(p.detach().to(device=device, dtype=torch.float32))
                 p.data = view
-                p.grad = self.grads[o:o + p.numel()].view(p.shape)
+                p.grad = self.grads[o:o + p.numel()].view(p.shape) if bind_grads else None
             for p in unused:
                 o = tail[id(p)]
                 view = self.params[o:o + p.numel()].view(p.shape)
@@ -328,6 +331,31 @@ class Engine:
         out = torch.empty(self.B, self.G, device=self.device, dtype=torch.float32)
         _lib.check(self.lib.gg_engine_generate(self.handle, _ptr(z), _ptr(out), int(training), _stream()))
         return out
+
+    # ---- module-level autograd (gemmgan_b200/standalone.py): forward keeping the backward's tensors + first-order backward
+    def generate_keep(self, z: torch.Tensor, training: bool) -> torch.Tensor:
+        z = self._f32(z)
+        out = torch.empty(self.B, self.G, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.gg_engine_generate_keep(self.handle, _ptr(z), _ptr(out), int(training), _stream()))
+        return out
+
+    def generate_backward(self, dout: torch.Tensor, want_dz: bool) -> Optional[torch.Tensor]:
+        d = self._f32(dout)
+        dz = torch.empty(self.B, self.L, device=self.device, dtype=torch.float32) if want_dz else None
+        _lib.check(self.lib.gg_engine_generate_backward(self.handle, _ptr(d), _ptr(dz), _stream()))
+        return dz
+
+    def critic_keep(self, genes: torch.Tensor, training: bool) -> torch.Tensor:
+        g = self._f32(genes)
+        out = torch.empty(self.B, 1, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.gg_engine_critic_keep(self.handle, _ptr(g), _ptr(out), int(training), _stream()))
+        return out
+
+    def critic_backward(self, dscore: torch.Tensor, want_dx: bool) -> Optional[torch.Tensor]:
+        d = self._f32(dscore.reshape(-1))
+        dx = torch.empty(self.B, self.G, device=self.device, dtype=torch.float32) if want_dx else None
+        _lib.check(self.lib.gg_engine_critic_backward(self.handle, _ptr(d), _ptr(dx), _stream()))
+        return dx
 
     def gradient_penalty(self, real, fake, alpha, training: bool = True) -> torch.Tensor:
         r, f, a = self._f32(real), self._f32(fake), self._f32(alpha)

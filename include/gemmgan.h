@@ -298,6 +298,18 @@ int gg_engine_gradient_penalty(gg_engine* e, const float* real_f32, const float*
  * into the critic's gradient buffer (biases get no GP gradient: the masks are piecewise constant). */
 int gg_engine_gp_step(gg_engine* e, const float* real_f32, const float* fake_f32, const float* alpha, float* gp_out,
                       void* stream);
+/* Module-level autograd (SURVEY.md section 8 b: generator.forward / discriminator.forward of
+ * src/conditional_gan_cross_attention_with_film.py:128-164 / :198-233 as free-standing differentiable nn.Modules, outside
+ * WGAN_GP.train): gg_engine_generate_keep / gg_engine_critic_keep are gg_engine_generate / gg_engine_critic keeping what
+ * the backward reads (one replica); the *_backward calls take the upstream gradient (d loss / d output, device fp32
+ * [B, G] / [B]) and fill the net's gradient buffer (overwriting it, like the grads entry points), plus — when the
+ * pointer is not NULL — the gradient w.r.t. the first input (z [B, L] / gene profiles [B, G], fp32). First order only:
+ * the gradient penalty's double backward is gg_engine_disc_grads / gg_engine_gp_step. The staged batch must not change
+ * between a *_keep forward and its backward; a later forward of the same net replaces what was kept. */
+int gg_engine_generate_keep(gg_engine* e, const float* z, float* out_f32, int training, void* stream);
+int gg_engine_generate_backward(gg_engine* e, const float* dout_f32, float* dz_f32, void* stream);
+int gg_engine_critic_keep(gg_engine* e, const float* genes_f32, float* score_f32, int training, void* stream);
+int gg_engine_critic_backward(gg_engine* e, const float* dscore_f32, float* dgenes_f32, void* stream);
 /* out[b, :] (fp32) = mean over the rows p with pad[b, p] == 0 of x[b, p, :] — the masked mean of
  * conditional_gan_concat.py:137-138 ('image' conditioning), taken BEFORE the affine encoder. pad may be NULL. */
 int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream);
