@@ -377,6 +377,8 @@ def main():
     _lib.check(L.gg_gemm_profile_end(C.byref(ms), C.byref(fl), C.byref(nl)))
     el_ms, el_fl, el_by, el_n = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
     _lib.check(L.gg_enc_layer_profile(C.byref(el_ms), C.byref(el_fl), C.byref(el_by), C.byref(el_n)))
+    wg_ms, wg_fl, wg_by, wg_n = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
+    _lib.check(L.gg_wgrad_group_profile(C.byref(wg_ms), C.byref(wg_fl), C.byref(wg_by), C.byref(wg_n)))
     if args.gemm_csv and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.gemm_csv)), exist_ok=True)
         _lib.check(L.gg_gemm_profile_dump(args.gemm_csv.encode()))
@@ -473,6 +475,20 @@ def main():
                                        tensor_frac=(fl.value + el_fl.value) / tot_s / 1e12 / pk["tflops"],
                                        hbm_gbs=(by + el_by.value) / tot_s / 1e9,
                                        hbm_frac=(by + el_by.value) / tot_s / 1e9 / pk["hbm"])
+
+    # the grouped weight-gradient kernel (wgrad_group.cu: every dW = dY^T X of one backward flush as one persistent tcgen05
+    # launch, K = the token rows): its operands are activations written moments earlier (L2-resident at cfg3), so the byte
+    # bound below is the HBM one an out-of-cache run would meet; the tensor view is given next to it
+    if wg_n.value > 0 and wg_ms.value > 0:
+        ws = wg_ms.value * 1e-3
+        w_tf, w_gbs = wg_fl.value / ws / 1e12, wg_by.value / ws / 1e9
+        roofline["wgrad_group"] = dict(
+            kernel="wgrad_group_kernel (tcgen05, MN-major operands by 3-D TMA boxes, split-K with in-kernel reduction)",
+            launches_per_step=int(wg_n.value), ms_per_step=wg_ms.value, flops_per_step=wg_fl.value,
+            bytes_per_step=wg_by.value, tensor_tflops=w_tf, tensor_frac=w_tf / pk["tflops"], hbm_gbs=w_gbs,
+            hbm_frac=w_gbs / pk["hbm"],
+            bound="hbm" if wg_by.value / (pk["hbm"] * 1e9) >= wg_fl.value / (pk["tflops"] * 1e12) else "tensor",
+            frac=max(w_tf / pk["tflops"], w_gbs / pk["hbm"]), share_of_profiled_call=wg_ms.value / profiled_call_ms)
 
     # ---- end-to-end through the public API with pinned host tensors
     e2e = None

@@ -63,7 +63,8 @@ class AttnArgs(C.Structure):
                 ("drop_p", C.c_float), ("rng", C.c_void_p), ("site", C.c_uint32),
                 ("o", C.c_void_p), ("ldo", C.c_int64),
                 ("dout", C.c_void_p), ("lddo", C.c_int64), ("dq", C.c_void_p), ("lddq", C.c_int64),
-                ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddkv", C.c_int64), ("stat", C.c_void_p)]
+                ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddkv", C.c_int64), ("stat", C.c_void_p),
+                ("dbits", C.c_void_p)]
 
 
 class EncLayerParams(C.Structure):
@@ -118,6 +119,9 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_set_lanes.argtypes = [vp, i32]
     L.gg_engine_set_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.gg_engine_set_labels.argtypes = [vp, vp, vp, vp]
+    L.gg_dropout_bits_words.argtypes = [i64]
+    L.gg_dropout_bits_words.restype = i64
+    L.gg_dropout_bits.argtypes = [vp, C.c_uint32, f32, i64, vp, vp]
     L.gg_engine_set_batchnorm.argtypes = [vp, vp, vp, C.c_float, C.c_float]
     L.gg_engine_generate_keep.argtypes = [vp, vp, vp, i32, vp]
     L.gg_engine_generate_backward.argtypes = [vp, vp, vp, vp]
@@ -153,6 +157,8 @@ def declare(L: C.CDLL) -> None:
     L.gg_encoder_ffn_bwd.argtypes = [C.POINTER(EncFfnBwdParams), vp]
     L.gg_enc_layer_profile.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_longlong)]
+    L.gg_wgrad_group_profile.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_longlong)]
     declare_evalmetrics(L)
     L.gg_launch_count.argtypes = [i32]
     L.gg_launch_count.restype = C.c_longlong
@@ -177,5 +183,5 @@ EXPORTS = [
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",
     "gg_pairwise_distance", "gg_row_kth_smallest", "gg_row_membership", "gg_col_hits", "gg_standardize_columns",
     "gg_gene_correlation", "gg_gamma_moments_workspace_bytes", "gg_gamma_moments",
-    "gg_encoder_layer_fwd", "gg_encoder_ffn_bwd", "gg_enc_layer_set_trace", "gg_enc_layer_profile", "gg_attention_fwd", "gg_attention_bwd", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
+    "gg_encoder_layer_fwd", "gg_encoder_ffn_bwd", "gg_enc_layer_set_trace", "gg_enc_layer_profile", "gg_wgrad_group_profile", "gg_attention_fwd", "gg_attention_bwd", "gg_dropout_bits", "gg_dropout_bits_words", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

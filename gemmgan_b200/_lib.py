@@ -13,7 +13,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libgemmgan_sm100a.so"
 
 GG_OK = 0
-ABI_VERSION = 3   # must equal GG_ABI_VERSION of include/gemmgan.h: bumped with every struct / signature change
+ABI_VERSION = 4   # must equal GG_ABI_VERSION of include/gemmgan.h: bumped with every struct / signature change
 ACT_NONE, ACT_LEAKY, ACT_FILM = 0, 1, 2
 IMPL_TCGEN05, IMPL_SIMT_F32 = 0, 1
 

@@ -542,6 +542,33 @@ __device__ __forceinline__ float quad_add(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
+// ---- precomputed dropout keep bits (AttnArgs::dbits). The mid / long self-attention kernels spend most of their issue
+// slots on Philox when they draw the masks themselves (a 16 x 16 score tile of one warp meets ~40 eight-element groups
+// of the stream, and the backward draws them twice more: cfg2 forward 354 -> 1180 us with dropout on). One pass of
+// dropout_bits_kernel draws every group exactly once — bit idx of the mask = element idx of the stream, 1 = kept —
+// and forward and backward read 16-bit windows of it (L2-resident: S*S bits per head).
+__device__ __forceinline__ uint32_t keep_window16(const uint32_t* __restrict__ bits, uint64_t o) {
+  const uint64_t w = o >> 5;
+  const uint64_t two = static_cast<uint64_t>(__ldg(bits + w)) | (static_cast<uint64_t>(__ldg(bits + w + 1)) << 32);
+  return static_cast<uint32_t>(two >> (static_cast<uint32_t>(o) & 31u)) & 0xFFFFu;
+}
+
+__global__ void __launch_bounds__(256)
+    dropout_bits_kernel(const uint64_t* __restrict__ rng, uint32_t site, float p, int64_t n_words,
+                        uint32_t* __restrict__ out) {
+  pdl_entry();
+  const uint64_t seed = rng[0], step = rng[1];
+  const uint32_t thr = dropout_thr(p);
+  for (int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; w < n_words;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      v |= keep_bits8(dropout_words(seed, step, site, static_cast<uint64_t>(w) * 4 + k), thr) << (8 * k);
+    out[w] = v;
+  }
+}
+
 // C[16 x 16] (2 n-tiles) = A[16 x 64] * B^T with B stored [16 rows (n)][64 (k)]: both row-major tiles in smem
 __device__ __forceinline__ void mma_ab_t(float (&c)[2][4], const bf16* A, const bf16* B, int lane) {
 #pragma unroll
@@ -879,7 +906,21 @@ __global__ void __launch_bounds__(NT * 32) attn_self_mid_kernel(const AttnArgs a
     }
     // dropout multipliers folded into a bit mask (bit kt*8 + rh*4 + e = dropped)
     uint64_t dropped = 0;
-    if (drop) {
+    if (drop && a.dbits) {
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const int i = qt * 16 + g + rh * 8;
+        if (i >= S) continue;
+        const uint64_t pbase = ((static_cast<uint64_t>(b) * a.H + h) * S + i) * static_cast<uint64_t>(S);
+#pragma unroll
+        for (int kt = 0; kt < NT; ++kt) {
+          const uint32_t win = keep_window16(a.dbits, pbase + kt * 16);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (!((win >> ((e >> 1) * 8 + 2 * t + (e & 1))) & 1u)) dropped |= 1ull << (kt * 8 + rh * 4 + e);
+        }
+      }
+    } else if (drop) {
       DropoutStream ds(seed, step, a.site, a.drop_p);
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
@@ -1098,7 +1139,16 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
     for (int n = 0; n < 8; ++n)
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[n][j] = 0.f;
+    // rows of this thread in the precomputed keep-bit mask (rows >= S read row S - 1: their results are never stored)
+    const uint64_t wrow[2] = {(head_base + min(qt * 16 + g, S - 1)) * static_cast<uint64_t>(S),
+                              (head_base + min(qt * 16 + g + 8, S - 1)) * static_cast<uint64_t>(S)};
+    const bool use_bits = drop && a.dbits != nullptr;
     for (int kt = 0; kt < NT; ++kt) {
+      uint32_t win[2] = {0xFFFFu, 0xFFFFu};
+      if (MODE == 0 && use_bits) {
+        win[0] = keep_window16(a.dbits, wrow[0] + kt * 16);
+        win[1] = keep_window16(a.dbits, wrow[1] + kt * 16);
+      }
       float sc[2][4];
       mma_ab_t(sc, Qt, Ks + kt * SELF_TILE, lane);
       float pv[2][4];
@@ -1132,7 +1182,13 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
         }
       }
       if (MODE == 0) {
-        if (drop) {
+        if (drop && a.dbits) {
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              pv[rh][e] = ((win[rh] >> ((e >> 1) * 8 + 2 * t + (e & 1))) & 1u) ? pv[rh][e] * keep_scale : 0.f;
+        } else if (drop) {
           DropoutStream ds(seed, step, a.site, a.drop_p);
 #pragma unroll
           for (int rh = 0; rh < 2; ++rh) {
@@ -1206,6 +1262,11 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
     const float m_safe[2] = {m_run[0] == -INFINITY ? 0.f : m_run[0], m_run[1] == -INFINITY ? 0.f : m_run[1]};
     const float delta[2] = {row_delta[qt * 16 + g], row_delta[qt * 16 + g + 8]};
     for (int kt = 0; kt < NT; ++kt) {
+      uint32_t win[2] = {0xFFFFu, 0xFFFFu};
+      if (use_bits) {
+        win[0] = keep_window16(a.dbits, wrow[0] + kt * 16);
+        win[1] = keep_window16(a.dbits, wrow[1] + kt * 16);
+      }
       float sc[2][4], dp[2][4];
       mma_ab_t(sc, Qt, Ks + kt * SELF_TILE, lane);
       mma_ab_t(dp, Gt, Vs + kt * SELF_TILE, lane);  // dP~ = dO V^T
@@ -1220,7 +1281,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
           const int j = key_of(kt, e);
           const float pij = kval[j] ? fast_ex2(fmaf(sc[e >> 1][rh * 2 + (e & 1)], SCALE_LOG2E, -m_safe[rh])) * inv_l[rh] : 0.f;
           float mult = 1.f;
-          if (drop && i < S && j < S) mult = ds.keep(pbase + j) ? keep_scale : 0.f;
+          if (use_bits) mult = ((win[rh] >> ((e >> 1) * 8 + 2 * t + (e & 1))) & 1u) ? keep_scale : 0.f;
+          else if (drop && i < S && j < S) mult = ds.keep(pbase + j) ? keep_scale : 0.f;
           dsv[rh][e] = pij * (dp[e >> 1][rh * 2 + (e & 1)] * mult - delta[rh]);
         }
       }
@@ -1251,6 +1313,15 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
       mma_ab_t(dpt, Vs + kt * SELF_TILE, Gs + qt * SELF_TILE, lane);  // dP~^T = V dO^T
       float pT[2][4], dsT[2][4];  // [key row half][e]: query column i = qt*16 + (e>>1)*8 + 2t + (e&1)
       DropoutStream ds(seed, step, a.site, a.drop_p);
+      const bool use_bits2 = drop && a.dbits != nullptr;
+      uint32_t winq[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};  // keys kt*16 .. +15 of this thread's four query rows
+      if (use_bits2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = min(qt * 16 + (e >> 1) * 8 + 2 * t + (e & 1), S - 1);
+          winq[e] = keep_window16(a.dbits, (head_base + i) * static_cast<uint64_t>(S) + kt * 16);
+        }
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = qt * 16 + (e >> 1) * 8 + 2 * t + (e & 1);
@@ -1262,7 +1333,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
           const bool kv = rh == 0 ? kv0 : kv1;
           const float pij = kv ? fast_ex2(fmaf(st[e >> 1][rh * 2 + (e & 1)], SCALE_LOG2E, -mi)) * il : 0.f;
           float mult = 1.f;
-          if (drop && i < S && j < S) mult = ds.keep(pbase + j) ? keep_scale : 0.f;
+          if (use_bits2) mult = ((winq[e] >> (g + rh * 8)) & 1u) ? keep_scale : 0.f;
+          else if (drop && i < S && j < S) mult = ds.keep(pbase + j) ? keep_scale : 0.f;
           pT[rh][e] = pij * mult;
           dsT[rh][e] = pij * (dpt[e >> 1][rh * 2 + (e & 1)] * mult - dl);
         }
@@ -1503,6 +1575,17 @@ static int check_args(const AttnArgs& a) {
   GG_REQUIRE(a.Lk >= 1 && a.Lk <= 32 * ATT_MAXC && a.Lq >= 1 && a.Lq <= 32 * ATT_MAXC,
              "attention length Lq=%d Lk=%d unsupported (<= %d)", a.Lq, a.Lk, 32 * ATT_MAXC);
   GG_REQUIRE(a.drop_p == 0.f || a.rng, "dropout needs rng state");
+  return GG_OK;
+}
+
+int64_t dropout_bits_words(int64_t n_elems) { return (n_elems + 31) / 32 + 4; }
+int k_dropout_bits(const uint64_t* rng, uint32_t site, float p, int64_t n_elems, uint32_t* out, cudaStream_t st) {
+  GG_REQUIRE(rng && out && n_elems >= 0, "bad dropout-bits argument");
+  const int64_t n_words = dropout_bits_words(n_elems);
+  int64_t blocks = (n_words + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_k(dropout_bits_kernel, static_cast<unsigned>(blocks), 256, 0, st, rng, site, p, n_words, out);
+  GG_LAUNCH_CHECK();
   return GG_OK;
 }
 

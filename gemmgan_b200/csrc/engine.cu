@@ -83,6 +83,7 @@ struct NetShadow {
 };
 
 struct TowerLayer {
+  uint32_t* dbits = nullptr;  // keep bits of the attention-probability dropout of this layer pass (17 .. 320 tokens)
   bf16 *qkv, *ao, *z1, *x1, *h, *z2;
   float *mean1, *rstd1, *mean2, *rstd2;
 };
@@ -309,6 +310,7 @@ struct gg_engine {
   bool text_lane_fwd = true, text_lane_bwd = false;  // GEMMGAN_TEXT_LANE = <fwd><bwd> digits overrides
   bool split_tail_flush = false;  // measured: splitting the last flush costs 0.28 ms / train() (the grouped kernel occupies every SM)
   bool fuse_bias = true;  // GEMMGAN_FUSE_BIAS=0: keep every bias gradient in the grouped column-sum kernel
+  bool attn_bits = true;  // GEMMGAN_ATTN_BITS=0: the 17 .. 320-token attention kernels draw their dropout masks themselves
   bool fused_layer = true;  // GEMMGAN_FUSED_LAYER=0: encoder layers as seven launches instead of enc_layer.cu's one
   // one workspace per flush in flight: flushes of one entry point run back to back on their lane, so
   // they rotate through GROUP_WS_SLOTS regions
@@ -409,6 +411,8 @@ static void layout_tower(gg_engine& e, Tower& t, int Rmax, Arena& ar) {
     L.x1 = ar.take<bf16>(rows * E);
     L.h = ar.take<bf16>(rows * F);
     L.z2 = ar.take<bf16>(rows * E);
+    if (c.dropout_p > 0.f && S > 16 && !e.attn)
+      L.dbits = ar.take<uint32_t>(dropout_bits_words(static_cast<int64_t>(Rmax) * B * c.n_heads * S * S));
     L.mean1 = ar.take<float>(rows);
     L.rstd1 = ar.take<float>(rows);
     L.mean2 = ar.take<float>(rows);
@@ -732,6 +736,10 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
     a.nb = R * B; a.H = c.n_heads; a.hd = e.hd; a.Lq = S; a.Lk = S;
     a.drop_p = p; a.rng = e.rng; a.site = site + 0;
     a.o = L.ao; a.ldo = E;
+    if (p > 0.f && L.dbits && e.attn_bits) {  // draw the probability-dropout mask once: forward and backward read bits
+      GG_TRY(k_dropout_bits(e.rng, site + 0, p, static_cast<int64_t>(R) * B * c.n_heads * S * S, L.dbits, st));
+      a.dbits = L.dbits;
+    }
     GG_TRY(k_attention_fwd(a, st));
     GG_TRY(e.linear(ln, rows, E, E, Op{L.ao, E}, e.W(net, ls + GG_L_OUT_W),
                     Epi().bias(e.P(net, ls + GG_L_OUT_B)).obf(t.tmpE, E)));
@@ -988,6 +996,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     a.mask = e.mask_s; a.mask_mod = B;
     a.nb = n; a.H = c.n_heads; a.hd = e.hd; a.Lq = S; a.Lk = S;
     a.drop_p = p; a.rng = e.rng; a.site = site + 0;
+    if (p > 0.f && L.dbits && e.attn_bits) a.dbits = L.dbits;  // the forward of this step drew them
     a.o = L.ao; a.ldo = E;  // forward output (kept for the out-projection's weight gradient): delta_i = dO_i . O_i
     a.dout = g.gao; a.lddo = E; a.dq = lg.gqkv; a.lddq = 3 * E;
     a.dk = lg.gqkv + E; a.dv = lg.gqkv + 2 * E; a.lddkv = 3 * E;
@@ -1169,6 +1178,8 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
     e->fuse_bias = !(fb && fb[0] == '0');
     const char* fl = getenv("GEMMGAN_FUSED_LAYER");
     e->fused_layer = !(fl && fl[0] == '0');
+    const char* ab = getenv("GEMMGAN_ATTN_BITS");
+    e->attn_bits = !(ab && ab[0] == '0');
   }
   for (int l = 1; l < gg_engine::NLANES; ++l)
     GG_CUDA_CHECK(cudaStreamCreateWithFlags(&e->cur[l], cudaStreamNonBlocking));
@@ -1684,6 +1695,10 @@ extern "C" void* gg_engine_buffer(gg_engine* e, const char* name, int64_t* rows,
 extern "C" int gg_attention_fwd(const gg_attn_args* a, void* stream) {
   GG_REQUIRE(a && a->q && a->k && a->v && a->o, "null argument");
   return k_attention_fwd(*reinterpret_cast<const AttnArgs*>(a), reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int64_t gg_dropout_bits_words(int64_t n_elems) { return dropout_bits_words(n_elems); }
+extern "C" int gg_dropout_bits(const uint64_t* rng, uint32_t site, float p, int64_t n_elems, uint32_t* out, void* stream) {
+  return k_dropout_bits(rng, site, p, n_elems, out, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int gg_attention_bwd(const gg_attn_args* a, void* stream) {
   GG_REQUIRE(a && a->q && a->k && a->v && a->dout && a->dq && a->dk && a->dv, "null argument");

@@ -738,7 +738,8 @@ struct AuxProfile {
   double flops = 0.0, bytes = 0.0;
   long long launches = 0;
 };
-static AuxProfile g_aux;
+static AuxProfile g_auxes[2];  // 0: fused encoder-layer kernels (enc_layer.cu), 1: grouped weight-gradient kernel
+#define g_aux g_auxes[0]
 struct StampRecord {
   double flops, bytes;
 };
@@ -761,27 +762,31 @@ static cudaError_t prof_record(cudaEvent_t ev, cudaStream_t stream) {
 
 // Event pair around a launch of another tensor-core kernel of the library while the live profiler is on:
 // prof_aux_begin before the launch (records its algorithmic flops / bytes), prof_aux_end after it.
-int prof_aux_begin(double flops, double bytes, cudaStream_t stream) {
+static int prof_chan_begin(AuxProfile& a, double flops, double bytes, cudaStream_t stream) {
   if (!g_prof.on) return GG_OK;
-  if (g_aux.used + 2 > g_aux.ev.size()) {
-    cudaEvent_t a, b;
-    GG_CUDA_CHECK(cudaEventCreate(&a));
-    GG_CUDA_CHECK(cudaEventCreate(&b));
-    g_aux.ev.push_back(a);
-    g_aux.ev.push_back(b);
+  if (a.used + 2 > a.ev.size()) {
+    cudaEvent_t e0, e1;
+    GG_CUDA_CHECK(cudaEventCreate(&e0));
+    GG_CUDA_CHECK(cudaEventCreate(&e1));
+    a.ev.push_back(e0);
+    a.ev.push_back(e1);
   }
-  g_aux.flops += flops;
-  g_aux.bytes += bytes;
-  g_aux.launches += 1;
-  GG_CUDA_CHECK(prof_record(g_aux.ev[g_aux.used], stream));
+  a.flops += flops;
+  a.bytes += bytes;
+  a.launches += 1;
+  GG_CUDA_CHECK(prof_record(a.ev[a.used], stream));
   return GG_OK;
 }
-int prof_aux_end(cudaStream_t stream) {
+static int prof_chan_end(AuxProfile& a, cudaStream_t stream) {
   if (!g_prof.on) return GG_OK;
-  GG_CUDA_CHECK(prof_record(g_aux.ev[g_aux.used + 1], stream));
-  g_aux.used += 2;
+  GG_CUDA_CHECK(prof_record(a.ev[a.used + 1], stream));
+  a.used += 2;
   return GG_OK;
 }
+int prof_aux_begin(double flops, double bytes, cudaStream_t stream) { return prof_chan_begin(g_auxes[0], flops, bytes, stream); }
+int prof_aux_end(cudaStream_t stream) { return prof_chan_end(g_auxes[0], stream); }
+int prof_wgrad_begin(double flops, double bytes, cudaStream_t stream) { return prof_chan_begin(g_auxes[1], flops, bytes, stream); }
+int prof_wgrad_end(cudaStream_t stream) { return prof_chan_end(g_auxes[1], stream); }
 
 template <int BN, int STAGES, int EPIW, bool PAIR = false>
 static int launch_tc(const CUtensorMap* maps, const GemmArgs& args, cudaStream_t stream) {
@@ -1043,25 +1048,34 @@ extern "C" int gg_gemm_profile_begin(void) {
   gg::g_prof.flops = 0.0;
   gg::g_prof.bytes = 0.0;
   gg::g_prof.launches = 0;
-  gg::g_aux.used = 0;
-  gg::g_aux.flops = gg::g_aux.bytes = 0.0;
-  gg::g_aux.launches = 0;
+  for (gg::AuxProfile& a : gg::g_auxes) {
+    a.used = 0;
+    a.flops = a.bytes = 0.0;
+    a.launches = 0;
+  }
   return GG_OK;
 }
 // The fused encoder-layer launches of the last profiled region (call after gg_gemm_profile_end).
-extern "C" int gg_enc_layer_profile(double* ms, double* flops, double* bytes, long long* launches) {
-  using namespace gg;
+static int aux_profile_read(const gg::AuxProfile& a, double* ms, double* flops, double* bytes, long long* launches) {
   double total = 0.0;
-  for (size_t i = 0; i + 1 < g_aux.used; i += 2) {
+  for (size_t i = 0; i + 1 < a.used; i += 2) {
     float t = 0.f;
-    GG_CUDA_CHECK(cudaEventElapsedTime(&t, g_aux.ev[i], g_aux.ev[i + 1]));
+    GG_CUDA_CHECK(cudaEventElapsedTime(&t, a.ev[i], a.ev[i + 1]));
     total += t;
   }
   if (ms) *ms = total;
-  if (flops) *flops = g_aux.flops;
-  if (bytes) *bytes = g_aux.bytes;
-  if (launches) *launches = g_aux.launches;
+  if (flops) *flops = a.flops;
+  if (bytes) *bytes = a.bytes;
+  if (launches) *launches = a.launches;
   return GG_OK;
+}
+extern "C" int gg_enc_layer_profile(double* ms, double* flops, double* bytes, long long* launches) {
+  return aux_profile_read(gg::g_auxes[0], ms, flops, bytes, launches);
+}
+// The grouped weight-gradient launches (wgrad_group.cu) of the last profiled region: summed duration, 2*M*N*K flops and
+// algorithmic bytes (each bf16 operand matrix once, each fp32 output once).
+extern "C" int gg_wgrad_group_profile(double* ms, double* flops, double* bytes, long long* launches) {
+  return aux_profile_read(gg::g_auxes[1], ms, flops, bytes, launches);
 }
 // Synchronises the device and returns the summed duration (ms), FLOPs (2*M*N*K) and count of the
 // tcgen05 GEMM launches issued since gg_gemm_profile_begin().

@@ -67,6 +67,10 @@ int k_bn_fwd(const bf16* x, int64_t ldx, const float* gamma, const float* beta, 
 int k_bn_bwd(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, const float* mean, const float* rstd,
              const float* gamma, bf16* dx, int64_t lddx, float* dgamma, float* dbeta, int B, int E, cudaStream_t st);
 
+// live profiler channel of the grouped weight-gradient kernel (gemm.cu; no-ops unless gg_gemm_profile_begin is active)
+int prof_wgrad_begin(double flops, double bytes, cudaStream_t stream);
+int prof_wgrad_end(cudaStream_t stream);
+
 // ---- enc_layer.cu: one encoder layer forward as one tcgen05 kernel (S <= 16 tokens, E = 256, ffn = 512, 4 heads)
 typedef gg_enc_layer_params EncLayerParams;
 int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st);
@@ -133,10 +137,14 @@ struct AttnArgs {
   bf16* dq; int64_t lddq;                    // [nb*Lq, H*hd]   (per replica even if q is shared)
   bf16* dk; bf16* dv; int64_t lddkv;         // [nb*Lk, ...]    (per replica even if kv is shared)
   float* stat;                               // backward scratch: 2 * nb * H * Lq floats (lse, delta)
+  const uint32_t* dbits;                     // optional precomputed keep bits of the site (k_dropout_bits), or NULL
 };
 static_assert(sizeof(AttnArgs) == sizeof(gg_attn_args), "AttnArgs must mirror gg_attn_args");
 int k_attention_fwd(const AttnArgs& a, cudaStream_t st);
 int k_attention_bwd(const AttnArgs& a, cudaStream_t st);
+// keep bits of a dropout site drawn once (AttnArgs::dbits); words = dropout_bits_words(n_elems)
+int64_t dropout_bits_words(int64_t n_elems);
+int k_dropout_bits(const uint64_t* rng, uint32_t site, float p, int64_t n_elems, uint32_t* out, cudaStream_t st);
 
 // ---- optim.cu -------------------------------------------------------------------------------
 // total = sqrt(sum g^2) over n elements -> norm_out[0]; clip coefficient -> norm_out[1]

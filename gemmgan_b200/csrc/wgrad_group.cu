@@ -492,8 +492,18 @@ int k_wgrad_group(const WgradItem* items, int n, void* workspace, int64_t worksp
   int slots = num_sms;
   if (sm_cap > 0 && sm_cap < slots) slots = sm_cap;
   const unsigned grid = static_cast<unsigned>(work < slots ? work : slots);
+  {
+    double fl = 0.0, by = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const WgradItem& it = items[i];
+      fl += 2.0 * it.M * it.N * it.K;
+      by += 2.0 * (static_cast<double>(it.M) + it.N) * it.K + 4.0 * it.M * it.N;
+    }
+    GG_TRY_RC(prof_wgrad_begin(fl, by, st));
+  }
   launch_k(wgrad_group_kernel, grid, THREADS, SMEM_BYTES, st, P);
   GG_LAUNCH_CHECK();
+  GG_TRY_RC(prof_wgrad_end(st));
   return GG_OK;
 }
 

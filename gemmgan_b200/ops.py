@@ -118,9 +118,18 @@ def colsum_group(problems, workspace=None):
     return workspace
 
 
-def attention(qkv, nb, H, Lq, Lk=None, mask=None, drop_p=0.0, rng=None, site=0, dout=None):
+def dropout_bits(rng, site, p, n_elems):
+    """Keep bits of a dropout site drawn once (gg_dropout_bits): uint32 words, bit idx = element idx."""
+    L = _lib.lib()
+    out = torch.empty(int(L.gg_dropout_bits_words(n_elems)), dtype=torch.int32, device=rng.device)
+    _lib.check(L.gg_dropout_bits(rng.data_ptr(), site, float(p), n_elems, out.data_ptr(), _stream()))
+    return out
+
+
+def attention(qkv, nb, H, Lq, Lk=None, mask=None, drop_p=0.0, rng=None, site=0, dout=None, precomputed_bits=False):
     """Self-attention on a packed [nb*L, 3*H*hd] bf16 qkv tensor (the encoder-layer layout). Returns o, or
-    (o, dqkv) when `dout` is given (gg_attention_fwd / gg_attention_bwd)."""
+    (o, dqkv) when `dout` is given (gg_attention_fwd / gg_attention_bwd). precomputed_bits: draw the dropout mask
+    once with gg_dropout_bits and hand it to both passes (what the engine does for 17 .. 320 tokens)."""
     from . import _abi_decl as A
 
     L = _lib.lib()
@@ -133,6 +142,9 @@ def attention(qkv, nb, H, Lq, Lk=None, mask=None, drop_p=0.0, rng=None, site=0, 
         a.mask, a.mask_mod = mask.data_ptr(), mask.shape[0]
     a.nb, a.H, a.hd, a.Lq, a.Lk = nb, H, E // H, Lq, Lk
     a.drop_p, a.rng, a.site = drop_p, (rng.data_ptr() if rng is not None else None), site
+    if precomputed_bits and drop_p > 0.0:
+        bits = dropout_bits(rng, site, drop_p, nb * H * Lq * Lk)
+        a.dbits = bits.data_ptr()
     o = torch.empty(nb * Lq, E, device=qkv.device, dtype=torch.bfloat16)
     a.o, a.ldo = o.data_ptr(), E
     _lib.check(L.gg_attention_fwd(C.byref(a), _stream()))

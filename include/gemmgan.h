@@ -34,7 +34,7 @@ extern "C" {
 #define GG_ERR_CUDA (-3)
 #define GG_ERR_WORKSPACE (-4)
 
-#define GG_ABI_VERSION 3
+#define GG_ABI_VERSION 4
 
 const char* gg_last_error(void);
 int gg_abi_version(void);
@@ -347,9 +347,18 @@ typedef struct gg_attn_args {
   void* dq; int64_t lddq;
   void* dk; void* dv; int64_t lddkv;
   float* stat;
+  /* optional (may be NULL): the keep bits of this site's dropout stream drawn once by gg_dropout_bits (bit idx = element
+   * idx = ((b * H + h) * Lq + i) * Lk + j, 1 = kept), read by the 17..320-token self-attention kernels in forward and
+   * backward instead of drawing Philox groups per score tile; results are identical with and without it */
+  const uint32_t* dbits;
 } gg_attn_args;
 int gg_attention_fwd(const gg_attn_args* a, void* stream);
 int gg_attention_bwd(const gg_attn_args* a, void* stream);
+/* Keep bits of n_elems consecutive elements of the dropout stream {seed, step} at `rng` (device uint64[2]), site `site`,
+ * probability p: out[w] bit k = element 32 * w + k kept. `out` holds gg_dropout_bits_words(n_elems) uint32 words (the
+ * count includes the slack the attention kernels' unaligned 16-bit windows may touch). */
+int64_t gg_dropout_bits_words(int64_t n_elems);
+int gg_dropout_bits(const uint64_t* rng, uint32_t site, float p, int64_t n_elems, uint32_t* out, void* stream);
 
 /* One post-norm nn.TransformerEncoderLayer forward (d_model 256, 4 heads x 64, ffn 512, relu, dropout p) as ONE kernel
  * for short sequences (S <= 16 tokens: the paper model's 8 patches + CLS): in-proj, masked softmax attention, out-proj,
@@ -406,6 +415,8 @@ int gg_enc_layer_set_trace(void* device_buf);
 /* Live profile (bench.py): summed CUDA-event duration, algorithmic FLOPs / bytes and count of the fused encoder-layer
  * launches between gg_gemm_profile_begin and gg_gemm_profile_end (call after the latter). */
 int gg_enc_layer_profile(double* ms, double* flops, double* bytes, long long* launches);
+/* Same for the grouped weight-gradient launches (wgrad_group.cu): 2*M*N*K flops, bf16 operands + fp32 outputs once. */
+int gg_wgrad_group_profile(double* ms, double* flops, double* bytes, long long* launches);
 
 /* Grouped weight gradients: out_i[M_i, N_i] (fp32, pitch ld) = dY_i^T X_i for up to 32 problems in ONE launch
  * (autograd's grad_output.t().mm(input) of every Linear of one backward pass, :412 / :455). dY_i is stored

@@ -22,3 +22,7 @@ extern "C" int gg_attention_bwd(const gg_attn_args* a, void* stream) {
   GG_REQUIRE(a && a->q && a->k && a->v && a->dout && a->dq && a->dk && a->dv, "null argument");
   return gg::k_attention_bwd(*reinterpret_cast<const gg::AttnArgs*>(a), reinterpret_cast<cudaStream_t>(stream));
 }
+extern "C" int64_t gg_dropout_bits_words(int64_t n_elems) { return gg::dropout_bits_words(n_elems); }
+extern "C" int gg_dropout_bits(const uint64_t* rng, uint32_t site, float p, int64_t n_elems, uint32_t* out, void* stream) {
+  return gg::k_dropout_bits(rng, site, p, n_elems, out, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in gemmgan.h but not exported"
     assert set(_abi_decl.EXPORTS) <= set(names)
-    assert L.gg_abi_version() == _lib.ABI_VERSION == 3
+    assert L.gg_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header_sizes(tmp_path):

@@ -28,7 +28,7 @@ def check(L, rc):
     assert rc == 0, L.gg_last_error()
 
 
-def self_attention(L, qkv, nb, H, S, mask=None, drop_p=0.0, rng=None, site=0, dout=None):
+def self_attention(L, qkv, nb, H, S, mask=None, drop_p=0.0, rng=None, site=0, dout=None, precomputed_bits=False):
     """gemmgan_b200.ops.attention on host tensors: packed [nb*S, 3*H*hd] bf16 qkv (the encoder-layer layout)."""
     E = qkv.shape[1] // 3
     a = A.AttnArgs()
@@ -38,6 +38,14 @@ def self_attention(L, qkv, nb, H, S, mask=None, drop_p=0.0, rng=None, site=0, do
         a.mask, a.mask_mod = mask.data_ptr(), mask.shape[0]
     a.nb, a.H, a.hd, a.Lq, a.Lk = nb, H, E // H, S, S
     a.drop_p, a.rng, a.site = drop_p, (rng.data_ptr() if rng is not None else None), site
+    if precomputed_bits:   # the keep bits of the site drawn once (gg_dropout_bits), read by forward and backward
+        L.gg_dropout_bits_words.restype = C.c_int64
+        L.gg_dropout_bits_words.argtypes = [C.c_int64]
+        L.gg_dropout_bits.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]
+        n = nb * H * S * S
+        bits = torch.empty(int(L.gg_dropout_bits_words(n)), dtype=torch.int32)
+        check(L, L.gg_dropout_bits(rng.data_ptr(), site, drop_p, n, bits.data_ptr(), None))
+        a.dbits = bits.data_ptr()
     o = torch.empty(nb * S, E, dtype=torch.bfloat16)
     a.o, a.ldo = o.data_ptr(), E
     check(L, L.gg_attention_fwd(C.byref(a), None))
@@ -88,6 +96,23 @@ def test_self_attention_matches_sdpa(emu, nb, H, hd, S, masked):
     o_ref, g_ref = reference(qkv, nb, H, S, mask, dout)
     assert (o.float() - o_ref).abs().max().item() <= 1e-2 * o_ref.abs().max().item()
     assert (dqkv.float() - g_ref).abs().max().item() <= 1.5e-2 * g_ref.abs().max().item()
+
+
+@pytest.mark.parametrize("nb,S,masked", [(3, 65, True), (2, 17, False), (2, 140, True), (1, 257, False)])
+def test_precomputed_dropout_bits_equal_the_in_kernel_masks(emu, nb, S, masked):
+    """The mid / long kernels reading 16-bit windows of the once-drawn keep bits (AttnArgs.dbits) make exactly the
+    decisions they make when they draw the Philox groups themselves: outputs and gradients bitwise equal."""
+    H, E = 4, 256
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(nb * S, 3 * E, generator=g).bfloat16()
+    dout = torch.randn(nb * S, E, generator=g).bfloat16()
+    mask = None
+    if masked:
+        mask = (torch.arange(S)[None, :] >= (S - 1 - torch.arange(nb) * 3)[:, None]).to(torch.uint8)
+    rng = torch.tensor([99, 12], dtype=torch.int64)
+    o1, d1 = self_attention(emu, qkv, nb, H, S, mask=mask, drop_p=0.1, rng=rng, site=8, dout=dout)
+    o2, d2 = self_attention(emu, qkv, nb, H, S, mask=mask, drop_p=0.1, rng=rng, site=8, dout=dout, precomputed_bits=True)
+    assert torch.equal(o1, o2) and torch.equal(d1, d2)
 
 
 @pytest.mark.parametrize("nb,S", [(6, 9), (2, 65), (1, 140)])

@@ -76,6 +76,35 @@ def test_attention_dropout_forward_backward_consistent(nb, L):
     assert (o0.float() - o1.float()).abs().mean().item() > 1e-3
 
 
+@pytest.mark.parametrize("nb,L,masked", [(16, 65, False), (8, 100, True), (5, 17, False), (4, 257, True), (3, 290, False),
+                                         (6, 129, True)])
+def test_precomputed_dropout_bits_equal_the_in_kernel_masks(nb, L, masked):
+    """gg_dropout_bits draws the attention-probability keep bits once per layer pass; the mid / long kernels read 16-bit
+    windows of them in forward and backward (engine.cu::tower_forward). Same stream, same decisions: outputs and all three
+    gradients are bitwise those of the kernels drawing Philox groups themselves."""
+    H, hd = 4, 64
+    E = H * hd
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn(nb * L, 3 * E, device="cuda", generator=g).to(torch.bfloat16)
+    dout = torch.randn(nb * L, E, device="cuda", generator=g).to(torch.bfloat16)
+    mask = None
+    if masked:
+        mask = (torch.arange(L, device="cuda")[None, :] >= (L - torch.arange(nb, device="cuda") % 7)[:, None]).to(torch.uint8)
+    rng = torch.tensor([1234567, 42], device="cuda", dtype=torch.int64)
+    o1, d1 = ops.attention(qkv, nb, H, L, mask=mask, drop_p=0.1, rng=rng, site=8, dout=dout)
+    o2, d2 = ops.attention(qkv, nb, H, L, mask=mask, drop_p=0.1, rng=rng, site=8, dout=dout, precomputed_bits=True)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2) and torch.equal(d1, d2)
+    # the bit stream itself against the scalar definition (philox.cuh::dropout_keep) through a numpy port
+    from test_gpu_enc_layer import philox_keep
+    n = nb * H * L * L
+    bits = ops.dropout_bits(rng, 8, 0.1, n).cpu().numpy().view("uint32")
+    idx = torch.randint(0, n, (4096,), generator=torch.Generator().manual_seed(0)).numpy().astype("uint64")
+    got = (bits[idx >> 5] >> (idx & 31).astype("uint32")) & 1
+    want = philox_keep(1234567, 42, 8, idx, 0.1)
+    assert (got.astype(bool) == want).all()
+
+
 def _cross(q, kv, nb, H, Lk, mask=None, dout=None, kv_rows_shared=False):
     """Single-query cross-attention through the C ABI: q [nb, E], kv [nb(or nb/2)*Lk, 2E] (k | v)."""
     import ctypes as C
