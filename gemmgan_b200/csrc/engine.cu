@@ -310,6 +310,7 @@ struct gg_engine {
   bool text_lane_fwd = true, text_lane_bwd = false;  // GEMMGAN_TEXT_LANE = <fwd><bwd> digits overrides
   bool split_tail_flush = false;  // measured: splitting the last flush costs 0.28 ms / train() (the grouped kernel occupies every SM)
   bool fuse_bias = true;  // GEMMGAN_FUSE_BIAS=0: keep every bias gradient in the grouped column-sum kernel
+  bool gp_tf32 = false;   // GEMMGAN_GP_TF32=1 (gg_engine_gp_step)
   bool attn_bits = true;  // GEMMGAN_ATTN_BITS=0: the 17 .. 320-token attention kernels draw their dropout masks themselves
   bool fused_layer = true;  // GEMMGAN_FUSED_LAYER=0: encoder layers as seven launches instead of enc_layer.cu's one
   // one workspace per flush in flight: flushes of one entry point run back to back on their lane, so
@@ -1071,7 +1072,11 @@ static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, 
   TrunkBufs& t = e.tb;
   cudaStream_t st = e.S(0);
   const int B = c.B, H = c.H, G = c.G, E = c.E, net = GG_NET_DISC;
-  if (fake_f32 && real_f32) {
+  if (fake_f32 && real_f32 && H == 256 && !e.gp_tf32) {
+    // fp32 profiles read in place, converted on chip, weight k-blocks multicast across a cluster (xw_f32.cu)
+    const Op W1 = e.W(net, GG_P_TR0_W);
+    GG_TRY(k_xw_f32(fake_f32, real_f32, B, G, W1.p, W1.ld, t.a1x, e.splitk_l[0], e.splitk_bytes, st));
+  } else if (fake_f32 && real_f32) {
     const int64_t ldw = static_cast<int64_t>(G) + (e.cond ? E : 0);
     GG_TRY(e.linear_tf32(0, B, H, G, fake_f32, G, e.P(net, GG_P_TR0_W), ldw, Epi().of32(t.a1x, H)));
     GG_TRY(e.linear_tf32(0, B, H, G, real_f32, G, e.P(net, GG_P_TR0_W), ldw,
@@ -1604,14 +1609,17 @@ extern "C" int gg_engine_gp_step(gg_engine* e, const float* real_f32, const floa
   const gg_model_cfg& c = e->cfg;
   TrunkBufs& t = e->tb;
   const int B = c.B, H = c.H, G = c.G, net = GG_NET_DISC;
-  // The only [B, G] work of the penalty is critic layer 1 on real and fake. Default: cast both to bf16 once (as the
-  // training step does with its resident bf16 [fake; real] matrix), then one bf16 GEMM. GEMMGAN_GP_TF32=1: read both
-  // fp32 tensors in place with TF32 tensor-core GEMMs against the fp32 master weights -- no cast pass, 8 B G bytes of
-  // HBM traffic in all, but MEASURED SLOWER (B = 16384, G = 20000: 1.47 ms vs 1.15 ms): every 128-row tile re-streams
-  // the fp32 weight matrix (20 MB) from L2, and the L2 -> shared-memory fabric (~7 TB/s), not HBM, becomes the bound;
-  // it needs the weight k-blocks multicast across a cluster of M-tiles to pay off.
+  // The only [B, G] work of the penalty is critic layer 1 on real and fake. Default (H = 256): xw_f32.cu reads the two fp32
+  // tensors in place — 8 B G bytes of HBM traffic in all — converting to bf16 on chip and multicasting the weight k-blocks
+  // across a cluster of row tiles (round-2 history: cast pass + bf16 GEMM 1.15 ms at B = 16384, G = 20000; TF32 GEMMs on the
+  // fp32 tensors against the fp32 master weights 1.47 ms: every 128-row tile re-streamed the 20 MB fp32 weight matrix from
+  // L2 and the L2 -> shared-memory fabric, not HBM, became the bound).
+  // GEMMGAN_GP_DIRECT=0: cast both tensors to bf16 first (1.5x the HBM bytes), then the step's bf16 GEMM; GEMMGAN_GP_TF32=1:
+  // TF32 GEMMs on the fp32 tensors and fp32 master weights (measured slower: the fp32 weight matrix re-streamed per tile)
+  static const bool gp_direct = [] { const char* v = getenv("GEMMGAN_GP_DIRECT"); return !(v && v[0] == '0'); }();
   static const bool gp_tf32 = [] { const char* v = getenv("GEMMGAN_GP_TF32"); return v && v[0] == '1'; }();
-  const bool direct = gp_tf32 && c.gemm_impl == GG_IMPL_TCGEN05 && G % 4 == 0 &&
+  e->gp_tf32 = gp_tf32;
+  const bool direct = (gp_tf32 || (gp_direct && H == 256)) && c.gemm_impl == GG_IMPL_TCGEN05 && G % 4 == 0 &&
                       ((reinterpret_cast<uintptr_t>(real_f32) | reinterpret_cast<uintptr_t>(fake_f32)) & 15) == 0;
   if (direct) {
     GG_TRY(disc_forward_gp(*e, 1, 0.f, alpha, 0, 0, 0, fake_f32, real_f32));
@@ -1638,6 +1646,12 @@ extern "C" int gg_engine_gp_step(gg_engine* e, const float* real_f32, const floa
 // out[b, :] = sum over the non-padded rows p of x[b, p, :] / count_b  (conditional_gan_concat.py:137-138 /
 // :184-185 apply the Linear encoder to every patch and then take this masked mean; the encoder is affine, so
 // the mean is taken first and the encoder runs once per sample).
+extern "C" int gg_xw_f32(const float* x0, const float* x1, int32_t B, int32_t K, const void* w_bf16, int64_t ldw, float* out,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  return k_xw_f32(x0, x1, B, K, reinterpret_cast<const bf16*>(w_bf16), ldw, out, workspace, workspace_bytes,
+                  reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream) {
   GG_REQUIRE(x && out && B > 0 && P > 0 && D > 0, "bad argument");
   return k_masked_mean_rows(x, pad, out, B, P, D, reinterpret_cast<cudaStream_t>(stream));

@@ -67,6 +67,11 @@ int k_bn_fwd(const bf16* x, int64_t ldx, const float* gamma, const float* beta, 
 int k_bn_bwd(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, const float* mean, const float* rstd,
              const float* gamma, bf16* dx, int64_t lddx, float* dgamma, float* dbeta, int B, int E, cudaStream_t st);
 
+// ---- xw_f32.cu: critic layer 1 on the two fp32 [B, K] gene matrices of the gradient penalty, read in place (fp32 -> bf16
+// on chip, weight k-blocks TMA-multicast across a cluster): out [2B, 256] fp32
+int k_xw_f32(const float* x0, const float* x1, int B, int K, const bf16* w, int64_t ldw, float* out, void* workspace,
+             int64_t workspace_bytes, cudaStream_t st);
+
 // live profiler channel of the grouped weight-gradient kernel (gemm.cu; no-ops unless gg_gemm_profile_begin is active)
 int prof_wgrad_begin(double flops, double bytes, cudaStream_t stream);
 int prof_wgrad_end(cudaStream_t stream);

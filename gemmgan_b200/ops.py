@@ -118,6 +118,19 @@ def colsum_group(problems, workspace=None):
     return workspace
 
 
+def xw_f32(x0, x1, w_bf16, workspace_mb=96):
+    """[x0; x1] . w^T for two fp32 [B, K] matrices read in place and a bf16 [256, K] weight (gg_xw_f32) -> fp32 [2B, 256]."""
+    L = _lib.lib()
+    B, K = x0.shape
+    assert x1.shape == x0.shape and w_bf16.shape == (256, K) and x0.is_contiguous() and x1.is_contiguous()
+    assert w_bf16.stride(1) == 1 and w_bf16.stride(0) % 8 == 0
+    out = torch.empty(2 * B, 256, device=x0.device, dtype=torch.float32)
+    ws = torch.empty(workspace_mb << 20, device=x0.device, dtype=torch.uint8) if workspace_mb else None
+    _lib.check(L.gg_xw_f32(x0.data_ptr(), x1.data_ptr(), B, K, w_bf16.data_ptr(), w_bf16.stride(0), out.data_ptr(),
+                           None if ws is None else ws.data_ptr(), 0 if ws is None else ws.numel(), _stream()))
+    return out
+
+
 def dropout_bits(rng, site, p, n_elems):
     """Keep bits of a dropout site drawn once (gg_dropout_bits): uint32 words, bit idx = element idx."""
     L = _lib.lib()

@@ -310,6 +310,13 @@ int gg_engine_generate_keep(gg_engine* e, const float* z, float* out_f32, int tr
 int gg_engine_generate_backward(gg_engine* e, const float* dout_f32, float* dz_f32, void* stream);
 int gg_engine_critic_keep(gg_engine* e, const float* genes_f32, float* score_f32, int training, void* stream);
 int gg_engine_critic_backward(gg_engine* e, const float* dscore_f32, float* dgenes_f32, void* stream);
+/* Critic layer 1 on the two fp32 [B, K] gene matrices of the gradient penalty (real / fake of WGAN_GP.gradient_penalty,
+ * src/vanilla_gan_unconditional.py:304-327), read in place: out[0:B] = x0 . w^T, out[B:2B] = x1 . w^T (fp32 [2B, 256]);
+ * w = bf16 [256, K] with pitch ldw (elements). The fp32 -> bf16 conversion happens on chip and the weight k-blocks are
+ * TMA-multicast across a cluster of row tiles (csrc/xw_f32.cu). x rows 16-byte aligned, K % 4 == 0. workspace (may be
+ * NULL): split-K partial sums, up to 8 * 2B * 256 floats are used. */
+int gg_xw_f32(const float* x0, const float* x1, int32_t B, int32_t K, const void* w_bf16, int64_t ldw, float* out,
+              void* workspace, int64_t workspace_bytes, void* stream);
 /* out[b, :] (fp32) = mean over the rows p with pad[b, p] == 0 of x[b, p, :] — the masked mean of
  * conditional_gan_concat.py:137-138 ('image' conditioning), taken BEFORE the affine encoder. pad may be NULL. */
 int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream);

@@ -32,6 +32,10 @@ int k_wgrad_group(const WgradItem*, int, void*, int64_t, cudaStream_t) {
   set_error("the grouped weight-gradient kernel is tcgen05 only (not available in the host emulation)");
   return GG_ERR_ARCH;
 }
+int k_xw_f32(const float*, const float*, int, int, const bf16*, int64_t, float*, void*, int64_t, cudaStream_t) {
+  set_error("the fp32-input critic layer-1 kernel is tcgen05 only (not available in the host emulation)");
+  return GG_ERR_ARCH;
+}
 int k_enc_ffn_bwd(const EncFfnBwdParams&, cudaStream_t) {
   set_error("the fused ffn-backward kernel is tcgen05 only (not available in the host emulation)");
   return GG_ERR_ARCH;
