@@ -79,7 +79,8 @@ class EncLayerParams(C.Structure):
                 ("rng", C.c_void_p), ("site", C.c_uint32),
                 ("qkv", C.c_void_p), ("ao", C.c_void_p), ("z1", C.c_void_p), ("x1", C.c_void_p), ("h", C.c_void_p),
                 ("z2", C.c_void_p), ("out", C.c_void_p),
-                ("mean1", C.c_void_p), ("rstd1", C.c_void_p), ("mean2", C.c_void_p), ("rstd2", C.c_void_p)]
+                ("mean1", C.c_void_p), ("rstd1", C.c_void_p), ("mean2", C.c_void_p), ("rstd2", C.c_void_p),
+                ("dbits1", C.c_void_p), ("dbits2", C.c_void_p), ("dbits3", C.c_void_p)]
 
 
 class EncFfnBwdParams(C.Structure):
@@ -87,7 +88,7 @@ class EncFfnBwdParams(C.Structure):
     _fields_ = [("rows", C.c_int64), ("dout", C.c_void_p), ("z2", C.c_void_p), ("mean2", C.c_void_p),
                 ("rstd2", C.c_void_p), ("gamma2", C.c_void_p), ("h", C.c_void_p), ("w2t", C.c_void_p),
                 ("ld_w2t", C.c_int64), ("w1t", C.c_void_p), ("ld_w1t", C.c_int64), ("drop_p", C.c_float),
-                ("rng", C.c_void_p), ("site", C.c_uint32), ("gh", C.c_void_p), ("gb", C.c_void_p)]
+                ("rng", C.c_void_p), ("site", C.c_uint32), ("gh", C.c_void_p), ("gb", C.c_void_p), ("dbits", C.c_void_p)]
 
 
 class ColsumItem(C.Structure):

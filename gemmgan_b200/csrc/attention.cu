@@ -1578,7 +1578,49 @@ static int check_args(const AttnArgs& a) {
   return GG_OK;
 }
 
+// the same for up to three sites in one launch (the three per-element dropout sites of an encoder layer pass)
+struct DropBitsJobs {
+  uint32_t site[3];
+  int64_t n_words[3];
+  uint32_t* out[3];
+};
+__global__ void __launch_bounds__(256) dropout_bits3_kernel(const uint64_t* __restrict__ rng, float p, const DropBitsJobs jobs) {
+  pdl_entry();
+  const uint64_t seed = rng[0], step = rng[1];
+  const uint32_t thr = dropout_thr(p);
+  const int64_t total = jobs.n_words[0] + jobs.n_words[1] + jobs.n_words[2];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int j = 0;
+    int64_t w = i;
+    if (w >= jobs.n_words[0]) { w -= jobs.n_words[0]; j = 1; }
+    if (j == 1 && w >= jobs.n_words[1]) { w -= jobs.n_words[1]; j = 2; }
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      v |= keep_bits8(dropout_words(seed, step, jobs.site[j], static_cast<uint64_t>(w) * 4 + k), thr) << (8 * k);
+    jobs.out[j][w] = v;
+  }
+}
+
 int64_t dropout_bits_words(int64_t n_elems) { return (n_elems + 31) / 32 + 4; }
+int k_dropout_bits3(const uint64_t* rng, float p, const uint32_t (&site)[3], const int64_t (&n_elems)[3], uint32_t* const (&out)[3],
+                    cudaStream_t st) {
+  DropBitsJobs jobs;
+  int64_t total = 0;
+  for (int j = 0; j < 3; ++j) {
+    GG_REQUIRE(out[j] && n_elems[j] >= 0, "bad dropout-bits argument");
+    jobs.site[j] = site[j];
+    jobs.n_words[j] = dropout_bits_words(n_elems[j]);
+    jobs.out[j] = out[j];
+    total += jobs.n_words[j];
+  }
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_k(dropout_bits3_kernel, static_cast<unsigned>(blocks), 256, 0, st, rng, p, jobs);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
 int k_dropout_bits(const uint64_t* rng, uint32_t site, float p, int64_t n_elems, uint32_t* out, cudaStream_t st) {
   GG_REQUIRE(rng && out && n_elems >= 0, "bad dropout-bits argument");
   const int64_t n_words = dropout_bits_words(n_elems);

@@ -77,6 +77,7 @@ struct Args {
   uint32_t site;
   bf16 *qkv, *ao, *z1, *x1, *h, *z2, *out;
   float *mean1, *rstd1, *mean2, *rstd2;
+  const uint32_t *dbits1, *dbits2, *dbits3;  // precomputed keep bits of sites + 1 .. + 3 (or null: drawn here)
   long long* trace;  // diagnostics (gg_enc_layer_set_trace): clock64() stamps of CTA 0's first tile, 3 roles x 64
 };
 constexpr int TRACE_SLOTS = 64;
@@ -297,6 +298,8 @@ __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_base, uin
   }
 }
 
+// BITS: the dropout keep bits of sites + 1 .. + 3 come precomputed (Args::dbits*): no Philox in the LayerNorm / ffn epilogues
+template <bool BITS>
 __global__ void __launch_bounds__(THREADS, 1)
     enc_layer_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWin,
                          const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmW1,
@@ -593,9 +596,15 @@ __global__ void __launch_bounds__(THREADS, 1)
       // unrounded values into BUF0: x1 (the next MMA's A operand) or the layer output.
       // (the dropout keep bits of a phase are drawn BEFORE waiting for its accumulator: the epilogue warps idle there
       // while the MMA waits for its weight stages, and the Philox rounds are a third of the epilogue's instructions)
-      auto draw_masks = [&](uint32_t site, uint64_t elem0, uint32_t (&km)[2]) {
+      auto draw_masks = [&](uint32_t site, const uint32_t* bits, uint64_t elem0, uint32_t (&km)[2]) {
         km[0] = km[1] = 0;
-        if (drop) {
+        if (BITS) {  // elem0 is a multiple of 64: the thread's 64 keep bits are one aligned 8-byte word
+          if (drop && grow < a.rows_total) {
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(bits + (elem0 >> 5)));
+            km[0] = w.x;
+            km[1] = w.y;
+          }
+        } else if (drop) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             km[j >> 2] |= keep8(seed, step, site, (elem0 >> 3) + j, thr) << (8 * (j & 3));
@@ -680,7 +689,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         EL_STAMP(2, ts++);
       };
       uint32_t km[2];
-      draw_masks(a.site + 1, static_cast<uint64_t>(grow) * E + part * 64, km);
+      draw_masks(a.site + 1, a.dbits1, static_cast<uint64_t>(grow) * E + part * 64, km);
       EL_STAMP(2, ts++);
       mbar_wait(&bars[B_ACC2FULL], par);
       EL_STAMP(2, ts++);
@@ -699,7 +708,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       // ------------------------------------------------------------ ffn1 epilogues: h = drop(relu(x1 W1^T + b1))
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        draw_masks(a.site + 2, static_cast<uint64_t>(grow) * F + half * 256 + part * 64, km);
+        draw_masks(a.site + 2, a.dbits2, static_cast<uint64_t>(grow) * F + half * 256 + part * 64, km);
         mbar_wait(&bars[half == 0 ? B_F1AFULL : B_F1BFULL], par);
         tc_fence_after_sync();
         const uint32_t tm_acc = tm_lane + (half == 0 ? 256 : 0);
@@ -750,7 +759,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
 
       // ------------------------------------------------------------ ffn2 epilogue: out = LN2(x1 + drop(ff))
-      draw_masks(a.site + 3, static_cast<uint64_t>(grow) * E + part * 64, km);
+      draw_masks(a.site + 3, a.dbits3, static_cast<uint64_t>(grow) * E + part * 64, km);
       mbar_wait(&bars[B_OUTFULL], par);
       EL_STAMP(2, ts++);
       tc_fence_after_sync();
@@ -805,6 +814,9 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
   a.x1 = static_cast<bf16*>(p.x1); a.h = static_cast<bf16*>(p.h); a.z2 = static_cast<bf16*>(p.z2);
   a.out = static_cast<bf16*>(p.out);
   a.mean1 = p.mean1; a.rstd1 = p.rstd1; a.mean2 = p.mean2; a.rstd2 = p.rstd2;
+  GG_REQUIRE((p.dbits1 && p.dbits2 && p.dbits3) || (!p.dbits1 && !p.dbits2 && !p.dbits3),
+             "fused encoder layer: the precomputed dropout bits come as all three sites or none");
+  a.dbits1 = p.dbits1; a.dbits2 = p.dbits2; a.dbits3 = p.dbits3;
   a.trace = g_el_trace;
   CUtensorMap mX, mWin, mWo, mW1, mW2, mQKV, mAO, mZ1, mX1, mH, mZ2, mOut;
   GG_TRY_RC(encode_tma_map(&mX, p.x, E, a.rows_total, E, a.rows_pt, false));
@@ -825,7 +837,9 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(enc_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(enc_layer_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(enc_layer_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   GG_CUDA_CHECK(attr_err);
   static int num_sms = 0;
@@ -842,7 +856,10 @@ int k_enc_layer_fwd(const EncLayerParams& p, cudaStream_t st) {
     const double by = rows * E * 2 * 2 + (3.0 * E * E + E * E + 2.0 * E * F) * 2 + srows * (3 * E + 4 * E + F) * 2 + srows * 16;
     GG_TRY_RC(prof_aux_begin(fl, by, st));
   }
-  launch_k(enc_layer_fwd_kernel, static_cast<unsigned>(grid), THREADS, SMEM_BYTES, st, mX, mWin, mWo, mW1, mW2, mQKV, mAO, mZ1, mX1, mH, mZ2, mOut, a);
+  if (a.dbits1 && a.drop_p > 0.f)
+    launch_k(enc_layer_fwd_kernel<true>, static_cast<unsigned>(grid), THREADS, SMEM_BYTES, st, mX, mWin, mWo, mW1, mW2, mQKV, mAO, mZ1, mX1, mH, mZ2, mOut, a);
+  else
+    launch_k(enc_layer_fwd_kernel<false>, static_cast<unsigned>(grid), THREADS, SMEM_BYTES, st, mX, mWin, mWo, mW1, mW2, mQKV, mAO, mZ1, mX1, mH, mZ2, mOut, a);
   GG_LAUNCH_CHECK();
   GG_TRY_RC(prof_aux_end(st));
   return GG_OK;
@@ -878,6 +895,7 @@ struct BArgs {
   float drop_p;
   const uint64_t* rng;
   uint32_t site;     // dropout site of the LayerNorm-2 residual branch (layer site + 3)
+  const uint32_t* dbits;  // its precomputed keep bits, or null
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
@@ -1018,7 +1036,13 @@ __global__ void __launch_bounds__(THREADS, 1)
       const bool valid = grow < a.rows;
       const int trow = tile * 128;
       uint32_t km[2] = {0, 0};
-      if (drop) {
+      if (drop && a.dbits) {
+        if (valid) {
+          const uint2 w = __ldg(reinterpret_cast<const uint2*>(a.dbits + ((static_cast<uint64_t>(grow) * E + part * 64) >> 5)));
+          km[0] = w.x;
+          km[1] = w.y;
+        }
+      } else if (drop) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           km[j >> 2] |= keep8(seed, step, a.site, ((static_cast<uint64_t>(grow) * E + part * 64) >> 3) + j, thr) << (8 * (j & 3));
@@ -1170,6 +1194,7 @@ int k_enc_ffn_bwd(const EncFfnBwdParams& p, cudaStream_t st) {
   a.mean = p.mean2; a.rstd = p.rstd2; a.gamma = p.gamma2;
   a.h = static_cast<const bf16*>(p.h);
   a.drop_p = p.drop_p; a.rng = p.rng; a.site = p.site;
+  a.dbits = p.dbits;
   CUtensorMap mG, mZ, mW2T, mW1T, mGH, mGB;
   GG_TRY_RC(encode_tma_map(&mG, p.dout, E, p.rows, E, 128, false));
   GG_TRY_RC(encode_tma_map(&mZ, p.z2, E, p.rows, E, 128, false));

@@ -84,6 +84,7 @@ struct NetShadow {
 
 struct TowerLayer {
   uint32_t* dbits = nullptr;  // keep bits of the attention-probability dropout of this layer pass (17 .. 320 tokens)
+  uint32_t* lbits[3] = {nullptr, nullptr, nullptr};  // fused layer (<= 16 tokens): keep bits of sites + 1, + 2, + 3
   bf16 *qkv, *ao, *z1, *x1, *h, *z2;
   float *mean1, *rstd1, *mean2, *rstd2;
 };
@@ -199,6 +200,24 @@ struct gg_engine {
     if (dst != 0) forked[dst] = true;
     return GG_OK;
   }
+  // the two halves of wait_lane apart: an event recorded on `src` now, waited for by `dst` later
+  int record_lane(int src, cudaEvent_t* ev_out) {
+    src = L(src);
+    *ev_out = nullptr;
+    if (src != 0 && !forked[src]) return GG_OK;
+    cudaEvent_t ev = evs[ev_next];
+    ev_next = (ev_next + 1) % NEVENTS;
+    GG_CUDA_CHECK(cudaEventRecord(ev, cur[src]));
+    *ev_out = ev;
+    return GG_OK;
+  }
+  int wait_event(int dst, cudaEvent_t ev) {
+    if (!ev) return GG_OK;
+    dst = L(dst);
+    GG_CUDA_CHECK(cudaStreamWaitEvent(cur[dst], ev, 0));
+    if (dst != 0) forked[dst] = true;
+    return GG_OK;
+  }
   int join_all() {
     for (int l = 1; l < NLANES; ++l) {
       int rc = join(l);
@@ -310,6 +329,11 @@ struct gg_engine {
   bool text_lane_fwd = true, text_lane_bwd = false;  // GEMMGAN_TEXT_LANE = <fwd><bwd> digits overrides
   bool split_tail_flush = false;  // measured: splitting the last flush costs 0.28 ms / train() (the grouped kernel occupies every SM)
   bool fuse_bias = true;  // GEMMGAN_FUSE_BIAS=0: keep every bias gradient in the grouped column-sum kernel
+  // GEMMGAN_LAYER_BITS=1: the fused layer kernels (<= 16 tokens) read precomputed keep bits too. MEASURED SLOWER at cfg3
+  // (7.39 vs 7.00 ms per train() on the same box): the fused kernel already draws its masks while its epilogue warps
+  // wait for the accumulators, so nothing leaves its critical path, and the extra mask launches take SM time from the
+  // tower head. Off by default; results are bitwise the same either way (tests/test_gpu_enc_layer.py).
+  bool layer_bits = false;
   bool gp_tf32 = false;   // GEMMGAN_GP_TF32=1 (gg_engine_gp_step)
   bool attn_bits = true;  // GEMMGAN_ATTN_BITS=0: the 17 .. 320-token attention kernels draw their dropout masks themselves
   bool fused_layer = true;  // GEMMGAN_FUSED_LAYER=0: encoder layers as seven launches instead of enc_layer.cu's one
@@ -320,6 +344,11 @@ struct gg_engine {
 };
 
 namespace gg {
+
+static bool layer_bits_requested() {
+  static const bool on = [] { const char* v = getenv("GEMMGAN_LAYER_BITS"); return v && v[0] == '1'; }();
+  return on;
+}
 
 static bool slot_matrix_shape(const gg_model_cfg& c, int net, int slot, int* rows, int* cols) {
   const int E = c.E, F = c.ffn, condw = c.variant == GG_VARIANT_VANILLA ? 0 : E;
@@ -414,6 +443,11 @@ static void layout_tower(gg_engine& e, Tower& t, int Rmax, Arena& ar) {
     L.z2 = ar.take<bf16>(rows * E);
     if (c.dropout_p > 0.f && S > 16 && !e.attn)
       L.dbits = ar.take<uint32_t>(dropout_bits_words(static_cast<int64_t>(Rmax) * B * c.n_heads * S * S));
+    if (c.dropout_p > 0.f && S <= 16 && !e.attn && layer_bits_requested()) {
+      L.lbits[0] = ar.take<uint32_t>(dropout_bits_words(rows * E));
+      L.lbits[1] = ar.take<uint32_t>(dropout_bits_words(rows * F));
+      L.lbits[2] = ar.take<uint32_t>(dropout_bits_words(rows * E));
+    }
     L.mean1 = ar.take<float>(rows);
     L.rstd1 = ar.take<float>(rows);
     L.mean2 = ar.take<float>(rows);
@@ -676,6 +710,22 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
   // text side of the paper model (:140, :149-152): token projection, the patch2text query and the text2patch
   // keys / values depend on the text only — they run on lane 2 next to the patch encoder of lane `ln`
   const int tl = e.text_lane_fwd ? 2 : ln;
+  // The per-element dropout masks of the fused layer kernels depend on nothing but the step counter: they are drawn here,
+  // once, next to the tower head (side lane), and the layer kernels read bits instead of running Philox in their epilogues
+  const bool layer_bits = p > 0.f && e.layer_bits && e.fused_layer && cfg_fused_layer_ok(e) && t.L[0].lbits[0] != nullptr;
+  cudaEvent_t bits_ready = nullptr;
+  if (layer_bits) {
+    const int bl = 2;
+    GG_TRY(e.wait_lane(bl, ln));
+    for (int l = 0; l < c.n_layers; ++l) {
+      const uint32_t site = site0 + 8u * l;
+      const uint32_t sites[3] = {site + 1, site + 2, site + 3};
+      const int64_t n[3] = {static_cast<int64_t>(rows) * E, static_cast<int64_t>(rows) * F, static_cast<int64_t>(rows) * E};
+      uint32_t* const outs[3] = {t.L[l].lbits[0], t.L[l].lbits[1], t.L[l].lbits[2]};
+      GG_TRY(k_dropout_bits3(e.rng, p, sites, n, outs, e.S(bl)));
+    }
+    if (e.L(bl) != e.L(ln)) GG_TRY(e.record_lane(bl, &bits_ready));  // waited for just before the first layer
+  }
   if (e.paper) {
     const Op Wp = e.W(net, GG_P_P2T_IN_W), Wt = e.W(net, GG_P_T2P_IN_W);
     const float* bp = e.P(net, GG_P_P2T_IN_B);
@@ -707,6 +757,7 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
     const uint32_t site = site0 + 8u * l;
     if (e.fused_layer && cfg_fused_layer_ok(e)) {
       // the whole post-norm layer as one tcgen05 kernel (enc_layer.cu): same tensors, same dropout streams
+      if (l == 0 && bits_ready) GG_TRY(e.wait_event(ln, bits_ready));
       EncLayerParams q;
       memset(&q, 0, sizeof(q));
       q.nb = R * B; q.S = S; q.E = E; q.F = F; q.n_heads = c.n_heads;
@@ -724,6 +775,7 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
       q.drop_p = p; q.eps = c.ln_eps; q.rng = e.rng; q.site = site;
       q.qkv = L.qkv; q.ao = L.ao; q.z1 = L.z1; q.x1 = L.x1; q.h = L.h; q.z2 = L.z2; q.out = t.X[l + 1];
       q.mean1 = L.mean1; q.rstd1 = L.rstd1; q.mean2 = L.mean2; q.rstd2 = L.rstd2;
+      if (p > 0.f && L.lbits[0] && e.layer_bits) { q.dbits1 = L.lbits[0]; q.dbits2 = L.lbits[1]; q.dbits3 = L.lbits[2]; }
       GG_TRY(k_enc_layer_fwd(q, st));
       continue;
     }
@@ -962,6 +1014,7 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
       q.w2t = e.sh[net].wt[ls + GG_L_FF2_W].p; q.ld_w2t = e.sh[net].wt[ls + GG_L_FF2_W].ld;
       q.w1t = e.sh[net].wt[ls + GG_L_FF1_W].p; q.ld_w1t = e.sh[net].wt[ls + GG_L_FF1_W].ld;
       q.drop_p = p; q.rng = e.rng; q.site = site + 3;
+      if (p > 0.f && L.lbits[2] && e.layer_bits && e.fused_layer && cfg_fused_layer_ok(e)) q.dbits = L.lbits[2];
       q.gh = lg.gh; q.gb = g.gb;
       GG_TRY(k_enc_ffn_bwd(q, st));
       GG_TRY(e.wgrad(E, F, rows, Op{dff, E}, Op{L.h, F}, e.Gr(net, ls + GG_L_FF2_W), F));
@@ -1183,6 +1236,7 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
     e->fuse_bias = !(fb && fb[0] == '0');
     const char* fl = getenv("GEMMGAN_FUSED_LAYER");
     e->fused_layer = !(fl && fl[0] == '0');
+    e->layer_bits = layer_bits_requested();
     const char* ab = getenv("GEMMGAN_ATTN_BITS");
     e->attn_bits = !(ab && ab[0] == '0');
   }

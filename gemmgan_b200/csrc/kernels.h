@@ -150,6 +150,8 @@ int k_attention_bwd(const AttnArgs& a, cudaStream_t st);
 // keep bits of a dropout site drawn once (AttnArgs::dbits); words = dropout_bits_words(n_elems)
 int64_t dropout_bits_words(int64_t n_elems);
 int k_dropout_bits(const uint64_t* rng, uint32_t site, float p, int64_t n_elems, uint32_t* out, cudaStream_t st);
+int k_dropout_bits3(const uint64_t* rng, float p, const uint32_t (&site)[3], const int64_t (&n_elems)[3], uint32_t* const (&out)[3],
+                    cudaStream_t st);
 
 // ---- optim.cu -------------------------------------------------------------------------------
 // total = sqrt(sum g^2) over n elements -> norm_out[0]; clip coefficient -> norm_out[1]

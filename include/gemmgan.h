@@ -393,6 +393,10 @@ typedef struct gg_enc_layer_params {
   const uint64_t* rng; uint32_t site;
   void *qkv, *ao, *z1, *x1, *h, *z2, *out;
   float *mean1, *rstd1, *mean2, *rstd2;
+  /* optional (all three or none): keep bits of the dropout sites site + 1 ([rows, E]), site + 2 ([rows, F]), site + 3
+   * ([rows, E]) drawn beforehand by gg_dropout_bits (bit idx = row * width + column); the kernel then reads one 64-bit
+   * word per thread and phase instead of running eight Philox groups. Same decisions, same results. */
+  const uint32_t *dbits1, *dbits2, *dbits3;
 } gg_enc_layer_params;
 int gg_encoder_layer_fwd(const gg_enc_layer_params* p, void* stream);
 /* The feed-forward half of the same layer's BACKWARD, dependent chain only, as one kernel: LayerNorm-2 backward of
@@ -414,6 +418,7 @@ typedef struct gg_enc_ffn_bwd_params {
   float drop_p; const uint64_t* rng; uint32_t site;
   void* gh;
   void* gb;
+  const uint32_t* dbits; /* optional: keep bits of `site` ([rows, 256]) as handed to gg_encoder_layer_fwd (dbits3) */
 } gg_enc_ffn_bwd_params;
 int gg_encoder_ffn_bwd(const gg_enc_ffn_bwd_params* p, void* stream);
 /* Diagnostics: CTA 0 of every following gg_encoder_layer_fwd launch stamps clock64() per pipeline role for its first

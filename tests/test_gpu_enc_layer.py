@@ -92,7 +92,7 @@ def make_weights(bias, seed=0):
     return W
 
 
-def run_kernel(x, W, mask, nb, S, p, seed, step, site, save_rows):
+def run_kernel(x, W, mask, nb, S, p, seed, step, site, save_rows, precomputed_bits=False):
     L = _lib.lib()
     rows = nb * S
     dev = x.device
@@ -114,6 +114,11 @@ def run_kernel(x, W, mask, nb, S, p, seed, step, site, save_rows):
     P.drop_p, P.eps, P.rng, P.site = p, 1e-5, rng.data_ptr(), site
     for k in out:
         setattr(P, k, out[k].data_ptr())
+    if precomputed_bits:   # the engine's way: the three per-element masks drawn once by gg_dropout_bits
+        from gemmgan_b200 import ops
+        keep = [ops.dropout_bits(rng, site + 1, p, rows * E), ops.dropout_bits(rng, site + 2, p, rows * F),
+                ops.dropout_bits(rng, site + 3, p, rows * E)]
+        P.dbits1, P.dbits2, P.dbits3 = (k.data_ptr() for k in keep)
     _lib.check(L.gg_encoder_layer_fwd(C.byref(P), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     return out
@@ -159,6 +164,20 @@ def test_fused_layer_matches_torch(nb, S, bias, masked, p, save):
         if n_save:
             assert torch.allclose(got[k][:n_save], want[k][:n_save], rtol=2e-2, atol=2e-3), k
         assert torch.isnan(got[k][n_save:]).all(), k
+
+
+@pytest.mark.parametrize("nb,S,save", [(40, 9, -1), (300, 9, 9 * 200), (37, 16, -1), (3072, 9, 0)])
+def test_fused_layer_with_precomputed_dropout_bits_is_bitwise_the_same(nb, S, save):
+    """Reading the keep bits gg_dropout_bits drew (what the engine does: the masks depend only on the step counter and are
+    drawn next to the tower head) instead of running Philox in the epilogues: every output tensor bit for bit."""
+    _lib.require_device(0)
+    torch.manual_seed(2)
+    x = torch.randn(nb * S, E, device="cuda").bfloat16()
+    W = make_weights(True)
+    a = run_kernel(x, W, None, nb, S, 0.1, 0x77AA, 3, 16, save)
+    b = run_kernel(x, W, None, nb, S, 0.1, 0x77AA, 3, 16, save, precomputed_bits=True)
+    for k in a:
+        assert torch.equal(torch.nan_to_num(a[k].float(), nan=-7.0), torch.nan_to_num(b[k].float(), nan=-7.0)), k
 
 
 def test_fused_layer_is_deterministic_and_dropout_changes_with_the_step():
