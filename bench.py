@@ -321,6 +321,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("GEMMGAN_NUMA_BIND", "1") != "0":   # pinned batch buffers on the GPU's own NUMA node
+            from gemmgan_b200.ddp import bind_to_gpu_numa_node
+            cfg["numa_node"] = bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     _lib.require_device(local)

@@ -1358,6 +1358,418 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
   }
 }
 
+// ---- second form of the long kernel (default): register-blocked against shared-memory bandwidth.
+// ncu of the kernel above at cfg2 (profiles/r02_attn_long_ncu_full_summary.txt): backward "Mem Busy" 78 %, tensor pipe 29 %:
+// with one 16-row tile per warp every m16n8k16 pair is fed by its own ldmatrix.x4 (12 per 16 MMAs forward, 52 per 64
+// backward). Here a warp owns TWO query tiles in the forward and in backward phase 1 — the A fragments of Q (and dO) stay in
+// registers for the whole key walk and every K / V fragment load feeds both tiles — and in phase 2 the A fragments of its key
+// tile (K, V) are loaded once: 4 ldmatrix per 16 MMAs forward, 24 per 64 backward. Half as many warps (9 for 257 tokens), so
+// the register cap of the launch bound doubles.
+__device__ __forceinline__ void load_a_frags(uint32_t (&fa)[4][4], const bf16* A, int lane) {
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) ldsm_x4(fa[kk], A + arow * SELF_PITCH + kk * 16 + acol);
+}
+// C[q] (16 x 16) = A[q] (fragments) * B^T, B = one 16-row tile [16 (n)][64 (k)] in smem, for NQ A tiles at once
+template <int NQ>
+__device__ __forceinline__ void mma_frags_bt(float (&c)[NQ][2][4], const uint32_t (&fa)[NQ][4][4], const bf16* B, int lane) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[q][nt][j] = 0.f;
+  const int brow = (lane & 7) + (lane >> 4) * 8, bcol = ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t b[4];
+    ldsm_x4(b, B + brow * SELF_PITCH + kk * 16 + bcol);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      mma16816(c[q][0], fa[q][kk], b[0], b[1]);
+      mma16816(c[q][1], fa[q][kk], b[2], b[3]);
+    }
+  }
+}
+// O[q] (16 x 64) += P[q] (16 x 16 fragments) * B, B = [16 (k)][64 (n)] row-major in smem, for NQ tiles at once
+template <int NQ>
+__device__ __forceinline__ void mma_frags_b_acc(float (&o)[NQ][8][4], const uint32_t (&pa)[NQ][4], const bf16* B, int lane) {
+  const int brow = (lane & 7) + ((lane >> 3) & 1) * 8, bcol = (lane >> 4) * 8;
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    uint32_t b[4];
+    ldsm_x4_t(b, B + brow * SELF_PITCH + np * 16 + bcol);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      mma16816(o[q][2 * np], pa[q], b[0], b[1]);
+      mma16816(o[q][2 * np + 1], pa[q], b[2], b[3]);
+    }
+  }
+}
+
+template <int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) attn_self_long2_kernel(const AttnArgs a) {
+  pdl_entry();
+  extern __shared__ __align__(16) uint8_t smem_long[];
+  const int S = a.Lq;
+  const int NT = (S + 15) / 16;
+  const int ROWS = NT * 16;
+  constexpr int NTEN = MODE == 1 ? 4 : 3;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_long);
+  bf16* Ks = Qs + ROWS * SELF_PITCH;
+  bf16* Vs = Ks + ROWS * SELF_PITCH;
+  bf16* Gs = Vs + ROWS * SELF_PITCH;                   // dO (backward only)
+  bf16* stage_all = Qs + NTEN * ROWS * SELF_PITCH;     // one 16-row staging tile per warp
+  float* row_m = reinterpret_cast<float*>(stage_all + WARPS * SELF_TILE);  // backward: per query row
+  float* row_il = row_m + ROWS;
+  float* row_delta = row_il + ROWS;
+  uint8_t* kval = reinterpret_cast<uint8_t*>(row_delta + ROWS);                 // key j usable (in range, not padded)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = static_cast<int>(blockIdx.x) / a.H, h = static_cast<int>(blockIdx.x) % a.H;
+  const uint8_t* mk = a.mask ? a.mask + static_cast<int64_t>(b % a.mask_mod) * S : nullptr;
+  {
+    const int col = h * SELF_HD;
+    const int64_t qb = static_cast<int64_t>(a.q_mod >= a.nb ? b : b % a.q_mod) * S;
+    const int64_t kb = static_cast<int64_t>(a.kv_mod >= a.nb ? b : b % a.kv_mod) * S;
+    for (int idx = threadIdx.x; idx < ROWS * 8; idx += WARPS * 32) {
+      const int row = idx >> 3, part = idx & 7;
+      const bool valid = row < S;
+      bf16* dst = Qs + row * SELF_PITCH + part * 8;
+      cp_async16(dst, valid ? a.q + (qb + row) * a.ldq + col + part * 8 : a.q, valid);
+      cp_async16(dst + ROWS * SELF_PITCH, valid ? a.k + (kb + row) * a.ldkv + col + part * 8 : a.q, valid);
+      cp_async16(dst + 2 * ROWS * SELF_PITCH, valid ? a.v + (kb + row) * a.ldkv + col + part * 8 : a.q, valid);
+      if (MODE == 1)
+        cp_async16(dst + 3 * ROWS * SELF_PITCH,
+                   valid ? a.dout + (static_cast<int64_t>(b) * S + row) * a.lddo + col + part * 8 : a.q, valid);
+    }
+    for (int j = threadIdx.x; j < ROWS; j += WARPS * 32) kval[j] = (j < S && !(mk && mk[j])) ? 1 : 0;
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncthreads();
+  const float scale = 0.125f;
+  const int g = lane >> 2, t = lane & 3;
+  bf16* stage = stage_all + warp * SELF_TILE;
+  const bool drop = a.drop_p > 0.f;
+  uint64_t seed = 0, step = 0;
+  if (drop) {
+    seed = a.rng[0];
+    step = a.rng[1];
+  }
+  const bool use_bits = drop && a.dbits != nullptr;
+  const float keep_scale = drop ? 1.f / (1.f - a.drop_p) : 1.f;
+  const uint64_t head_base = (static_cast<uint64_t>(b) * a.H + h) * static_cast<uint64_t>(S);  // + i -> row of P
+  auto key_of = [&](int kt, int e) { return kt * 16 + (e >> 1) * 8 + 2 * t + (e & 1); };
+  // keep decision of element (i, j) when the masks are not precomputed
+  auto keep_of = [&](int i, int j) {
+    return dropout_keep(seed, step, a.site, (head_base + i) * static_cast<uint64_t>(S) + j, a.drop_p);
+  };
+
+  for (int qp = warp; qp * 2 < NT; qp += WARPS) {
+    const int qt0 = qp * 2;
+    const int nq = qt0 + 1 < NT ? 2 : 1;  // the last pair of an odd tile count has one tile (the other: tile qt0 again, unused)
+    const int qts[2] = {qt0, nq == 2 ? qt0 + 1 : qt0};
+    uint32_t qa[2][4][4];
+    load_a_frags(qa[0], Qs + qts[0] * SELF_TILE, lane);
+    load_a_frags(qa[1], Qs + qts[1] * SELF_TILE, lane);
+    uint64_t wrow[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh)
+        wrow[q][rh] = (head_base + min(qts[q] * 16 + g + rh * 8, S - 1)) * static_cast<uint64_t>(S);
+    // ---- online softmax statistics (and, forward, the output) over the key tiles
+    float m_run[2][2], l_thr[2][2];
+    float o[2][8][4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      m_run[q][0] = m_run[q][1] = -INFINITY;
+      l_thr[q][0] = l_thr[q][1] = 0.f;
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[q][n][j] = 0.f;
+    }
+    for (int kt = 0; kt < NT; ++kt) {
+      uint32_t win[2][2] = {{0xFFFFu, 0xFFFFu}, {0xFFFFu, 0xFFFFu}};
+      if (MODE == 0 && use_bits) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) win[q][rh] = keep_window16(a.dbits, wrow[q][rh] + kt * 16);
+      }
+      uint32_t kv4 = 0;  // validity of this thread's four key columns
+#pragma unroll
+      for (int e = 0; e < 4; ++e) kv4 |= kval[key_of(kt, e)] ? (1u << e) : 0u;
+      float sc[2][2][4];
+      mma_frags_bt<2>(sc, qa, Ks + kt * SELF_TILE, lane);
+      uint32_t pa[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float pv[2][4];
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          float tm = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v = ((kv4 >> e) & 1u) ? sc[q][e >> 1][rh * 2 + (e & 1)] * SCALE_LOG2E : -INFINITY;
+            pv[rh][e] = v;
+            tm = fmaxf(tm, v);
+          }
+          tm = quad_max(tm);
+          const float m_new = fmaxf(m_run[q][rh], tm);  // running maximum, log2 domain
+          const float m_use = m_new == -INFINITY ? 0.f : m_new;
+          const float corr = fast_ex2(m_run[q][rh] - m_use);  // m_run = -inf -> 0
+          m_run[q][rh] = m_new;
+          float ls = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            pv[rh][e] = fast_ex2(pv[rh][e] - m_use);
+            ls += pv[rh][e];
+          }
+          l_thr[q][rh] = l_thr[q][rh] * corr + ls;
+          if (MODE == 0) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+              o[q][n][rh * 2] *= corr;
+              o[q][n][rh * 2 + 1] *= corr;
+            }
+          }
+        }
+        if (MODE == 0) {
+          if (use_bits) {
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                pv[rh][e] = ((win[q][rh] >> ((e >> 1) * 8 + 2 * t + (e & 1))) & 1u) ? pv[rh][e] * keep_scale : 0.f;
+          } else if (drop) {
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh) {
+              const int i = qts[q] * 16 + g + rh * 8;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = key_of(kt, e);
+                if (i < S && j < S) pv[rh][e] = keep_of(i, j) ? pv[rh][e] * keep_scale : 0.f;
+              }
+            }
+          }
+          pa[q][0] = pack_bf16(pv[0][0], pv[0][1]);
+          pa[q][1] = pack_bf16(pv[1][0], pv[1][1]);
+          pa[q][2] = pack_bf16(pv[0][2], pv[0][3]);
+          pa[q][3] = pack_bf16(pv[1][2], pv[1][3]);
+        }
+      }
+      if (MODE == 0) mma_frags_b_acc<2>(o, pa, Vs + kt * SELF_TILE, lane);
+    }
+    float inv_l[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const float l = quad_add(l_thr[q][rh]);
+        inv_l[q][rh] = l > 0.f ? 1.f / l : 0.f;
+      }
+    if (MODE == 0) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q >= nq) break;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          o[q][n][0] *= inv_l[q][0]; o[q][n][1] *= inv_l[q][0];
+          o[q][n][2] *= inv_l[q][1]; o[q][n][3] *= inv_l[q][1];
+        }
+        store_tile(stage, o[q], 1.f, a.o + (static_cast<int64_t>(b) * S + qts[q] * 16) * a.ldo + h * SELF_HD, a.ldo,
+                   min(16, S - qts[q] * 16), lane);
+      }
+      continue;
+    }
+    // ---- backward, phase 1: delta_i = dO_i . O_i, then dQ for both tiles
+    float m_safe[2][2], delta[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int qt = qts[q];
+      const int rows_valid = min(16, S - qt * 16);
+      const bf16* Gt = Gs + qt * SELF_TILE;
+      {
+        const int r = lane >> 1, hf = lane & 1;  // row of the tile, half of the 64 head dims
+        float acc = 0.f;
+        if (r < rows_valid) {
+          const bf16* orow = a.o + (static_cast<int64_t>(b) * S + qt * 16 + r) * a.ldo + h * SELF_HD + hf * 32;
+          const bf16* grow = Gt + r * SELF_PITCH + hf * 32;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 ov = __ldg(reinterpret_cast<const uint4*>(orow) + c);
+            const uint4 gv = *reinterpret_cast<const uint4*>(grow + c * 8);
+            const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&ov);
+            const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&gv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 fx = __bfloat1622float2(x[k]), fy = __bfloat1622float2(y[k]);
+              acc = fmaf(fx.x, fy.x, acc);
+              acc = fmaf(fx.y, fy.y, acc);
+            }
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (hf == 0 && q < nq) row_delta[qt * 16 + r] = acc;
+      }
+      if (t == 0 && q < nq) {
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          const int i = qt * 16 + g + rh * 8;
+          row_m[i] = m_run[q][rh] == -INFINITY ? 0.f : m_run[q][rh];
+          row_il[i] = i < S ? inv_l[q][rh] : 0.f;  // rows beyond S contribute nothing in phase 2
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        m_safe[q][rh] = m_run[q][rh] == -INFINITY ? 0.f : m_run[q][rh];
+        delta[q][rh] = row_delta[qt * 16 + g + rh * 8];
+      }
+    }
+    // the dO fragments stay in registers too when the launch bound leaves room (<= 8 warps: 255 registers per thread; 9
+    // and 10 warps put three warps on one scheduler and cap the kernel at 168)
+    constexpr bool HOIST_G = WARPS <= 8;
+    uint32_t ga[2][4][4];
+    if (HOIST_G) {
+      load_a_frags(ga[0], Gs + qts[0] * SELF_TILE, lane);
+      load_a_frags(ga[1], Gs + qts[1] * SELF_TILE, lane);
+    }
+    for (int kt = 0; kt < NT; ++kt) {
+      uint32_t win[2][2] = {{0xFFFFu, 0xFFFFu}, {0xFFFFu, 0xFFFFu}};
+      if (use_bits) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) win[q][rh] = keep_window16(a.dbits, wrow[q][rh] + kt * 16);
+      }
+      uint32_t kv4 = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) kv4 |= kval[key_of(kt, e)] ? (1u << e) : 0u;
+      float sc[2][2][4], dp[2][2][4];
+      mma_frags_bt<2>(sc, qa, Ks + kt * SELF_TILE, lane);
+      if (!HOIST_G) {
+        load_a_frags(ga[0], Gs + qts[0] * SELF_TILE, lane);
+        load_a_frags(ga[1], Gs + qts[1] * SELF_TILE, lane);
+      }
+      mma_frags_bt<2>(dp, ga, Vs + kt * SELF_TILE, lane);  // dP~ = dO V^T
+      uint32_t da[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float dsv[2][4];
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          const int i = qts[q] * 16 + g + rh * 8;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float pij = ((kv4 >> e) & 1u)
+                                  ? fast_ex2(fmaf(sc[q][e >> 1][rh * 2 + (e & 1)], SCALE_LOG2E, -m_safe[q][rh])) * inv_l[q][rh]
+                                  : 0.f;
+            float mult = 1.f;
+            if (use_bits) {
+              mult = ((win[q][rh] >> ((e >> 1) * 8 + 2 * t + (e & 1))) & 1u) ? keep_scale : 0.f;
+            } else if (drop) {
+              const int j = key_of(kt, e);
+              if (i < S && j < S) mult = keep_of(i, j) ? keep_scale : 0.f;
+            }
+            dsv[rh][e] = pij * (dp[q][e >> 1][rh * 2 + (e & 1)] * mult - delta[q][rh]);
+          }
+        }
+        da[q][0] = pack_bf16(dsv[0][0], dsv[0][1]);
+        da[q][1] = pack_bf16(dsv[1][0], dsv[1][1]);
+        da[q][2] = pack_bf16(dsv[0][2], dsv[0][3]);
+        da[q][3] = pack_bf16(dsv[1][2], dsv[1][3]);
+      }
+      mma_frags_b_acc<2>(o, da, Ks + kt * SELF_TILE, lane);  // dQ += dS K
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (q >= nq) break;
+      store_tile(stage, o[q], scale, a.dq + (static_cast<int64_t>(b) * S + qts[q] * 16) * a.lddq + h * SELF_HD, a.lddq,
+                 min(16, S - qts[q] * 16), lane);
+    }
+  }
+  if (MODE == 0) return;
+  __syncthreads();
+  // ---- backward, phase 2: warp = key tile (A fragments of K and V held in registers); rows of the score fragments are
+  // KEYS, columns are QUERIES
+  for (int kt = warp; kt < NT; kt += WARPS) {
+    const int rows_valid = min(16, S - kt * 16);
+    const bool kv0 = kval[kt * 16 + g] != 0, kv1 = kval[kt * 16 + g + 8] != 0;
+    uint32_t ka[1][4][4], va[1][4][4];
+    load_a_frags(ka[0], Ks + kt * SELF_TILE, lane);
+    load_a_frags(va[0], Vs + kt * SELF_TILE, lane);
+    float ok[1][8][4], ov[1][8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ok[0][n][j] = ov[0][n][j] = 0.f;
+    for (int qt = 0; qt < NT; ++qt) {
+      uint32_t winq[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};  // keys kt*16 .. +15 of this thread's four query rows
+      if (use_bits) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = min(qt * 16 + (e >> 1) * 8 + 2 * t + (e & 1), S - 1);
+          winq[e] = keep_window16(a.dbits, (head_base + i) * static_cast<uint64_t>(S) + kt * 16);
+        }
+      }
+      float st[1][2][4], dpt[1][2][4];
+      mma_frags_bt<1>(st, ka, Qs + qt * SELF_TILE, lane);   // S^T = K Q^T
+      mma_frags_bt<1>(dpt, va, Gs + qt * SELF_TILE, lane);  // dP~^T = V dO^T
+      float pT[2][4], dsT[2][4];  // [key row half][e]: query column i = qt*16 + (e>>1)*8 + 2t + (e&1)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = qt * 16 + (e >> 1) * 8 + 2 * t + (e & 1);
+        const float mi = row_m[i], il = row_il[i], dl = row_delta[i];
+#pragma unroll
+        for (int rh = 0; rh < 2; ++rh) {
+          const int j = kt * 16 + g + rh * 8;
+          const bool kv = rh == 0 ? kv0 : kv1;
+          const float pij = kv ? fast_ex2(fmaf(st[0][e >> 1][rh * 2 + (e & 1)], SCALE_LOG2E, -mi)) * il : 0.f;
+          float mult = 1.f;
+          if (use_bits) mult = ((winq[e] >> (g + rh * 8)) & 1u) ? keep_scale : 0.f;
+          else if (drop && i < S && j < S) mult = keep_of(i, j) ? keep_scale : 0.f;
+          pT[rh][e] = pij * mult;
+          dsT[rh][e] = pij * (dpt[0][e >> 1][rh * 2 + (e & 1)] * mult - dl);
+        }
+      }
+      uint32_t fa[1][4];
+      fa[0][0] = pack_bf16(dsT[0][0], dsT[0][1]);
+      fa[0][1] = pack_bf16(dsT[1][0], dsT[1][1]);
+      fa[0][2] = pack_bf16(dsT[0][2], dsT[0][3]);
+      fa[0][3] = pack_bf16(dsT[1][2], dsT[1][3]);
+      mma_frags_b_acc<1>(ok, fa, Qs + qt * SELF_TILE, lane);  // dK += dS^T Q
+      fa[0][0] = pack_bf16(pT[0][0], pT[0][1]);
+      fa[0][1] = pack_bf16(pT[1][0], pT[1][1]);
+      fa[0][2] = pack_bf16(pT[0][2], pT[0][3]);
+      fa[0][3] = pack_bf16(pT[1][2], pT[1][3]);
+      mma_frags_b_acc<1>(ov, fa, Gs + qt * SELF_TILE, lane);  // dV += P~^T dO
+    }
+    store_tile(stage, ok[0], scale, a.dk + (static_cast<int64_t>(b) * S + kt * 16) * a.lddkv + h * SELF_HD, a.lddkv,
+               rows_valid, lane);
+    store_tile(stage, ov[0], 1.f, a.dv + (static_cast<int64_t>(b) * S + kt * 16) * a.lddkv + h * SELF_HD, a.lddkv,
+               rows_valid, lane);
+  }
+}
+
+template <int MODE, int WARPS>
+static int launch_long2_w(const AttnArgs& a, cudaStream_t st) {
+  const int rows = (a.Lq + 15) / 16 * 16;
+  const size_t smem = static_cast<size_t>((MODE == 1 ? 4 : 3) * rows * SELF_PITCH + WARPS * SELF_TILE) * 2 +
+                      static_cast<size_t>(rows) * (3 * 4 + 1) + 16;
+  static size_t configured = 0;
+  if (smem > configured) {
+    GG_CUDA_CHECK(cudaFuncSetAttribute(attn_self_long2_kernel<MODE, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    configured = smem;
+  }
+  launch_k(attn_self_long2_kernel<MODE, WARPS>, static_cast<unsigned>(a.nb) * a.H, WARPS * 32, smem, st, a);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 template <int MODE, int WARPS>
 static int launch_long_w(const AttnArgs& a, cudaStream_t st) {
   const int rows = (a.Lq + 15) / 16 * 16;
@@ -1377,6 +1789,25 @@ static int launch_long_w(const AttnArgs& a, cudaStream_t st) {
 template <int MODE>
 static int launch_long(const AttnArgs& a, cudaStream_t st) {
   GG_REQUIRE(MODE == 0 || a.o != nullptr, "long self-attention backward needs the forward output (a.o)");
+  // Which form runs where is measured (tests/gpu_attn_bench.py sweep, 768 sequences, dropout on, us old -> new):
+  //   forward   129: 226 -> 179   161: 273 -> 224   193: 359 -> 382   257: 542 -> 628   289: 630 -> 677   320: 773 -> 730
+  //   backward  129: 481 -> 567   161: 592 -> 704   225: 940 -> 932   257: 1501 -> 1281  289: 1831 -> 1552  320: 1895 -> 1653
+  // (two tiles per warp halve the warps of the CTA: the forward of 13 .. 19 tiles misses them more than it gains from the
+  // fragment reuse; the backward, bound by the shared-memory pipe, gains from 15 tiles on).
+  // GEMMGAN_ATTN_LONG2=0 / 1 forces the first / second form everywhere.
+  static const int force = [] { const char* v = getenv("GEMMGAN_ATTN_LONG2"); return v ? (v[0] == '0' ? 0 : 1) : -1; }();
+  const int nt = (a.Lq + 15) / 16;
+  const bool long2 = force >= 0 ? force == 1 : (MODE == 0 ? (nt <= 11 || nt == 20) : nt >= 15);
+  if (long2) {
+    switch (((a.Lq + 15) / 16 + 1) / 2) {  // one warp per pair of query tiles
+      case 5: return launch_long2_w<MODE, 5>(a, st);
+      case 6: return launch_long2_w<MODE, 6>(a, st);
+      case 7: return launch_long2_w<MODE, 7>(a, st);
+      case 8: return launch_long2_w<MODE, 8>(a, st);
+      case 9: return launch_long2_w<MODE, 9>(a, st);
+      default: return launch_long2_w<MODE, 10>(a, st);
+    }
+  }
   switch ((a.Lq + 15) / 16) {  // one warp per tile where a 17th .. 19th tile would otherwise cost a second round
     case 17: return launch_long_w<MODE, 17>(a, st);
     case 18: return launch_long_w<MODE, 18>(a, st);

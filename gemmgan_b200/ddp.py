@@ -24,6 +24,35 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """One process per GPU: run this process (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA
+    node the GPU hangs off. With 8 ranks each copying ~110 MB of fp32 batch per step, host buffers that all sit on one
+    node make every other rank's H2D copies cross the socket interconnect. Reads sysfs only (no libnuma); returns the
+    node, or None when the platform does not expose one (then nothing changes). Call before allocating pinned memory."""
+    import os
+
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def dist_or_none():
     import torch.distributed as dist
 

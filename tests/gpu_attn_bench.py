@@ -36,6 +36,10 @@ def run(nb, S, p, iters=5, bits=False):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":      # long-kernel sizes, dropout on with precomputed bits
+        for S in (129, 145, 161, 193, 225, 257, 289, 320):
+            run(768, S, 0.1, bits=True)
+        sys.exit(0)
     for nb, S in ((768, 257), (12288, 65), (768, 129)):
         for p, bits in ((0.0, False), (0.1, False), (0.1, True)):
             run(nb, S, p, bits=bits)
