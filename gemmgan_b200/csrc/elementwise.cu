@@ -245,6 +245,21 @@ int k_sum_replicas(const bf16* in, bf16* out, int R, int64_t n, cudaStream_t st)
   return GG_OK;
 }
 
+// out[r * n + i] = in[r * n + i] + add[i]  (bf16 rows + an fp32 row block shared by the R replicas)
+__global__ void add_bcast_replicas_kernel(const bf16* __restrict__ in, const float* __restrict__ add, bf16* __restrict__ out,
+                                          int R, int64_t n) {
+  pdl_entry();
+  const int64_t total = static_cast<int64_t>(R) * n;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(__bfloat162float(in[i]) + add[i % n]);
+}
+int k_add_bcast_replicas(const bf16* in, const float* add, bf16* out, int R, int64_t n, cudaStream_t st) {
+  launch_k(add_bcast_replicas_kernel, grid_for(static_cast<int64_t>(R) * n, 256), 256, 0, st, in, add, out, R, n);
+  GG_LAUNCH_CHECK();
+  return GG_OK;
+}
+
 // Label-conditioned baseline (benchmark_generative_model.py:138-150): the conditioning vector of sample b is the
 // concatenation of one row of each embedding table. Tables are the fp32 master parameters (a few KB: L2 resident).
 __global__ void embed_gather_kernel(const float* __restrict__ emb0, const float* __restrict__ emb1,

@@ -94,6 +94,7 @@ struct Tower {
   bf16 *mod, *te, *X[3];
   TowerLayer L[2];
   bf16 *qp, *kvp, *ap, *pv, *qt, *kvt, *at, *c, *tmpE;
+  float* ot = nullptr;  // T == 1: out-projection of the single text token's value vector [B, E] (shared by the replicas)
   bf16 *pe_h = nullptr, *pe_ln = nullptr, *zero = nullptr;  // IMG: relu(patch projection), its LayerNorm, zeros
   float *pe_mean = nullptr, *pe_rstd = nullptr;
 };
@@ -103,6 +104,7 @@ struct LayerGrads {  // per layer: side-lane weight-gradient GEMMs read these wh
 };
 struct GradScratch {
   bf16 *dc, *dat, *dqt, *dkvt, *dkvt_sum, *dp, *dap, *dqp, *dqp_sum, *dkvp;
+  bf16* dcs = nullptr;  // T == 1: dc summed over the replicas [B, E]
   bf16 *ga, *gb, *gao, *dte, *dte0, *dpe, *dmod, *dgb;
   bf16 *dpe_z = nullptr, *dpe_h = nullptr;  // IMG: gradient before the patch LayerNorm / before the ReLU
   float* lnp_pe = nullptr;
@@ -334,6 +336,12 @@ struct gg_engine {
   // wait for the accumulators, so nothing leaves its critical path, and the extra mask launches take SM time from the
   // tower head. Off by default; results are bitwise the same either way (tests/test_gpu_enc_layer.py).
   bool layer_bits = false;
+  // One text token (T == 1: BASELINE configs 1-3): the text2patch attention is a softmax over ONE key, i.e. exactly 1 for
+  // every query, so its output is that token's value vector whatever the query is, and no gradient reaches the query or the
+  // key (d softmax = 0). The engine then skips the query projection, both attention launches and their backward, and forms
+  // c = pv + (v_text Wo^T + bo) with the text-only term computed once on the text lane. GEMMGAN_T1_SHORTCUT=0 runs the
+  // general path (same numbers to bf16 rounding; tests compare both).
+  bool t1_shortcut = true;
   bool gp_tf32 = false;   // GEMMGAN_GP_TF32=1 (gg_engine_gp_step)
   bool attn_bits = true;  // GEMMGAN_ATTN_BITS=0: the 17 .. 320-token attention kernels draw their dropout masks themselves
   bool fused_layer = true;  // GEMMGAN_FUSED_LAYER=0: encoder layers as seven launches instead of enc_layer.cu's one
@@ -462,6 +470,7 @@ static void layout_tower(gg_engine& e, Tower& t, int Rmax, Arena& ar) {
   t.kvt = ar.take<bf16>(B * T * 2 * E);
   t.at = ar.take<bf16>(rb * E);
   t.c = ar.take<bf16>(rb * E);
+  t.ot = ar.take<float>(B * E);
   t.tmpE = ar.take<bf16>(rows * E);
   if (e.img) {
     t.pe_h = ar.take<bf16>(B * P * E);
@@ -518,6 +527,7 @@ static int64_t layout(gg_engine& e, uint8_t* base) {
     g.dap = ar.take<bf16>(n * E);
     g.dqp = ar.take<bf16>(n * E);
     g.dqp_sum = ar.take<bf16>(B * E);
+    g.dcs = ar.take<bf16>(B * E);
     g.dkvp = ar.take<bf16>(rows * 2 * E);
     g.ga = ar.take<bf16>(rows * E);
     g.gb = ar.take<bf16>(rows * E);
@@ -736,6 +746,9 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
     GG_TRY(e.linear(tl, B, E, E, Op{t.te, static_cast<int64_t>(T) * E}, Wp, Epi().bias(bp).obf(t.qp, E)));
     GG_TRY(e.linear(tl, B * T, 2 * E, E, Op{t.te, E}, Op{Wt.p + static_cast<int64_t>(E) * Wt.ld, Wt.ld},
                     Epi().bias(bt ? bt + E : nullptr).obf(t.kvt, 2 * E)));
+    if (T == 1 && e.t1_shortcut)  // the whole text2patch branch of this step: (v_text Wo^T + bo), once for all replicas
+      GG_TRY(e.linear(tl, B, E, E, Op{t.kvt + E, 2 * E}, e.W(net, GG_P_T2P_OUT_W),
+                      Epi().bias(e.P(net, GG_P_T2P_OUT_B)).of32(t.ot, E)));
   }
   if (e.img) {
     // conditional_gan_img_transformer.py:111-115: patches_encoder = Linear -> ReLU -> LayerNorm (no dropout: once
@@ -824,6 +837,8 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
   GG_TRY(k_attention_fwd(a, st));
   GG_TRY(e.linear(ln, R * B, E, E, Op{t.ap, E}, e.W(net, GG_P_P2T_OUT_W),
                   Epi().bias(e.P(net, GG_P_P2T_OUT_B)).obf(t.pv, E)));
+  if (T == 1 && e.t1_shortcut)  // softmax over the one text token = 1: c = pv + (v_text Wo^T + bo) (:151-155)
+    return k_add_bcast_replicas(t.pv, t.ot, t.c, R, static_cast<int64_t>(B) * E, st);
   // text2patch: query = that vector, keys/values = encoded text tokens (:151-152)
   GG_TRY(e.linear(ln, R * B, E, E, Op{t.pv, E}, Wt, Epi().bias(bt).obf(t.qt, E)));
   memset(&a, 0, sizeof(a));
@@ -923,11 +938,37 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     float* gWt = e.Gr(net, GG_P_T2P_IN_W);
     float* gbp = e.Gr(net, GG_P_P2T_IN_B);
     float* gbt = e.Gr(net, GG_P_T2P_IN_B);
+    const bool t1 = T == 1 && e.t1_shortcut;
+    const bf16* dp_chain = g.dp;  // gradient w.r.t. pv that the patch2text backward continues from
+    AttnArgs a;
+    if (t1) {
+      // c = pv + (v_text Wo_t^T + bo_t): dp = dc; everything else of the text2patch branch sees dc summed over the
+      // replicas and only feeds the text encoder (lane `bl`, off the dependent chain). No gradient reaches the query
+      // projection or the key projection: their slices of the in-proj gradient are exactly zero, as in the reference.
+      dp_chain = dc;
+      const int bl1 = e.text_lane_bwd ? 2 : 0;
+      GG_TRY(e.wait_lane(bl1, 0));
+      cudaStream_t sb = e.S(bl1);
+      const bf16* dcs = dc;
+      if (Rg > 1) {
+        GG_TRY(k_sum_replicas(dc, g.dcs, Rg, static_cast<int64_t>(B) * E, sb));
+        dcs = g.dcs;
+      }
+      GG_TRY(e.wgrad(E, E, B, Op{dcs, E}, Op{t.kvt + E, 2 * E}, e.Gr(net, GG_P_T2P_OUT_W), E));
+      GG_TRY(e.bgrad(dcs, E, B, E, e.Gr(net, GG_P_T2P_OUT_B)));
+      GG_CUDA_CHECK(cudaMemsetAsync(g.dkvt_sum, 0, sizeof(bf16) * static_cast<size_t>(B) * 2 * E, sb));
+      GG_TRY(e.dgrad(bl1, B, E, E, Op{dcs, E}, e.W(net, GG_P_T2P_OUT_W), Epi().obf(g.dkvt_sum + E, 2 * E)));  // dV
+      GG_CUDA_CHECK(cudaMemsetAsync(gWt, 0, sizeof(float) * static_cast<size_t>(E) * E, sb));   // query projection: 0
+      if (gbt) GG_CUDA_CHECK(cudaMemsetAsync(gbt, 0, sizeof(float) * static_cast<size_t>(E), sb));
+      GG_TRY(e.wgrad(2 * E, E, B, Op{g.dkvt_sum, 2 * E}, Op{t.te, E}, gWt + static_cast<int64_t>(E) * E, E));
+      GG_TRY(e.bgrad(g.dkvt_sum, 2 * E, B, 2 * E, gbt ? gbt + E : nullptr));
+      GG_TRY(e.dgrad(bl1, B, E, 2 * E, Op{g.dkvt_sum, 2 * E}, Wt_kv, Epi().obf(g.dte, E)));
+    }
+    if (!t1) {
     // c = at Wo_t^T + bo_t + pv
     GG_TRY(e.wgrad(E, E, n, Op{dc, E}, Op{t.at, E}, e.Gr(net, GG_P_T2P_OUT_W), E));
     GG_TRY(e.bgrad(dc, E, n, E, e.Gr(net, GG_P_T2P_OUT_B)));
     GG_TRY(e.dgrad(0, n, E, E, Op{dc, E}, e.W(net, GG_P_T2P_OUT_W), Epi().obf(g.dat, E)));
-    AttnArgs a;
     memset(&a, 0, sizeof(a));
     a.q = t.qt; a.ldq = E; a.q_mod = n;
     a.k = t.kvt; a.v = t.kvt + E; a.ldkv = 2 * E; a.kv_mod = B;
@@ -953,10 +994,12 @@ static int tower_backward(gg_engine& e, int net, int Rg, float p, const bf16* dc
     GG_TRY(e.wgrad(2 * E, E, B * T, Op{dkvt, 2 * E}, Op{t.te, E}, gWt + static_cast<int64_t>(E) * E, E));
     GG_TRY(e.bgrad(dkvt, 2 * E, B * T, 2 * E, gbt ? gbt + E : nullptr));
     GG_TRY(e.dgrad(bl, B * T, E, 2 * E, Op{dkvt, 2 * E}, Wt_kv, Epi().obf(g.dte, E)));
+    }  // !t1
+    const int bl = e.text_lane_bwd ? 2 : 0;
     // pv = ap Wo_p^T + bo_p
-    GG_TRY(e.wgrad(E, E, n, Op{g.dp, E}, Op{t.ap, E}, e.Gr(net, GG_P_P2T_OUT_W), E));
-    GG_TRY(e.bgrad(g.dp, E, n, E, e.Gr(net, GG_P_P2T_OUT_B)));
-    GG_TRY(e.dgrad(0, n, E, E, Op{g.dp, E}, e.W(net, GG_P_P2T_OUT_W), Epi().obf(g.dap, E)));
+    GG_TRY(e.wgrad(E, E, n, Op{dp_chain, E}, Op{t.ap, E}, e.Gr(net, GG_P_P2T_OUT_W), E));
+    GG_TRY(e.bgrad(dp_chain, E, n, E, e.Gr(net, GG_P_P2T_OUT_B)));
+    GG_TRY(e.dgrad(0, n, E, E, Op{dp_chain, E}, e.W(net, GG_P_P2T_OUT_W), Epi().obf(g.dap, E)));
     memset(&a, 0, sizeof(a));
     a.q = t.qp; a.ldq = E; a.q_mod = B;
     a.k = t.kvp; a.v = t.kvp + E; a.ldkv = 2 * E; a.kv_mod = n;
@@ -1237,6 +1280,8 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
     const char* fl = getenv("GEMMGAN_FUSED_LAYER");
     e->fused_layer = !(fl && fl[0] == '0');
     e->layer_bits = layer_bits_requested();
+    const char* t1 = getenv("GEMMGAN_T1_SHORTCUT");
+    e->t1_shortcut = !(t1 && t1[0] == '0');
     const char* ab = getenv("GEMMGAN_ATTN_BITS");
     e->attn_bits = !(ab && ab[0] == '0');
   }

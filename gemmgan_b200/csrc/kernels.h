@@ -33,6 +33,8 @@ int k_relu_bwd(const bf16* g, const bf16* h, bf16* out, int64_t n, cudaStream_t 
 int k_unassemble_tokens(const bf16* dx, bf16* dpe, float* dcls, int R, int B, int S, int E, cudaStream_t st);
 // out[i] = sum_r in[r * n + i]
 int k_sum_replicas(const bf16* in, bf16* out, int R, int64_t n, cudaStream_t st);
+// out[r * n + i] = in[r * n + i] + add[i] for r < R (add: fp32, shared by the replicas)
+int k_add_bcast_replicas(const bf16* in, const float* add, bf16* out, int R, int64_t n, cudaStream_t st);
 // dst[b * stride_rows, :] += src[b, :]   (bf16, E columns)
 int k_scatter_add_rows(bf16* dst, const bf16* src, int B, int stride_rows, int E, cudaStream_t st);
 // dst[b, 0, :] = src[b, :], other token rows zero: dst [B, S, E]

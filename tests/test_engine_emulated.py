@@ -161,6 +161,16 @@ def test_steps_at_the_reference_feature_widths(rt, variant, P):
     run_steps(rt, variant, "adam", 0.0, dict(FULL, P=P))
 
 
+@pytest.mark.parametrize("variant", ["paper", "cross"])
+@pytest.mark.parametrize("shortcut", ["1", "0"])
+def test_single_text_token_step(rt, monkeypatch, variant, shortcut):
+    """T = 1 (BASELINE configs 1-3): the text2patch attention is a softmax over one key. With GEMMGAN_T1_SHORTCUT (default)
+    the engine forms c = pv + (v_text Wo^T + bo) directly and sends no gradient to the query / key projections (exact
+    zeros, as autograd produces); the general path ("0") runs the attention kernels. Both against the oracle."""
+    monkeypatch.setenv("GEMMGAN_T1_SHORTCUT", shortcut)
+    run_steps(rt, variant, "adam", 0.0, dict(SMALL, T=1))
+
+
 def test_cfg4_like_token_counts(rt):
     """64 patches + CLS = 65 tokens (mma.sync mid kernel) and 32 text tokens (single-query attention over 65 / 32 keys):
     BASELINE config 4's sequence lengths at a batch the emulation finishes quickly."""
