@@ -1924,7 +1924,10 @@ __global__ void __launch_bounds__(128) attn_q1_kernel(const AttnArgs a) {
 
 static bool aligned16(const void* p);
 static bool q1_path(const AttnArgs& a) {
-  if (!(a.Lq == 1 && a.Lk > SM_MAXL && a.Lk <= 32 * Q1_MAXK && a.hd == 64 && a.drop_p == 0.f)) return false;
+  // Also for <= 16 keys (the patch2text attention over 9 tokens at cfg3): one launch forward and ONE backward instead of the
+  // generic short-sequence pair (25 + 30 us on the dependent chain); 6.77 -> 6.64 ms per train(). GEMMGAN_Q1_SMALL=0: off.
+  static const bool q1_small = [] { const char* v = getenv("GEMMGAN_Q1_SMALL"); return !(v && v[0] == '0'); }();
+  if (!(a.Lq == 1 && (a.Lk > SM_MAXL || q1_small) && a.Lk <= 32 * Q1_MAXK && a.hd == 64 && a.drop_p == 0.f)) return false;
   return a.ldq % 8 == 0 && a.ldkv % 8 == 0 && aligned16(a.q) && aligned16(a.k) && aligned16(a.v) &&
          (!a.dout || (a.lddo % 8 == 0 && aligned16(a.dout)));
 }
