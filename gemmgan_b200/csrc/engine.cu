@@ -1162,8 +1162,14 @@ static int gen_forward(gg_engine& e, const float* z, float p, float* out_f32, in
 // critic trunk forward on npass row groups; nx = number of gene matrices in xfr (1: fake, 2: fake+real)
 // fake_f32 / real_f32 (both non-null): the first layer reads those fp32 [B, G] tensors directly (TF32) instead of the bf16
 // [fake; real] matrix x
+// defer_score: the caller runs critic_scores() itself (on a side lane: in the training steps the scores only feed the loss
+// statistics, the backward starts from h2's signs)
+static int critic_scores(gg_engine& e, int npass, cudaStream_t st) {
+  const gg_model_cfg& c = e.cfg;
+  return k_rowdot_bias(e.tb.h2f, e.P(GG_NET_DISC, GG_P_FIN_W), e.P(GG_NET_DISC, GG_P_FIN_B), e.tb.score, npass * c.B, c.H, st);
+}
 static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, int R, const float* alpha,
-                                const float* fake_f32 = nullptr, const float* real_f32 = nullptr) {
+                                const float* fake_f32 = nullptr, const float* real_f32 = nullptr, bool defer_score = false) {
   const gg_model_cfg& c = e.cfg;
   TrunkBufs& t = e.tb;
   cudaStream_t st = e.S(0);
@@ -1190,7 +1196,7 @@ static int critic_trunk_forward(gg_engine& e, const bf16* x, int nx, int npass, 
   GG_TRY(k_trunk1_combine(t.a1x, a1c, e.P(net, GG_P_TR0_B), alpha, t.h1, B, H, npass, R, c.slope, st));
   GG_TRY(e.linear(0, npass * B, H, H, Op{t.h1, H}, e.W(net, GG_P_TR1_W),
                   Epi().bias(e.P(net, GG_P_TR1_B)).act(GG_ACT_LEAKY, c.slope).obf(t.h2, H).of32(t.h2f, H)));
-  GG_TRY(k_rowdot_bias(t.h2f, e.P(net, GG_P_FIN_W), e.P(net, GG_P_FIN_B), t.score, npass * B, H, st));
+  if (!defer_score) GG_TRY(critic_scores(e, npass, st));
   return GG_OK;
 }
 
@@ -1209,11 +1215,12 @@ static int disc_forward_gp(gg_engine& e, int R, float p, const float* alpha, int
   GG_TRY(e.mm(2, H, H, G, W1x, 0, W1x, 0, Epi().of32(t.Mg, H).obf(t.Mgb, H)));
   if (e.cond) GG_TRY(tower_forward(e, net, R, p, 0, save_reps));
   GG_TRY(e.join(fake_lane));
-  GG_TRY(critic_trunk_forward(e, e.xfr, 2, 3, R, alpha, fake_f32, real_f32));
+  GG_TRY(critic_trunk_forward(e, e.xfr, 2, 3, R, alpha, fake_f32, real_f32, /*defer_score=*/gp_lane != 0));
   // The penalty's own chain (u2 -> u1 -> y = u1 M -> row norms -> losses) feeds only the loss statistics and the
   // GP weight gradients: in the training step it runs on `gp_lane` next to the backward chain of lane 0.
   if (gp_lane != 0) GG_TRY(e.fork(gp_lane));
   cudaStream_t st = e.S(gp_lane);
+  if (gp_lane != 0) GG_TRY(critic_scores(e, 3, st));  // D(fake), D(real), D(x_hat): loss statistics only
   const float* w3 = e.P(net, GG_P_FIN_W);
   const bf16* h1i = t.h1 + static_cast<int64_t>(2) * B * H;
   const bf16* h2i = t.h2 + static_cast<int64_t>(2) * B * H;
@@ -1527,8 +1534,10 @@ static int gen_grads_impl(gg_engine* e, const float* z, int training, int phase,
   e->bn_training = training;
   GG_TRY(gen_forward(*e, z, p, nullptr, 0, true));
   GG_TRY(e->join(1));
-  GG_TRY(critic_trunk_forward(*e, e->xfr, 1, 1, 1, nullptr));
-  GG_TRY(k_gen_loss(t.score, e->stats, B, inv_b, st));
+  GG_TRY(critic_trunk_forward(*e, e->xfr, 1, 1, 1, nullptr, nullptr, nullptr, /*defer_score=*/true));
+  GG_TRY(e->fork(1));  // -mean D(G(z)) is a statistic: the backward starts from h2's signs
+  GG_TRY(critic_scores(*e, 1, e->S(1)));
+  GG_TRY(k_gen_loss(t.score, e->stats, B, inv_b, e->S(1)));
   // ---- critic trunk input gradient (critic weights frozen, its tower is not on G's path)
   const Op W1x = e->W(D, GG_P_TR0_W), W2 = e->W(D, GG_P_TR1_W);
   GG_TRY(k_score_bwd(t.h2, e->P(D, GG_P_FIN_W), t.da2, nullptr, B, B, H, c.slope, -1.f, -1.f, inv_b, st));
