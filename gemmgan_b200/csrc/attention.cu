@@ -800,6 +800,26 @@ __global__ void __launch_bounds__(SELF_THREADS) attn_self_small_kernel(const Att
 // tile) recomputes P, dP = dO V^T, dS = P o (dP - delta), dQ = dS K and leaves bf16 dS / P in shared memory;
 // phase 2 (warp = key tile) forms dK = dS^T Q and dV = P^T dO from them through ldmatrix.trans. No atomics.
 // (The CUDA-core kernels above took 2.6 ms forward / 10 ms backward per call at 12288 sequences x 65 tokens.)
+// A fragments (16 x 64) of a tile held in registers across a walk over B tiles, and C = A * B^T from them
+__device__ __forceinline__ void load_a_frags16(uint32_t (&fa)[4][4], const bf16* A, int lane) {
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) ldsm_x4(fa[kk], A + arow * SELF_PITCH + kk * 16 + acol);
+}
+__device__ __forceinline__ void mma_afrag_bt(float (&c)[2][4], const uint32_t (&fa)[4][4], const bf16* B, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[nt][j] = 0.f;
+  const int brow = (lane & 7) + (lane >> 4) * 8, bcol = ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t b[4];
+    ldsm_x4(b, B + brow * SELF_PITCH + kk * 16 + bcol);
+    mma16816(c[0], fa[kk], b[0], b[1]);
+    mma16816(c[1], fa[kk], b[2], b[3]);
+  }
+}
 __device__ __forceinline__ void mma_frag_b_acc(float (&o)[8][4], const uint32_t (&a)[4], const bf16* B, int lane) {
   const int brow = (lane & 7) + ((lane >> 3) & 1) * 8, bcol = (lane >> 4) * 8;
 #pragma unroll
@@ -874,8 +894,10 @@ __global__ void __launch_bounds__(NT * 32) attn_self_mid_kernel(const AttnArgs a
     float p[NT][2][4];  // [key tile][row half][e]
     {
       float sc[NT][2][4];
+      uint32_t qa[4][4];  // the query tile's A fragments: loaded once, not once per key tile
+      load_a_frags16(qa, Qt, lane);
 #pragma unroll
-      for (int kt = 0; kt < NT; ++kt) mma_ab_t(sc[kt], Qt, Ks + kt * SELF_TILE, lane);
+      for (int kt = 0; kt < NT; ++kt) mma_afrag_bt(sc[kt], qa, Ks + kt * SELF_TILE, lane);
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
         float m = -INFINITY;
@@ -961,10 +983,12 @@ __global__ void __launch_bounds__(NT * 32) attn_self_mid_kernel(const AttnArgs a
     const bf16* Gt = Gs + qt * SELF_TILE;
     float delta[2] = {0.f, 0.f};
     float dsv[NT][2][4];
+    uint32_t ga[4][4];
+    load_a_frags16(ga, Gt, lane);
 #pragma unroll
     for (int kt = 0; kt < NT; ++kt) {
       float dp[2][4];
-      mma_ab_t(dp, Gt, Vs + kt * SELF_TILE, lane);  // dP~ = dO V^T
+      mma_afrag_bt(dp, ga, Vs + kt * SELF_TILE, lane);  // dP~ = dO V^T
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
@@ -1132,6 +1156,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
   for (int qt = warp; qt < NT; qt += WARPS) {
     const bf16* Qt = Qs + qt * SELF_TILE;
     const int rows_valid = min(16, S - qt * 16);
+    uint32_t qa[4][4];  // the query tile's A fragments stay in registers for both key walks
+    load_a_frags16(qa, Qt, lane);
     // ---- online softmax statistics (and, forward, the output) over the key tiles
     float m_run[2] = {-INFINITY, -INFINITY}, l_thr[2] = {0.f, 0.f};
     float o[8][4];
@@ -1150,7 +1176,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
         win[1] = keep_window16(a.dbits, wrow[1] + kt * 16);
       }
       float sc[2][4];
-      mma_ab_t(sc, Qt, Ks + kt * SELF_TILE, lane);
+      mma_afrag_bt(sc, qa, Ks + kt * SELF_TILE, lane);
       float pv[2][4];
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
@@ -1268,7 +1294,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_self_long_kernel(const AttnAr
         win[1] = keep_window16(a.dbits, wrow[1] + kt * 16);
       }
       float sc[2][4], dp[2][4];
-      mma_ab_t(sc, Qt, Ks + kt * SELF_TILE, lane);
+      mma_afrag_bt(sc, qa, Ks + kt * SELF_TILE, lane);
       mma_ab_t(dp, Gt, Vs + kt * SELF_TILE, lane);  // dP~ = dO V^T
       float dsv[2][4];
       DropoutStream ds(seed, step, a.site, a.drop_p);
