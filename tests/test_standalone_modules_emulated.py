@@ -95,7 +95,7 @@ def compare_grads(ref_net, net, total=0.08):
     assert (num / max(den, 1e-30)) ** 0.5 <= total
 
 
-@pytest.mark.parametrize("variant", ["paper", "film", "attn", "vanilla"])
+@pytest.mark.parametrize("variant", ["paper", "film", "attn", "vanilla", "cross", "img"])
 def test_critic_module_is_differentiable(host, variant):
     """d(sum w_b D(x_b)) / d{parameters, x} through `discriminator(x, ...)` alone — two forwards (as D(fake), D(real)
     in a hand-written critic loss) and ONE backward."""
