@@ -342,6 +342,7 @@ struct gg_engine {
   // c = pv + (v_text Wo^T + bo) with the text-only term computed once on the text lane. GEMMGAN_T1_SHORTCUT=0 runs the
   // general path (same numbers to bf16 rounding; tests compare both).
   bool t1_shortcut = true;
+  bool film_fused = true;  // GEMMGAN_FILM_FUSED=0: film_apply_kernel + patch GEMM + token assembly as three launches
   bool gp_tf32 = false;   // GEMMGAN_GP_TF32=1 (gg_engine_gp_step)
   bool attn_bits = true;  // GEMMGAN_ATTN_BITS=0: the 17 .. 320-token attention kernels draw their dropout masks themselves
   bool fused_layer = true;  // GEMMGAN_FUSED_LAYER=0: encoder layers as seven launches instead of enc_layer.cu's one
@@ -711,11 +712,16 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
   // FiLM parameters from the text CLS / text vector (:129-134); conditional_gan_cross_attention.py has no FiLM
   // (:128-130): its patch encoder reads the patch embeddings as they are
   const bf16* pin = e.patches;
+  // FiLM in the A-operand path of the patch encoder (film_patch.cu): modulation, projection, bias, CLS rows and the copies
+  // for the dropout replicas in one launch; the modulated patches are stored only when this pass will be back-propagated
+  const bool film_fused = e.film && e.film_fused && c.gemm_impl == GG_IMPL_TCGEN05 && E == 256 && Dp % 64 == 0;
   if (e.film) {
     GG_TRY(e.linear(ln, B, 2 * Dp, Dt, Op{e.text, static_cast<int64_t>(T) * Dt}, e.W(net, GG_P_FILM_W),
                     Epi().bias(e.P(net, GG_P_FILM_B)).act(GG_ACT_FILM).of32(t.gb, 2 * Dp)));
-    GG_TRY(k_film_apply(e.patches, t.gb, t.mod, B, P, Dp, st));
-    pin = t.mod;
+    if (!film_fused) {
+      GG_TRY(k_film_apply(e.patches, t.gb, t.mod, B, P, Dp, st));
+      pin = t.mod;
+    }
   }
   // text side of the paper model (:140, :149-152): token projection, the patch2text query and the text2patch
   // keys / values depend on the text only — they run on lane 2 next to the patch encoder of lane `ln`
@@ -758,6 +764,10 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
     GG_TRY(k_add_ln_fwd(t.zero, t.pe_h, e.P(net, GG_P_PENC_LN_W), e.P(net, GG_P_PENC_LN_B), t.tmpE, t.pe_ln, t.pe_mean,
                         t.pe_rstd, static_cast<int64_t>(B) * P, E, c.ln_eps, 0.f, e.rng, 0, st));
     GG_TRY(k_assemble_tokens(t.X[0], e.P(net, GG_P_CLS), R, B, S, E, st, t.pe_ln));
+  } else if (film_fused) {
+    const Op Wpe = e.W(net, GG_P_PATCH_W);
+    GG_TRY(k_film_patch(e.patches, t.gb, Wpe.p, Wpe.ld, e.P(net, GG_P_PATCH_B), e.P(net, GG_P_CLS), t.X[0],
+                        save_reps > 0 ? t.mod : nullptr, B, P, R, Dp, st));
   } else {
     // patch projection written straight behind the CLS row of replica 0 (:139-142)
     GG_TRY(e.linear(ln, B * P, E, Dp, Op{pin, Dp}, e.W(net, GG_P_PATCH_W),
@@ -1287,6 +1297,8 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
     const char* fl = getenv("GEMMGAN_FUSED_LAYER");
     e->fused_layer = !(fl && fl[0] == '0');
     e->layer_bits = layer_bits_requested();
+    const char* ff = getenv("GEMMGAN_FILM_FUSED");
+    e->film_fused = !(ff && ff[0] == '0');
     const char* t1 = getenv("GEMMGAN_T1_SHORTCUT");
     e->t1_shortcut = !(t1 && t1[0] == '0');
     const char* ab = getenv("GEMMGAN_ATTN_BITS");
@@ -1758,6 +1770,14 @@ extern "C" int gg_xw_f32(const float* x0, const float* x1, int32_t B, int32_t K,
                          void* workspace, int64_t workspace_bytes, void* stream) {
   return k_xw_f32(x0, x1, B, K, reinterpret_cast<const bf16*>(w_bf16), ldw, out, workspace, workspace_bytes,
                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gg_film_patch_encode(const void* patches_bf16, const float* gamma_beta, const void* w_bf16, int64_t ldw,
+                                    const float* bias, const float* cls, void* x0_bf16, void* mod_bf16, int32_t B, int32_t P,
+                                    int32_t R, int32_t Dp, void* stream) {
+  return k_film_patch(reinterpret_cast<const bf16*>(patches_bf16), gamma_beta, reinterpret_cast<const bf16*>(w_bf16), ldw, bias,
+                      cls, reinterpret_cast<bf16*>(x0_bf16), reinterpret_cast<bf16*>(mod_bf16), B, P, R, Dp,
+                      reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream) {

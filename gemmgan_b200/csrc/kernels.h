@@ -74,6 +74,10 @@ int k_bn_bwd(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, const flo
 int k_xw_f32(const float* x0, const float* x1, int B, int K, const bf16* w, int64_t ldw, float* out, void* workspace,
              int64_t workspace_bytes, cudaStream_t st);
 
+// ---- film_patch.cu: FiLM modulation in the A-operand path of the patch-encoder GEMM + bias + CLS rows + replica copies
+int k_film_patch(const bf16* patches, const float* gb, const bf16* w, int64_t ldw, const float* bias, const float* cls, bf16* x0,
+                 bf16* mod, int B, int P, int R, int Dp, cudaStream_t st);
+
 // live profiler channel of the grouped weight-gradient kernel (gemm.cu; no-ops unless gg_gemm_profile_begin is active)
 int prof_wgrad_begin(double flops, double bytes, cudaStream_t stream);
 int prof_wgrad_end(cudaStream_t stream);

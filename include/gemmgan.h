@@ -317,6 +317,15 @@ int gg_engine_critic_backward(gg_engine* e, const float* dscore_f32, float* dgen
  * NULL): split-K partial sums, up to 8 * 2B * 256 floats are used. */
 int gg_xw_f32(const float* x0, const float* x1, int32_t B, int32_t K, const void* w_bf16, int64_t ldw, float* out,
               void* workspace, int64_t workspace_bytes, void* stream);
+/* FiLM + patch encoder + CLS token of the paper / film models in one kernel (src/conditional_gan_cross_attention_with_film.py
+ * :129-142: `patches = gamma * patches + beta`, `patches_encoder(patches)`, `torch.cat((cls, patches), 1)`): x0 [R, B, P + 1,
+ * 256] bf16 with row (r, b, 0) = cls and row (r, b, 1 + j) = (gamma_b * patches[b, j] + beta_b) w^T + bias for each of the R
+ * dropout replicas. patches bf16 [B * P, Dp] (Dp % 64 == 0), gamma_beta fp32 [B, 2 * Dp] (gamma | beta, already tanh'ed /
+ * clamped), w bf16 [256, Dp] with pitch ldw, bias (may be NULL) / cls fp32 [256]. mod (may be NULL) receives the
+ * modulated patches [B * P, Dp] bf16 that the weight gradient of the encoder reads in the backward. */
+int gg_film_patch_encode(const void* patches_bf16, const float* gamma_beta, const void* w_bf16, int64_t ldw, const float* bias,
+                         const float* cls, void* x0_bf16, void* mod_bf16, int32_t B, int32_t P, int32_t R, int32_t Dp,
+                         void* stream);
 /* out[b, :] (fp32) = mean over the rows p with pad[b, p] == 0 of x[b, p, :] — the masked mean of
  * conditional_gan_concat.py:137-138 ('image' conditioning), taken BEFORE the affine encoder. pad may be NULL. */
 int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream);

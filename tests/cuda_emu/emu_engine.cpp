@@ -36,6 +36,11 @@ int k_xw_f32(const float*, const float*, int, int, const bf16*, int64_t, float*,
   set_error("the fp32-input critic layer-1 kernel is tcgen05 only (not available in the host emulation)");
   return GG_ERR_ARCH;
 }
+int k_film_patch(const bf16*, const float*, const bf16*, int64_t, const float*, const float*, bf16*, bf16*, int, int, int, int,
+                 cudaStream_t) {
+  set_error("the fused FiLM patch-encoder kernel is tcgen05 only (not available in the host emulation)");
+  return GG_ERR_ARCH;
+}
 int k_enc_ffn_bwd(const EncFfnBwdParams&, cudaStream_t) {
   set_error("the fused ffn-backward kernel is tcgen05 only (not available in the host emulation)");
   return GG_ERR_ARCH;
