@@ -121,6 +121,7 @@ def declare(L: C.CDLL) -> None:
     L.gg_engine_set_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.gg_engine_set_labels.argtypes = [vp, vp, vp, vp]
     L.gg_film_patch_encode.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.gg_gemm_layernorm.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, f32, f32, vp, C.c_uint32, vp]
     L.gg_xw_f32.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp, i64, vp]
     L.gg_dropout_bits_words.argtypes = [i64]
     L.gg_dropout_bits_words.restype = i64
@@ -186,5 +187,5 @@ EXPORTS = [
     "gg_launch_count", "gg_launch_count_add", "gg_gemm_profile_begin", "gg_gemm_profile_end", "gg_gemm_profile_dump", "gg_gemm_set_trace", "gg_gemm_profile_bytes", "gg_gemm_set_timer", "gg_gemm_timer_slots",
     "gg_pairwise_distance", "gg_row_kth_smallest", "gg_row_membership", "gg_col_hits", "gg_standardize_columns",
     "gg_gene_correlation", "gg_gamma_moments_workspace_bytes", "gg_gamma_moments",
-    "gg_encoder_layer_fwd", "gg_encoder_ffn_bwd", "gg_enc_layer_set_trace", "gg_enc_layer_profile", "gg_wgrad_group_profile", "gg_attention_fwd", "gg_attention_bwd", "gg_dropout_bits", "gg_dropout_bits_words", "gg_xw_f32", "gg_film_patch_encode", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
+    "gg_encoder_layer_fwd", "gg_encoder_ffn_bwd", "gg_enc_layer_set_trace", "gg_enc_layer_profile", "gg_wgrad_group_profile", "gg_attention_fwd", "gg_attention_bwd", "gg_dropout_bits", "gg_dropout_bits_words", "gg_xw_f32", "gg_gemm_layernorm", "gg_film_patch_encode", "gg_wgrad_group", "gg_wgrad_group_workspace_bytes", "gg_colsum_group", "gg_colsum_group_workspace_bytes",
 ]

@@ -342,6 +342,7 @@ struct gg_engine {
   // c = pv + (v_text Wo^T + bo) with the text-only term computed once on the text lane. GEMMGAN_T1_SHORTCUT=0 runs the
   // general path (same numbers to bf16 rounding; tests compare both).
   bool t1_shortcut = true;
+  bool gemm_ln = true;     // GEMMGAN_GEMM_LN=0: out-projection / linear2 and their add + LayerNorm as two launches each
   bool film_fused = true;  // GEMMGAN_FILM_FUSED=0: film_apply_kernel + patch GEMM + token assembly as three launches
   bool gp_tf32 = false;   // GEMMGAN_GP_TF32=1 (gg_engine_gp_step)
   bool attn_bits = true;  // GEMMGAN_ATTN_BITS=0: the 17 .. 320-token attention kernels draw their dropout masks themselves
@@ -817,16 +818,30 @@ static int tower_forward(gg_engine& e, int net, int R, float p, int ln, int save
       a.dbits = L.dbits;
     }
     GG_TRY(k_attention_fwd(a, st));
+    // out-projection / linear2 with the residual + dropout + LayerNorm in the GEMM epilogue (gemm_ln.cu), else two launches
+    const bool gemm_ln = e.gemm_ln && c.gemm_impl == GG_IMPL_TCGEN05 && E == 256 && F % 64 == 0;
+    if (gemm_ln) {
+      const Op wo = e.W(net, ls + GG_L_OUT_W);
+      GG_TRY(k_gemm_ln(L.ao, E, wo.p, wo.ld, E, e.P(net, ls + GG_L_OUT_B), t.X[l], e.P(net, ls + GG_L_N1_W),
+                       e.P(net, ls + GG_L_N1_B), L.z1, L.x1, L.mean1, L.rstd1, rows, c.ln_eps, p, e.rng, site + 1, st));
+    } else {
     GG_TRY(e.linear(ln, rows, E, E, Op{L.ao, E}, e.W(net, ls + GG_L_OUT_W),
                     Epi().bias(e.P(net, ls + GG_L_OUT_B)).obf(t.tmpE, E)));
     GG_TRY(k_add_ln_fwd(t.X[l], t.tmpE, e.P(net, ls + GG_L_N1_W), e.P(net, ls + GG_L_N1_B), L.z1, L.x1, L.mean1,
                         L.rstd1, rows, E, c.ln_eps, p, e.rng, site + 1, st));
+    }
     GG_TRY(e.linear(ln, rows, F, E, Op{L.x1, E}, e.W(net, ls + GG_L_FF1_W),
                     Epi().bias(e.P(net, ls + GG_L_FF1_B)).act(GG_ACT_LEAKY, 0.f).drop(p, e.rng, site + 2).obf(L.h, F)));
+    if (gemm_ln) {
+      const Op w2 = e.W(net, ls + GG_L_FF2_W);
+      GG_TRY(k_gemm_ln(L.h, F, w2.p, w2.ld, F, e.P(net, ls + GG_L_FF2_B), L.x1, e.P(net, ls + GG_L_N2_W),
+                       e.P(net, ls + GG_L_N2_B), L.z2, t.X[l + 1], L.mean2, L.rstd2, rows, c.ln_eps, p, e.rng, site + 3, st));
+    } else {
     GG_TRY(e.linear(ln, rows, E, F, Op{L.h, F}, e.W(net, ls + GG_L_FF2_W),
                     Epi().bias(e.P(net, ls + GG_L_FF2_B)).obf(t.tmpE, E)));
     GG_TRY(k_add_ln_fwd(L.x1, t.tmpE, e.P(net, ls + GG_L_N2_W), e.P(net, ls + GG_L_N2_B), L.z2, t.X[l + 1],
                         L.mean2, L.rstd2, rows, E, c.ln_eps, p, e.rng, site + 3, st));
+    }
   }
   if (!e.paper) return GG_OK;  // film: conditioning = CLS row of X[n_layers]
   bf16* Xf = t.X[c.n_layers];
@@ -1297,6 +1312,8 @@ extern "C" int gg_engine_create(const gg_model_cfg* cfg, const gg_net_buffers* g
     const char* fl = getenv("GEMMGAN_FUSED_LAYER");
     e->fused_layer = !(fl && fl[0] == '0');
     e->layer_bits = layer_bits_requested();
+    const char* gl = getenv("GEMMGAN_GEMM_LN");
+    e->gemm_ln = !(gl && gl[0] == '0');
     const char* ff = getenv("GEMMGAN_FILM_FUSED");
     e->film_fused = !(ff && ff[0] == '0');
     const char* t1 = getenv("GEMMGAN_T1_SHORTCUT");
@@ -1778,6 +1795,16 @@ extern "C" int gg_film_patch_encode(const void* patches_bf16, const float* gamma
   return k_film_patch(reinterpret_cast<const bf16*>(patches_bf16), gamma_beta, reinterpret_cast<const bf16*>(w_bf16), ldw, bias,
                       cls, reinterpret_cast<bf16*>(x0_bf16), reinterpret_cast<bf16*>(mod_bf16), B, P, R, Dp,
                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gg_gemm_layernorm(const void* a_bf16, int64_t lda, const void* w_bf16, int64_t ldw, int32_t K, const float* bias,
+                                 const void* res_bf16, const float* gamma, const float* beta, void* z_bf16, void* out_bf16,
+                                 float* mean, float* rstd, int64_t rows, float eps, float drop_p, const uint64_t* rng,
+                                 uint32_t site, void* stream) {
+  return k_gemm_ln(reinterpret_cast<const bf16*>(a_bf16), lda, reinterpret_cast<const bf16*>(w_bf16), ldw, K, bias,
+                   reinterpret_cast<const bf16*>(res_bf16), gamma, beta, reinterpret_cast<bf16*>(z_bf16),
+                   reinterpret_cast<bf16*>(out_bf16), mean, rstd, rows, eps, drop_p, rng, site,
+                   reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream) {

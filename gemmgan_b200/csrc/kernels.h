@@ -78,6 +78,11 @@ int k_xw_f32(const float* x0, const float* x1, int B, int K, const bf16* w, int6
 int k_film_patch(const bf16* patches, const float* gb, const bf16* w, int64_t ldw, const float* bias, const float* cls, bf16* x0,
                  bf16* mod, int B, int P, int R, int Dp, cudaStream_t st);
 
+// ---- gemm_ln.cu: z = res + dropout(a w^T + bias), out = LayerNorm(z) (256 columns) in one tcgen05 kernel
+int k_gemm_ln(const bf16* a, int64_t lda, const bf16* w, int64_t ldw, int K, const float* bias, const bf16* res,
+              const float* gamma, const float* beta, bf16* z, bf16* out, float* mean, float* rstd, int64_t rows, float eps,
+              float drop_p, const uint64_t* rng, uint32_t site, cudaStream_t st);
+
 // live profiler channel of the grouped weight-gradient kernel (gemm.cu; no-ops unless gg_gemm_profile_begin is active)
 int prof_wgrad_begin(double flops, double bytes, cudaStream_t stream);
 int prof_wgrad_end(cudaStream_t stream);

@@ -326,6 +326,14 @@ int gg_xw_f32(const float* x0, const float* x1, int32_t B, int32_t K, const void
 int gg_film_patch_encode(const void* patches_bf16, const float* gamma_beta, const void* w_bf16, int64_t ldw, const float* bias,
                          const float* cls, void* x0_bf16, void* mod_bf16, int32_t B, int32_t P, int32_t R, int32_t Dp,
                          void* stream);
+/* `x = norm(x + dropout(linear(a)))` of a post-norm encoder layer (torch/nn/modules/transformer.py: norm1 / _sa_block's
+ * out_proj, norm2 / linear2; reference :114-119) as one kernel for d_model = 256: z = res + dropout(a w^T + bias) (bf16, kept
+ * for the backward), out = LayerNorm(z) * gamma + beta, mean / rstd per row (fp32). a bf16 [rows, K] (pitch lda, K % 64 == 0),
+ * w bf16 [256, K] (pitch ldw), res / z / out bf16 [rows, 256]; bias / beta may be NULL. Dropout: stream {seed, step} at rng,
+ * `site`, element index row * 256 + column (the indexing of the stand-alone LayerNorm kernels). */
+int gg_gemm_layernorm(const void* a_bf16, int64_t lda, const void* w_bf16, int64_t ldw, int32_t K, const float* bias,
+                      const void* res_bf16, const float* gamma, const float* beta, void* z_bf16, void* out_bf16, float* mean,
+                      float* rstd, int64_t rows, float eps, float drop_p, const uint64_t* rng, uint32_t site, void* stream);
 /* out[b, :] (fp32) = mean over the rows p with pad[b, p] == 0 of x[b, p, :] — the masked mean of
  * conditional_gan_concat.py:137-138 ('image' conditioning), taken BEFORE the affine encoder. pad may be NULL. */
 int gg_masked_mean_rows(const float* x, const uint8_t* pad, float* out, int B, int P, int D, void* stream);

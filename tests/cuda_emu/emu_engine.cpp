@@ -41,6 +41,11 @@ int k_film_patch(const bf16*, const float*, const bf16*, int64_t, const float*, 
   set_error("the fused FiLM patch-encoder kernel is tcgen05 only (not available in the host emulation)");
   return GG_ERR_ARCH;
 }
+int k_gemm_ln(const bf16*, int64_t, const bf16*, int64_t, int, const float*, const bf16*, const float*, const float*, bf16*, bf16*,
+              float*, float*, int64_t, float, float, const uint64_t*, uint32_t, cudaStream_t) {
+  set_error("the GEMM + LayerNorm kernel is tcgen05 only (not available in the host emulation)");
+  return GG_ERR_ARCH;
+}
 int k_enc_ffn_bwd(const EncFfnBwdParams&, cudaStream_t) {
   set_error("the fused ffn-backward kernel is tcgen05 only (not available in the host emulation)");
   return GG_ERR_ARCH;
