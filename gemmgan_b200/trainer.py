@@ -140,6 +140,10 @@ class TrainerBase:
         self.gen, self.disc = gen.to(self.device), disc.to(self.device)
         self.gen._gg_owner = self
         self.disc._gg_owner = self
+        # new networks (fit() builds again, as the reference's does at :620-623): the flat buffers, engines and
+        # captured graphs of the previous pair must not outlive it, or the engine would keep training the old modules
+        self._flat_gen = self._flat_disc = None
+        self._engines.clear()
 
     def _flatten(self):
         if self._flat_gen is None:

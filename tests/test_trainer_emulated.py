@@ -1,0 +1,328 @@
+"""The drop-in trainer classes themselves on the CPU suite: `WGAN_GP` / `WGAN_GP_nocond` of the root modules
+(gemmgan_b200/trainer.py::TrainerBase) driving the engine compiled for the host (tests/cuda_emu/emu_engine.cpp,
+all-CUDA-core configuration), called the way a user of the reference calls them — build_WGAN_GP(), init_train(),
+train(...), fit(loader), generate_samples(...), state_dict()s — against the oracle (oracle/restated.py, pinned to
+the unmodified reference; src/conditional_gan_cross_attention_with_film.py:256-477,
+src/vanilla_gan_unconditional.py:211-431) and against themselves.
+
+What this adds to tests/test_engine_emulated.py (which drives runtime.Engine directly): the host logic between the
+reference-facing methods and the engine — one engine per batch size sharing the flat buffers (a last partial batch, a
+validation loader of another batch size), networks rebuilt by fit(), noise staged up front, LR halving through
+`param_groups`, optimizer / network checkpoints. Not covered here (GPU only): CUDA graphs, lanes, prefetch, NCCL.
+"""
+import contextlib
+import importlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+import emu_build
+from gemmgan_b200 import _abi_decl as A
+from gemmgan_b200 import _lib, runtime, trainer
+from oracle import restated
+
+TOL = 2e-2
+COS_FLOOR = 0.75       # see update_cosine()
+SMALL = dict(G=203, P=5, T=3, embed=32, hidden=32, latent=16, text_dim=24, patch_dim=32)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    L = emu_build.build("engine", tmp_path_factory.mktemp("cuda_emu"), cudart=True)
+    A.declare(L)
+    return L
+
+
+class _Event:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+@pytest.fixture()
+def host(emu, monkeypatch):
+    """The trainer on the host: the library is the emulated build, the device is the CPU, steps run eagerly."""
+    monkeypatch.setattr(_lib, "lib", lambda: emu)
+    monkeypatch.setattr(_lib, "require_device", lambda dev=0: None)
+    monkeypatch.setattr(_lib, "require_cuda_tensor_device", lambda dev, what: None)
+    monkeypatch.setattr(runtime, "_stream", lambda: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    orig_engine = runtime.Engine.__init__
+
+    def simt(self, *a, **kw):          # the host build has no tcgen05 GEMMs: CUDA-core fp32 check path, one lane
+        kw["gemm_impl"] = _lib.IMPL_SIMT_F32
+        orig_engine(self, *a, **kw)
+        self.set_lanes(False)
+    monkeypatch.setattr(runtime.Engine, "__init__", simt)
+    orig_common = trainer.TrainerBase._init_common
+
+    def common(self, *a, **kw):
+        with monkeypatch.context() as mp:      # (only here: torch.optim of the oracle asks torch.cuda too)
+            mp.setattr(torch.cuda, "is_available", lambda: True)
+            mp.setattr(torch.cuda, "current_device", lambda: 0)
+            orig_common(self, *a, **kw)
+        self.device = torch.device("cpu")
+        self.use_cuda_graphs = False
+        self.dropout_p = 0.0           # (the masks are the engine's own stream; covered by the GPU suite)
+    monkeypatch.setattr(trainer.TrainerBase, "_init_common", common)
+    monkeypatch.setattr(trainer.TrainerBase, "prefetch", lambda self, *t: None)   # a copy stream: GPU only
+    return trainer
+
+
+def make(variant, optimizer="adam", seed=11, **kw):
+    """(oracle, drop-in trainer) holding the same initial weights."""
+    c = SMALL
+    H, G = c["hidden"], c["G"]
+    torch.manual_seed(seed)
+    o = restated.OracleWGANGP(variant, G, latent=c["latent"], embed=c["embed"], hidden=H, optimizer=optimizer,
+                              negative_slope=0.0, dropout=0.0, text_dim=c["text_dim"], patch_dim=c["patch_dim"])
+    torch.manual_seed(seed)
+    if variant == "vanilla":
+        m = importlib.import_module("vanilla_gan_unconditional")
+        t = m.WGAN_GP_nocond(input_dims=G, latent_dims=c["latent"], vocab_sizes=[], generator_dims=[H, H, G],
+                             discriminator_dims=[H, H, 1], optimizer=optimizer, **kw)
+        t.build_WGAN_GP_nocond()
+    else:
+        m = importlib.import_module({"paper": "conditional_gan_cross_attention_with_film",
+                                     "film": "conditional_gan_film"}[variant])
+        t = m.WGAN_GP(input_dims=G, latent_dims=c["latent"], embedding_dims=c["embed"], generator_dims=[H, H, G],
+                      discriminator_dims=[H, H, 1], text_embedding_dims=c["text_dim"],
+                      patches_embedding_dims=c["patch_dim"], optimizer=optimizer, **kw)
+        t.build_WGAN_GP()
+    t.init_train()
+    for a, b in ((o.gen, t.gen), (o.disc, t.disc)):
+        for (k1, v1), (k2, v2) in zip(a.state_dict().items(), b.state_dict().items()):
+            assert k1 == k2 and torch.equal(v1, v2), k1
+    return o, t
+
+
+def batch(variant, B, seed):
+    c = SMALL
+    return restated.synthetic_batch(variant, B, c["G"], P=c["P"], T=c["T"], seed=seed, ragged=True,
+                                    text_dim=c["text_dim"], patch_dim=c["patch_dim"])
+
+
+def call_train(t, variant, x, cond, zs=None, alphas=None):
+    """train() in each variant's own argument order (…with_film.py:463, conditional_gan_film.py:432,
+    vanilla_gan_unconditional.py:417); cond is in model-argument order."""
+    if variant == "vanilla":
+        t.train(x, zs=zs, alphas=alphas)
+    elif variant == "paper":
+        patches, ppad, text, tpad = cond
+        t.train(x, text, tpad, patches, ppad, zs=zs, alphas=alphas)
+    else:
+        text, patches, ppad = cond
+        t.train(x, text, patches, ppad, zs=zs, alphas=alphas)
+
+
+def noise(B, n_critic=5, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    zs = [torch.randn(B, SMALL["latent"], generator=g) for _ in range(n_critic + 1)]
+    alphas = [torch.rand(B, 1, generator=g) for _ in range(n_critic)]
+    return zs, alphas
+
+
+def snapshot(tr):
+    return ({k: v.clone() for k, v in tr.disc.state_dict().items()}, {k: v.clone() for k, v in tr.gen.state_dict().items()})
+
+
+def update_cosine(before, ref_net, net):
+    """Cosine between the two UPDATE vectors (weights after - weights before, every tensor concatenated). The first
+    Adam / RMSprop steps are lr * sign(g) / 10 lr * sign(g) for every entry, so rounding in near-zero gradient entries
+    becomes full steps: the cosine is about the share of entries whose sign agrees (the measure
+    tests/test_gpu_parity_full.py uses on the B200)."""
+    ur = torch.cat([(v - before[k]).flatten() for k, v in ref_net.state_dict().items()])
+    ug = torch.cat([(v - before[k]).flatten() for k, v in net.state_dict().items()])
+    return float(ur @ ug / (ur.norm() * ug.norm()).clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("variant,optimizer", [("vanilla", "adam"), ("vanilla", "rms_prop"), ("paper", "adam"),
+                                               ("film", "rms_prop")])
+def test_train_call_matches_the_oracle(host, variant, optimizer):
+    """One train() (5 critic steps + 1 generator step) through the reference-facing method: loss statistics and the
+    weights both networks end up with."""
+    o, t = make(variant, optimizer)
+    B = 8
+    x, cond = batch(variant, B, seed=3)
+    zs, alphas = noise(B)
+    bd, bg = snapshot(o)
+    o.train(x, cond, zs, alphas)
+    call_train(t, variant, x, cond, zs, alphas)
+    scale = max(1.0, float(np.abs(o.d_batch_loss).max()))
+    assert np.abs(t.d_batch_loss - o.d_batch_loss).max() <= TOL * scale, (t.d_batch_loss, o.d_batch_loss)
+    assert abs(float(t.g_batch_loss[0]) - float(o.g_batch_loss[0])) <= TOL * max(1.0, abs(float(o.g_batch_loss[0])))
+    cd, cg = update_cosine(bd, o.disc, t.disc), update_cosine(bg, o.gen, t.gen)
+    print(f"{variant}/{optimizer}: update cosine critic {cd:.4f} generator {cg:.4f}")
+    assert cd > COS_FLOOR and cg > COS_FLOOR, (cd, cg)
+    # observable side effects of the reference's train_gen (:433-438)
+    assert all(not p.requires_grad for p in t.disc.parameters()) and all(p.requires_grad for p in t.gen.parameters())
+
+
+def test_noise_drawn_inside_train_follows_the_reference_order(host):
+    """Without explicit noise train() draws z, alpha, z, alpha, ..., z from torch's global stream — the order of the
+    reference's loop (:463-477, :354) — so seeding both sides gives the same call."""
+    o, t = make("vanilla", "adam")
+    B = 8
+    x, cond = batch("vanilla", B, seed=3)
+    bd, bg = snapshot(o)
+    torch.manual_seed(123)
+    o.train(x, cond)
+    torch.manual_seed(123)
+    call_train(t, "vanilla", x, cond)
+    assert np.abs(t.d_batch_loss - o.d_batch_loss).max() <= TOL * max(1.0, float(np.abs(o.d_batch_loss).max()))
+    assert update_cosine(bd, o.disc, t.disc) > COS_FLOOR and update_cosine(bg, o.gen, t.gen) > COS_FLOOR
+
+
+def test_fit_rebuilds_the_networks_and_trains_the_new_ones(host, tmp_path):
+    """fit() builds the networks again (reference :620-623). A trainer that was already built and stepped must then
+    train — and checkpoint — the NEW pair, not the one its flat buffers were made from."""
+    _, t = make("vanilla", "adam", results_dire=str(tmp_path))
+    x, cond = batch("vanilla", 8, seed=3)
+    call_train(t, "vanilla", x, cond)
+    old_gen = t.gen
+    data = [(batch("vanilla", 8, seed=20 + i)[0],) for i in range(3)]
+    t.fit(data, epochs=1)
+    assert t.gen is not old_gen and t._flat_gen.module is t.gen and t._flat_disc.module is t.disc
+    w0 = t.gen.final_layer.weight.detach().clone()
+    call_train(t, "vanilla", x, cond)
+    assert float((t.gen.final_layer.weight - w0).abs().max()) > 0.0
+    saved = torch.load(tmp_path / "generator_last_epoch.pt")
+    assert torch.equal(saved["final_layer.weight"], w0)           # what fit() trained is what it saved
+    assert len(t.loss_dict["d loss"]) == 1 and np.isfinite(t.loss_dict["g loss"][0])
+
+
+@pytest.mark.parametrize("variant", ["vanilla", "paper"])
+def test_engines_of_other_batch_sizes_follow_the_weights(host, variant):
+    """len(dataset) % B != 0 and a validation loader of another batch size: every batch size has its own engine with
+    its own bf16 weight shadows. Training with one engine must be seen by the others — compare with the oracle taking
+    the same sequence of batches, and generation at a third batch size with a fresh trainer loaded from the weights."""
+    o, t = make(variant, "adam")
+    sizes = [8, 8, 3, 8, 3]                      # two epochs of 19 rows at B = 8
+    bd, bg = snapshot(o)
+    for i, B in enumerate(sizes):
+        x, cond = batch(variant, B, seed=40 + i)
+        zs, alphas = noise(B, seed=60 + i)
+        o.train(x, cond, zs, alphas)
+        call_train(t, variant, x, cond, zs, alphas)
+    assert len(t._engines) == 2
+    assert np.abs(t.d_batch_loss - o.d_batch_loss).max() <= TOL * max(1.0, float(np.abs(o.d_batch_loss).max()))
+    cd, cg = update_cosine(bd, o.disc, t.disc), update_cosine(bg, o.gen, t.gen)
+    print(f"{variant}: update cosine over 30 steps on two engines: critic {cd:.4f} generator {cg:.4f}")
+    assert cd > COS_FLOOR and cg > COS_FLOOR, (cd, cg)
+    # a validation batch of 5 rows, first on a new engine, then again after more training on the B = 8 engine
+    xv, cv = batch(variant, 5, seed=77)
+
+    def generate(tr):
+        torch.manual_seed(9)
+        if variant == "vanilla":
+            return tr.generate_samples(xv)[1]
+        patches, ppad, text, tpad = cv
+        return tr.generate_samples(xv, text, tpad, patches, ppad)[1]
+
+    def fresh_copy():
+        _, f = make(variant, "adam", seed=99)
+        f.gen.load_state_dict(t.gen.state_dict())
+        f.disc.load_state_dict(t.disc.state_dict())
+        return f
+
+    assert torch.equal(generate(t), generate(fresh_copy()))
+    x, cond = batch(variant, 8, seed=50)
+    call_train(t, variant, x, cond, *noise(8, seed=70))
+    assert len(t._engines) == 3
+    assert torch.equal(generate(t), generate(fresh_copy()))      # the B = 5 engine refreshed its shadows
+
+
+def test_lr_halving_through_param_groups_reaches_the_kernel(host):
+    """fit() halves both learning rates through optimizer.param_groups (:649-657): the engine's update must use them."""
+    o, t = make("vanilla", "rms_prop")
+    B = 8
+    x, cond = batch("vanilla", B, seed=3)
+    for tr in (o, t):
+        for opt in (tr.optimizer_disc, tr.optimizer_gen):
+            for g in opt.param_groups:
+                g["lr"] *= 0.5
+    w0 = t.gen.final_layer.weight.detach().clone()
+    zs, alphas = noise(B)
+    bd, bg = snapshot(o)
+    o.train(x, cond, zs, alphas)
+    call_train(t, "vanilla", x, cond, zs, alphas)
+    assert update_cosine(bd, o.disc, t.disc) > COS_FLOOR and update_cosine(bg, o.gen, t.gen) > COS_FLOOR
+    ud = torch.cat([(v - bd[k]).flatten() for k, v in t.disc.state_dict().items()])
+    ur = torch.cat([(v - bd[k]).flatten() for k, v in o.disc.state_dict().items()])
+    assert 0.9 < float(ud.norm() / ur.norm()) < 1.1               # half the rate moved the weights half as far
+    # RMSprop's first step moves every weight with a non-zero gradient by lr / sqrt(1 - alpha) = 10 lr = 2.5e-3
+    step = float((t.gen.final_layer.weight - w0).abs().max())
+    assert 2.0e-3 <= step <= 2.6e-3, step
+    t._epoch_lr_decay(100, 100)
+    assert t.optimizer_gen.param_groups[0]["lr"] == pytest.approx(1.25e-4)
+    t._epoch_lr_decay(101, 100)
+    assert t.optimizer_gen.param_groups[0]["lr"] == pytest.approx(1.25e-4)
+
+
+@pytest.mark.parametrize("optimizer", ["adam", "rms_prop"])
+def test_checkpoint_of_networks_and_optimizers_resumes_bitwise(host, optimizer):
+    """torch.save of the four state_dicts after some training, loaded into a new trainer: both continue identically
+    (the optimizer state lives in the flat buffers the kernel updates; state_dict() sees it through views)."""
+    _, t = make("vanilla", optimizer)
+    B = 8
+    x, cond = batch("vanilla", B, seed=3)
+    call_train(t, "vanilla", x, cond, *noise(B, seed=1))
+    buf = io.BytesIO()
+    torch.save({"gen": t.gen.state_dict(), "disc": t.disc.state_dict(), "og": t.optimizer_gen.state_dict(),
+                "od": t.optimizer_disc.state_dict()}, buf)
+    buf.seek(0)
+    ck = torch.load(buf)
+    _, r = make("vanilla", optimizer, seed=99)
+    call_train(r, "vanilla", x, cond, *noise(B, seed=2))           # r has engines and state of its own by now
+    r.gen.load_state_dict(ck["gen"])
+    r.disc.load_state_dict(ck["disc"])
+    r.optimizer_gen.load_state_dict(ck["og"])
+    r.optimizer_disc.load_state_dict(ck["od"])
+    x2, cond2 = batch("vanilla", B, seed=4)
+    call_train(t, "vanilla", x2, cond2, *noise(B, seed=3))
+    call_train(r, "vanilla", x2, cond2, *noise(B, seed=3))
+    for (k, a), (_, b) in zip(t.gen.state_dict().items(), r.gen.state_dict().items()):
+        assert torch.equal(a, b), k
+    for (k, a), (_, b) in zip(t.disc.state_dict().items(), r.disc.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert np.array_equal(t.d_batch_loss, r.d_batch_loss)
+
+
+def test_single_steps_and_module_calls_through_the_trainer(host):
+    """train_disc / train_gen / gradient_penalty / gen(...) / disc(...) in the reference's signatures (:351-461)."""
+    o, t = make("paper", "adam")
+    B = 8
+    x, cond = batch("paper", B, seed=3)
+    patches, ppad, text, tpad = cond
+    zs, alphas = noise(B)
+    o.train_disc(x, zs[0], cond, alphas[0])
+    t.train_disc(x, zs[0], text, tpad, patches, ppad, alpha=alphas[0])
+    assert np.abs(t.d_batch_loss - o.d_batch_loss).max() <= TOL * max(1.0, float(np.abs(o.d_batch_loss).max()))
+    assert all(p.requires_grad for p in t.disc.parameters()) and all(not p.requires_grad for p in t.gen.parameters())
+    # the prototype encoder layer the reference registers but never runs keeps grad None (:114)
+    assert all(p.grad is None for p in t.disc.patches_transformer_layer.parameters())
+    assert t.disc.final_layer.weight.grad is not None
+    o.train_gen(zs[1], cond)
+    t.train_gen(zs[1], text, tpad, patches, ppad)
+    assert abs(float(t.g_batch_loss[0]) - float(o.g_batch_loss[0])) <= TOL * max(1.0, abs(float(o.g_batch_loss[0])))
+    t.gen.eval(), t.disc.eval(), o.gen.eval(), o.disc.eval()
+    with torch.no_grad():
+        fake_o = o.gen(zs[2], *cond)
+        fake_t = t.gen(zs[2], *cond)
+        assert float((fake_t - fake_o).abs().max()) <= TOL * float(fake_o.abs().max())
+        s_o, s_t = o.disc(x, *cond), t.disc(x, *cond)
+        assert s_t.shape == s_o.shape == (B, 1)
+        assert float((s_t - s_o).abs().max()) <= TOL * max(1.0, float(s_o.abs().max()))
+    t.disc.train(), o.disc.train()
+    gp_o = o.gradient_penalty(x, fake_o, cond, alphas[1])
+    gp_t = t.gradient_penalty(x, fake_o, patches, ppad, text, tpad, alpha=alphas[1])
+    assert abs(float(gp_t) - float(gp_o)) <= TOL * max(1.0, abs(float(gp_o)))
