@@ -98,3 +98,68 @@ def test_label_conditioned_nets_mirror_the_oracle_layout():
     import pytest
     with pytest.raises(NotImplementedError):
         bm.generator(16, [], [10], [32, 32, 203])   # one variable: 128 != the hard-coded 256 (reference shape error)
+
+
+def _cfg(variant, B=1024, G=18868, P=8, T=1):
+    c = _abi_decl.ModelCfg()
+    c.variant = variant
+    c.B, c.G, c.L, c.E, c.H = B, G, 256, 256, 256
+    c.Dt, c.Dp, c.P, c.T = 768, 1024, P, T
+    c.n_layers, c.n_heads, c.ffn = 2, 4, 512
+    c.tower_bias = 1
+    c.slope, c.dropout_p, c.gp_weight = 0.0, 0.1, 10.0
+    c.clip_d, c.clip_g, c.ln_eps = 10.0, 2.0, 1e-5
+    c.optimizer = _abi_decl.OPT_RMSPROP
+    c.gemm_impl = _lib.IMPL_TCGEN05
+    c.seed = 0
+    return c
+
+
+def test_host_only_entry_points_validate_and_report_errors():
+    """Error behaviour of the REAL library on a machine without a GPU (host-only entry points; no compute): a negative
+    code and a message behind gg_last_error(), never a crash or a silent default; workspace sizes of the BASELINE
+    configurations fit one B200 (180 GB) with room for the batch tensors."""
+    from gemmgan_b200.models import VARIANT_IDS
+
+    L = _lib.lib()
+    _abi_decl.declare(L)
+    L.gg_last_error.restype = C.c_char_p
+    n = C.c_int64(0)
+    sizes = {}
+    for name, kw in (("cfg3", dict(B=1024, G=18868, P=8, T=1)), ("cfg2", dict(B=256, G=18868, P=256, T=1)),
+                     ("cfg4", dict(B=4096, G=20000, P=64, T=32))):
+        c = _cfg(VARIANT_IDS["paper"], **kw)
+        assert L.gg_engine_workspace_bytes(C.byref(c), C.byref(n)) == 0, L.gg_last_error()
+        sizes[name] = n.value
+        assert 0 < n.value < 120 * 2**30 and n.value % 256 == 0, (name, n.value)
+    assert sizes["cfg4"] > sizes["cfg3"]
+    bad = [(_cfg(99), b"variant"), (_cfg(VARIANT_IDS["paper"], B=0), b"sizes"),
+           (_cfg(VARIANT_IDS["paper"], P=400), b"token counts"), (_cfg(VARIANT_IDS["paper"], T=0), b"token counts")]
+    c = _cfg(VARIANT_IDS["paper"])
+    c.n_heads = 3
+    bad.append((c, b"head"))
+    c = _cfg(VARIANT_IDS["paper"])
+    c.dropout_p = 1.5
+    bad.append((c, b"dropout"))
+    for c, word in bad:
+        rc = L.gg_engine_workspace_bytes(C.byref(c), C.byref(n))
+        assert rc == -1, (word, rc)                                  # GG_ERR_ARG
+        assert word in L.gg_last_error(), (word, L.gg_last_error())
+    assert L.gg_engine_workspace_bytes(None, C.byref(n)) == -1
+
+
+def test_product_refuses_to_run_without_a_cuda_device():
+    """No CPU fallback: without a GPU the library's device check fails and the drop-in trainers raise on construction."""
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this is the no-GPU half; the GPU suite covers the other")
+    L = _lib.lib()
+    assert L.gg_check_device(0) != 0
+    with pytest.raises((_lib.GGError, RuntimeError)):
+        _lib.require_device(0)
+    import vanilla_gan_unconditional as v
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        v.WGAN_GP_nocond(input_dims=200, latent_dims=16, vocab_sizes=[], generator_dims=[32, 32, 200],
+                         discriminator_dims=[32, 32, 1])
