@@ -10,7 +10,6 @@ reference-facing methods and the engine — one engine per batch size sharing th
 validation loader of another batch size), networks rebuilt by fit(), noise staged up front, LR halving through
 `param_groups`, optimizer / network checkpoints. Not covered here (GPU only): CUDA graphs, lanes, prefetch, NCCL.
 """
-import contextlib
 import importlib
 import io
 
@@ -19,8 +18,8 @@ import pytest
 import torch
 
 import emu_build
+import host_trainer
 from gemmgan_b200 import _abi_decl as A
-from gemmgan_b200 import _lib, runtime, trainer
 from oracle import restated
 
 TOL = 2e-2
@@ -35,47 +34,10 @@ def emu(tmp_path_factory):
     return L
 
 
-class _Event:
-    def __init__(self, *a, **k):
-        pass
-
-    def record(self, *a):
-        pass
-
-    def synchronize(self):
-        pass
-
-
 @pytest.fixture()
 def host(emu, monkeypatch):
     """The trainer on the host: the library is the emulated build, the device is the CPU, steps run eagerly."""
-    monkeypatch.setattr(_lib, "lib", lambda: emu)
-    monkeypatch.setattr(_lib, "require_device", lambda dev=0: None)
-    monkeypatch.setattr(_lib, "require_cuda_tensor_device", lambda dev, what: None)
-    monkeypatch.setattr(runtime, "_stream", lambda: None)
-    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
-    monkeypatch.setattr(torch.cuda, "Event", _Event)
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
-    orig_engine = runtime.Engine.__init__
-
-    def simt(self, *a, **kw):          # the host build has no tcgen05 GEMMs: CUDA-core fp32 check path, one lane
-        kw["gemm_impl"] = _lib.IMPL_SIMT_F32
-        orig_engine(self, *a, **kw)
-        self.set_lanes(False)
-    monkeypatch.setattr(runtime.Engine, "__init__", simt)
-    orig_common = trainer.TrainerBase._init_common
-
-    def common(self, *a, **kw):
-        with monkeypatch.context() as mp:      # (only here: torch.optim of the oracle asks torch.cuda too)
-            mp.setattr(torch.cuda, "is_available", lambda: True)
-            mp.setattr(torch.cuda, "current_device", lambda: 0)
-            orig_common(self, *a, **kw)
-        self.device = torch.device("cpu")
-        self.use_cuda_graphs = False
-        self.dropout_p = 0.0           # (the masks are the engine's own stream; covered by the GPU suite)
-    monkeypatch.setattr(trainer.TrainerBase, "_init_common", common)
-    monkeypatch.setattr(trainer.TrainerBase, "prefetch", lambda self, *t: None)   # a copy stream: GPU only
-    return trainer
+    return host_trainer.apply(monkeypatch.setattr, emu)
 
 
 def make(variant, optimizer="adam", seed=11, **kw):
