@@ -168,7 +168,7 @@ def test_engines_of_other_batch_sizes_follow_the_weights(host, variant):
     its own bf16 weight shadows. Training with one engine must be seen by the others — compare with the oracle taking
     the same sequence of batches, and generation at a third batch size with a fresh trainer loaded from the weights."""
     o, t = make(variant, "adam")
-    sizes = [8, 8, 3, 8, 3]                      # two epochs of 19 rows at B = 8
+    sizes = [8, 3, 8]                            # 11 rows at B = 8, then the next epoch
     bd, bg = snapshot(o)
     for i, B in enumerate(sizes):
         x, cond = batch(variant, B, seed=40 + i)
@@ -178,7 +178,7 @@ def test_engines_of_other_batch_sizes_follow_the_weights(host, variant):
     assert len(t._engines) == 2
     assert np.abs(t.d_batch_loss - o.d_batch_loss).max() <= TOL * max(1.0, float(np.abs(o.d_batch_loss).max()))
     cd, cg = update_cosine(bd, o.disc, t.disc), update_cosine(bg, o.gen, t.gen)
-    print(f"{variant}: update cosine over 30 steps on two engines: critic {cd:.4f} generator {cg:.4f}")
+    print(f"{variant}: update cosine over 18 steps on two engines: critic {cd:.4f} generator {cg:.4f}")
     assert cd > COS_FLOOR and cg > COS_FLOOR, (cd, cg)
     # a validation batch of 5 rows, first on a new engine, then again after more training on the B = 8 engine
     xv, cv = batch(variant, 5, seed=77)
