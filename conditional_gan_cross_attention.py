@@ -19,7 +19,7 @@ import torch
 
 import conditional_gan_cross_attention_with_film as _paper
 from conditional_gan_cross_attention_with_film import (D_loss, G_loss, build_discriminator,  # noqa: F401
-                                                        build_generator, build_linear_block, parse_args,
+                                                        build_generator, build_linear_block,
                                                         wasserstein_loss)
 from gemmgan_b200.models import CrossDiscriminator, CrossGenerator
 
@@ -60,17 +60,14 @@ class WGAN_GP(_paper.WGAN_GP):
         self._attach(gen, disc)
 
 
-if __name__ == '__main__':
-    from gemmgan_b200.synthetic import synthetic_loader
+def parse_args(argv=None):
+    """The reference's flags [see gemmgan_b200/cli.py]."""
+    from gemmgan_b200.cli import build_parser
 
-    args = parse_args()
-    torch.manual_seed(args.seed)
-    loader = synthetic_loader('paper', n_samples=args.batch_size * 4, batch_size=args.batch_size,
-                              n_genes=args.n_genes, n_patches=args.num_patches, n_tokens=args.num_text_tokens,
-                              seed=args.seed)
-    model = WGAN_GP(input_dims=args.n_genes, latent_dims=args.latent_dim, embedding_dims=args.embedding_dim,
-                    generator_dims=[args.hidden_dim, args.hidden_dim, args.n_genes],
-                    discriminator_dims=[args.hidden_dim, args.hidden_dim, 1], optimizer=args.optimizer,
-                    results_dire=args.output_path)
-    model.fit(loader, None, None, epochs=args.num_epochs)
-    print(model.loss_dict)
+    return build_parser('cross').parse_args(argv)
+
+
+if __name__ == '__main__':
+    from gemmgan_b200.cli import main
+
+    main('cross')

@@ -164,31 +164,14 @@ class WGAN_GP(TrainerBase):
             self._fit_evaluation(epoch, epochs, train_data, val_data, test_data, val)
 
 
-def parse_args():
-    p = argparse.ArgumentParser()
-    p.add_argument('--seed', type=int, default=42)
-    p.add_argument('--num_epochs', type=int, default=1)
-    p.add_argument('--batch_size', type=int, default=8)
-    p.add_argument('--latent_dim', type=int, default=256)
-    p.add_argument('--hidden_dim', type=int, default=256)
-    p.add_argument('--embedding_dim', type=int, default=256)
-    p.add_argument('--num_patches', type=int, default=256)
-    p.add_argument('--n_genes', type=int, default=18868)
-    p.add_argument('--output_path', type=str, default='')
-    p.add_argument('--optimizer', type=str, default='rms_prop')
-    return p.parse_args()
+def parse_args(argv=None):
+    """The reference's flags [see gemmgan_b200/cli.py]."""
+    from gemmgan_b200.cli import build_parser
+
+    return build_parser('img').parse_args(argv)
 
 
 if __name__ == '__main__':
-    from gemmgan_b200.synthetic import synthetic_loader
+    from gemmgan_b200.cli import main
 
-    args = parse_args()
-    torch.manual_seed(args.seed)
-    loader = synthetic_loader('film', n_samples=args.batch_size * 4, batch_size=args.batch_size,
-                              n_genes=args.n_genes, n_patches=args.num_patches, seed=args.seed)
-    model = WGAN_GP(input_dims=args.n_genes, latent_dims=args.latent_dim, embedding_dims=args.embedding_dim,
-                    generator_dims=[args.hidden_dim, args.hidden_dim, args.n_genes],
-                    discriminator_dims=[args.hidden_dim, args.hidden_dim, 1], optimizer=args.optimizer,
-                    results_dire=args.output_path)
-    model.fit(loader, None, None, epochs=args.num_epochs)
-    print(model.loss_dict)
+    main('img')

@@ -5,7 +5,7 @@
 // translation unit includes this header and then the .cu file. It is not a CPU path of the product: nothing under
 // gemmgan_b200/ can load the result, and it is orders of magnitude too slow to be one.
 //
-// Execution model: the threads of a CTA are fibers (ucontext) scheduled round-robin on one host thread, the CTAs of a
+// Execution model: the threads of a CTA are fibers (hand-written switch on x86-64, else ucontext) scheduled round-robin on one host thread, the CTAs of a
 // launch are spread over the host's cores. `__shared__` becomes `thread_local` (one copy per host thread = per
 // CTA in flight), __syncthreads() a counting barrier that exited threads leave (as on the GPU), __shfl_down_sync an
 // exchange through a per-warp slot array. What this cannot show: data races inside a CTA (fibers never run
@@ -47,13 +47,69 @@ struct Cta {
   Barrier bar;
   Warp warps[MAX_THREADS / 32];
 };
+// Context switch between fibers. glibc's swapcontext() makes an rt_sigprocmask system call per switch, and a warp
+// shuffle is four switches per lane: on x86-64 the switch is done by hand instead (callee-saved registers, stack
+// pointer, MXCSR / x87 control word — what the System V ABI lets a function call preserve). AddressSanitizer has to
+// see stack switches through its swapcontext interceptor, so that mode (and every other architecture) keeps ucontext.
+#if defined(__x86_64__) && !defined(__SANITIZE_ADDRESS__) && !defined(GG_EMU_UCONTEXT)
+#define GG_EMU_FAST_SWITCH 1
+struct Context {
+  void* sp = nullptr;
+};
+__attribute__((naked, noinline)) static void switch_context(Context* /*from: rdi*/, Context* /*to: rsi*/) {
+  asm volatile(
+      "pushq %rbp\n\t"
+      "pushq %rbx\n\t"
+      "pushq %r12\n\t"
+      "pushq %r13\n\t"
+      "pushq %r14\n\t"
+      "pushq %r15\n\t"
+      "subq $8, %rsp\n\t"
+      "stmxcsr (%rsp)\n\t"
+      "fnstcw 4(%rsp)\n\t"
+      "movq %rsp, (%rdi)\n\t"
+      "movq (%rsi), %rsp\n\t"
+      "ldmxcsr (%rsp)\n\t"
+      "fldcw 4(%rsp)\n\t"
+      "addq $8, %rsp\n\t"
+      "popq %r15\n\t"
+      "popq %r14\n\t"
+      "popq %r13\n\t"
+      "popq %r12\n\t"
+      "popq %rbx\n\t"
+      "popq %rbp\n\t"
+      "ret\n\t");
+}
+// A fresh fiber: its first switch-in "returns" into `entry` with the stack aligned as after a call instruction.
+inline void make_context(Context& c, char* stack, size_t bytes, void (*entry)()) {
+  uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + bytes) & ~static_cast<uintptr_t>(15);
+  uint64_t* sp = reinterpret_cast<uint64_t*>(top);
+  *--sp = 0;                                        // return address of `entry` (it never returns)
+  *--sp = reinterpret_cast<uint64_t>(entry);        // popped by `ret`
+  for (int i = 0; i < 6; ++i) *--sp = 0;            // rbp, rbx, r12 .. r15
+  *--sp = 0x1F80ull | (0x037Full << 32);            // default MXCSR, default x87 control word
+  c.sp = sp;
+}
+#else
+struct Context {
+  ucontext_t uc;
+};
+inline void switch_context(Context* from, Context* to) { swapcontext(&from->uc, &to->uc); }
+inline void make_context(Context& c, char* stack, size_t bytes, void (*entry)()) {
+  getcontext(&c.uc);
+  c.uc.uc_stack.ss_sp = stack;
+  c.uc.uc_stack.ss_size = bytes;
+  c.uc.uc_link = nullptr;
+  makecontext(&c.uc, entry, 0);
+}
+#endif
 struct Fiber {
-  ucontext_t ctx;
+  Context ctx;
   bool done = false;
   uint3 tid;
 };
 struct Worker {  // per host thread
-  ucontext_t sched;
+  Context sched;
   std::vector<Fiber> fibers;
   std::vector<char> stacks;
   int cur = 0;
@@ -66,7 +122,7 @@ thread_local dim3 t_block_dim, t_grid_dim;
 
 inline void yield() {
   Worker* w = t_worker;
-  swapcontext(&w->fibers[w->cur].ctx, &w->sched);
+  switch_context(&w->fibers[w->cur].ctx, &w->sched);
 }
 inline void barrier_wait(Barrier& b) {
   const long g = b.gen;
@@ -91,7 +147,7 @@ inline void fiber_entry() {
   barrier_leave(w->cta.warps[t / 32].bar);
   barrier_leave(w->cta.bar);
   w->fibers[t].done = true;
-  swapcontext(&w->fibers[t].ctx, &w->sched);  // never resumed
+  switch_context(&w->fibers[t].ctx, &w->sched);  // never resumed
 }
 
 // Runs one CTA of `nthreads` threads on the calling host thread.
@@ -109,11 +165,7 @@ inline void run_cta(int nthreads, dim3 block, const std::function<void()>& body)
     Fiber& f = w->fibers[t];
     f.tid = uint3{static_cast<unsigned>(t) % block.x, (static_cast<unsigned>(t) / block.x) % block.y,
                   static_cast<unsigned>(t) / (block.x * block.y)};
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = w->stacks.data() + static_cast<size_t>(t) * STACK_BYTES;
-    f.ctx.uc_stack.ss_size = STACK_BYTES;
-    f.ctx.uc_link = nullptr;
-    makecontext(&f.ctx, fiber_entry, 0);
+    make_context(f.ctx, w->stacks.data() + static_cast<size_t>(t) * STACK_BYTES, STACK_BYTES, fiber_entry);
   }
   for (int remaining = nthreads; remaining > 0;) {
     for (int t = 0; t < nthreads; ++t) {
@@ -121,7 +173,7 @@ inline void run_cta(int nthreads, dim3 block, const std::function<void()>& body)
       if (f.done) continue;
       w->cur = t;
       t_thread = f.tid;
-      swapcontext(&w->sched, &f.ctx);
+      switch_context(&w->sched, &f.ctx);
       if (f.done) --remaining;
     }
   }
