@@ -169,27 +169,14 @@ class WGAN_GP_benchmark(TrainerBase):
                 self._save_checkpoints('last_epoch')
 
 
-def parse_args():
-    p = argparse.ArgumentParser(description='WGAN-GP')
-    p.add_argument('--output_path', type=str, default='')
-    p.add_argument('--batch_size', type=int, default=8)
-    p.add_argument('--epochs', type=int, default=1)
-    p.add_argument('--latent_dim', type=int, default=256)
-    p.add_argument('--n_genes', type=int, default=18868)
-    p.add_argument('--seed', type=int, default=42)
-    return p.parse_args()
+def parse_args(argv=None):
+    """The reference's flags [:906-915]; see gemmgan_b200/cli.py."""
+    from gemmgan_b200.cli import build_parser
+
+    return build_parser('label').parse_args(argv)
 
 
 if __name__ == '__main__':
-    from gemmgan_b200.synthetic import synthetic_loader
+    from gemmgan_b200.cli import main
 
-    args = parse_args()
-    torch.manual_seed(args.seed)
-    loader = synthetic_loader('label', n_samples=args.batch_size * 4, batch_size=args.batch_size, n_genes=args.n_genes,
-                              seed=args.seed)
-    model = WGAN_GP_benchmark(input_dims=args.n_genes, latent_dims=args.latent_dim, vocab_sizes=[10, 10],
-                              generator_dims=[256, 256, args.n_genes], discriminator_dims=[256, 256, 1],
-                              negative_slope=0.0, is_bn=False, lr_d=5e-4, lr_g=5e-4, gp_weight=10, p_aug=0,
-                              norm_scale=0.5, results_dire=args.output_path)
-    model.fit(loader, None, epochs=args.epochs)
-    print(model.loss_dict)
+    main('label')

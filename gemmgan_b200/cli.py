@@ -1,4 +1,4 @@
-"""`python <drop-in script>.py ...`: the command line of the reference's conditional scripts on the sm_100a engine.
+"""`python <drop-in script>.py ...`: the command line of the reference's training scripts on the sm_100a engine.
 
 The reference scripts end in the same block (src/conditional_gan_cross_attention_with_film.py:902-995, and
 conditional_gan_film.py:1014-1100, conditional_gan_cross_attention.py:869-960, conditional_gan_img_transformer.py:994-1080,
@@ -35,10 +35,34 @@ SCRIPTS = {
     "img": ("conditional_gan_img_transformer", "multi_patch_gan_dataloader", "film"),
     "attn": ("conditional_gan_attention", "multi_patch_gan_dataloader", "film"),
     "concat": ("conditional_gan_concat", "multi_patch_gan_dataloader", "film"),
+    # gene-expression-only and label-conditioned scripts: other flags (vanilla_gan_unconditional.py:765-799,
+    # benchmark_generative_model.py:906-962), fit(train, test, epochs)
+    "vanilla": ("vanilla_gan_unconditional", "data_loader", "vanilla"),
+    "label": ("benchmark_generative_model", "benchmark_gan_dataloader", "label"),
 }
 
 
+def _build_simple_parser() -> argparse.ArgumentParser:
+    """Flags of the unconditional / label-conditioned scripts (vanilla_gan_unconditional.py:765-775)."""
+    p = argparse.ArgumentParser(description='WGAN-GP')
+    p.add_argument('--dataset_path', type=str, default='', help="path to dataset ('' = synthetic batches)")
+    p.add_argument('--output_path', type=str, default='', help='path to save the model')
+    p.add_argument('--batch_size', type=int, default=8, help='input batch size for training (default: 8)')
+    p.add_argument('--epochs', type=int, default=500, help='number of epochs to train (default: 500)')
+    p.add_argument('--latent_dim', type=int, default=256, help='latent dimensions (default: 256)')
+    p.add_argument('--num_workers', type=int, default=4, help='number of workers for data loading')
+    p.add_argument('--seed', type=int, default=42, help='random seed (default: 42)')
+    # this implementation
+    p.add_argument('--optimizer', type=str, default='rms_prop')
+    p.add_argument('--hidden_dim', type=int, default=256, help='the reference hard-codes 256')
+    p.add_argument('--n_genes', type=int, default=18868, help='synthetic batches: number of genes')
+    p.add_argument('--synthetic_batches', type=int, default=4, help='synthetic batches per epoch')
+    return p
+
+
 def build_parser(script: str) -> argparse.ArgumentParser:
+    if script in ("vanilla", "label"):
+        return _build_simple_parser()
     p = argparse.ArgumentParser(description="Train a conditional GAN model")
     # the reference's flags (…with_film.py:903-917)
     p.add_argument('--seed', type=int, default=42, help='Random seed for reproducibility')
@@ -125,9 +149,52 @@ def build_model(script: str, args, n_genes: int):
     return m.WGAN_GP(**kw)
 
 
+def _label_vocabularies(dataset_path):
+    """Numbers of distinct disease types / primary sites among the listed cases (benchmark_generative_model.py:931-945)."""
+    import pickle
+
+    with open(os.path.join(dataset_path, 'metainfos.pkl'), 'rb') as f:
+        meta = pickle.load(f)
+    with open(os.path.join(dataset_path, 'case_ids.txt')) as f:
+        cases = {c.strip() for c in f.read().splitlines()}
+    return [len({m[key] for c, m in meta.items() if c in cases}) for key in ('disease_type', 'primary_site')]
+
+
+def _main_simple(script: str, args):
+    """vanilla_gan_unconditional.py:777-799 / benchmark_generative_model.py:917-962."""
+    module, loader_module, layout = SCRIPTS[script]
+    m = importlib.import_module(module)
+    vocab = [10, 10]
+    if args.dataset_path:
+        lm = importlib.import_module(loader_module)
+        fn = lm.dataloader_tcga if script == "vanilla" else lm.dataloader_benchmark_conditional_gan
+        train, _, test, n_genes = fn(dataset_path=Path(args.dataset_path), batch_size=args.batch_size,
+                                     num_workers=args.num_workers, seed=args.seed)
+        if script == "label":
+            vocab = _label_vocabularies(args.dataset_path)
+    else:
+        import torch
+
+        from .synthetic import synthetic_loader
+
+        torch.manual_seed(args.seed)
+        train, test, n_genes = synthetic_loader(layout, n_samples=args.batch_size * args.synthetic_batches,
+                                                batch_size=args.batch_size, n_genes=args.n_genes, seed=args.seed), None, args.n_genes
+    h = args.hidden_dim
+    kw = dict(input_dims=n_genes, latent_dims=args.latent_dim, generator_dims=[h, h, n_genes],
+              discriminator_dims=[h, h, 1], negative_slope=0.0, is_bn=False, lr_d=5e-4, lr_g=5e-4, gp_weight=10, p_aug=0,
+              norm_scale=0.5, optimizer=args.optimizer, results_dire=args.output_path)
+    model = m.WGAN_GP_nocond(vocab_sizes=[], **kw) if script == "vanilla" else m.WGAN_GP_benchmark(vocab_sizes=vocab, **kw)
+    model.fit(train, test, epochs=args.epochs)
+    print(model.loss_dict)
+    return model
+
+
 def main(script: str, argv=None):
     args = build_parser(script).parse_args(argv)
     print(f'Arguments: {args.__dict__}')
+    if script in ("vanilla", "label"):
+        return _main_simple(script, args)
     train, val, test, n_genes = load_data(script, args)
     model = build_model(script, args, n_genes)
     if script == "attn":    # fit(train_data, test_data, epochs, val) in this script (conditional_gan_attention.py:523)

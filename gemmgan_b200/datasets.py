@@ -1,9 +1,11 @@
 """On-disk dataset readers that yield the batch tuples the WGAN-GP step consumes.
 
 Behavioural mirror of the reference's two loaders (same file layout on disk, same splits under the same seed,
-same normalisation, same tuple layouts), written once and shared by the two drop-in modules at the repo root:
+same normalisation, same tuple layouts), written once and shared by the drop-in modules at the repo root:
   multi_patch_gan_dataloader.py             src/multi_patch_gan_dataloader.py:9-262   (film / concat / img variants)
   multi_patch_multi_token_gan_dataloader.py src/multi_patch_multi_token_gan_dataloader.py:11-187 (paper / cross)
+  data_loader.py                            src/data_loader.py:11-174 (dataloader_tcga: the unconditional script)
+  benchmark_gan_dataloader.py               src/benchmark_gan_dataloader.py:10-199 (label-conditioned baseline)
 
 Dataset directory (reference :153-166 / :84-97):
   rna_seq.parquet                       [cases x genes] expression table, index = case id
@@ -182,12 +184,14 @@ class _Prepared:
         self.genes = [f.values for f in frames]
         with open(dataset_path / "metainfos.pkl", "rb") as f:
             meta = pickle.load(f)
+        self.meta = meta
         self.disease = self._encode(meta, "disease_type")
         self.site = self._encode(meta, "primary_site")
 
-    def _encode(self, meta, key):
+    def _encode(self, meta, key, parts=(0, 1, 2)):
+        """Label codes = rank of the name among the sorted names seen in the splits `parts`."""
         raw = [[meta[c][key] for c in ids] for ids in self.case_ids]
-        code = {name: i for i, name in enumerate(sorted({v for part in raw for v in part}))}
+        code = {name: i for i, name in enumerate(sorted({v for k in parts for v in raw[k]}))}
         return [[code[v] for v in part] for part in raw]
 
 
@@ -232,6 +236,63 @@ def multi_patch_multi_token_loaders(dataset_path, normalize=True, percentage_to_
                                          dataset_path / patch_embeddings_folder, p.genes[i], p.disease[i], p.site[i],
                                          num_patches=num_patches) for i in range(3)]
     return (*_loaders(ds, batch_size, num_workers, g), p.n_genes)
+
+
+# --------------------------------------------------- gene-only and label-conditioned loaders (vanilla / benchmark scripts)
+class BenchmarkGANDataset(Dataset):
+    """(gene_expression[G] f32, disease_type i64, primary_site i64) per case: src/benchmark_gan_dataloader.py:10-37."""
+
+    def __init__(self, case_ids, gene_expressions, disease_types, primary_sites):
+        self.case_ids = case_ids
+        self.gene_expressions = gene_expressions
+        self.disease_types = disease_types
+        self.primary_sites = primary_sites
+
+    def __len__(self):
+        return self.gene_expressions.shape[0]
+
+    def __getitem__(self, idx):
+        return (torch.tensor(self.gene_expressions[idx], dtype=torch.float32),
+                torch.tensor(self.disease_types[idx], dtype=torch.long),
+                torch.tensor(self.primary_sites[idx], dtype=torch.long))
+
+
+# both scripts intersect the cases with these two tables "to reproduce the same split as in the contrastive training
+# and conditional gan training" (src/data_loader.py:109-116, src/benchmark_gan_dataloader.py:112-119)
+_SPLIT_TEXT_TABLE = "text_embeddings_contrastive_256.parquet"
+_SPLIT_PATCH_FOLDER = "patch_embeddings_contrastive_256"
+
+
+def tcga_loaders(dataset_path, normalize=True, percentage_to_remove=90, norm_type="standardize", batch_size=8, seed=42,
+                 num_workers=4):
+    """dataloader_tcga of src/data_loader.py:87-174 (vanilla_gan_unconditional.py:778): TensorDatasets of the
+    normalised expression tables, float64 as pandas hands them out (the trainer casts, vanilla :424); training and
+    validation loaders shuffle, the test loader does not."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    torch.manual_seed(seed)
+    p = _Prepared(Path(dataset_path), _SPLIT_TEXT_TABLE, _SPLIT_PATCH_FOLDER, normalize, percentage_to_remove, norm_type)
+    from torch.utils.data import TensorDataset
+
+    mk = lambda x, shuffle: DataLoader(TensorDataset(torch.from_numpy(np.array(x))), batch_size=batch_size,  # noqa: E731
+                                       shuffle=shuffle, worker_init_fn=seed_worker, generator=g, num_workers=num_workers)
+    return mk(p.genes[0], True), mk(p.genes[1], True), mk(p.genes[2], False), p.n_genes
+
+
+def benchmark_loaders(dataset_path, normalize=True, percentage_to_remove=90, norm_type="standardize", num_patches=256,
+                      batch_size=8, seed=42, num_workers=4):
+    """dataloader_benchmark_conditional_gan of src/benchmark_gan_dataloader.py:89-199. Disease-type codes rank the
+    names of the training and test cases only (:160; a type seen only in the validation split raises KeyError there
+    as well), primary-site codes those of all three splits (:171); only the training loader shuffles (:190-195)."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    torch.manual_seed(seed)
+    p = _Prepared(Path(dataset_path), _SPLIT_TEXT_TABLE, _SPLIT_PATCH_FOLDER, normalize, percentage_to_remove, norm_type)
+    disease = p._encode(p.meta, "disease_type", parts=(0, 2))
+    ds = [BenchmarkGANDataset(p.case_ids[i], p.genes[i], disease[i], p.site[i]) for i in range(3)]
+    mk = lambda d, shuffle: DataLoader(d, batch_size=batch_size, shuffle=shuffle, worker_init_fn=seed_worker,  # noqa: E731
+                                       generator=g, num_workers=num_workers)
+    return mk(ds[0], True), mk(ds[1], False), mk(ds[2], False), p.n_genes
 
 
 # ------------------------------------------------------------------- device-resident datasets (SURVEY.md section 8 f2)

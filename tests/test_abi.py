@@ -68,7 +68,8 @@ def test_no_cpu_fallback_in_product_path():
     for fn in ("vanilla_gan_unconditional.py", "conditional_gan_film.py", "conditional_gan_cross_attention_with_film.py",
                "conditional_gan_cross_attention.py", "conditional_gan_img_transformer.py", "conditional_gan_concat.py",
                "conditional_gan_attention.py",
-               "multi_patch_gan_dataloader.py", "multi_patch_multi_token_gan_dataloader.py"):
+               "benchmark_generative_model.py", "multi_patch_gan_dataloader.py",
+               "multi_patch_multi_token_gan_dataloader.py", "data_loader.py", "benchmark_gan_dataloader.py"):
         text = open(os.path.join(ROOT, fn)).read()
         assert "oracle" not in text.replace("oracle/", ""), fn
 

@@ -129,3 +129,22 @@ def test_script_main_on_synthetic_batches(host, tmp_path):
     assert c.parse_args(["--condition_type", "image"]).condition_type == "image"
     with pytest.raises(SystemExit):
         cli.build_parser("film").parse_args(["--condition_type", "image"])      # only the concat script has it
+
+
+@pytest.mark.parametrize("script", ["vanilla", "label"])
+def test_gene_only_and_label_scripts_on_a_dataset_directory(host, script, dataset_dir, tmp_path):
+    """vanilla_gan_unconditional.py:777-799 / benchmark_generative_model.py:917-962: dataloader_tcga /
+    dataloader_benchmark_conditional_gan, vocabulary sizes read from metainfos.pkl, fit(train, test, epochs)."""
+    import shutil
+
+    shutil.copy(dataset_dir / "text.parquet", dataset_dir / "text_embeddings_contrastive_256.parquet")
+    shutil.copytree(dataset_dir / "patches", dataset_dir / "patch_embeddings_contrastive_256")
+    out = tmp_path / "run"
+    model = cli.main(script, ["--dataset_path", str(dataset_dir), "--output_path", str(out), "--batch_size", "16",
+                              "--epochs", "2", "--latent_dim", "16", "--hidden_dim", "32", "--num_workers", "0"])
+    assert len(model.loss_dict["d loss"]) == 2 and np.isfinite(model.loss_dict["d loss"]).all()
+    assert model.n_genes == N_GENES and sorted(model._engines) == [int(0.64 * N_CASES) % 16, 16]
+    if script == "label":
+        assert model.vocab_sizes == [3, 4] and model.gen.categorical_embedded_dims == 256
+    else:
+        assert (out / "generator_last_epoch.pt").exists()          # (:614-615; the label script saves at its test epochs)

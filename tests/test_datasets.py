@@ -106,3 +106,56 @@ def test_matches_reference_loader(dataset_dir, which):
             for a, b in zip(x, y):
                 assert a.dtype == b.dtype and torch.equal(a, b)
     sys.modules.pop(which, None)
+
+
+@pytest.fixture()
+def split_tables(dataset_dir):
+    """The two tables the gene-only / label loaders intersect the cases with (hard-coded names, src/data_loader.py:109-110)."""
+    import shutil
+
+    shutil.copy(dataset_dir / "text.parquet", dataset_dir / "text_embeddings_contrastive_256.parquet")
+    shutil.copytree(dataset_dir / "patches", dataset_dir / "patch_embeddings_contrastive_256")
+    return dataset_dir
+
+
+def test_gene_only_and_label_loader_tuples(split_tables):
+    import benchmark_gan_dataloader as b
+    import data_loader as d
+
+    train, val, test, n_genes = d.dataloader_tcga(dataset_path=split_tables, batch_size=5, num_workers=0, seed=42)
+    n = N_CASES - 1
+    assert n_genes == N_GENES - 1 and len(test.dataset) == n - int(0.64 * n) - int(0.16 * n)
+    (x,) = next(iter(test))
+    assert x.shape == (5, n_genes) and x.dtype == torch.float64      # the trainer casts (vanilla_gan_unconditional.py:424)
+    train, val, test, n_genes = b.dataloader_benchmark_conditional_gan(dataset_path=split_tables, batch_size=5,
+                                                                     num_workers=0, seed=42)
+    genes, disease, site = next(iter(train))
+    assert genes.shape == (5, n_genes) and genes.dtype == torch.float32
+    assert disease.dtype == site.dtype == torch.long and int(disease.max()) <= 2 and int(site.max()) <= 3
+    assert isinstance(test.dataset, b.BenchmarkGANDataset) and len(val.dataset) == int(0.16 * n)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("which,fn", [("data_loader", "dataloader_tcga"),
+                                      ("benchmark_gan_dataloader", "dataloader_benchmark_conditional_gan")])
+def test_gene_only_and_label_loaders_match_the_reference(split_tables, which, fn):
+    kw = dict(dataset_path=split_tables, batch_size=5, num_workers=0, seed=7)
+    for name in ("data_loader", "benchmark_gan_dataloader"):
+        sys.modules.pop(name, None)
+    ours_mod = __import__(which)
+    ours = getattr(ours_mod, fn)(**kw)
+    ours_batches = [[b for b in loader] for loader in ours[:3]]
+    for name in ("data_loader", "benchmark_gan_dataloader"):
+        sys.modules.pop(name, None)
+    ref_mod = ref_shim.load(which)
+    assert ref_mod.__file__ != ours_mod.__file__
+    ref = getattr(ref_mod, fn)(**kw)
+    assert ours[3] == ref[3]
+    for ob, loader in zip(ours_batches, ref[:3]):
+        rb = [b for b in loader]
+        assert len(ob) == len(rb)
+        for x, y in zip(ob, rb):
+            for a, b in zip(x, y):
+                assert a.dtype == b.dtype and torch.equal(a, b)
+    for name in ("data_loader", "benchmark_gan_dataloader"):
+        sys.modules.pop(name, None)

@@ -111,8 +111,8 @@ def test_fit_follows_the_reference_loop(host, variant, tmp_path):
     ref = oracle_fit(o, variant, loader, epochs)
     torch.manual_seed(7)
     t = make(variant, str(tmp_path))
-    if variant in ("attn", "label"):            # fit(train_data, test_data, epochs, val) in these two scripts
-        t.fit(loader, None, epochs=epochs)
+    if variant in ("attn", "label", "vanilla"):   # fit(train_data, test_data, epochs, val) in these three scripts
+        t.fit(loader, None, epochs)
     else:
         t.fit(loader, None, None, epochs=epochs)
     # same initial weights were drawn (fit() builds the nets from the seeded stream, as the reference does)

@@ -45,6 +45,8 @@ def test_fit_runs_and_saves_checkpoints(variant, tmp_path):
         bn = t.gen.attn_bn   # 2 epochs x 3 batches x (5 critic + 1 generator) training-mode generator forwards
         assert int(bn.num_batches_tracked) == 36 and bn.running_var.min().item() > 0
         assert not torch.equal(bn.running_mean, torch.zeros_like(bn.running_mean))
+    elif variant == "vanilla":   # vanilla_gan_unconditional.py:543: fit(train_data, test_data, epochs, val)
+        t.fit(loader, None, 2)
     else:
         t.fit(loader, None, None, epochs=2)
     for k in ("d loss", "d real loss", "d fake loss", "g loss"):

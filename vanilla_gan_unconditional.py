@@ -117,8 +117,9 @@ class WGAN_GP_nocond(TrainerBase):
             all_gen.append(x_gen.cpu().numpy())
         return np.vstack(all_real), np.vstack(all_gen)
 
-    def fit(self, train_data, val_data=None, test_data=None, epochs=1, val=True):
-        """Training loop of the reference fit() [:520-700] without its evaluation / plotting."""
+    def fit(self, train_data, test_data=None, epochs=1, val=True):
+        """Training loop of the reference fit(train_data, test_data, epochs, val) [:543-700] without its evaluation /
+        plotting (the test loader is only read by that part)."""
         self.build_WGAN_GP_nocond()
         if self.isTrain:
             self.init_train()
@@ -142,27 +143,14 @@ class WGAN_GP_nocond(TrainerBase):
                 self._save_checkpoints('last_epoch')
 
 
-def parse_args():
-    p = argparse.ArgumentParser()
-    p.add_argument('--seed', type=int, default=42)
-    p.add_argument('--num_epochs', type=int, default=1)
-    p.add_argument('--batch_size', type=int, default=64)
-    p.add_argument('--latent_dim', type=int, default=256)
-    p.add_argument('--hidden_dim', type=int, default=256)
-    p.add_argument('--n_genes', type=int, default=5000)
-    p.add_argument('--optimizer', type=str, default='rms_prop')
-    return p.parse_args()
+def parse_args(argv=None):
+    """The reference's flags [:765-775]; see gemmgan_b200/cli.py."""
+    from gemmgan_b200.cli import build_parser
+
+    return build_parser('vanilla').parse_args(argv)
 
 
 if __name__ == '__main__':
-    from gemmgan_b200.synthetic import synthetic_loader
+    from gemmgan_b200.cli import main
 
-    args = parse_args()
-    torch.manual_seed(args.seed)
-    loader = synthetic_loader('vanilla', n_samples=args.batch_size * 4, batch_size=args.batch_size,
-                              n_genes=args.n_genes, seed=args.seed)
-    model = WGAN_GP_nocond(input_dims=args.n_genes, latent_dims=args.latent_dim, vocab_sizes=[],
-                           generator_dims=[args.hidden_dim, args.hidden_dim, args.n_genes],
-                           discriminator_dims=[args.hidden_dim, args.hidden_dim, 1], optimizer=args.optimizer)
-    model.fit(loader, None, None, epochs=args.num_epochs)
-    print(model.loss_dict)
+    main('vanilla')
