@@ -21,7 +21,7 @@ import torch
 
 from gemmgan_b200.models import (LabelDiscriminator, LabelGenerator, build_linear_block, build_stack,  # noqa: F401
                                  categorical_embedding)
-from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, wasserstein_loss  # noqa: F401
+from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, save_numpy, wasserstein_loss  # noqa: F401
 
 
 def save_numpy(file, data):

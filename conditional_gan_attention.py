@@ -23,7 +23,7 @@ import torch
 
 from conditional_gan_film import WGAN_GP as _FilmStyleTrainer
 from gemmgan_b200.models import AttnDiscriminator, AttnGenerator, build_linear_block, build_stack  # noqa: F401
-from gemmgan_b200.trainer import D_loss, G_loss, wasserstein_loss  # noqa: F401
+from gemmgan_b200.trainer import D_loss, G_loss, save_numpy, wasserstein_loss  # noqa: F401
 
 
 def build_generator(input_dims, generator_dims, negative_slope=0.0, is_bn=False):
@@ -95,6 +95,11 @@ class WGAN_GP(_FilmStyleTrainer):
         if module is self.gen and module.training:
             self._count_bn_batches(1)
         return out
+
+    def generate_samples_all(self, data_loader, num_repeats=1, balanced=False, balanced_max_oversample=5):
+        """(real, generated, disease types real, disease types generated) [:407-506]; balanced=True = the class-balanced
+        branch [:409-480]."""
+        return self._generate_all_film_layout(data_loader, num_repeats, balanced, balanced_max_oversample, with_site=False)
 
     def fit(self, train_data, test_data=None, epochs=1, val=True):
         """Training loop of the reference fit() [:523-600] (learning rates halve every 50 epochs) without its

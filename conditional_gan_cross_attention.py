@@ -19,7 +19,7 @@ import torch
 
 import conditional_gan_cross_attention_with_film as _paper
 from conditional_gan_cross_attention_with_film import (D_loss, G_loss, build_discriminator,  # noqa: F401
-                                                        build_generator, build_linear_block,
+                                                        build_generator, build_linear_block, save_numpy,
                                                         wasserstein_loss)
 from gemmgan_b200.models import CrossDiscriminator, CrossGenerator
 

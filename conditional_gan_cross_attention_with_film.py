@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from gemmgan_b200.models import PaperDiscriminator, PaperGenerator, build_linear_block, build_stack  # noqa: F401
-from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, wasserstein_loss  # noqa: F401
+from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, save_numpy, wasserstein_loss  # noqa: F401
 
 
 def build_generator(input_dims, generator_dims, negative_slope=0.0, is_bn=False):

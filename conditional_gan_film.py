@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from gemmgan_b200.models import FilmDiscriminator, FilmGenerator, build_linear_block, build_stack  # noqa: F401
-from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, wasserstein_loss  # noqa: F401
+from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, save_numpy, wasserstein_loss  # noqa: F401
 
 
 def build_generator(input_dims, generator_dims, negative_slope=0.0, is_bn=False):
@@ -120,23 +120,11 @@ class WGAN_GP(TrainerBase):
             x_gen = self.gen(z, text_embedding, patches, padding_mask)
         return x_real, x_gen
 
-    def generate_samples_all(self, data_loader, num_repeats=1):
-        """Batch tuple layout of multi_patch_gan_dataloader.py:48:
-        (text_embedding, gene_expression, patches, padding_mask, disease_type, primary_site)."""
-        real, gen, dt_r, dt_g, ps_r, ps_g = [], [], [], [], [], []
-        for i in range(num_repeats):
-            for batch in data_loader:
-                text, genes, patches, ppad, dtype_, psite = batch[:6]
-                x_real, x_gen = self.generate_samples(genes.to(self.device), text, patches, ppad)
-                gen.append(x_gen.cpu().numpy())
-                dt_g.append(dtype_.cpu().numpy())
-                ps_g.append(psite.cpu().numpy())
-                if i == 0:
-                    real.append(x_real.cpu().numpy())
-                    dt_r.append(dtype_.cpu().numpy())
-                    ps_r.append(psite.cpu().numpy())
-        return (np.vstack(real), np.vstack(gen), np.concatenate(dt_r), np.concatenate(dt_g), np.concatenate(ps_r),
-                np.concatenate(ps_g))
+    def generate_samples_all(self, data_loader, num_repeats=1, balanced=False, balanced_max_oversample=5):
+        """Batch tuple layout of multi_patch_gan_dataloader.py:48: (text_embedding, gene_expression, patches,
+        padding_mask, disease_type, primary_site); returns the reference's 6-tuple [:447-563]. balanced=True ends in a
+        NameError in the reference and raises here."""
+        return self._generate_all_film_layout(data_loader, num_repeats, balanced, balanced_max_oversample, with_site=True)
 
     def fit(self, train_data, val_data=None, test_data=None, epochs=1, val=True):
         """Training loop of the reference fit() without its evaluation / plotting."""

@@ -206,8 +206,8 @@ class FilmDiscriminator(_Net):
         self._build(vector_dims, embedding_dims, discriminator_dims, text_embedding_dims, patches_embedding_dims,
                     negative_slope, is_bn)
 
-    def forward(self, x, text_embedding, patches, padding_mask):
-        return self._engine_forward(x, text_embedding, patches, padding_mask)
+    def forward(self, gene_expression, text_embedding, patches, padding_mask):
+        return self._engine_forward(gene_expression, text_embedding, patches, padding_mask)
 
 
 # ------------------------------------------------- image-transformer model (no text, no FiLM)
@@ -284,6 +284,9 @@ class ConcatDiscriminator(_ConcatNet):
                            negative_slope, is_bn)
         self.encoder = nn.Linear(input_embedding_dims, embedding_dims)
 
+    def forward(self, gene_expression, text_embedding, patches, padding_mask):   # the reference's argument name (:178)
+        return self._engine_forward(gene_expression, text_embedding, patches, padding_mask)
+
 
 # ----------------------------------------------------------------- single-attention model
 class _AttnNet(_Net):
@@ -356,6 +359,9 @@ class AttnDiscriminator(_AttnNet):
         self.discriminator_dims = discriminator_dims
         self._build_attn(vector_dims, embedding_dims, discriminator_dims, text_embedding_dims, patches_embedding_dims,
                          negative_slope, is_bn)
+
+    def forward(self, gene_expression, text_embedding, patches, padding_mask):   # the reference's argument name (:153)
+        return self._engine_forward(gene_expression, text_embedding, patches, padding_mask)
 
 
 # ------------------------------------------------------ label-conditioned baseline model

@@ -41,6 +41,12 @@ def D_loss(real_labels, fake_labels):
     return loss_real + loss_fake, loss_real, loss_fake
 
 
+def save_numpy(file, data):
+    """The scripts' helper for the .npy dumps (src/conditional_gan_cross_attention_with_film.py:28-30)."""
+    with open(file, 'wb') as f:
+        np.save(f, data)
+
+
 def _dist():
     import torch.distributed as dist
 
@@ -510,6 +516,97 @@ class TrainerBase:
         self._mark("d")
         self._mark("g")
 
+    # ---- generation over a loader (film-style batch tuples) ------------------------------------------
+    GEN_CHUNK = 64   # rows per generator call of the reference's class-balanced branch (conditional_gan_concat.py:488)
+
+    def _generate_all_film_layout(self, data_loader, num_repeats=1, balanced=False, balanced_max_oversample=5,
+                                  with_site=True):
+        """generate_samples_all of the scripts whose loader yields (text_embedding, gene_expression, patches,
+        padding_mask, disease_type, primary_site) (multi_patch_gan_dataloader.py:48). with_site=True: the 6-tuple of
+        conditional_gan_film.py:447-563 / conditional_gan_img_transformer.py; with_site=False: the 4-tuple
+        (real, generated, disease types real, disease types generated) of conditional_gan_concat.py:453-552 and
+        conditional_gan_attention.py:407-506.
+
+        balanced=True is the class-balanced branch of the two 4-tuple scripts (conditional_gan_concat.py:455-526):
+        one pass over the loader for the real arrays, then per disease type its rows plus up to
+        balanced_max_oversample x as many re-drawn ones (np.random.choice) generated GEN_CHUNK at a time from
+        `data_loader.dataset`, the result shuffled. The reference reads `dataset[idx]` once PER FIELD (five times per
+        sample; each read re-draws the patch subset of an over-long case), and so does this, so that a seeded numpy
+        stream gives the same rows, labels and order. Chunks shorter than GEN_CHUNK are zero-padded to it for the engine
+        (one engine instead of one per class remainder); z is drawn for the real rows only, as the reference does.
+        In the 6-tuple scripts that branch ends in a NameError (`all_primary_site_real`, conditional_gan_film.py:563)."""
+        n_fields = 6 if with_site else 5
+        if balanced and with_site:
+            raise NotImplementedError("balanced=True is broken in the reference for this script "
+                                      "(undefined all_primary_site_real at the return, conditional_gan_film.py:563)")
+        host = lambda t: t.detach().cpu().numpy()  # noqa: E731
+        if not balanced:
+            real, gen, labels_real, labels_gen = [], [], [[], []], [[], []]
+            for i in range(num_repeats):
+                for batch in data_loader:
+                    text, genes, patches, ppad = batch[:4]
+                    x_real, x_gen = self.generate_samples(genes.to(self.device), text, patches, ppad)
+                    gen.append(host(x_gen))
+                    for k in range(n_fields - 4):
+                        labels_gen[k].append(host(batch[4 + k]))
+                        if i == 0:
+                            labels_real[k].append(host(batch[4 + k]))
+                    if i == 0:
+                        real.append(host(x_real))
+            out = [np.vstack(real), np.vstack(gen)]
+            for k in range(n_fields - 4):
+                out += [np.concatenate(labels_real[k]), np.concatenate(labels_gen[k])]
+            return tuple(out)
+        real, disease_real = [], []
+        for batch in data_loader:
+            real.append(host(batch[1].clone().to(torch.float32)))
+            disease_real.append(host(batch[4]))
+        real, disease_real = np.vstack(real), np.concatenate(disease_real)
+        classes = np.unique(disease_real)
+        counts = np.bincount(disease_real)
+        most = counts.max()
+        rows_of = {c: np.where(disease_real == c)[0] for c in classes}
+        dataset = data_loader.dataset
+        gen, disease_gen = [], []
+        for _ in range(num_repeats):
+            for c in classes:
+                rows = rows_of[c]
+                if counts[c] < most:
+                    extra = min(most - counts[c], balanced_max_oversample * counts[c])
+                    rows = np.concatenate((rows, np.random.choice(rows, extra, replace=extra > len(rows))))
+                for s in range(0, len(rows), self.GEN_CHUNK):
+                    chunk = rows[s:s + self.GEN_CHUNK]
+                    # field by field per sample, in the reference's order (one dataset read per field)
+                    fields = [[] for _ in range(n_fields)]
+                    for r in chunk:
+                        for k in range(n_fields):
+                            fields[k].append(dataset[int(r)][k])
+                    text, genes, patches, ppad = (torch.stack(fields[k]) for k in range(4))
+                    gen.append(host(self._generate_padded(genes, text, patches, ppad, self.GEN_CHUNK)))
+                    disease_gen.append(np.asarray([int(v) for v in fields[4]], dtype=np.int64))
+        gen, disease_gen = np.vstack(gen), np.concatenate(disease_gen)
+        order = np.arange(gen.shape[0])
+        np.random.shuffle(order)
+        return real, gen[order], disease_real, disease_gen[order]
+
+    def _generate_padded(self, genes, text, patches, ppad, rows):
+        """generate_samples on n <= rows samples through the engine of batch size `rows`: z ~ N(0, 1) for the n real rows
+        (the reference's draw), the conditioning zero-padded; returns the n generated rows."""
+        n = genes.shape[0]
+        if n == rows:
+            return self.generate_samples(genes.to(self.device), text, patches, ppad)[1]
+        with torch.no_grad():
+            self.gen.eval()
+            z = torch.zeros(rows, self.latent_dims, device=self.device)
+            z[:n] = torch.normal(0, 1, size=(n, self.latent_dims), device=self.device)
+
+            def pad(t):
+                t = t.to(self.device)
+                out = torch.zeros((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+                out[:n] = t
+                return out
+            return self.gen(z, pad(text), pad(patches), pad(ppad))[:n]
+
     def set_requires_grad(self, nets, requires_grad=False):
         if not isinstance(nets, list):
             nets = [nets]
@@ -601,11 +698,15 @@ GENERATED_TEST_FILES = ("test_real", "test_gen", "test_labels_real", "test_label
 
 def save_generated_arrays(folder: str, train_out, test_out) -> None:
     """Writes what generate_samples_all returned for the training loader (real, gen, disease type real / gen, primary
-    site real / gen) and for the test loader under the reference's twelve file names (:793-806)."""
+    site real / gen) and for the test loader under the reference's twelve file names (:793-806); the scripts whose
+    generate_samples_all returns four arrays (no primary sites) leave the first eight
+    (conditional_gan_concat.py:760-767, conditional_gan_attention.py:639-646)."""
     os.makedirs(folder, exist_ok=True)
     for names, arrays in ((GENERATED_FILES, train_out), (GENERATED_TEST_FILES, test_out)):
+        if len(arrays) == 4:
+            names = names[:4]
         if len(arrays) != len(names):
-            raise ValueError(f"expected the 6-tuple of generate_samples_all, got {len(arrays)} arrays")
+            raise ValueError(f"expected the 6- or 4-tuple of generate_samples_all, got {len(arrays)} arrays")
         for name, a in zip(names, arrays):
             with open(os.path.join(folder, name + ".npy"), "wb") as f:
                 np.save(f, np.asarray(a))

@@ -20,7 +20,7 @@ import torch
 import emu_build
 import host_trainer
 from gemmgan_b200 import _abi_decl as A
-from oracle import restated
+from oracle import ref_shim, restated
 
 TOL = 2e-2
 COS_FLOOR = 0.75       # see update_cosine()
@@ -288,3 +288,103 @@ def test_single_steps_and_module_calls_through_the_trainer(host):
     gp_o = o.gradient_penalty(x, fake_o, cond, alphas[1])
     gp_t = t.gradient_penalty(x, fake_o, patches, ppad, text, tpad, alpha=alphas[1])
     assert abs(float(gp_t) - float(gp_o)) <= TOL * max(1.0, abs(float(gp_o)))
+
+
+# ----------------------------------------------------------------------- generate_samples_all, class-balanced branch
+class _Cases(torch.utils.data.Dataset):
+    """Film-layout items (text, genes, patches, pad, disease type, primary site) with the loaders' random patch subset
+    (np.random.choice per read of an over-long case, multi_patch_gan_dataloader.py:33-36) and skewed class counts."""
+
+    def __init__(self, n=45, P=4):
+        g = torch.Generator().manual_seed(3)
+        self.text = torch.randn(n, SMALL["text_dim"], generator=g)
+        self.genes = torch.randn(n, SMALL["G"], generator=g)
+        self.patches = [torch.randn(2 + i % 5, SMALL["patch_dim"], generator=g) for i in range(n)]   # 2..6 patches
+        self.disease = torch.tensor([0 if i % 3 else (1 if i % 9 else 2) for i in range(n)])          # 30 / 10 / 5
+        self.site = torch.arange(n) % 4
+        self.P = P
+
+    def __len__(self):
+        return len(self.genes)
+
+    def __getitem__(self, i):
+        p = self.patches[i]
+        if p.shape[0] > self.P:
+            p = p[np.random.choice(p.shape[0], self.P, replace=False)]
+        else:
+            p = torch.cat((p, torch.zeros(self.P - p.shape[0], p.shape[1])))
+        return self.text[i], self.genes[i], p, torch.zeros(self.P, dtype=torch.bool), self.disease[i], self.site[i]
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+def test_class_balanced_generation_matches_the_reference(host, tmp_path):
+    """conditional_gan_concat.py:453-552 with balanced=True against the drop-in on the same weights, numpy and torch
+    seeds: same real rows, same generated labels in the same (shuffled) order — i.e. the same np.random stream,
+    including the per-field dataset reads — and the generated profiles within the bf16 tolerance."""
+    import sys
+
+    import conditional_gan_concat as mine_mod
+
+    H, G = SMALL["hidden"], SMALL["G"]
+    kw = dict(input_dims=G, latent_dims=SMALL["latent"], input_embedding_dims=SMALL["text_dim"], embedding_dims=SMALL["embed"],
+              generator_dims=[H, H, G], discriminator_dims=[H, H, 1], condition_on="text",
+              results_dire=str(tmp_path))        # (the reference's constructor creates the directory, :260)
+    torch.manual_seed(5)
+    mine = mine_mod.WGAN_GP(**kw)
+    mine.build_WGAN_GP()
+    sys.modules.pop("conditional_gan_concat", None)
+    ref_mod = ref_shim.load("conditional_gan_concat")
+    assert ref_mod.__file__ != mine_mod.__file__
+    ref = ref_mod.WGAN_GP(**kw)
+    ref.build_WGAN_GP()
+    ref.gen.load_state_dict(mine.gen.state_dict())
+    loader = torch.utils.data.DataLoader(_Cases(), batch_size=8, shuffle=False)
+    outs = []
+    for tr in (ref, mine):
+        np.random.seed(11)
+        torch.manual_seed(12)
+        outs.append(tr.generate_samples_all(loader, num_repeats=2, balanced=True, balanced_max_oversample=3))
+    r, m = outs
+    assert len(r) == len(m) == 4
+    # 30 rows of class 0; class 1: 10 + min(20, 30) = 30; class 2: 5 + min(25, 15) = 20; two repeats
+    assert m[1].shape == r[1].shape == (2 * (30 + 30 + 20), G)
+    assert np.array_equal(r[0], m[0]) and np.array_equal(r[2], m[2]) and np.array_equal(r[3], m[3])
+    assert np.abs(m[1] - r[1]).max() <= TOL * np.abs(r[1]).max()
+    assert sorted(mine._engines) == [64]                       # chunks of 64, the remainders padded to it
+    # the unbalanced 4-tuple as well (partial last batch: 45 = 5 x 8 + 5)
+    outs = []
+    for tr in (ref, mine):
+        torch.manual_seed(13)
+        np.random.seed(14)
+        outs.append(tr.generate_samples_all(loader))
+    r, m = outs
+    assert len(m) == 4 and np.array_equal(r[0], m[0]) and np.array_equal(r[2], m[2]) and np.array_equal(r[3], m[3])
+    assert np.abs(m[1] - r[1]).max() <= TOL * np.abs(r[1]).max()
+    sys.modules.pop("conditional_gan_concat", None)
+
+
+def test_generated_array_tuples_follow_each_script(host, tmp_path):
+    """6 arrays from the film / img scripts (balanced=True raises, as the reference's NameError does), 4 from concat /
+    attn; save_generated_arrays writes twelve or eight files."""
+    from gemmgan_b200.trainer import save_generated_arrays
+
+    H, G = SMALL["hidden"], SMALL["G"]
+    loader = torch.utils.data.DataLoader(_Cases(n=11), batch_size=8, shuffle=False)
+    for name, n_out in (("conditional_gan_film", 6), ("conditional_gan_attention", 4)):
+        m = importlib.import_module(name)
+        t = m.WGAN_GP(input_dims=G, latent_dims=SMALL["latent"], embedding_dims=SMALL["embed"], generator_dims=[H, H, G],
+                      discriminator_dims=[H, H, 1], text_embedding_dims=SMALL["text_dim"],
+                      patches_embedding_dims=SMALL["patch_dim"])
+        t.build_WGAN_GP()
+        out = t.generate_samples_all(loader)
+        assert len(out) == n_out and out[1].shape == (11, G) and np.array_equal(out[2], out[3])
+        folder = tmp_path / name
+        save_generated_arrays(str(folder), out, out)
+        assert len(list(folder.iterdir())) == 2 * n_out
+        if n_out == 6:
+            assert np.array_equal(np.load(folder / "test_primary_site_real.npy"), np.arange(11) % 4)
+            with pytest.raises(NotImplementedError):
+                t.generate_samples_all(loader, balanced=True)
+        else:
+            balanced = t.generate_samples_all(loader, balanced=True)
+            assert len(balanced) == 4 and balanced[1].shape[0] == len(balanced[3]) > 11

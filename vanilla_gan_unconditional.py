@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from gemmgan_b200.models import VanillaDiscriminator, VanillaGenerator, build_linear_block, build_stack
-from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, wasserstein_loss  # noqa: F401
+from gemmgan_b200.trainer import D_loss, G_loss, TrainerBase, save_numpy, wasserstein_loss  # noqa: F401
 
 
 def build_generator(input_dims, generator_dims, negative_slope=0.0, is_bn=False):
@@ -42,6 +42,15 @@ def WGAN_GP_model_nocond(latent_dims, vector_dims, numerical_dims, vocab_sizes, 
     gen = generator_nocond(latent_dims, numerical_dims, vocab_sizes, generator_dims, negative_slope, is_bn)
     disc = discriminator_nocond(vector_dims, numerical_dims, vocab_sizes, discriminator_dims, negative_slope, is_bn)
     return gen, disc
+
+
+def categorical_embedding(vocab_sizes):
+    """One nn.Embedding(vs, int(sqrt(vs)) + 1) per categorical variable [:19-27]; unused by the unconditional nets
+    (vocab_sizes=[] in the script), kept for the module's public surface."""
+    embedder = torch.nn.ModuleList()
+    for vs in vocab_sizes:
+        embedder.append(torch.nn.Embedding(vs, int(vs ** 0.5) + 1))
+    return embedder
 
 
 class WGAN_GP_nocond(TrainerBase):
@@ -100,17 +109,17 @@ class WGAN_GP_nocond(TrainerBase):
             return eng.generate(x.to(self.device), training=module.training)
         return eng.critic(x.to(self.device), training=module.training)
 
-    def generate_samples(self, x):
+    def generate_samples(self, x_GE):
         with torch.no_grad():
             self.gen.eval()
-            x_real = x.clone().to(torch.float32)
+            x_real = x_GE.clone().to(torch.float32)
             z = torch.normal(0, 1, size=(x_real.shape[0], self.latent_dims), device=self.device)
             x_gen = self.gen(z)
         return x_real, x_gen
 
-    def generate_samples_all(self, data_loader):
+    def generate_samples_all(self, data):
         all_real, all_gen = [], []
-        for batch in data_loader:
+        for batch in data:
             x = batch[0] if isinstance(batch, (list, tuple)) else batch
             x_real, x_gen = self.generate_samples(x.to(self.device))
             all_real.append(x_real.cpu().numpy())
