@@ -148,7 +148,7 @@ class WGAN_GP(TrainerBase):
             self.loss_dict['d loss'].append(d_mean[0])
             self.loss_dict['d real loss'].append(d_mean[1])
             self.loss_dict['d fake loss'].append(d_mean[2])
-            self.loss_dict['g loss'].append((g_sum / max(n, 1))[0])
+            self.loss_dict['g loss'].append(np.atleast_1d(g_sum)[0])   # summed over the epoch's batches, not averaged, in the reference
             last = epoch == epochs - 1
             if self.result_dire and ((epoch + 1) % self.freq_compute_test == 0 or last):
                 tag = 'last_epoch' if last else f'epoch_{epoch + 1}'

@@ -87,8 +87,8 @@ def split(variant, batch):
 
 
 def oracle_fit(o, variant, loader, epochs):
-    """The reference's loop on the oracle: per-epoch means of d_batch_loss (and of g_batch_loss; the label baseline
-    SUMS the generator loss, benchmark_generative_model.py:638)."""
+    """The reference's loop on the oracle: per-epoch MEAN of d_batch_loss and SUM of g_batch_loss over the batches —
+    every script divides only the critic's (…with_film.py:695-699, vanilla_gan_unconditional.py:602-606)."""
     hist = {"d loss": [], "d real loss": [], "d fake loss": [], "g loss": []}
     for _ in range(epochs):
         d_sum, g_sum, n = 0.0, 0.0, 0
@@ -98,7 +98,7 @@ def oracle_fit(o, variant, loader, epochs):
             d_sum, g_sum, n = d_sum + o.d_batch_loss, g_sum + o.g_batch_loss, n + 1
         d = d_sum / n
         hist["d loss"].append(d[0]), hist["d real loss"].append(d[1]), hist["d fake loss"].append(d[2])
-        hist["g loss"].append(g_sum[0] if variant == "label" else (g_sum / n)[0])
+        hist["g loss"].append(g_sum[0])
     return hist
 
 

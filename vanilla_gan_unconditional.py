@@ -147,7 +147,7 @@ class WGAN_GP_nocond(TrainerBase):
             self.loss_dict['d loss'].append(d_mean[0])
             self.loss_dict['d real loss'].append(d_mean[1])
             self.loss_dict['d fake loss'].append(d_mean[2])
-            self.loss_dict['g loss'].append((g_sum / max(n, 1))[0])
+            self.loss_dict['g loss'].append(np.atleast_1d(g_sum)[0])   # summed over the epoch's batches, not averaged, in the reference
             if self.result_dire and epoch == epochs - 1:   # reference :614-615
                 self._save_checkpoints('last_epoch')
 
