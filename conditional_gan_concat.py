@@ -135,7 +135,7 @@ class WGAN_GP(TrainerBase):
         if self.isTrain:
             self.init_train()
         for epoch in range(epochs):
-            self._epoch_lr_decay(epoch, 100)
+            self._epoch_lr_decay(epoch, 50)   # both learning rates halve every 50 epochs in this script [:605-613]
             self.epoch = epoch
             d_sum, g_sum, n = 0.0, 0.0, 0
             for i, (data, nxt) in enumerate(self._lookahead(train_data)):

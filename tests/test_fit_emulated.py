@@ -102,8 +102,32 @@ def oracle_fit(o, variant, loader, epochs):
     return hist
 
 
+# epochs between two halvings of both learning rates: `if epoch % N == 0 and epoch != 0` in each script's fit()
+# (…with_film.py:649, conditional_gan_cross_attention.py:619, conditional_gan_film.py:614, conditional_gan_img_transformer.py:597,
+# conditional_gan_attention.py:547, conditional_gan_concat.py:605, vanilla_gan_unconditional.py:558, benchmark_generative_model.py:585)
+LR_HALVING = {"paper": 100, "cross": 100, "film": 100, "img": 100, "attn": 50, "concat": 50, "concat_image": 50,
+              "vanilla": 50, "label": 50}
+
+
+def test_lr_halving_table_is_the_reference():
+    import re
+
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("reference tree only exists in the build container")
+    for variant, module in MODULES.items():
+        src = open(os.path.join(ref_shim.REF_SRC, module + ".py")).read()
+        found = re.findall(r"if epoch % (\d+) == 0 and epoch != 0:", src)
+        assert found == [str(LR_HALVING[variant])], (module, found)
+
+
 @pytest.mark.parametrize("variant", sorted(MODULES))
-def test_fit_follows_the_reference_loop(host, variant, tmp_path):
+def test_fit_follows_the_reference_loop(host, variant, tmp_path, monkeypatch):
+    calls = []
+    decay = host.TrainerBase._epoch_lr_decay
+    monkeypatch.setattr(host.TrainerBase, "_epoch_lr_decay",
+                        lambda self, epoch, every: (calls.append(every), decay(self, epoch, every))[1])
     epochs = 2 if variant in ("vanilla", "label", "concat", "paper") else 1      # (suite time)
     loader = loader_for(variant)
     torch.manual_seed(7)
@@ -121,6 +145,7 @@ def test_fit_follows_the_reference_loop(host, variant, tmp_path):
         assert got.shape == (epochs,) and np.isfinite(got).all(), (k, got)
         tol = 3e-2 * max(1.0, float(np.abs(want).max()))
         assert np.abs(got - want).max() <= tol, (variant, k, got, want)
+    assert calls == [LR_HALVING[variant]] * epochs
     assert len(t._engines) == 2                 # B = 8 and the last partial batch of 3
     assert os.path.exists(tmp_path / "generator_last_epoch.pt") and os.path.exists(tmp_path / "discriminator_last_epoch.pt")
     sd = torch.load(tmp_path / "generator_last_epoch.pt")
