@@ -181,18 +181,25 @@ class TrainerBase:
                          clip_g=float(self.clip_g or 0.0), optimizer=self.optimizer.lower(),
                          seed=int(self.dropout_seed), gemm_impl=self.gemm_impl, device=self.device, **s)
             self._engines[B] = eng
-            d = _dist()
-            if d is not None:
-                # the all-reduce averages per-rank gradient MEANS with equal weight: that is the global-batch
-                # gradient only when every rank holds the same number of rows (e.g. DistributedSampler(drop_last=True))
-                sizes = torch.zeros(d.get_world_size(), dtype=torch.int64, device=self.device)
-                sizes[d.get_rank()] = B
-                d.all_reduce(sizes)
-                if int(sizes.min()) != int(sizes.max()):
-                    raise ValueError(f"data-parallel ranks must use equal per-rank batch sizes, got {sizes.tolist()}")
         else:
             eng.sync_params()
         return eng
+
+    def _check_equal_rank_batches(self, eng: Engine) -> None:
+        """Data parallel, once per TRAINING engine (first optimizer step, where every rank is present): the all-reduce
+        averages per-rank gradient MEANS with equal weight, which is the global-batch gradient only when every rank
+        holds the same number of rows (e.g. DistributedSampler(drop_last=True)). Not done at engine creation: rank 0
+        alone creates engines while it evaluates (generate_samples_all over a validation loader), and a collective
+        there would pair up with the other ranks' gradient all-reduces."""
+        d = _dist()
+        if d is None or getattr(eng, "_dp_batch_checked", False) or self._in_capture:
+            return
+        sizes = torch.zeros(d.get_world_size(), dtype=torch.int64, device=self.device)
+        sizes[d.get_rank()] = eng.B
+        d.all_reduce(sizes)
+        if int(sizes.min()) != int(sizes.max()):
+            raise ValueError(f"data-parallel ranks must use equal per-rank batch sizes, got {sizes.tolist()}")
+        eng._dp_batch_checked = True
 
     # ---- host -> device staging ----------------------------------------------------------
     def prefetch(self, *tensors):
@@ -355,6 +362,7 @@ class TrainerBase:
     def _step(self, eng: Engine, tag, net, flat, lr, grads_fn):
         """grads_fn(phase): phase 0 = whole backward, 1 = forward + trunk backward, 2 = tower backward."""
         lr = float(lr)
+        self._check_equal_rank_batches(eng)
         try:
             self._step_inner(eng, tag, net, flat, lr, grads_fn)
         finally:

@@ -3,8 +3,9 @@
 
 Covers what tests/test_dp_emulated.py (engine + buckets driven by hand) does not: the trainer's own data-parallel code —
 rank 0's initial weights broadcast to every replica whatever each rank's torch seed was, the staged gradient buckets
-issued from `_step_inner`, z / alpha drawn for the global batch and sliced (`dp_global_noise`), six optimizer steps of
-one train() call with the replicas staying bit-identical, and the refusal of unequal per-rank batches."""
+issued from `_step_inner`, z / alpha drawn for the global batch and sliced (`dp_global_noise`), the optimizer steps of
+two train() calls with the replicas staying bit-identical, rank 0 evaluating alone in between (a new engine without a
+collective), and the refusal of unequal per-rank batches."""
 import ctypes as C
 import os
 import socket
@@ -88,6 +89,16 @@ def _worker(rank, world, port, lib_path, out_dir, variant):
         x, cond = _batch(variant, world * B)
         torch.manual_seed(77)                           # shared noise seed (global z / alpha drawn on every rank)
         _train(t, variant, x, cond, slice(rank * B, (rank + 1) * B))
+        if rank == 0:
+            # rank 0 evaluates alone between epochs (fit()'s evaluation block): a new batch size means a new engine,
+            # created without any collective, or the other ranks' next gradient all-reduce would pair up with it
+            xv, cv = _batch(variant, 3)
+            if variant == "vanilla":
+                t.generate_samples(xv)
+            else:
+                t.generate_samples(xv, cv[2], cv[3], cv[0], cv[1])
+        torch.manual_seed(78)
+        _train(t, variant, x, cond, slice(rank * B, (rank + 1) * B))
         out = _state(t)
         out["init_disc"] = init
         torch.save(out, os.path.join(out_dir, f"rank{rank}.pt"))
@@ -133,6 +144,8 @@ def test_two_trainer_ranks_equal_one_trainer_on_the_global_batch(variant, tmp_pa
               "disc": {k: v.clone() for k, v in t.disc.state_dict().items()}}
     x, cond = _batch(variant, world * CFG["B"])
     torch.manual_seed(77)
+    _train(t, variant, x, cond)
+    torch.manual_seed(78)
     _train(t, variant, x, cond)
     one = _state(t)
     # losses: mean over ranks of the per-rank batch means = the global batch mean
