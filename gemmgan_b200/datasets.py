@@ -296,6 +296,16 @@ def benchmark_loaders(dataset_path, normalize=True, percentage_to_remove=90, nor
 
 
 # ------------------------------------------------------------------- device-resident datasets
+def _default_device():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _current_stream():
+    import ctypes as C
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
 class DeviceResidentLoader:
     """The batches of MultiPatchMultiTokenGANDataset / MultiPatchGANDataset + DataLoader, assembled ON THE GPU.
 
@@ -319,7 +329,7 @@ class DeviceResidentLoader:
         from . import _lib
 
         self._C, self._lib = C, _lib.lib()
-        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.device = device or _default_device()
         _lib.require_device(self.device.index or 0)
         self.batch_size, self.shuffle, self.generator = batch_size, shuffle, generator
         self.num_patches = dataset.num_patches
@@ -361,8 +371,7 @@ class DeviceResidentLoader:
         C = self._C
         from . import _lib
         _lib.check(self._lib.gg_gather_rows(C.c_void_p(src2d.data_ptr()), src2d.stride(0), C.c_void_p(index.data_ptr()),
-                                            C.c_void_p(out.data_ptr()), cols, rows, cols,
-                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                            C.c_void_p(out.data_ptr()), cols, rows, cols, _current_stream()))
         return out
 
     def __iter__(self):

@@ -7,7 +7,7 @@ import contextlib
 
 import torch
 
-from gemmgan_b200 import _lib, runtime, trainer
+from gemmgan_b200 import _lib, datasets, runtime, trainer
 
 
 class _Event:
@@ -26,6 +26,8 @@ def apply(setattr_, lib, dropout_p=0.0):
     setattr_(_lib, "require_device", lambda dev=0: None)
     setattr_(_lib, "require_cuda_tensor_device", lambda dev, what: None)
     setattr_(runtime, "_stream", lambda: None)
+    setattr_(datasets, "_default_device", lambda: torch.device("cpu"))     # DeviceResidentLoader: "HBM" = host memory
+    setattr_(datasets, "_current_stream", lambda: None)
     setattr_(torch.cuda, "device", lambda d: contextlib.nullcontext())
     setattr_(torch.cuda, "Event", _Event)
     setattr_(torch.Tensor, "pin_memory", lambda self: self)

@@ -148,3 +148,28 @@ def test_gene_only_and_label_scripts_on_a_dataset_directory(host, script, datase
         assert model.vocab_sizes == [3, 4] and model.gen.categorical_embedded_dims == 256
     else:
         assert (out / "generator_last_epoch.pt").exists()          # (:614-615; the label script saves at its test epochs)
+
+
+def test_device_resident_loader_feeds_the_script(host, dataset_dir, tmp_path):
+    """--device_loader: every split uploaded once, batches assembled by gg_gather_rows — here in host
+    memory by the emulated kernel. The batches equal the DataLoader's under the same numpy seed, and the script runs."""
+    import multi_patch_multi_token_gan_dataloader as m
+    from torch.utils.data import DataLoader
+
+    from gemmgan_b200.datasets import DeviceResidentLoader
+
+    train, _, _, _ = m.dataloader_multi_patch_conditional_gan(dataset_dir, num_patches=4, batch_size=8, num_workers=0,
+                                                              text_embedding_file="text.parquet",
+                                                              patch_embeddings_folder="patches",
+                                                              token_embeddings_folder="tokens")
+    np.random.seed(3)
+    want = list(DataLoader(train.dataset, batch_size=8, shuffle=False, num_workers=0))
+    np.random.seed(3)
+    got = list(DeviceResidentLoader(train.dataset, batch_size=8))
+    assert len(got) == len(want) == 7
+    for bw, bg in zip(want, got):
+        assert len(bw) == len(bg) == 7
+        for tw, tg in zip(bw, bg):
+            assert tg.dtype == tw.dtype and torch.equal(tg, tw)
+    model = cli.main("paper", flags(dataset_dir, tmp_path / "run", ["--device_loader"]))
+    assert len(model.loss_dict["d loss"]) == 1 and len(model.test_runs) == 2 and sorted(model.precision_scores) == [1]
