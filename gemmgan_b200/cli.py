@@ -44,14 +44,14 @@ SCRIPTS = {
 
 def _build_simple_parser() -> argparse.ArgumentParser:
     """Flags of the unconditional / label-conditioned scripts (vanilla_gan_unconditional.py:765-775)."""
-    p = argparse.ArgumentParser(description='WGAN-GP')
+    p = argparse.ArgumentParser(description='WGAN-GP training on the sm_100a engine (flags of the unconditional / label scripts)')
     p.add_argument('--dataset_path', type=str, default='', help="path to dataset ('' = synthetic batches)")
-    p.add_argument('--output_path', type=str, default='', help='path to save the model')
-    p.add_argument('--batch_size', type=int, default=8, help='input batch size for training (default: 8)')
-    p.add_argument('--epochs', type=int, default=500, help='number of epochs to train (default: 500)')
-    p.add_argument('--latent_dim', type=int, default=256, help='latent dimensions (default: 256)')
-    p.add_argument('--num_workers', type=int, default=4, help='number of workers for data loading')
-    p.add_argument('--seed', type=int, default=42, help='random seed (default: 42)')
+    p.add_argument('--output_path', type=str, default='', help='results directory')
+    p.add_argument('--batch_size', type=int, default=8, help='rows per batch')
+    p.add_argument('--epochs', type=int, default=500, help='training epochs')
+    p.add_argument('--latent_dim', type=int, default=256, help='width of z')
+    p.add_argument('--num_workers', type=int, default=4, help='DataLoader worker processes')
+    p.add_argument('--seed', type=int, default=42, help='seed of torch / numpy / the split')
     # this implementation
     p.add_argument('--optimizer', type=str, default='rms_prop')
     p.add_argument('--hidden_dim', type=int, default=256, help='the reference hard-codes 256')
@@ -63,24 +63,24 @@ def _build_simple_parser() -> argparse.ArgumentParser:
 def build_parser(script: str) -> argparse.ArgumentParser:
     if script in ("vanilla", "label"):
         return _build_simple_parser()
-    p = argparse.ArgumentParser(description="Train a conditional GAN model")
+    p = argparse.ArgumentParser(description="WGAN-GP training on the sm_100a engine (flags of the reference's conditional scripts)")
     # the reference's flags (…with_film.py:903-917)
-    p.add_argument('--seed', type=int, default=42, help='Random seed for reproducibility')
-    p.add_argument('--num_epochs', type=int, default=500, help='Number of epochs to train')
-    p.add_argument('--batch_size', type=int, default=8, help='Batch size for training')
-    p.add_argument('--latent_dim', type=int, default=256, help='Latent dimension for the model')
-    p.add_argument('--hidden_dim', type=int, default=256, help='Hidden dimension for the model')
-    p.add_argument('--embedding_dim', type=int, default=256, help='Embedding dimension for the model')
-    p.add_argument('--num_patches', type=int, default=256, help='Number of patches for multi-patch model')
+    p.add_argument('--seed', type=int, default=42, help='seed of torch / numpy / the split')
+    p.add_argument('--num_epochs', type=int, default=500, help='training epochs')
+    p.add_argument('--batch_size', type=int, default=8, help='rows per batch')
+    p.add_argument('--latent_dim', type=int, default=256, help='width of z')
+    p.add_argument('--hidden_dim', type=int, default=256, help='width of the two trunk layers')
+    p.add_argument('--embedding_dim', type=int, default=256, help='width of the conditioning vector')
+    p.add_argument('--num_patches', type=int, default=256, help='patch tokens per sample (sub-sampled / zero-padded to this)')
     p.add_argument('--dataset_path', type=str, default='', help="Path to the dataset ('' = synthetic batches)")
-    p.add_argument('--output_path', type=str, default='', help='Path to save the model')
-    p.add_argument('--num_workers', type=int, default=16, help='Number of workers for data loading')
-    p.add_argument('--freq_compute_test', type=int, default=50, help='Frequency of validation performance')
+    p.add_argument('--output_path', type=str, default='', help='results directory (checkpoints, .npy dumps)')
+    p.add_argument('--num_workers', type=int, default=16, help='DataLoader worker processes')
+    p.add_argument('--freq_compute_test', type=int, default=50, help='epochs between validation passes / checkpoints')
     p.add_argument('--freq_plot_images', type=int, default=16, help='Frequency for the plot (accepted, unused)')
-    p.add_argument('--optimizer', type=str, default='rms_prop', help='Optimizer to use for training')
+    p.add_argument('--optimizer', type=str, default='rms_prop', help='rms_prop | adam | adamw')
     if script == "concat":
         p.add_argument('--condition_type', type=str, default='text', choices=['text', 'image'],
-                       help='Condition type for the model')
+                       help='which embedding conditions the nets')
     # what the reference hard-codes in its loader / model calls (:925-949)
     p.add_argument('--text_embedding_file', type=str, default='clinical_modernbert_embeddings.parquet')
     p.add_argument('--patch_embeddings_folder', type=str, default='patch_embeddings_uni')
