@@ -388,3 +388,19 @@ def test_generated_array_tuples_follow_each_script(host, tmp_path):
         else:
             balanced = t.generate_samples_all(loader, balanced=True)
             assert len(balanced) == 4 and balanced[1].shape[0] == len(balanced[3]) > 11
+
+
+@pytest.mark.parametrize("variant,B", [("paper", 1), ("vanilla", 1), ("film", 2)])
+def test_smallest_batches_train(host, variant, B):
+    """A loader without drop_last can end an epoch with a batch of one or two rows: the step must still be the
+    reference's (batch means over B rows, per-row gradient penalty)."""
+    o, t = make(variant, "adam")
+    x, cond = batch(variant, B, seed=3)
+    zs, alphas = noise(B)
+    bd, bg = snapshot(o)
+    o.train(x, cond, zs, alphas)
+    call_train(t, variant, x, cond, zs, alphas)
+    scale = max(1.0, float(np.abs(o.d_batch_loss).max()))
+    assert np.abs(t.d_batch_loss - o.d_batch_loss).max() <= TOL * scale, (t.d_batch_loss, o.d_batch_loss)
+    assert abs(float(t.g_batch_loss[0]) - float(o.g_batch_loss[0])) <= TOL * max(1.0, abs(float(o.g_batch_loss[0])))
+    assert update_cosine(bd, o.disc, t.disc) > COS_FLOOR and update_cosine(bg, o.gen, t.gen) > COS_FLOOR
