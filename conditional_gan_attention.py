@@ -78,15 +78,25 @@ class WGAN_GP(_FilmStyleTrainer):
         # nn.BatchNorm1d.num_batches_tracked (only read when momentum is None; kept for state_dict equality)
         self.gen.attn_bn.num_batches_tracked += n
 
+    @staticmethod
+    def _need_two_rows(t):
+        # nn.BatchNorm1d in training mode refuses a single row (torch/nn/functional.py::_verify_batch_size); the
+        # generator's BatchNorm sees every batch of train_disc / train_gen in training mode [:322, :371]
+        if t.shape[0] == 1:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(t.shape)}")
+
     def train_disc(self, real_data, z, text_embedding, patches, padding_mask, alpha=None):
+        self._need_two_rows(z)
         super().train_disc(real_data, z, text_embedding, patches, padding_mask, alpha)
         self._count_bn_batches(1)
 
     def train_gen(self, z, text_embedding, patches, padding_mask):
+        self._need_two_rows(z)
         super().train_gen(z, text_embedding, patches, padding_mask)
         self._count_bn_batches(1)
 
     def train(self, gene_expression, text_embedding, patches, padding_mask, zs=None, alphas=None, prefetch=None):
+        self._need_two_rows(gene_expression)
         super().train(gene_expression, text_embedding, patches, padding_mask, zs, alphas, prefetch)
         self._count_bn_batches(self.n_critic + 1)
 

@@ -404,3 +404,22 @@ def test_smallest_batches_train(host, variant, B):
     assert np.abs(t.d_batch_loss - o.d_batch_loss).max() <= TOL * scale, (t.d_batch_loss, o.d_batch_loss)
     assert abs(float(t.g_batch_loss[0]) - float(o.g_batch_loss[0])) <= TOL * max(1.0, abs(float(o.g_batch_loss[0])))
     assert update_cosine(bd, o.disc, t.disc) > COS_FLOOR and update_cosine(bg, o.gen, t.gen) > COS_FLOOR
+
+
+def test_single_row_batch_is_refused_by_the_batchnorm_script(host):
+    """conditional_gan_attention.py: nn.BatchNorm1d in the generator raises on a training batch of one row; so does the
+    drop-in, with torch's message (eval-mode generation of one row works, as in the reference)."""
+    m = importlib.import_module("conditional_gan_attention")
+    H, G = SMALL["hidden"], SMALL["G"]
+    t = m.WGAN_GP(input_dims=G, latent_dims=SMALL["latent"], embedding_dims=SMALL["embed"], generator_dims=[H, H, G],
+                  discriminator_dims=[H, H, 1], text_embedding_dims=SMALL["text_dim"],
+                  patches_embedding_dims=SMALL["patch_dim"])
+    t.build_WGAN_GP()
+    t.init_train()
+    x, (text, patches, ppad) = batch("film", 1, seed=3)
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel when training"):
+        t.train(x, text, patches, ppad)
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+        t.train_gen(torch.randn(1, SMALL["latent"]), text, patches, ppad)
+    real, fake = t.generate_samples(x, text, patches, ppad)
+    assert fake.shape == (1, G) and torch.isfinite(fake).all()
