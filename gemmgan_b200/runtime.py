@@ -287,7 +287,29 @@ class Engine:
         t = t.contiguous()
         return t.view(torch.uint8) if t.dtype == torch.bool else t.to(torch.uint8)
 
+    def _expect(self, what: str, t: Optional[torch.Tensor], *shape: int) -> None:
+        """The library reads raw pointers with the engine's static sizes: a tensor of another size must fail here, with
+        the sizes in the message (the reference's torch modules raise a shape error at the first matmul), not read out
+        of bounds on the device."""
+        if t is None:
+            return
+        n = 1
+        for d in shape:
+            n *= d
+        if t.numel() != n or t.shape[0] != shape[0]:
+            raise ValueError(f"{what}: expected shape {tuple(shape)} for this engine "
+                             f"(variant {self.variant!r}, batch {self.B}), got {tuple(t.shape)}")
+        d, e = t.device, self.device
+        if d.type != e.type or (d.index is not None and e.index is not None and d.index != e.index):
+            raise ValueError(f"{what} is on {d}, the engine on {e}")
+
     def set_batch(self, genes=None, patches=None, patch_pad=None, text=None, text_pad=None) -> None:
+        c = self.cfg
+        self._expect("gene expression", genes, self.B, self.G)
+        self._expect("patches", patches, self.B, c.P, c.Dp)
+        self._expect("patch padding mask", patch_pad, self.B, c.P)
+        self._expect("text embedding", text, self.B, c.T, c.Dt)
+        self._expect("text padding mask", text_pad, self.B, c.T)
         g, p, t = self._f32(genes), self._f32(patches), self._f32(text)
         pm, tm = self._u8(patch_pad), self._u8(text_pad)
         self._keep = (g, p, t, pm, tm)  # keep alive until the enqueued casts have run
@@ -327,6 +349,7 @@ class Engine:
         _lib.check(self.lib.gg_engine_optim_step(self.handle, net, float(lr), _stream()))
 
     def generate(self, z: torch.Tensor, training: bool = False) -> torch.Tensor:
+        self._expect("z", z, self.B, self.L)
         z = self._f32(z)
         out = torch.empty(self.B, self.G, device=self.device, dtype=torch.float32)
         _lib.check(self.lib.gg_engine_generate(self.handle, _ptr(z), _ptr(out), int(training), _stream()))
@@ -334,6 +357,7 @@ class Engine:
 
     # ---- module-level autograd (gemmgan_b200/standalone.py): forward keeping the backward's tensors + first-order backward
     def generate_keep(self, z: torch.Tensor, training: bool) -> torch.Tensor:
+        self._expect("z", z, self.B, self.L)
         z = self._f32(z)
         out = torch.empty(self.B, self.G, device=self.device, dtype=torch.float32)
         _lib.check(self.lib.gg_engine_generate_keep(self.handle, _ptr(z), _ptr(out), int(training), _stream()))
@@ -346,6 +370,7 @@ class Engine:
         return dz
 
     def critic_keep(self, genes: torch.Tensor, training: bool) -> torch.Tensor:
+        self._expect("gene expression", genes, self.B, self.G)
         g = self._f32(genes)
         out = torch.empty(self.B, 1, device=self.device, dtype=torch.float32)
         _lib.check(self.lib.gg_engine_critic_keep(self.handle, _ptr(g), _ptr(out), int(training), _stream()))
@@ -358,6 +383,9 @@ class Engine:
         return dx
 
     def gradient_penalty(self, real, fake, alpha, training: bool = True) -> torch.Tensor:
+        self._expect("real data", real, self.B, self.G)
+        self._expect("fake data", fake, self.B, self.G)
+        self._expect("alpha", alpha, self.B, 1)
         r, f, a = self._f32(real), self._f32(fake), self._f32(alpha)
         out = torch.empty((), device=self.device, dtype=torch.float32)
         _lib.check(self.lib.gg_engine_gradient_penalty(self.handle, _ptr(r), _ptr(f), _ptr(a), int(training),
@@ -378,6 +406,7 @@ class Engine:
         _lib.check(self.lib.gg_engine_gp_step(self.handle, _ptr(r), _ptr(f), _ptr(a), _ptr(out), _stream()))
 
     def critic(self, genes: torch.Tensor, training: bool = False) -> torch.Tensor:
+        self._expect("gene expression", genes, self.B, self.G)
         g = self._f32(genes)
         out = torch.empty(self.B, 1, device=self.device, dtype=torch.float32)
         _lib.check(self.lib.gg_engine_critic(self.handle, _ptr(g), _ptr(out), int(training), _stream()))

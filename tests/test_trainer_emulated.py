@@ -423,3 +423,25 @@ def test_single_row_batch_is_refused_by_the_batchnorm_script(host):
         t.train_gen(torch.randn(1, SMALL["latent"]), text, patches, ppad)
     real, fake = t.generate_samples(x, text, patches, ppad)
     assert fake.shape == (1, G) and torch.isfinite(fake).all()
+
+
+def test_wrong_tensor_sizes_fail_on_the_host(host):
+    """The library reads raw pointers with the engine's static sizes: a batch tensor of another width must raise with
+    the expected shape (the reference raises a matmul shape error), never be read out of bounds."""
+    _, t = make("paper", "adam")
+    x, (patches, ppad, text, tpad) = batch("paper", 8, seed=3)
+    t.train(x, text, tpad, patches, ppad)
+    with pytest.raises(ValueError, match=r"gene expression: expected shape \(8, 203\)"):
+        t.train(x[:, :200], text, tpad, patches, ppad)
+    with pytest.raises(ValueError, match="patches: expected shape"):
+        t.train(x, text, tpad, patches[:, :, :24], ppad)
+    with pytest.raises(ValueError, match="text embedding: expected shape"):
+        t.train(x, text[:, :, :16], tpad, patches, ppad)
+    with pytest.raises(ValueError, match="patch padding mask: expected shape"):
+        t.train(x, text, tpad, patches, ppad[:4])
+    with pytest.raises(ValueError, match="z: expected shape"):
+        t.gen(torch.randn(8, SMALL["latent"] + 8), patches, ppad, text, tpad)
+    with pytest.raises(ValueError, match="fake data: expected shape"):
+        t.gradient_penalty(x, x[:, :100], patches, ppad, text, tpad)
+    t.train(x, text, tpad, patches, ppad)           # and the trainer is still usable
+    assert np.isfinite(t.d_batch_loss).all()
