@@ -86,9 +86,11 @@ class WGAN_GP(_FilmStyleTrainer):
             raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(t.shape)}")
 
     def train_disc(self, real_data, z, text_embedding, patches, padding_mask, alpha=None):
-        self._need_two_rows(z)
+        counted = self.gen.training        # an eval-mode generator (after generate_samples) does not track batches
+        if counted:
+            self._need_two_rows(z)
         super().train_disc(real_data, z, text_embedding, patches, padding_mask, alpha)
-        self._count_bn_batches(1)
+        self._count_bn_batches(int(counted))
 
     def train_gen(self, z, text_embedding, patches, padding_mask):
         self._need_two_rows(z)
@@ -97,8 +99,9 @@ class WGAN_GP(_FilmStyleTrainer):
 
     def train(self, gene_expression, text_embedding, patches, padding_mask, zs=None, alphas=None, prefetch=None):
         self._need_two_rows(gene_expression)
+        counted = self.n_critic if self.gen.training else 0   # critic steps with the generator in eval mode do not count
         super().train(gene_expression, text_embedding, patches, padding_mask, zs, alphas, prefetch)
-        self._count_bn_batches(self.n_critic + 1)
+        self._count_bn_batches(counted + 1)
 
     def _module_forward(self, module, x, text_embedding, patches, padding_mask):
         out = super()._module_forward(module, x, text_embedding, patches, padding_mask)

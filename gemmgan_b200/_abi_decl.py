@@ -8,6 +8,7 @@ VARIANT_ATTN = 7   # conditional_gan_attention.py
 OPT_RMSPROP, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 NET_GEN, NET_DISC = 0, 1
 PHASE_STAGE0, PHASE_NO_JOIN = 16, 64
+TRAIN_GEN_EVAL = 2   # GG_TRAIN_GEN_EVAL: flag of gg_engine_disc_grads' `training` argument
 
 # enum gg_param_slot
 P_FILM_W, P_FILM_B, P_TEXT_W, P_TEXT_B, P_PATCH_W, P_PATCH_B, P_CLS = range(7)

@@ -1423,6 +1423,8 @@ extern "C" int gg_engine_set_labels(gg_engine* e, const int64_t* labels0, const 
 // phase 0: whole step; 1: forward + trunk backward (trunk gradients final on return); 2: tower backward
 static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int training, int phase, void* stream) {
   GG_REQUIRE(e && z && alpha, "null argument");
+  const bool gen_eval = (training & GG_TRAIN_GEN_EVAL) != 0;  // the generator was left in eval mode (see gemmgan.h)
+  training &= 1;
   const bool no_join = (phase & GG_PHASE_NO_JOIN) != 0;  // side lanes stay open: a later call joins them
   phase &= ~GG_PHASE_NO_JOIN;
   GG_REQUIRE((phase >= 0 && phase <= 2) || (phase >= GG_PHASE_STAGE0 && phase < GG_PHASE_STAGE0 + 16), "bad phase %d", phase);
@@ -1444,8 +1446,8 @@ static int disc_grads_impl(gg_engine* e, const float* z, const float* alpha, int
   // ---- forward: G(z) (no graph) on lane 1 next to the critic tower on lane 0; D on fake / real /
   // interpolated rows (:391-408), GP value (:351-374)
   GG_TRY(e->fork(1));
-  e->bn_training = training;
-  GG_TRY(gen_forward(*e, z, p, nullptr, 1, false));      // (no graph: the generator is not trained here)
+  e->bn_training = gen_eval ? 0 : training;
+  GG_TRY(gen_forward(*e, z, gen_eval ? 0.f : p, nullptr, 1, false));      // (no graph: the generator is not trained here)
   GG_TRY(disc_forward_gp(*e, R, p, alpha, 1, 1, Rg));  // the GP chain continues on lane 1
   const Op W1x = e->W(net, GG_P_TR0_W), W2 = e->W(net, GG_P_TR1_W);
   const float* w3 = e->P(net, GG_P_FIN_W);

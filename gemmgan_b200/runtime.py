@@ -323,15 +323,17 @@ class Engine:
         self._keep_labels = (y0, y1)
         _lib.check(self.lib.gg_engine_set_labels(self.handle, _ptr(y0), _ptr(y1), _stream()))
 
-    def disc_grads(self, z: torch.Tensor, alpha: torch.Tensor, training: bool = True, phase: int = 0) -> None:
-        """phase 0 = whole step; 1 = forward + trunk backward; 2 = tower backward (gg_engine_disc_grads_phase)."""
+    def disc_grads(self, z: torch.Tensor, alpha: torch.Tensor, training: bool = True, phase: int = 0,
+                   gen_eval: bool = False) -> None:
+        """phase 0 = whole step; 1 = forward + trunk backward; 2 = tower backward (gg_engine_disc_grads_phase).
+        gen_eval: the generator forward inside the step runs in eval mode (GG_TRAIN_GEN_EVAL)."""
         z, alpha = self._f32(z), self._f32(alpha)
         assert z.shape == (self.B, self.L) and alpha.numel() == self.B
+        mode = int(bool(training)) | (A.TRAIN_GEN_EVAL if gen_eval else 0)
         if phase == 0:
-            _lib.check(self.lib.gg_engine_disc_grads(self.handle, _ptr(z), _ptr(alpha), int(training), _stream()))
+            _lib.check(self.lib.gg_engine_disc_grads(self.handle, _ptr(z), _ptr(alpha), mode, _stream()))
         else:
-            _lib.check(self.lib.gg_engine_disc_grads_phase(self.handle, _ptr(z), _ptr(alpha), int(training), phase,
-                                                           _stream()))
+            _lib.check(self.lib.gg_engine_disc_grads_phase(self.handle, _ptr(z), _ptr(alpha), mode, phase, _stream()))
 
     def gen_grads(self, z: torch.Tensor, training: bool = True, phase: int = 0) -> None:
         z = self._f32(z)

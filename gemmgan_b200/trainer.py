@@ -443,8 +443,13 @@ class TrainerBase:
             zt, at, tag = eng.z_in, eng.alpha_in, "d"
         else:
             zt, at, tag = eng.z_all[slot], eng.alpha_all[slot], f"d{slot}"
+        # the reference's train_disc runs the generator in the mode it was left in (:390): eval after a generate_samples
+        # call (:603) until the next train_gen (:427). (Its own captured graph: the mode is baked into the kernels.)
+        gen_eval = not self.gen.training
+        if gen_eval:
+            tag += "e"
         self._step(eng, tag, A.NET_DISC, self._flat_disc, self._lr(self.optimizer_disc),
-                   lambda ph: eng.disc_grads(zt, at, training=True, phase=ph))
+                   lambda ph: eng.disc_grads(zt, at, training=True, phase=ph, gen_eval=gen_eval))
         if snapshot:
             self._snapshot(eng, "d")
 
@@ -509,7 +514,8 @@ class TrainerBase:
             finally:
                 self._in_capture = False
 
-        self._replay(eng, ("dg_call", float(self._lr(self.optimizer_disc)), float(self._lr(self.optimizer_gen)), n), whole)
+        self._replay(eng, ("dg_call", float(self._lr(self.optimizer_disc)), float(self._lr(self.optimizer_gen)), n,
+                           self.gen.training), whole)
         # host-visible side effects of the steps that a replay does not re-execute (:384-389, :433-438)
         self.disc.train()
         self.gen.train()

@@ -262,7 +262,12 @@ int gg_engine_set_labels(gg_engine* e, const int64_t* labels0, const int64_t* la
  * before the first forward of an ATTN engine. */
 int gg_engine_set_batchnorm(gg_engine* e, float* running_mean, float* running_var, float momentum, float eps);
 /* train_disc minus optimizer: fills critic grads + stats. z [B,L], alpha [B,1] fp32. training=1
- * uses dropout_p (three independently-dropped critic tower passes, as the reference). */
+ * uses dropout_p (three independently-dropped critic tower passes, as the reference).
+ * training | GG_TRAIN_GEN_EVAL: the generator forward inside the critic step runs in eval mode (no dropout in its tower,
+ * BatchNorm on its running statistics, which are left alone). The reference's train_disc uses the generator in whatever
+ * mode it was left in (:390; only train_gen calls gen.train(), :427), so the critic steps that follow a generate_samples
+ * call (gen.eval(), :603) see it that way. */
+#define GG_TRAIN_GEN_EVAL 2
 int gg_engine_disc_grads(gg_engine* e, const float* z, const float* alpha, int training, void* stream);
 /* train_gen minus optimizer: fills generator grads + stats. */
 int gg_engine_gen_grads(gg_engine* e, const float* z, int training, void* stream);

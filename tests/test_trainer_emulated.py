@@ -445,3 +445,55 @@ def test_wrong_tensor_sizes_fail_on_the_host(host):
         t.gradient_penalty(x, x[:, :100], patches, ppad, text, tpad)
     t.train(x, text, tpad, patches, ppad)           # and the trainer is still usable
     assert np.isfinite(t.d_batch_loss).all()
+
+
+def test_critic_steps_after_generation_see_an_eval_mode_generator(host):
+    """The reference's train_disc never calls gen.train() (conditional_gan_attention.py:322; …with_film.py:390): after
+    generate_samples (gen.eval()) the critic steps of the next train() run the generator in eval mode — in the
+    BatchNorm script on the running statistics, which then do not move — until train_gen switches it back. Checked on
+    the BatchNorm variant, where the difference is deterministic, against the oracle (which keeps the reference's
+    mode handling) and against the same call with the generator in training mode."""
+    m = importlib.import_module("conditional_gan_attention")
+    H, G = SMALL["hidden"], SMALL["G"]
+    kw = dict(input_dims=G, latent_dims=SMALL["latent"], embedding_dims=SMALL["embed"], generator_dims=[H, H, G],
+              discriminator_dims=[H, H, 1], text_embedding_dims=SMALL["text_dim"], patches_embedding_dims=SMALL["patch_dim"],
+              optimizer="adam")
+    B = 8
+    x, cond = batch("film", B, seed=3)
+    text, patches, ppad = cond
+    zs, alphas = noise(B)
+    results = {}
+    for mode in ("eval", "train"):
+        torch.manual_seed(11)
+        o = restated.OracleWGANGP("attn", G, latent=SMALL["latent"], embed=SMALL["embed"], hidden=H, optimizer="adam",
+                                  negative_slope=0.0, dropout=0.0, text_dim=SMALL["text_dim"], patch_dim=SMALL["patch_dim"])
+        torch.manual_seed(11)
+        t = m.WGAN_GP(**kw)
+        t.build_WGAN_GP()
+        t.init_train()
+        for tr in (o, t):                  # one ordinary call first: the running statistics are no longer (0, 1)
+            if tr is o:
+                tr.train(x, cond, *noise(B, seed=9))
+            else:
+                tr.train(x, text, patches, ppad, *noise(B, seed=9))
+        if mode == "eval":
+            o.gen.eval()
+            t.generate_samples(x, text, patches, ppad)      # leaves the generator in eval mode (:603)
+            assert not t.gen.training
+        tracked = int(t.gen.attn_bn.num_batches_tracked)
+        bd, bg = snapshot(o)
+        o.train(x, cond, zs, alphas)
+        t.train(x, text, patches, ppad, zs=zs, alphas=alphas)
+        assert t.gen.training and o.gen.training            # train_gen switched it back (:427)
+        scale = max(1.0, float(np.abs(o.d_batch_loss).max()))
+        assert np.abs(t.d_batch_loss - o.d_batch_loss).max() <= TOL * scale, (mode, t.d_batch_loss, o.d_batch_loss)
+        assert update_cosine(bd, o.disc, t.disc) > COS_FLOOR
+        ob, tb = o.gen.attn_bn, t.gen.attn_bn
+        assert float((tb.running_mean - ob.running_mean).abs().max()) <= TOL * max(1.0, float(ob.running_mean.abs().max()))
+        assert float((tb.running_var - ob.running_var).abs().max()) <= TOL * max(1.0, float(ob.running_var.abs().max()))
+        # eval mode: only train_gen's forward is a training-mode batch; training mode: all six
+        want = 1 if mode == "eval" else 6
+        assert int(tb.num_batches_tracked) - tracked == want and int(ob.num_batches_tracked) - tracked == want
+        results[mode] = (t.d_batch_loss.copy(), tb.running_mean.clone())
+    # and the two modes do differ (one momentum update of the statistics instead of six)
+    assert not torch.allclose(results["eval"][1], results["train"][1], rtol=1e-3, atol=1e-5)
