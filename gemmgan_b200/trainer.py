@@ -315,7 +315,9 @@ class TrainerBase:
             key = key + (self._graph_seq,)
         g = eng.graphs.get(key)
         if g is None:
-            kind = key[0][:1]  # 'd' / 'g': the library's one-time lazy initialisation is per step kind
+            # 'd' / 'g' (+ 'e' = critic step with an eval-mode generator): the library's one-time lazy initialisation is
+            # per step kind, and must not happen inside a capture
+            kind = key[0][:1] + ("e" if "e" in key[0].split("_")[0][1:] else "")
             if kind not in eng.warmed:
                 eng.warmed.add(kind)
                 body()
